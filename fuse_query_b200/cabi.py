@@ -1,0 +1,406 @@
+"""ctypes binding of libfuse_gpu.so — the C ABI declared in include/fuse_gpu.h.
+
+This is plumbing for the tests and bench.py (the reference-facing host mirror is C++, see
+csrc/host).  It never computes anything itself and has no fallback: if the library or a CUDA device
+is missing, calls raise FuseGpuError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libfuse_gpu.so")
+
+# fq_dtype tags (datavalues/data_value.rs:19-35 order)
+NULL, BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, UTF8, STRUCT = range(14)
+DTYPE_NAMES = ["Null", "Boolean", "Int8", "Int16", "Int32", "Int64", "UInt8", "UInt16", "UInt32", "UInt64",
+               "Float32", "Float64", "Utf8", "Struct"]
+DTYPE_SIZE = {BOOL: 1, I8: 1, I16: 2, I32: 4, I64: 8, U8: 1, U16: 2, U32: 4, U64: 8, F32: 4, F64: 8}
+
+OK, ERR_INTERNAL, ERR_PLAN, ERR_DIVIDE_BY_ZERO, ERR_UNSUPPORTED, ERR_CUDA, ERR_INVALID = range(7)
+EXPR_ALIAS, EXPR_CONSTANT, EXPR_FIELD, EXPR_ARITHMETIC, EXPR_COMPARISON, EXPR_LOGIC, EXPR_AGGREGATOR = range(7)
+PIPE_PROJECT, PIPE_AGGREGATE = 0, 1
+RUN_ACCUMULATE, RUN_LIMIT_EARLY_EXIT = 1, 2
+MAX_COLS = MAX_EXPRS = 8
+
+AGG = {"min": 0, "max": 1, "sum": 2, "count": 3}
+CMP = {"=": 0, "<": 1, "<=": 2, ">": 3, ">=": 4}
+ARITH = {"+": 0, "-": 1, "*": 2, "/": 3}
+LOGIC = {"and": 0, "or": 1}
+_TY = {"bool": BOOL, "i8": I8, "i16": I16, "i32": I32, "i64": I64, "u8": U8, "u16": U16, "u32": U32, "u64": U64,
+       "f32": F32, "f64": F64}
+
+
+class ScalarBits(C.Union):
+    _fields_ = [("i", C.c_int64), ("u", C.c_uint64), ("f", C.c_double)]
+
+
+class ExprNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("column", C.c_int32), ("dtype", C.c_int32), ("value", ScalarBits)]
+
+
+class CValue(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("some", C.c_int32), ("v", ScalarBits)]
+
+
+class Source(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_cols", C.c_int32), ("generated", C.c_int32),
+                ("cols", C.POINTER(C.c_void_p)), ("numbers_begin", C.c_uint64)]
+
+
+class PipeDesc(C.Structure):
+    _fields_ = [("n_cols", C.c_int32), ("col_dtypes", C.c_int32 * MAX_COLS), ("generated", C.c_int32),
+                ("nodes", C.POINTER(ExprNode)), ("n_nodes", C.c_int32), ("predicate", C.c_int32), ("kind", C.c_int32),
+                ("n_exprs", C.c_int32), ("exprs", C.c_int32 * MAX_EXPRS)]
+
+
+class FuseGpuError(Exception):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+        self.message = message
+
+
+EXPORTS = [
+    "fq_abi_version", "fq_ctx_create", "fq_ctx_destroy", "fq_last_error", "fq_ctx_launch_count", "fq_ctx_sm_count",
+    "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_free", "fq_column_dtype", "fq_column_len",
+    "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
+    "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
+    "fq_pipe_expr_dtype", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_aggregator_nodes",
+    "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libfuse_gpu.so (no build here: __graft_entry__.build() / fuse_query_b200.build does that)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FuseGpuError(ERR_CUDA, f"{LIB_PATH} is missing: run `python -m fuse_query_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32, u32, i64 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.c_int64
+    sig = {
+        "fq_abi_version": (u32, []),
+        "fq_ctx_create": (i32, [i32, C.POINTER(vp)]),
+        "fq_ctx_destroy": (None, [vp]),
+        "fq_last_error": (C.c_char_p, [vp]),
+        "fq_ctx_launch_count": (u64, [vp]),
+        "fq_ctx_sm_count": (i32, [vp]),
+        "fq_column_alloc": (i32, [vp, i32, u64, C.POINTER(vp)]),
+        "fq_column_wrap": (i32, [vp, i32, u64, vp, C.POINTER(vp)]),
+        "fq_column_slice": (i32, [vp, vp, u64, u64, C.POINTER(vp)]),
+        "fq_column_free": (None, [vp, vp]),
+        "fq_column_dtype": (i32, [vp]),
+        "fq_column_len": (u64, [vp]),
+        "fq_column_device_ptr": (vp, [vp]),
+        "fq_column_upload": (i32, [vp, vp, u64, vp, u64, vp]),
+        "fq_column_download": (i32, [vp, vp, u64, vp, u64, vp]),
+        "fq_stream_synchronize": (i32, [vp, vp]),
+        "fq_host_alloc": (i32, [vp, u64, C.POINTER(vp)]),
+        "fq_host_free": (None, [vp, vp]),
+        "fq_numbers_fill": (i32, [vp, vp, u64, u64, u64, vp]),
+        "fq_pipe_compile": (i32, [vp, C.POINTER(PipeDesc), C.POINTER(vp)]),
+        "fq_pipe_destroy": (None, [vp, vp]),
+        "fq_pipe_is_precompiled": (i32, [vp]),
+        "fq_pipe_source": (C.c_char_p, [vp]),
+        "fq_pipe_expr_dtype": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "fq_pipe_launch_aggregate": (i32, [vp, vp, C.POINTER(Source), u32, vp]),
+        "fq_pipe_fetch_aggregate": (i32, [vp, vp, C.POINTER(CValue), i32, C.POINTER(i32), C.POINTER(u64)]),
+        "fq_pipe_aggregator_nodes": (i32, [vp, vp, C.POINTER(i32), i32, C.POINTER(i32)]),
+        "fq_pipe_state_device": (i32, [vp, vp, C.POINTER(vp), C.POINTER(u64)]),
+        "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), u64, i64, u32, vp]),
+        "fq_pipe_fetch_project": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+# ---------------------------------------------------------------------------------------------
+# s-expression -> fq_expr_node[]  (same surface syntax as the oracle's, see oracle/fq_oracle.h)
+# ---------------------------------------------------------------------------------------------
+def _tokens(text: str) -> List[str]:
+    return text.replace("(", " ( ").replace(")", " ) ").split()
+
+
+class ExprBuilder:
+    """Accumulates the flat node array shared by a pipe's predicate and select expressions."""
+
+    def __init__(self, columns: Sequence[str]):
+        self.columns = list(columns)
+        self.nodes: List[ExprNode] = []
+
+    def _push(self, **kw) -> int:
+        n = ExprNode(left=-1, right=-1)
+        for k, v in kw.items():
+            setattr(n, k, v)
+        self.nodes.append(n)
+        return len(self.nodes) - 1
+
+    def add(self, sexpr: str) -> int:
+        toks = _tokens(sexpr)
+        root, rest = self._parse(toks, 0)
+        if rest != len(toks):
+            raise ValueError(f"trailing tokens in {sexpr!r}")
+        return root
+
+    def _parse(self, t: List[str], i: int) -> Tuple[int, int]:
+        if t[i] != "(":
+            raise ValueError(f"expected ( at {t[i:]}")
+        head = t[i + 1]
+        i += 2
+        if head == "col":
+            idx = self.columns.index(t[i])
+            node = self._push(kind=EXPR_FIELD, column=idx)
+            i += 1
+        elif head in _TY:
+            ty = _TY[head]
+            lit = t[i]
+            i += 1
+            bits = ScalarBits()
+            if ty == BOOL:
+                bits.i = 1 if lit == "true" else 0
+            elif ty in (F32, F64):
+                bits.f = float(lit)
+            elif ty in (U8, U16, U32, U64):
+                bits.u = int(lit)
+            else:
+                bits.i = int(lit)
+            node = self._push(kind=EXPR_CONSTANT, dtype=ty, value=bits)
+        elif head == "alias":
+            i += 1
+            child, i = self._parse(t, i)
+            node = self._push(kind=EXPR_ALIAS, left=child)
+        elif head.lower() in AGG:
+            child, i = self._parse(t, i)
+            node = self._push(kind=EXPR_AGGREGATOR, op=AGG[head.lower()], left=child)
+        else:
+            for table, kind in ((ARITH, EXPR_ARITHMETIC), (CMP, EXPR_COMPARISON), (LOGIC, EXPR_LOGIC)):
+                if head.lower() in table:
+                    l, i = self._parse(t, i)
+                    r, i = self._parse(t, i)
+                    node = self._push(kind=kind, op=table[head.lower()], left=l, right=r)
+                    break
+            else:
+                raise ValueError(f"unknown head {head!r}")
+        if t[i] != ")":
+            raise ValueError(f"expected ) at {t[i:]}")
+        return node, i + 1
+
+    def array(self):
+        arr = (ExprNode * max(1, len(self.nodes)))(*self.nodes)
+        return arr
+
+
+# ---------------------------------------------------------------------------------------------
+# thin object wrappers
+# ---------------------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        st = lib().fq_ctx_create(device, C.byref(self._h))
+        if st:
+            raise FuseGpuError(st, lib().fq_last_error(None).decode())
+        self.device = device
+
+    def check(self, st: int):
+        if st:
+            raise FuseGpuError(st, lib().fq_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().fq_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def launch_count(self) -> int:
+        return lib().fq_ctx_launch_count(self._h)
+
+    @property
+    def sm_count(self) -> int:
+        return lib().fq_ctx_sm_count(self._h)
+
+    # ---- columns ----
+    def column(self, dtype: int, n: int) -> "Column":
+        h = C.c_void_p()
+        self.check(lib().fq_column_alloc(self._h, dtype, n, C.byref(h)))
+        return Column(self, h)
+
+    def wrap(self, dtype: int, n: int, device_ptr: int) -> "Column":
+        h = C.c_void_p()
+        self.check(lib().fq_column_wrap(self._h, dtype, n, C.c_void_p(device_ptr), C.byref(h)))
+        return Column(self, h)
+
+    def numbers(self, begin: int, n: int, stream: int = 0) -> "Column":
+        """Materialised system.numbers_mt shard [begin, begin+n) (one fill kernel)."""
+        col = self.column(U64, n)
+        self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
+        return col
+
+    def from_numpy(self, a, stream: int = 0) -> "Column":
+        import numpy as np
+        tag = {np.dtype(np.int8): I8, np.dtype(np.int16): I16, np.dtype(np.int32): I32, np.dtype(np.int64): I64,
+               np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.uint32): U32, np.dtype(np.uint64): U64,
+               np.dtype(np.float32): F32, np.dtype(np.float64): F64}[a.dtype]
+        a = np.ascontiguousarray(a)
+        col = self.column(tag, len(a))
+        if len(a):
+            self.check(lib().fq_column_upload(self._h, col._h, 0, C.c_void_p(a.ctypes.data), len(a), C.c_void_p(stream)))
+            self.synchronize(stream)
+        return col
+
+    def synchronize(self, stream: int = 0):
+        self.check(lib().fq_stream_synchronize(self._h, C.c_void_p(stream)))
+
+    # ---- pipes ----
+    def pipe(self, exprs: Sequence[str], *, columns: Sequence[str] = ("number",), dtypes: Sequence[int] = (U64,),
+             predicate: Optional[str] = None, aggregate: bool = False, generated: bool = False) -> "Pipe":
+        b = ExprBuilder(columns)
+        pred = b.add(predicate) if predicate else -1
+        roots = [b.add(e) for e in exprs]
+        d = PipeDesc()
+        d.n_cols = len(columns)
+        for i, t in enumerate(dtypes):
+            d.col_dtypes[i] = t
+        d.generated = int(generated)
+        nodes = b.array()
+        d.nodes = C.cast(nodes, C.POINTER(ExprNode))
+        d.n_nodes = len(b.nodes)
+        d.predicate = pred
+        d.kind = PIPE_AGGREGATE if aggregate else PIPE_PROJECT
+        d.n_exprs = len(roots)
+        for i, r in enumerate(roots):
+            d.exprs[i] = r
+        h = C.c_void_p()
+        self.check(lib().fq_pipe_compile(self._h, C.byref(d), C.byref(h)))
+        return Pipe(self, h, b, roots, aggregate, generated)
+
+
+class Column:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    def free(self):
+        if self._h:
+            lib().fq_column_free(self.ctx._h, self._h)
+            self._h = None
+
+    @property
+    def dtype(self) -> int:
+        return lib().fq_column_dtype(self._h)
+
+    def __len__(self) -> int:
+        return lib().fq_column_len(self._h)
+
+    @property
+    def device_ptr(self) -> int:
+        return lib().fq_column_device_ptr(self._h) or 0
+
+    def slice(self, offset: int, n: int) -> "Column":
+        h = C.c_void_p()
+        self.ctx.check(lib().fq_column_slice(self.ctx._h, self._h, offset, n, C.byref(h)))
+        return Column(self.ctx, h)
+
+    def to_numpy(self, n: Optional[int] = None, stream: int = 0):
+        import numpy as np
+        npdt = {BOOL: np.uint8, I8: np.int8, I16: np.int16, I32: np.int32, I64: np.int64, U8: np.uint8, U16: np.uint16,
+                U32: np.uint32, U64: np.uint64, F32: np.float32, F64: np.float64}[self.dtype]
+        n = len(self) if n is None else n
+        out = np.empty(n, dtype=npdt)
+        if n:
+            self.ctx.check(lib().fq_column_download(self.ctx._h, self._h, 0, C.c_void_p(out.ctypes.data), n, C.c_void_p(stream)))
+            self.ctx.synchronize(stream)
+        return out
+
+
+def make_source(cols: Sequence[Column], n_rows: int, *, generated: bool = False, begin: int = 0):
+    arr = (C.c_void_p * max(1, len(cols)))(*[c._h for c in cols])
+    s = Source()
+    s.n_rows = n_rows
+    s.n_cols = len(cols)
+    s.generated = int(generated)
+    s.cols = C.cast(arr, C.POINTER(C.c_void_p))
+    s.numbers_begin = begin
+    s._keep = arr
+    return s
+
+
+class Pipe:
+    def __init__(self, ctx: Context, h, builder: ExprBuilder, roots: List[int], aggregate: bool, generated: bool):
+        self.ctx, self._h, self.builder, self.roots = ctx, h, builder, roots
+        self.aggregate, self.generated = aggregate, generated
+
+    def destroy(self):
+        if self._h:
+            lib().fq_pipe_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    @property
+    def precompiled(self) -> bool:
+        return bool(lib().fq_pipe_is_precompiled(self._h))
+
+    @property
+    def source(self) -> str:
+        return lib().fq_pipe_source(self._h).decode()
+
+    def expr_dtype(self, i: int) -> int:
+        out = C.c_int32()
+        self.ctx.check(lib().fq_pipe_expr_dtype(self.ctx._h, self._h, i, C.byref(out)))
+        return out.value
+
+    def aggregator_nodes(self) -> List[int]:
+        n = C.c_int32()
+        buf = (C.c_int32 * 64)()
+        self.ctx.check(lib().fq_pipe_aggregator_nodes(self.ctx._h, self._h, buf, 64, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
+
+    def state_device(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(lib().fq_pipe_state_device(self.ctx._h, self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ---- aggregate ----
+    def launch_aggregate(self, source: Source, *, accumulate: bool = False, stream: int = 0):
+        self.ctx.check(lib().fq_pipe_launch_aggregate(self.ctx._h, self._h, C.byref(source), RUN_ACCUMULATE if accumulate else 0,
+                                                       C.c_void_p(stream)))
+
+    def fetch_aggregate(self):
+        """-> (list of (dtype, value|None) per Aggregator leaf, or None for DataValue::Null; rows_selected)"""
+        vals = (CValue * 64)()
+        n, rows = C.c_int32(), C.c_uint64()
+        self.ctx.check(lib().fq_pipe_fetch_aggregate(self.ctx._h, self._h, vals, 64, C.byref(n), C.byref(rows)))
+        out = []
+        for i in range(n.value):
+            v = vals[i]
+            if v.dtype == NULL:
+                out.append(None)
+            elif not v.some:
+                out.append((v.dtype, None))
+            elif v.dtype in (F32, F64):
+                out.append((v.dtype, v.v.f))
+            elif v.dtype in (U8, U16, U32, U64):
+                out.append((v.dtype, v.v.u))
+            else:
+                out.append((v.dtype, v.v.i))
+        return out, rows.value
+
+    # ---- projection / filter ----
+    def launch_project(self, source: Source, outs: Sequence[Column], capacity: int, *, limit: int = -1, early_exit: bool = False,
+                       stream: int = 0):
+        arr = (C.c_void_p * max(1, len(outs)))(*[c._h for c in outs])
+        self.ctx.check(lib().fq_pipe_launch_project(self.ctx._h, self._h, C.byref(source), arr, capacity, limit,
+                                                     RUN_LIMIT_EARLY_EXIT if early_exit else 0, C.c_void_p(stream)))
+
+    def fetch_project(self) -> Tuple[int, int]:
+        sel, wr = C.c_uint64(), C.c_uint64()
+        self.ctx.check(lib().fq_pipe_fetch_project(self.ctx._h, self._h, C.byref(sel), C.byref(wr)))
+        return sel.value, wr.value

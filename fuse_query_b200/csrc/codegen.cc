@@ -1,0 +1,502 @@
+// codegen.cc — expression trees -> CUDA source of the specialising struct Q (see codegen.h).
+//
+// Typing follows the reference exactly: Function::return_type (functions/function.rs:28-38),
+// numerical_coercion / equal_coercion (datavalues/data_type.rs:27-98), Count -> UInt64
+// (functions/function_aggregator.rs:38-43); the emitted arithmetic restates what the reference asks
+// of arrow 2.0 (cast both sides to the coerced type, wrapping integer lanes, truncating divide that
+// errors on a zero divisor: datavalues/data_array_arithmetic.rs:33-54).
+#include "codegen.h"
+
+#include <cctype>
+#include <cinttypes>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <set>
+
+namespace fq {
+
+const char *dtype_name(fq_dtype t) {
+  static const char *n[] = {"Null", "Boolean", "Int8", "Int16", "Int32", "Int64", "UInt8",
+                            "UInt16", "UInt32", "UInt64", "Float32", "Float64", "Utf8", "Struct"};
+  return (t >= 0 && t <= FQ_STRUCT) ? n[t] : "?";
+}
+size_t dtype_size(fq_dtype t) {
+  switch (t) {
+    case FQ_BOOL: case FQ_I8: case FQ_U8: return 1;
+    case FQ_I16: case FQ_U16: return 2;
+    case FQ_I32: case FQ_U32: case FQ_F32: return 4;
+    case FQ_I64: case FQ_U64: case FQ_F64: return 8;
+    default: return 0;
+  }
+}
+static bool is_numeric(fq_dtype t) { return t >= FQ_I8 && t <= FQ_F64; }
+static bool is_float(fq_dtype t) { return t == FQ_F32 || t == FQ_F64; }
+static bool is_signed_int(fq_dtype t) { return t >= FQ_I8 && t <= FQ_I64; }
+
+static const char *ctype(fq_dtype t) {
+  static const char *n[] = {"void", "bool", "fq_i8", "fq_i16", "fq_i32", "fq_i64", "fq_u8",
+                            "fq_u16", "fq_u32", "fq_u64", "float", "double", "void", "void"};
+  return n[t];
+}
+static const char *arith_sym(int op) { static const char *s[] = {"+", "-", "*", "/"}; return s[op & 3]; }
+static const char *cmp_sym(int op) { static const char *s[] = {"=", "<", "<=", ">", ">="}; return s[op % 5]; }
+static const char *cmp_c(int op) { static const char *s[] = {"==", "<", "<=", ">", ">="}; return s[op % 5]; }
+static const char *agg_name(int op) { static const char *s[] = {"min", "max", "sum", "count"}; return s[op & 3]; }
+
+static std::string fmt(const char *f, ...) __attribute__((format(printf, 1, 2)));
+static std::string fmt(const char *f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+int numerical_coercion(const char *op, fq_dtype l, fq_dtype r, fq_dtype *out, std::string *err) {
+  if (!is_numeric(l) || !is_numeric(r)) {
+    *err = fmt("Internal Error: Unsupported (%s) %s (%s)", dtype_name(l), op, dtype_name(r));
+    return FQ_ERR_INTERNAL;
+  }
+  if (l == r) { *out = l; return FQ_OK; }
+  static const fq_dtype order[] = {FQ_F64, FQ_F32, FQ_I64, FQ_I32, FQ_I16, FQ_I8, FQ_U64, FQ_U32, FQ_U16, FQ_U8};
+  for (fq_dtype t : order)
+    if (l == t || r == t) { *out = t; return FQ_OK; }
+  *err = fmt("Internal Error: Unsupported (%s) %s (%s)", dtype_name(l), op, dtype_name(r));
+  return FQ_ERR_INTERNAL;
+}
+static int equal_coercion(const char *op, fq_dtype l, fq_dtype r, fq_dtype *out, std::string *err) {
+  if (l == r) { *out = l; return FQ_OK; }
+  return numerical_coercion(op, l, r, out, err);
+}
+
+namespace {
+
+struct Gen {
+  const fq_pipe_desc &d;
+  std::vector<fq_dtype> ty;     // inferred, FQ_NULL = not visited
+  std::vector<char> visited, scalar;
+  std::set<int> used_cols;
+  std::string err;
+  int status = FQ_OK;
+  bool const_div0 = false;
+
+  explicit Gen(const fq_pipe_desc &desc) : d(desc), ty(desc.n_nodes, FQ_NULL), visited(desc.n_nodes, 0), scalar(desc.n_nodes, 0) {}
+
+  bool fail(int st, const std::string &m) {
+    if (status == FQ_OK) { status = st; err = m; }
+    return false;
+  }
+  const fq_expr_node *node(int i) {
+    if (i < 0 || i >= d.n_nodes) { fail(FQ_ERR_INVALID, fmt("Internal Error: expression node index %d out of range", i)); return nullptr; }
+    return &d.nodes[i];
+  }
+  fq_dtype col_dtype(int c) const { return (d.generated && c == 0) ? (fq_dtype)FQ_U64 : d.col_dtypes[c]; }
+
+  // Function::return_type + the checks eval would make
+  bool infer(int i, int depth = 0) {
+    const fq_expr_node *n = node(i);
+    if (!n) return false;
+    if (depth > 128) return fail(FQ_ERR_PLAN, "Error during plan: expression depth more than 128");
+    if (visited[i]) return status == FQ_OK;
+    visited[i] = 1;
+    switch (n->kind) {
+      case FQ_EXPR_FIELD: {
+        if (n->column < 0 || n->column >= d.n_cols)
+          return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Invalid argument error: Unable to get field at index %d", n->column));
+        fq_dtype t = col_dtype(n->column);
+        if (!is_numeric(t))
+          return fail(FQ_ERR_UNSUPPORTED, fmt("Unsupported on the device path: column of type %s", dtype_name(t)));
+        ty[i] = t;
+        used_cols.insert(n->column);
+        return true;
+      }
+      case FQ_EXPR_CONSTANT:
+        if (!(is_numeric(n->dtype) || n->dtype == FQ_BOOL))
+          return fail(FQ_ERR_UNSUPPORTED, fmt("Unsupported on the device path: constant of type %s", dtype_name(n->dtype)));
+        ty[i] = n->dtype;
+        scalar[i] = 1;
+        return true;
+      case FQ_EXPR_ALIAS:
+      case FQ_EXPR_AGGREGATOR:
+        if (!infer(n->left, depth + 1)) return false;
+        ty[i] = ty[n->left];
+        scalar[i] = scalar[n->left];
+        return true;
+      case FQ_EXPR_ARITHMETIC: {
+        if (!infer(n->left, depth + 1) || !infer(n->right, depth + 1)) return false;
+        fq_dtype t;
+        int st = numerical_coercion(arith_sym(n->op), ty[n->left], ty[n->right], &t, &err);
+        if (st) { status = st; return false; }
+        if (scalar[n->left] && scalar[n->right])
+          return fail(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: arithmetic between two constants (the reference yields a 1-row array)");
+        ty[i] = t;
+        return true;
+      }
+      case FQ_EXPR_COMPARISON: {
+        if (!infer(n->left, depth + 1) || !infer(n->right, depth + 1)) return false;
+        if (scalar[n->left] && scalar[n->right])  // data_array_comparison.rs:87-92
+          return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Cannot do data_array %s, left:%s, right:%s", cmp_sym(n->op),
+                                          dtype_name(ty[n->left]), dtype_name(ty[n->right])));
+        fq_dtype t;
+        int st = equal_coercion(cmp_sym(n->op), ty[n->left], ty[n->right], &t, &err);
+        if (st) { status = st; return false; }
+        if (t == FQ_BOOL)  // macros.rs:55-76: no Boolean arm
+          return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Unsupported arithmetic_compute::%s for data type: Boolean",
+                                          (const char *[]){"eq", "lt", "lt_eq", "gt", "gt_eq"}[n->op % 5]));
+        ty[i] = FQ_BOOL;
+        return true;
+      }
+      case FQ_EXPR_LOGIC: {
+        if (!infer(n->left, depth + 1) || !infer(n->right, depth + 1)) return false;
+        const char *sym = n->op == FQ_LG_AND ? "and" : "or";
+        if (scalar[n->left] || scalar[n->right])  // data_array_logic.rs:25-30
+          return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Cannot do data_array %s, left:%s, right:%s", sym,
+                                          dtype_name(ty[n->left]), dtype_name(ty[n->right])));
+        for (int c : {n->left, n->right})
+          if (ty[c] != FQ_BOOL)
+            return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Cannot downcast_array from datatype:%s item to:BooleanArray", dtype_name(ty[c])));
+        ty[i] = FQ_BOOL;
+        return true;
+      }
+      default:
+        return fail(FQ_ERR_INVALID, fmt("Internal Error: unknown expression node kind %d", n->kind));
+    }
+  }
+
+  static std::string literal(fq_dtype t, fq_scalar_bits v) {
+    switch (t) {
+      case FQ_BOOL: return v.i ? "true" : "false";
+      case FQ_I8: case FQ_I16: case FQ_I32:
+        return fmt("((%s)(%" PRId64 "))", ctype(t), v.i);
+      case FQ_I64:
+        if (v.i == INT64_MIN) return "((fq_i64)(-9223372036854775807ll - 1))";
+        return fmt("((fq_i64)(%" PRId64 "ll))", v.i);
+      case FQ_U8: case FQ_U16: case FQ_U32:
+        return fmt("((%s)(%" PRIu64 "u))", ctype(t), v.u);
+      case FQ_U64: return fmt("((fq_u64)(%" PRIu64 "ull))", v.u);
+      case FQ_F32: return fmt("((float)(%a))", (double)(float)v.f);
+      case FQ_F64: return fmt("((double)(%a))", v.f);
+      default: return "0";
+    }
+  }
+  std::string cast(const std::string &e, fq_dtype from, fq_dtype to) {
+    if (from == to) return e;
+    return fmt("fq_cast<%s, %s>(", ctype(to), ctype(from)) + e + ", err)";
+  }
+  // row-wise value of node i (its own dtype), reading row slot `r.c<k>[v]`
+  std::string emit(int i) {
+    const fq_expr_node &n = d.nodes[i];
+    switch (n.kind) {
+      case FQ_EXPR_FIELD: return fmt("r.c%d[v]", n.column);
+      case FQ_EXPR_CONSTANT: return literal(n.dtype, n.value);
+      case FQ_EXPR_ALIAS: case FQ_EXPR_AGGREGATOR: return emit(n.left);  // function_aggregator.rs:53-55
+      case FQ_EXPR_ARITHMETIC: {
+        fq_dtype t = ty[i];
+        std::string a = cast(emit(n.left), ty[n.left], t), b = cast(emit(n.right), ty[n.right], t);
+        if (n.op == FQ_AR_DIV) {
+          const fq_expr_node &rn = d.nodes[n.right];
+          if (scalar[n.right] && rn.kind == FQ_EXPR_CONSTANT &&
+              (is_float(rn.dtype) ? rn.value.f == 0.0 : rn.value.u == 0))
+            const_div0 = true;
+          return fmt("fq_div<%s>(", ctype(t)) + a + ", " + b + ", err)";
+        }
+        const char *f = n.op == FQ_AR_ADD ? "fq_add" : n.op == FQ_AR_SUB ? "fq_sub" : "fq_mul";
+        return fmt("%s<%s>(", f, ctype(t)) + a + ", " + b + ")";
+      }
+      case FQ_EXPR_COMPARISON: {
+        fq_dtype t;
+        std::string e;
+        equal_coercion(cmp_sym(n.op), ty[n.left], ty[n.right], &t, &e);
+        return "(" + cast(emit(n.left), ty[n.left], t) + " " + cmp_c(n.op) + " " + cast(emit(n.right), ty[n.right], t) + ")";
+      }
+      case FQ_EXPR_LOGIC:  // non-short-circuit: both sides are evaluated (and may raise) in the reference
+        return "(" + emit(n.left) + (n.op == FQ_LG_AND ? " & " : " | ") + emit(n.right) + ")";
+    }
+    return "0";
+  }
+
+  // Aggregator leaves reachable without crossing another Aggregator
+  void collect_aggs(int i, std::set<int> &out) {
+    const fq_expr_node &n = d.nodes[i];
+    switch (n.kind) {
+      case FQ_EXPR_AGGREGATOR: out.insert(i); break;
+      case FQ_EXPR_ALIAS: collect_aggs(n.left, out); break;
+      case FQ_EXPR_ARITHMETIC: case FQ_EXPR_COMPARISON: case FQ_EXPR_LOGIC:
+        collect_aggs(n.left, out);
+        collect_aggs(n.right, out);
+        break;
+      default: break;
+    }
+  }
+};
+
+uint64_t fnv1a(const std::string &s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+
+std::string identity_of(int op, fq_dtype t) {
+  if (op == FQ_AGG_SUM || op == FQ_AGG_COUNT) return fmt("(%s)0", ctype(t));
+  if (op == FQ_AGG_MIN) return fmt("fq_traits<%s>::hi()", ctype(t));
+  return fmt("fq_traits<%s>::lo()", ctype(t));
+}
+
+}  // namespace
+
+int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
+  *out = Generated();
+  if (d.n_cols < 0 || d.n_cols > FQ_MAX_COLS || d.n_exprs < 1 || d.n_exprs > FQ_MAX_EXPRS || !d.nodes || d.n_nodes < 1) {
+    *err = "Error during plan: pipe needs 1..8 select expressions over at most 8 input columns";
+    return FQ_ERR_PLAN;
+  }
+  if (d.generated && d.n_cols < 1) {
+    *err = "Error during plan: generated numbers source needs column 0";
+    return FQ_ERR_PLAN;
+  }
+  Gen g(d);
+  if (d.predicate >= 0) {
+    if (!g.infer(d.predicate)) { *err = g.err; return g.status; }
+    if (g.ty[d.predicate] != FQ_BOOL || g.scalar[d.predicate]) {  // transform_filter.rs:45-50
+      *err = "Internal Error: cannot downcast to boolean array";
+      return FQ_ERR_INTERNAL;
+    }
+  }
+  for (int e = 0; e < d.n_exprs; e++) {
+    if (!g.infer(d.exprs[e])) { *err = g.err; return g.status; }
+    out->expr_dtypes.push_back(g.ty[d.exprs[e]]);
+  }
+  out->kind = d.kind;
+  out->has_pred = d.predicate >= 0;
+  out->generated_source = d.generated != 0;
+
+  std::set<int> aggs;
+  if (d.kind == FQ_PIPE_AGGREGATE) {
+    for (int e = 0; e < d.n_exprs; e++) g.collect_aggs(d.exprs[e], aggs);
+    for (int a : aggs) {
+      const fq_expr_node &n = d.nodes[a];
+      fq_dtype t = n.op == FQ_AGG_COUNT ? (fq_dtype)FQ_U64 : g.ty[n.left];
+      if (n.op != FQ_AGG_COUNT && !is_numeric(t)) {  // data_array_aggregate.rs:153-161
+        *err = fmt("Internal Error: Unsupported data_array_%s for data type: %s", agg_name(n.op), dtype_name(t));
+        return FQ_ERR_INTERNAL;
+      }
+      out->agg_nodes.push_back(a);
+      out->agg_ops.push_back(n.op);
+      out->agg_dtypes.push_back(t);
+    }
+    // select expression types: Count -> UInt64 at the leaf (function_aggregator.rs:38-43)
+    std::function<int(int, fq_dtype *)> rtype = [&](int i, fq_dtype *t) -> int {
+      const fq_expr_node &n = d.nodes[i];
+      if (n.kind == FQ_EXPR_AGGREGATOR && n.op == FQ_AGG_COUNT) { *t = FQ_U64; return FQ_OK; }
+      if (n.kind == FQ_EXPR_ALIAS) return rtype(n.left, t);
+      if (n.kind == FQ_EXPR_ARITHMETIC) {
+        fq_dtype a, b;
+        if (int st = rtype(n.left, &a)) return st;
+        if (int st = rtype(n.right, &b)) return st;
+        return numerical_coercion(arith_sym(n.op), a, b, t, err);
+      }
+      *t = g.ty[i];
+      return FQ_OK;
+    };
+    for (int e = 0; e < d.n_exprs; e++)
+      if (int st = rtype(d.exprs[e], &out->expr_dtypes[e])) return st;
+  }
+
+  // ---- vector width and Rows layout ----
+  size_t min_w = 8;
+  for (int c : g.used_cols) { size_t w = dtype_size(g.col_dtype(c)); if (w < min_w) min_w = w; }
+  int V = (int)(16 / min_w);
+  if (V < 2) V = 2;
+  out->vec = V;
+  out->used_cols.assign(g.used_cols.begin(), g.used_cols.end());
+  for (int c : g.used_cols)
+    if (!(d.generated && c == 0)) out->row_bytes += (int)dtype_size(g.col_dtype(c));
+
+  std::string s;
+  s += "struct Q_@ {\n";
+  s += fmt("  static constexpr int V = %d;\n  static constexpr int NSLOTS = %d;\n  static constexpr bool HAS_PRED = %s;\n", V,
+           (int)out->agg_nodes.size(), out->has_pred ? "true" : "false");
+  s += "  struct Rows {";
+  for (int c : g.used_cols) s += fmt(" %s c%d[V];", ctype(g.col_dtype(c)), c);
+  s += " };\n";
+  s += "  __device__ static __forceinline__ void load(Rows &r, const fq_launch_params &p, fq_u64 g) {\n";
+  for (int c : g.used_cols) {
+    if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
+    else s += fmt("    fq_load_vec<%s, V>(r.c%d, p.cols[%d], g);\n", ctype(g.col_dtype(c)), c, c);
+  }
+  s += "  }\n";
+  s += "  __device__ static __forceinline__ void load1(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
+  for (int c : g.used_cols) {
+    if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
+    else s += fmt("    r.c%d[0] = __ldg((const %s *)p.cols[%d] + row);\n", c, ctype(g.col_dtype(c)), c);
+  }
+  s += "  }\n";
+  s += "  __device__ static __forceinline__ void copy_row(Rows &dst, int v, const Rows &one) {\n";
+  for (int c : g.used_cols) s += fmt("    dst.c%d[v] = one.c%d[0];\n", c, c);
+  s += "  }\n";
+  s += "  __device__ static __forceinline__ bool pred(const Rows &r, int v, fq_u32 &err) {\n";
+  s += "    return " + (out->has_pred ? g.emit(d.predicate) : std::string("true")) + ";\n  }\n";
+
+  if (d.kind == FQ_PIPE_AGGREGATE) {
+    const int n = (int)out->agg_nodes.size();
+    s += "  struct Acc {";
+    for (int k = 0; k < n; k++) s += fmt(" %s a%d;", ctype(out->agg_dtypes[k]), k);
+    s += " };\n";
+    s += "  __device__ static __forceinline__ void init(Acc &a) {\n";
+    for (int k = 0; k < n; k++) s += fmt("    a.a%d = %s;\n", k, identity_of(out->agg_ops[k], out->agg_dtypes[k]).c_str());
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void consume(Acc &a, const Rows &r, int v, fq_u64 &nsel, fq_u32 &err) {\n";
+    if (out->has_pred) s += "    if (!pred(r, v, err)) return;\n    nsel += 1;\n";
+    for (int k = 0; k < n; k++) {
+      const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
+      const char *T = ctype(out->agg_dtypes[k]);
+      std::string arg = g.emit(an.left);
+      switch (an.op) {
+        case FQ_AGG_SUM: s += fmt("    a.a%d = fq_add<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
+        case FQ_AGG_MIN: s += fmt("    a.a%d = fq_min<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
+        case FQ_AGG_MAX: s += fmt("    a.a%d = fq_max<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
+        default:  // Count evaluates (and discards) its argument, function_aggregator.rs:58-66: keep its error checks only
+          s += "    { auto unused = " + arg + "; (void)unused; }\n";
+      }
+    }
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void merge(Acc &a, const Acc &b) {\n";
+    for (int k = 0; k < n; k++) {
+      const char *T = ctype(out->agg_dtypes[k]);
+      const char *f = out->agg_ops[k] == FQ_AGG_MIN ? "fq_min" : out->agg_ops[k] == FQ_AGG_MAX ? "fq_max" : "fq_add";
+      s += fmt("    a.a%d = %s<%s>(a.a%d, b.a%d);\n", k, f, T, k, k);
+    }
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void shfl(Acc &a, int m) {\n";
+    for (int k = 0; k < n; k++) s += fmt("    a.a%d = fq_shfl_xor<%s>(a.a%d, m);\n", k, ctype(out->agg_dtypes[k]), k);
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void store(const Acc &a, fq_u64 *o) {\n";
+    for (int k = 0; k < n; k++) s += fmt("    o[%d] = fq_pack<%s>(a.a%d);\n", k, ctype(out->agg_dtypes[k]), k);
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void unpack(Acc &a, const fq_u64 *o) {\n";
+    for (int k = 0; k < n; k++) s += fmt("    a.a%d = fq_unpack<%s>(o[%d]);\n", k, ctype(out->agg_dtypes[k]), k);
+    s += "  }\n";
+  } else {
+    s += "  __device__ static __forceinline__ void emit(const Rows &r, int v, const fq_launch_params &p, fq_u64 pos, fq_u32 &err) {\n";
+    for (int e = 0; e < d.n_exprs; e++) {
+      fq_dtype t = out->expr_dtypes[e];
+      s += fmt("    ((%s *)p.outs[%d])[pos] = ", t == FQ_BOOL ? "fq_u8" : ctype(t), e) + g.emit(d.exprs[e]) + ";\n";
+    }
+    s += "  }\n";
+  }
+  s += "};\n";
+  if (d.kind == FQ_PIPE_AGGREGATE) {
+    s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS) fqk_@_agg_u4(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 4>(p); }\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n";
+  } else if (out->has_pred) {
+    s += "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, FQ_SEL_UNROLL>(p); }\n";
+  } else {
+    s += "extern \"C\" __global__ void __launch_bounds__(FQ_MAP_THREADS, FQ_MAP_MIN_BLOCKS) fqk_@_map(const __grid_constant__ fq_launch_params p) { fq_map_kernel<Q_@, FQ_MAP_UNROLL>(p); }\n";
+  }
+
+  if (g.status != FQ_OK) { *err = g.err; return g.status; }
+  out->const_divide_by_zero = g.const_div0;
+  char tag[32];
+  snprintf(tag, sizeof tag, "%016" PRIx64, fnv1a(s));
+  out->tag = tag;
+  std::string src;
+  for (size_t i = 0; i < s.size(); i++) {
+    if (s[i] == '@') src += out->tag; else src += s[i];
+  }
+  out->source = src;
+  out->node_dtypes = g.ty;
+  return FQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// s-expression reader (build-time AOT list, C++ tests)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SexprParser {
+  const std::string &t;
+  size_t i = 0;
+  const std::vector<std::string> &cols;
+  std::vector<fq_expr_node> *nodes;
+  std::string err;
+
+  std::string tok() {
+    while (i < t.size() && isspace((unsigned char)t[i])) i++;
+    size_t b = i;
+    if (i < t.size() && (t[i] == '(' || t[i] == ')')) { i++; return t.substr(b, 1); }
+    while (i < t.size() && !isspace((unsigned char)t[i]) && t[i] != '(' && t[i] != ')') i++;
+    return t.substr(b, i - b);
+  }
+  int push(fq_expr_node n) { nodes->push_back(n); return (int)nodes->size() - 1; }
+  int parse() {
+    if (tok() != "(") { err = "expected ("; return -1; }
+    std::string h = tok();
+    fq_expr_node n;
+    memset(&n, 0, sizeof n);
+    n.left = n.right = -1;
+    static const struct { const char *name; int kind, op; } ops[] = {
+        {"+", FQ_EXPR_ARITHMETIC, FQ_AR_ADD}, {"-", FQ_EXPR_ARITHMETIC, FQ_AR_SUB}, {"*", FQ_EXPR_ARITHMETIC, FQ_AR_MUL},
+        {"/", FQ_EXPR_ARITHMETIC, FQ_AR_DIV}, {"=", FQ_EXPR_COMPARISON, FQ_CMP_EQ}, {"<", FQ_EXPR_COMPARISON, FQ_CMP_LT},
+        {"<=", FQ_EXPR_COMPARISON, FQ_CMP_LTEQ}, {">", FQ_EXPR_COMPARISON, FQ_CMP_GT}, {">=", FQ_EXPR_COMPARISON, FQ_CMP_GTEQ},
+        {"and", FQ_EXPR_LOGIC, FQ_LG_AND}, {"or", FQ_EXPR_LOGIC, FQ_LG_OR}, {"min", FQ_EXPR_AGGREGATOR, FQ_AGG_MIN},
+        {"max", FQ_EXPR_AGGREGATOR, FQ_AGG_MAX}, {"sum", FQ_EXPR_AGGREGATOR, FQ_AGG_SUM}, {"count", FQ_EXPR_AGGREGATOR, FQ_AGG_COUNT}};
+    static const struct { const char *name; fq_dtype t; } tys[] = {
+        {"bool", FQ_BOOL}, {"i8", FQ_I8}, {"i16", FQ_I16}, {"i32", FQ_I32}, {"i64", FQ_I64}, {"u8", FQ_U8},
+        {"u16", FQ_U16}, {"u32", FQ_U32}, {"u64", FQ_U64}, {"f32", FQ_F32}, {"f64", FQ_F64}};
+    bool done = false;
+    if (h == "col") {
+      std::string name = tok();
+      n.kind = FQ_EXPR_FIELD;
+      n.column = -1;
+      for (size_t c = 0; c < cols.size(); c++) if (cols[c] == name) n.column = (int)c;
+      if (n.column < 0) { err = "unknown column " + name; return -1; }
+      done = true;
+    } else if (h == "alias") {
+      tok();
+      n.kind = FQ_EXPR_ALIAS;
+      n.left = parse();
+      if (n.left < 0) return -1;
+      done = true;
+    }
+    for (auto &ty : tys)
+      if (!done && h == ty.name) {
+        std::string lit = tok();
+        n.kind = FQ_EXPR_CONSTANT;
+        n.dtype = ty.t;
+        if (ty.t == FQ_BOOL) n.value.i = lit == "true";
+        else if (is_float(ty.t)) n.value.f = ty.t == FQ_F32 ? (double)strtof(lit.c_str(), nullptr) : strtod(lit.c_str(), nullptr);
+        else if (is_signed_int(ty.t)) n.value.i = strtoll(lit.c_str(), nullptr, 10);
+        else n.value.u = strtoull(lit.c_str(), nullptr, 10);
+        done = true;
+      }
+    for (auto &o : ops)
+      if (!done && h == o.name) {
+        n.kind = o.kind;
+        n.op = o.op;
+        n.left = parse();
+        if (n.left < 0) return -1;
+        if (o.kind != FQ_EXPR_AGGREGATOR) {
+          n.right = parse();
+          if (n.right < 0) return -1;
+        }
+        done = true;
+      }
+    if (!done) { err = "unknown head " + h; return -1; }
+    if (tok() != ")") { err = "expected )"; return -1; }
+    return push(n);
+  }
+};
+}  // namespace
+
+int parse_sexpr(const std::string &text, const std::vector<std::string> &cols, std::vector<fq_expr_node> *nodes, int *root,
+                std::string *err) {
+  SexprParser p{text, 0, cols, nodes, {}};
+  int r = p.parse();
+  if (r < 0) { *err = "Error during plan: " + p.err + " in `" + text + "`"; return FQ_ERR_PLAN; }
+  *root = r;
+  return FQ_OK;
+}
+
+}  // namespace fq

@@ -1,0 +1,44 @@
+// codegen.h — lowers a pipe description (expression trees over typed input columns) to the CUDA
+// source of the struct `Q` that specialises the kernel skeletons in kernels/fq_skeleton.cuh.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fuse_gpu.h"
+
+namespace fq {
+
+struct Generated {
+  std::string source;      // struct Q_<hash> + extern "C" kernel wrappers (skeleton not included)
+  std::string tag;         // 16 hex digits: FNV-1a of the specialised text, names the kernels
+  int kind = 0;            // FQ_PIPE_*
+  bool has_pred = false;
+  bool generated_source = false;
+  int vec = 2;             // rows per thread per vector load group (Q::V)
+  int row_bytes = 0;       // bytes read per row (materialised columns actually referenced)
+  std::vector<int> used_cols;
+  // aggregate pipes: Aggregator leaves in node-index order
+  std::vector<int> agg_nodes, agg_ops;
+  std::vector<fq_dtype> agg_dtypes;     // state type of each leaf (Count -> UInt64)
+  // select expressions
+  std::vector<fq_dtype> expr_dtypes;    // Function::return_type
+  std::vector<fq_dtype> node_dtypes;    // per node, FQ_NULL when not reachable
+  bool const_divide_by_zero = false;    // a literal zero divisor is evaluated for every scanned row
+};
+
+// Returns FQ_OK or an fq_status; `err` receives the FuseQueryError-style message.
+int generate(const fq_pipe_desc &desc, Generated *out, std::string *err);
+
+// numerical_coercion / equal_coercion of datavalues/data_type.rs:27-98
+int numerical_coercion(const char *op, fq_dtype l, fq_dtype r, fq_dtype *out, std::string *err);
+const char *dtype_name(fq_dtype t);   // arrow DataType Debug
+size_t dtype_size(fq_dtype t);
+
+// Tiny s-expression reader used by the build-time AOT generator and the C++ tests:
+//   (col number) (u64 1) (+ a b) (sum a) (alias c1 a) ...   `cols` maps names to column indexes.
+int parse_sexpr(const std::string &text, const std::vector<std::string> &cols, std::vector<fq_expr_node> *nodes,
+                int *root, std::string *err);
+
+}  // namespace fq

@@ -1,0 +1,644 @@
+// fuse_gpu.cu — implementation of the C ABI in include/fuse_gpu.h.
+//
+// Host side of libfuse_gpu.so: contexts, device columns, the pipe compiler front end (codegen ->
+// precompiled table lookup -> NVRTC), launch shapes and result decoding.  No torch, no Python.
+// libcuda and libnvrtc are dlopen'ed on first use so the library loads (and exports its symbols) on a
+// machine without a GPU; every data-path entry point then fails loudly with FQ_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fuse_gpu.h"
+#include "codegen.h"
+#include "kernels/fq_skeleton.cuh"
+#include "generated/skeleton_embed.h"  // static const char fq_skeleton_src[]
+
+// ---------------------------------------------------------------------------------------------
+// precompiled kernels (generated/aot_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+struct fq_aot_entry { const char *name; const void *fn; };
+extern "C" const fq_aot_entry fq_aot_table[];
+extern "C" const int fq_aot_count;
+
+namespace {
+
+thread_local std::string g_err;
+
+fq_status set_err(fq_status st, const char *f, ...) __attribute__((format(printf, 2, 3)));
+fq_status set_err(fq_status st, const char *f, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  g_err = buf;
+  return st;
+}
+#define CUDA_TRY(expr)                                                                                \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) return set_err(FQ_ERR_CUDA, "CUDA error: %s (%s)", cudaGetErrorString(e_), #expr); \
+  } while (0)
+
+// ---- driver API + NVRTC through dlopen ----
+typedef int CUresult_;
+typedef struct CUmod_st *CUmodule_;
+typedef struct CUfunc_st *CUfunction_;
+struct Driver {
+  void *h = nullptr;
+  CUresult_ (*cuModuleLoadData)(CUmodule_ *, const void *) = nullptr;
+  CUresult_ (*cuModuleGetFunction)(CUfunction_ *, CUmodule_, const char *) = nullptr;
+  CUresult_ (*cuModuleUnload)(CUmodule_) = nullptr;
+  CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **,
+                              void **) = nullptr;
+  CUresult_ (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction_, int, size_t) = nullptr;
+  CUresult_ (*cuGetErrorString)(CUresult_, const char **) = nullptr;
+  std::string why;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { why = dlerror(); return false; }
+#define SYM(n) *(void **)(&n) = dlsym(h, #n)
+    SYM(cuModuleLoadData); SYM(cuModuleGetFunction); SYM(cuModuleUnload); SYM(cuLaunchKernel);
+    SYM(cuOccupancyMaxActiveBlocksPerMultiprocessor); SYM(cuGetErrorString);
+#undef SYM
+    if (!cuModuleLoadData || !cuModuleGetFunction || !cuLaunchKernel || !cuOccupancyMaxActiveBlocksPerMultiprocessor) {
+      why = "libcuda.so.1 lacks required symbols";
+      return false;
+    }
+    return true;
+  }
+  std::string err(CUresult_ r) {
+    const char *s = nullptr;
+    if (cuGetErrorString) cuGetErrorString(r, &s);
+    return s ? s : "unknown driver error";
+  }
+};
+typedef struct _nvrtcProgram *nvrtcProgram_;
+struct Nvrtc {
+  void *h = nullptr;
+  int (*nvrtcCreateProgram)(nvrtcProgram_ *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*nvrtcCompileProgram)(nvrtcProgram_, int, const char *const *) = nullptr;
+  int (*nvrtcGetCUBINSize)(nvrtcProgram_, size_t *) = nullptr;
+  int (*nvrtcGetCUBIN)(nvrtcProgram_, char *) = nullptr;
+  int (*nvrtcGetProgramLogSize)(nvrtcProgram_, size_t *) = nullptr;
+  int (*nvrtcGetProgramLog)(nvrtcProgram_, char *) = nullptr;
+  int (*nvrtcDestroyProgram)(nvrtcProgram_ *) = nullptr;
+  const char *(*nvrtcGetErrorString)(int) = nullptr;
+  std::string why;
+  bool load() {
+    if (h) return true;
+    const char *cands[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char *c : cands) {
+      h = dlopen(c, RTLD_NOW);
+      if (h) break;
+    }
+    if (!h) { why = dlerror(); return false; }
+#define SYM(n) *(void **)(&n) = dlsym(h, #n)
+    SYM(nvrtcCreateProgram); SYM(nvrtcCompileProgram); SYM(nvrtcGetCUBINSize); SYM(nvrtcGetCUBIN);
+    SYM(nvrtcGetProgramLogSize); SYM(nvrtcGetProgramLog); SYM(nvrtcDestroyProgram); SYM(nvrtcGetErrorString);
+#undef SYM
+    if (!nvrtcCreateProgram || !nvrtcCompileProgram || !nvrtcGetCUBIN) { why = "libnvrtc lacks required symbols"; return false; }
+    return true;
+  }
+};
+Driver g_drv;
+Nvrtc g_nvrtc;
+std::mutex g_mu;
+
+struct Kernel {
+  const void *aot = nullptr;   // host stub of a precompiled kernel (cudaLaunchKernel)
+  CUfunction_ jit = nullptr;   // NVRTC-built (cuLaunchKernel)
+  int threads = 256;
+  int blocks_per_sm = 1;
+  bool valid() const { return aot || jit; }
+};
+
+struct Module {  // one compiled specialisation, shared by every pipe with the same tag
+  std::map<std::string, Kernel> kernels;
+  bool precompiled = false;
+  CUmodule_ mod = nullptr;
+};
+
+}  // namespace
+
+struct fq_ctx {
+  int device = 0;
+  int sm_count = 0;
+  uint64_t launches = 0;
+  std::mutex mu;
+  std::map<std::string, Module> modules;  // tag -> module
+};
+
+struct fq_column {
+  fq_dtype dtype = FQ_NULL;
+  uint64_t len = 0;
+  void *ptr = nullptr;
+  bool owned = false;
+};
+
+struct fq_pipe {
+  fq::Generated gen;
+  Kernel k_agg_u4, k_agg_u8, k_select, k_map;
+  bool precompiled = false;
+  int n_slots = 0;          // FQ_STATE_HDR + leaves
+  uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
+  uint64_t *h_state = nullptr, *h_result = nullptr;  // pinned
+  int partials_cap = 0;
+  uint64_t tiles_cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool launched = false, launched_project = false;
+  uint64_t capacity_eff = 0;
+  bool skipped = false;     // project launch over zero rows
+};
+
+namespace {
+
+fq_status use(fq_ctx *ctx) {
+  if (!ctx) return set_err(FQ_ERR_INVALID, "Internal Error: null context");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return FQ_OK;
+}
+
+__global__ void __launch_bounds__(256) fq_fill_numbers(fq_u64 *dst, fq_u64 begin, fq_u64 n) {
+  // two values (16 B) per thread per step; dst is 16-byte aligned when (dst offset) is even
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  const bool aligned = (((fq_u64)dst) & 15) == 0;
+  if (aligned) {
+    const fq_u64 nvec = n / 2;
+    for (fq_u64 g = tid; g < nvec; g += nthreads) {
+      ulonglong2 v;
+      v.x = begin + 2 * g;
+      v.y = begin + 2 * g + 1;
+      reinterpret_cast<ulonglong2 *>(dst)[g] = v;
+    }
+    if (tid == 0 && (n & 1)) dst[n - 1] = begin + n - 1;
+  } else {
+    for (fq_u64 i = tid; i < n; i += nthreads) dst[i] = begin + i;
+  }
+}
+
+fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m) {
+  if (!g_nvrtc.load()) return set_err(FQ_ERR_CUDA, "NVRTC unavailable: %s", g_nvrtc.why.c_str());
+  if (!g_drv.load()) return set_err(FQ_ERR_CUDA, "CUDA driver unavailable: %s", g_drv.why.c_str());
+  std::string src = std::string(fq_skeleton_src) + "\n" + gen.source;
+  nvrtcProgram_ prog = nullptr;
+  int r = g_nvrtc.nvrtcCreateProgram(&prog, src.c_str(), ("fq_" + gen.tag + ".cu").c_str(), 0, nullptr, nullptr);
+  if (r) return set_err(FQ_ERR_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.nvrtcGetErrorString(r));
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  r = g_nvrtc.nvrtcCompileProgram(prog, 3, opts);
+  if (r) {
+    size_t n = 0;
+    g_nvrtc.nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, 0);
+    if (n) g_nvrtc.nvrtcGetProgramLog(prog, &log[0]);
+    g_nvrtc.nvrtcDestroyProgram(&prog);
+    return set_err(FQ_ERR_CUDA, "NVRTC compile failed: %s\n%.1500s", g_nvrtc.nvrtcGetErrorString(r), log.c_str());
+  }
+  size_t n = 0;
+  g_nvrtc.nvrtcGetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  g_nvrtc.nvrtcGetCUBIN(prog, cubin.data());
+  g_nvrtc.nvrtcDestroyProgram(&prog);
+  cudaFree(nullptr);  // make sure the primary context exists and is current
+  CUresult_ cr = g_drv.cuModuleLoadData(&m->mod, cubin.data());
+  if (cr) return set_err(FQ_ERR_CUDA, "cuModuleLoadData: %s", g_drv.err(cr).c_str());
+  (void)ctx;
+  return FQ_OK;
+}
+
+fq_status resolve_kernel(Module *m, const std::string &name, int threads, Kernel *out) {
+  auto it = m->kernels.find(name);
+  if (it != m->kernels.end()) { *out = it->second; return FQ_OK; }
+  Kernel k;
+  k.threads = threads;
+  if (m->precompiled) {
+    for (int i = 0; i < fq_aot_count; i++)
+      if (name == fq_aot_table[i].name) k.aot = fq_aot_table[i].fn;
+    if (!k.aot) return set_err(FQ_ERR_INTERNAL, "Internal Error: precompiled kernel %s missing", name.c_str());
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.aot, threads, 0));
+  } else {
+    CUresult_ cr = g_drv.cuModuleGetFunction(&k.jit, m->mod, name.c_str());
+    if (cr) return set_err(FQ_ERR_CUDA, "cuModuleGetFunction(%s): %s", name.c_str(), g_drv.err(cr).c_str());
+    cr = g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.jit, threads, 0);
+    if (cr) return set_err(FQ_ERR_CUDA, "cuOccupancy: %s", g_drv.err(cr).c_str());
+  }
+  if (k.blocks_per_sm < 1) k.blocks_per_sm = 1;
+  m->kernels[name] = k;
+  *out = k;
+  return FQ_OK;
+}
+
+fq_status launch(fq_ctx *ctx, const Kernel &k, unsigned grid, const fq_launch_params &p, void *stream) {
+  void *args[] = {(void *)&p};
+  if (k.aot) {
+    CUDA_TRY(cudaLaunchKernel(k.aot, dim3(grid), dim3(k.threads), args, 0, (cudaStream_t)stream));
+  } else {
+    CUresult_ cr = g_drv.cuLaunchKernel(k.jit, grid, 1, 1, (unsigned)k.threads, 1, 1, 0, stream, args, nullptr);
+    if (cr) return set_err(FQ_ERR_CUDA, "cuLaunchKernel: %s", g_drv.err(cr).c_str());
+  }
+  ctx->launches++;
+  return FQ_OK;
+}
+
+fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_params *p) {
+  if (!src) return set_err(FQ_ERR_INVALID, "Internal Error: null source");
+  if ((src->generated != 0) != pipe->gen.generated_source)
+    return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a %s source", pipe->gen.generated_source ? "generated" : "materialised");
+  p->n_rows = src->n_rows;
+  p->numbers_begin = src->numbers_begin;
+  for (int c : pipe->gen.used_cols) {
+    if (pipe->gen.generated_source && c == 0) continue;
+    if (c >= src->n_cols || !src->cols || !src->cols[c]) return set_err(FQ_ERR_INVALID, "Internal Error: source lacks column %d", c);
+    const fq_column *col = src->cols[c];
+    if (col->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: column %d has %" PRIu64 " rows, source says %" PRIu64, c, col->len, src->n_rows);
+    if (((uintptr_t)col->ptr & 15) != 0) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: column %d is not 16-byte aligned", c);
+    p->cols[c] = col->ptr;
+  }
+  return FQ_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+uint32_t fq_abi_version(void) { return FQ_ABI_VERSION; }
+
+const char *fq_last_error(const fq_ctx *) { return g_err.c_str(); }
+
+fq_status fq_ctx_create(int32_t device, fq_ctx **out) {
+  if (!out) return set_err(FQ_ERR_INVALID, "Internal Error: null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_err(FQ_ERR_CUDA, "CUDA error: no usable CUDA device (%s); libfuse_gpu has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_err(FQ_ERR_INVALID, "Internal Error: device %d out of range (%d devices)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(nullptr));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_err(FQ_ERR_CUDA, "CUDA error: device %d is sm_%d%d; libfuse_gpu is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  fq_ctx *c = new fq_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return FQ_OK;
+}
+
+void fq_ctx_destroy(fq_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto &kv : ctx->modules)
+    if (kv.second.mod && g_drv.cuModuleUnload) g_drv.cuModuleUnload(kv.second.mod);
+  delete ctx;
+}
+
+uint64_t fq_ctx_launch_count(const fq_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t fq_ctx_sm_count(const fq_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+// ---- columns ----
+fq_status fq_column_alloc(fq_ctx *ctx, fq_dtype dtype, uint64_t len, fq_column **out) {
+  if (fq_status st = use(ctx)) return st;
+  size_t w = fq::dtype_size(dtype);
+  if (!w) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: column of type %s", fq::dtype_name(dtype));
+  fq_column *c = new fq_column();
+  c->dtype = dtype;
+  c->len = len;
+  c->owned = true;
+  size_t bytes = (size_t)len * w;
+  bytes = (bytes + 255) & ~(size_t)255;  // whole vector groups stay in bounds
+  cudaError_t e = cudaMalloc(&c->ptr, bytes ? bytes : 256);
+  if (e != cudaSuccess) {
+    delete c;
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (cudaMalloc of %zu bytes)", cudaGetErrorString(e), bytes);
+  }
+  *out = c;
+  return FQ_OK;
+}
+fq_status fq_column_wrap(fq_ctx *ctx, fq_dtype dtype, uint64_t len, void *device_values, fq_column **out) {
+  if (!ctx || !out) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (!fq::dtype_size(dtype)) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: column of type %s", fq::dtype_name(dtype));
+  if (((uintptr_t)device_values & 15) != 0) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: wrapped buffer is not 16-byte aligned");
+  fq_column *c = new fq_column();
+  c->dtype = dtype;
+  c->len = len;
+  c->ptr = device_values;
+  *out = c;
+  return FQ_OK;
+}
+fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset, uint64_t len, fq_column **out) {
+  if (!ctx || !parent || !out) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (offset + len > parent->len) return set_err(FQ_ERR_INVALID, "Internal Error: slice [%" PRIu64 ", +%" PRIu64 ") exceeds %" PRIu64 " rows", offset, len, parent->len);
+  fq_column *c = new fq_column();
+  c->dtype = parent->dtype;
+  c->len = len;
+  c->ptr = (char *)parent->ptr + offset * fq::dtype_size(parent->dtype);
+  *out = c;
+  return FQ_OK;
+}
+void fq_column_free(fq_ctx *ctx, fq_column *col) {
+  if (!col) return;
+  if (col->owned && col->ptr) {
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(col->ptr);
+  }
+  delete col;
+}
+fq_dtype fq_column_dtype(const fq_column *col) { return col ? col->dtype : FQ_NULL; }
+uint64_t fq_column_len(const fq_column *col) { return col ? col->len : 0; }
+void *fq_column_device_ptr(const fq_column *col) { return col ? col->ptr : nullptr; }
+
+fq_status fq_column_upload(fq_ctx *ctx, fq_column *col, uint64_t row_offset, const void *host, uint64_t n_rows, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || row_offset + n_rows > col->len) return set_err(FQ_ERR_INVALID, "Internal Error: upload out of range");
+  size_t w = fq::dtype_size(col->dtype);
+  CUDA_TRY(cudaMemcpyAsync((char *)col->ptr + row_offset * w, host, n_rows * w, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return FQ_OK;
+}
+fq_status fq_column_download(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host, uint64_t n_rows, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || row_offset + n_rows > col->len) return set_err(FQ_ERR_INVALID, "Internal Error: download out of range");
+  size_t w = fq::dtype_size(col->dtype);
+  CUDA_TRY(cudaMemcpyAsync(host, (const char *)col->ptr + row_offset * w, n_rows * w, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return FQ_OK;
+}
+fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return FQ_OK;
+}
+fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out) {
+  if (fq_status st = use(ctx)) return st;
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return FQ_OK;
+}
+void fq_host_free(fq_ctx *ctx, void *p) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (p) cudaFreeHost(p);
+}
+
+fq_status fq_numbers_fill(fq_ctx *ctx, fq_column *col, uint64_t row_offset, uint64_t begin, uint64_t n_rows, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || col->dtype != FQ_U64) return set_err(FQ_ERR_INVALID, "Internal Error: numbers column must be UInt64");
+  if (row_offset + n_rows > col->len) return set_err(FQ_ERR_INVALID, "Internal Error: fill out of range");
+  if (n_rows == 0) return FQ_OK;
+  uint64_t want = (n_rows / 2 + 255) / 256;
+  unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)ctx->sm_count * 8);
+  fq_fill_numbers<<<grid, 256, 0, (cudaStream_t)stream>>>((fq_u64 *)col->ptr + row_offset, begin, n_rows);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return FQ_OK;
+}
+
+// ---- pipes ----
+fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) {
+  if (fq_status st = use(ctx)) return st;
+  if (!desc || !out) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *out = nullptr;
+  fq_pipe *pipe = new fq_pipe();
+  std::string err;
+  int st = fq::generate(*desc, &pipe->gen, &err);
+  if (st) {
+    delete pipe;
+    return set_err(st, "%s", err.c_str());
+  }
+  const fq::Generated &gen = pipe->gen;
+  Module *m;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->modules.find(gen.tag);
+    if (it == ctx->modules.end()) {
+      Module mod;
+      const std::string probe = "fqk_" + gen.tag + "_";
+      for (int i = 0; i < fq_aot_count; i++)
+        if (strncmp(fq_aot_table[i].name, probe.c_str(), probe.size()) == 0) mod.precompiled = true;
+      if (getenv("FQ_FORCE_JIT")) mod.precompiled = false;
+      if (!mod.precompiled) {
+        std::lock_guard<std::mutex> lk2(g_mu);
+        if (fq_status s2 = compile_jit(ctx, gen, &mod)) { delete pipe; return s2; }
+      }
+      it = ctx->modules.emplace(gen.tag, mod).first;
+    }
+    m = &it->second;
+    pipe->precompiled = m->precompiled;
+    fq_status s2 = FQ_OK;
+    const std::string base = "fqk_" + gen.tag;
+    if (gen.kind == FQ_PIPE_AGGREGATE) {
+      s2 = resolve_kernel(m, base + "_agg_u4", FQ_AGG_THREADS, &pipe->k_agg_u4);
+      if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", FQ_AGG_THREADS, &pipe->k_agg_u8);
+    } else if (gen.has_pred) {
+      s2 = resolve_kernel(m, base + "_select", FQ_SEL_THREADS, &pipe->k_select);
+    } else {
+      s2 = resolve_kernel(m, base + "_map", FQ_MAP_THREADS, &pipe->k_map);
+    }
+    if (s2) { delete pipe; return s2; }
+  }
+  pipe->n_slots = FQ_STATE_HDR + (int)gen.agg_nodes.size();
+  cudaError_t e = cudaMalloc(&pipe->d_state, sizeof(uint64_t) * pipe->n_slots);
+  if (e == cudaSuccess) e = cudaMemset(pipe->d_state, 0, sizeof(uint64_t) * pipe->n_slots);
+  if (e == cudaSuccess) e = cudaMalloc(&pipe->d_ctl, 64);
+  if (e == cudaSuccess) e = cudaMemset(pipe->d_ctl, 0, 64);
+  if (e == cudaSuccess) e = cudaHostAlloc(&pipe->h_state, sizeof(uint64_t) * pipe->n_slots, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&pipe->h_result, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pipe->ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fq_pipe_destroy(ctx, pipe);
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (pipe buffers)", cudaGetErrorString(e));
+  }
+  memset(pipe->h_state, 0, sizeof(uint64_t) * pipe->n_slots);
+  memset(pipe->h_result, 0, 64);
+  *out = pipe;
+  return FQ_OK;
+}
+
+void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
+  if (!pipe) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(pipe->d_state);
+  cudaFree(pipe->d_partials);
+  cudaFree(pipe->d_ctl);
+  cudaFree(pipe->d_tiles);
+  if (pipe->h_state) cudaFreeHost(pipe->h_state);
+  if (pipe->h_result) cudaFreeHost(pipe->h_result);
+  if (pipe->ev) cudaEventDestroy(pipe->ev);
+  delete pipe;
+}
+
+int32_t fq_pipe_is_precompiled(const fq_pipe *pipe) { return pipe && pipe->precompiled; }
+const char *fq_pipe_source(const fq_pipe *pipe) { return pipe ? pipe->gen.source.c_str() : ""; }
+
+fq_status fq_pipe_expr_dtype(fq_ctx *, const fq_pipe *pipe, int32_t i, fq_dtype *out) {
+  if (!pipe || !out || i < 0 || i >= (int)pipe->gen.expr_dtypes.size()) return set_err(FQ_ERR_INVALID, "Internal Error: bad expression index");
+  *out = pipe->gen.expr_dtypes[i];
+  return FQ_OK;
+}
+
+fq_status fq_pipe_aggregator_nodes(fq_ctx *, const fq_pipe *pipe, int32_t *nodes, int32_t cap, int32_t *n) {
+  if (!pipe || !n) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *n = (int32_t)pipe->gen.agg_nodes.size();
+  for (int i = 0; i < *n && i < cap && nodes; i++) nodes[i] = pipe->gen.agg_nodes[i];
+  return FQ_OK;
+}
+
+fq_status fq_pipe_state_device(fq_ctx *, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes) {
+  if (!pipe || !dev_ptr || !n_bytes) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *dev_ptr = pipe->d_state;
+  *n_bytes = sizeof(uint64_t) * pipe->n_slots;
+  return FQ_OK;
+}
+
+fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, uint32_t flags, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  fq_launch_params p;
+  memset(&p, 0, sizeof p);
+  if (fq_status st = bind_source(pipe, src, &p)) return st;
+  static const bool want_u8 = getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8;
+  const Kernel &k = want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
+  const int unroll = want_u8 ? 8 : 4;
+  // persistent grid: every resident CTA slot of every SM, fewer when the shard has fewer chunks
+  const uint64_t chunk_rows = (uint64_t)k.threads * unroll * pipe->gen.vec;
+  const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
+  static const int bps_env = getenv("FQ_AGG_BLOCKS_PER_SM") ? atoi(getenv("FQ_AGG_BLOCKS_PER_SM")) : 0;
+  const int bps = bps_env > 0 ? std::min(bps_env, k.blocks_per_sm) : k.blocks_per_sm;
+  unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * bps, chunks));
+  if ((int)grid > pipe->partials_cap) {
+    cudaFree(pipe->d_partials);
+    pipe->d_partials = nullptr;
+    int cap = std::max<int>((int)grid, ctx->sm_count * k.blocks_per_sm);
+    CUDA_TRY(cudaMalloc(&pipe->d_partials, sizeof(uint64_t) * pipe->n_slots * cap));
+    pipe->partials_cap = cap;
+  }
+  p.partials = (fq_u64 *)pipe->d_partials;
+  p.state = (fq_u64 *)pipe->d_state;
+  p.ticket = (fq_u32 *)(pipe->d_ctl + 4);
+  p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
+  if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+  CUDA_TRY(cudaMemcpyAsync(pipe->h_state, pipe->d_state, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
+  pipe->launched = true;
+  return FQ_OK;
+}
+
+static fq_status decode_err(uint64_t bits) {
+  if (bits & FQ_E_DIVZERO) return set_err(FQ_ERR_DIVIDE_BY_ZERO, "Internal Error: Divide by zero error");
+  if (bits & FQ_E_CAST)
+    return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: a numeric cast went out of range (arrow yields NULL; nullable results are not carried yet)");
+  return FQ_OK;
+}
+
+fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
+                                  uint64_t *rows_selected) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  const int n = (int)pipe->gen.agg_nodes.size();
+  if (n_states) *n_states = n;
+  if (pipe->launched) CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  const uint64_t nsel = pipe->h_state[0], folded = pipe->h_state[2];
+  if (rows_selected) *rows_selected = nsel;
+  if (fq_status st = decode_err(pipe->h_state[1])) return st;
+  for (int k = 0; k < n && k < cap && states; k++) {
+    fq_value &v = states[k];
+    memset(&v, 0, sizeof v);
+    if (!pipe->launched || folded == 0) { v.dtype = FQ_NULL; continue; }  // state still DataValue::Null
+    const int op = pipe->gen.agg_ops[k];
+    const fq_dtype t = pipe->gen.agg_dtypes[k];
+    const uint64_t bits = pipe->h_state[FQ_STATE_HDR + k];
+    v.dtype = t;
+    if (op == FQ_AGG_COUNT) {  // state (+) UInt64(rows) per block, function_aggregator.rs:61-66
+      v.some = 1;
+      v.v.u = nsel;
+      continue;
+    }
+    v.some = nsel > 0;  // arrow sum/min/max of an empty array is None
+    if (!v.some) continue;
+    if (t == FQ_F32 || t == FQ_F64) memcpy(&v.v.f, &bits, 8);
+    else v.v.u = bits;
+  }
+  return FQ_OK;
+}
+
+fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols, uint64_t capacity,
+                                 int64_t limit, uint32_t flags, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_PROJECT) return set_err(FQ_ERR_INVALID, "Internal Error: not a projection pipe");
+  fq_launch_params p;
+  memset(&p, 0, sizeof p);
+  if (fq_status st = bind_source(pipe, src, &p)) return st;
+  uint64_t cap = capacity;
+  if (limit >= 0 && (uint64_t)limit < cap) cap = (uint64_t)limit;
+  const int ne = (int)pipe->gen.expr_dtypes.size();
+  for (int e = 0; e < ne; e++) {
+    const fq_column *c = out_cols ? out_cols[e] : nullptr;
+    if (!c) return set_err(FQ_ERR_INVALID, "Internal Error: missing output column %d", e);
+    if (c->dtype != pipe->gen.expr_dtypes[e])
+      return set_err(FQ_ERR_INVALID, "Internal Error: output column %d is %s, expression yields %s", e, fq::dtype_name(c->dtype),
+                     fq::dtype_name(pipe->gen.expr_dtypes[e]));
+    if (c->len < cap && c->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: output column %d shorter than capacity", e);
+    p.outs[e] = c->ptr;
+  }
+  p.capacity = cap;
+  pipe->capacity_eff = cap;
+  p.result = (fq_u64 *)pipe->d_ctl;
+  p.tile_counter = (fq_u32 *)(pipe->d_ctl + 2);
+  p.done = (fq_u32 *)(pipe->d_ctl + 3);
+  p.stop_after = ((flags & FQ_RUN_LIMIT_EARLY_EXIT) && limit > 0) ? (uint64_t)limit : 0;
+  CUDA_TRY(cudaMemsetAsync(pipe->d_ctl, 0, 32, (cudaStream_t)stream));
+  pipe->skipped = false;
+  if (src->n_rows == 0) {
+    pipe->skipped = true;
+  } else if (pipe->gen.has_pred) {
+    const Kernel &k = pipe->k_select;
+    const uint64_t tile_rows = (uint64_t)k.threads * FQ_SEL_UNROLL * pipe->gen.vec;
+    p.n_tiles = (src->n_rows + tile_rows - 1) / tile_rows;
+    if (p.n_tiles > pipe->tiles_cap) {
+      cudaFree(pipe->d_tiles);
+      pipe->d_tiles = nullptr;
+      CUDA_TRY(cudaMalloc(&pipe->d_tiles, sizeof(uint64_t) * p.n_tiles));
+      pipe->tiles_cap = p.n_tiles;
+    }
+    p.tile_status = (fq_u64 *)pipe->d_tiles;
+    CUDA_TRY(cudaMemsetAsync(pipe->d_tiles, 0, sizeof(uint64_t) * p.n_tiles, (cudaStream_t)stream));
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, p.n_tiles));
+    if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+  } else {
+    const Kernel &k = pipe->k_map;
+    const uint64_t chunk_rows = (uint64_t)k.threads * FQ_MAP_UNROLL * pipe->gen.vec;
+    const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
+    if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+  }
+  CUDA_TRY(cudaMemcpyAsync(pipe->h_result, pipe->d_ctl, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
+  pipe->launched_project = true;
+  return FQ_OK;
+}
+
+fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selected, uint64_t *rows_written) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || !pipe->launched_project) return set_err(FQ_ERR_INVALID, "Internal Error: no projection launch to fetch");
+  CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  const uint64_t sel = pipe->skipped ? 0 : pipe->h_result[0];
+  if (rows_selected) *rows_selected = sel;
+  if (rows_written) *rows_written = std::min(sel, pipe->capacity_eff);
+  return decode_err(pipe->h_result[1]);
+}
+
+}  // extern "C"

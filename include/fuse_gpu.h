@@ -1,0 +1,218 @@
+/*
+ * fuse_gpu.h — C ABI of libfuse_gpu.so: the B200 (sm_100a) replacement for fuse-query's vectorised
+ * Source -> Filter -> Projection -> AggregatePartial / Limit hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  A Rust FFI crate
+ * (`extern "C"` block) binds exactly these symbols; the C++ host mirror under
+ * fuse_query_b200/csrc/host and the Python ctypes layer call nothing else.  Citations are
+ * file:line under /root/reference/src and name the reference interface each entry point replaces.
+ *
+ * Conventions
+ *   - every function returns an fq_status (0 = ok); fq_last_error(ctx) returns the message, which
+ *     reproduces the reference's FuseQueryError Display text where one exists (error.rs:10-20);
+ *   - nothing throws or aborts across the ABI;
+ *   - handles are opaque, created/destroyed by the library; host buffers belong to the caller;
+ *   - every launch takes a CUDA stream (cudaStream_t / CUstream passed as void*, NULL = the
+ *     legacy default stream) and is asynchronous; results are read with the matching *_fetch call;
+ *   - a context binds one CUDA device; calls set the device themselves, so any host thread may
+ *     drive any context (the reference runs one tokio task per partition pipe,
+ *     processors/processor_merge.rs:46-62).
+ */
+#ifndef FUSE_GPU_H
+#define FUSE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQ_ABI_VERSION 1
+
+/* status codes; FQ_ERR_INTERNAL/FQ_ERR_PLAN map onto FuseQueryError::{Internal,Plan} (error.rs:10-20) */
+typedef int32_t fq_status;
+enum {
+  FQ_OK = 0,
+  FQ_ERR_INTERNAL = 1,       /* "Internal Error: ..." */
+  FQ_ERR_PLAN = 2,           /* "Error during plan: ..." */
+  FQ_ERR_DIVIDE_BY_ZERO = 3, /* arrow DivideByZero -> "Internal Error: Divide by zero error" */
+  FQ_ERR_UNSUPPORTED = 4,    /* well-formed request the device path does not implement (never a silent fallback) */
+  FQ_ERR_CUDA = 5,           /* CUDA runtime / driver / NVRTC failure */
+  FQ_ERR_INVALID = 6         /* bad handle / argument */
+};
+
+/* DataType / DataValue tags in the declaration order of datavalues/data_value.rs:19-35 */
+typedef int32_t fq_dtype;
+enum {
+  FQ_NULL = 0, FQ_BOOL = 1, FQ_I8 = 2, FQ_I16 = 3, FQ_I32 = 4, FQ_I64 = 5, FQ_U8 = 6, FQ_U16 = 7,
+  FQ_U32 = 8, FQ_U64 = 9, FQ_F32 = 10, FQ_F64 = 11, FQ_UTF8 = 12, FQ_STRUCT = 13
+};
+
+/* operator enums of datavalues/data_value_operator.rs:5-81 */
+enum { FQ_AGG_MIN = 0, FQ_AGG_MAX = 1, FQ_AGG_SUM = 2, FQ_AGG_COUNT = 3 };
+enum { FQ_CMP_EQ = 0, FQ_CMP_LT = 1, FQ_CMP_LTEQ = 2, FQ_CMP_GT = 3, FQ_CMP_GTEQ = 4 };
+enum { FQ_AR_ADD = 0, FQ_AR_SUB = 1, FQ_AR_MUL = 2, FQ_AR_DIV = 3 };
+enum { FQ_LG_AND = 0, FQ_LG_OR = 1 };
+
+/* ---------------------------------------------------------------------------------------------
+ * Expression trees: a flat array of nodes restating `enum Function` (functions/function.rs:16-25).
+ * Children are indexes into the same array; every expression handed to the library is a root index.
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  FQ_EXPR_ALIAS = 0,      /* function_alias.rs: transparent, child in `left` */
+  FQ_EXPR_CONSTANT = 1,   /* function_constant.rs: dtype + value */
+  FQ_EXPR_FIELD = 2,      /* function_field.rs: input column index in `column` */
+  FQ_EXPR_ARITHMETIC = 3, /* function_arithmetic.rs: op in FQ_AR_* */
+  FQ_EXPR_COMPARISON = 4, /* function_comparison.rs: op in FQ_CMP_* */
+  FQ_EXPR_LOGIC = 5,      /* function_logic.rs: op in FQ_LG_* */
+  FQ_EXPR_AGGREGATOR = 6  /* function_aggregator.rs: op in FQ_AGG_*, argument in `left` */
+};
+
+typedef union fq_scalar_bits {
+  int64_t i;  /* FQ_BOOL, FQ_I8..FQ_I64 */
+  uint64_t u; /* FQ_U8..FQ_U64 */
+  double f;   /* FQ_F32 (rounded to float by the library), FQ_F64 */
+} fq_scalar_bits;
+
+typedef struct fq_expr_node {
+  int32_t kind;   /* FQ_EXPR_* */
+  int32_t op;     /* operator for ARITHMETIC / COMPARISON / LOGIC / AGGREGATOR */
+  int32_t left;   /* child index or -1 */
+  int32_t right;  /* child index or -1 */
+  int32_t column; /* FIELD: index into the pipe's input columns */
+  fq_dtype dtype; /* CONSTANT: value type */
+  fq_scalar_bits value;
+} fq_expr_node;
+
+/* DataValue restricted to what crosses the boundary (aggregate states, scalar results) */
+typedef struct fq_value {
+  fq_dtype dtype; /* FQ_NULL = DataValue::Null */
+  int32_t some;   /* 0 = Type(None) */
+  fq_scalar_bits v;
+} fq_value;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fq_ctx fq_ctx;
+
+uint32_t fq_abi_version(void);
+fq_status fq_ctx_create(int32_t device, fq_ctx **out);
+void fq_ctx_destroy(fq_ctx *ctx);
+/* message of the last failing call on this context from the calling thread ("" if none);
+ * ctx == NULL returns the message of a failed fq_ctx_create */
+const char *fq_last_error(const fq_ctx *ctx);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+uint64_t fq_ctx_launch_count(const fq_ctx *ctx);
+/* multiprocessor count of the bound device (grid sizing is the library's job; exposed for reports) */
+int32_t fq_ctx_sm_count(const fq_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Columns — device-resident Arrow-layout buffers replacing ArrayRef inside DataBlock
+ * (datablocks/data_block.rs:10-14): contiguous little-endian values, 256-byte aligned.
+ * Validity bitmaps are not carried yet: every column is NOT NULL like numbers_mt's
+ * (datasources/system/numbers_table.rs:21-25).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fq_column fq_column;
+
+fq_status fq_column_alloc(fq_ctx *ctx, fq_dtype dtype, uint64_t len, fq_column **out);
+/* borrow device memory owned by the caller (e.g. a torch tensor); must be 16-byte aligned */
+fq_status fq_column_wrap(fq_ctx *ctx, fq_dtype dtype, uint64_t len, void *device_values, fq_column **out);
+/* zero-copy view of rows [offset, offset+len) of `parent` (arrow slice); parent must outlive it */
+fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset, uint64_t len, fq_column **out);
+void fq_column_free(fq_ctx *ctx, fq_column *col);
+fq_dtype fq_column_dtype(const fq_column *col);
+uint64_t fq_column_len(const fq_column *col);
+void *fq_column_device_ptr(const fq_column *col);
+/* async copies of `n_rows` values starting at row `row_offset`; host memory should be pinned */
+fq_status fq_column_upload(fq_ctx *ctx, fq_column *col, uint64_t row_offset, const void *host, uint64_t n_rows, void *stream);
+fq_status fq_column_download(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host, uint64_t n_rows, void *stream);
+fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream);
+/* pinned host staging memory */
+fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out);
+void fq_host_free(fq_ctx *ctx, void *p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Source — system.numbers_mt shards.  Replaces NumbersStream::poll_next materialising 10 000-row
+ * UInt64Arrays (datasources/system/numbers_stream.rs:68-83): one fill kernel writes the whole
+ * shard [begin, end] (inclusive, like the partition names of numbers_table.rs:29-55) into HBM.
+ * The "generated" mode has no column at all: see fq_source.numbers_begin.
+ * ------------------------------------------------------------------------------------------- */
+fq_status fq_numbers_fill(fq_ctx *ctx, fq_column *col, uint64_t row_offset, uint64_t begin, uint64_t n_rows, void *stream);
+
+typedef struct fq_source {
+  uint64_t n_rows;
+  int32_t n_cols;             /* materialised input columns (0 in generated mode) */
+  int32_t generated;          /* 1: column 0 is UInt64 `numbers_begin + row`, produced in-kernel */
+  const fq_column *const *cols;
+  uint64_t numbers_begin;
+} fq_source;
+
+/* ---------------------------------------------------------------------------------------------
+ * Pipes — one fused kernel per Source -> [Filter] -> (Projection | AggregatePartial) [-> Limit]
+ * chain of processors/pipeline_builder.rs:26-106.  Compiling a pipe specialises the kernel for the
+ * expression trees (precompiled table for the README shapes, NVRTC for everything else).
+ * ------------------------------------------------------------------------------------------- */
+#define FQ_MAX_COLS 8
+#define FQ_MAX_EXPRS 8
+
+enum { FQ_PIPE_PROJECT = 0, FQ_PIPE_AGGREGATE = 1 };
+
+typedef struct fq_pipe_desc {
+  int32_t n_cols;                   /* input schema */
+  fq_dtype col_dtypes[FQ_MAX_COLS];
+  int32_t generated;                /* specialise for fq_source.generated (column 0 = UInt64 numbers) */
+  const fq_expr_node *nodes;
+  int32_t n_nodes;
+  int32_t predicate;                /* root of the WHERE predicate (transform_filter.rs:38-55) or -1 */
+  int32_t kind;                     /* FQ_PIPE_PROJECT (transform_projection.rs:45-56) or FQ_PIPE_AGGREGATE
+                                       (transform_aggregate_partial.rs:50-78) */
+  int32_t n_exprs;
+  int32_t exprs[FQ_MAX_EXPRS];      /* roots of the select expressions */
+} fq_pipe_desc;
+
+typedef struct fq_pipe fq_pipe;
+
+fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out);
+void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe);
+/* 1 if the kernel came from the library's precompiled table, 0 if NVRTC built it */
+int32_t fq_pipe_is_precompiled(const fq_pipe *pipe);
+/* generated CUDA source of the specialised part (diagnostics / DESIGN.md) */
+const char *fq_pipe_source(const fq_pipe *pipe);
+/* Function::return_type of select expression i over the pipe's schema (functions/function.rs:28-38) */
+fq_status fq_pipe_expr_dtype(fq_ctx *ctx, const fq_pipe *pipe, int32_t i, fq_dtype *out);
+
+/* ---- aggregate pipes: Function::accumulate over a whole shard (function_aggregator.rs:57-100) ----
+ * The device keeps one running state per Aggregator leaf.  FQ_RUN_ACCUMULATE folds this launch into
+ * the running state (successive blocks of one partition); without it the state restarts from Null.
+ * FQ_RUN_BLOCK_QUIRKS additionally tracks what the reference's 10 000-row block loop would have
+ * seen (an empty post-filter block poisons Sum) — reported by fetch, never applied silently. */
+enum { FQ_RUN_ACCUMULATE = 1, FQ_RUN_LIMIT_EARLY_EXIT = 2 };
+
+fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, uint32_t flags, void *stream);
+/* Waits for the last launch and returns, for each Aggregator leaf in node-index order, the state
+ * Function::accumulate_result would hold (function_aggregator.rs:102-104): Null if no launch folded
+ * any block, Type(None) for Sum/Min/Max over zero rows, else Type(Some(v)).  rows_selected is the
+ * post-filter row count.  A zero divisor anywhere in the scanned rows yields FQ_ERR_DIVIDE_BY_ZERO. */
+fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
+                                  uint64_t *rows_selected);
+/* node indexes of the Aggregator leaves, in the order fetch reports them */
+fq_status fq_pipe_aggregator_nodes(fq_ctx *ctx, const fq_pipe *pipe, int32_t *nodes, int32_t cap, int32_t *n);
+/* device address of the raw running state (8-byte slots: rows_selected, error bits, then one slot per
+ * leaf) for collectives that merge states on the device (ncclAllGather of 8*(2+n) bytes) */
+fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes);
+
+/* ---- projection pipes: filter_record_batch + projection (+ LimitStream) in one pass ----
+ * out_cols[i] receives select expression i for the rows that pass the predicate, in row order
+ * (arrow filter keeps order, transform_filter.rs:51-54).  At most min(limit, capacity) rows are
+ * written (limit < 0 = none; stream_limit.rs:28-48); rows_selected reports every matching row
+ * unless FQ_RUN_LIMIT_EARLY_EXIT let the scan stop once `limit` rows were found. */
+fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols,
+                                 uint64_t capacity, int64_t limit, uint32_t flags, void *stream);
+fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selected, uint64_t *rows_written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUSE_GPU_H */

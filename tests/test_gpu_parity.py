@@ -1,0 +1,430 @@
+"""Parity of the CUDA path (through the C ABI, libfuse_gpu.so) against the CPU oracle.
+
+Bit-exact for every integer / index result.  Floating-point sums are compared with a stated
+tolerance (the reduction order differs from the reference's sequential fold); float min/max and
+element-wise float arithmetic are exact.
+"""
+import numpy as np
+import pytest
+
+from fuse_query_b200 import cabi
+from oracle import binding as o
+
+pytestmark = pytest.mark.gpu
+
+NUM = "(col number)"
+README_AGGS = {
+    "sum": [f"(sum {NUM})"],
+    "max": [f"(max {NUM})"],
+    "max_plus_1": [f"(max (+ {NUM} (u64 1)))"],
+    "count": [f"(count {NUM})"],
+    "avg": [f"(/ (sum {NUM}) (count {NUM}))"],
+    "headline": [f"(/ (sum {NUM}) (count {NUM}))", f"(max {NUM})", f"(min {NUM})"],
+    "cfg2": [f"(max (+ {NUM} (u64 1)))", f"(min {NUM})", f"(count {NUM})"],
+}
+README_PRED = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))"
+README_PROJ = [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cabi.Context(0)  # raises (never skips) when the CUDA path is unavailable
+    yield c
+    c.close()
+
+
+def splitmix64(n, seed=0x5EED):
+    """Non-monotone full-range u64 test column."""
+    x = (np.arange(n, dtype=np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def leaf_sexprs(exprs):
+    """Aggregator leaves of the select expressions, in the order the device reports them (node order =
+    post-order of each expression in turn)."""
+    leaves = []
+
+    def walk(toks, i):
+        assert toks[i] == "("
+        head = toks[i + 1]
+        start = i
+        i += 2
+        if head in ("col",) or head in cabi._TY:
+            i += 1
+        elif head == "alias":
+            i += 1
+            i = walk(toks, i)
+        elif head in cabi.AGG:
+            depth, j = 0, start
+            while True:
+                depth += toks[j] == "("
+                depth -= toks[j] == ")"
+                j += 1
+                if depth == 0:
+                    break
+            leaves.append(" ".join(toks[start:j]).replace("( ", "(").replace(" )", ")"))
+            return j
+        else:
+            i = walk(toks, i)
+            i = walk(toks, i)
+        assert toks[i] == ")"
+        return i + 1
+
+    for e in exprs:
+        walk(cabi._tokens(e), 0)
+    return leaves
+
+
+def oracle_leaf_values(exprs, **kw):
+    # the C ABI scans exactly the rows it is given; the reference's NumbersStream tail quirk
+    # is a property of the source and is mirrored by the host-side NumbersStream, not by the kernels
+    kw.setdefault("tail_quirk", False)
+    out = []
+    for leaf in leaf_sexprs(exprs):
+        r = o.run_query([leaf], is_aggregate=True, **kw)
+        out.append(r.columns[0].to_list()[0])
+    return out
+
+
+def gpu_leaf_values(pipe, src, **kw):
+    pipe.launch_aggregate(src, **kw)
+    states, rows = pipe.fetch_aggregate()
+    return [None if s is None else s[1] for s in states], rows
+
+
+# ---------------------------------------------------------------------------------------------
+# source
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("begin,n", [(0, 0), (0, 1), (7, 2), (5, 3), (10**12, 10001), (123, 1 << 20), (0, 1000003)])
+def test_numbers_fill(ctx, begin, n):
+    col = ctx.numbers(begin, n)
+    got = col.to_numpy()
+    assert np.array_equal(got, np.arange(begin, begin + n, dtype=np.uint64))
+    col.free()
+
+
+def test_numbers_fill_unaligned_offset(ctx):
+    col = ctx.column(cabi.U64, 1001)
+    ctx.check(cabi.lib().fq_numbers_fill(ctx._h, col._h, 1, 50, 1000, None))
+    assert np.array_equal(col.to_numpy()[1:], np.arange(50, 1050, dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# aggregates: the README queries (BASELINE configs[0], [1]) against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("generated", [False, True], ids=["materialised", "generated"])
+@pytest.mark.parametrize("name", list(README_AGGS))
+def test_readme_aggregates_10m(ctx, name, generated):
+    n = 10_000_000
+    exprs = README_AGGS[name]
+    pipe = ctx.pipe(exprs, aggregate=True, generated=generated)
+    assert pipe.precompiled, "README shapes must come from the precompiled table"
+    col = None if generated else ctx.numbers(0, n)
+    src = cabi.make_source([] if generated else [col], n, generated=generated, begin=0)
+    got, rows = gpu_leaf_values(pipe, src)
+    assert rows == n
+    assert got == oracle_leaf_values(exprs, total=n, worker_threads=8, use_threads=True)
+    pipe.destroy()
+    if col:
+        col.free()
+
+
+def test_config0_sum_10m_known_answer(ctx):
+    n = 10_000_000
+    pipe = ctx.pipe(README_AGGS["sum"], aggregate=True)
+    col = ctx.numbers(0, n)
+    got, _ = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    assert got == [49999995000000]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 511, 2048, 2049, 4097, 65537, 1_000_003])
+def test_aggregate_ragged_sizes(ctx, n):
+    exprs = README_AGGS["headline"] + [f"(count {NUM})"]
+    data = splitmix64(n)
+    col = ctx.from_numpy(data)
+    pipe = ctx.pipe(exprs, aggregate=True)
+    got, rows = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    assert rows == n
+    if n == 0:
+        # arrow sum/min/max over an empty array is None; count is 0 (data_array_aggregate.rs:103-114)
+        assert got == [None, 0, None, None, 0]
+    else:
+        s = int(data.sum(dtype=np.uint64))
+        assert got == [s, n, int(data.max()), int(data.min()), n]
+        assert got == oracle_leaf_values(exprs, table={"number": o.from_numpy(data)}, worker_threads=8)
+
+
+def test_state_is_null_before_any_launch(ctx):
+    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True)
+    states, rows = pipe.fetch_aggregate()
+    assert states == [None, None, None, None] and rows == 0  # AggregatorFunction state starts Null
+
+
+def test_accumulate_across_blocks_equals_one_launch(ctx):
+    """Successive reference blocks fold into one running state (function_aggregator.rs:57-100)."""
+    n = 300_007
+    data = splitmix64(n, seed=7)
+    col = ctx.from_numpy(data)
+    exprs = [f"(sum (* {NUM} (u64 3)))", f"(min {NUM})", f"(max (/ {NUM} (u64 7)))", f"(count {NUM})"]
+    pipe = ctx.pipe(exprs, aggregate=True)
+    one, _ = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    bounds = [0, 10_000, 10_001, 150_000, n]
+    for k in range(len(bounds) - 1):
+        part = col.slice(bounds[k], bounds[k + 1] - bounds[k]) if bounds[k] % 2 == 0 else None
+        if part is None:  # odd offsets break 16-byte alignment: re-upload that block
+            part = ctx.from_numpy(data[bounds[k]:bounds[k + 1]])
+        pipe.launch_aggregate(cabi.make_source([part], bounds[k + 1] - bounds[k]), accumulate=k > 0)
+    states, rows = pipe.fetch_aggregate()
+    assert rows == n
+    assert [s[1] for s in states] == one
+
+
+def test_u64_sum_wraps_like_the_reference(ctx):
+    """the sum over 10^10 rows exceeds 2^64 and wraps; checked here on a small column of huge values."""
+    data = np.full(1000, (1 << 63) + 12345, dtype=np.uint64)
+    col = ctx.from_numpy(data)
+    pipe = ctx.pipe([f"(sum {NUM})"], aggregate=True)
+    got, _ = gpu_leaf_values(pipe, cabi.make_source([col], len(data)))
+    assert got == [(1000 * ((1 << 63) + 12345)) % (1 << 64)]
+    assert got == oracle_leaf_values([f"(sum {NUM})"], table={"number": o.from_numpy(data)})
+
+
+# ---------------------------------------------------------------------------------------------
+# expression trees through NVRTC: arithmetic / comparison / logic over random data
+# ---------------------------------------------------------------------------------------------
+JIT_AGG_CASES = [
+    [f"(sum (+ (* {NUM} {NUM}) (u64 17)))", f"(max (- {NUM} (u64 5)))"],
+    [f"(min (/ (u64 1000000007) (+ (/ {NUM} (u64 4611686018427387904)) (u64 1))))"],
+    [f"(sum (/ {NUM} (u64 3)))", f"(count (+ {NUM} (u64 1)))", f"(max (* (/ {NUM} (u64 1000)) (u64 999)))"],
+]
+
+
+@pytest.mark.parametrize("exprs", JIT_AGG_CASES)
+def test_jit_aggregates_match_oracle(ctx, exprs):
+    n = 200_003
+    data = splitmix64(n, seed=11)
+    col = ctx.from_numpy(data)
+    pipe = ctx.pipe(exprs, aggregate=True)
+    assert not pipe.precompiled
+    got, _ = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    assert got == oracle_leaf_values(exprs, table={"number": o.from_numpy(data)}, worker_threads=8)
+
+
+def test_filtered_aggregate_matches_oracle(ctx):
+    n = 123_457
+    data = splitmix64(n, seed=3) >> np.uint64(40)
+    col = ctx.from_numpy(data)
+    pred = f"(and (> {NUM} (u64 1000)) (<= (/ {NUM} (u64 2)) (u64 4000000)))"
+    exprs = [f"(min {NUM})", f"(max {NUM})", f"(count {NUM})"]
+    pipe = ctx.pipe(exprs, predicate=pred, aggregate=True)
+    got, rows = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    mask = (data > 1000) & ((data // 2) <= 4000000)
+    assert rows == int(mask.sum())
+    assert got == [int(data[mask].min()), int(data[mask].max()), rows]
+    # min/max/count survive fully-filtered blocks in the reference (SURVEY F8 only poisons Sum)
+    assert got == oracle_leaf_values(exprs, table={"number": o.from_numpy(data)}, predicate=pred, worker_threads=8)
+
+
+def test_divide_by_zero_is_an_error(ctx):
+    data = np.array([5, 4, 0, 2], dtype=np.uint64)
+    col = ctx.from_numpy(data)
+    pipe = ctx.pipe([f"(sum (/ (u64 100) {NUM}))"], aggregate=True)
+    pipe.launch_aggregate(cabi.make_source([col], 4))
+    with pytest.raises(cabi.FuseGpuError) as ei:
+        pipe.fetch_aggregate()
+    assert ei.value.status == cabi.ERR_DIVIDE_BY_ZERO
+    with pytest.raises(o.OracleError) as oi:
+        o.run_query([f"(sum (/ (u64 100) {NUM}))"], table={"number": o.from_numpy(data)}, is_aggregate=True)
+    assert str(ei.value) == str(oi.value) == "Internal Error: Divide by zero error"
+
+
+def test_type_errors_reproduce_reference_text(ctx):
+    with pytest.raises(cabi.FuseGpuError) as ei:
+        ctx.pipe([f"(sum (and {NUM} {NUM}))"], aggregate=True)
+    with pytest.raises(o.OracleError) as oi:
+        o.run_query([f"(sum (and {NUM} {NUM}))"], total=8, is_aggregate=True)
+    assert str(ei.value) == str(oi.value)
+    with pytest.raises(cabi.FuseGpuError) as ei:
+        ctx.pipe([NUM], predicate=f"(+ {NUM} (u64 1))")
+    assert str(ei.value) == "Internal Error: cannot downcast to boolean array"
+
+
+MIXED = {
+    "a": (cabi.I64, np.int64), "b": (cabi.I32, np.int32), "c": (cabi.F64, np.float64), "d": (cabi.U16, np.uint16),
+}
+
+
+def mixed_table(n, seed=5):
+    rng = np.random.default_rng(seed)
+    return {
+        "a": rng.integers(-10**12, 10**12, n, dtype=np.int64),
+        "b": rng.integers(-50000, 50000, n, dtype=np.int32),
+        "c": rng.normal(0, 1000, n),
+        "d": rng.integers(1, 60000, n, dtype=np.uint16),
+    }
+
+
+def test_mixed_type_columns_and_coercion(ctx):
+    """Int64/Int32/Float64/UInt16 columns: coercion lattice of data_type.rs:27-87, integer lanes exact,
+    float sum within 1e-9 relative (reduction order)."""
+    n = 100_003
+    tbl = mixed_table(n)
+    names = list(tbl)
+    cols = [ctx.from_numpy(tbl[k]) for k in names]
+    dtypes = [MIXED[k][0] for k in names]
+    exprs = ["(sum (+ (col a) (col b)))", "(min (* (col b) (col d)))", "(max (- (col a) (col d)))", "(sum (col c))",
+             "(max (+ (col c) (col b)))", "(min (/ (col a) (col d)))", "(count (col d))"]
+    pred = "(< (col b) (col d))"
+    pipe = ctx.pipe(exprs, columns=names, dtypes=dtypes, predicate=pred, aggregate=True)
+    got, rows = gpu_leaf_values(pipe, cabi.make_source(cols, n))
+    want = oracle_leaf_values(exprs, table={k: o.from_numpy(v) for k, v in tbl.items()}, predicate=pred, worker_threads=1)
+    assert [pipe.expr_dtype(i) for i in range(len(exprs))] == [cabi.I64, cabi.I32, cabi.I64, cabi.F64, cabi.F64, cabi.I64, cabi.U64]
+    for i, (g, w) in enumerate(zip(got, want)):
+        if i == 3:
+            assert abs(g - w) <= 1e-9 * max(1.0, abs(w))  # float sum: stated tolerance
+        else:
+            assert g == w, (i, g, w)
+
+
+# ---------------------------------------------------------------------------------------------
+# filter -> projection -> limit
+# ---------------------------------------------------------------------------------------------
+def run_project(ctx, pipe, src, n_exprs, capacity, **kw):
+    outs = [ctx.column(pipe.expr_dtype(i), max(capacity, 1)) for i in range(n_exprs)]
+    pipe.launch_project(src, outs, capacity, **kw)
+    sel, written = pipe.fetch_project()
+    res = [c.to_numpy(written) for c in outs]
+    for c in outs:
+        c.free()
+    return sel, written, res
+
+
+@pytest.mark.parametrize("generated", [False, True], ids=["materialised", "generated"])
+def test_readme_filter_projection_limit(ctx, generated):
+    """BASELINE configs[2] at the README's own size (10^7 rows): rows (1,0),(2,0),(3,1); 66 rows match."""
+    n = 10_000_000
+    pipe = ctx.pipe(README_PROJ, predicate=README_PRED, generated=generated)
+    assert pipe.precompiled
+    col = None if generated else ctx.numbers(0, n)
+    src = cabi.make_source([] if generated else [col], n, generated=generated)
+    sel, written, (c1, c2) = run_project(ctx, pipe, src, 2, capacity=3, limit=3)
+    assert (sel, written) == (66, 3)
+    assert list(zip(c1.tolist(), c2.tolist())) == [(1, 0), (2, 0), (3, 1)]
+    want = o.run_query(README_PROJ, total=n, predicate=README_PRED, limit=3, worker_threads=8)
+    assert list(zip(c1.tolist(), c2.tolist())) == want.rows() and want.names == ["c1", "c2"]
+    # no limit: all 66 rows, in order
+    sel, written, (c1, c2) = run_project(ctx, pipe, src, 2, capacity=1000)
+    want = o.run_query(README_PROJ, total=n, predicate=README_PRED, worker_threads=8)
+    assert sel == written == 66 and list(zip(c1.tolist(), c2.tolist())) == want.rows()
+    # early exit gives the same rows
+    sel, written, (c1, c2) = run_project(ctx, pipe, src, 2, capacity=3, limit=3, early_exit=True)
+    assert written == 3 and sel >= 3 and list(zip(c1.tolist(), c2.tolist())) == [(1, 0), (2, 0), (3, 1)]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 2047, 2048, 2049, 6145, 250_001])
+@pytest.mark.parametrize("limit", [-1, 0, 1, 1000])
+def test_compaction_is_order_preserving(ctx, n, limit):
+    """Dense, irregular selection (multiples of 3 of a shuffled column): arrow filter keeps row order."""
+    data = splitmix64(n, seed=21) >> np.uint64(8)
+    col = ctx.from_numpy(data)
+    pred = f"(= (* (/ {NUM} (u64 3)) (u64 3)) {NUM})"
+    exprs = [NUM, f"(+ (/ {NUM} (u64 3)) (u64 1))", f"(< {NUM} (u64 36028797018963968))"]
+    pipe = ctx.pipe(exprs, predicate=pred)
+    cap = max(n, 1)
+    sel, written, res = run_project(ctx, pipe, cabi.make_source([col], n), 3, capacity=cap, limit=limit)
+    mask = (data % 3) == 0
+    keep = data[mask]
+    assert sel == len(keep)
+    if limit >= 0:
+        keep = keep[:limit]
+    assert written == len(keep)
+    assert np.array_equal(res[0], keep)
+    assert np.array_equal(res[1], keep // 3 + 1)
+    assert np.array_equal(res[2].astype(bool), keep < (1 << 55))
+    want = o.run_query(exprs, table={"number": o.from_numpy(data)}, predicate=pred, limit=None if limit < 0 else limit,
+                       worker_threads=1, tail_quirk=False)
+    assert want.n_rows == written
+    assert np.array_equal(want.columns[0].values, res[0]) and np.array_equal(want.columns[1].values, res[1])
+
+
+def test_projection_without_filter(ctx):
+    n = 70_001
+    data = splitmix64(n, seed=2)
+    col = ctx.from_numpy(data)
+    exprs = [f"(+ {NUM} (u64 1))", f"(/ {NUM} (u64 2))", f"(>= {NUM} (u64 9223372036854775808))"]
+    pipe = ctx.pipe(exprs)
+    sel, written, res = run_project(ctx, pipe, cabi.make_source([col], n), 3, capacity=n)
+    assert sel == written == n
+    assert np.array_equal(res[0], data + np.uint64(1)) and np.array_equal(res[1], data // 2)
+    assert np.array_equal(res[2].astype(bool), data >= (1 << 63))
+    want = o.run_query(exprs, table={"number": o.from_numpy(data)}, worker_threads=1, tail_quirk=False)
+    assert np.array_equal(want.columns[0].values, res[0]) and np.array_equal(want.columns[1].values, res[1])
+    assert np.array_equal(want.columns[2].values, res[2])
+
+
+def test_capacity_truncates_but_counts_everything(ctx):
+    n = 50_000
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe([NUM], predicate=f"(> {NUM} (u64 9))")
+    sel, written, res = run_project(ctx, pipe, cabi.make_source([col], n), 1, capacity=100)
+    assert sel == n - 10 and written == 100
+    assert np.array_equal(res[0], np.arange(10, 110, dtype=np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes: closed-form known answers + size-independent properties
+# ---------------------------------------------------------------------------------------------
+def closed_form(n):
+    s = (n * (n - 1) // 2) % (1 << 64)
+    return {"sum": s, "count": n, "max": n - 1, "min": 0}
+
+
+@pytest.mark.parametrize("n", [10**9, 10**10], ids=["1e9", "1e10"])
+def test_baseline_sizes_generated(ctx, n):
+    exprs = README_AGGS["headline"] + README_AGGS["cfg2"]
+    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True, generated=True)
+    got, rows = gpu_leaf_values(pipe, cabi.make_source([], n, generated=True))
+    cf = closed_form(n)
+    assert rows == n and got == [cf["sum"], n, cf["max"], 0]
+    pipe2 = ctx.pipe(README_AGGS["cfg2"], aggregate=True, generated=True)
+    got, _ = gpu_leaf_values(pipe2, cabi.make_source([], n, generated=True))
+    assert got == [n, 0, n]
+    if n == 10**10:  # the u64 sum wraps, sum/count is integer division
+        assert cf["sum"] == 13106511847580896768 and cf["sum"] // n == 1310651184
+
+
+def test_baseline_1e9_materialised_and_split_invariance(ctx):
+    """configs[1]/[2] at full size on a materialised shard; the aggregate of the whole equals the fold of
+    8 partition launches (merge is associative + commutative on wrapping u64)."""
+    n = 10**9
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True)
+    whole, rows = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    cf = closed_form(n)
+    assert rows == n and whole == [cf["sum"], n, cf["max"], 0]
+    parts = o.generate_parts(n)
+    for k, (b, e) in enumerate(parts):
+        pipe.launch_aggregate(cabi.make_source([col.slice(b, e - b + 1)], e - b + 1), accumulate=k > 0)
+    states, rows = pipe.fetch_aggregate()
+    assert rows == n and [s[1] for s in states] == whole
+    # configs[2]: filter + projection + limit over 10^9 rows
+    p3 = ctx.pipe(README_PROJ, predicate=README_PRED)
+    sel, written, (c1, c2) = run_project(ctx, p3, cabi.make_source([col], n), 2, capacity=3, limit=3)
+    assert sel == 66 and list(zip(c1.tolist(), c2.tolist())) == [(1, 0), (2, 0), (3, 1)]
+    col.free()
+
+
+def test_baseline_1e10_materialised_headline(ctx):
+    """configs[3]: 80 GB shard resident in HBM; sum wraps to 13106511847580896768."""
+    n = 10**10
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True)
+    got, rows = gpu_leaf_values(pipe, cabi.make_source([col], n))
+    assert rows == n and got == [13106511847580896768, n, n - 1, 0]
+    assert got[0] // got[1] == 1310651184
+    col.free()
