@@ -18,6 +18,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 GEN = os.path.join(CSRC, "generated")
 LIB = os.path.join(PKG, "libfuse_gpu.so")
+HOST_SRC = ["host/datavalues.cc", "host/functions.cc", "host/planners.cc", "host/pipeline.cc", "bindings/py_host.cc"]
+HOST_HDR = ["host/fq_host.h", "host/host_internal.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -34,7 +36,13 @@ def _sources():
     files = [os.path.join(CSRC, f) for f in ("fuse_gpu.cu", "codegen.cc", "codegen.h", "aot_pipes.txt")]
     files += [os.path.join(CSRC, "kernels", "fq_skeleton.cuh"), os.path.join(CSRC, "tools", "aotgen.cc"),
               os.path.join(os.path.dirname(PKG), "include", "fuse_gpu.h"), os.path.abspath(__file__)]
+    files += [os.path.join(CSRC, f) for f in HOST_SRC + HOST_HDR]
     return files
+
+
+def host_module_path() -> str:
+    import sysconfig
+    return os.path.join(PKG, "_fuse_host" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
 def _digest() -> str:
@@ -49,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(GEN, exist_ok=True)
     stamp = os.path.join(GEN, "build.stamp")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and os.path.exists(LIB) and os.path.exists(host_module_path()) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     # (1) + (2) precompiled pipes through the library's own code generator
     aotgen = os.path.join(GEN, "aotgen")
@@ -79,6 +87,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cg = os.path.join(GEN, "codegen.o")
     _run(["g++", "-O2", "-std=c++17", "-fPIC", "-c", os.path.join(CSRC, "codegen.cc"), "-o", cg])
     _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [cg, "-ldl", "-Xlinker", "--no-undefined"])
+    # (5) the C++ host mirror of the reference's function / processor / planner surface + its pybind11 view;
+    #     it calls nothing but the C ABI of libfuse_gpu.so
+    import pybind11
+    import sysconfig
+    inc = ["-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"]]
+    hobjs = []
+    procs = []
+    for src in HOST_SRC:
+        obj = os.path.join(GEN, src.replace("/", "_") + ".o")
+        cmd = ["g++", "-O1" if "bindings" in src else "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-c", os.path.join(CSRC, src), "-o", obj] + inc
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        hobjs.append(obj)
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + out)
+            raise RuntimeError("build step failed: host mirror")
+    _run(["g++", "-shared", "-o", host_module_path()] + hobjs + ["-L" + PKG, "-l:libfuse_gpu.so", "-Wl,-rpath,$ORIGIN"])
     with open(stamp, "w") as f:
         f.write(digest)
     if verbose:

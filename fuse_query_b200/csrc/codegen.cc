@@ -107,7 +107,7 @@ struct Gen {
         if (n->column < 0 || n->column >= d.n_cols)
           return fail(FQ_ERR_INTERNAL, fmt("Internal Error: Invalid argument error: Unable to get field at index %d", n->column));
         fq_dtype t = col_dtype(n->column);
-        if (!is_numeric(t))
+        if (!is_numeric(t) && t != FQ_BOOL)
           return fail(FQ_ERR_UNSUPPORTED, fmt("Unsupported on the device path: column of type %s", dtype_name(t)));
         ty[i] = t;
         used_cols.insert(n->column);
@@ -331,7 +331,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   s += "  __device__ static __forceinline__ void load1(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
   for (int c : g.used_cols) {
     if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
-    else s += fmt("    r.c%d[0] = __ldg((const %s *)p.cols[%d] + row);\n", c, ctype(g.col_dtype(c)), c);
+    else s += fmt("    r.c%d[0] = fq_ld1<%s>(p.cols[%d], row);\n", c, ctype(g.col_dtype(c)), c);
   }
   s += "  }\n";
   s += "  __device__ static __forceinline__ void copy_row(Rows &dst, int v, const Rows &one) {\n";

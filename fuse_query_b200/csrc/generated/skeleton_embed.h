@@ -104,6 +104,10 @@ __device__ __forceinline__ fq_u64 fq_ld_cg(const fq_u64 *p) {
   return v;
 }
 
+// one value (scalar tails, ragged last tile)
+template <class T> __device__ __forceinline__ T fq_ld1(const void *base, fq_u64 row) { return __ldg((const T *)base + row); }
+template <> __device__ __forceinline__ bool fq_ld1<bool>(const void *base, fq_u64 row) { return __ldg((const fq_u8 *)base + row) != 0; }
+
 // Load V consecutive values of type T (V * sizeof(T) bytes, a multiple of 16 or a power of two below)
 template <class T, int V>
 __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u64 group) {
@@ -127,7 +131,7 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
     for (int k = 0; k < V; k++) dst[k] = u.t[k];
   } else {
 #pragma unroll
-    for (int k = 0; k < V; k++) dst[k] = __ldg((const T *)p + k);
+    for (int k = 0; k < V; k++) dst[k] = fq_ld1<T>(p, k);
   }
 }
 
@@ -156,15 +160,15 @@ FQ_TRAITS(double, double, 1, 1, -__longlong_as_double(0x7ff0000000000000ll), __l
 
 // wrapping integer add / sub / mul (arrow `add` etc. on integer lanes), plain IEEE for floats
 template <class T> __device__ __forceinline__ T fq_add(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a + b;
+  if constexpr (fq_traits<T>::is_float) retur)FQSK"
+R"FQSK(n a + b;
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a + (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_sub(T a, T b) {
   if constexpr (fq_traits<T>::is_float) return a - b;
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a - (U)b); }
 }
-)FQSK"
-R"FQSK(template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
+template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
   if constexpr (fq_traits<T>::is_float) return a * b;
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a * (U)b); }
 }
@@ -344,7 +348,8 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   }
   fq_block_reduce<Q>(acc, nsel, err, sm);
   if (threadIdx.x == 0) {
-    if (!Q::HAS_PRED) nsel = p.n_rows;
+)FQSK"
+R"FQSK(    if (!Q::HAS_PRED) nsel = p.n_rows;
     fq_u64 folded = 1, scanned = p.n_rows;
     if (p.accumulate) {
       typename Q::Acc o;
@@ -353,8 +358,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
       nsel += p.state[0];
       err |= (fq_u32)p.state[1];
       folded += p.state[2];
-      scanned +=)FQSK"
-R"FQSK( p.state[3];
+      scanned += p.state[3];
     }
     p.state[0] = nsel;
     p.state[1] = err;

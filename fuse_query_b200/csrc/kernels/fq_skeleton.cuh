@@ -103,6 +103,10 @@ __device__ __forceinline__ fq_u64 fq_ld_cg(const fq_u64 *p) {
   return v;
 }
 
+// one value (scalar tails, ragged last tile)
+template <class T> __device__ __forceinline__ T fq_ld1(const void *base, fq_u64 row) { return __ldg((const T *)base + row); }
+template <> __device__ __forceinline__ bool fq_ld1<bool>(const void *base, fq_u64 row) { return __ldg((const fq_u8 *)base + row) != 0; }
+
 // Load V consecutive values of type T (V * sizeof(T) bytes, a multiple of 16 or a power of two below)
 template <class T, int V>
 __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u64 group) {
@@ -126,7 +130,7 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
     for (int k = 0; k < V; k++) dst[k] = u.t[k];
   } else {
 #pragma unroll
-    for (int k = 0; k < V; k++) dst[k] = __ldg((const T *)p + k);
+    for (int k = 0; k < V; k++) dst[k] = fq_ld1<T>(p, k);
   }
 }
 

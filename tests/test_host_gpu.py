@@ -1,0 +1,311 @@
+"""The C++ host mirror (Function / DataBlock / IProcessor / Pipeline / executors) driving the CUDA path,
+written the way the reference's own tests are (src/functions/*_test.rs, src/transforms/*_test.rs,
+src/executors/*_test.rs) and checked against the reference's golden vectors and the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from fuse_query_b200 import _fuse_host as h
+from oracle import binding as o
+
+pytestmark = pytest.mark.gpu
+DT = h.DataType
+E = h.ExpressionPlan
+TAG = {"Null": 0, "Boolean": 1, "Int8": 2, "Int16": 3, "Int32": 4, "Int64": 5, "UInt8": 6, "UInt16": 7, "UInt32": 8, "UInt64": 9,
+       "Float32": 10, "Float64": 11, "Utf8": 12}
+NP = {"Boolean": np.bool_, "Int8": np.int8, "Int16": np.int16, "Int32": np.int32, "Int64": np.int64, "UInt8": np.uint8,
+      "UInt16": np.uint16, "UInt32": np.uint32, "UInt64": np.uint64, "Float32": np.float32, "Float64": np.float64}
+OPS = {"Add": h.ops.Add, "Sub": h.ops.Sub, "Mul": h.ops.Mul, "Div": h.ops.Div, "Eq": h.ops.Eq, "Lt": h.ops.Lt, "LtEq": h.ops.LtEq,
+       "Gt": h.ops.Gt, "GtEq": h.ops.GtEq, "And": h.ops.And, "Or": h.ops.Or, "Min": h.ops.Min, "Max": h.ops.Max, "Sum": h.ops.Sum,
+       "Count": h.ops.Count}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return h.GpuContext.create(0)
+
+
+def make_ctx(gpu, workers=0, **opts):
+    c = h.FuseQueryContext.create_ctx(workers, gpu)
+    for k, v in opts.items():
+        setattr(c.options, k, v)
+    return c
+
+
+def to_array(gpu, spec):
+    return h.DataArray.from_numpy(gpu, np.asarray(spec["values"], dtype=NP[spec["array"]]))
+
+
+def to_value(spec):
+    return h.DataValue(TAG[spec["value"]], spec["v"])
+
+
+def operand(gpu, spec):
+    return h.DataColumnarValue.Array(to_array(gpu, spec)) if "array" in spec else h.DataColumnarValue.Scalar(to_value(spec))
+
+
+def ident(c):
+    return f"{c['source'].split('/')[-1]}-{c['name']}"
+
+
+def has_utf8(case):
+    return any(isinstance(case.get(k), dict) and (case[k].get("array") == "Utf8" or case[k].get("value") == "Utf8")
+               for k in ("left", "right", "array"))
+
+
+# ---------------------------------------------------------------------------------------------
+# datavalues: the reference's table-driven vectors for array (op) array / scalar (data_array_*_test.rs)
+# ---------------------------------------------------------------------------------------------
+DV = golden("ref_datavalues.json")
+
+
+@pytest.mark.parametrize("case", [c for c in DV if c["kind"] in ("array_arithmetic", "array_comparison", "array_logic")], ids=ident)
+def test_data_array_ops(gpu, case):
+    if has_utf8(case) and not case["error"]:
+        pytest.skip("Utf8 arrays are outside the device path (SURVEY §8f rank 1)")
+    fn = {"array_arithmetic": h.data_array_arithmetic_op, "array_comparison": h.data_array_comparison_op,
+          "array_logic": h.data_array_logic_op}[case["kind"]]
+    if has_utf8(case):
+        # the reference's error text is still reproduced by the typing rules before anything reaches the device
+        with pytest.raises(h.FuseQueryError) as e:
+            h.numerical_coercion({"Add": "+", "Sub": "-", "Mul": "*", "Div": "/"}[case["op"]], TAG[case["left"]["array"]], TAG[case["right"]["array"]])
+        assert str(e.value) == case["error"]
+        return
+    got = fn(gpu, OPS[case["op"]], operand(gpu, case["left"]), operand(gpu, case["right"]))
+    exp = case["expect"]
+    assert h.data_type_name(got.data_type()) == exp["array"]
+    assert got.to_list() == np.asarray(exp["values"], dtype=NP[exp["array"]]).tolist()
+
+
+@pytest.mark.parametrize("case", [c for c in DV if c["kind"] == "array_aggregate" and not has_utf8(c)], ids=ident)
+def test_data_array_aggregate(gpu, case):
+    got = h.data_array_aggregate_op(gpu, OPS[case["op"]], to_array(gpu, case["array"]))
+    assert got == to_value(case["expect"])
+
+
+# ---------------------------------------------------------------------------------------------
+# functions: function_{arithmetic,comparison,logic,aggregator}_test.rs
+# ---------------------------------------------------------------------------------------------
+FN = golden("ref_functions.json")
+
+
+def fn_from_sexpr(s):
+    """s-expression (as recorded by the extractor) -> Function via the reference's try_create constructors."""
+    toks = s.replace("(", " ( ").replace(")", " ) ").split()
+
+    def parse(i):
+        assert toks[i] == "("
+        head = toks[i + 1]
+        i += 2
+        if head == "col":
+            return h.FieldFunction.try_create(toks[i]), i + 2
+        ty = {"i8": DT.Int8, "i16": DT.Int16, "i32": DT.Int32, "i64": DT.Int64, "u8": DT.UInt8, "u16": DT.UInt16, "u32": DT.UInt32,
+              "u64": DT.UInt64, "f32": DT.Float32, "f64": DT.Float64}
+        if head in ty:
+            v = float(toks[i]) if head[0] == "f" else int(toks[i])
+            return h.ConstantFunction.try_create(h.DataValue(ty[head], v)), i + 2
+        args = []
+        while toks[i] != ")":
+            a, i = parse(i)
+            args.append(a)
+        return h.ScalarFunctionFactory.get(head, args), i + 1
+
+    return parse(0)[0]
+
+
+def block_of(gpu, spec):
+    cols = [to_array(gpu, c) for c in spec["columns"]]
+    schema = h.DataSchema([h.DataField(n, TAG[c["array"]], False) for n, c in zip(spec["names"], spec["columns"])])
+    return h.DataBlock.create(schema, cols)
+
+
+@pytest.mark.parametrize("case", [c for c in FN if c["kind"] == "function_eval"], ids=ident)
+def test_function_eval(gpu, case):
+    func = fn_from_sexpr(case["sexpr"])
+    block = block_of(gpu, case["block"])
+    assert str(func) == case["display"]                       # Display check
+    assert func.nullable(block.schema()) == case["nullable"]  # Nullable check
+    v = func.eval(gpu, block)
+    assert func.return_type(block.schema()) == v.data_type()  # Type check
+    assert h.data_type_name(v.data_type()) == case["expect"]["array"]
+    assert v.to_array(gpu, 0).to_list() == case["expect"]["values"]
+
+
+@pytest.mark.parametrize("case", [c for c in FN if c["kind"] == "function_aggregate"], ids=ident)
+def test_aggregator_function(gpu, case):
+    """function_aggregator_test.rs:168-188: accumulate x evals, accumulate x (evals-1), merge both states."""
+    proto = fn_from_sexpr(case["sexpr"])
+    block = block_of(gpu, case["block"])
+    func1 = proto.clone()
+    for _ in range(case["evals"]):
+        func1.accumulate(gpu, block)
+    state1 = func1.accumulate_result()
+    func2 = proto.clone()
+    for _ in range(1, case["evals"]):
+        func2.accumulate(gpu, block)
+    state2 = func2.accumulate_result()
+    final_func = proto.clone()
+    final_func.set_depth(0)
+    final_func.merge_state(state1)
+    final_func.merge_state(state2)
+    assert final_func.merge_result() == to_value(case["expect"])
+
+
+def test_function_errors_carry_reference_text(gpu):
+    block = block_of(gpu, {"names": ["a"], "columns": [{"array": "UInt64", "values": [4, 0, 2]}]})
+    div = h.ArithmeticFunction.try_create(h.ops.Div, [h.ConstantFunction.try_create(h.DataValue(DT.UInt64, 8)), h.FieldFunction.try_create("a")])
+    with pytest.raises(h.FuseQueryError) as e:
+        div.eval(gpu, block)
+    assert str(e.value) == "Internal Error: Divide by zero error"
+    with pytest.raises(h.FuseQueryError) as e:
+        h.FieldFunction.try_create("a").accumulate_result()
+    assert str(e.value) == "Internal Error: Unsupported aggregate operation for function field"
+    with pytest.raises(h.FuseQueryError) as e:
+        h.ScalarFunctionFactory.get("avg", [h.FieldFunction.try_create("a")])
+    assert str(e.value) == "Internal Error: Unsupported Function: avg"
+    with pytest.raises(h.FuseQueryError) as e:
+        h.FieldFunction.try_create("zz").eval(gpu, block)
+    assert "Unable to get field named \"zz\"" in str(e.value)
+
+
+# ---------------------------------------------------------------------------------------------
+# transforms / pipeline: transform_*_test.rs, processor_merge_test.rs (testdata/number.rs fixtures)
+# ---------------------------------------------------------------------------------------------
+def number_source_transform_for_test(ctx, numbers):
+    """testdata/number.rs:53-70."""
+    table = ctx.get_table("system", "numbers_mt")
+    plan = h.Planner().build_from_sql(ctx, f"select number from system.numbers_mt({numbers})").children_to_plans()[0]
+    return h.SourceTransform.try_create(ctx, "system", "numbers_mt", plan.partitions), table.schema()
+
+
+def rows_of(blocks):
+    out = []
+    for b in blocks:
+        cols = [b.column(i).to_list() for i in range(b.num_columns())]
+        out += list(zip(*cols)) if cols else []
+    return out
+
+
+@pytest.mark.parametrize("fuse_blocks", [0, 10000], ids=["whole-partition-blocks", "reference-10000-row-blocks"])
+def test_transform_aggregate(gpu, fuse_blocks):
+    """transform_aggregate_test.rs:19-57: sum(number)+2 over numbers_mt(16) through Partial -> Merge -> Final = 122."""
+    ctx = make_ctx(gpu, 0, fuse=False, block_rows=fuse_blocks)
+    pipeline = h.Pipeline.create()
+    a, schema = number_source_transform_for_test(ctx, 16)
+    pipeline.add_source(a)
+    plan = h.PlanBuilder.create(schema).aggregate([], [E.BinaryExpression(E.Function("sum", [E.Field("number")]), "+", E.Constant(h.DataValue(DT.UInt64, 2)))]).build()
+    pipeline.add_simple_transform(lambda: h.AggregatePartialTransform.try_create(ctx, plan.schema(), plan.expr))
+    pipeline.merge_processor()
+    pipeline.add_simple_transform(lambda: h.AggregateFinalTransform.try_create(ctx, plan.schema(), plan.expr))
+    blocks = pipeline.execute().collect()
+    assert [b.column(0).to_list() for b in blocks if b.num_rows() > 0] == [[122]]
+    assert blocks[0].column(0).data_type() == DT.UInt64
+
+
+def test_transform_filter(gpu):
+    """transform_filter_test.rs:19-42: number = 1 over numbers_mt(8) -> [1]."""
+    ctx = make_ctx(gpu, 0, fuse=False)
+    pipeline = h.Pipeline.create()
+    a, schema = number_source_transform_for_test(ctx, 8)
+    pipeline.add_source(a)
+    pred = E.BinaryExpression(E.Field("number"), "=", E.Constant(h.DataValue(DT.Int64, 1)))   # constant(1): i64 literal in the Rust test
+    pipeline.add_simple_transform(lambda: h.FilterTransform.try_create(ctx, pred))
+    pipeline.merge_processor()
+    blocks = pipeline.execute().collect()
+    assert [b.column(0).to_list() for b in blocks if b.num_rows() > 0] == [[1]]
+
+
+def test_transform_limit_and_source(gpu):
+    """transform_limit_test.rs: limit 2 -> 2 rows; transform_source_test.rs: two numbers_mt(8) sources -> 16 rows;
+    processor_merge_test.rs:17-26: first block of numbers_mt(16) is [0, 1]."""
+    ctx = make_ctx(gpu, 0, fuse=False)
+    pipeline = h.Pipeline.create()
+    pipeline.add_source(number_source_transform_for_test(ctx, 8)[0])
+    pipeline.merge_processor()
+    pipeline.add_simple_transform(lambda: h.LimitTransform.try_create(2))
+    assert sum(b.num_rows() for b in pipeline.execute().collect()) == 2
+    p2 = h.Pipeline.create()
+    p2.add_source(number_source_transform_for_test(ctx, 8)[0])
+    p2.add_source(number_source_transform_for_test(ctx, 8)[0])
+    p2.merge_processor()
+    assert sum(b.num_rows() for b in p2.execute().collect()) == 16
+    ctx16 = make_ctx(gpu, 0, fuse=False, block_rows=10000)   # reference block split: one block per 2-row partition
+    plan = h.Planner().build_from_sql(ctx16, "select number from system.numbers_mt(16)").children_to_plans()[0]
+    p3 = h.Pipeline.create()
+    for part in plan.partitions:
+        p3.add_source(h.SourceTransform.try_create(ctx16, "system", "numbers_mt", [part]))
+    p3.merge_processor()
+    assert p3.execute().next().column(0).to_list() == [0, 1]
+
+
+# ---------------------------------------------------------------------------------------------
+# executors: SQL in, blocks out — fused and reference-shaped pipelines against the oracle
+# ---------------------------------------------------------------------------------------------
+NUM = "(col number)"
+QUERIES = [
+    # (sql, oracle exprs, predicate, is_aggregate, limit)
+    ("select sum(number) from system.numbers_mt({n})", [f"(sum {NUM})"], None, True, None),
+    ("select max(number+1), min(number), count(number) from system.numbers_mt({n})",
+     [f"(max (+ {NUM} (u64 1)))", f"(min {NUM})", f"(count {NUM})"], None, True, None),
+    ("select sum(number)/count(number), max(number), min(number) from system.numbers_mt({n})",
+     [f"(/ (sum {NUM}) (count {NUM}))", f"(max {NUM})", f"(min {NUM})"], None, True, None),
+    ("select sum(number+1)+2 as sumx from system.numbers_mt({n})", [f"(alias sumx (+ (sum (+ {NUM} (u64 1))) (u64 2)))"], None, True, None),
+    ("select (number+1) as c1, number/2 as c2 from system.numbers_mt({n}) where (c1+c2+1) < 100 limit 3",
+     [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"],
+     f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))", False, 3),
+    ("select number*3 as t, number from system.numbers_mt({n}) where number*3 >= 30 and number < 1000 limit 50",
+     [f"(alias t (* {NUM} (u64 3)))", NUM], f"(and (>= (* {NUM} (u64 3)) (u64 30)) (< {NUM} (u64 1000)))", False, 50),
+    ("select min(number), max(number), count(number) from system.numbers_mt({n}) where number/7*7 = number",
+     [f"(min {NUM})", f"(max {NUM})", f"(count {NUM})"], f"(= (* (/ {NUM} (u64 7)) (u64 7)) {NUM})", True, None),
+]
+
+
+@pytest.mark.parametrize("mode", ["fused", "fused-generated", "reference-shaped"])
+@pytest.mark.parametrize("n", [16, 80000, 10_000_000])
+@pytest.mark.parametrize("q", QUERIES, ids=[q[0][:48] for q in QUERIES])
+def test_select_executor_matches_oracle(gpu, q, n, mode):
+    sql, exprs, pred, is_agg, limit = q
+    if mode == "reference-shaped" and n > 80000:
+        pytest.skip("one kernel per 10 000-row block per node: covered at the smaller sizes")
+    workers = {"fused": 1, "fused-generated": 0, "reference-shaped": 0}[mode]
+    ctx = make_ctx(gpu, workers, fuse=mode != "reference-shaped", generated=mode == "fused-generated",
+                   block_rows=10000 if mode == "reference-shaped" else 0)
+    blocks = h.execute_sql(ctx, sql.format(n=n))
+    want = o.run_query(exprs, total=n, predicate=pred, is_aggregate=is_agg, limit=limit, worker_threads=workers, use_threads=True)
+    assert rows_of(blocks) == want.rows()
+    assert blocks[0].schema().names() == want.names
+    assert [h.data_type_name(t) for t in blocks[0].schema().types()] == [o.DTYPE_NAMES[c.dtype] for c in want.columns]
+
+
+@pytest.mark.parametrize("n", [80008, 1_000_000, 12345, 10001])
+def test_numbers_stream_tail_quirk_is_reproduced(gpu, n):
+    """SURVEY F7 (numbers_stream.rs:44-46): numbers_mt(80008) emits 16 rows per... the reference drops rows when a
+    partition is >= 10 000 rows and not a multiple of 10 000.  The source mirror reproduces it by default."""
+    sql = f"select count(number), sum(number), max(number) from system.numbers_mt({n})"
+    exprs = [f"(count {NUM})", f"(sum {NUM})", f"(max {NUM})"]
+    want = o.run_query(exprs, total=n, is_aggregate=True, worker_threads=0)
+    for opts in (dict(fuse=True), dict(fuse=True, generated=True), dict(fuse=False, block_rows=10000)):
+        assert rows_of(h.execute_sql(make_ctx(gpu, 0, **opts), sql)) == want.rows()
+    if n == 80008:
+        assert want.rows()[0][0] == 16   # 8 partitions x 2 rows survive
+    fixed = o.run_query(exprs, total=n, is_aggregate=True, worker_threads=0, tail_quirk=False)
+    assert rows_of(h.execute_sql(make_ctx(gpu, 1, tail_quirk=False), sql)) == fixed.rows() == [(n, n * (n - 1) // 2, n - 1)]
+
+
+def test_explain_executor(gpu):
+    ctx = make_ctx(gpu, 0, fuse=False)
+    blocks = h.execute_sql(ctx, "explain select (number+1) as c1, number/2 as c2 from system.numbers_mt(10000000) where (c1+c2+1) < 100 limit 3")
+    text = blocks[0].column(0).to_list()
+    assert blocks[0].schema().names() == ["explain"] and len(text) == 2
+    assert text[0].startswith("└─ Limit: 3\n  └─ Projection: (number + 1) as c1, (number / 2) as c2\n    └─ Filter: ((((number + 1) + (number / 2)) + 1) < 100)")
+    assert "SourceTransform × 8 processors" in text[1]
+
+
+def test_readme_headline_query_10b_through_sql(gpu):
+    """BASELINE configs[3] end to end through plan_select/executor_select, generated and materialised shards."""
+    sql = "select sum(number)/count(number), max(number), min(number) from system.numbers_mt(10000000000)"
+    for opts in (dict(generated=True), dict(generated=False)):
+        blocks = h.execute_sql(make_ctx(gpu, 1, **opts), sql)
+        assert rows_of(blocks) == [(1310651184, 9999999999, 0)]
+        assert blocks[0].schema().names() == ["Sum(number) / Count(number)", "Max(number)", "Min(number)"]
+    h.numbers_cache_clear()

@@ -1,0 +1,155 @@
+"""Host-side logic of the C++ mirror that needs no GPU: SQL -> plan -> optimizer -> pipeline shape, checked
+against the reference's golden EXPLAIN strings (tests/golden/ref_strings.json, README.md:100-117), and the
+scalar state plumbing (DataValue JSON wire format, scalar merges) against the reference's vectors."""
+import json
+
+import pytest
+
+from conftest import golden
+from fuse_query_b200 import _fuse_host as h
+
+DT = h.DataType
+TAG = {"Null": 0, "Boolean": 1, "Int8": 2, "Int16": 3, "Int32": 4, "Int64": 5, "UInt8": 6, "UInt16": 7, "UInt32": 8, "UInt64": 9,
+       "Float32": 10, "Float64": 11, "Utf8": 12}
+OPS = {"Add": h.ops.Add, "Sub": h.ops.Sub, "Mul": h.ops.Mul, "Div": h.ops.Div, "Min": h.ops.Min, "Max": h.ops.Max, "Sum": h.ops.Sum,
+       "Count": h.ops.Count}
+
+
+@pytest.fixture()
+def ctx():
+    # FuseQueryContext::create_ctx(0, ...) as in the reference tests: 8 source pipes; no device bound
+    c = h.FuseQueryContext.create_ctx(0)
+    c.options.fuse = False   # reference-shaped pipeline (one processor per plan node)
+    return c
+
+
+STRINGS = golden("ref_strings.json")
+
+
+@pytest.mark.parametrize("case", [c for c in STRINGS if c["sql"]], ids=lambda c: c["source"])
+def test_reference_golden_plan_and_pipeline_strings(ctx, case):
+    plan = h.Planner().build_from_sql(ctx, case["sql"])
+    if case["optimized"]:
+        plan = h.FilterPushDownOptimizer.create().optimize(plan)
+    if case["pipeline"]:
+        assert str(h.PipelineBuilder.create(ctx, plan).build()) == case["expect"]
+    else:
+        assert str(plan) == case["expect"]
+
+
+def test_plan_filter_golden(ctx):
+    """plan_filter_test.rs:18-21 builds the plan programmatically: project(field number) over filter(number = 1)."""
+    case = [c for c in STRINGS if "plan_filter_test" in c["source"]][0]
+    src = h.Planner().build_from_sql(ctx, "select number from system.numbers_mt").children_to_plans()[0]
+    E = h.ExpressionPlan
+    plan = (h.PlanBuilder.from_plan(src).filter(E.BinaryExpression(E.Field("number"), "=", E.Constant(h.DataValue(DT.Int64, 1))))
+            .project([E.Field("number")]).build())
+    assert str(plan) == case["expect"]
+
+
+README_SQL = "select (number+1) as c1, number/2 as c2 from system.numbers_mt(10000000) where (c1+c2+1) < 100 limit 3"
+
+
+def test_readme_explain(ctx):
+    """README.md:100-117."""
+    plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, "explain " + README_SQL))
+    assert plan.name() == "ExplainPlan"
+    assert str(plan) == ("└─ Limit: 3\n  └─ Projection: (number + 1) as c1, (number / 2) as c2\n"
+                         "    └─ Filter: ((((number + 1) + (number / 2)) + 1) < 100)\n"
+                         "      └─ ReadDataSource: scan parts [8](Read from system.numbers_mt table)")
+    pipeline = h.PipelineBuilder.create(ctx, plan.input).build()
+    assert str(pipeline) == ("\n  └─ LimitTransform × 1 processor\n    └─ Merge (LimitTransform × 8 processors) to (MergeProcessor × 1)\n"
+                             "      └─ LimitTransform × 8 processors\n        └─ ProjectionTransform × 8 processors\n"
+                             "          └─ FilterTransform × 8 processors\n            └─ SourceTransform × 8 processors")
+
+
+def test_fused_pipeline_shape():
+    c = h.FuseQueryContext.create_ctx(1)   # one worker: all 8 partitions in one source pipe (pipeline_builder.rs:75-84)
+    plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(c, README_SQL))
+    assert str(h.PipelineBuilder.create(c, plan).build()) == "\n  └─ GpuPipeTransform × 1 processor"
+    agg = h.Planner().build_from_sql(c, "select sum(number)/count(number), max(number), min(number) from system.numbers_mt(10000000000)")
+    assert str(h.PipelineBuilder.create(c, agg).build()) == ("\n  └─ AggregateFinalTransform × 1 processor\n    └─ GpuPipeTransform × 1 processor")
+    c.worker_threads = 0
+    assert str(h.PipelineBuilder.create(c, agg).build()) == (
+        "\n  └─ AggregateFinalTransform × 1 processor\n    └─ Merge (GpuPipeTransform × 8 processors) to (MergeProcessor × 1)\n"
+        "      └─ GpuPipeTransform × 8 processors")
+
+
+def test_generate_parts_and_read_plan(ctx):
+    names = [p.name for p in h.NumbersTable.generate_parts(10**10)]
+    assert names[0] == "10000000000-0-1249999999" and names[7] == "10000000000-8750000000-9999999999"
+    assert [p.name for p in h.NumbersTable.generate_parts(5)] == ["5-0-4"]
+    assert [p.name for p in h.NumbersTable.generate_parts(19)][-1] == "19-14-18"   # last part takes total % 8
+    plan = h.Planner().build_from_sql(ctx, "select number from system.numbers_mt")   # default 10 000 rows (numbers_table.rs:69)
+    assert plan.children_to_plans()[0].partitions[0].name == "10000-0-1249"
+
+
+def test_literal_typing_and_column_names(ctx):
+    """plan_parser.rs:223-238: non-negative integer -> UInt64, non-integer -> Float64; names are Debug of the function."""
+    plan = h.Planner().build_from_sql(ctx, "select sum(number)/count(number), max(number+1), number*2.5 x from system.numbers_mt(8)".replace(", number*2.5 x", ""))
+    assert plan.schema().names() == ["Sum(number) / Count(number)", "Max(number + 1)"]
+    assert plan.schema().types() == [DT.UInt64, DT.UInt64]
+    p2 = h.Planner().build_from_sql(ctx, "select number*2.5 as x, number+1 from system.numbers_mt(8)")
+    assert p2.schema().names() == ["x", "number + 1"] and p2.schema().types() == [DT.Float64, DT.UInt64]
+
+
+@pytest.mark.parametrize("sql,err", [
+    ("select number from system.nope", "Internal Error: Cannot find the table: nope"),
+    ("select number from nodb.numbers_mt", "Internal Error: Cannot find the database: nodb"),
+    ("select avg(number) from system.numbers_mt", "Internal Error: Unsupported Function: avg"),
+    ("select number from system.numbers_mt limit number", "Error during plan: Unexpected expression for LIMIT clause"),
+    ("select sum(number), number from system.numbers_mt", "Error during plan: Projection references non-aggregate values"),
+    ("select number from system.numbers_mt having number > 1", "Internal Error: HAVING is not implemented yet"),
+    ("select number from system.numbers_mt where number > -1", "Error during plan: Unsupported ExpressionPlan: - 1"),
+])
+def test_planner_errors(ctx, sql, err):
+    with pytest.raises(h.FuseQueryError) as e:
+        h.Planner().build_from_sql(ctx, sql)
+    assert str(e.value) == err
+
+
+def test_where_aggregate_rejected(ctx):
+    plan = h.Planner().build_from_sql(ctx, "select number from system.numbers_mt where sum(number) > 1")
+    with pytest.raises(h.FuseQueryError) as e:
+        h.PipelineBuilder.create(ctx, plan).build()
+    assert str(e.value) == "Internal Error: Aggregate function (sum([number]) > 1) is found in WHERE in query"
+
+
+# ---- scalar state plumbing against the reference's vectors ----
+def to_value(spec):
+    return h.DataValue(TAG[spec["value"]], spec["v"])
+
+
+@pytest.mark.parametrize("case", [c for c in golden("ref_datavalues.json") if c["kind"].startswith("value_")],
+                         ids=lambda c: f"{c['source'].split('/')[-1]}-{c['name']}")
+def test_data_value_ops(case):
+    fn = h.data_value_aggregate_op if case["kind"] == "value_aggregate" else h.data_value_arithmetic_op
+    try:
+        got = fn(OPS[case["op"]], to_value(case["left"]), to_value(case["right"]))
+    except h.FuseQueryError as e:
+        assert case["error"] and str(e) == case["error"]
+        return
+    assert got == to_value(case["expect"])
+
+
+def test_partial_state_wire_format():
+    """transform_aggregate_partial.rs:61-66: serde_json of DataValue::Struct."""
+    st = h.DataValue(DT.Struct, [h.DataValue(DT.UInt64, 4999999950000000), h.DataValue(DT.UInt64, 1250000000)])
+    js = st.to_json()
+    assert js == '{"Struct":[{"UInt64":4999999950000000},{"UInt64":1250000000}]}'
+    assert h.DataValue.from_json(js) == st
+    assert h.DataValue.Null().to_json() == '"Null"' and h.DataValue(DT.UInt64).to_json() == '{"UInt64":null}'
+    assert h.DataValue.from_json('{"Struct":["Null",{"Int64":-3},{"Float64":2.5}]}').value[1] == h.DataValue(DT.Int64, -3)
+    # byte-for-byte the oracle's format too
+    from oracle import binding as o
+    assert o.value_to_json(o.Value(o.STRUCT, (o.Value(o.U64, 4999999950000000), o.Value(o.U64, 1250000000)))) == js
+
+
+def test_merge_protocol_without_device():
+    """AggregateFinalTransform's merge is host logic (function_aggregator.rs:106-143): sum/count with depth indexing."""
+    E = h.ExpressionPlan
+    f = E.BinaryExpression(E.Function("sum", [E.Field("number")]), "/", E.Function("count", [E.Field("number")])).to_function()
+    assert str(f) == "Sum(number) / Count(number)"
+    for js in ('{"Struct":[{"UInt64":10},{"UInt64":4}]}', '{"Struct":[{"UInt64":60},{"UInt64":24}]}'):
+        f.merge_state(h.DataValue.from_json(js).value)
+    assert f.merge_result() == h.DataValue(DT.UInt64, 2)   # 70 / 28, integer division (function_aggregator_test.rs:118-140)
