@@ -126,7 +126,7 @@ def lib():
 
 
 # ---------------------------------------------------------------------------------------------
-# s-expression -> fq_expr_node[]  (same surface syntax as the oracle's, see oracle/fq_oracle.h)
+# s-expression -> fq_expr_node[]  (the test-side s-expression syntax: (col x) (u64 1) (+ a b) (sum a) (alias n a) ...)
 # ---------------------------------------------------------------------------------------------
 def _tokens(text: str) -> List[str]:
     return text.replace("(", " ( ").replace(")", " ) ").split()
