@@ -291,7 +291,34 @@ def run_ours(args):
                 per_query.setdefault(name, {})[mode] = {"ms": round(q_ms, 4), "rows_per_s": n / (q_ms * 1e-3),
                                                         "gb_per_s": (0 if g else 8) * n / (q_ms * 1e-3) / 1e9}
                 p.destroy()
+        # BASELINE configs[1] and [2] on the first 10^9 rows of the shard
+        n2 = min(n, 1_000_000_000)
+        for mode in ("materialised", "generated"):
+            g = mode == "generated"
+            if g is False and generated:
+                continue
+            s2 = cabi.make_source([] if g else [col], n2, generated=g, begin=begin)
+            p = ctx.pipe([f"(max (+ {NUM} (u64 1)))", f"(min {NUM})", f"(count {NUM})"], aggregate=True, generated=g)
+            per_query.setdefault("cfg1: max(number+1),min(number),count(number) @1e9", {})[mode] = time_launches(
+                torch, lambda: p.launch_aggregate(s2, stream=stream), n2, 0 if g else 8)
+            p.destroy()
+            pred = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))"
+            p = ctx.pipe([f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"], predicate=pred, generated=g)
+            outs = [ctx.column(cabi.U64, 3), ctx.column(cabi.U64, 3)]
+            for early in (False, True):
+                key = "cfg2: filter+projection+limit 3 @1e9" + (" (limit early exit)" if early else " (full scan)")
+                per_query.setdefault(key, {})[mode] = time_launches(
+                    torch, lambda: p.launch_project(s2, outs, 3, limit=3, early_exit=early, stream=stream), n2, 0 if g else 8)
+            sel, written = p.fetch_project()
+            assert written == 3 and outs[0].to_numpy(3).tolist() == [1, 2, 3] and outs[1].to_numpy(3).tolist() == [0, 0, 1]
+            p.destroy()
     barrier()
+    sql_e2e = None
+    if rank == 0 and world == 1 and not args.no_query_table:
+        if col is not None:
+            col.free()
+            col = None
+        sql_e2e = run_sql_e2e(local, total)
 
     if rank == 0:
         peak, which = peaks()
@@ -314,7 +341,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "fq_agg_kernel (fqk_*_agg_u4)", "kernel_ms": kernel_ms, "peak_source": which,
                          "algorithmic_bytes_per_launch": row_bytes * n},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "sql_e2e": sql_e2e,
         }
         if world == 1 and not args.no_cpu_baseline:
             rows = cpu_sample_rows()
@@ -325,6 +352,46 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_launches(torch, launch, rows, row_bytes, reps=3):
+    for _ in range(2):
+        launch()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        launch()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return {"ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3), "gb_per_s": row_bytes * rows / (ms * 1e-3) / 1e9}
+
+
+def run_sql_e2e(device, total):
+    """The call a user of the reference makes: SQL text in, result rows out (Planner -> Optimizer -> PipelineBuilder ->
+    SelectExecutor, mysql_handler.rs:52-75), wall clock including planning, kernel launches and the D2H of the result.
+    numbers_mt is a generator table: `generated` computes it in-kernel, `materialised` scans the shard resident in HBM
+    (filled on first use, like a table load; that first query is reported separately)."""
+    from fuse_query_b200 import _fuse_host as h
+    gpu = h.GpuContext.create(device)
+    sql = HEADLINE_SQL.replace("10000000000", str(total))
+    exp = expected(total)
+    out = {}
+    for mode in ("generated", "materialised"):
+        c = h.FuseQueryContext.create_ctx(1, gpu)
+        c.options.generated = mode == "generated"
+        t0 = time.time()
+        rows = [tuple(b.column(i).to_list()[0] for i in range(b.num_columns())) for b in h.execute_sql(c, sql)]
+        first = time.time() - t0
+        assert rows == [(exp["avg"], exp["max"], exp["min"])], rows
+        reps = 5
+        t0 = time.time()
+        for _ in range(reps):
+            h.execute_sql(c, sql)[0].column(0).to_list()
+        dt = (time.time() - t0) / reps
+        out[mode] = {"ms_per_query": 1e3 * dt, "rows_per_s": total / dt, "first_query_ms": 1e3 * first}
+    h.numbers_cache_clear()
+    return out
 
 
 def run_e2e(args, ctx, torch, dist, rank, world, local):

@@ -117,6 +117,37 @@ Driver g_drv;
 Nvrtc g_nvrtc;
 std::mutex g_mu;
 
+// Launch shapes.  Defaults are the macros the precompiled kernels were built with; FQ_TUNE_* environment
+// overrides (kernel tuning experiments only) force the NVRTC path so kernel and host agree.
+struct Shapes {
+  int agg_threads = FQ_AGG_THREADS, agg_min_blocks = FQ_AGG_MIN_BLOCKS, agg_min_blocks_u8 = FQ_AGG_MIN_BLOCKS_U8;
+  int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
+  int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
+  bool tuned = false;
+  Shapes() {
+    auto env = [&](const char *name, int *v) {
+      const char *e = getenv(name);
+      if (e && atoi(e) > 0) { *v = atoi(e); tuned = true; }
+    };
+    env("FQ_TUNE_AGG_THREADS", &agg_threads); env("FQ_TUNE_AGG_MIN_BLOCKS", &agg_min_blocks);
+    env("FQ_TUNE_AGG_MIN_BLOCKS_U8", &agg_min_blocks_u8);
+    env("FQ_TUNE_SEL_THREADS", &sel_threads); env("FQ_TUNE_SEL_MIN_BLOCKS", &sel_min_blocks); env("FQ_TUNE_SEL_UNROLL", &sel_unroll); env("FQ_TUNE_SEL_SEG", &sel_seg); env("FQ_TUNE_SEL_LOOK", &sel_look);
+    env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
+  }
+  std::string defines() const {
+    char b[768];
+    snprintf(b, sizeof b,
+             "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_SEL_THREADS %d\n"
+             "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
+             agg_threads, agg_min_blocks, agg_min_blocks_u8, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
+    return b;
+  }
+};
+const Shapes &shapes() {
+  static Shapes s;
+  return s;
+}
+
 struct Kernel {
   const void *aot = nullptr;   // host stub of a precompiled kernel (cudaLaunchKernel)
   CUfunction_ jit = nullptr;   // NVRTC-built (cuLaunchKernel)
@@ -193,7 +224,7 @@ __global__ void __launch_bounds__(256) fq_fill_numbers(fq_u64 *dst, fq_u64 begin
 fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m) {
   if (!g_nvrtc.load()) return set_err(FQ_ERR_CUDA, "NVRTC unavailable: %s", g_nvrtc.why.c_str());
   if (!g_drv.load()) return set_err(FQ_ERR_CUDA, "CUDA driver unavailable: %s", g_drv.why.c_str());
-  std::string src = std::string(fq_skeleton_src) + "\n" + gen.source;
+  std::string src = shapes().defines() + std::string(fq_skeleton_src) + "\n" + gen.source;
   nvrtcProgram_ prog = nullptr;
   int r = g_nvrtc.nvrtcCreateProgram(&prog, src.c_str(), ("fq_" + gen.tag + ".cu").c_str(), 0, nullptr, nullptr);
   if (r) return set_err(FQ_ERR_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.nvrtcGetErrorString(r));
@@ -429,7 +460,7 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       const std::string probe = "fqk_" + gen.tag + "_";
       for (int i = 0; i < fq_aot_count; i++)
         if (strncmp(fq_aot_table[i].name, probe.c_str(), probe.size()) == 0) mod.precompiled = true;
-      if (getenv("FQ_FORCE_JIT")) mod.precompiled = false;
+      if (getenv("FQ_FORCE_JIT") || shapes().tuned) mod.precompiled = false;
       if (!mod.precompiled) {
         std::lock_guard<std::mutex> lk2(g_mu);
         if (fq_status s2 = compile_jit(ctx, gen, &mod)) { delete pipe; return s2; }
@@ -441,12 +472,12 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     fq_status s2 = FQ_OK;
     const std::string base = "fqk_" + gen.tag;
     if (gen.kind == FQ_PIPE_AGGREGATE) {
-      s2 = resolve_kernel(m, base + "_agg_u4", FQ_AGG_THREADS, &pipe->k_agg_u4);
-      if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", FQ_AGG_THREADS, &pipe->k_agg_u8);
+      s2 = resolve_kernel(m, base + "_agg_u4", shapes().agg_threads, &pipe->k_agg_u4);
+      if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", shapes().agg_threads, &pipe->k_agg_u8);
     } else if (gen.has_pred) {
-      s2 = resolve_kernel(m, base + "_select", FQ_SEL_THREADS, &pipe->k_select);
+      s2 = resolve_kernel(m, base + "_select", shapes().sel_threads + 32, &pipe->k_select);   // worker warps + one scan warp
     } else {
-      s2 = resolve_kernel(m, base + "_map", FQ_MAP_THREADS, &pipe->k_map);
+      s2 = resolve_kernel(m, base + "_map", shapes().map_threads, &pipe->k_map);
     }
     if (s2) { delete pipe; return s2; }
   }
@@ -606,7 +637,11 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     pipe->skipped = true;
   } else if (pipe->gen.has_pred) {
     const Kernel &k = pipe->k_select;
-    const uint64_t tile_rows = (uint64_t)k.threads * FQ_SEL_UNROLL * pipe->gen.vec;
+    // work unit = segment of sel_seg tiles; p.n_tiles counts segments (one look-back descriptor each)
+    const int vec = pipe->gen.vec;
+    const int sel_u = shapes().sel_unroll * vec <= 32 ? shapes().sel_unroll : 32 / vec;              // fq_sel_shape<V>::U
+    const int sel_seg = shapes().sel_seg * sel_u * vec <= 64 ? shapes().sel_seg : 64 / (sel_u * vec);  // fq_sel_shape<V>::SEG
+    const uint64_t tile_rows = (uint64_t)(k.threads - 32) * sel_u * vec * sel_seg;
     p.n_tiles = (src->n_rows + tile_rows - 1) / tile_rows;
     if (p.n_tiles > pipe->tiles_cap) {
       cudaFree(pipe->d_tiles);
@@ -616,11 +651,13 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     }
     p.tile_status = (fq_u64 *)pipe->d_tiles;
     CUDA_TRY(cudaMemsetAsync(pipe->d_tiles, 0, sizeof(uint64_t) * p.n_tiles, (cudaStream_t)stream));
-    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, p.n_tiles));
+    static const int sel_bps_env = getenv("FQ_SEL_BLOCKS_PER_SM") ? atoi(getenv("FQ_SEL_BLOCKS_PER_SM")) : 0;
+    const int sel_bps = sel_bps_env > 0 ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   } else {
     const Kernel &k = pipe->k_map;
-    const uint64_t chunk_rows = (uint64_t)k.threads * FQ_MAP_UNROLL * pipe->gen.vec;
+    const uint64_t chunk_rows = (uint64_t)k.threads * shapes().map_unroll * pipe->gen.vec;
     const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;

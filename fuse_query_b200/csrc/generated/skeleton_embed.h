@@ -40,9 +40,11 @@ typedef signed char fq_i8;
 #define FQ_AGG_THREADS 256
 #define FQ_AGG_MIN_BLOCKS 4
 #define FQ_AGG_MIN_BLOCKS_U8 2
-#define FQ_SEL_THREADS 256
-#define FQ_SEL_MIN_BLOCKS 3
+#define FQ_SEL_THREADS 384
+#define FQ_SEL_MIN_BLOCKS 2
 #define FQ_SEL_UNROLL 4
+#define FQ_SEL_SEG 8
+#define FQ_SEL_LOOK 2
 #define FQ_MAP_THREADS 256
 #define FQ_MAP_MIN_BLOCKS 4
 #define FQ_MAP_UNROLL 4
@@ -160,8 +162,8 @@ FQ_TRAITS(double, double, 1, 1, -__longlong_as_double(0x7ff0000000000000ll), __l
 
 // wrapping integer add / sub / mul (arrow `add` etc. on integer lanes), plain IEEE for floats
 template <class T> __device__ __forceinline__ T fq_add(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) retur)FQSK"
-R"FQSK(n a + b;
+  )FQSK"
+R"FQSK(if constexpr (fq_traits<T>::is_float) return a + b;
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a + (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_sub(T a, T b) {
@@ -346,10 +348,10 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
     nsel += fq_ld_cg(in);
     err |= (fq_u32)fq_ld_cg(in + 1);
   }
-  fq_block_reduce<Q>(acc, nsel, err, sm);
+  fq_block_reduce<Q>(acc,)FQSK"
+R"FQSK( nsel, err, sm);
   if (threadIdx.x == 0) {
-)FQSK"
-R"FQSK(    if (!Q::HAS_PRED) nsel = p.n_rows;
+    if (!Q::HAS_PRED) nsel = p.n_rows;
     fq_u64 folded = 1, scanned = p.n_rows;
     if (p.accumulate) {
       typename Q::Acc o;
@@ -372,146 +374,282 @@ R"FQSK(    if (!Q::HAS_PRED) nsel = p.n_rows;
 // ---------------------------------------------------------------------------------------------
 // fq_select_kernel — fused predicate + order-preserving stream compaction + projection (+ limit).
 //
-// Tile = blockDim.x * U vector groups; warp w owns the contiguous run of 32 * U groups at
-// tile_base + w * 32 * U, so row order = (warp, u, lane, v).  Ranks: one __ballot_sync per (u, v),
-// __popc of the lower-lane mask; warp totals through shared memory; tile prefix by a decoupled
-// look-back over 64-bit descriptors {flag:2, count:62} (tile ids handed out by atomicAdd so every
-// predecessor of a running tile has started).  Selected rows are projected at scatter time.
-// Algorithmic traffic: sizeof(row) read per row + sum(sizeof(out_i)) written per selected row.
+// CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
+// (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
+// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are handed out by
+// atomicAdd (every predecessor of a running segment has started).
+//   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
+//                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
+//   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
+//                     segment's global base by a decoupled look-back over 64-bit descriptors {flag:2, count:62};
+//   workers, pass 2   (one segment behind) warps that selected something in a tile re-read that tile (still in the
+//                     126 MB L2: <= resident CTAs * 2 * 128 KB are in flight), rank rows with __ballot_sync / __popc
+//                     of the lower-lane mask and write each selected row once, projected at scatter time.
+// The look-back of segment k (a chain of global round trips that also waits for the slowest predecessor)
+// overlaps the workers' pass 1 of segment k + 1: named barriers FULL[k&1] (workers arrive, scan waits) and
+// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
+// warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back per 16-KB tile cannot keep up
+// with HBM at all (0.7 TB/s measured).
+// Rows beyond min(limit, capacity) are counted, not written.  Early exit: the segment that reaches `stop_after`
+// raises a flag; a CTA that sees it when claiming publishes a saturated prefix for the claimed segment and leaves.
+// Algorithmic traffic: sizeof(row) read per row from HBM + sum(sizeof(out_i)) written per selected row.
 // ---------------------------------------------------------------------------------------------
 #define FQ_TILE_AGG (1ull << 62)
 #define FQ_TILE_PREFIX (2ull << 62)
 #define FQ_TILE_VALUE(x) ((x) & ((1ull << 62) - 1))
 #define FQ_TILE_FLAG(x) ((x) >> 62)
 
+__device__ __forceinline__ void fq_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void fq_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Tile access is split in two so that a tile's loads can be in flight while the previous tile is ranked:
+// fq_tile_load only issues the loads (full tiles vectorised, the ragged last one row by row), fq_tile_pred
+// evaluates the predicate on rows that exist: bit (u * V + v) of the returned mask is set for kept rows.
+// `wthreads` = worker threads of the CTA (the tile geometry ignores the scan warp).
 template <class Q, int U>
+__device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 tile, int wthreads, typename Q::Rows (&rows)[U]) {
+  constexpr int V = Q::V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u64 tile_groups = (fq_u64)wthreads * U;
+  const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
+  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+#pragma unroll
+    for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
+  } else if (tile * tile_groups * V < p.n_rows) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const fq_u64 row0 = (g0 + 32ull * u) * V;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        if (row0 + v < p.n_rows) {
+          typename Q::Rows one;
+          Q::load1(one, p, row0 + v);
+          Q::copy_row(rows[u], v, one);
+        }
+      }
+    }
+  }
+}
+template <class Q, int U>
+__device__ __forceinline__ fq_u32 fq_tile_pred(const fq_launch_params &p, fq_u64 tile, int wthreads, const typename Q::Rows (&rows)[U], fq_u32 &err) {
+  constexpr int V = Q::V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u64 tile_groups = (fq_u64)wthreads * U;
+  fq_u32 keep = 0;
+  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int v = 0; v < V; v++) keep |= (Q::pred(rows[u], v, err) ? 1u : 0u) << (u * V + v);
+  } else if (tile * tile_groups * V < p.n_rows) {
+    const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const fq_u64 row0 = (g0 + 32ull * u) * V;
+#pragma unroll
+      for (int v = 0; v < V; v++)
+        if (row0 + v < p.n_rows) keep |= (Q::pred(rows[u], v, err) ? 1u : 0u) << (u * V + v);
+    }
+  }
+  return keep;
+}
+
+// tile / segment shape for a given vector width: at most 32 predicate bits per thread per tile and 64 per segment
+template <int V> struct fq_sel_shape {
+  static constexpr int U = (FQ_SEL_UNROLL * V <= 32) ? FQ_SEL_UNROLL : (32 / V);
+  static constexpr int SEG = (FQ_SEL_SEG * U * V <= 64) ? FQ_SEL_SEG : (64 / (U * V));
+};
+
+enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 4 };  // named barrier ids (FULL/DONE take +0/+1)
+
+template <class Q, int U, int SEG>
 __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
-  __shared__ fq_u32 s_warp_tot[FQ_MAX_WARPS];
-  __shared__ fq_u64 s_tile_excl;
-  __shared__ fq_u64 s_tile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int BITS = U * V;                 // predicate bits per thread per tile
+  static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
+  __shared__ fq_u32 s_cnt[2][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
+  __shared__ fq_u64 s_excl[2];                    // global base of the segment in each ring slot
+  __shared__ fq_u64 s_seg[4];                     // claimed segment ids (ring of 4: the scan warp lags the workers)
+  __shared__ fq_u32 s_stop[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wthreads = (int)blockDim.x - 32, nwarps = wthreads >> 5, allthreads = (int)blockDim.x;
+  const bool is_scan = (int)threadIdx.x >= wthreads;
   const fq_u32 lt_mask = (1u << lane) - 1u;
-  const fq_u64 tile_groups = (fq_u64)blockDim.x * U;
-  const fq_u64 tile_rows = tile_groups * V;
+  const fq_u64 n_seg = p.n_tiles;
   fq_u32 err = 0;
 
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(p.tile_counter, 1u);
-    __syncthreads();
-    const fq_u64 tile = s_tile;
-    if (tile >= p.n_tiles) break;
+  // Claiming a segment and observing the early-exit flag happen together: a claimed segment is ALWAYS published
+  // (successors may be waiting on it in their look-back).
+  auto claim = [&](int slot) {
+    const fq_u64 c = atomicAdd(p.tile_counter, 1u);
+    const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
+    if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
+    s_seg[slot] = c;
+    s_stop[slot] = st;
+  };
+  if (threadIdx.x == 0) claim(0);
+  __syncthreads();
 
-    const bool skip = p.stop_after != 0 && fq_ld_volatile32(p.done) != 0;  // uniform per CTA? no: re-read below
-    __shared__ fq_u32 s_skip;
-    if (threadIdx.x == 0) s_skip = skip ? 1u : 0u;
-    __syncthreads();
-
-    typename Q::Rows rows[U];
-    fq_u32 keep = 0;  // bit (u * V + v)
-    fq_u32 rank[U];
-    fq_u32 wtotal = 0;
-    if (!s_skip) {
-      const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
-      const bool full = (tile + 1) * tile_rows <= p.n_rows;
-      if (full) {
+  if (is_scan) {
+    // ================= scan warp =================
+    for (int k = 0;; k++) {
+      const int b = k & 1;
+      fq_bar_sync(FQ_BAR_FULL + b, allthreads);
+      const fq_u64 seg = s_seg[k & 3];
+      if (!(seg < n_seg) || s_stop[k & 3]) break;
+      // counts -> exclusive offsets in (tile, warp) order; segment total
+      const int entries = SEG * nwarps;
+      const int per = (entries + 31) / 32;
+      fq_u32 local = 0;
+      for (int j = 0; j < per; j++) {
+        const int i = lane * per + j;
+        if (i < entries) local += s_cnt[b][i / nwarps][i )FQSK"
+R"FQSK(% nwarps];
+      }
+      fq_u32 incl_lane = local;
 #pragma unroll
-        for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-          for (int v = 0; v < V; v++) keep |= (Q::pred(rows[u], v, err) ? 1u : 0u) << (u * V + v);
+      for (int m = 1; m < 32; m <<= 1) {
+        const fq_u32 o = __shfl_up_sync(0xffffffffu, incl_lane, m);
+        if (lane >= m) incl_lane += o;
+      }
+      const fq_u32 tot = __shfl_sync(0xffffffffu, incl_lane, 31);
+      fq_u32 run = incl_lane - local;
+      for (int j = 0; j < per; j++) {
+        const int i = lane * per + j;
+        if (i < entries) {
+          const fq_u32 c = s_cnt[b][i / nwarps][i % nwarps];
+          s_cnt[b][i / nwarps][i % nwarps] = run;
+          run += c;
+        }
+      }
+      // decoupled look-back
+      fq_u64 excl = 0;
+      if (seg == 0) {
+        if (lane == 0) fq_st_volatile(p.tile_status, FQ_TILE_PREFIX | (fq_u64)tot);
       } else {
+        if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_AGG | (fq_u64)tot);
+        fq_i64 look = (fq_i64)seg - 1;
+        for (;;) {
+          // FQ_SEL_LOOK * 32 predecessors per poll: lane l inspects look - 32 * j - l for j = 0 .. FQ_SEL_LOOK - 1
+          fq_u64 st[FQ_SEL_LOOK];
+          bool ready;
+          do {
+            ready = true;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const fq_u64 row0 = (g0 + 32ull * u) * V;
+            for (int j = 0; j < FQ_SEL_LOOK; j++) {
+              const fq_i64 idx = look - 32 * j - lane;
+              st[j] = idx >= 0 ? fq_ld_volatile(p.tile_status + idx) : FQ_TILE_PREFIX;   // before segment 0: prefix 0
+              ready = ready && FQ_TILE_FLAG(st[j]) != 0;
+            }
+          } while (!ready);
+          fq_u64 contrib = 0;
+          bool found = false;
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            if (row0 + v < p.n_rows) {
-              typename Q::Rows one;
-              Q::load1(one, p, row0 + v);
-              Q::copy_row(rows[u], v, one);
-              keep |= (Q::pred(rows[u], v, err) ? 1u : 0u) << (u * V + v);
+          for (int j = 0; j < FQ_SEL_LOOK; j++) {
+            if (!found) {
+              const fq_u32 pm = __ballot_sync(0xffffffffu, FQ_TILE_FLAG(st[j]) == 2);
+              if (pm) {
+                if (lane <= __ffs(pm) - 1) contrib += FQ_TILE_VALUE(st[j]);
+                found = true;
+              } else {
+                contrib += FQ_TILE_VALUE(st[j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int m = 16; m > 0; m >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, m);
+          excl += contrib;
+          if (found) break;
+          look -= 32 * FQ_SEL_LOOK;
+        }
+        if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_PREFIX | (excl + tot));
+      }
+      if (lane == 0) {
+        s_excl[b] = excl;
+        const fq_u64 incl = excl + tot;
+        if (p.stop_after != 0 && incl >= p.stop_after) {
+          *(volatile fq_u32 *)p.done = 1u;
+          atomicMax(p.result, incl);   // the last segment may never run: report what is known
+        }
+        if (seg == n_seg - 1) atomicMax(p.result, incl);
+      }
+      __syncwarp();
+      fq_bar_arrive(FQ_BAR_DONE + b, allthreads);
+    }
+    return;
+  }
+
+  // ================= worker warps =================
+  fq_u64 keep_prev = 0, seg_prev = 0;
+  bool have_prev = false;
+  for (int k = 0;; k++) {
+    const int b = k & 1;
+    const fq_u64 seg = s_seg[k & 3];
+    const bool active = seg < n_seg && !s_stop[k & 3];
+    if (threadIdx.x == 0 && active) claim((k + 1) & 3);   // consumed at the next iteration: its latency is hidden
+
+    // ---- pass 1: one streaming read of the segment, one bit per row ----
+    fq_u64 keepbits = 0;
+    if (active) {
+      typename Q::Rows rows0[U], rows_n[U];
+      fq_tile_load<Q, U>(p, seg * SEG, wthreads, rows0);
+#pragma unroll
+      for (int t = 0; t < SEG; t++) {
+        if (t + 1 < SEG) fq_tile_load<Q, U>(p, seg * SEG + t + 1, wthreads, rows_n);   // next tile's loads in flight
+        const fq_u32 keep = fq_tile_pred<Q, U>(p, seg * SEG + t, wthreads, rows0, err);
+        keepbits |= (fq_u64)keep << (t * BITS);
+        const fq_u32 wcount = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
+        if (lane == 0) s_cnt[b][t][warp] = wcount;
+        if (t + 1 < SEG) {
+#pragma unroll
+          for (int u = 0; u < U; u++) rows0[u] = rows_n[u];
+        }
+      }
+    }
+    __syncwarp();
+    fq_bar_arrive(FQ_BAR_FULL + b, allthreads);   // hand the counts (or the end marker) to the scan warp
+
+    // ---- pass 2 of the PREVIOUS segment: its look-back ran while this segment was streamed ----
+    if (have_prev) {
+      const int pb = b ^ 1;
+      fq_bar_sync(FQ_BAR_DONE + pb, allthreads);
+      const fq_u64 base = s_excl[pb];
+      if (base < p.capacity) {
+#pragma unroll
+        for (int t = 0; t < SEG; t++) {
+          const fq_u32 keep = (fq_u32)(keep_prev >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
+          if (__any_sync(0xffffffffu, keep != 0)) {
+            typename Q::Rows rows[U];
+            fq_tile_load<Q, U>(p, seg_prev * SEG + t, wthreads, rows);   // L2 hit
+            fq_u64 pos0 = base + s_cnt[pb][t][warp];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              fq_u32 before = 0, tot = 0;
+#pragma unroll
+              for (int v = 0; v < V; v++) {
+                const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
+                before += __popc(bmask & lt_mask);
+                tot += __popc(bmask);
+              }
+              fq_u64 pos = pos0 + before;
+#pragma unroll
+              for (int v = 0; v < V; v++) {
+                if ((keep >> (u * V + v)) & 1u) {
+                  if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+                  pos++;
+                }
+              }
+              pos0 += tot;
             }
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        fq_u32 before = 0, tot = 0;
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const fq_u32 b = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
-          before += __popc(b & lt_mask);
-          tot += __popc(b);
-        }
-        rank[u] = wtotal + before;
-        wtotal += tot;
-      }
     }
-    if (lane == 0) s_warp_tot[warp] = wtotal;
-    __syncthreads();
-
-    fq_u32 warp_off = 0, tile_total = 0;
-    for (int w = 0; w < nwarps; w++) {
-      const fq_u32 t = s_warp_tot[w];
-      if (w < warp) warp_off += t;
-      tile_total += t;
-    }
-
-    // decoupled look-back, done by warp 0
-    if (warp == 0) {
-      fq_u64 excl = 0;
-      if (s_skip) {
-        // the scan already found `stop_after` rows: publish a saturated prefix so successors write nothing
-        if (lane == 0) fq_st_volatile(p.tile_status + tile, FQ_TILE_PREFIX | p.stop_after);
-        excl = p.stop_after;
-      } else if (tile == 0) {
-        if (lane == 0) fq_st_volatile(p.tile_status, FQ_TILE_PREFIX | (fq_u64)tile_total);
-      } else {
-        if (lane == 0) fq_st_volatile(p.tile_status + tile, FQ_TILE_AGG | (fq_u64)tile_total);
-        fq_i64 look = (fq_i64)tile - 1;
-        for (;;) {
-          const fq_i64 idx = look - lane;
-          fq_u64 s = FQ_TILE_PREFIX;  // virtual tiles before tile 0: prefix 0
-          if (idx >= 0) {
-            do { s = fq_ld_volatile(p.tile_status + idx); } while (FQ_TILE_FLAG(s) == 0);
-          }
-          const fq_u32 pm = __ballot_sync(0xffffffffu, FQ_TILE_FLAG(s) == 2);
-          const int first = pm ? (__ffs(pm) - 1) : 32;
-          fq_u64 contrib = (lane <= first) ? FQ_TILE_VALUE(s) : 0ull;
-#pragma unroll
-          for (int m = 16; m > 0; m >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, m);
-          excl += contrib;
-          if (pm) break;
-          look -= 32;
-        }
-        if (lane == 0) fq_st_volatile(p.tile_status + tile, FQ_TILE_PREFIX | (excl + tile_total));
-      }
-      if (lane == 0) {
-        s_tile_excl = excl;
-        const fq_u64 incl = excl + tile_total;
-        if (p.stop_after != 0 && incl >= p.stop_after) *(volatile fq_u32 *)p.done = 1u;
-        if (tile == p.n_tiles - 1) p.result[0] = incl;
-      }
-    }
-    __syncthreads();
-
-    if (tile_total != 0 && !s_skip) {
-      const fq_u64 base = s_tile_excl + warp_off;
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        fq_u64 pos = base + rank[u];
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          if ((keep >> (u * V + v)) & 1u) {
-            if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
-            pos++;
-          }
-        }
-      }
-    }
+    if (!active) break;
+    keep_prev = keepbits;
+    seg_prev = seg;
+    have_prev = true;
+    fq_bar_sync(FQ_BAR_WORKERS, wthreads);   // s_seg[(k+1)&3] visible; every worker is done with ring slot b^1
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
