@@ -246,6 +246,8 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def("schema", [](const PlanNode &p) { return std::const_pointer_cast<DataSchema>(p.schema()); })
       .def("children_to_plans", &PlanNode::children_to_plans)
       .def_readonly("partitions", &PlanNode::partitions)
+      .def_readonly("db", &PlanNode::db)
+      .def_readonly("table", &PlanNode::table)
       .def_readonly("expr", &PlanNode::expr)
       .def_readonly("predicate", &PlanNode::predicate)
       .def_readonly("n", &PlanNode::n)
@@ -315,7 +317,13 @@ PYBIND11_MODULE(_fuse_host, m) {
   py::class_<LimitTransform, IProcessor, std::shared_ptr<LimitTransform>>(m, "LimitTransform")
       .def_static("try_create", [](size_t n) { return std::make_shared<LimitTransform>(n); });
   py::class_<MergeProcessor, IProcessor, std::shared_ptr<MergeProcessor>>(m, "MergeProcessor").def(py::init<>());
-  py::class_<GpuPipeTransform, IProcessor, std::shared_ptr<GpuPipeTransform>>(m, "GpuPipeTransform").def("describe", &GpuPipeTransform::describe);
+  py::class_<GpuPipeTransform, IProcessor, std::shared_ptr<GpuPipeTransform>>(m, "GpuPipeTransform")
+      .def_static("try_create",
+                  [](FuseQueryContextRef c, std::string db, std::string table, Partitions parts, std::optional<ExpressionPlan> pred, bool is_agg,
+                     std::shared_ptr<DataSchema> schema, std::vector<ExpressionPlan> exprs, std::optional<size_t> limit) {
+                    return std::make_shared<GpuPipeTransform>(c, db, table, parts, pred, is_agg, schema, exprs, limit);
+                  })
+      .def("describe", &GpuPipeTransform::describe);
 
   py::class_<Pipeline>(m, "Pipeline")
       .def(py::init<>())

@@ -160,24 +160,34 @@ FQ_TRAITS(float, float, 1, 1, -__int_as_float(0x7f800000), __int_as_float(0x7f80
 FQ_TRAITS(double, double, 1, 1, -__longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0x7ff0000000000000ll))
 #undef FQ_TRAITS
 
-// wrapping integer add / sub / mul (arrow `add` etc. on integer lanes), plain IEEE for floats
+// wrapping integer add / sub / mul (arrow `add` etc. on integer lanes).  Float lanes use the round-to-nearest
+// intrinsics, which the compiler never contracts int)FQSK"
+R"FQSK(o FMAs: `a * b + c` must round twice like the reference's
+// separate Arrow passes do (a contracted FMA differs in the last bit).
+__device__ __forceinline__ float fq_fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fq_fadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float fq_fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double fq_fsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fq_fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double fq_fmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float fq_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double fq_fdiv(double a, double b) { return __ddiv_rn(a, b); }
 template <class T> __device__ __forceinline__ T fq_add(T a, T b) {
-  )FQSK"
-R"FQSK(if constexpr (fq_traits<T>::is_float) return a + b;
+  if constexpr (fq_traits<T>::is_float) return fq_fadd(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a + (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_sub(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a - b;
+  if constexpr (fq_traits<T>::is_float) return fq_fsub(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a - (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a * b;
+  if constexpr (fq_traits<T>::is_float) return fq_fmul(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a * (U)b); }
 }
 // arrow `divide`: any zero divisor is an error (integer and float lanes alike); integers truncate
 template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
   if (b == (T)0) { err |= FQ_E_DIVZERO; return (T)0; }
-  if constexpr (fq_traits<T>::is_float) return a / b;
+  if constexpr (fq_traits<T>::is_float) return fq_fdiv(a, b);
   else if constexpr (fq_traits<T>::is_signed) {
     typedef typename fq_traits<T>::unsigned_t U;
     if (b == (T)-1) return (T)(U)((U)0 - (U)a);  // MIN / -1 wraps instead of trapping
@@ -317,7 +327,8 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
-    Q::consume(acc, r, 0, nsel, err);
+   )FQSK"
+R"FQSK( Q::consume(acc, r, 0, nsel, err);
   }
 
   fq_block_reduce<Q>(acc, nsel, err, sm);
@@ -348,8 +359,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
     nsel += fq_ld_cg(in);
     err |= (fq_u32)fq_ld_cg(in + 1);
   }
-  fq_block_reduce<Q>(acc,)FQSK"
-R"FQSK( nsel, err, sm);
+  fq_block_reduce<Q>(acc, nsel, err, sm);
   if (threadIdx.x == 0) {
     if (!Q::HAS_PRED) nsel = p.n_rows;
     fq_u64 folded = 1, scanned = p.n_rows;
@@ -480,7 +490,8 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
 
   // Claiming a segment and observing the early-exit flag happen together: a claimed segment is ALWAYS published
   // (successors may be waiting on it in their look-back).
-  auto claim = [&](int slot) {
+)FQSK"
+R"FQSK(  auto claim = [&](int slot) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
     const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
     if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
@@ -503,8 +514,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
       fq_u32 local = 0;
       for (int j = 0; j < per; j++) {
         const int i = lane * per + j;
-        if (i < entries) local += s_cnt[b][i / nwarps][i )FQSK"
-R"FQSK(% nwarps];
+        if (i < entries) local += s_cnt[b][i / nwarps][i % nwarps];
       }
       fq_u32 incl_lane = local;
 #pragma unroll
@@ -686,7 +696,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
     for (int v = 0; v < V; v++)
       if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
   }
-  for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
+  for (fq_u64 row = nvec * )FQSK"
+R"FQSK(V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
     if (row < p.capacity) Q::emit(r, 0, p, row, err);

@@ -159,23 +159,33 @@ FQ_TRAITS(float, float, 1, 1, -__int_as_float(0x7f800000), __int_as_float(0x7f80
 FQ_TRAITS(double, double, 1, 1, -__longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0x7ff0000000000000ll))
 #undef FQ_TRAITS
 
-// wrapping integer add / sub / mul (arrow `add` etc. on integer lanes), plain IEEE for floats
+// wrapping integer add / sub / mul (arrow `add` etc. on integer lanes).  Float lanes use the round-to-nearest
+// intrinsics, which the compiler never contracts into FMAs: `a * b + c` must round twice like the reference's
+// separate Arrow passes do (a contracted FMA differs in the last bit).
+__device__ __forceinline__ float fq_fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fq_fadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float fq_fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double fq_fsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fq_fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double fq_fmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float fq_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double fq_fdiv(double a, double b) { return __ddiv_rn(a, b); }
 template <class T> __device__ __forceinline__ T fq_add(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a + b;
+  if constexpr (fq_traits<T>::is_float) return fq_fadd(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a + (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_sub(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a - b;
+  if constexpr (fq_traits<T>::is_float) return fq_fsub(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a - (U)b); }
 }
 template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
-  if constexpr (fq_traits<T>::is_float) return a * b;
+  if constexpr (fq_traits<T>::is_float) return fq_fmul(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a * (U)b); }
 }
 // arrow `divide`: any zero divisor is an error (integer and float lanes alike); integers truncate
 template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
   if (b == (T)0) { err |= FQ_E_DIVZERO; return (T)0; }
-  if constexpr (fq_traits<T>::is_float) return a / b;
+  if constexpr (fq_traits<T>::is_float) return fq_fdiv(a, b);
   else if constexpr (fq_traits<T>::is_signed) {
     typedef typename fq_traits<T>::unsigned_t U;
     if (b == (T)-1) return (T)(U)((U)0 - (U)a);  // MIN / -1 wraps instead of trapping

@@ -1,0 +1,67 @@
+"""Multi-GPU execution of a SELECT: one process per GPU (torch.distributed), partitions split across ranks.
+
+The reference runs one pipe per chunk of partitions and merges them at MergeProcessor
+(processors/pipeline_builder.rs:73-95, processor_merge.rs:37-66).  Here each rank runs the fused GpuPipeTransform
+over ITS consecutive partitions; what crosses ranks is exactly what crosses the reference's merge channel:
+the partial-state block (one Utf8/JSON row per aggregate expression, transform_aggregate_partial.rs:61-72) or the
+filtered + projected rows.  The final stage (AggregateFinalTransform / LimitTransform) is the unchanged host logic.
+torch.distributed is plumbing: NCCL (or gloo) carries a few hundred bytes per rank.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _fuse_host as h
+
+
+def _my_partitions(parts: list, rank: int, world: int) -> list:
+    per = max(1, len(parts) // world)
+    return parts[rank * per:(rank + 1) * per] if rank < world - 1 else parts[rank * per:]
+
+
+def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_object) -> Tuple[List[str], List[tuple]]:
+    """Returns (column names, rows) on every rank.  `all_gather_object(obj) -> list` is the collective
+    (torch.distributed.all_gather_object bound to a group)."""
+    plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, sql))
+    plans = plan.children_to_plans()
+    src = plans[0]
+    if src.name() != "ReadSourcePlan":
+        raise h.FuseQueryError("Internal Error: distributed execution needs a table source")
+    i = 1
+    pred = None
+    if i < len(plans) and plans[i].name() == "FilterPlan":
+        pred = plans[i].predicate
+        i += 1
+    sel = plans[i]
+    is_agg = sel.name() == "AggregatePlan"
+    i += 1
+    limit = plans[i].n if i < len(plans) and plans[i].name() == "LimitPlan" else None
+    parts = _my_partitions(list(src.partitions), rank, world)
+    names = sel.schema().names()
+    local_blocks = []
+    if parts:
+        pipe = h.GpuPipeTransform.try_create(ctx, src.db, src.table, parts, pred, is_agg, sel.schema(), sel.expr,
+                                             None if is_agg else limit)
+        local_blocks = pipe.execute().collect()
+    if is_agg:
+        mine = [b.column(0).to_list() for b in local_blocks]            # JSON rows of this rank's partial block(s)
+        gathered = all_gather_object(mine)
+        blocks = [h.DataBlock.create(sel.schema(), [h.DataArray.utf8(rows)]) for per_rank in gathered for rows in per_rank]
+        final = h.AggregateFinalTransform.try_create(ctx, sel.schema(), sel.expr)
+        final.connect_to(h.DataBlockSource(blocks))
+        out = final.execute().collect()
+        rows = [tuple(b.column(c).to_list()[0] for c in range(b.num_columns())) for b in out]
+        if limit is not None:
+            rows = rows[:limit]
+        return names, rows
+    mine = [[b.column(c).to_numpy() for c in range(b.num_columns())] for b in local_blocks]
+    gathered = all_gather_object(mine)
+    rows: List[tuple] = []
+    for per_rank in gathered:                                           # rank order = partition order (a legal merge order)
+        for cols in per_rank:
+            rows.extend(zip(*[np.asarray(c).tolist() for c in cols]))
+    if limit is not None:                                               # LimitTransform x 1 after the merge
+        rows = rows[:limit]
+    return names, rows

@@ -309,3 +309,50 @@ def test_readme_headline_query_10b_through_sql(gpu):
         assert rows_of(blocks) == [(1310651184, 9999999999, 0)]
         assert blocks[0].schema().names() == ["Sum(number) / Count(number)", "Max(number)", "Min(number)"]
     h.numbers_cache_clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-process execution: two ranks (gloo plumbing, both on cuda:0) run the fused pipes of their own partitions
+# ---------------------------------------------------------------------------------------------
+def _dist_worker(rank, world, port, sqls, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fuse_query_b200 import _fuse_host as hh
+    from fuse_query_b200.distributed import execute_sql_distributed
+    ctx = hh.FuseQueryContext.create_ctx(1, hh.GpuContext.create(0))
+
+    def gather(obj):
+        res = [None] * world
+        dist.all_gather_object(res, obj)
+        return res
+
+    results = [execute_sql_distributed(ctx, s, rank, world, gather) for s in sqls]
+    if rank == 0:
+        out.put(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_distributed_sql(gpu):
+    import os
+    import torch.multiprocessing as mp
+    n = 16_000_000
+    sqls = [f"select sum(number)/count(number), max(number), min(number) from system.numbers_mt({n})",
+            f"select (number+1) as c1, number/2 as c2 from system.numbers_mt({n}) where (c1+c2+1) < 100 limit 3",
+            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number"]
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = 29800 + (os.getpid() % 150)
+    procs = [mpctx.Process(target=_dist_worker, args=(r, 2, port, sqls, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    s = n * (n - 1) // 2
+    assert got[0] == (["Sum(number) / Count(number)", "Max(number)", "Min(number)"], [(s // n, n - 1, 0)])
+    assert got[1] == (["c1", "c2"], [(1, 0), (2, 0), (3, 1)])
+    assert got[2] == (["number"], [(k * 1000000,) for k in range(16)])
