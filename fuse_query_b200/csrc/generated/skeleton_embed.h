@@ -470,15 +470,15 @@ template <int V> struct fq_sel_shape {
   static constexpr int SEG = (FQ_SEL_SEG * U * V <= 64) ? FQ_SEL_SEG : (64 / (U * V));
 };
 
-enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 4 };  // named barrier ids (FULL/DONE take +0/+1)
+enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2)
 
 template <class Q, int U, int SEG>
 __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
   constexpr int BITS = U * V;                 // predicate bits per thread per tile
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
-  __shared__ fq_u32 s_cnt[2][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
-  __shared__ fq_u64 s_excl[2];                    // global base of the segment in each ring slot
+  __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
+  __shared__ fq_u64 s_excl[FQ_SEL_RING];                    // global base of the segment in each ring slot
   __shared__ fq_u64 s_seg[4];                     // claimed segment ids (ring of 4: the scan warp lags the workers)
   __shared__ fq_u32 s_stop[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -489,9 +489,9 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   fq_u32 err = 0;
 
   // Claiming a segment and observing the early-exit flag happen together: a claimed segment is ALWAYS published
-  // (successors may be waiting on it in their look-back).
-)FQSK"
-R"FQSK(  auto claim = [&](int slot) {
+  // (successors may )FQSK"
+R"FQSK(be waiting on it in their look-back).
+  auto claim = [&](int slot) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
     const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
     if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
@@ -504,7 +504,7 @@ R"FQSK(  auto claim = [&](int slot) {
   if (is_scan) {
     // ================= scan warp =================
     for (int k = 0;; k++) {
-      const int b = k & 1;
+      const int b = k % FQ_SEL_RING;
       fq_bar_sync(FQ_BAR_FULL + b, allthreads);
       const fq_u64 seg = s_seg[k & 3];
       if (!(seg < n_seg) || s_stop[k & 3]) break;
@@ -590,10 +590,44 @@ R"FQSK(  auto claim = [&](int slot) {
   }
 
   // ================= worker warps =================
-  fq_u64 keep_prev = 0, seg_prev = 0;
-  bool have_prev = false;
+  // scatter of segment j: its look-back had two segment-streaming times to complete
+  auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
+    fq_bar_sync(FQ_BAR_DONE + sb, allthreads);
+    const fq_u64 base = s_excl[sb];
+    if (base >= p.capacity) return;
+#pragma unroll
+    for (int t = 0; t < SEG; t++) {
+      const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
+      if (__any_sync(0xffffffffu, keep != 0)) {
+        typename Q::Rows rows[U];
+        fq_tile_load<Q, U>(p, sseg * SEG + t, wthreads, rows);   // L2 hit
+        fq_u64 pos0 = base + s_cnt[sb][t][warp];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          fq_u32 before = 0, tot = 0;
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
+            before += __popc(bmask & lt_mask);
+            tot += __popc(bmask);
+          }
+          fq_u64 pos = pos0 + before;
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            if ((keep >> (u * V + v)) & 1u) {
+              if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+              pos++;
+            }
+          }
+          pos0 += tot;
+        }
+      }
+    }
+  };
+  fq_u64 keep1 = 0, seg1 = 0, keep2 = 0, seg2 = 0;   // segments k-1 and k-2, still to be scattered
+  int pending = 0;
   for (int k = 0;; k++) {
-    const int b = k & 1;
+    const int b = k % FQ_SEL_RING;
     const fq_u64 seg = s_seg[k & 3];
     const bool active = seg < n_seg && !s_stop[k & 3];
     if (threadIdx.x == 0 && active) claim((k + 1) & 3);   // consumed at the next iteration: its latency is hidden
@@ -619,47 +653,21 @@ R"FQSK(  auto claim = [&](int slot) {
     __syncwarp();
     fq_bar_arrive(FQ_BAR_FULL + b, allthreads);   // hand the counts (or the end marker) to the scan warp
 
-    // ---- pass 2 of the PREVIOUS segment: its look-back ran while this segment was streamed ----
-    if (have_prev) {
-      const int pb = b ^ 1;
-      fq_bar_sync(FQ_BAR_DONE + pb, allthreads);
-      const fq_u64 base = s_excl[pb];
-      if (base < p.capacity) {
-#pragma unroll
-        for (int t = 0; t < SEG; t++) {
-          const fq_u32 keep = (fq_u32)(keep_prev >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
-          if (__any_sync(0xffffffffu, keep != 0)) {
-            typename Q::Rows rows[U];
-            fq_tile_load<Q, U>(p, seg_prev * SEG + t, wthreads, rows);   // L2 hit
-            fq_u64 pos0 = base + s_cnt[pb][t][warp];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              fq_u32 before = 0, tot = 0;
-#pragma unroll
-              for (int v = 0; v < V; v++) {
-                const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
-                before += __popc(bmask & lt_mask);
-                tot += __popc(bmask);
-              }
-              fq_u64 pos = pos0 + before;
-#pragma unroll
-              for (int v = 0; v < V; v++) {
-                if ((keep >> (u * V + v)) & 1u) {
-                  if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
-                  pos++;
-                }
-              }
-              pos0 += tot;
-            }
-          }
-        }
-      }
+    // ---- pass 2 of segment k-2 (while the scan warp resolves k-1 and k) ----
+    if (pending == 2) {
+      scatter(seg2, keep2, (k + 1) % FQ_SEL_RING);   // (k - 2) mod 3
+      pending = 1;
     }
-    if (!active) break;
-    keep_prev = keepbits;
-    seg_prev = seg;
-    have_prev = true;
-    fq_bar_sync(FQ_BAR_WORKERS, wthreads);   // s_seg[(k+1)&3] visible; every worker is done with ring slot b^1
+    if (!active) {
+      if (pending == 1) scatter(seg1, keep1, (k + 2) % FQ_SEL_RING);   // (k - 1) mod 3
+      break;
+    }
+    keep2 = keep1;
+    seg2 = seg1;
+    keep1 = keepbits;
+    seg1 = seg;
+    pending += 1;
+    fq_bar_sync(FQ_BAR_WORKERS, wthreads);   // s_seg[(k+1)&3] visible; every worker is done with the ring slot reused next
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
@@ -687,7 +695,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
         if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
     }
   }
-  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.)FQSK"
+R"FQSK(x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
@@ -696,8 +705,7 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
     for (int v = 0; v < V; v++)
       if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
   }
-  for (fq_u64 row = nvec * )FQSK"
-R"FQSK(V + tid; row < p.n_rows; row += nthreads) {
+  for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
     if (row < p.capacity) Q::emit(r, 0, p, row, err);
