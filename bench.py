@@ -49,6 +49,17 @@ README_QUERIES = {
 }
 
 
+def ncu_traffic(rows_per_launch: int, generated: bool):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the aggregate kernel from the committed ncu --set full capture of THIS
+    workload (profiles/r01_traffic_headline_1e10.json); None when the launch differs from the captured one."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic_headline_1e10.json")
+    if generated or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    return t["traffic"] if t["rows"] == rows_per_launch else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -338,7 +349,7 @@ def run_ours(args):
                        "merge": "nccl all_gather of the 64-byte state" if world > 1 else "single GPU",
                        "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
             "hbm_gb_per_s": row_bytes * total * args.steps / secs / 1e9,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n, generated),
                          "kernel": "fq_agg_kernel (fqk_*_agg_u4)", "kernel_ms": kernel_ms, "peak_source": which,
                          "algorithmic_bytes_per_launch": row_bytes * n},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "sql_e2e": sql_e2e,
