@@ -386,8 +386,8 @@ R"FQSK( Q::consume(acc, r, 0, nsel, err);
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
 // (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
-// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are handed out by
-// atomicAdd (every predecessor of a running segment has started).
+// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are assigned round-robin to
+// the CTAs of a persistent, fully resident grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
 //                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
 //   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
@@ -472,6 +472,49 @@ template <int V> struct fq_sel_shape {
 
 enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2)
 
+// Pass 2 of one segment (kept out of line: it runs once per 128 KB and would otherwise double the register
+// pressure of the streaming loop).  `cnt` = this segment's ring slot of exclusive offsets, `base` its global base.
+template <class Q, int U, int SEG>
+__device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64 sseg, fq_u64 skeep, const fq_u32 (*cnt)[FQ_MAX_WARPS],
+                                               fq_u64 base, int wthreads, fq_u32 *err_out) {
+  constexpr int V = Q::V;
+  constexpr int BITS = U * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u32 lt_mask = (1u << lane) - 1u;
+  fq_u32 err = 0;
+  if (base >= p.capacity) return;
+#pragma unroll
+  for (int t = 0; t < SEG; t++) {
+    const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
+    if (__any_sync(0xffffffffu, keep != 0)) {
+      typename Q::Rows rows[U];
+      fq_tile_load<Q, U>(p, sseg * SEG + t, wthreads, rows);   // L2 hit
+      fq_u64 pos0 = base + cnt[t][warp];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        fq_u32 before = 0, tot = 0;
+#pragma unroll
+        fo)FQSK"
+R"FQSK(r (int v = 0; v < V; v++) {
+          const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
+          before += __popc(bmask & lt_mask);
+          tot += __popc(bmask);
+        }
+        fq_u64 pos = pos0 + before;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          if ((keep >> (u * V + v)) & 1u) {
+            if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+            pos++;
+          }
+        }
+        pos0 += tot;
+      }
+    }
+  }
+  if (err) *err_out |= err;
+}
+
 template <class Q, int U, int SEG>
 __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
@@ -479,8 +522,9 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
   __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
   __shared__ fq_u64 s_excl[FQ_SEL_RING];                    // global base of the segment in each ring slot
-  __shared__ fq_u64 s_seg[4];                     // claimed segment ids (ring of 4: the scan warp lags the workers)
-  __shared__ fq_u32 s_stop[4];
+  __shared__ volatile fq_u64 s_seg[4];           // claimed segment ids: ring of 4 (the scan warp lags the workers by up to 2)
+  __shared__ volatile fq_u32 s_stop[4];
+  __shared__ volatile int s_ready[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wthreads = (int)blockDim.x - 32, nwarps = wthreads >> 5, allthreads = (int)blockDim.x;
   const bool is_scan = (int)threadIdx.x >= wthreads;
@@ -488,17 +532,25 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   const fq_u64 n_seg = p.n_tiles;
   fq_u32 err = 0;
 
-  // Claiming a segment and observing the early-exit flag happen together: a claimed segment is ALWAYS published
-  // (successors may )FQSK"
-R"FQSK(be waiting on it in their look-back).
-  auto claim = [&](int slot) {
+  // Segments are claimed dynamically (atomicAdd): only running CTAs own segments, so every predecessor of a running
+  // segment has started and the look-back makes progress whatever else shares the GPU.  Claiming and observing the
+  // early-exit flag happen together: a claimed segment is ALWAYS published (a successor may already be polling it); a CTA
+  // that sees the flag publishes a saturated prefix for the segment it just claimed and leaves.
+  // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and hands it to the other warps through a
+  // shared-memory ring (s_ready[slot] == k + 2): no block-wide barrier per segment, warps run ahead on their own.
+  auto publish_claim = [&](int k, fq_u64 c, fq_u32 st) {   // claim of iteration k
+    s_seg[k & 3] = c;
+    s_stop[k & 3] = st;
+    __threadfence_block();
+    s_ready[k & 3] = k + 1;
+  };
+  if (threadIdx.x >= 1 && threadIdx.x < 4) s_ready[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
     const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
     if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
-    s_seg[slot] = c;
-    s_stop[slot] = st;
-  };
-  if (threadIdx.x == 0) claim(0);
+    publish_claim(0, c, st);
+  }
   __syncthreads();
 
   if (is_scan) {
@@ -593,44 +645,27 @@ R"FQSK(be waiting on it in their look-back).
   // scatter of segment j: its look-back had two segment-streaming times to complete
   auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
     fq_bar_sync(FQ_BAR_DONE + sb, allthreads);
-    const fq_u64 base = s_excl[sb];
-    if (base >= p.capacity) return;
-#pragma unroll
-    for (int t = 0; t < SEG; t++) {
-      const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
-      if (__any_sync(0xffffffffu, keep != 0)) {
-        typename Q::Rows rows[U];
-        fq_tile_load<Q, U>(p, sseg * SEG + t, wthreads, rows);   // L2 hit
-        fq_u64 pos0 = base + s_cnt[sb][t][warp];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          fq_u32 before = 0, tot = 0;
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
-            before += __popc(bmask & lt_mask);
-            tot += __popc(bmask);
-          }
-          fq_u64 pos = pos0 + before;
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            if ((keep >> (u * V + v)) & 1u) {
-              if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
-              pos++;
-            }
-          }
-          pos0 += tot;
-        }
-      }
-    }
+    fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], wthreads, &err);
   };
   fq_u64 keep1 = 0, seg1 = 0, keep2 = 0, seg2 = 0;   // segments k-1 and k-2, still to be scattered
   int pending = 0;
   for (int k = 0;; k++) {
     const int b = k % FQ_SEL_RING;
+    if (lane == 0) {
+      while (s_ready[k & 3] != k + 1) {}   // claim of this iteration (made one segment ago by thread 0)
+    }
+    __syncwarp();
     const fq_u64 seg = s_seg[k & 3];
-    const bool active = seg < n_seg && !s_stop[k & 3];
-    if (threadIdx.x == 0 && active) claim((k + 1) & 3);   // consumed at the next iteration: its latency is hidden
+    const bool stop = s_stop[k & 3] != 0;
+    const bool active = seg < n_seg && !stop;
+
+    // thread 0: claim the next segment now, publish it after pass 1 (the atomic's round trip hides behind the streaming)
+    fq_u64 next_c = 0;
+    fq_u32 next_st = 0;
+    if (threadIdx.x == 0 && active) {
+      next_c = atomicAdd(p.tile_counter, 1u);
+      next_st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
+    }
 
     // ---- pass 1: one streaming read of the segment, one bit per row ----
     fq_u64 keepbits = 0;
@@ -646,9 +681,14 @@ R"FQSK(be waiting on it in their look-back).
         if (lane == 0) s_cnt[b][t][warp] = wcount;
         if (t + 1 < SEG) {
 #pragma unroll
-          for (int u = 0; u < U; u++) rows0[u] = rows_n[u];
+          for (int u = 0; u <)FQSK"
+R"FQSK( U; u++) rows0[u] = rows_n[u];
         }
       }
+    }
+    if (threadIdx.x == 0 && active) {
+      if (next_st && next_c < n_seg) fq_st_volatile(p.tile_status + next_c, FQ_TILE_PREFIX | p.stop_after);
+      publish_claim(k + 1, next_c, next_st);
     }
     __syncwarp();
     fq_bar_arrive(FQ_BAR_FULL + b, allthreads);   // hand the counts (or the end marker) to the scan warp
@@ -666,8 +706,7 @@ R"FQSK(be waiting on it in their look-back).
     seg2 = seg1;
     keep1 = keepbits;
     seg1 = seg;
-    pending += 1;
-    fq_bar_sync(FQ_BAR_WORKERS, wthreads);   // s_seg[(k+1)&3] visible; every worker is done with the ring slot reused next
+    pending += 1;   // no block-wide sync here: warps run ahead into the next segment on their own
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
@@ -695,8 +734,7 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
         if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
     }
   }
-  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.)FQSK"
-R"FQSK(x + threadIdx.x;
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
