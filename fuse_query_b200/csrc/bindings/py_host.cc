@@ -273,8 +273,15 @@ PYBIND11_MODULE(_fuse_host, m) {
   py::class_<NumbersTable, ITable, std::shared_ptr<NumbersTable>>(m, "NumbersTable")
       .def(py::init<>())
       .def_static("generate_parts", &NumbersTable::generate_parts);
+  py::class_<MemoryTable, ITable, std::shared_ptr<MemoryTable>>(m, "MemoryTable")
+      .def(py::init([](std::string db, std::string name, std::shared_ptr<DataSchema> schema, std::vector<DataArrayRef> cols) {
+        return std::make_shared<MemoryTable>(std::move(db), std::move(name), schema, std::move(cols));
+      }))
+      .def("num_rows", &MemoryTable::num_rows);
   py::class_<DataSource, std::shared_ptr<DataSource>>(m, "DataSource")
       .def(py::init<>())
+      .def("add_database", &DataSource::add_database)
+      .def("add_table", &DataSource::add_table)
       .def("get_table", &DataSource::get_table);
   py::class_<GpuOptions>(m, "GpuOptions")
       .def_readwrite("fuse", &GpuOptions::fuse)
@@ -288,6 +295,7 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def_readwrite("worker_threads", &FuseQueryContext::worker_threads)
       .def_readwrite("options", &FuseQueryContext::options)
       .def("get_table", &FuseQueryContext::get_table)
+      .def("datasource", &FuseQueryContext::datasource)
       .def("get_current_database", &FuseQueryContext::get_current_database)
       .def("set_current_database", &FuseQueryContext::set_current_database);
   py::class_<Planner>(m, "Planner").def(py::init<>()).def("build_from_sql", &Planner::build_from_sql);

@@ -384,10 +384,29 @@ class NumbersTable : public ITable {
   DataSchemaRef schema_;
 };
 
+// A table whose columns are resident in HBM (the ITable the README calls "Remote (S3 or other table
+// storage engine)" would land its Arrow column chunks here).  Partitioned and streamed exactly like numbers_mt:
+// generate_parts over the row count, partition names "N-start-end", blocks = zero-copy slices of the device columns.
+class MemoryTable : public ITable {
+ public:
+  MemoryTable(std::string db, std::string name, DataSchemaRef schema, std::vector<DataArrayRef> columns);
+  std::string name() const override { return name_; }
+  DataSchemaRef schema() const override { return schema_; }
+  PlanNode read_plan(const PlanNode &push_down_plan) const override;
+  SendableDataBlockStream read(FuseQueryContextRef ctx, const Partitions &parts) const override;
+  uint64_t num_rows() const { return columns_.empty() ? 0 : columns_[0]->len(); }
+
+ private:
+  std::string db_, name_;
+  DataSchemaRef schema_;
+  std::vector<DataArrayRef> columns_;
+};
+
 // datasources/datasource.rs: catalog db -> table
 class DataSource {
  public:
   DataSource();
+  void add_database(const std::string &db) { dbs_[db]; }
   void add_table(const std::string &db, ITableRef table);
   ITableRef get_table(const std::string &db, const std::string &table) const;
 
@@ -412,6 +431,7 @@ class FuseQueryContext : public std::enable_shared_from_this<FuseQueryContext> {
   std::string get_current_database() const;
   void set_current_database(const std::string &db);
   ITableRef get_table(const std::string &db, const std::string &table) const;
+  std::shared_ptr<DataSource> datasource() const { return datasource_; }
   GpuContextRef gpu() const;     // throws when the context was built without a device (planning-only use)
 
  private:

@@ -193,6 +193,56 @@ SendableDataBlockStream NumbersTable::read(FuseQueryContextRef ctx, const Partit
   return std::make_unique<NumbersStream>(std::move(ctx), schema_, parts);
 }
 
+// ---- MemoryTable ----
+MemoryTable::MemoryTable(std::string db, std::string name, DataSchemaRef schema, std::vector<DataArrayRef> columns)
+    : db_(std::move(db)), name_(std::move(name)), schema_(std::move(schema)), columns_(std::move(columns)) {
+  if (schema_->fields.size() != columns_.size()) throw FuseQueryError::internal("MemoryTable: schema and columns differ in length");
+  for (size_t i = 0; i < columns_.size(); i++) {
+    if (columns_[i]->len() != columns_[0]->len()) throw FuseQueryError::internal("MemoryTable: columns differ in length");
+    if (columns_[i]->data_type() != schema_->fields[i].data_type) throw FuseQueryError::internal("MemoryTable: column type differs from the schema");
+  }
+}
+PlanNode MemoryTable::read_plan(const PlanNode &) const {
+  PlanNode p;
+  p.kind = PlanNode::ReadSource;
+  p.db = db_;
+  p.table = name_;
+  p.table_type = "Memory";
+  p.schema_ = schema_;
+  if (num_rows() > 0) p.partitions = NumbersTable::generate_parts(num_rows());
+  p.description = "(Read from " + name_ + " table)";
+  return p;
+}
+namespace {
+class MemoryStream : public IDataBlockStream {
+ public:
+  MemoryStream(FuseQueryContextRef ctx, DataSchemaRef schema, std::vector<DataArrayRef> cols, const Partitions &parts)
+      : schema_(std::move(schema)), cols_(std::move(cols)) {
+    // no tail quirk here: that is a NumbersStream bug, not a property of tables
+    for (const RowRange &r : emitted_ranges(parts, false)) {
+      const uint64_t step = ctx->options.block_rows ? ctx->options.block_rows : r.rows;
+      for (uint64_t off = 0; off < r.rows; off += step) blocks_.push_back({r.begin + off, std::min(step, r.rows - off)});
+    }
+  }
+  std::optional<DataBlock> next() override {
+    if (i_ >= blocks_.size()) return std::nullopt;
+    const RowRange b = blocks_[i_++];
+    std::vector<DataArrayRef> out;
+    for (auto &c : cols_) out.push_back((b.begin == 0 && b.rows == c->len()) ? c : c->slice(b.begin, b.rows));
+    return DataBlock(schema_, out);
+  }
+
+ private:
+  DataSchemaRef schema_;
+  std::vector<DataArrayRef> cols_;
+  std::vector<RowRange> blocks_;
+  size_t i_ = 0;
+};
+}  // namespace
+SendableDataBlockStream MemoryTable::read(FuseQueryContextRef ctx, const Partitions &parts) const {
+  return std::make_unique<MemoryStream>(std::move(ctx), schema_, columns_, parts);
+}
+
 // ---------------------------------------------------------------------------------------------
 // datastreams
 // ---------------------------------------------------------------------------------------------

@@ -356,3 +356,28 @@ def test_two_rank_distributed_sql(gpu):
     assert got[0] == (["Sum(number) / Count(number)", "Max(number)", "Min(number)"], [(s // n, n - 1, 0)])
     assert got[1] == (["c1", "c2"], [(1, 0), (2, 0), (3, 1)])
     assert got[2] == (["number"], [(k * 1000000,) for k in range(16)])
+
+
+# ---------------------------------------------------------------------------------------------
+# a real (non-generated) table resident in HBM: same pipeline, SQL over user columns
+# ---------------------------------------------------------------------------------------------
+def test_memory_table_sql_matches_oracle(gpu):
+    from fuse_query_b200.tables import register_table
+    rng = np.random.default_rng(99)
+    n = 123_457
+    data = {"k": rng.integers(0, 1 << 50, n, dtype=np.uint64), "v": rng.integers(-10**9, 10**9, n, dtype=np.int64),
+            "w": rng.integers(1, 1000, n, dtype=np.uint16)}
+    for workers, fuse in ((1, True), (0, True), (0, False)):
+        ctx = make_ctx(gpu, workers, fuse=fuse, block_rows=0 if fuse else 10000)
+        register_table(ctx, gpu, "default", "t", data)
+        table = {k: o.from_numpy(v) for k, v in data.items()}
+        blocks = h.execute_sql(ctx, "select sum(v), min(v / w), max(k + w), count(k) from t where v < 500000000")
+        want = o.run_query(["(sum (col v))", "(min (/ (col v) (col w)))", "(max (+ (col k) (col w)))", "(count (col k))"], table=table,
+                           predicate="(< (col v) (i64 500000000))" if False else "(< (col v) (u64 500000000))", is_aggregate=True,
+                           worker_threads=workers, tail_quirk=False)
+        assert rows_of(blocks) == want.rows()
+        assert blocks[0].schema().names() == ["Sum(v)", "Min(v / w)", "Max(k + w)", "Count(k)"] == want.names
+        blocks = h.execute_sql(ctx, "select k, v * w as vw from t where w = 7 limit 20")
+        want = o.run_query(["(col k)", "(alias vw (* (col v) (col w)))"], table=table, predicate="(= (col w) (u64 7))", limit=20,
+                           worker_threads=workers, tail_quirk=False)
+        assert rows_of(blocks) == want.rows() and len(want.rows()) == 20
