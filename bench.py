@@ -116,13 +116,14 @@ def shard_of(rank: int, world: int, total: int):
 
 
 def fold_states(rows):
-    """Merge per-rank raw state slots [rows_selected, err, folded, scanned, sum, count, max, min]
-    (AggregatorFunction::merge_state, function_aggregator.rs:106-139) and apply merge_result."""
+    """Merge per-rank raw state slots [6 header slots: rows_selected, err, folded, scanned, blocks, empty blocks | sum, count,
+    max, min] (AggregatorFunction::merge_state, function_aggregator.rs:106-139) and apply merge_result."""
     M = (1 << 64) - 1
-    s = sum(r[4] for r in rows) & M
+    H = 6  # FQ_STATE_HEADER_SLOTS
+    s = sum(r[H] for r in rows) & M
     c = sum(r[0] for r in rows) & M
-    mx = max(r[6] for r in rows)
-    mn = min(r[7] for r in rows)
+    mx = max(r[H + 2] for r in rows)
+    mn = min(r[H + 3] for r in rows)
     return {"sum": s, "count": c, "avg": s // c, "max": mx, "min": mn}
 
 

@@ -22,7 +22,8 @@ DTYPE_SIZE = {BOOL: 1, I8: 1, I16: 2, I32: 4, I64: 8, U8: 1, U16: 2, U32: 4, U64
 OK, ERR_INTERNAL, ERR_PLAN, ERR_DIVIDE_BY_ZERO, ERR_UNSUPPORTED, ERR_CUDA, ERR_INVALID = range(7)
 EXPR_ALIAS, EXPR_CONSTANT, EXPR_FIELD, EXPR_ARITHMETIC, EXPR_COMPARISON, EXPR_LOGIC, EXPR_AGGREGATOR = range(7)
 PIPE_PROJECT, PIPE_AGGREGATE = 0, 1
-RUN_ACCUMULATE, RUN_LIMIT_EARLY_EXIT = 1, 2
+RUN_ACCUMULATE, RUN_LIMIT_EARLY_EXIT, RUN_BLOCK_STATS = 1, 2, 4
+STATE_HEADER_SLOTS = 6   # FQ_STATE_HEADER_SLOTS
 MAX_COLS = MAX_EXPRS = 8
 
 AGG = {"min": 0, "max": 1, "sum": 2, "count": 3}
@@ -69,7 +70,7 @@ EXPORTS = [
     "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_free", "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
-    "fq_pipe_expr_dtype", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_aggregator_nodes",
+    "fq_pipe_expr_dtype", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project",
 ]
 
@@ -112,6 +113,7 @@ def lib():
         "fq_pipe_expr_dtype": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "fq_pipe_launch_aggregate": (i32, [vp, vp, C.POINTER(Source), u32, vp]),
         "fq_pipe_fetch_aggregate": (i32, [vp, vp, C.POINTER(CValue), i32, C.POINTER(i32), C.POINTER(u64)]),
+        "fq_pipe_fetch_block_stats": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "fq_pipe_aggregator_nodes": (i32, [vp, vp, C.POINTER(i32), i32, C.POINTER(i32)]),
         "fq_pipe_state_device": (i32, [vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), u64, i64, u32, vp]),
@@ -369,9 +371,15 @@ class Pipe:
         return p.value, n.value
 
     # ---- aggregate ----
-    def launch_aggregate(self, source: Source, *, accumulate: bool = False, stream: int = 0):
-        self.ctx.check(lib().fq_pipe_launch_aggregate(self.ctx._h, self._h, C.byref(source), RUN_ACCUMULATE if accumulate else 0,
-                                                       C.c_void_p(stream)))
+    def launch_aggregate(self, source: Source, *, accumulate: bool = False, block_stats: bool = False, stream: int = 0):
+        flags = (RUN_ACCUMULATE if accumulate else 0) | (RUN_BLOCK_STATS if block_stats else 0)
+        self.ctx.check(lib().fq_pipe_launch_aggregate(self.ctx._h, self._h, C.byref(source), flags, C.c_void_p(stream)))
+
+    def fetch_block_stats(self) -> Tuple[int, int]:
+        """(reference 10 000-row blocks scanned, blocks in which the predicate kept no row)"""
+        b, e = C.c_uint64(), C.c_uint64()
+        self.ctx.check(lib().fq_pipe_fetch_block_stats(self.ctx._h, self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
 
     def fetch_aggregate(self):
         """-> (list of (dtype, value|None) per Aggregator leaf, or None for DataValue::Null; rows_selected)"""

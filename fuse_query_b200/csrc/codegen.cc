@@ -317,8 +317,12 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
 
   std::string s;
   s += "struct Q_@ {\n";
-  s += fmt("  static constexpr int V = %d;\n  static constexpr int NSLOTS = %d;\n  static constexpr bool HAS_PRED = %s;\n", V,
-           (int)out->agg_nodes.size(), out->has_pred ? "true" : "false");
+  bool has_sum = false;
+  for (int op : out->agg_ops) has_sum = has_sum || op == FQ_AGG_SUM;
+  out->track_blocks = out->has_pred && has_sum;   // only Sum is poisoned by an empty block
+  s += fmt("  static constexpr int V = %d;\n  static constexpr int NSLOTS = %d;\n  static constexpr bool HAS_PRED = %s;\n"
+           "  static constexpr bool TRACK_BLOCKS = %s;\n", V,
+           (int)out->agg_nodes.size(), out->has_pred ? "true" : "false", out->track_blocks ? "true" : "false");
   s += "  struct Rows {";
   for (int c : g.used_cols) s += fmt(" %s c%d[V];", ctype(g.col_dtype(c)), c);
   s += " };\n";
@@ -348,8 +352,8 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     s += "  __device__ static __forceinline__ void init(Acc &a) {\n";
     for (int k = 0; k < n; k++) s += fmt("    a.a%d = %s;\n", k, identity_of(out->agg_ops[k], out->agg_dtypes[k]).c_str());
     s += "  }\n";
-    s += "  __device__ static __forceinline__ void consume(Acc &a, const Rows &r, int v, fq_u64 &nsel, fq_u32 &err) {\n";
-    if (out->has_pred) s += "    if (!pred(r, v, err)) return;\n    nsel += 1;\n";
+    s += "  __device__ static __forceinline__ bool consume(Acc &a, const Rows &r, int v, fq_u64 &nsel, fq_u32 &err) {\n";
+    if (out->has_pred) s += "    if (!pred(r, v, err)) return false;\n    nsel += 1;\n";
     for (int k = 0; k < n; k++) {
       const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
       const char *T = ctype(out->agg_dtypes[k]);
@@ -362,7 +366,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
           s += "    { auto unused = " + arg + "; (void)unused; }\n";
       }
     }
-    s += "  }\n";
+    s += "    return true;\n  }\n";
     s += "  __device__ static __forceinline__ void merge(Acc &a, const Acc &b) {\n";
     for (int k = 0; k < n; k++) {
       const char *T = ctype(out->agg_dtypes[k]);

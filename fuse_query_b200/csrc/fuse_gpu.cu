@@ -185,6 +185,8 @@ struct fq_pipe {
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
   uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
+  uint32_t *d_blocks = nullptr;   // reference-block hit bitmap (FQ_RUN_BLOCK_STATS)
+  uint64_t blocks_cap = 0;
   uint64_t *h_state = nullptr, *h_result = nullptr;  // pinned
   int partials_cap = 0;
   uint64_t tiles_cap = 0;
@@ -506,6 +508,7 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
   cudaFree(pipe->d_partials);
   cudaFree(pipe->d_ctl);
   cudaFree(pipe->d_tiles);
+  cudaFree(pipe->d_blocks);
   if (pipe->h_state) cudaFreeHost(pipe->h_state);
   if (pipe->h_result) cudaFreeHost(pipe->h_result);
   if (pipe->ev) cudaEventDestroy(pipe->ev);
@@ -561,6 +564,17 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   p.state = (fq_u64 *)pipe->d_state;
   p.ticket = (fq_u32 *)(pipe->d_ctl + 4);
   p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
+  if ((flags & FQ_RUN_BLOCK_STATS) && pipe->gen.track_blocks && src->n_rows > 0) {
+    const uint64_t words = ((src->n_rows + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS + 31) / 32;
+    if (words > pipe->blocks_cap) {
+      cudaFree(pipe->d_blocks);
+      pipe->d_blocks = nullptr;
+      CUDA_TRY(cudaMalloc(&pipe->d_blocks, sizeof(uint32_t) * words));
+      pipe->blocks_cap = words;
+    }
+    CUDA_TRY(cudaMemsetAsync(pipe->d_blocks, 0, sizeof(uint32_t) * words, (cudaStream_t)stream));
+    p.block_hit = pipe->d_blocks;
+  }
   if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   CUDA_TRY(cudaMemcpyAsync(pipe->h_state, pipe->d_state, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
@@ -603,6 +617,15 @@ fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, 
     if (t == FQ_F32 || t == FQ_F64) memcpy(&v.v.f, &bits, 8);
     else v.v.u = bits;
   }
+  return FQ_OK;
+}
+
+fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks, uint64_t *empty_blocks) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  if (pipe->launched) CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  if (blocks) *blocks = pipe->launched ? pipe->h_state[4] : 0;
+  if (empty_blocks) *empty_blocks = pipe->launched ? pipe->h_state[5] : 0;
   return FQ_OK;
 }
 

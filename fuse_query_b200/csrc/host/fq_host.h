@@ -422,6 +422,10 @@ struct GpuOptions {
                                  // reference uses 10 000, numbers_stream.rs:29)
   bool tail_quirk = true;        // reproduce numbers_stream.rs:44-46 for sizes that trigger it
   bool limit_early_exit = true;  // let a LIMIT stop the scan (the reference stops pulling blocks, stream_limit.rs:28-31)
+  bool block_quirks = true;      // fused aggregate pipes reproduce SURVEY F8: with a WHERE clause, a Sum whose predicate
+                                 // empties one of the reference's 10 000-row blocks fails like the reference does
+                                 // ("DataValue to array cannot be NONE NULL"); false = return the merged sum instead
+  bool align_runs = false;       // internal: only merge partitions into one device block when block boundaries line up
 };
 class FuseQueryContext : public std::enable_shared_from_this<FuseQueryContext> {
  public:

@@ -99,7 +99,7 @@ PlanNode NumbersTable::read_plan(const PlanNode &push_down_plan) const {   // :6
 // is not a multiple of it, its last block ends at block_begin + remain, so the partition emits only
 // block_size * (n_blocks - 1) + remain + 1 rows (a contiguous prefix).
 struct RowRange { uint64_t begin, rows; };
-static std::vector<RowRange> emitted_ranges(const Partitions &parts, bool tail_quirk) {
+static std::vector<RowRange> emitted_ranges(const Partitions &parts, bool tail_quirk, bool align_runs = false) {
   std::vector<RowRange> out;
   const uint64_t block_size = 10000;
   for (const auto &part : parts) {
@@ -110,7 +110,8 @@ static std::vector<RowRange> emitted_ranges(const Partitions &parts, bool tail_q
     uint64_t nblk = count / block_size, remain = count % block_size;
     uint64_t rows = count;
     if (tail_quirk && nblk > 0 && remain > 0) rows = block_size * (nblk - 1) + remain + 1;
-    if (!out.empty() && out.back().begin + out.back().rows == begin) out.back().rows += rows;
+    // merging two partitions into one run keeps the reference's block boundaries only if the run so far is whole blocks
+    if (!out.empty() && out.back().begin + out.back().rows == begin && (!align_runs || out.back().rows % block_size == 0)) out.back().rows += rows;
     else out.push_back({begin, rows});
   }
   return out;
@@ -158,7 +159,7 @@ class NumbersStream : public IDataBlockStream {
  public:
   NumbersStream(FuseQueryContextRef ctx, DataSchemaRef schema, const Partitions &parts) : ctx_(std::move(ctx)), schema_(std::move(schema)) {
     const GpuOptions &o = ctx_->options;
-    for (const RowRange &r : emitted_ranges(parts, o.tail_quirk)) {
+    for (const RowRange &r : emitted_ranges(parts, o.tail_quirk, o.align_runs)) {
       if (o.block_rows == 0) { blocks_.push_back({r, r}); continue; }
       for (uint64_t off = 0; off < r.rows; off += o.block_rows) blocks_.push_back({{r.begin + off, std::min(o.block_rows, r.rows - off)}, r});
     }
@@ -219,7 +220,7 @@ class MemoryStream : public IDataBlockStream {
   MemoryStream(FuseQueryContextRef ctx, DataSchemaRef schema, std::vector<DataArrayRef> cols, const Partitions &parts)
       : schema_(std::move(schema)), cols_(std::move(cols)) {
     // no tail quirk here: that is a NumbersStream bug, not a property of tables
-    for (const RowRange &r : emitted_ranges(parts, false)) {
+    for (const RowRange &r : emitted_ranges(parts, false, ctx->options.align_runs)) {
       const uint64_t step = ctx->options.block_rows ? ctx->options.block_rows : r.rows;
       for (uint64_t off = 0; off < r.rows; off += step) blocks_.push_back({r.begin + off, std::min(step, r.rows - off)});
     }
@@ -430,6 +431,7 @@ std::string GpuPipeTransform::describe() const {
   return s;
 }
 
+static void collect_leaves(const Function &f, std::vector<const Function *> *out);
 // states of one select expression in accumulate_result order (function_arithmetic.rs:69-75)
 static void collect_states(const Function &f, const std::map<const Function *, DataValue> &leaf, std::vector<DataValue> *out) {
   switch (f.kind) {
@@ -456,14 +458,21 @@ SendableDataBlockStream GpuPipeTransform::execute() {
   GpuContextRef gpu = ctx_->gpu();
   ITableRef table = ctx_->get_table(db_, table_);
   // the source emits one device block per contiguous run of this pipe's partitions
-  GpuOptions saved = ctx_->options;
-  ctx_->options.block_rows = 0;
-  SendableDataBlockStream source = table->read(ctx_, partitions_);
-  ctx_->options = saved;
-
   FunctionRef pred = predicate_ ? predicate_->to_function() : nullptr;
   std::vector<FunctionRef> funcs;
   for (const auto &e : exprs_) funcs.push_back(e.to_function());
+  // per-block Sum folding of the reference is observable when a WHERE clause can empty a block
+  bool track_blocks = false;
+  if (is_aggregate_ && pred && ctx_->options.block_quirks) {
+    std::vector<const Function *> ls;
+    for (auto &f : funcs) collect_leaves(*f, &ls);
+    for (const Function *l : ls) track_blocks = track_blocks || l->op == FQ_AGG_SUM;
+  }
+  GpuOptions saved = ctx_->options;
+  ctx_->options.block_rows = 0;
+  ctx_->options.align_runs = track_blocks;
+  SendableDataBlockStream source = table->read(ctx_, partitions_);
+  ctx_->options = saved;
 
   if (is_aggregate_) {
     PipeRef pipe;
@@ -482,7 +491,8 @@ SendableDataBlockStream GpuPipeTransform::execute() {
       }
       BoundSource bs;
       bind_source(lw, *block, &bs);
-      gpu->check(fq_pipe_launch_aggregate(gpu->raw(), pipe->pipe, &bs.src, launches > 0 ? FQ_RUN_ACCUMULATE : 0, gpu->stream));
+      gpu->check(fq_pipe_launch_aggregate(gpu->raw(), pipe->pipe, &bs.src,
+                                          (launches > 0 ? FQ_RUN_ACCUMULATE : 0) | (track_blocks ? FQ_RUN_BLOCK_STATS : 0), gpu->stream));
       launches++;
     }
     std::map<const Function *, DataValue> leaf_state;
@@ -492,6 +502,13 @@ SendableDataBlockStream GpuPipeTransform::execute() {
       int32_t n = 0;
       uint64_t sel = 0;
       gpu->check(fq_pipe_fetch_aggregate(gpu->raw(), pipe->pipe, st.data(), (int32_t)st.size(), &n, &sel));
+      if (track_blocks) {
+        uint64_t blocks = 0, empty = 0;
+        gpu->check(fq_pipe_fetch_block_stats(gpu->raw(), pipe->pipe, &blocks, &empty));
+        // function_aggregator.rs:88-97: state = state + arrow_sum(block); the second block onwards goes through
+        // DataValue::to_array, which refuses Type(None) (data_value.rs:104-109) — on either side of the add
+        if (blocks >= 2 && empty > 0) throw FuseQueryError::internal("DataValue to array cannot be NONE NULL");
+      }
       std::vector<int32_t> nodes(leaves.size() + 1);
       int32_t nn = 0;
       gpu->check(fq_pipe_aggregator_nodes(gpu->raw(), pipe->pipe, nodes.data(), (int32_t)nodes.size(), &nn));

@@ -49,7 +49,9 @@ typedef signed char fq_i8;
 #define FQ_MAP_UNROLL 4
 #endif
 
-#define FQ_STATE_HDR 4        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned
+#define FQ_STATE_HDR 6        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned,
+                              // [4] reference (10 000-row) blocks seen, [5] of which had no selected row
+#define FQ_REF_BLOCK_ROWS 10000ull   // NumbersStream block size, datasources/system/numbers_stream.rs:29
 #define FQ_MAX_WARPS 32
 
 // Kernel parameter block (one struct for every kernel so the host launch path is uniform).
@@ -62,6 +64,7 @@ struct fq_launch_params {
   fq_u64 *state;         // [FQ_STATE_HDR + Q::NSLOTS] running state of the pipe
   fq_u32 *ticket;
   fq_u32 accumulate;
+  fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   // select / map
   void *outs[8];
   fq_u64 capacity;       // rows written are those with rank < capacity (min(limit, capacity) on the host)
@@ -281,6 +284,38 @@ __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &ns
 }
 
 // ---------------------------------------------------------------------------------------------
+// Reference-block tracking.  The reference folds Sum per 10 000-row block: a block in which the WHERE
+// clause keeps no row yields arrow sum(empty) = None, and `state + None` fails ("DataValue to array cannot be NONE",
+// datavalues/data_value.rs:104-109 via data_value_arithmetic.rs:19-24).  To be able to report the same outcome the
+// fused scan records which reference blocks saw at least one selected row: one bit per block, warp-aggregated.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fq_mark_one(fq_u32 *hit, fq_u64 blk) {
+  fq_u32 *w = hit + (blk >> 5);
+  const fq_u32 bit = 1u << (blk & 31);
+  if (!(*(volatile fq_u32 *)w & bit)) atomicOr(w, bit);
+}
+// per-lane form (divergent callers): `kept` has bit v set when row row0 + v was selected
+template <int V> __device__ __forceinline__ void fq_mark_blocks_lane(const fq_launch_params &p, fq_u64 row0, fq_u32 kept) {
+  if (!kept) return;
+  const fq_u64 first = row0 / FQ_REF_BLOCK_ROWS, last = (row0 + V - 1) / FQ_REF_BLOCK_ROWS;
+  if (first == last) { fq_mark_one(p.block_hit, first); return; }
+#pragma unroll
+  for (int v = 0; v < V; v++)
+    if ((kept >> v) & 1u) fq_mark_one(p.block_hit, (row0 + v) / FQ_REF_BLOCK_ROWS);
+}
+// whole-warp form: the lanes hold 32 consecutive vector groups (32 * V consecutive rows)
+template <int V> __device__ __forceinline__ void fq_mark_blocks_warp(const fq_launch_params &p, fq_u64 row0, fq_u32 kept) {
+  if (!__any_sync(0xffffffffu, kept != 0)) return;
+  const fq_u64 first = __shfl_sync(0xffffffffu, row0, 0) / FQ_REF_BLOCK_ROWS;
+  const fq_u64 last = (__shfl_sync(0xffffffffu, row0, 31) + V - 1) / FQ_REF_BLOCK_ROWS;
+  if (first == last) {
+    if ((threadIdx.x & 31) == 0) fq_mark_one(p.block_hit, first);
+  } else {
+    fq_mark_blocks_lane<V>(p, row0, kept);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fq_agg_kernel — single-pass multi-aggregate scan.
 //
 // Grid: persistent, (SM count x resident CTAs) blocks.  Each CTA walks contiguous chunks of
@@ -294,6 +329,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   constexpr int S = FQ_STATE_HDR + Q::NSLOTS;
   __shared__ fq_u64 sm[FQ_MAX_WARPS][S];
   __shared__ fq_u32 s_last;
+  __shared__ fq_u32 s_hits;
 
   typename Q::Acc acc;
   Q::init(acc);
@@ -309,9 +345,14 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++)
+    for (int u = 0; u < UNROLL; u++) {
+      fq_u32 kept = 0;
 #pragma unroll
-      for (int v = 0; v < V; v++) Q::consume(acc, rows[u], v, nsel, err);
+      for (int v = 0; v < V; v++) kept |= (Q::consume(acc, rows[u], v, nsel, err) ? 1u : 0u) << v;
+      if constexpr (Q::TRACK_BLOCKS) {
+        if (p.block_hit) fq_mark_blocks_warp<V>(p, (g0 + (fq_u64)u * blockDim.x) * V, kept);
+      }
+    }
   }
   // remainder groups (< one chunk) and the scalar tail (< V rows), spread over the whole grid
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,13 +360,20 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
+    fq_u32 kept = 0;
 #pragma unroll
-    for (int v = 0; v < V; v++) Q::consume(acc, r, v, nsel, err);
+    for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
+    if constexpr (Q::TRACK_BLOCKS) {
+      if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
+    }
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
-    Q::consume(acc, r, 0, nsel, err);
+    const bool kept = Q::consume(acc, r, 0, nsel, err);
+    if constexpr (Q::TRACK_BLOCKS) {
+      if (p.block_hit && kept) fq_mark_one(p.block_hit, row / FQ_REF_BLOCK_ROWS);
+    }
   }
 
   fq_block_reduce<Q>(acc, nsel, err, sm);
@@ -336,9 +384,26 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
     Q::store(acc, out + FQ_STATE_HDR);
     __threadfence();
     s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    s_hits = 0;
   }
   __syncthreads();
   if (!s_last) return;
+
+  // reference blocks of this launch that saw a selected row
+  fq_u64 ref_blocks = 0;
+  if constexpr (Q::TRACK_BLOCKS) {
+    if (p.block_hit) {
+      ref_blocks = (p.n_rows + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS;
+      const fq_u64 words = (ref_blocks + 31) / 32;
+      fq_u32 h = 0;
+      for (fq_u64 w = threadIdx.x; w < words; w += blockDim.x) {
+        fq_u32 x;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(x) : "l"(p.block_hit + w));
+        h += __popc(x);
+      }
+      if (h) atomicAdd(&s_hits, h);
+    }
+  }
 
   // last CTA: fold every CTA's partial, then fold into (or restart) the running state
   __threadfence();
@@ -360,6 +425,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   if (threadIdx.x == 0) {
     if (!Q::HAS_PRED) nsel = p.n_rows;
     fq_u64 folded = 1, scanned = p.n_rows;
+    fq_u64 blocks = ref_blocks, empty_blocks = ref_blocks - s_hits;   // s_hits is complete: fq_block_reduce synchronised the CTA
     if (p.accumulate) {
       typename Q::Acc o;
       Q::unpack(o, p.state + FQ_STATE_HDR);
@@ -368,11 +434,15 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
       err |= (fq_u32)p.state[1];
       folded += p.state[2];
       scanned += p.state[3];
+      blocks += p.state[4];
+      empty_blocks += p.state[5];
     }
     p.state[0] = nsel;
     p.state[1] = err;
     p.state[2] = folded;
     p.state[3] = scanned;
+    p.state[4] = blocks;
+    p.state[5] = empty_blocks;
     Q::store(acc, p.state + FQ_STATE_HDR);
     *p.ticket = 0;
   }

@@ -186,9 +186,11 @@ fq_status fq_pipe_expr_dtype(fq_ctx *ctx, const fq_pipe *pipe, int32_t i, fq_dty
 /* ---- aggregate pipes: Function::accumulate over a whole shard (function_aggregator.rs:57-100) ----
  * The device keeps one running state per Aggregator leaf.  FQ_RUN_ACCUMULATE folds this launch into
  * the running state (successive blocks of one partition); without it the state restarts from Null.
- * FQ_RUN_BLOCK_QUIRKS additionally tracks what the reference's 10 000-row block loop would have
- * seen (an empty post-filter block poisons Sum) — reported by fetch, never applied silently. */
-enum { FQ_RUN_ACCUMULATE = 1, FQ_RUN_LIMIT_EARLY_EXIT = 2 };
+ * FQ_RUN_BLOCK_STATS additionally records, for pipes with a WHERE predicate and a Sum leaf, how many of
+ * the reference's 10 000-row blocks (numbers_stream.rs:29, counted from row 0 of each launch) kept no row:
+ * the reference folds Sum per block and an empty block poisons its state.  The counts are
+ * reported by fq_pipe_fetch_block_stats; what to do with them is the caller's decision. */
+enum { FQ_RUN_ACCUMULATE = 1, FQ_RUN_LIMIT_EARLY_EXIT = 2, FQ_RUN_BLOCK_STATS = 4 };
 
 fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, uint32_t flags, void *stream);
 /* Waits for the last launch and returns, for each Aggregator leaf in node-index order, the state
@@ -197,10 +199,15 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
  * post-filter row count.  A zero divisor anywhere in the scanned rows yields FQ_ERR_DIVIDE_BY_ZERO. */
 fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
                                   uint64_t *rows_selected);
+/* after fq_pipe_fetch_aggregate: reference blocks scanned / left empty by the predicate over the launches folded so far
+ * (both 0 when the pipe has no predicate + Sum leaf or FQ_RUN_BLOCK_STATS was not set) */
+fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks, uint64_t *empty_blocks);
 /* node indexes of the Aggregator leaves, in the order fetch reports them */
 fq_status fq_pipe_aggregator_nodes(fq_ctx *ctx, const fq_pipe *pipe, int32_t *nodes, int32_t cap, int32_t *n);
-/* device address of the raw running state (8-byte slots: rows_selected, error bits, then one slot per
- * leaf) for collectives that merge states on the device (ncclAllGather of 8*(2+n) bytes) */
+/* device address of the raw running state: FQ_STATE_HEADER_SLOTS 8-byte header slots (rows selected, error bits,
+ * launches folded, rows scanned, reference blocks, empty reference blocks) then one slot per leaf — for collectives
+ * that merge states on the device (ncclAllGather of n_bytes) */
+#define FQ_STATE_HEADER_SLOTS 6
 fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes);
 
 /* ---- projection pipes: filter_record_batch + projection (+ LimitStream) in one pass ----

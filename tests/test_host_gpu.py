@@ -381,3 +381,40 @@ def test_memory_table_sql_matches_oracle(gpu):
         want = o.run_query(["(col k)", "(alias vw (* (col v) (col w)))"], table=table, predicate="(= (col w) (u64 7))", limit=20,
                            worker_threads=workers, tail_quirk=False)
         assert rows_of(blocks) == want.rows() and len(want.rows()) == 20
+
+
+# ---------------------------------------------------------------------------------------------
+# with a WHERE clause the reference folds Sum per 10 000-row block and an emptied block poisons it
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sql_where,pred,expect_error", [
+    ("number >= 60000", f"(>= {NUM} (u64 60000))", True),                 # partitions 0..2 have only empty blocks
+    ("number/10000*10000 = number", f"(= (* (/ {NUM} (u64 10000)) (u64 10000)) {NUM})", False),   # one row kept in every block
+    ("number/20000*20000 = number", f"(= (* (/ {NUM} (u64 20000)) (u64 20000)) {NUM})", True),    # every other block empty
+    ("number < 5", f"(< {NUM} (u64 5))", True),
+])
+def test_sum_with_where_reproduces_reference_block_poisoning(gpu, sql_where, pred, expect_error):
+    n = 160_000   # 8 partitions of 2 blocks
+    sql = f"select sum(number), count(number) from system.numbers_mt({n}) where {sql_where}"
+    exprs = [f"(sum {NUM})", f"(count {NUM})"]
+    msg = "Internal Error: DataValue to array cannot be NONE NULL"
+    for workers in (0, 1, 2):
+        try:
+            want = o.run_query(exprs, total=n, predicate=pred, is_aggregate=True, worker_threads=workers).rows()
+            oerr = None
+        except o.OracleError as e:
+            want, oerr = None, str(e)
+        assert (oerr == msg) == expect_error
+        for opts in (dict(fuse=True), dict(fuse=True, generated=True), dict(fuse=False, block_rows=10000)):
+            ctx = make_ctx(gpu, workers, **opts)
+            if expect_error:
+                with pytest.raises(h.FuseQueryError) as e:
+                    h.execute_sql(ctx, sql)
+                assert str(e.value) == msg
+            else:
+                assert rows_of(h.execute_sql(ctx, sql)) == want
+    # block_quirks = False: the mathematically merged answer instead of the reference's failure
+    ctx = make_ctx(gpu, 1, block_quirks=False)
+    x = np.arange(n, dtype=np.uint64)
+    keep = {"number >= 60000": x >= 60000, "number/10000*10000 = number": x % 10000 == 0, "number/20000*20000 = number": x % 20000 == 0,
+            "number < 5": x < 5}[sql_where]
+    assert rows_of(h.execute_sql(ctx, sql)) == [(int(x[keep].sum()), int(keep.sum()))]
