@@ -390,6 +390,15 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       s += fmt("    ((%s *)p.outs[%d])[pos] = ", t == FQ_BOOL ? "fq_u8" : ctype(t), e) + g.emit(d.exprs[e]) + ";\n";
     }
     s += "  }\n";
+    // whole vector group at once (projection without a filter): V values per output column, one vector store each
+    s += "  __device__ static __forceinline__ void emit_vec(const Rows &r, const fq_launch_params &p, fq_u64 row0, fq_u32 &err) {\n";
+    for (int e = 0; e < d.n_exprs; e++) {
+      fq_dtype t = out->expr_dtypes[e];
+      const char *T = t == FQ_BOOL ? "fq_u8" : ctype(t);
+      s += fmt("    { %s o[V];\n#pragma unroll\n      for (int v = 0; v < V; v++) o[v] = ", T) + g.emit(d.exprs[e]) +
+           fmt(";\n      fq_store_vec<%s, V>(p.outs[%d], row0, o); }\n", T, e);
+    }
+    s += "  }\n";
   }
   s += "};\n";
   if (d.kind == FQ_PIPE_AGGREGATE) {

@@ -140,7 +140,42 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
-// ---------------------------------------------------------------------------------------------
+// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
+// `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
+template <class T, int V>
+__device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
+  constexpr int BYTES = V * (int)sizeof(T);
+  char *p = (char *)base + first * sizeof(T);
+  if constexpr (BYTES >= 16) {
+    union { fq_b16 q[BYTES / 16]; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+#pragma unroll
+    for (int k = 0; k < BYTES / 16; k++)
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16 * k), "r"(u.q[k].x), "r"(u.q[k].y), "r"(u.q[k].z), "r"(u.q[k].w) : "memory");
+  } else if constexpr (BYTES == 8) {
+    union { fq_u64 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u64 *)p = u.q;
+  } else if constexpr (BYTES == 4) {
+    union { fq_u32 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u32 *)p = u.q;
+  } else if constexpr (BYTES == 2) {
+    union { fq_u16 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u16 *)p = u.q;
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k++) ((T *)p)[k] = src[k];
+  }
+}
+
+// -----------------------------------------------------------------------------)FQSK"
+R"FQSK(----------------
 // arithmetic helpers used by generated code (semantics of arrow 2.0 as the reference calls it)
 // ---------------------------------------------------------------------------------------------
 template <class T> struct fq_traits;
@@ -159,8 +194,7 @@ FQ_TRAITS(fq_u8, fq_u8, 0, 0, (fq_u8)0, (fq_u8)255)
 FQ_TRAITS(fq_u16, fq_u16, 0, 0, (fq_u16)0, (fq_u16)65535)
 FQ_TRAITS(fq_u32, fq_u32, 0, 0, 0u, 4294967295u)
 FQ_TRAITS(fq_u64, fq_u64, 0, 0, 0ull, 18446744073709551615ull)
-FQ_TRAITS(float, float, 1, 1, -__int_as_float()FQSK"
-R"FQSK(0x7f800000), __int_as_float(0x7f800000))
+FQ_TRAITS(float, float, 1, 1, -__int_as_float(0x7f800000), __int_as_float(0x7f800000))
 FQ_TRAITS(double, double, 1, 1, -__longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0x7ff0000000000000ll))
 #undef FQ_TRAITS
 
@@ -288,7 +322,8 @@ __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &ns
 // ---------------------------------------------------------------------------------------------
 // Reference-block tracking.  The reference folds Sum per 10 000-row block: a block in which the WHERE
 // clause keeps no row yields arrow sum(empty) = None, and `state + None` fails ("DataValue to array cannot be NONE",
-// datavalues/data_value.rs:104-109 via data_value_arithmetic.rs:19-24).  To be able to report the same outcome the
+// datavalues)FQSK"
+R"FQSK(/data_value.rs:104-109 via data_value_arithmetic.rs:19-24).  To be able to report the same outcome the
 // fused scan records which reference blocks saw at least one selected row: one bit per block, warp-aggregated.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fq_mark_one(fq_u32 *hit, fq_u64 blk) {
@@ -308,8 +343,7 @@ template <int V> __device__ __forceinline__ void fq_mark_blocks_lane(const fq_la
 // whole-warp form: the lanes hold 32 consecutive vector groups (32 * V consecutive rows)
 template <int V> __device__ __forceinline__ void fq_mark_blocks_warp(const fq_launch_params &p, fq_u64 row0, fq_u32 kept) {
   if (!__any_sync(0xffffffffu, kept != 0)) return;
-  const fq_u64 first = __shfl_syn)FQSK"
-R"FQSK(c(0xffffffffu, row0, 0) / FQ_REF_BLOCK_ROWS;
+  const fq_u64 first = __shfl_sync(0xffffffffu, row0, 0) / FQ_REF_BLOCK_ROWS;
   const fq_u64 last = (__shfl_sync(0xffffffffu, row0, 31) + V - 1) / FQ_REF_BLOCK_ROWS;
   if (first == last) {
     if ((threadIdx.x & 31) == 0) fq_mark_one(p.block_hit, first);
@@ -467,7 +501,8 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
 //                     of the lower-lane mask and write each selected row once, projected at scatter time.
 // The look-back of segment k (a chain of global round trips that also waits for the slowest predecessor)
 // overlaps the workers' pass 1 of segment k + 1: named barriers FULL[k&1] (workers arrive, scan waits) and
-// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
+// )FQSK"
+R"FQSK(DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
 // warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back per 16-KB tile cannot keep up
 // with HBM at all (0.7 TB/s measured).
 // Rows beyond min(limit, capacity) are counted, not written.  Early exit: the segment that reaches `stop_after`
@@ -483,8 +518,7 @@ __device__ __forceinline__ void fq_bar_sync(int id, int count) { asm volatile("b
 __device__ __forceinline__ void fq_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Tile access is split in two so that a tile's loads can be in flight while the previous tile is ranked:
-// fq_tile_load only issues the loads (full tiles vectorised, the ragged last one row by row), fq_tile)FQSK"
-R"FQSK(_pred
+// fq_tile_load only issues the loads (full tiles vectorised, the ragged last one row by row), fq_tile_pred
 // evaluates the predicate on rows that exist: bit (u * V + v) of the returned mask is set for kept rows.
 // `wthreads` = worker threads of the CTA (the tile geometry ignores the scan warp).
 template <class Q, int U>
@@ -628,7 +662,8 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     for (int k = 0;; k++) {
       const int b = k % FQ_SEL_RING;
       fq_bar_sync(FQ_BAR_FULL + b, allthreads);
-      const fq_u64 seg = s_seg[k & 3];
+     )FQSK"
+R"FQSK( const fq_u64 seg = s_seg[k & 3];
       if (!(seg < n_seg) || s_stop[k & 3]) break;
       // counts -> exclusive offsets in (tile, warp) order; segment total
       const int entries = SEG * nwarps;
@@ -662,8 +697,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
         if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_AGG | (fq_u64)tot);
         fq_i64 look = (fq_i64)seg - 1;
         for (;;) {
-          // FQ_SEL_LOOK * 32 predecesso)FQSK"
-R"FQSK(rs per poll: lane l inspects look - 32 * j - l for j = 0 .. FQ_SEL_LOOK - 1
+          // FQ_SEL_LOOK * 32 predecessors per poll: lane l inspects look - 32 * j - l for j = 0 .. FQ_SEL_LOOK - 1
           fq_u64 st[FQ_SEL_LOOK];
           bool ready;
           do {
@@ -799,9 +833,13 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const fq_u64 row0 = (g0 + (fq_u64)u * blockDim.x) * V;
+      if (row0 + V <= p.capacity) {
+        Q::emit_vec(rows[u], p, row0, err);   // one vector store per output column
+      } else {
 #pragma unroll
-      for (int v = 0; v < V; v++)
-        if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+        for (int v = 0; v < V; v++)
+          if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+      }
     }
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -809,9 +847,13 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
+    if (g * V + V <= p.capacity) {
+      Q::emit_vec(r, p, g * V, err);
+    } else {
 #pragma unroll
-    for (int v = 0; v < V; v++)
-      if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
+      for (int v = 0; v < V; v++)
+        if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
+    }
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;

@@ -139,6 +139,40 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
+// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
+// `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
+template <class T, int V>
+__device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
+  constexpr int BYTES = V * (int)sizeof(T);
+  char *p = (char *)base + first * sizeof(T);
+  if constexpr (BYTES >= 16) {
+    union { fq_b16 q[BYTES / 16]; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+#pragma unroll
+    for (int k = 0; k < BYTES / 16; k++)
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16 * k), "r"(u.q[k].x), "r"(u.q[k].y), "r"(u.q[k].z), "r"(u.q[k].w) : "memory");
+  } else if constexpr (BYTES == 8) {
+    union { fq_u64 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u64 *)p = u.q;
+  } else if constexpr (BYTES == 4) {
+    union { fq_u32 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u32 *)p = u.q;
+  } else if constexpr (BYTES == 2) {
+    union { fq_u16 q; T t[V]; } u;
+#pragma unroll
+    for (int k = 0; k < V; k++) u.t[k] = src[k];
+    *(fq_u16 *)p = u.q;
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k++) ((T *)p)[k] = src[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // arithmetic helpers used by generated code (semantics of arrow 2.0 as the reference calls it)
 // ---------------------------------------------------------------------------------------------
@@ -794,9 +828,13 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const fq_u64 row0 = (g0 + (fq_u64)u * blockDim.x) * V;
+      if (row0 + V <= p.capacity) {
+        Q::emit_vec(rows[u], p, row0, err);   // one vector store per output column
+      } else {
 #pragma unroll
-      for (int v = 0; v < V; v++)
-        if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+        for (int v = 0; v < V; v++)
+          if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+      }
     }
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -804,9 +842,13 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
+    if (g * V + V <= p.capacity) {
+      Q::emit_vec(r, p, g * V, err);
+    } else {
 #pragma unroll
-    for (int v = 0; v < V; v++)
-      if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
+      for (int v = 0; v < V; v++)
+        if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
+    }
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
