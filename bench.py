@@ -49,6 +49,13 @@ README_QUERIES = {
 }
 
 
+def agg_kernel_name(generated: bool) -> str:
+    v = os.environ.get("FQ_AGG_VARIANT", "tma")
+    if generated or v != "tma":
+        return "fq_agg_kernel (fqk_*_agg_%s): LDG.128 streaming" % ("u8" if v == "u8" else "u4")
+    return "fq_agg_tma_kernel (fqk_*_agg_tma): cp.async.bulk staged, 4 x 32 KB ring per SM"
+
+
 def ncu_traffic(rows_per_launch: int, generated: bool):
     """dram__bytes_read.sum + dram__bytes_write.sum of the aggregate kernel from the committed ncu --set full capture of THIS
     workload (profiles/r01_traffic_headline_1e10.json); None when the launch differs from the captured one."""
@@ -351,7 +358,7 @@ def run_ours(args):
                        "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
             "hbm_gb_per_s": row_bytes * total * args.steps / secs / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n, generated),
-                         "kernel": "fq_agg_kernel (fqk_*_agg_u4)", "kernel_ms": kernel_ms, "peak_source": which,
+                         "kernel": agg_kernel_name(generated), "kernel_ms": kernel_ms, "peak_source": which,
                          "algorithmic_bytes_per_launch": row_bytes * n},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "sql_e2e": sql_e2e,
         }

@@ -82,6 +82,14 @@ struct Gen {
   std::string err;
   int status = FQ_OK;
   bool const_div0 = false;
+  int quiet_depth = 0;
+
+  bool trivial(int i) const {
+    if (i < 0 || i >= d.n_nodes) return false;
+    const fq_expr_node &n = d.nodes[i];
+    if (n.kind == FQ_EXPR_FIELD || n.kind == FQ_EXPR_CONSTANT) return true;
+    return n.kind == FQ_EXPR_ALIAS && trivial(n.left);
+  }
 
   explicit Gen(const fq_pipe_desc &desc) : d(desc), ty(desc.n_nodes, FQ_NULL), visited(desc.n_nodes, 0), scalar(desc.n_nodes, 0) {}
 
@@ -110,7 +118,7 @@ struct Gen {
         if (!is_numeric(t) && t != FQ_BOOL)
           return fail(FQ_ERR_UNSUPPORTED, fmt("Unsupported on the device path: column of type %s", dtype_name(t)));
         ty[i] = t;
-        used_cols.insert(n->column);
+        if (quiet_depth == 0) used_cols.insert(n->column);
         return true;
       }
       case FQ_EXPR_CONSTANT:
@@ -120,11 +128,18 @@ struct Gen {
         scalar[i] = 1;
         return true;
       case FQ_EXPR_ALIAS:
-      case FQ_EXPR_AGGREGATOR:
-        if (!infer(n->left, depth + 1)) return false;
+      case FQ_EXPR_AGGREGATOR: {
+        // Count(arg) evaluates and discards its argument (function_aggregator.rs:58-66).  A bare column or literal cannot
+        // fail, so nothing has to be read for it: the column is typed but not marked as used.
+        const bool quiet = n->kind == FQ_EXPR_AGGREGATOR && n->op == FQ_AGG_COUNT && trivial(n->left) && d.kind == FQ_PIPE_AGGREGATE;
+        if (quiet) quiet_depth++;
+        const bool ok = infer(n->left, depth + 1);
+        if (quiet) quiet_depth--;
+        if (!ok) return false;
         ty[i] = ty[n->left];
         scalar[i] = scalar[n->left];
         return true;
+      }
       case FQ_EXPR_ARITHMETIC: {
         if (!infer(n->left, depth + 1) || !infer(n->right, depth + 1)) return false;
         fq_dtype t;
@@ -341,6 +356,27 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   s += "  __device__ static __forceinline__ void copy_row(Rows &dst, int v, const Rows &one) {\n";
   for (int c : g.used_cols) s += fmt("    dst.c%d[v] = one.c%d[0];\n", c, c);
   s += "  }\n";
+  // staged (bulk-copy) access: every referenced column must be materialised
+  out->tma_ok = !g.used_cols.empty() && !(d.generated && g.used_cols.count(0));
+  s += fmt("  static constexpr int ROW_BYTES = %d;\n", out->row_bytes);
+  if (out->tma_ok) {
+    s += "  __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
+    int prefix = 0;
+    for (int c : g.used_cols) {
+      int w = (int)dtype_size(g.col_dtype(c));
+      s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
+      prefix += w;
+    }
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void load_smem(Rows &r, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group) {\n";
+    prefix = 0;
+    for (int c : g.used_cols) {
+      int w = (int)dtype_size(g.col_dtype(c));
+      s += fmt("    fq_lds_vec<%s, V>(r.c%d, stage + (size_t)tile_rows * %d, group);\n", ctype(g.col_dtype(c)), c, prefix);
+      prefix += w;
+    }
+    s += "  }\n";
+  }
   s += "  __device__ static __forceinline__ bool pred(const Rows &r, int v, fq_u32 &err) {\n";
   s += "    return " + (out->has_pred ? g.emit(d.predicate) : std::string("true")) + ";\n  }\n";
 
@@ -363,7 +399,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         case FQ_AGG_MIN: s += fmt("    a.a%d = fq_min<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
         case FQ_AGG_MAX: s += fmt("    a.a%d = fq_max<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
         default:  // Count evaluates (and discards) its argument, function_aggregator.rs:58-66: keep its error checks only
-          s += "    { auto unused = " + arg + "; (void)unused; }\n";
+          if (!g.trivial(an.left)) s += "    { auto unused = " + arg + "; (void)unused; }\n";
       }
     }
     s += "    return true;\n  }\n";
@@ -403,6 +439,8 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   s += "};\n";
   if (d.kind == FQ_PIPE_AGGREGATE) {
     s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS) fqk_@_agg_u4(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 4>(p); }\n";
+    if (out->tma_ok)
+      s += "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_agg_tma(const __grid_constant__ fq_launch_params p) { fq_agg_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n";
     s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n";
   } else if (out->has_pred) {
     s += "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS + 32, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, fq_sel_shape<Q_@::V>::U, fq_sel_shape<Q_@::V>::SEG>(p); }\n";

@@ -25,6 +25,7 @@ struct Generated {
   // select expressions
   std::vector<fq_dtype> expr_dtypes;    // Function::return_type
   std::vector<fq_dtype> node_dtypes;    // per node, FQ_NULL when not reachable
+  bool tma_ok = false;                  // every referenced column is materialised: the bulk-copy staged kernel exists
   bool track_blocks = false;            // aggregate pipe with a predicate and a Sum leaf: reference-block tracking compiled in
   bool const_divide_by_zero = false;    // a literal zero divisor is evaluated for every scanned row
 };

@@ -23,6 +23,10 @@
 #include "kernels/fq_skeleton.cuh"
 #include "generated/skeleton_embed.h"  // static const char fq_skeleton_src[]
 
+#ifndef FQ_AGG_DEFAULT_VARIANT
+#define FQ_AGG_DEFAULT_VARIANT "tma"   // bulk-copy staged kernel when every referenced column is materialised, else u4
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // precompiled kernels (generated/aot_kernels.cu)
 // ---------------------------------------------------------------------------------------------
@@ -62,6 +66,7 @@ struct Driver {
   CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **,
                               void **) = nullptr;
   CUresult_ (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction_, int, size_t) = nullptr;
+  CUresult_ (*cuFuncSetAttribute)(CUfunction_, int, int) = nullptr;
   CUresult_ (*cuGetErrorString)(CUresult_, const char **) = nullptr;
   std::string why;
   bool load() {
@@ -70,7 +75,7 @@ struct Driver {
     if (!h) { why = dlerror(); return false; }
 #define SYM(n) *(void **)(&n) = dlsym(h, #n)
     SYM(cuModuleLoadData); SYM(cuModuleGetFunction); SYM(cuModuleUnload); SYM(cuLaunchKernel);
-    SYM(cuOccupancyMaxActiveBlocksPerMultiprocessor); SYM(cuGetErrorString);
+    SYM(cuOccupancyMaxActiveBlocksPerMultiprocessor); SYM(cuGetErrorString); SYM(cuFuncSetAttribute);
 #undef SYM
     if (!cuModuleLoadData || !cuModuleGetFunction || !cuLaunchKernel || !cuOccupancyMaxActiveBlocksPerMultiprocessor) {
       why = "libcuda.so.1 lacks required symbols";
@@ -121,6 +126,8 @@ std::mutex g_mu;
 // overrides (kernel tuning experiments only) force the NVRTC path so kernel and host agree.
 struct Shapes {
   int agg_threads = FQ_AGG_THREADS, agg_min_blocks = FQ_AGG_MIN_BLOCKS, agg_min_blocks_u8 = FQ_AGG_MIN_BLOCKS_U8;
+  int tma_threads = FQ_TMA_THREADS, tma_unroll = FQ_TMA_UNROLL, tma_stages = FQ_TMA_STAGES, tma_min_blocks = FQ_TMA_MIN_BLOCKS;
+  int tma_stages_env = 0;   // FQ_TUNE_TMA_STAGES: ring depth override (<= FQ_TMA_STAGES)
   int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
   int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
   bool tuned = false;
@@ -131,15 +138,19 @@ struct Shapes {
     };
     env("FQ_TUNE_AGG_THREADS", &agg_threads); env("FQ_TUNE_AGG_MIN_BLOCKS", &agg_min_blocks);
     env("FQ_TUNE_AGG_MIN_BLOCKS_U8", &agg_min_blocks_u8);
+    env("FQ_TUNE_TMA_THREADS", &tma_threads); env("FQ_TUNE_TMA_UNROLL", &tma_unroll);
+    if (getenv("FQ_TUNE_TMA_STAGES") && atoi(getenv("FQ_TUNE_TMA_STAGES")) > 0) tma_stages_env = atoi(getenv("FQ_TUNE_TMA_STAGES"));
+    env("FQ_TUNE_TMA_MIN_BLOCKS", &tma_min_blocks);
     env("FQ_TUNE_SEL_THREADS", &sel_threads); env("FQ_TUNE_SEL_MIN_BLOCKS", &sel_min_blocks); env("FQ_TUNE_SEL_UNROLL", &sel_unroll); env("FQ_TUNE_SEL_SEG", &sel_seg); env("FQ_TUNE_SEL_LOOK", &sel_look);
     env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
   }
   std::string defines() const {
-    char b[768];
+    char b[1024];
     snprintf(b, sizeof b,
-             "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_SEL_THREADS %d\n"
+             "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_TMA_THREADS %d\n"
+             "#define FQ_TMA_UNROLL %d\n#define FQ_TMA_STAGES %d\n#define FQ_TMA_MIN_BLOCKS %d\n#define FQ_SEL_THREADS %d\n"
              "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
-             agg_threads, agg_min_blocks, agg_min_blocks_u8, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
+             agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
     return b;
   }
 };
@@ -153,6 +164,7 @@ struct Kernel {
   CUfunction_ jit = nullptr;   // NVRTC-built (cuLaunchKernel)
   int threads = 256;
   int blocks_per_sm = 1;
+  unsigned smem = 0;           // dynamic shared memory per CTA
   bool valid() const { return aot || jit; }
 };
 
@@ -181,7 +193,8 @@ struct fq_column {
 
 struct fq_pipe {
   fq::Generated gen;
-  Kernel k_agg_u4, k_agg_u8, k_select, k_map;
+  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_map;
+  unsigned tma_stages = 0;
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
   uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
@@ -252,20 +265,27 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m) {
   return FQ_OK;
 }
 
-fq_status resolve_kernel(Module *m, const std::string &name, int threads, Kernel *out) {
+fq_status resolve_kernel(Module *m, const std::string &name, int threads, Kernel *out, unsigned smem = 0) {
   auto it = m->kernels.find(name);
   if (it != m->kernels.end()) { *out = it->second; return FQ_OK; }
   Kernel k;
   k.threads = threads;
+  k.smem = smem;
   if (m->precompiled) {
     for (int i = 0; i < fq_aot_count; i++)
       if (name == fq_aot_table[i].name) k.aot = fq_aot_table[i].fn;
     if (!k.aot) return set_err(FQ_ERR_INTERNAL, "Internal Error: precompiled kernel %s missing", name.c_str());
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.aot, threads, 0));
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k.aot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.aot, threads, smem));
   } else {
     CUresult_ cr = g_drv.cuModuleGetFunction(&k.jit, m->mod, name.c_str());
     if (cr) return set_err(FQ_ERR_CUDA, "cuModuleGetFunction(%s): %s", name.c_str(), g_drv.err(cr).c_str());
-    cr = g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.jit, threads, 0);
+    if (smem > 48 * 1024) {
+      if (!g_drv.cuFuncSetAttribute) return set_err(FQ_ERR_CUDA, "cuFuncSetAttribute unavailable");
+      cr = g_drv.cuFuncSetAttribute(k.jit, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
+      if (cr) return set_err(FQ_ERR_CUDA, "cuFuncSetAttribute(%s): %s", name.c_str(), g_drv.err(cr).c_str());
+    }
+    cr = g_drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k.jit, threads, smem);
     if (cr) return set_err(FQ_ERR_CUDA, "cuOccupancy: %s", g_drv.err(cr).c_str());
   }
   if (k.blocks_per_sm < 1) k.blocks_per_sm = 1;
@@ -277,9 +297,9 @@ fq_status resolve_kernel(Module *m, const std::string &name, int threads, Kernel
 fq_status launch(fq_ctx *ctx, const Kernel &k, unsigned grid, const fq_launch_params &p, void *stream) {
   void *args[] = {(void *)&p};
   if (k.aot) {
-    CUDA_TRY(cudaLaunchKernel(k.aot, dim3(grid), dim3(k.threads), args, 0, (cudaStream_t)stream));
+    CUDA_TRY(cudaLaunchKernel(k.aot, dim3(grid), dim3(k.threads), args, k.smem, (cudaStream_t)stream));
   } else {
-    CUresult_ cr = g_drv.cuLaunchKernel(k.jit, grid, 1, 1, (unsigned)k.threads, 1, 1, 0, stream, args, nullptr);
+    CUresult_ cr = g_drv.cuLaunchKernel(k.jit, grid, 1, 1, (unsigned)k.threads, 1, 1, k.smem, stream, args, nullptr);
     if (cr) return set_err(FQ_ERR_CUDA, "cuLaunchKernel: %s", g_drv.err(cr).c_str());
   }
   ctx->launches++;
@@ -476,6 +496,16 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     if (gen.kind == FQ_PIPE_AGGREGATE) {
       s2 = resolve_kernel(m, base + "_agg_u4", shapes().agg_threads, &pipe->k_agg_u4);
       if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", shapes().agg_threads, &pipe->k_agg_u8);
+      if (!s2 && gen.tma_ok) {
+        // ring depth: as many tiles as fit ~128 KB per CTA (measured optimum on B200), at least 2, at most the template bound
+        const unsigned tile_bytes = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec * gen.row_bytes;
+        unsigned stages = shapes().tma_stages_env > 0 ? (unsigned)shapes().tma_stages_env : (128u * 1024u) / tile_bytes;
+        stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_TMA_STAGES);
+        if (stages * tile_bytes <= 200 * 1024) {
+          s2 = resolve_kernel(m, base + "_agg_tma", shapes().tma_threads + 32, &pipe->k_agg_tma, stages * tile_bytes);
+          pipe->tma_stages = stages;
+        }
+      }
     } else if (gen.has_pred) {
       s2 = resolve_kernel(m, base + "_select", shapes().sel_threads + 32, &pipe->k_select);   // worker warps + one scan warp
     } else {
@@ -544,11 +574,14 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   fq_launch_params p;
   memset(&p, 0, sizeof p);
   if (fq_status st = bind_source(pipe, src, &p)) return st;
-  static const bool want_u8 = getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8;
-  const Kernel &k = want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
-  const int unroll = want_u8 ? 8 : 4;
+  // kernel variant: FQ_AGG_VARIANT = tma (default: bulk-copy staged; needs every referenced column materialised) | u4 | u8
+  static const std::string variant = getenv("FQ_AGG_VARIANT") ? getenv("FQ_AGG_VARIANT") : (getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8 ? "u8" : FQ_AGG_DEFAULT_VARIANT);
+  const bool use_tma = variant == "tma" && pipe->k_agg_tma.valid();
+  const bool want_u8 = variant == "u8";
+  const Kernel &k = use_tma ? pipe->k_agg_tma : want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
+  const int unroll = use_tma ? shapes().tma_unroll : want_u8 ? 8 : 4;
   // persistent grid: every resident CTA slot of every SM, fewer when the shard has fewer chunks
-  const uint64_t chunk_rows = (uint64_t)k.threads * unroll * pipe->gen.vec;
+  const uint64_t chunk_rows = (uint64_t)(use_tma ? k.threads - 32 : k.threads) * unroll * pipe->gen.vec;
   const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
   static const int bps_env = getenv("FQ_AGG_BLOCKS_PER_SM") ? atoi(getenv("FQ_AGG_BLOCKS_PER_SM")) : 0;
   const int bps = bps_env > 0 ? std::min(bps_env, k.blocks_per_sm) : k.blocks_per_sm;
@@ -564,6 +597,7 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   p.state = (fq_u64 *)pipe->d_state;
   p.ticket = (fq_u32 *)(pipe->d_ctl + 4);
   p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
+  p.stages = pipe->tma_stages;
   if ((flags & FQ_RUN_BLOCK_STATS) && pipe->gen.track_blocks && src->n_rows > 0) {
     const uint64_t words = ((src->n_rows + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS + 31) / 32;
     if (words > pipe->blocks_cap) {
