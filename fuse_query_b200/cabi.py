@@ -53,7 +53,7 @@ class Source(C.Structure):
 
 
 class PipeDesc(C.Structure):
-    _fields_ = [("n_cols", C.c_int32), ("col_dtypes", C.c_int32 * MAX_COLS), ("generated", C.c_int32),
+    _fields_ = [("n_cols", C.c_int32), ("col_dtypes", C.c_int32 * MAX_COLS), ("col_nullable", C.c_int32 * MAX_COLS), ("generated", C.c_int32),
                 ("nodes", C.POINTER(ExprNode)), ("n_nodes", C.c_int32), ("predicate", C.c_int32), ("kind", C.c_int32),
                 ("n_exprs", C.c_int32), ("exprs", C.c_int32 * MAX_EXPRS)]
 
@@ -67,10 +67,10 @@ class FuseGpuError(Exception):
 
 EXPORTS = [
     "fq_abi_version", "fq_ctx_create", "fq_ctx_destroy", "fq_last_error", "fq_ctx_launch_count", "fq_ctx_sm_count",
-    "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_free", "fq_column_dtype", "fq_column_len",
+    "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free", "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
-    "fq_pipe_expr_dtype", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
+    "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project",
 ]
 
@@ -96,6 +96,8 @@ def lib():
         "fq_column_alloc": (i32, [vp, i32, u64, C.POINTER(vp)]),
         "fq_column_wrap": (i32, [vp, i32, u64, vp, C.POINTER(vp)]),
         "fq_column_slice": (i32, [vp, vp, u64, u64, C.POINTER(vp)]),
+        "fq_column_set_validity": (i32, [vp, vp, vp]),
+        "fq_column_validity": (vp, [vp]),
         "fq_column_free": (None, [vp, vp]),
         "fq_column_dtype": (i32, [vp]),
         "fq_column_len": (u64, [vp]),
@@ -111,12 +113,13 @@ def lib():
         "fq_pipe_is_precompiled": (i32, [vp]),
         "fq_pipe_source": (C.c_char_p, [vp]),
         "fq_pipe_expr_dtype": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "fq_pipe_expr_nullable": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "fq_pipe_launch_aggregate": (i32, [vp, vp, C.POINTER(Source), u32, vp]),
         "fq_pipe_fetch_aggregate": (i32, [vp, vp, C.POINTER(CValue), i32, C.POINTER(i32), C.POINTER(u64)]),
         "fq_pipe_fetch_block_stats": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "fq_pipe_aggregator_nodes": (i32, [vp, vp, C.POINTER(i32), i32, C.POINTER(i32)]),
         "fq_pipe_state_device": (i32, [vp, vp, C.POINTER(vp), C.POINTER(u64)]),
-        "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), u64, i64, u32, vp]),
+        "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), C.POINTER(vp), u64, i64, u32, vp]),
         "fq_pipe_fetch_project": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -248,8 +251,19 @@ class Context:
         self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
         return col
 
-    def from_numpy(self, a, stream: int = 0) -> "Column":
+    def from_numpy(self, a, valid=None, stream: int = 0) -> "Column":
+        """Upload values; `valid` (bool / 0-1 array, one entry per row) attaches a validity column."""
         import numpy as np
+        if valid is not None:
+            col = self.from_numpy(a, None, stream)
+            v = np.ascontiguousarray(np.asarray(valid).astype(np.uint8))
+            vcol = self.column(BOOL, len(v))
+            if len(v):
+                self.check(lib().fq_column_upload(self._h, vcol._h, 0, C.c_void_p(v.ctypes.data), len(v), C.c_void_p(stream)))
+                self.synchronize(stream)
+            self.check(lib().fq_column_set_validity(self._h, col._h, vcol._h))
+            col._validity = vcol
+            return col
         tag = {np.dtype(np.int8): I8, np.dtype(np.int16): I16, np.dtype(np.int32): I32, np.dtype(np.int64): I64,
                np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.uint32): U32, np.dtype(np.uint64): U64,
                np.dtype(np.float32): F32, np.dtype(np.float64): F64}[a.dtype]
@@ -265,7 +279,8 @@ class Context:
 
     # ---- pipes ----
     def pipe(self, exprs: Sequence[str], *, columns: Sequence[str] = ("number",), dtypes: Sequence[int] = (U64,),
-             predicate: Optional[str] = None, aggregate: bool = False, generated: bool = False) -> "Pipe":
+             predicate: Optional[str] = None, aggregate: bool = False, generated: bool = False,
+             nullable: Sequence[bool] = ()) -> "Pipe":
         b = ExprBuilder(columns)
         pred = b.add(predicate) if predicate else -1
         roots = [b.add(e) for e in exprs]
@@ -273,6 +288,8 @@ class Context:
         d.n_cols = len(columns)
         for i, t in enumerate(dtypes):
             d.col_dtypes[i] = t
+        for i, f in enumerate(nullable):
+            d.col_nullable[i] = int(bool(f))
         d.generated = int(generated)
         nodes = b.array()
         d.nodes = C.cast(nodes, C.POINTER(ExprNode))
@@ -308,9 +325,18 @@ class Column:
         return lib().fq_column_device_ptr(self._h) or 0
 
     def slice(self, offset: int, n: int) -> "Column":
+        """A view of rows [offset, offset+n); the validity column, when there is one, is sliced alongside."""
         h = C.c_void_p()
         self.ctx.check(lib().fq_column_slice(self.ctx._h, self._h, offset, n, C.byref(h)))
-        return Column(self.ctx, h)
+        out = Column(self.ctx, h)
+        out._parent = self
+        return out
+
+    @property
+    def validity(self) -> Optional["Column"]:
+        """The attached validity column (one BOOL byte per row, 1 = valid), or None for a NOT NULL column."""
+        h = lib().fq_column_validity(self._h)
+        return Column(self.ctx, h) if h else None
 
     def to_numpy(self, n: Optional[int] = None, stream: int = 0):
         import numpy as np
@@ -353,6 +379,11 @@ class Pipe:
     @property
     def source(self) -> str:
         return lib().fq_pipe_source(self._h).decode()
+
+    def expr_nullable(self, i: int) -> bool:
+        out = C.c_int32()
+        self.ctx.check(lib().fq_pipe_expr_nullable(self.ctx._h, self._h, i, C.byref(out)))
+        return bool(out.value)
 
     def expr_dtype(self, i: int) -> int:
         out = C.c_int32()
@@ -403,9 +434,12 @@ class Pipe:
 
     # ---- projection / filter ----
     def launch_project(self, source: Source, outs: Sequence[Column], capacity: int, *, limit: int = -1, early_exit: bool = False,
-                       stream: int = 0):
+                       out_valid: Optional[Sequence[Optional[Column]]] = None, stream: int = 0):
         arr = (C.c_void_p * max(1, len(outs)))(*[c._h for c in outs])
-        self.ctx.check(lib().fq_pipe_launch_project(self.ctx._h, self._h, C.byref(source), arr, capacity, limit,
+        varr = None
+        if out_valid is not None:
+            varr = (C.c_void_p * max(1, len(outs)))(*[None if c is None else c._h for c in out_valid])
+        self.ctx.check(lib().fq_pipe_launch_project(self.ctx._h, self._h, C.byref(source), arr, varr, capacity, limit,
                                                      RUN_LIMIT_EARLY_EXIT if early_exit else 0, C.c_void_p(stream)))
 
     def fetch_project(self) -> Tuple[int, int]:

@@ -162,15 +162,32 @@ PYBIND11_MODULE(_fuse_host, m) {
         py::array c = py::array::ensure(a, py::array::c_style);
         return DataArray::from_host(gpu, dtype_of_numpy(c), c.data(), (uint64_t)c.size());
       })
+      .def_static("from_numpy_masked", [](GpuContextRef gpu, py::array a, py::array valid) {
+        py::array c = py::array::ensure(a, py::array::c_style);
+        py::array v = py::array::ensure(valid.attr("astype")("uint8"), py::array::c_style);
+        if (v.size() != c.size()) throw FuseQueryError::internal("validity and values differ in length");
+        auto arr = DataArray::from_host(gpu, dtype_of_numpy(c), c.data(), (uint64_t)c.size());
+        arr->set_validity(DataArray::from_host(gpu, FQ_BOOL, v.data(), (uint64_t)v.size()));
+        return arr;
+      })
+      .def("validity", &DataArray::validity)
+      .def("null_count", &DataArray::null_count)
       .def_static("utf8", &DataArray::utf8)
       .def("data_type", &DataArray::data_type)
       .def("__len__", &DataArray::len)
       .def("slice", &DataArray::slice)
       .def("value", &DataArray::value)
       .def("to_numpy", &array_to_python)
-      .def("to_list", [](const DataArrayRef &a) -> py::object {
+      .def("to_list", [](const DataArrayRef &a) -> py::object {   // NULL slots come back as None
         py::object o = array_to_python(a);
-        return a->is_utf8() ? o : o.attr("tolist")();
+        if (a->is_utf8()) return o;
+        py::list vals = o.attr("tolist")();
+        if (a->validity()) {
+          py::list ok = array_to_python(a->validity()).attr("tolist")();
+          for (size_t i = 0; i < vals.size(); i++)
+            if (!ok[i].cast<bool>()) vals[i] = py::none();
+        }
+        return std::move(vals);
       });
 
   py::class_<DataColumnarValue>(m, "DataColumnarValue")

@@ -197,40 +197,105 @@ struct Gen {
       default: return "0";
     }
   }
-  std::string cast(const std::string &e, fq_dtype from, fq_dtype to) {
-    if (from == to) return e;
-    return fmt("fq_cast<%s, %s>(", ctype(to), ctype(from)) + e + ", err)";
+  bool nullable_col(int c) const { return !(d.generated && c == 0) && d.col_nullable[c] != 0; }
+  // arrow cast S -> T yields NULL for values T cannot represent (num::cast): can that happen at all?
+  static bool cast_fallible(fq_dtype from, fq_dtype to) {
+    if (from == to || is_float(to) || from == FQ_BOOL || to == FQ_BOOL) return false;
+    if (is_float(from)) return true;
+    const int bf = (int)dtype_size(from) * 8, bt = (int)dtype_size(to) * 8;
+    if (is_signed_int(to)) return is_signed_int(from) ? bf > bt : bf >= bt;
+    return is_signed_int(from) ? true : bf > bt;
   }
-  // row-wise value of node i (its own dtype), reading row slot `r.c<k>[v]`
-  std::string emit(int i) {
-    const fq_expr_node &n = d.nodes[i];
-    switch (n.kind) {
-      case FQ_EXPR_FIELD: return fmt("r.c%d[v]", n.column);
-      case FQ_EXPR_CONSTANT: return literal(n.dtype, n.value);
-      case FQ_EXPR_ALIAS: case FQ_EXPR_AGGREGATOR: return emit(n.left);  // function_aggregator.rs:53-55
-      case FQ_EXPR_ARITHMETIC: {
-        fq_dtype t = ty[i];
-        std::string a = cast(emit(n.left), ty[n.left], t), b = cast(emit(n.right), ty[n.right], t);
-        if (n.op == FQ_AR_DIV) {
-          const fq_expr_node &rn = d.nodes[n.right];
-          if (scalar[n.right] && rn.kind == FQ_EXPR_CONSTANT &&
-              (is_float(rn.dtype) ? rn.value.f == 0.0 : rn.value.u == 0))
-            const_div0 = true;
-          return fmt("fq_div<%s>(", ctype(t)) + a + ", " + b + ", err)";
-        }
-        const char *f = n.op == FQ_AR_ADD ? "fq_add" : n.op == FQ_AR_SUB ? "fq_sub" : "fq_mul";
-        return fmt("%s<%s>(", f, ctype(t)) + a + ", " + b + ")";
-      }
-      case FQ_EXPR_COMPARISON: {
-        fq_dtype t;
-        std::string e;
-        equal_coercion(cmp_sym(n.op), ty[n.left], ty[n.right], &t, &e);
-        return "(" + cast(emit(n.left), ty[n.left], t) + " " + cmp_c(n.op) + " " + cast(emit(n.right), ty[n.right], t) + ")";
-      }
-      case FQ_EXPR_LOGIC:  // non-short-circuit: both sides are evaluated (and may raise) in the reference
-        return "(" + emit(n.left) + (n.op == FQ_LG_AND ? " & " : " | ") + emit(n.right) + ")";
+
+  // Row-level code of one generated function, in SSA form: every node is evaluated once into `n<i>` (value) and, when
+  // it can be NULL at all, `k<i>` (validity).  Validity follows arrow: a slot is null when either operand is null
+  // (combine_option_bitmap) or a coercion cast cannot represent the value; "true" means statically never null.
+  struct Emitter {
+    Gen &g;
+    std::string body;   // statements, indented by `ind`
+    std::string ind;
+    std::vector<std::string> val, ok;
+    std::vector<char> done;
+    Emitter(Gen &gen, const std::string &indent) : g(gen), ind(indent), val(gen.d.n_nodes), ok(gen.d.n_nodes), done(gen.d.n_nodes, 0) {}
+
+    static std::string conj(const std::vector<std::string> &terms) {
+      std::string o;
+      for (const auto &t : terms)
+        if (!t.empty() && t != "true") o += (o.empty() ? "" : " & ") + t;
+      return o.empty() ? "true" : o;
     }
-    return "0";
+    // operand `c` converted to type `t`: value expression and (possibly empty) representability check
+    std::pair<std::string, std::string> coerce(int c, fq_dtype t) {
+      const fq_dtype from = g.ty[c];
+      if (from == t) return {val[c], ""};
+      std::string v = fmt("fq_cast_v<%s, %s>(", ctype(t), ctype(from)) + val[c] + ")";
+      std::string k = cast_fallible(from, t) ? fmt("fq_cast_ok<%s, %s>(", ctype(t), ctype(from)) + val[c] + ")" : "";
+      return {v, k};
+    }
+    void node(int i) {
+      if (done[i]) return;
+      done[i] = 1;
+      const fq_expr_node &n = g.d.nodes[i];
+      switch (n.kind) {
+        case FQ_EXPR_FIELD:
+          val[i] = fmt("r.c%d[v]", n.column);
+          ok[i] = g.nullable_col(n.column) ? fmt("r.k%d[v]", n.column) : "true";
+          return;
+        case FQ_EXPR_CONSTANT:
+          val[i] = literal(n.dtype, n.value);
+          ok[i] = "true";
+          return;
+        case FQ_EXPR_ALIAS: case FQ_EXPR_AGGREGATOR:   // Aggregator::eval is transparent, function_aggregator.rs:53-55
+          node(n.left);
+          val[i] = val[n.left];
+          ok[i] = ok[n.left];
+          return;
+        default: break;
+      }
+      node(n.left);
+      node(n.right);
+      fq_dtype t = g.ty[i];
+      if (n.kind == FQ_EXPR_COMPARISON) {
+        std::string e;
+        equal_coercion(cmp_sym(n.op), g.ty[n.left], g.ty[n.right], &t, &e);
+      } else if (n.kind == FQ_EXPR_LOGIC) {
+        t = FQ_BOOL;
+      }
+      auto a = coerce(n.left, t), b = coerce(n.right, t);
+      const std::string valid = conj({ok[n.left], ok[n.right], a.second, b.second});
+      const std::string name = fmt("n%d", i);
+      std::string rhs;
+      const char *T = n.kind == FQ_EXPR_ARITHMETIC ? ctype(t) : "bool";
+      if (n.kind == FQ_EXPR_ARITHMETIC) {
+        if (n.op == FQ_AR_DIV) {
+          const fq_expr_node &rn = g.d.nodes[n.right];
+          if (g.scalar[n.right] && rn.kind == FQ_EXPR_CONSTANT && (is_float(rn.dtype) ? rn.value.f == 0.0 : rn.value.u == 0))
+            g.const_div0 = true;
+          rhs = fmt("fq_div<%s>(", ctype(t)) + a.first + ", " + b.first + ", " + valid + ", err)";
+        } else {
+          const char *f = n.op == FQ_AR_ADD ? "fq_add" : n.op == FQ_AR_SUB ? "fq_sub" : "fq_mul";
+          rhs = fmt("%s<%s>(", f, ctype(t)) + a.first + ", " + b.first + ")";
+        }
+      } else if (n.kind == FQ_EXPR_COMPARISON) {
+        rhs = "(" + a.first + " " + cmp_c(n.op) + " " + b.first + ")";
+      } else {  // non-short-circuit: both sides are evaluated (and may raise) in the reference
+        rhs = "(" + a.first + (n.op == FQ_LG_AND ? " & " : " | ") + b.first + ")";
+      }
+      body += ind + "const " + T + " " + name + " = " + rhs + ";\n";
+      val[i] = name;
+      if (valid == "true") {
+        ok[i] = "true";
+      } else {
+        body += ind + fmt("const bool k%d = ", i) + valid + ";\n";
+        ok[i] = fmt("k%d", i);
+      }
+    }
+  };
+  // can node i ever be NULL?  (same rules as the emitter, without emitting)
+  bool maybe_null(int i) {
+    Emitter e(*this, "");
+    e.node(i);
+    return e.ok[i] != "true";
   }
 
   // Aggregator leaves reachable without crossing another Aggregator
@@ -330,34 +395,61 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   for (int c : g.used_cols)
     if (!(d.generated && c == 0)) out->row_bytes += (int)dtype_size(g.col_dtype(c));
 
+  // nullable inputs that are actually referenced; validity travels as one byte per row next to the values
+  std::vector<int> null_cols;
+  for (int c : g.used_cols)
+    if (g.nullable_col(c)) null_cols.push_back(c);
+  // per aggregate leaf: does its argument ever yield NULL?  then the leaf counts its valid rows (sum/min/max of no valid
+  // row is None, arrow sum / min / max skip nulls)
+  std::vector<int> leaf_counted;
+  for (size_t k = 0; k < out->agg_nodes.size(); k++) {
+    const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
+    const bool counted = an.op != FQ_AGG_COUNT && g.maybe_null(an.left);
+    leaf_counted.push_back(counted ? 1 : 0);
+  }
+  const int n_leaves = (int)out->agg_nodes.size();
+  int n_slots = n_leaves;
+  out->agg_count_slot.assign(n_leaves, -1);
+  for (int k = 0; k < n_leaves; k++)
+    if (leaf_counted[k]) out->agg_count_slot[k] = n_slots++;
+  out->n_slots = n_slots;
+  out->null_cols = null_cols;
+  out->expr_nullable.assign(d.n_exprs, 0);
+  if (d.kind == FQ_PIPE_PROJECT)
+    for (int e = 0; e < d.n_exprs; e++) out->expr_nullable[e] = g.maybe_null(d.exprs[e]) ? 1 : 0;
+
   std::string s;
   s += "struct Q_@ {\n";
   bool has_sum = false;
   for (int op : out->agg_ops) has_sum = has_sum || op == FQ_AGG_SUM;
   out->track_blocks = out->has_pred && has_sum;   // only Sum is poisoned by an empty block
   s += fmt("  static constexpr int V = %d;\n  static constexpr int NSLOTS = %d;\n  static constexpr bool HAS_PRED = %s;\n"
-           "  static constexpr bool TRACK_BLOCKS = %s;\n", V,
-           (int)out->agg_nodes.size(), out->has_pred ? "true" : "false", out->track_blocks ? "true" : "false");
+           "  static constexpr bool TRACK_BLOCKS = %s;\n", V, n_slots, out->has_pred ? "true" : "false", out->track_blocks ? "true" : "false");
   s += "  struct Rows {";
   for (int c : g.used_cols) s += fmt(" %s c%d[V];", ctype(g.col_dtype(c)), c);
+  for (int c : null_cols) s += fmt(" bool k%d[V];", c);
   s += " };\n";
   s += "  __device__ static __forceinline__ void load(Rows &r, const fq_launch_params &p, fq_u64 g) {\n";
   for (int c : g.used_cols) {
     if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
     else s += fmt("    fq_load_vec<%s, V>(r.c%d, p.cols[%d], g);\n", ctype(g.col_dtype(c)), c, c);
   }
+  for (int c : null_cols) s += fmt("    fq_load_vec<bool, V>(r.k%d, p.cols_valid[%d], g);\n", c, c);
   s += "  }\n";
   s += "  __device__ static __forceinline__ void load1(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
   for (int c : g.used_cols) {
     if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
     else s += fmt("    r.c%d[0] = fq_ld1<%s>(p.cols[%d], row);\n", c, ctype(g.col_dtype(c)), c);
   }
+  for (int c : null_cols) s += fmt("    r.k%d[0] = fq_ld1<bool>(p.cols_valid[%d], row);\n", c, c);
   s += "  }\n";
   s += "  __device__ static __forceinline__ void copy_row(Rows &dst, int v, const Rows &one) {\n";
   for (int c : g.used_cols) s += fmt("    dst.c%d[v] = one.c%d[0];\n", c, c);
+  for (int c : null_cols) s += fmt("    dst.k%d[v] = one.k%d[0];\n", c, c);
   s += "  }\n";
-  // staged (bulk-copy) access: every referenced column must be materialised
+  // staged (bulk-copy) access: every referenced column must be materialised; validity bytes are staged like a column
   out->tma_ok = !g.used_cols.empty() && !(d.generated && g.used_cols.count(0));
+  out->row_bytes += (int)null_cols.size();
   s += fmt("  static constexpr int ROW_BYTES = %d;\n", out->row_bytes);
   if (out->tma_ok) {
     s += "  __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
@@ -367,6 +459,10 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
       prefix += w;
     }
+    for (int c : null_cols) {
+      s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
+      prefix += 1;
+    }
     s += "  }\n";
     s += "  __device__ static __forceinline__ void load_smem(Rows &r, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group) {\n";
     prefix = 0;
@@ -375,32 +471,54 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       s += fmt("    fq_lds_vec<%s, V>(r.c%d, stage + (size_t)tile_rows * %d, group);\n", ctype(g.col_dtype(c)), c, prefix);
       prefix += w;
     }
+    for (int c : null_cols) {
+      s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
+      prefix += 1;
+    }
     s += "  }\n";
   }
+  // WHERE: a NULL predicate keeps nothing
   s += "  __device__ static __forceinline__ bool pred(const Rows &r, int v, fq_u32 &err) {\n";
-  s += "    return " + (out->has_pred ? g.emit(d.predicate) : std::string("true")) + ";\n  }\n";
+  if (out->has_pred) {
+    Gen::Emitter e(g, "    ");
+    e.node(d.predicate);
+    s += e.body + "    return " + Gen::Emitter::conj({e.val[d.predicate], e.ok[d.predicate]}) + ";\n  }\n";
+  } else {
+    s += "    return true;\n  }\n";
+  }
 
   if (d.kind == FQ_PIPE_AGGREGATE) {
-    const int n = (int)out->agg_nodes.size();
+    const int n = n_leaves;
     s += "  struct Acc {";
     for (int k = 0; k < n; k++) s += fmt(" %s a%d;", ctype(out->agg_dtypes[k]), k);
+    for (int k = 0; k < n; k++)
+      if (leaf_counted[k]) s += fmt(" fq_u64 c%d;", k);
     s += " };\n";
     s += "  __device__ static __forceinline__ void init(Acc &a) {\n";
     for (int k = 0; k < n; k++) s += fmt("    a.a%d = %s;\n", k, identity_of(out->agg_ops[k], out->agg_dtypes[k]).c_str());
+    for (int k = 0; k < n; k++)
+      if (leaf_counted[k]) s += fmt("    a.c%d = 0;\n", k);
     s += "  }\n";
     s += "  __device__ static __forceinline__ bool consume(Acc &a, const Rows &r, int v, fq_u64 &nsel, fq_u32 &err) {\n";
     if (out->has_pred) s += "    if (!pred(r, v, err)) return false;\n    nsel += 1;\n";
-    for (int k = 0; k < n; k++) {
-      const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
-      const char *T = ctype(out->agg_dtypes[k]);
-      std::string arg = g.emit(an.left);
-      switch (an.op) {
-        case FQ_AGG_SUM: s += fmt("    a.a%d = fq_add<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
-        case FQ_AGG_MIN: s += fmt("    a.a%d = fq_min<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
-        case FQ_AGG_MAX: s += fmt("    a.a%d = fq_max<%s>(a.a%d, ", k, T, k) + arg + ");\n"; break;
-        default:  // Count evaluates (and discards) its argument, function_aggregator.rs:58-66: keep its error checks only
-          if (!g.trivial(an.left)) s += "    { auto unused = " + arg + "; (void)unused; }\n";
+    {
+      Gen::Emitter e(g, "    ");
+      std::string upd;
+      for (int k = 0; k < n; k++) {
+        const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
+        const char *T = ctype(out->agg_dtypes[k]);
+        if (an.op == FQ_AGG_COUNT) {
+          // Count evaluates (and discards) its argument, function_aggregator.rs:58-66: only its error checks remain
+          if (!g.trivial(an.left)) { e.node(an.left); upd += "    (void)" + e.val[an.left] + ";\n"; }
+          continue;
+        }
+        e.node(an.left);
+        const char *f = an.op == FQ_AGG_SUM ? "fq_add" : an.op == FQ_AGG_MIN ? "fq_min" : "fq_max";
+        std::string step = fmt("a.a%d = %s<%s>(a.a%d, ", k, f, T, k) + e.val[an.left] + ");";
+        if (leaf_counted[k]) upd += "    if (" + e.ok[an.left] + ") { " + step + fmt(" a.c%d += 1; }\n", k);
+        else upd += "    " + step + "\n";
       }
+      s += e.body + upd;
     }
     s += "    return true;\n  }\n";
     s += "  __device__ static __forceinline__ void merge(Acc &a, const Acc &b) {\n";
@@ -408,31 +526,64 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       const char *T = ctype(out->agg_dtypes[k]);
       const char *f = out->agg_ops[k] == FQ_AGG_MIN ? "fq_min" : out->agg_ops[k] == FQ_AGG_MAX ? "fq_max" : "fq_add";
       s += fmt("    a.a%d = %s<%s>(a.a%d, b.a%d);\n", k, f, T, k, k);
+      if (leaf_counted[k]) s += fmt("    a.c%d += b.c%d;\n", k, k);
     }
     s += "  }\n";
     s += "  __device__ static __forceinline__ void shfl(Acc &a, int m) {\n";
-    for (int k = 0; k < n; k++) s += fmt("    a.a%d = fq_shfl_xor<%s>(a.a%d, m);\n", k, ctype(out->agg_dtypes[k]), k);
+    for (int k = 0; k < n; k++) {
+      s += fmt("    a.a%d = fq_shfl_xor<%s>(a.a%d, m);\n", k, ctype(out->agg_dtypes[k]), k);
+      if (leaf_counted[k]) s += fmt("    a.c%d = fq_shfl_xor<fq_u64>(a.c%d, m);\n", k, k);
+    }
     s += "  }\n";
     s += "  __device__ static __forceinline__ void store(const Acc &a, fq_u64 *o) {\n";
-    for (int k = 0; k < n; k++) s += fmt("    o[%d] = fq_pack<%s>(a.a%d);\n", k, ctype(out->agg_dtypes[k]), k);
+    for (int k = 0; k < n; k++) {
+      s += fmt("    o[%d] = fq_pack<%s>(a.a%d);\n", k, ctype(out->agg_dtypes[k]), k);
+      if (leaf_counted[k]) s += fmt("    o[%d] = a.c%d;\n", out->agg_count_slot[k], k);
+    }
     s += "  }\n";
     s += "  __device__ static __forceinline__ void unpack(Acc &a, const fq_u64 *o) {\n";
-    for (int k = 0; k < n; k++) s += fmt("    a.a%d = fq_unpack<%s>(o[%d]);\n", k, ctype(out->agg_dtypes[k]), k);
+    for (int k = 0; k < n; k++) {
+      s += fmt("    a.a%d = fq_unpack<%s>(o[%d]);\n", k, ctype(out->agg_dtypes[k]), k);
+      if (leaf_counted[k]) s += fmt("    a.c%d = o[%d];\n", k, out->agg_count_slot[k]);
+    }
     s += "  }\n";
   } else {
     s += "  __device__ static __forceinline__ void emit(const Rows &r, int v, const fq_launch_params &p, fq_u64 pos, fq_u32 &err) {\n";
-    for (int e = 0; e < d.n_exprs; e++) {
-      fq_dtype t = out->expr_dtypes[e];
-      s += fmt("    ((%s *)p.outs[%d])[pos] = ", t == FQ_BOOL ? "fq_u8" : ctype(t), e) + g.emit(d.exprs[e]) + ";\n";
+    {
+      Gen::Emitter e(g, "    ");
+      std::string st;
+      for (int x = 0; x < d.n_exprs; x++) {
+        fq_dtype t = out->expr_dtypes[x];
+        e.node(d.exprs[x]);
+        st += fmt("    ((%s *)p.outs[%d])[pos] = ", t == FQ_BOOL ? "fq_u8" : ctype(t), x) + e.val[d.exprs[x]] + ";\n";
+        if (out->expr_nullable[x]) st += fmt("    ((fq_u8 *)p.outs_valid[%d])[pos] = ", x) + e.ok[d.exprs[x]] + ";\n";
+      }
+      s += e.body + st;
     }
     s += "  }\n";
     // whole vector group at once (projection without a filter): V values per output column, one vector store each
     s += "  __device__ static __forceinline__ void emit_vec(const Rows &r, const fq_launch_params &p, fq_u64 row0, fq_u32 &err) {\n";
-    for (int e = 0; e < d.n_exprs; e++) {
-      fq_dtype t = out->expr_dtypes[e];
-      const char *T = t == FQ_BOOL ? "fq_u8" : ctype(t);
-      s += fmt("    { %s o[V];\n#pragma unroll\n      for (int v = 0; v < V; v++) o[v] = ", T) + g.emit(d.exprs[e]) +
-           fmt(";\n      fq_store_vec<%s, V>(p.outs[%d], row0, o); }\n", T, e);
+    for (int x = 0; x < d.n_exprs; x++) {
+      fq_dtype t = out->expr_dtypes[x];
+      s += fmt("    %s o%d[V];\n", t == FQ_BOOL ? "fq_u8" : ctype(t), x);
+      if (out->expr_nullable[x]) s += fmt("    fq_u8 q%d[V];\n", x);
+    }
+    s += "#pragma unroll\n    for (int v = 0; v < V; v++) {\n";
+    {
+      Gen::Emitter e(g, "      ");
+      std::string st;
+      for (int x = 0; x < d.n_exprs; x++) {
+        e.node(d.exprs[x]);
+        st += fmt("      o%d[v] = ", x) + e.val[d.exprs[x]] + ";\n";
+        if (out->expr_nullable[x]) st += fmt("      q%d[v] = ", x) + e.ok[d.exprs[x]] + ";\n";
+      }
+      s += e.body + st;
+    }
+    s += "    }\n";
+    for (int x = 0; x < d.n_exprs; x++) {
+      fq_dtype t = out->expr_dtypes[x];
+      s += fmt("    fq_store_vec<%s, V>(p.outs[%d], row0, o%d);\n", t == FQ_BOOL ? "fq_u8" : ctype(t), x, x);
+      if (out->expr_nullable[x]) s += fmt("    fq_store_vec<fq_u8, V>(p.outs_valid[%d], row0, q%d);\n", x, x);
     }
     s += "  }\n";
   }

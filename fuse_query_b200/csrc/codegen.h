@@ -19,11 +19,15 @@ struct Generated {
   int vec = 2;             // rows per thread per vector load group (Q::V)
   int row_bytes = 0;       // bytes read per row (materialised columns actually referenced)
   std::vector<int> used_cols;
+  std::vector<int> null_cols;           // referenced columns that carry validity
   // aggregate pipes: Aggregator leaves in node-index order
   std::vector<int> agg_nodes, agg_ops;
   std::vector<fq_dtype> agg_dtypes;     // state type of each leaf (Count -> UInt64)
+  std::vector<int> agg_count_slot;      // slot holding the leaf's count of valid rows, -1 when its argument is never NULL
+  int n_slots = 0;                      // leaves + valid-row counts
   // select expressions
   std::vector<fq_dtype> expr_dtypes;    // Function::return_type
+  std::vector<int> expr_nullable;       // projection pipes: can select expression i yield NULL?
   std::vector<fq_dtype> node_dtypes;    // per node, FQ_NULL when not reachable
   bool tma_ok = false;                  // every referenced column is materialised: the bulk-copy staged kernel exists
   bool track_blocks = false;            // aggregate pipe with a predicate and a Sum leaf: reference-block tracking compiled in

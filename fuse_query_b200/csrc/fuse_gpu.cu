@@ -189,6 +189,8 @@ struct fq_column {
   uint64_t len = 0;
   void *ptr = nullptr;
   bool owned = false;
+  const fq_column *validity = nullptr;   // FQ_BOOL, one byte per row; borrowed unless owns_validity (slices)
+  bool owns_validity = false;
 };
 
 struct fq_pipe {
@@ -319,6 +321,16 @@ fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_param
     if (col->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: column %d has %" PRIu64 " rows, source says %" PRIu64, c, col->len, src->n_rows);
     if (((uintptr_t)col->ptr & 15) != 0) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: column %d is not 16-byte aligned", c);
     p->cols[c] = col->ptr;
+    const bool want_valid = std::find(pipe->gen.null_cols.begin(), pipe->gen.null_cols.end(), c) != pipe->gen.null_cols.end();
+    if (want_valid) {
+      if (!col->validity) return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a nullable column %d but the column carries no validity", c);
+      if (col->validity->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: validity of column %d is shorter than the source", c);
+      if (((uintptr_t)col->validity->ptr & 15) != 0)
+        return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: validity of column %d is not 16-byte aligned", c);
+      p->cols_valid[c] = col->validity->ptr;
+    } else if (col->validity) {
+      return set_err(FQ_ERR_INVALID, "Internal Error: column %d carries validity but the pipe was compiled for a NOT NULL column", c);
+    }
   }
   return FQ_OK;
 }
@@ -403,11 +415,29 @@ fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset,
   c->dtype = parent->dtype;
   c->len = len;
   c->ptr = (char *)parent->ptr + offset * fq::dtype_size(parent->dtype);
+  if (parent->validity) {
+    fq_column *v = nullptr;
+    if (fq_status st = fq_column_slice(ctx, parent->validity, offset, len, &v)) { delete c; return st; }
+    c->validity = v;
+    c->owns_validity = true;
+  }
   *out = c;
   return FQ_OK;
 }
+fq_status fq_column_set_validity(fq_ctx *ctx, fq_column *col, const fq_column *validity) {
+  if (!ctx || !col) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (validity && (validity->dtype != FQ_BOOL || validity->len < col->len))
+    return set_err(FQ_ERR_INVALID, "Internal Error: validity must be a Boolean column at least as long as the values");
+  if (col->owns_validity && col->validity) fq_column_free(ctx, const_cast<fq_column *>(col->validity));
+  col->validity = validity;
+  col->owns_validity = false;
+  return FQ_OK;
+}
+const fq_column *fq_column_validity(const fq_column *col) { return col ? col->validity : nullptr; }
+
 void fq_column_free(fq_ctx *ctx, fq_column *col) {
   if (!col) return;
+  if (col->owns_validity && col->validity) fq_column_free(ctx, const_cast<fq_column *>(col->validity));
   if (col->owned && col->ptr) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(col->ptr);
@@ -513,7 +543,7 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     }
     if (s2) { delete pipe; return s2; }
   }
-  pipe->n_slots = FQ_STATE_HDR + (int)gen.agg_nodes.size();
+  pipe->n_slots = FQ_STATE_HDR + gen.n_slots;
   cudaError_t e = cudaMalloc(&pipe->d_state, sizeof(uint64_t) * pipe->n_slots);
   if (e == cudaSuccess) e = cudaMemset(pipe->d_state, 0, sizeof(uint64_t) * pipe->n_slots);
   if (e == cudaSuccess) e = cudaMalloc(&pipe->d_ctl, 64);
@@ -551,6 +581,12 @@ const char *fq_pipe_source(const fq_pipe *pipe) { return pipe ? pipe->gen.source
 fq_status fq_pipe_expr_dtype(fq_ctx *, const fq_pipe *pipe, int32_t i, fq_dtype *out) {
   if (!pipe || !out || i < 0 || i >= (int)pipe->gen.expr_dtypes.size()) return set_err(FQ_ERR_INVALID, "Internal Error: bad expression index");
   *out = pipe->gen.expr_dtypes[i];
+  return FQ_OK;
+}
+
+fq_status fq_pipe_expr_nullable(fq_ctx *, const fq_pipe *pipe, int32_t i, int32_t *out) {
+  if (!pipe || !out || i < 0 || i >= (int)pipe->gen.expr_dtypes.size()) return set_err(FQ_ERR_INVALID, "Internal Error: bad expression index");
+  *out = i < (int)pipe->gen.expr_nullable.size() ? pipe->gen.expr_nullable[i] : 0;
   return FQ_OK;
 }
 
@@ -646,7 +682,8 @@ fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, 
       v.v.u = nsel;
       continue;
     }
-    v.some = nsel > 0;  // arrow sum/min/max of an empty array is None
+    // arrow sum/min/max skip nulls and are None when no valid row was seen (empty input included)
+    v.some = pipe->gen.agg_count_slot[k] >= 0 ? pipe->h_state[FQ_STATE_HDR + pipe->gen.agg_count_slot[k]] > 0 : nsel > 0;
     if (!v.some) continue;
     if (t == FQ_F32 || t == FQ_F64) memcpy(&v.v.f, &bits, 8);
     else v.v.u = bits;
@@ -663,8 +700,8 @@ fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks
   return FQ_OK;
 }
 
-fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols, uint64_t capacity,
-                                 int64_t limit, uint32_t flags, void *stream) {
+fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols,
+                                 fq_column *const *out_valid, uint64_t capacity, int64_t limit, uint32_t flags, void *stream) {
   if (fq_status st = use(ctx)) return st;
   if (!pipe || pipe->gen.kind != FQ_PIPE_PROJECT) return set_err(FQ_ERR_INVALID, "Internal Error: not a projection pipe");
   fq_launch_params p;
@@ -681,6 +718,12 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
                      fq::dtype_name(pipe->gen.expr_dtypes[e]));
     if (c->len < cap && c->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: output column %d shorter than capacity", e);
     p.outs[e] = c->ptr;
+    if (e < (int)pipe->gen.expr_nullable.size() && pipe->gen.expr_nullable[e]) {
+      const fq_column *vcol = out_valid ? out_valid[e] : nullptr;
+      if (!vcol || vcol->dtype != FQ_BOOL || (vcol->len < cap && vcol->len < capacity))
+        return set_err(FQ_ERR_INVALID, "Internal Error: select expression %d can yield NULL: a Boolean validity output column is required", e);
+      p.outs_valid[e] = vcol->ptr;
+    }
   }
   p.capacity = cap;
   pipe->capacity_eff = cap;

@@ -63,6 +63,7 @@ typedef signed char fq_i8;
 struct fq_launch_params {
   fq_u64 n_rows;
   const void *cols[8];
+  const void *cols_valid[8];  // per input column: one byte per row (1 = valid) or null when the column is NOT NULL
   fq_u64 numbers_begin;  // generated mode: column 0 = numbers_begin + row
   // aggregate
   fq_u64 *partials;      // [gridDim.x][FQ_STATE_HDR + Q::NSLOTS]
@@ -73,6 +74,7 @@ struct fq_launch_params {
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   // select / map
   void *outs[8];
+  void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
   fq_u64 capacity;       // rows written are those with rank < capacity (min(limit, capacity) on the host)
   fq_u64 *tile_status;   // decoupled look-back descriptors, zeroed before the launch
   fq_u32 *tile_counter;  // dynamic tile ids (forward progress for the look-back), zeroed before the launch
@@ -158,14 +160,14 @@ __device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (
 #pragma unroll
     for (int k = 0; k < BYTES / 16; k++)
       asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16 * k), "r"(u.q[k].x), "r"(u.q[k].y), "r"(u.q[k].z), "r"(u.q[k].w) : "memory");
-  } else if constexpr (BYTES == 8) {
+  } )FQSK"
+R"FQSK(else if constexpr (BYTES == 8) {
     union { fq_u64 q; T t[V]; } u;
 #pragma unroll
     for (int k = 0; k < V; k++) u.t[k] = src[k];
     *(fq_u64 *)p = u.q;
   } else if constexpr (BYTES == 4) {
-    union { fq_u32)FQSK"
-R"FQSK( q; T t[V]; } u;
+    union { fq_u32 q; T t[V]; } u;
 #pragma unroll
     for (int k = 0; k < V; k++) u.t[k] = src[k];
     *(fq_u32 *)p = u.q;
@@ -226,9 +228,13 @@ template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
   if constexpr (fq_traits<T>::is_float) return fq_fmul(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a * (U)b); }
 }
-// arrow `divide`: any zero divisor is an error (integer and float lanes alike); integers truncate
-template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
-  if (b == (T)0) { err |= FQ_E_DIVZERO; return (T)0; }
+// arrow `divide`: a zero divisor in a VALID slot is an error (integer and float lanes alike; null slots are skipped,
+// math_divide checks the combined validity bitmap first); integers truncate
+template <class T> __device__ __forceinline__ T fq_div(T a, T b, bool valid, fq_u32 &err) {
+  if (b == (T)0) {
+    if (valid) err |= FQ_E_DIVZERO;
+    return (T)0;
+  }
   if constexpr (fq_traits<T>::is_float) return fq_fdiv(a, b);
   else if constexpr (fq_traits<T>::is_signed) {
     typedef typename fq_traits<T>::unsigned_t U;
@@ -239,28 +245,32 @@ template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
 template <class T> __device__ __forceinline__ T fq_min(T a, T b) { return b < a ? b : a; }
 template <class T> __device__ __forceinline__ T fq_max(T a, T b) { return b > a ? b : a; }
 
-// arrow numeric `cast` (num::cast): a value that does not fit the target becomes null.  The device
-// path carries no validity yet, so such a row raises FQ_E_CAST and the launch reports "unsupported".
-template <class T, class S> __device__ __forceinline__ T fq_cast(S x, fq_u32 &err) {
-  if constexpr (fq_traits<T>::is_float) return (T)x;
+// arrow numeric `cast` (num::cast): a value that does not fit the target becomes NULL.  fq_cast_ok says whether the
+// value is representable, fq_cast_v converts it (0 when it is not); codegen ANDs fq_cast_ok into the row's validity.
+template <class T, class S> __device__ __forceinline__ bool fq_cast_ok(S x) {
+  if constexpr (fq_traits<T>::is_float) return true;
   else if constexpr (fq_traits<S>::is_float) {
     const double d = (double)x;
+    if (d != d) return false;
     const double t = d < 0 ? -floor(-d) : floor(d);
-    bool ok;
-    if constexpr (sizeof(T) == 8 && fq_traits<T>::is_signed) ok = t >= -9223372036854775808.0 && t < 9223372036854775808.0;
-    else if constexpr (sizeof(T) == 8) ok = t > -1.0 && t < 18446744073709551616.0;
-    else ok = t >= (double)fq_traits<T>::lo() && t <= (double)fq_traits<T>::hi();
-    if (!ok || d != d) { err |= FQ_E_CAST; return (T)0; }
-    return (T)t;
+    if constexpr (sizeof(T) == 8 && fq_traits<T>::is_signed) return t >= -9223372036854775808.0 && t < 9223372036854775808.0;
+    else if constexpr (sizeof(T) == 8) return t > -1.0 && t < 18446744073709551616.0;
+    else return t >= (double)fq_traits<T>::lo() && t <= (double)fq_traits<T>::hi();
   } else if constexpr (fq_traits<S>::is_signed && !fq_traits<T>::is_signed) {
-    if (x < 0 || (fq_u64)x > (fq_u64)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
-    return (T)x;
+    return x >= 0 && (fq_u64)x <= (fq_u64)fq_traits<T>::hi();
   } else if constexpr (!fq_traits<S>::is_signed && fq_traits<T>::is_signed) {
-    if ((fq_u64)x > (fq_u64)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
-    return (T)x;
+    return (fq_u64)x <= (fq_u64)fq_traits<T>::hi();
   } else {
-    if (x < (S)fq_traits<T>::lo() && sizeof(S) > sizeof(T)) { err |= FQ_E_CAST; return (T)0; }
-    if (sizeof(S) > sizeof(T) && x > (S)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
+    if constexpr (sizeof(S) > sizeof(T)) return x >= (S)fq_traits<T>::lo() && x <= (S)fq_traits<T>::hi();
+    else return true;
+  }
+}
+template <class T, class S> __device__ __forceinline__ T fq_cast_v(S x) {
+  if constexpr (fq_traits<S>::is_float && !fq_traits<T>::is_float) {
+    if (!fq_cast_ok<T, S>(x)) return (T)0;
+    const double d = (double)x;
+    return (T)(d < 0 ? -floor(-d) : floor(d));
+  } else {
     return (T)x;
   }
 }
@@ -300,7 +310,8 @@ __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &ns
   __syncthreads();  // sm may still be read by a previous use
   if (lane == 0) {
     sm[warp][0] = nsel;
-    sm[warp][1] = err;
+    sm[war)FQSK"
+R"FQSK(p][1] = err;
     Q::store(acc, &sm[warp][FQ_STATE_HDR]);
   }
   __syncthreads();
@@ -318,8 +329,7 @@ __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &ns
       typename Q::Acc o = acc;
       Q::shfl(o, m);
       Q::merge(acc, o);
-      nsel += __shfl_xor_syn)FQSK"
-R"FQSK(c(0xffffffffu, nsel, m);
+      nsel += __shfl_xor_sync(0xffffffffu, nsel, m);
       err |= __shfl_xor_sync(0xffffffffu, err, m);
     }
   }
@@ -501,13 +511,13 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fq_agg_tma_kernel — the same single-pass multi-aggregate scan, staged through shared memory by the bulk-copy
+// fq_agg_tma_kernel — the same single-pass multi-aggreg)FQSK"
+R"FQSK(ate scan, staged through shared memory by the bulk-copy
 // engine (cp.async.bulk, SASS UBLKCP) instead of per-thread LDG.
 //
 // CTA = C consumer warps + 1 producer warp.  Tile = 32 * C * U vector groups of every referenced column; a ring
 // of STAGES tiles lives in dynamic shared memory.  Producer (one elected lane): wait empty[s] -> arrive.expect_tx
-// full[s] -> one cp.async.bulk per column (contiguous tile_rows * sizeof(T) bytes, co)FQSK"
-R"FQSK(mpletes on full[s]).
+// full[s] -> one cp.async.bulk per column (contiguous tile_rows * sizeof(T) bytes, completes on full[s]).
 // Consumers: wait full[s] -> LDS.128 (consecutive lanes on consecutive 16-B words: conflict-free) -> accumulate in
 // registers -> one arrive per warp on empty[s].  Bytes in flight are set by stages * tile bytes, not by registers:
 // one CTA per SM with 4 x 32 KB measured best on B200 (10.70 ms for 80 GB vs 11.04 ms for the LDG kernel; more
@@ -655,12 +665,12 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 //   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
 //                     segment's global base by a decoupled look-back over 64-bit descriptors {flag:2, count:62};
 //   workers, pass 2   (one segment behind) warps that selected something in a tile re-read that tile (still in the
-//                     126 MB L2: <= resident CTAs * 2 * 128 KB are in flight), rank rows with __ballot_sync / __popc
+//                     126 MB L2: <= resident CTAs * 2 * 128 KB are in flight), rank rows with )FQSK"
+R"FQSK(__ballot_sync / __popc
 //                     of the lower-lane mask and write each selected row once, projected at scatter time.
 // The look-back of segment k (a chain of global round trips that also waits for the slowest predecessor)
 // overlaps the workers' pass 1 of segment k + 1: named barriers FULL[k&1] (workers arrive, scan waits) and
-// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers inste)FQSK"
-R"FQSK(ad, ncu showed 16-25
+// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
 // warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back per 16-KB tile cannot keep up
 // with HBM at all (0.7 TB/s measured).
 // Rows beyond min(limit, capacity) are counted, not written.  Early exit: the segment that reaches `stop_after`
@@ -809,7 +819,8 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   if (threadIdx.x >= 1 && threadIdx.x < 4) s_ready[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
-    const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
+    const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) !=)FQSK"
+R"FQSK( 0) ? 1u : 0u;
     if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
     publish_claim(0, c, st);
   }
@@ -822,8 +833,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
       fq_bar_sync(FQ_BAR_FULL + b, allthreads);
       const fq_u64 seg = s_seg[k & 3];
       if (!(seg < n_seg) || s_stop[k & 3]) break;
-      //)FQSK"
-R"FQSK( counts -> exclusive offsets in (tile, warp) order; segment total
+      // counts -> exclusive offsets in (tile, warp) order; segment total
       const int entries = SEG * nwarps;
       const int per = (entries + 31) / 32;
       fq_u32 local = 0;
@@ -1015,7 +1025,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
-    Q::load1(r, p, row);
+    Q::load1(r, p, row))FQSK"
+R"FQSK(;
     if (row < p.capacity) Q::emit(r, 0, p, row, err);
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);

@@ -433,6 +433,20 @@ DataArrayRef DataArray::from_host(GpuContextRef ctx, DataType t, const void *dat
   }
   return a;
 }
+void DataArray::set_validity(DataArrayRef validity) {
+  if (is_utf8()) throw FuseQueryError::internal("validity on a Utf8 array is not supported");
+  if (validity && (validity->data_type() != FQ_BOOL || validity->len() < len_)) throw FuseQueryError::internal("validity must be a Boolean array of the same length");
+  ctx_->check(fq_column_set_validity(ctx_->raw(), col_, validity ? validity->column() : nullptr));
+  validity_ = std::move(validity);
+}
+uint64_t DataArray::null_count() const {
+  if (!validity_ || !len_) return 0;
+  std::vector<unsigned char> v(len_);
+  validity_->to_host(v.data());
+  uint64_t n = 0;
+  for (unsigned char b : v) n += b == 0;
+  return n;
+}
 DataArrayRef DataArray::utf8(std::vector<std::string> values) {
   auto a = std::shared_ptr<DataArray>(new DataArray());
   a->dtype_ = FQ_UTF8;
@@ -447,7 +461,9 @@ DataArrayRef DataArray::slice(uint64_t offset, uint64_t len) {
   }
   fq_column *c = nullptr;
   ctx_->check(fq_column_slice(ctx_->raw(), col_, offset, len, &c));
-  return device(ctx_, c, parent_ ? parent_ : shared_from_this());  // the owner of the buffer stays alive
+  DataArrayRef out = device(ctx_, c, parent_ ? parent_ : shared_from_this());  // the owner of the buffer stays alive
+  if (validity_) out->validity_ = validity_->slice(offset, len);   // the C ABI sliced the device validity alongside
+  return out;
 }
 void DataArray::to_host(void *out) const {
   if (is_utf8()) throw FuseQueryError::internal("to_host on a Utf8 array");
@@ -463,6 +479,12 @@ DataValue DataArray::value(uint64_t index) const {
   ctx_->check(fq_column_download(ctx_->raw(), col_, index, buf, 1, ctx_->stream));
   ctx_->check(fq_stream_synchronize(ctx_->raw(), ctx_->stream));
   DataValue v = DataValue::None(dtype_);
+  if (validity_) {
+    unsigned char ok = 1;
+    ctx_->check(fq_column_download(ctx_->raw(), validity_->column(), index, &ok, 1, ctx_->stream));
+    ctx_->check(fq_stream_synchronize(ctx_->raw(), ctx_->stream));
+    if (!ok) return v;   // Type(None)
+  }
   v.some = true;
   switch (dtype_) {
     case FQ_BOOL: v.i = buf[0] != 0; break;

@@ -95,6 +95,10 @@ class DataArray : public std::enable_shared_from_this<DataArray> {
   static std::shared_ptr<DataArray> device(GpuContextRef ctx, fq_column *col, std::shared_ptr<DataArray> parent = nullptr);
   static std::shared_ptr<DataArray> alloc(GpuContextRef ctx, DataType t, uint64_t len);
   static std::shared_ptr<DataArray> from_host(GpuContextRef ctx, DataType t, const void *data, uint64_t len);
+  // validity: a Boolean array of the same length (one byte per row, 1 = valid) or null for a NOT NULL array
+  void set_validity(std::shared_ptr<DataArray> validity);
+  const std::shared_ptr<DataArray> &validity() const { return validity_; }
+  uint64_t null_count() const;
   static std::shared_ptr<DataArray> utf8(std::vector<std::string> values);
   DataType data_type() const { return dtype_; }
   uint64_t len() const { return len_; }
@@ -113,6 +117,7 @@ class DataArray : public std::enable_shared_from_this<DataArray> {
   uint64_t len_ = 0;
   fq_column *col_ = nullptr;
   std::shared_ptr<DataArray> parent_;
+  std::shared_ptr<DataArray> validity_;
   std::vector<std::string> strings_;
 };
 using DataArrayRef = std::shared_ptr<DataArray>;

@@ -33,6 +33,7 @@ int Lowering::column_of(const DataBlock &block, const std::string &name) {
   }
   block_cols.push_back(bi);
   col_dtypes.push_back(t);
+  col_nullable.push_back(!block.generated && block.column((size_t)bi)->validity() ? 1 : 0);
   return (int)block_cols.size() - 1;
 }
 int Lowering::lower(const Function &f, const DataBlock &block) {
@@ -77,6 +78,7 @@ fq_pipe_desc Lowering::desc(int kind, int predicate, const std::vector<int> &roo
   memset(&d, 0, sizeof d);
   d.n_cols = (int)col_dtypes.size();
   for (size_t k = 0; k < col_dtypes.size(); k++) d.col_dtypes[k] = col_dtypes[k];
+  for (size_t k = 0; k < col_nullable.size(); k++) d.col_nullable[k] = col_nullable[k];
   d.generated = generated;
   d.nodes = nodes.data();
   d.n_nodes = (int)nodes.size();
@@ -121,17 +123,25 @@ ProjectResult run_project(GpuContextRef ctx, const DataBlock &block, const Funct
   uint64_t cap = rows;
   if (limit >= 0 && (uint64_t)limit < cap) cap = (uint64_t)limit;
   ProjectResult res;
-  std::vector<fq_column *> outs;
+  std::vector<fq_column *> outs, outs_valid;
+  std::vector<DataArrayRef> valids;
   for (size_t e = 0; e < funcs.size(); e++) {
     fq_dtype t;
+    int32_t nullable = 0;
     ctx->check(fq_pipe_expr_dtype(ctx->raw(), pipe->pipe, (int)e, &t));
+    ctx->check(fq_pipe_expr_nullable(ctx->raw(), pipe->pipe, (int)e, &nullable));
     res.columns.push_back(DataArray::alloc(ctx, t, cap));
     outs.push_back(res.columns.back()->column());
+    valids.push_back(nullable ? DataArray::alloc(ctx, FQ_BOOL, cap) : nullptr);
+    outs_valid.push_back(nullable ? valids.back()->column() : nullptr);
   }
   BoundSource bs;
   bind_source(lw, block, &bs);
-  ctx->check(fq_pipe_launch_project(ctx->raw(), pipe->pipe, &bs.src, outs.data(), cap, limit, early_exit ? FQ_RUN_LIMIT_EARLY_EXIT : 0, ctx->stream));
+  ctx->check(fq_pipe_launch_project(ctx->raw(), pipe->pipe, &bs.src, outs.data(), outs_valid.data(), cap, limit,
+                                    early_exit ? FQ_RUN_LIMIT_EARLY_EXIT : 0, ctx->stream));
   ctx->check(fq_pipe_fetch_project(ctx->raw(), pipe->pipe, &res.rows_selected, &res.rows_written));
+  for (size_t e = 0; e < funcs.size(); e++)
+    if (valids[e]) res.columns[e]->set_validity(valids[e]);
   if (res.rows_written < cap)
     for (auto &c : res.columns) c = c->slice(0, res.rows_written);
   return res;

@@ -10,6 +10,7 @@ struct Lowering {
   std::vector<fq_expr_node> nodes;
   std::vector<int> block_cols;        // pipe column -> block column
   std::vector<DataType> col_dtypes;
+  std::vector<int> col_nullable;
   std::map<const Function *, int> node_of;
   bool generated = false;
   int column_of(const DataBlock &block, const std::string &name);

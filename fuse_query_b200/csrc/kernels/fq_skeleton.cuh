@@ -62,6 +62,7 @@ typedef signed char fq_i8;
 struct fq_launch_params {
   fq_u64 n_rows;
   const void *cols[8];
+  const void *cols_valid[8];  // per input column: one byte per row (1 = valid) or null when the column is NOT NULL
   fq_u64 numbers_begin;  // generated mode: column 0 = numbers_begin + row
   // aggregate
   fq_u64 *partials;      // [gridDim.x][FQ_STATE_HDR + Q::NSLOTS]
@@ -72,6 +73,7 @@ struct fq_launch_params {
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   // select / map
   void *outs[8];
+  void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
   fq_u64 capacity;       // rows written are those with rank < capacity (min(limit, capacity) on the host)
   fq_u64 *tile_status;   // decoupled look-back descriptors, zeroed before the launch
   fq_u32 *tile_counter;  // dynamic tile ids (forward progress for the look-back), zeroed before the launch
@@ -224,9 +226,13 @@ template <class T> __device__ __forceinline__ T fq_mul(T a, T b) {
   if constexpr (fq_traits<T>::is_float) return fq_fmul(a, b);
   else { typedef typename fq_traits<T>::unsigned_t U; return (T)(U)((U)a * (U)b); }
 }
-// arrow `divide`: any zero divisor is an error (integer and float lanes alike); integers truncate
-template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
-  if (b == (T)0) { err |= FQ_E_DIVZERO; return (T)0; }
+// arrow `divide`: a zero divisor in a VALID slot is an error (integer and float lanes alike; null slots are skipped,
+// math_divide checks the combined validity bitmap first); integers truncate
+template <class T> __device__ __forceinline__ T fq_div(T a, T b, bool valid, fq_u32 &err) {
+  if (b == (T)0) {
+    if (valid) err |= FQ_E_DIVZERO;
+    return (T)0;
+  }
   if constexpr (fq_traits<T>::is_float) return fq_fdiv(a, b);
   else if constexpr (fq_traits<T>::is_signed) {
     typedef typename fq_traits<T>::unsigned_t U;
@@ -237,28 +243,32 @@ template <class T> __device__ __forceinline__ T fq_div(T a, T b, fq_u32 &err) {
 template <class T> __device__ __forceinline__ T fq_min(T a, T b) { return b < a ? b : a; }
 template <class T> __device__ __forceinline__ T fq_max(T a, T b) { return b > a ? b : a; }
 
-// arrow numeric `cast` (num::cast): a value that does not fit the target becomes null.  The device
-// path carries no validity yet, so such a row raises FQ_E_CAST and the launch reports "unsupported".
-template <class T, class S> __device__ __forceinline__ T fq_cast(S x, fq_u32 &err) {
-  if constexpr (fq_traits<T>::is_float) return (T)x;
+// arrow numeric `cast` (num::cast): a value that does not fit the target becomes NULL.  fq_cast_ok says whether the
+// value is representable, fq_cast_v converts it (0 when it is not); codegen ANDs fq_cast_ok into the row's validity.
+template <class T, class S> __device__ __forceinline__ bool fq_cast_ok(S x) {
+  if constexpr (fq_traits<T>::is_float) return true;
   else if constexpr (fq_traits<S>::is_float) {
     const double d = (double)x;
+    if (d != d) return false;
     const double t = d < 0 ? -floor(-d) : floor(d);
-    bool ok;
-    if constexpr (sizeof(T) == 8 && fq_traits<T>::is_signed) ok = t >= -9223372036854775808.0 && t < 9223372036854775808.0;
-    else if constexpr (sizeof(T) == 8) ok = t > -1.0 && t < 18446744073709551616.0;
-    else ok = t >= (double)fq_traits<T>::lo() && t <= (double)fq_traits<T>::hi();
-    if (!ok || d != d) { err |= FQ_E_CAST; return (T)0; }
-    return (T)t;
+    if constexpr (sizeof(T) == 8 && fq_traits<T>::is_signed) return t >= -9223372036854775808.0 && t < 9223372036854775808.0;
+    else if constexpr (sizeof(T) == 8) return t > -1.0 && t < 18446744073709551616.0;
+    else return t >= (double)fq_traits<T>::lo() && t <= (double)fq_traits<T>::hi();
   } else if constexpr (fq_traits<S>::is_signed && !fq_traits<T>::is_signed) {
-    if (x < 0 || (fq_u64)x > (fq_u64)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
-    return (T)x;
+    return x >= 0 && (fq_u64)x <= (fq_u64)fq_traits<T>::hi();
   } else if constexpr (!fq_traits<S>::is_signed && fq_traits<T>::is_signed) {
-    if ((fq_u64)x > (fq_u64)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
-    return (T)x;
+    return (fq_u64)x <= (fq_u64)fq_traits<T>::hi();
   } else {
-    if (x < (S)fq_traits<T>::lo() && sizeof(S) > sizeof(T)) { err |= FQ_E_CAST; return (T)0; }
-    if (sizeof(S) > sizeof(T) && x > (S)fq_traits<T>::hi()) { err |= FQ_E_CAST; return (T)0; }
+    if constexpr (sizeof(S) > sizeof(T)) return x >= (S)fq_traits<T>::lo() && x <= (S)fq_traits<T>::hi();
+    else return true;
+  }
+}
+template <class T, class S> __device__ __forceinline__ T fq_cast_v(S x) {
+  if constexpr (fq_traits<S>::is_float && !fq_traits<T>::is_float) {
+    if (!fq_cast_ok<T, S>(x)) return (T)0;
+    const double d = (double)x;
+    return (T)(d < 0 ? -floor(-d) : floor(d));
+  } else {
     return (T)x;
   }
 }

@@ -13,24 +13,42 @@ _TAG = {np.dtype(np.bool_): h.DataType.Boolean, np.dtype(np.int8): h.DataType.In
         np.dtype(np.float32): h.DataType.Float32, np.dtype(np.float64): h.DataType.Float64}
 
 
+def _arrow_column(col):
+    """pyarrow ChunkedArray/Array -> (values, validity bytes or None).  The arrow null bitmap (1 bit per row, LSB first)
+    becomes the device layout: one byte per row, 1 = valid."""
+    import pyarrow as pa
+    arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    if not arr.null_count:
+        return arr.to_numpy(zero_copy_only=False), None
+    valid = np.asarray(arr.is_valid().to_numpy(zero_copy_only=False)).astype(np.uint8)
+    zero = False if pa.types.is_boolean(arr.type) else 0
+    values = arr.fill_null(zero).to_numpy(zero_copy_only=False)   # the payload of a NULL slot is never read as a value
+    return values, valid
+
+
 def register_table(ctx, gpu, db: str, name: str, columns: Mapping[str, "np.ndarray"]):
-    """Upload `columns` (numpy arrays, or a pyarrow.Table / dict of pyarrow arrays without nulls) to HBM and register
-    them as table `db.name`.  Returns the MemoryTable."""
+    """Upload `columns` to HBM and register them as table `db.name`.  Returns the MemoryTable.
+
+    A column is a numpy array (NOT NULL), a numpy masked array, a `(values, valid)` pair (valid: 1 = not NULL), or a
+    pyarrow array; a pyarrow.Table is taken column by column.  Columns with NULLs become nullable fields whose validity
+    rides beside the values as one byte per row."""
     if hasattr(columns, "column_names"):  # pyarrow.Table
         tbl = columns
-        columns = {}
-        for n in tbl.column_names:
-            col = tbl.column(n)
-            if col.null_count:
-                raise h.FuseQueryError(f"Internal Error: Unsupported on the device path: column {n} has NULLs")
-            columns[n] = col.to_numpy()
+        columns = {n: _arrow_column(tbl.column(n)) for n in tbl.column_names}
     fields, arrays = [], []
     for n, a in columns.items():
+        valid = None
+        if isinstance(a, tuple):
+            a, valid = a
+        elif isinstance(a, np.ma.MaskedArray):
+            a, valid = a.filled(0), (None if a.mask is np.ma.nomask else (~np.ma.getmaskarray(a)).astype(np.uint8))
+        elif hasattr(a, "null_count"):          # pyarrow Array / ChunkedArray
+            a, valid = _arrow_column(a)
         a = np.ascontiguousarray(np.asarray(a))
         if a.dtype not in _TAG:
             raise h.FuseQueryError(f"Internal Error: Unsupported on the device path: column {n} of dtype {a.dtype}")
-        fields.append(h.DataField(n, _TAG[a.dtype], False))
-        arrays.append(h.DataArray.from_numpy(gpu, a))
+        fields.append(h.DataField(n, _TAG[a.dtype], valid is not None))
+        arrays.append(h.DataArray.from_numpy(gpu, a) if valid is None else h.DataArray.from_numpy_masked(gpu, a, np.asarray(valid)))
     table = h.MemoryTable(db, name, h.DataSchema(fields), arrays)
     ds = ctx.datasource()
     ds.add_database(db) if not _has_db(ds, db) else None

@@ -111,8 +111,9 @@ int32_t fq_ctx_sm_count(const fq_ctx *ctx);
 /* ---------------------------------------------------------------------------------------------
  * Columns — device-resident Arrow-layout buffers replacing ArrayRef inside DataBlock
  * (datablocks/data_block.rs:10-14): contiguous little-endian values, 256-byte aligned.
- * Validity bitmaps are not carried yet: every column is NOT NULL like numbers_mt's
- * (datasources/system/numbers_table.rs:21-25).
+ * numbers_mt's column is NOT NULL (datasources/system/numbers_table.rs:21-25) and carries nothing else.
+ * A nullable column additionally points at a validity column: FQ_BOOL, one byte per row (1 = valid) — Arrow's
+ * bit-packed validity is unpacked when it is uploaded, so that slicing and compaction stay byte-addressed.
  * ------------------------------------------------------------------------------------------- */
 typedef struct fq_column fq_column;
 
@@ -121,6 +122,10 @@ fq_status fq_column_alloc(fq_ctx *ctx, fq_dtype dtype, uint64_t len, fq_column *
 fq_status fq_column_wrap(fq_ctx *ctx, fq_dtype dtype, uint64_t len, void *device_values, fq_column **out);
 /* zero-copy view of rows [offset, offset+len) of `parent` (arrow slice); parent must outlive it */
 fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset, uint64_t len, fq_column **out);
+/* attach (validity != NULL) or detach a validity column; it is borrowed and must outlive `col`; slices of `col`
+ * made afterwards slice it too */
+fq_status fq_column_set_validity(fq_ctx *ctx, fq_column *col, const fq_column *validity);
+const fq_column *fq_column_validity(const fq_column *col);
 void fq_column_free(fq_ctx *ctx, fq_column *col);
 fq_dtype fq_column_dtype(const fq_column *col);
 uint64_t fq_column_len(const fq_column *col);
@@ -162,6 +167,7 @@ enum { FQ_PIPE_PROJECT = 0, FQ_PIPE_AGGREGATE = 1 };
 typedef struct fq_pipe_desc {
   int32_t n_cols;                   /* input schema */
   fq_dtype col_dtypes[FQ_MAX_COLS];
+  int32_t col_nullable[FQ_MAX_COLS]; /* 1: the column carries validity (fq_column_set_validity) */
   int32_t generated;                /* specialise for fq_source.generated (column 0 = UInt64 numbers) */
   const fq_expr_node *nodes;
   int32_t n_nodes;
@@ -182,6 +188,9 @@ int32_t fq_pipe_is_precompiled(const fq_pipe *pipe);
 const char *fq_pipe_source(const fq_pipe *pipe);
 /* Function::return_type of select expression i over the pipe's schema (functions/function.rs:28-38) */
 fq_status fq_pipe_expr_dtype(fq_ctx *ctx, const fq_pipe *pipe, int32_t i, fq_dtype *out);
+/* projection pipes: 1 when select expression i can yield NULL (a nullable input, or a coercion cast that arrow turns
+ * into NULL when the value does not fit): the launch then needs a validity output column for it */
+fq_status fq_pipe_expr_nullable(fq_ctx *ctx, const fq_pipe *pipe, int32_t i, int32_t *out);
 
 /* ---- aggregate pipes: Function::accumulate over a whole shard (function_aggregator.rs:57-100) ----
  * The device keeps one running state per Aggregator leaf.  FQ_RUN_ACCUMULATE folds this launch into
@@ -215,8 +224,10 @@ fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr,
  * (arrow filter keeps order, transform_filter.rs:51-54).  At most min(limit, capacity) rows are
  * written (limit < 0 = none; stream_limit.rs:28-48); rows_selected reports every matching row
  * unless FQ_RUN_LIMIT_EARLY_EXIT let the scan stop once `limit` rows were found. */
+/* out_valid[i] (FQ_BOOL, one byte per output row) is required for expressions fq_pipe_expr_nullable reports; the
+ * array itself may be NULL when no expression is nullable. */
 fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols,
-                                 uint64_t capacity, int64_t limit, uint32_t flags, void *stream);
+                                 fq_column *const *out_valid, uint64_t capacity, int64_t limit, uint32_t flags, void *stream);
 fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selected, uint64_t *rows_written);
 
 #ifdef __cplusplus

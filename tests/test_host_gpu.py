@@ -383,6 +383,54 @@ def test_memory_table_sql_matches_oracle(gpu):
         assert rows_of(blocks) == want.rows() and len(want.rows()) == 20
 
 
+def test_nullable_memory_table_sql_matches_oracle(gpu):
+    """NULLs in user columns (numpy masked arrays, (values, valid) pairs, pyarrow arrays) ride through the same pipes:
+    arrow's null propagation for arithmetic / comparison / logic, NULL predicate slots keep nothing, Sum/Min/Max skip
+    NULL slots and Count is the block length (data_array_aggregate.rs:29)."""
+    import pyarrow as pa
+    from fuse_query_b200.tables import register_table
+    rng = np.random.default_rng(7)
+    n = 96_000
+    k = rng.integers(0, 1 << 50, n, dtype=np.uint64)
+    v = rng.integers(-10**9, 10**9, n, dtype=np.int64)
+    w = rng.integers(1, 1000, n, dtype=np.uint16)
+    kv = (rng.random(n) > 0.3).astype(np.uint8)
+    vv = (rng.random(n) > 0.1).astype(np.uint8)
+    data = {"k": (k, kv), "v": np.ma.MaskedArray(v, mask=~vv.astype(bool)), "w": pa.array(w)}
+    table = {"k": o.array(o.U64, k, kv), "v": o.array(o.I64, v, vv), "w": o.array(o.U16, w)}
+    for workers, fuse in ((1, True), (0, True), (0, False)):
+        ctx = make_ctx(gpu, workers, fuse=fuse, block_rows=0 if fuse else 10000)
+        t = register_table(ctx, gpu, "default", "t", data)
+        assert [f.nullable for f in t.schema().fields] == [True, True, False]
+        blocks = h.execute_sql(ctx, "select sum(v), min(v / w), max(k + w), count(k), sum(k + v) from t where v < 500000000")
+        want = o.run_query(["(sum (col v))", "(min (/ (col v) (col w)))", "(max (+ (col k) (col w)))", "(count (col k))",
+                            "(sum (+ (col k) (col v)))"], table=table, predicate="(< (col v) (u64 500000000))", is_aggregate=True,
+                           worker_threads=workers, tail_quirk=False)
+        assert rows_of(blocks) == want.rows()
+        blocks = h.execute_sql(ctx, "select k, v * w as vw, k + v from t where w = 7 limit 40")
+        want = o.run_query(["(col k)", "(alias vw (* (col v) (col w)))", "(+ (col k) (col v))"], table=table,
+                           predicate="(= (col w) (u64 7))", limit=40, worker_threads=workers, tail_quirk=False)
+        got = rows_of(blocks)
+        assert got == want.rows() and len(got) == 40
+        assert any(x is None for r in got for x in r)
+        blocks = h.execute_sql(ctx, "select w from t where k > 1000 and v > 0 limit 15")
+        want = o.run_query(["(col w)"], table=table, predicate="(and (> (col k) (u64 1000)) (> (col v) (u64 0)))", limit=15,
+                           worker_threads=workers, tail_quirk=False)
+        assert rows_of(blocks) == want.rows()
+
+
+def test_pyarrow_table_with_nulls_registers_nullable_fields(gpu):
+    import pyarrow as pa
+    from fuse_query_b200.tables import register_table
+    ctx = make_ctx(gpu, 1, fuse=True)
+    tbl = pa.table({"x": pa.array([1, None, 3, None, 5], type=pa.uint64()), "y": pa.array([10, 20, 30, 40, 50], type=pa.int32())})
+    t = register_table(ctx, gpu, "default", "pt", tbl)
+    assert [f.nullable for f in t.schema().fields] == [True, False]
+    assert rows_of(h.execute_sql(ctx, "select x + y, y from pt")) == [(11, 10), (None, 20), (33, 30), (None, 40), (55, 50)]
+    assert rows_of(h.execute_sql(ctx, "select sum(x), count(x), max(x + y) from pt")) == [(9, 5, 55)]
+    assert rows_of(h.execute_sql(ctx, "select y from pt where x > 1")) == [(30,), (50,)]
+
+
 # ---------------------------------------------------------------------------------------------
 # SURVEY F8: with a WHERE clause the reference folds Sum per 10 000-row block and an emptied block poisons it
 # ---------------------------------------------------------------------------------------------
