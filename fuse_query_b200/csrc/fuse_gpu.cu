@@ -23,6 +23,9 @@
 #include "kernels/fq_skeleton.cuh"
 #include "generated/skeleton_embed.h"  // static const char fq_skeleton_src[]
 
+#ifndef FQ_SEL_DEFAULT_VARIANT
+#define FQ_SEL_DEFAULT_VARIANT "tma"   // "tma": pass 1 of the select kernel staged by bulk copies
+#endif
 #ifndef FQ_AGG_DEFAULT_VARIANT
 #define FQ_AGG_DEFAULT_VARIANT "tma"   // bulk-copy staged kernel when every referenced column is materialised, else u4
 #endif
@@ -130,6 +133,8 @@ struct Shapes {
   int tma_stages_env = 0;   // FQ_TUNE_TMA_STAGES: ring depth override (<= FQ_TMA_STAGES)
   int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
   int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
+  int selt_threads = FQ_SELT_THREADS, selt_unroll = FQ_SELT_UNROLL, selt_seg = FQ_SELT_SEG;
+  int selt_stages_env = 0;  // FQ_TUNE_SELT_STAGES: ring depth override (<= FQ_SELT_STAGES)
   bool tuned = false;
   Shapes() {
     auto env = [&](const char *name, int *v) {
@@ -142,15 +147,18 @@ struct Shapes {
     if (getenv("FQ_TUNE_TMA_STAGES") && atoi(getenv("FQ_TUNE_TMA_STAGES")) > 0) tma_stages_env = atoi(getenv("FQ_TUNE_TMA_STAGES"));
     env("FQ_TUNE_TMA_MIN_BLOCKS", &tma_min_blocks);
     env("FQ_TUNE_SEL_THREADS", &sel_threads); env("FQ_TUNE_SEL_MIN_BLOCKS", &sel_min_blocks); env("FQ_TUNE_SEL_UNROLL", &sel_unroll); env("FQ_TUNE_SEL_SEG", &sel_seg); env("FQ_TUNE_SEL_LOOK", &sel_look);
+    env("FQ_TUNE_SELT_THREADS", &selt_threads); env("FQ_TUNE_SELT_UNROLL", &selt_unroll); env("FQ_TUNE_SELT_SEG", &selt_seg);
+    if (getenv("FQ_TUNE_SELT_STAGES") && atoi(getenv("FQ_TUNE_SELT_STAGES")) > 0) selt_stages_env = atoi(getenv("FQ_TUNE_SELT_STAGES"));
     env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
   }
   std::string defines() const {
-    char b[1024];
+    char b[1536];
     snprintf(b, sizeof b,
+             "#define FQ_SELT_THREADS %d\n#define FQ_SELT_UNROLL %d\n#define FQ_SELT_SEG %d\n#define FQ_SELT_STAGES 8\n"
              "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_TMA_THREADS %d\n"
              "#define FQ_TMA_UNROLL %d\n#define FQ_TMA_STAGES %d\n#define FQ_TMA_MIN_BLOCKS %d\n#define FQ_SEL_THREADS %d\n"
              "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
-             agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
+             selt_threads, selt_unroll, selt_seg, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
     return b;
   }
 };
@@ -195,8 +203,8 @@ struct fq_column {
 
 struct fq_pipe {
   fq::Generated gen;
-  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_map;
-  unsigned tma_stages = 0;
+  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map;
+  unsigned tma_stages = 0, selt_stages = 0;
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
   uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
@@ -538,6 +546,17 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       }
     } else if (gen.has_pred) {
       s2 = resolve_kernel(m, base + "_select", shapes().sel_threads + 32, &pipe->k_select);   // worker warps + one scan warp
+      if (!s2 && gen.tma_ok) {
+        // staged variant: consumer warps + scan warp + producer warp; ring of ~128 KB per CTA, at least 2 tiles
+        const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
+        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.row_bytes;
+        unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (128u * 1024u) / tile_bytes;
+        stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);
+        if (stages * tile_bytes <= 200 * 1024) {
+          s2 = resolve_kernel(m, base + "_select_tma", shapes().selt_threads + 64, &pipe->k_select_tma, stages * tile_bytes);
+          pipe->selt_stages = stages;
+        }
+      }
     } else {
       s2 = resolve_kernel(m, base + "_map", shapes().map_threads, &pipe->k_map);
     }
@@ -611,7 +630,7 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   memset(&p, 0, sizeof p);
   if (fq_status st = bind_source(pipe, src, &p)) return st;
   // kernel variant: FQ_AGG_VARIANT = tma (default: bulk-copy staged; needs every referenced column materialised) | u4 | u8
-  static const std::string variant = getenv("FQ_AGG_VARIANT") ? getenv("FQ_AGG_VARIANT") : (getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8 ? "u8" : FQ_AGG_DEFAULT_VARIANT);
+  const std::string variant = getenv("FQ_AGG_VARIANT") ? getenv("FQ_AGG_VARIANT") : (getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8 ? "u8" : FQ_AGG_DEFAULT_VARIANT);
   const bool use_tma = variant == "tma" && pipe->k_agg_tma.valid();
   const bool want_u8 = variant == "u8";
   const Kernel &k = use_tma ? pipe->k_agg_tma : want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
@@ -736,12 +755,17 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   if (src->n_rows == 0) {
     pipe->skipped = true;
   } else if (pipe->gen.has_pred) {
-    const Kernel &k = pipe->k_select;
+    // kernel variant: FQ_SEL_VARIANT = tma (default: pass 1 staged by bulk copies; needs every referenced column materialised) | ldg
+    const std::string variant = getenv("FQ_SEL_VARIANT") ? getenv("FQ_SEL_VARIANT") : FQ_SEL_DEFAULT_VARIANT;   // read per launch: tests switch it
+    const bool use_tma = variant == "tma" && pipe->k_select_tma.valid();
+    const Kernel &k = use_tma ? pipe->k_select_tma : pipe->k_select;
     // work unit = segment of sel_seg tiles; p.n_tiles counts segments (one look-back descriptor each)
     const int vec = pipe->gen.vec;
-    const int sel_u = shapes().sel_unroll * vec <= 32 ? shapes().sel_unroll : 32 / vec;              // fq_sel_shape<V>::U
-    const int sel_seg = shapes().sel_seg * sel_u * vec <= 64 ? shapes().sel_seg : 64 / (sel_u * vec);  // fq_sel_shape<V>::SEG
-    const uint64_t tile_rows = (uint64_t)(k.threads - 32) * sel_u * vec * sel_seg;
+    const int cfg_u = use_tma ? shapes().selt_unroll : shapes().sel_unroll, cfg_seg = use_tma ? shapes().selt_seg : shapes().sel_seg;
+    const int sel_u = cfg_u * vec <= 32 ? cfg_u : 32 / vec;                        // fq_sel_shape<V>::U / fq_selt_shape<V>::U
+    const int sel_seg = cfg_seg * sel_u * vec <= 64 ? cfg_seg : 64 / (sel_u * vec);  // ...::SEG
+    const uint64_t tile_rows = (uint64_t)(k.threads - (use_tma ? 64 : 32)) * sel_u * vec * sel_seg;
+    p.stages = pipe->selt_stages;
     p.n_tiles = (src->n_rows + tile_rows - 1) / tile_rows;
     if (p.n_tiles > pipe->tiles_cap) {
       cudaFree(pipe->d_tiles);
@@ -752,7 +776,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     p.tile_status = (fq_u64 *)pipe->d_tiles;
     CUDA_TRY(cudaMemsetAsync(pipe->d_tiles, 0, sizeof(uint64_t) * p.n_tiles, (cudaStream_t)stream));
     static const int sel_bps_env = getenv("FQ_SEL_BLOCKS_PER_SM") ? atoi(getenv("FQ_SEL_BLOCKS_PER_SM")) : 0;
-    const int sel_bps = sel_bps_env > 0 ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
+    const int sel_bps = (sel_bps_env > 0 && !use_tma) ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   } else {

@@ -47,10 +47,16 @@ typedef signed char fq_i8;
 #define FQ_SEL_MIN_BLOCKS 2
 #define FQ_SEL_UNROLL 4
 #define FQ_SEL_SEG 8
-#define FQ_SEL_LOOK 2
+#define FQ_SEL_LOOK 5        // look-back window = 160 descriptors per poll (>= the CTAs of a 1-CTA/SM grid)
 #define FQ_MAP_THREADS 256
 #define FQ_MAP_MIN_BLOCKS 4
 #define FQ_MAP_UNROLL 4
+#endif
+#ifndef FQ_SELT_THREADS
+#define FQ_SELT_THREADS 512  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp)
+#define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
+#define FQ_SELT_SEG 8        // tiles per segment (one look-back each): 256 KB of a UInt64 column
+#define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~128 KB in flight per SM)
 #endif
 
 #define FQ_STATE_HDR 6        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned,
@@ -740,8 +746,136 @@ template <int V> struct fq_sel_shape {
 
 enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2)
 
+// scan warp, step 1: per-(tile, worker warp) selected counts -> exclusive offsets inside the segment (in place,
+// (tile, warp) order); returns the segment total.  Called by all 32 lanes of the scan warp.
+template <int SEG>
+__device__ __forceinline__ fq_u32 fq_sel_scan_counts(fq_u32 (*cnt)[FQ_MAX_WARPS], int nwarps) {
+  const int lane = threadIdx.x & 31;
+  const int entries = SEG * nwarps;
+  const int per = (entries + 31) / 32;
+  fq_u32 local = 0;
+  for (int j = 0; j < per; j++) {
+    const int i = lane * per + j;
+    if (i < entries) local += cnt[i / nwarps][i % nwarps];
+  }
+  fq_u32 incl_lane = local;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const fq_u32 o = __shfl_up_sync(0xffffffffu, incl_lane, m);
+    if (lane >= m) incl_lane += o;
+  }
+  const fq_u32 tot = __shfl_sync(0xffffffffu, incl_lane, 31);
+  fq_u32 run = incl_lane - local;
+  for (int j = 0; j < per; j++) {
+    const int i = lane * per + j;
+    if (i < entries) {
+      const fq_u32 c = cnt[i / nwarps][i % nwarps];
+      cnt[i / nwarps][i % nwarps] = run;
+      run += c;
+    }
+  }
+  return tot;
+}
+
+// Workers, end of pass 1: lane 0 of every worker warp adds the warp's selected count of the segment to a packed
+// shared-memory word {arrivals:32, count:32}; the last warp to arrive publishes the segment's descriptor (aggregate;
+// prefix for segment 0).  The aggregate therefore becomes visible the moment the segment has been streamed and never
+// queues behind the scan warp, which may still be looking back for the previous segment — with the scan warp
+// publishing it, every look-back waited for the look-backs before it (a convoy: 7-10 us per segment per CTA).
+__device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
+  const unsigned long long old = atomicAdd(acc, (1ull << 32) | (unsigned long long)wsum);
+  if ((int)(old >> 32) == nwarps - 1) {
+    const fq_u64 tot = (fq_u64)((fq_u32)old + wsum);
+    *acc = 0ull;   // the slot is reused three segments later, after two named barriers
+    fq_st_volatile(p.tile_status + seg, (seg == 0 ? FQ_TILE_PREFIX : FQ_TILE_AGG) | tot);
+  }
+}
+
+// scan warp, step 2: resolve the segment's exclusive global base by a look-back over the 64-bit descriptors
+// {flag:2, count:62} of its predecessors, publish the inclusive prefix.
+//
+// A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  So when it
+// looks back from segment `seg` it already knows the inclusive prefix `prev_incl` of the segment `prev_seg` it
+// resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
+// and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
+// published prefix, prefixes are published only when a look-back ends, and with hundreds of segments in flight the
+// chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
+// the CTA's own history the walk is 1-2 polls of FQ_SEL_LOOK * 32 descriptors, independent of the others' progress.
+// A nearer published prefix still ends the walk early; the first segment of a CTA (prev_seg < 0) walks to one.
+__device__ __forceinline__ fq_u64 fq_sel_lookback(const fq_launch_params &p, fq_u64 seg, fq_u32 tot, fq_i64 prev_seg, fq_u64 prev_incl) {
+  const int lane = threadIdx.x & 31;
+  fq_u64 excl = 0;
+  if (seg == 0) return 0;   // its descriptor (a prefix) was published by the workers, like every aggregate
+  fq_i64 look = (fq_i64)seg - 1;
+  for (;;) {
+    // FQ_SEL_LOOK * 32 predecessors per poll: lane l inspects look - 32 * j - l for j = 0 .. FQ_SEL_LOOK - 1
+    fq_u64 st[FQ_SEL_LOOK];
+    bool ready;
+    do {
+      ready = true;
+#pragma unroll
+      for (int j = 0; j < FQ_SEL_LOOK; j++) {
+        const fq_i64 idx = look - 32 * j - lane;
+        if (idx < 0) st[j] = FQ_TILE_PREFIX;                                            // before segment 0: prefix 0
+        else if (idx <= prev_seg) st[j] = FQ_TILE_PREFIX | (idx == prev_seg ? prev_incl : 0ull);   // own history
+        else st[j] = fq_ld_volatile(p.tile_status + idx);
+        ready = ready && FQ_TILE_FLAG(st[j]) != 0;
+      }
+    } while (!ready);   // lanes whose descriptors are published leave the poll; the ballot below reconverges the warp
+    fq_u64 contrib = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < FQ_SEL_LOOK; j++) {
+      if (!found) {
+        const fq_u32 pm = __ballot_sync(0xffffffffu, FQ_TILE_FLAG(st[j]) == 2);
+        if (pm) {
+          if (lane <= __ffs(pm) - 1) contrib += FQ_TILE_VALUE(st[j]);
+          found = true;
+        } else {
+          contrib += FQ_TILE_VALUE(st[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, m);
+    excl += contrib;
+    if (found) break;
+    look -= 32 * FQ_SEL_LOOK;
+  }
+  if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_PREFIX | (excl + tot));
+  return excl;
+}
+
 // Pass 2 of one segment (kept out of line: it runs once per 128 KB and would otherwise double the register
 // pressure of the streaming loop).  `cnt` = this segment's ring slot of exclusive offsets, `base` its global base.
+// One vector group (V rows) of a tile for the calling thread: group u of worker warp `warp`, i.e. the rows
+// fq_tile_load puts in rows[u].  Ragged tiles row by row.
+template <class Q, int U>
+__device__ __forceinline__ void fq_group_load(const fq_launch_params &p, fq_u64 tile, int wthreads, int u, typename Q::Rows &r) {
+  constexpr int V = Q::V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u64 tile_groups = (fq_u64)wthreads * U;
+  const fq_u64 g = tile * tile_groups + (fq_u64)warp * 32 * U + lane + 32ull * u;
+  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+    Q::load(r, p, g);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      if (g * V + v < p.n_rows) {
+        typename Q::Rows one;
+        Q::load1(one, p, g * V + v);
+        Q::copy_row(r, v, one);
+      }
+    }
+  }
+}
+
+// Pass 2 of one segment (kept out of line: it runs once per 128 KB and would otherwise double the register
+// pressure of the streaming loop).  `cnt` = this segment's ring slot of exclusive offsets, `base` its global base.
+// Dense tiles (the warp kept at least 1/8 of its rows) re-read the warp's whole run with all loads in flight; sparse
+// tiles load only the vector groups of the threads that kept something (a 1/1024 selection re-reads 3 % of the tile
+// instead of 25 %).  Per-thread predicated loads for both cases were measured slower on dense selections (7.9 vs
+// 5.9 ms for all of 1e9 rows).  The re-reads hit L2: at most resident CTAs * 3 segments are between the passes.
 template <class Q, int U, int SEG>
 __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64 sseg, fq_u64 skeep, const fq_u32 (*cnt)[FQ_MAX_WARPS],
                                                fq_u64 base, int wthreads, fq_u32 *err_out) {
@@ -754,10 +888,12 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
 #pragma unroll
   for (int t = 0; t < SEG; t++) {
     const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
-    if (__any_sync(0xffffffffu, keep != 0)) {
+    const fq_u32 wkept = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
+    if (wkept == 0) continue;
+    fq_u64 pos0 = base + cnt[t][warp];
+    if (wkept * 8 >= 32 * BITS) {
       typename Q::Rows rows[U];
       fq_tile_load<Q, U>(p, sseg * SEG + t, wthreads, rows);   // L2 hit
-      fq_u64 pos0 = base + cnt[t][warp];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         fq_u32 before = 0, tot = 0;
@@ -777,6 +913,30 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
         }
         pos0 += tot;
       }
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < U; u++) {
+        const fq_u32 ku = (keep >> (u * V)) & ((1u << V) - 1u);
+        if (__ballot_sync(0xffffffffu, ku != 0) == 0) continue;
+        typename Q::Rows r;
+        if (ku) fq_group_load<Q, U>(p, sseg * SEG + t, wthreads, u, r);
+        fq_u32 before = 0, tot = 0;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const fq_u32 bmask = __ballot_sync(0xffffffffu, (ku >> v) & 1u);
+          before += __popc(bmask & lt_mask);
+          tot += __popc(bmask);
+        }
+        fq_u64 pos = pos0 + before;
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          if ((ku >> v) & 1u) {
+            if (pos < p.capacity) Q::emit(r, v, p, pos, err);
+            pos++;
+          }
+        }
+        pos0 += tot;
+      }
     }
   }
   if (err) *err_out |= err;
@@ -789,6 +949,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
   __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
   __shared__ fq_u64 s_excl[FQ_SEL_RING];                    // global base of the segment in each ring slot
+  __shared__ unsigned long long s_acc[FQ_SEL_RING];         // {arrived worker warps, selected rows} of the segment being streamed
   __shared__ volatile fq_u64 s_seg[4];           // claimed segment ids: ring of 4 (the scan warp lags the workers by up to 2)
   __shared__ volatile fq_u32 s_stop[4];
   __shared__ volatile int s_ready[4];
@@ -812,6 +973,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     s_ready[k & 3] = k + 1;
   };
   if (threadIdx.x >= 1 && threadIdx.x < 4) s_ready[threadIdx.x] = 0;
+  if (threadIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
     const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
@@ -822,77 +984,17 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
 
   if (is_scan) {
     // ================= scan warp =================
+    fq_i64 prev_seg = -1;      // the segment this CTA resolved last and its inclusive prefix (see fq_sel_lookback)
+    fq_u64 prev_incl = 0;
     for (int k = 0;; k++) {
       const int b = k % FQ_SEL_RING;
       fq_bar_sync(FQ_BAR_FULL + b, allthreads);
       const fq_u64 seg = s_seg[k & 3];
       if (!(seg < n_seg) || s_stop[k & 3]) break;
-      // counts -> exclusive offsets in (tile, warp) order; segment total
-      const int entries = SEG * nwarps;
-      const int per = (entries + 31) / 32;
-      fq_u32 local = 0;
-      for (int j = 0; j < per; j++) {
-        const int i = lane * per + j;
-        if (i < entries) local += s_cnt[b][i / nwarps][i % nwarps];
-      }
-      fq_u32 incl_lane = local;
-#pragma unroll
-      for (int m = 1; m < 32; m <<= 1) {
-        const fq_u32 o = __shfl_up_sync(0xffffffffu, incl_lane, m);
-        if (lane >= m) incl_lane += o;
-      }
-      const fq_u32 tot = __shfl_sync(0xffffffffu, incl_lane, 31);
-      fq_u32 run = incl_lane - local;
-      for (int j = 0; j < per; j++) {
-        const int i = lane * per + j;
-        if (i < entries) {
-          const fq_u32 c = s_cnt[b][i / nwarps][i % nwarps];
-          s_cnt[b][i / nwarps][i % nwarps] = run;
-          run += c;
-        }
-      }
-      // decoupled look-back
-      fq_u64 excl = 0;
-      if (seg == 0) {
-        if (lane == 0) fq_st_volatile(p.tile_status, FQ_TILE_PREFIX | (fq_u64)tot);
-      } else {
-        if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_AGG | (fq_u64)tot);
-        fq_i64 look = (fq_i64)seg - 1;
-        for (;;) {
-          // FQ_SEL_LOOK * 32 predecessors per poll: lane l inspects look - 32 * j - l for j = 0 .. FQ_SEL_LOOK - 1
-          fq_u64 st[FQ_SEL_LOOK];
-          bool ready;
-          do {
-            ready = true;
-#pragma unroll
-            for (int j = 0; j < FQ_SEL_LOOK; j++) {
-              const fq_i64 idx = look - 32 * j - lane;
-              st[j] = idx >= 0 ? fq_ld_volatile(p.tile_status + idx) : FQ_TILE_PREFIX;   // before segment 0: prefix 0
-              ready = ready && FQ_TILE_FLAG(st[j]) != 0;
-            }
-          } while (!ready);
-          fq_u64 contrib = 0;
-          bool found = false;
-#pragma unroll
-          for (int j = 0; j < FQ_SEL_LOOK; j++) {
-            if (!found) {
-              const fq_u32 pm = __ballot_sync(0xffffffffu, FQ_TILE_FLAG(st[j]) == 2);
-              if (pm) {
-                if (lane <= __ffs(pm) - 1) contrib += FQ_TILE_VALUE(st[j]);
-                found = true;
-              } else {
-                contrib += FQ_TILE_VALUE(st[j]);
-              }
-            }
-          }
-#pragma unroll
-          for (int m = 16; m > 0; m >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, m);
-          excl += contrib;
-          if (found) break;
-          look -= 32 * FQ_SEL_LOOK;
-        }
-        if (lane == 0) fq_st_volatile(p.tile_status + seg, FQ_TILE_PREFIX | (excl + tot));
-      }
+      const fq_u32 tot = fq_sel_scan_counts<SEG>(s_cnt[b], nwarps);
+      const fq_u64 excl = fq_sel_lookback(p, seg, tot, prev_seg, prev_incl);
+      prev_seg = (fq_i64)seg;
+      prev_incl = excl + tot;
       if (lane == 0) {
         s_excl[b] = excl;
         const fq_u64 incl = excl + tot;
@@ -938,6 +1040,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     fq_u64 keepbits = 0;
     if (active) {
       typename Q::Rows rows0[U], rows_n[U];
+      fq_u32 wsum = 0;
       fq_tile_load<Q, U>(p, seg * SEG, wthreads, rows0);
 #pragma unroll
       for (int t = 0; t < SEG; t++) {
@@ -946,11 +1049,13 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
         keepbits |= (fq_u64)keep << (t * BITS);
         const fq_u32 wcount = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
         if (lane == 0) s_cnt[b][t][warp] = wcount;
+        wsum += wcount;
         if (t + 1 < SEG) {
 #pragma unroll
           for (int u = 0; u < U; u++) rows0[u] = rows_n[u];
         }
       }
+      if (lane == 0) fq_sel_publish_agg(p, seg, &s_acc[b], wsum, nwarps);
     }
     if (threadIdx.x == 0 && active) {
       if (next_st && next_c < n_seg) fq_st_volatile(p.tile_status + next_c, FQ_TILE_PREFIX | p.stop_after);
@@ -973,6 +1078,196 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     keep1 = keepbits;
     seg1 = seg;
     pending += 1;   // no block-wide sync here: warps run ahead into the next segment on their own
+  }
+  if (err) atomicOr((fq_u32 *)(p.result + 1), err);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fq_select_tma_kernel — the select kernel with pass 1 staged by the bulk-copy engine.
+//
+// One CTA per SM = C consumer warps + 1 scan warp + 1 producer warp.  The producer lane claims segments
+// (atomicAdd), hands the ids to the other warps through a shared-memory ring and keeps a ring of `stages` tiles
+// in flight with cp.async.bulk (one copy per referenced column per tile, completion on full[s]); bytes in flight per
+// SM are therefore independent of the consumers' registers and of the time they spend in pass 2.  Consumers read
+// each staged tile with LDS.128 (lane l of warp w, group u: vector group w * 32U + 32u + l — the row order of
+// fq_tile_load, so pass 2 and the ranking code are shared with fq_select_kernel), evaluate the predicate, keep one
+// bit per row and per-(tile, warp) counts, and release the slot (one arrive per warp on empty[s]).  Scan warp,
+// look-back, named-barrier ring FULL/DONE and pass 2 (re-read of kept tiles from L2) are those of fq_select_kernel.
+// Tiles that are not entirely inside the source (the ragged end) are never staged: consumers load them with
+// fq_tile_load.  Producer and consumers count staged tiles with the same rule, so their slot/parity stay in step.
+// ---------------------------------------------------------------------------------------------
+template <int V> struct fq_selt_shape {
+  static constexpr int U = (FQ_SELT_UNROLL * V <= 32) ? FQ_SELT_UNROLL : (32 / V);
+  static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT_SEG : (64 / (U * V));
+};
+#define FQ_SELT_CLAIMS 16   // claim ring: the producer runs at most stages/SEG + 1 segments ahead of pass 1, the scan warp 2 behind
+
+template <class Q, int U, int SEG, int STAGES>
+__device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) {
+  constexpr int V = Q::V;
+  constexpr int BITS = U * V;
+  static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
+  extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
+  __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];
+  __shared__ fq_u64 s_excl[FQ_SEL_RING];
+  __shared__ unsigned long long s_acc[FQ_SEL_RING];
+  __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
+  __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
+  __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
+  __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];   // full[0..STAGES), empty[0..STAGES)
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cthreads = (int)blockDim.x - 64, cwarps = cthreads >> 5, barthreads = cthreads + 32;
+  const bool is_scan = (int)threadIdx.x >= cthreads && (int)threadIdx.x < cthreads + 32;
+  const bool is_producer = (int)threadIdx.x >= cthreads + 32;
+  const fq_u32 tile_groups = (fq_u32)cthreads * U;
+  const fq_u64 tile_rows = (fq_u64)tile_groups * V;
+  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u64 n_full_tiles = p.n_rows / tile_rows;
+  const fq_u64 n_seg = p.n_tiles;
+  const int stages = (int)p.stages;
+  fq_u32 err = 0;
+
+  if (threadIdx.x < FQ_SELT_CLAIMS) s_ready[threadIdx.x] = 0;
+  if (threadIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) {
+      fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
+      fq_mbar_init(fq_smem_addr(&s_bars[STAGES + s]), cwarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (is_producer) {
+    // ================= producer warp (one lane) =================
+    if (lane == 0) {
+      int slot = 0;          // ring slot and round of the next staged tile (no 64-bit divisions in the loop)
+      fq_u32 round = 0;
+      fq_u64 c = atomicAdd(p.tile_counter, 1u);
+      for (int k = 0;; k++) {
+        const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
+        // a claimed segment is always published: a successor's look-back may already be polling it
+        if (st && c < n_seg) fq_st_volatile(p.tile_status + c, FQ_TILE_PREFIX | p.stop_after);
+        s_seg[k % FQ_SELT_CLAIMS] = c;
+        s_stop[k % FQ_SELT_CLAIMS] = st;
+        __threadfence_block();
+        s_ready[k % FQ_SELT_CLAIMS] = k + 1;
+        if (!(c < n_seg) || st) break;
+        // the next claim's round trip to L2 overlaps the copies of this segment (its value is first used next iteration)
+        const fq_u64 c_next = atomicAdd(p.tile_counter, 1u);
+#pragma unroll 1
+        for (int t = 0; t < SEG; t++) {
+          const fq_u64 tile = c * SEG + t;
+          if (tile < n_full_tiles) {
+            if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
+            const fq_u32 full = fq_smem_addr(&s_bars[slot]);
+            fq_mbar_expect_tx(full, stage_bytes);
+            Q::tma_issue(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
+            if (++slot == stages) { slot = 0; round++; }
+          }
+        }
+        c = c_next;
+      }
+    }
+    return;
+  }
+
+  if (is_scan) {
+    // ================= scan warp =================
+    fq_i64 prev_seg = -1;      // the segment this CTA resolved last and its inclusive prefix (see fq_sel_lookback)
+    fq_u64 prev_incl = 0;
+    for (int k = 0;; k++) {
+      const int b = k % FQ_SEL_RING;
+      fq_bar_sync(FQ_BAR_FULL + b, barthreads);
+      const fq_u64 seg = s_seg[k % FQ_SELT_CLAIMS];
+      if (!(seg < n_seg) || s_stop[k % FQ_SELT_CLAIMS]) break;
+      const fq_u32 tot = fq_sel_scan_counts<SEG>(s_cnt[b], cwarps);
+      const fq_u64 excl = fq_sel_lookback(p, seg, tot, prev_seg, prev_incl);
+      prev_seg = (fq_i64)seg;
+      prev_incl = excl + tot;
+      if (lane == 0) {
+        s_excl[b] = excl;
+        const fq_u64 incl = excl + tot;
+        if (p.stop_after != 0 && incl >= p.stop_after) {
+          *(volatile fq_u32 *)p.done = 1u;
+          atomicMax(p.result, incl);
+        }
+        if (seg == n_seg - 1) atomicMax(p.result, incl);
+      }
+      __syncwarp();
+      fq_bar_arrive(FQ_BAR_DONE + b, barthreads);
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
+    fq_bar_sync(FQ_BAR_DONE + sb, barthreads);
+    fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, &err);
+  };
+  fq_u64 keep1 = 0, seg1 = 0, keep2 = 0, seg2 = 0;
+  int pending = 0;
+  int slot = 0;          // ring slot and round of the next staged tile (same count as the producer's)
+  fq_u32 round = 0;
+  for (int k = 0;; k++) {
+    const int b = k % FQ_SEL_RING;
+    if (lane == 0) {
+      while (s_ready[k % FQ_SELT_CLAIMS] != k + 1) {}
+    }
+    __syncwarp();
+    const fq_u64 seg = s_seg[k % FQ_SELT_CLAIMS];
+    const bool active = seg < n_seg && s_stop[k % FQ_SELT_CLAIMS] == 0;
+
+    fq_u64 keepbits = 0;
+    if (active) {
+      fq_u32 wsum = 0;
+#pragma unroll
+      for (int t = 0; t < SEG; t++) {
+        const fq_u64 tile = seg * SEG + t;
+        fq_u32 keep = 0;
+        if (tile < n_full_tiles) {
+          fq_mbar_wait(fq_smem_addr(&s_bars[slot]), round & 1);
+          const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
+          typename Q::Rows rows[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
+#pragma unroll
+          for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int v = 0; v < V; v++) keep |= (Q::pred(rows[u], v, err) ? 1u : 0u) << (u * V + v);
+          __syncwarp();
+          if (lane == 0) fq_mbar_arrive(fq_smem_addr(&s_bars[STAGES + slot]));
+          if (++slot == stages) { slot = 0; round++; }
+        } else {   // ragged or empty tile at the end of the source
+          typename Q::Rows rows[U];
+          fq_tile_load<Q, U>(p, tile, cthreads, rows);
+          keep = fq_tile_pred<Q, U>(p, tile, cthreads, rows, err);
+        }
+        keepbits |= (fq_u64)keep << (t * BITS);
+        const fq_u32 wcount = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
+        if (lane == 0) s_cnt[b][t][warp] = wcount;
+        wsum += wcount;
+      }
+      if (lane == 0) fq_sel_publish_agg(p, seg, &s_acc[b], wsum, cwarps);
+    }
+    __syncwarp();
+    fq_bar_arrive(FQ_BAR_FULL + b, barthreads);
+
+    if (pending == 2) {
+      scatter(seg2, keep2, (k + 1) % FQ_SEL_RING);
+      pending = 1;
+    }
+    if (!active) {
+      if (pending == 1) scatter(seg1, keep1, (k + 2) % FQ_SEL_RING);
+      break;
+    }
+    keep2 = keep1;
+    seg2 = seg1;
+    keep1 = keepbits;
+    seg1 = seg;
+    pending += 1;
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }

@@ -1,0 +1,131 @@
+"""Both select kernels (FQ_SEL_VARIANT = ldg | tma) against closed forms and the oracle: order-preserving compaction
+over ragged sizes around every tile / segment / ring boundary, dense and sparse selections, limits, early exit,
+several input columns of different widths, validity.  (transform_filter.rs:38-55, transform_projection.rs:45-56,
+stream_limit.rs:28-48.)  Integer results bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from fuse_query_b200 import cabi
+from oracle import binding as o
+
+pytestmark = pytest.mark.gpu
+NUM = "(col number)"
+README_PRED = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))"
+PROJ = [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"]
+
+
+@pytest.fixture(params=["ldg", "tma"])
+def variant(request):
+    old = os.environ.get("FQ_SEL_VARIANT")
+    os.environ["FQ_SEL_VARIANT"] = request.param     # read by the library at every launch
+    yield request.param
+    if old is None:
+        os.environ.pop("FQ_SEL_VARIANT", None)
+    else:
+        os.environ["FQ_SEL_VARIANT"] = old
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cabi.Context(0)
+    yield c
+    c.close()
+
+
+# tile = 4096 rows (tma) / 3072 rows (ldg); segment = 32768 / 24576 rows; 148 CTAs x 4-slot ring
+SIZES = [1, 2, 15, 4095, 4096, 4097, 16385, 24576, 24577, 32767, 32768, 32769, 65536 + 1, 148 * 32768 - 1, 148 * 32768,
+         148 * 32768 * 3 + 4097, 20_000_019]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_every_kth_row_is_kept_in_order(ctx, variant, n):
+    k = 7
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(PROJ, predicate=f"(= (* (/ {NUM} (u64 {k})) (u64 {k})) {NUM})")
+    want = np.arange(0, n, k, dtype=np.uint64)
+    outs = [ctx.column(cabi.U64, len(want) + 5), ctx.column(cabi.U64, len(want) + 5)]
+    pipe.launch_project(cabi.make_source([col], n), outs, len(want) + 5)
+    sel, written = pipe.fetch_project()
+    assert sel == written == len(want)
+    assert np.array_equal(outs[0].to_numpy(written), want + 1)
+    assert np.array_equal(outs[1].to_numpy(written), want // 2)
+    for c in outs + [col]:
+        c.free()
+    pipe.destroy()
+
+
+@pytest.mark.parametrize("n", [4097, 148 * 16384 + 33, 5_000_001])
+def test_all_rows_kept_and_none_kept(ctx, variant, n):
+    col = ctx.numbers(0, n)
+    src = cabi.make_source([col], n)
+    pipe = ctx.pipe(PROJ, predicate=f"(>= {NUM} (u64 0))")
+    outs = [ctx.column(cabi.U64, n), ctx.column(cabi.U64, n)]
+    pipe.launch_project(src, outs, n)
+    assert pipe.fetch_project() == (n, n)
+    assert np.array_equal(outs[0].to_numpy(n), np.arange(1, n + 1, dtype=np.uint64))
+    assert np.array_equal(outs[1].to_numpy(n), np.arange(n, dtype=np.uint64) // 2)
+    none = ctx.pipe(PROJ, predicate=f"(< {NUM} (u64 0))")
+    none.launch_project(src, outs, n)
+    assert none.fetch_project() == (0, 0)
+
+
+@pytest.mark.parametrize("limit,early", [(3, False), (3, True), (1000, True), (0, False)])
+def test_readme_query_with_limit(ctx, variant, limit, early):
+    n = 30_000_011
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(PROJ, predicate=README_PRED)
+    outs = [ctx.column(cabi.U64, 128), ctx.column(cabi.U64, 128)]
+    pipe.launch_project(cabi.make_source([col], n), outs, 128, limit=limit, early_exit=early)
+    sel, written = pipe.fetch_project()
+    w = min(limit, 66)
+    assert written == w
+    assert sel >= w if early else sel == 66          # with early exit only a lower bound is known
+    assert np.array_equal(outs[0].to_numpy(w), np.arange(1, w + 1, dtype=np.uint64))
+    assert np.array_equal(outs[1].to_numpy(w), np.arange(w, dtype=np.uint64) // 2)
+
+
+def test_early_exit_in_the_middle_of_a_long_scan(ctx, variant):
+    n = 40_000_000
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe([NUM], predicate=f"(>= {NUM} (u64 20000000))")
+    outs = [ctx.column(cabi.U64, 10)]
+    pipe.launch_project(cabi.make_source([col], n), outs, 10, limit=10, early_exit=True)
+    sel, written = pipe.fetch_project()
+    assert written == 10 and sel >= 10
+    assert np.array_equal(outs[0].to_numpy(10), np.arange(20_000_000, 20_000_010, dtype=np.uint64))
+
+
+def test_mixed_width_nullable_columns_match_oracle(ctx, variant):
+    n = 300_017
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 1 << 40, n, dtype=np.uint64)
+    b = rng.integers(-1000, 1000, n).astype(np.int16)
+    c = rng.normal(0, 100, n)
+    av = (rng.random(n) > 0.25).astype(np.uint8)
+    cols = [ctx.from_numpy(a, av), ctx.from_numpy(b), ctx.from_numpy(c)]
+    table = {"a": o.array(o.U64, a, av), "b": o.array(o.I16, b), "c": o.array(o.F64, c)}
+    exprs = ["(+ (col a) (col b))", "(* (col c) (col b))", "(col b)"]
+    pred = "(and (> (col b) (i16 -500)) (< (col a) (u64 800000000000)))"
+    want = o.run_query(exprs, table=table, predicate=pred, worker_threads=1, tail_quirk=False)
+    pipe = ctx.pipe(exprs, columns=["a", "b", "c"], dtypes=[cabi.U64, cabi.I16, cabi.F64], predicate=pred, nullable=[True, False, False])
+    outs = [ctx.column(pipe.expr_dtype(i), n) for i in range(3)]
+    ov = [ctx.column(cabi.BOOL, n) if pipe.expr_nullable(i) else None for i in range(3)]
+    pipe.launch_project(cabi.make_source(cols, n), outs, n, out_valid=ov)
+    sel, written = pipe.fetch_project()
+    assert sel == written == want.n_rows > 0
+    for i, wc in enumerate(want.columns):
+        wv = np.ones(written, np.uint8) if wc.valid is None else wc.valid
+        gv = np.ones(written, np.uint8) if ov[i] is None else ov[i].to_numpy(written)
+        assert np.array_equal(gv, wv)
+        m = wv.astype(bool)
+        assert np.array_equal(outs[i].to_numpy(written)[m].astype(wc.values.dtype), wc.values[m], equal_nan=wc.dtype == o.F64)
+
+
+def test_variants_launch_different_kernels(ctx):
+    """The environment switch must really select another kernel (both are precompiled for the README pipe)."""
+    pipe = ctx.pipe(PROJ, predicate=README_PRED)
+    assert pipe.precompiled
+    src = pipe.source
+    assert "_select_tma(" in src and "_select(" in src
