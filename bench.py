@@ -198,6 +198,32 @@ def cpu_model():
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process (and so the first-touch placement of its pinned host buffers) to the CPUs of the NUMA node
+    the GPU hangs off: with 8 ranks the e2e leg otherwise pulls half of its host column across the socket link.
+    Returns a short description for the JSON line; does nothing when sysfs does not say."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: unknown"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} cpus)"
+    except Exception as e:  # sysfs layout differs / container hides it: keep the default placement
+        return f"numa: not bound ({type(e).__name__})"
+
+
 class DevPtr:
     """__cuda_array_interface__ view of a raw device buffer (the pipe's running state) for torch."""
 
@@ -217,6 +243,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "numa: single rank, not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = cabi.Context(local)
@@ -353,6 +380,7 @@ def run_ours(args):
             "config": {"workload": HEADLINE_SQL if total == TOTAL_ROWS else HEADLINE_SQL.replace("10000000000", str(total)),
                        "rows_total": total, "rows_per_gpu": n, "source": args.mode,
                        "partitioning": f"{8 // world if world <= 8 else 1} of the reference's 8 partitions per GPU",
+                       "host_affinity": numa,
                        "l2": "inputs (>= 10 GB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "merge": "nccl all_gather of the 64-byte state" if world > 1 else "single GPU",
                        "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},

@@ -327,14 +327,13 @@ fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_param
     if (c >= src->n_cols || !src->cols || !src->cols[c]) return set_err(FQ_ERR_INVALID, "Internal Error: source lacks column %d", c);
     const fq_column *col = src->cols[c];
     if (col->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: column %d has %" PRIu64 " rows, source says %" PRIu64, c, col->len, src->n_rows);
-    if (((uintptr_t)col->ptr & 15) != 0) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: column %d is not 16-byte aligned", c);
+    if (((uintptr_t)col->ptr & 15) != 0) p->unaligned = 1;   // a slice off the 16-byte grid: the kernels read it row by row
     p->cols[c] = col->ptr;
     const bool want_valid = std::find(pipe->gen.null_cols.begin(), pipe->gen.null_cols.end(), c) != pipe->gen.null_cols.end();
     if (want_valid) {
       if (!col->validity) return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a nullable column %d but the column carries no validity", c);
       if (col->validity->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: validity of column %d is shorter than the source", c);
-      if (((uintptr_t)col->validity->ptr & 15) != 0)
-        return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: validity of column %d is not 16-byte aligned", c);
+      if (((uintptr_t)col->validity->ptr & 15) != 0) p->unaligned = 1;
       p->cols_valid[c] = col->validity->ptr;
     } else if (col->validity) {
       return set_err(FQ_ERR_INVALID, "Internal Error: column %d carries validity but the pipe was compiled for a NOT NULL column", c);

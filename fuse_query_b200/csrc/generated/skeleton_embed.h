@@ -78,6 +78,7 @@ struct fq_launch_params {
   fq_u32 accumulate;
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
+  fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -153,11 +154,11 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
-// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
+// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is t)FQSK"
+R"FQSK(hat wide.
 // `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
 template <class T, int V>
-__de)FQSK"
-R"FQSK(vice__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
+__device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
   constexpr int BYTES = V * (int)sizeof(T);
   char *p = (char *)base + first * sizeof(T);
   if constexpr (BYTES >= 16) {
@@ -300,10 +301,10 @@ template <class T> __device__ __forceinline__ T fq_shfl_xor(T x, int m) {
 // ---------------------------------------------------------------------------------------------
 // block-level reduction of a generated accumulator:  registers -> warp shuffles -> shared -> warp 0
 // result valid in thread 0
-// ---------------------------------------------------------------------------------------------
+// -----------------------------------------------------------------)FQSK"
+R"FQSK(----------------------------
 template <class Q>
-__device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &nsel, fq_u32)FQSK"
-R"FQSK( &err,
+__device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &nsel, fq_u32 &err,
                                                 fq_u64 (*sm)[FQ_STATE_HDR + Q::NSLOTS]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
 #pragma unroll
@@ -473,7 +474,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   fq_u32 err = 0;
   fq_u64 nsel = 0;
 
-  const fq_u64 nvec = p.n_rows / V;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;   // unaligned slices: everything through the row-by-row tail
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
   for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {
@@ -497,13 +498,13 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
-    fq_u32 kept = 0;
+    fq_u3)FQSK"
+R"FQSK(2 kept = 0;
 #pragma unroll
     for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
     if constexpr (Q::TRACK_BLOCKS) {
       if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
-)FQSK"
-R"FQSK(    }
+    }
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
@@ -583,7 +584,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
-  const fq_u64 n_tiles = p.n_rows / tile_rows;   // full tiles only
+  const fq_u64 n_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // full tiles only (none when a column is an unaligned slice)
   const int stages = (int)p.stages;
 
   if (threadIdx.x == 0) {
@@ -636,7 +637,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
     // rows past the last full tile: plain loads, spread over the consumers of the whole grid
     const fq_u64 ctid = (fq_u64)blockIdx.x * cthreads + threadIdx.x;
     const fq_u64 cn = (fq_u64)gridDim.x * cthreads;
-    const fq_u64 nvec = p.n_rows / V;
+    const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
     for (fq_u64 g = n_tiles * tile_groups + ctid; g < nvec; g += cn) {
       typename Q::Rows r;
       Q::load(r, p, g);
@@ -663,12 +664,12 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 // fq_select_kernel — fused predicate + order-preserving stream compaction + projection (+ limit).
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
-// (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
+// (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at)FQSK"
+R"FQSK(
 // tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are assigned round-robin to
 // the CTAs of a persistent, fully resident grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
-//                 )FQSK"
-R"FQSK(    row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
+//                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
 //   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
 //                     segment's global base by a decoupled look-back over 64-bit descriptors {flag:2, count:62};
 //   workers, pass 2   (one segment behind) warps that selected something in a tile re-read that tile (still in the
@@ -701,7 +702,7 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
     for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
   } else if (tile * tile_groups * V < p.n_rows) {
@@ -725,7 +726,7 @@ __device__ __forceinline__ fq_u32 fq_tile_pred(const fq_launch_params &p, fq_u64
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   fq_u32 keep = 0;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
@@ -804,11 +805,11 @@ __device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq
 // resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
 // and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
 // published prefix, prefixes are published only when a look-back ends, and with hundreds of segments in flight the
-// chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
+// chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segme)FQSK"
+R"FQSK(nt per look-back latency).  Bounded by
 // the CTA's own history the walk is 1-2 polls of FQ_SEL_LOOK * 32 descriptors, independent of the others' progress.
 // A nearer published prefix still ends the walk early; the first segment of a CTA (prev_seg < 0) walks to one.
-__device__ __forceinline__ fq_u64 fq_sel_lookback(const fq_la)FQSK"
-R"FQSK(unch_params &p, fq_u64 seg, fq_u32 tot, fq_i64 prev_seg, fq_u64 prev_incl) {
+__device__ __forceinline__ fq_u64 fq_sel_lookback(const fq_launch_params &p, fq_u64 seg, fq_u32 tot, fq_i64 prev_seg, fq_u64 prev_incl) {
   const int lane = threadIdx.x & 31;
   fq_u64 excl = 0;
   if (seg == 0) return 0;   // its descriptor (a prefix) was published by the workers, like every aggregate
@@ -862,7 +863,7 @@ __device__ __forceinline__ void fq_group_load(const fq_launch_params &p, fq_u64 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   const fq_u64 g = tile * tile_groups + (fq_u64)warp * 32 * U + lane + 32ull * u;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
     Q::load(r, p, g);
   } else {
 #pragma unroll
@@ -971,7 +972,8 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   // early-exit flag happen together: a claimed segment is ALWAYS published (a successor may already be polling it); a CTA
   // that sees the flag publishes a saturated prefix for the segment it just claimed and leaves.
   // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and hands it to the other warps through a
-  // shared-memory ring (s_ready[slot] == k + 2): no block-wide barrier per segment, warps run ahead on their own.
+  // shared-memory ring (s_ready[slot])FQSK"
+R"FQSK( == k + 2): no block-wide barrier per segment, warps run ahead on their own.
   auto publish_claim = [&](int k, fq_u64 c, fq_u32 st) {   // claim of iteration k
     s_seg[k & 3] = c;
     s_stop[k & 3] = st;
@@ -979,8 +981,7 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     s_ready[k & 3] = k + 1;
   };
   if (threadIdx.x >= 1 && threadIdx.x < 4) s_ready[threadIdx.x] = 0;
-  if (thre)FQSK"
-R"FQSK(adIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
+  if (threadIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     const fq_u64 c = atomicAdd(p.tile_counter, 1u);
     const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
@@ -1130,13 +1131,14 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
-  const fq_u64 n_full_tiles = p.n_rows / tile_rows;
+  const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
   const int stages = (int)p.stages;
   fq_u32 err = 0;
 
   if (threadIdx.x < FQ_SELT_CLAIMS) s_ready[threadIdx.x] = 0;
-  if (threadIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
+  if (threadIdx.x < FQ_SEL_RING) s_acc[thre)FQSK"
+R"FQSK(adIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; s++) {
       fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
@@ -1148,8 +1150,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   __syncthreads();
 
   if (is_producer) {
-    // ================= producer wa)FQSK"
-R"FQSK(rp (one lane) =================
+    // ================= producer warp (one lane) =================
     if (lane == 0) {
       int slot = 0;          // ring slot and round of the next staged tile (no 64-bit divisions in the loop)
       fq_u32 round = 0;
@@ -1287,7 +1288,7 @@ template <class Q, int UNROLL>
 __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
   fq_u32 err = 0;
-  const fq_u64 nvec = p.n_rows / V;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
   for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {

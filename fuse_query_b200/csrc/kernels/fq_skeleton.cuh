@@ -77,6 +77,7 @@ struct fq_launch_params {
   fq_u32 accumulate;
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
+  fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -470,7 +471,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   fq_u32 err = 0;
   fq_u64 nsel = 0;
 
-  const fq_u64 nvec = p.n_rows / V;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;   // unaligned slices: everything through the row-by-row tail
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
   for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {
@@ -579,7 +580,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
-  const fq_u64 n_tiles = p.n_rows / tile_rows;   // full tiles only
+  const fq_u64 n_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // full tiles only (none when a column is an unaligned slice)
   const int stages = (int)p.stages;
 
   if (threadIdx.x == 0) {
@@ -632,7 +633,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
     // rows past the last full tile: plain loads, spread over the consumers of the whole grid
     const fq_u64 ctid = (fq_u64)blockIdx.x * cthreads + threadIdx.x;
     const fq_u64 cn = (fq_u64)gridDim.x * cthreads;
-    const fq_u64 nvec = p.n_rows / V;
+    const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
     for (fq_u64 g = n_tiles * tile_groups + ctid; g < nvec; g += cn) {
       typename Q::Rows r;
       Q::load(r, p, g);
@@ -696,7 +697,7 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
     for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
   } else if (tile * tile_groups * V < p.n_rows) {
@@ -720,7 +721,7 @@ __device__ __forceinline__ fq_u32 fq_tile_pred(const fq_launch_params &p, fq_u64
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   fq_u32 keep = 0;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
@@ -856,7 +857,7 @@ __device__ __forceinline__ void fq_group_load(const fq_launch_params &p, fq_u64 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const fq_u64 tile_groups = (fq_u64)wthreads * U;
   const fq_u64 g = tile * tile_groups + (fq_u64)warp * 32 * U + lane + 32ull * u;
-  if ((tile + 1) * tile_groups * V <= p.n_rows) {
+  if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
     Q::load(r, p, g);
   } else {
 #pragma unroll
@@ -1123,7 +1124,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
-  const fq_u64 n_full_tiles = p.n_rows / tile_rows;
+  const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
   const int stages = (int)p.stages;
   fq_u32 err = 0;
@@ -1279,7 +1280,7 @@ template <class Q, int UNROLL>
 __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
   fq_u32 err = 0;
-  const fq_u64 nvec = p.n_rows / V;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
   for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {

@@ -56,6 +56,26 @@ def register_table(ctx, gpu, db: str, name: str, columns: Mapping[str, "np.ndarr
     return table
 
 
+def register_parquet(ctx, gpu, db: str, name: str, path, columns=None):
+    """Read a Parquet file (or a directory of them) column by column into HBM and register it as table `db.name`:
+    the reference's "table storage engine" slot (`datasources/table.rs:13-22`, README "Remote (S3 or other table
+    storage engine)") filled with the one format this image can decode (pyarrow).  Decoding is host work done once at
+    registration; queries then run against the resident columns.  `columns` restricts what is loaded."""
+    import pyarrow.parquet as pq
+    return register_table(ctx, gpu, db, name, pq.read_table(str(path), columns=list(columns) if columns else None))
+
+
+def register_arrow_ipc(ctx, gpu, db: str, name: str, path, columns=None):
+    """Same for an Arrow IPC (Feather v2) file, memory-mapped: the uploads read straight from the page cache."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+    with pa.memory_map(str(path), "r") as f:
+        tbl = ipc.open_file(f).read_all()
+        if columns:
+            tbl = tbl.select(list(columns))
+        return register_table(ctx, gpu, db, name, tbl)
+
+
 def _has_db(ds, db: str) -> bool:
     try:
         ds.get_table(db, "\0")

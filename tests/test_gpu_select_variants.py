@@ -123,6 +123,50 @@ def test_mixed_width_nullable_columns_match_oracle(ctx, variant):
         assert np.array_equal(outs[i].to_numpy(written)[m].astype(wc.values.dtype), wc.values[m], equal_nan=wc.dtype == o.F64)
 
 
+@pytest.mark.parametrize("off", [1, 3, 8, 13, 16, 10_001])
+def test_unaligned_slices_fall_back_to_row_loads(ctx, variant, off):
+    """A slice that does not start on a 16-byte boundary (MemoryTable partitions of odd sizes, arrow::Array::slice in the
+    reference) is read row by row: select, projection-only and aggregate pipes, both aggregate kernels."""
+    n_all, n = 700_000, 650_003
+    rng = np.random.default_rng(off)
+    a = rng.integers(0, 1 << 40, n_all, dtype=np.uint64)
+    b = rng.integers(-100, 100, n_all).astype(np.int8)
+    bv = (rng.random(n_all) > 0.3).astype(np.uint8)
+    A, B = ctx.from_numpy(a), ctx.from_numpy(b, bv)
+    sa, sb = A.slice(off, n), B.slice(off, n)
+    src = cabi.make_source([sa, sb], n)
+    x, y, yv = a[off:off + n], b[off:off + n].astype(np.int64), bv[off:off + n].astype(bool)
+    kw = dict(columns=["a", "b"], dtypes=[cabi.U64, cabi.I8], nullable=[False, True])
+    # filter + projection
+    pipe = ctx.pipe(["(col a)", "(+ (col a) (col b))"], predicate="(> (col b) (i8 10))", **kw)
+    outs = [ctx.column(cabi.U64, n), ctx.column(cabi.I64, n)]
+    ov = [None, ctx.column(cabi.BOOL, n)]
+    pipe.launch_project(src, outs, n, out_valid=ov)
+    sel, written = pipe.fetch_project()
+    keep = yv & (y > 10)
+    assert sel == written == int(keep.sum())
+    assert np.array_equal(outs[0].to_numpy(written), x[keep])
+    assert np.array_equal(outs[1].to_numpy(written), (x[keep].astype(np.int64) + y[keep]))
+    assert ov[1].to_numpy(written).all()
+    # projection only
+    pipe = ctx.pipe(["(* (col a) (u64 3))"], **kw)
+    out = ctx.column(cabi.U64, n)
+    pipe.launch_project(src, [out], n)
+    assert pipe.fetch_project() == (n, n)
+    assert np.array_equal(out.to_numpy(n), x * np.uint64(3))
+    # aggregates (bulk-copy staged and LDG kernels)
+    for agg_variant in ("tma", "u4"):
+        os.environ["FQ_AGG_VARIANT"] = agg_variant
+        try:
+            pipe = ctx.pipe(["(sum (col a))", "(max (col b))", "(count (col a))", "(min (col a))"], aggregate=True, **kw)
+            pipe.launch_aggregate(src)
+            states, rows = pipe.fetch_aggregate()
+        finally:
+            os.environ.pop("FQ_AGG_VARIANT", None)
+        assert rows == n
+        assert [v for _, v in states] == [int(x.sum(dtype=np.uint64)), int(y[yv].max()), n, int(x.min())]
+
+
 def test_variants_launch_different_kernels(ctx):
     """The environment switch must really select another kernel (both are precompiled for the README pipe)."""
     pipe = ctx.pipe(PROJ, predicate=README_PRED)

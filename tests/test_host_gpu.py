@@ -419,6 +419,38 @@ def test_nullable_memory_table_sql_matches_oracle(gpu):
         assert rows_of(blocks) == want.rows()
 
 
+def test_parquet_and_arrow_ipc_files_become_resident_tables(gpu, tmp_path):
+    """a real ITable fed from column files.  Same queries, same oracle."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+    import pyarrow.parquet as pq
+    from fuse_query_b200.tables import register_arrow_ipc, register_parquet
+    rng = np.random.default_rng(11)
+    n = 50_000
+    price = rng.integers(1, 10_000, n, dtype=np.int64)
+    qty = rng.integers(1, 100, n, dtype=np.uint32)
+    disc = np.round(rng.random(n), 3)
+    dv = rng.random(n) > 0.2
+    tbl = pa.table({"price": pa.array(price), "qty": pa.array(qty), "disc": pa.array(disc, mask=~dv), "unused": pa.array(price)})
+    pq.write_table(tbl, tmp_path / "t.parquet", row_group_size=7_000)
+    with ipc.new_file(str(tmp_path / "t.arrow"), tbl.schema) as w:
+        w.write_table(tbl, max_chunksize=9_999)
+    table = {"price": o.array(o.I64, price), "qty": o.array(o.U32, qty), "disc": o.array(o.F64, disc, dv.astype(np.uint8))}
+    for reg, fname, tname in ((register_parquet, "t.parquet", "pq"), (register_arrow_ipc, "t.arrow", "ipc")):
+        ctx = make_ctx(gpu, 1, fuse=True)
+        t = reg(ctx, gpu, "default", tname, tmp_path / fname, columns=["price", "qty", "disc"])
+        assert t.schema().names() == ["price", "qty", "disc"] and t.num_rows() == n
+        assert [f.nullable for f in t.schema().fields] == [False, False, True]
+        got = rows_of(h.execute_sql(ctx, f"select sum(price * qty), max(disc), min(price / qty), count(disc) from {tname} where qty > 10"))
+        want = o.run_query(["(sum (* (col price) (col qty)))", "(max (col disc))", "(min (/ (col price) (col qty)))", "(count (col disc))"],
+                           table=table, predicate="(> (col qty) (u64 10))", is_aggregate=True, worker_threads=1, tail_quirk=False)
+        assert got == want.rows()
+        got = rows_of(h.execute_sql(ctx, f"select price, disc * qty from {tname} where disc < 0.5 limit 25"))
+        want = o.run_query(["(col price)", "(* (col disc) (col qty))"], table=table, predicate="(< (col disc) (f64 0.5))", limit=25,
+                           worker_threads=1, tail_quirk=False)
+        assert got == want.rows() and len(got) == 25
+
+
 def test_pyarrow_table_with_nulls_registers_nullable_fields(gpu):
     import pyarrow as pa
     from fuse_query_b200.tables import register_table
