@@ -138,15 +138,15 @@ def test_unaligned_slices_fall_back_to_row_loads(ctx, variant, off):
     x, y, yv = a[off:off + n], b[off:off + n].astype(np.int64), bv[off:off + n].astype(bool)
     kw = dict(columns=["a", "b"], dtypes=[cabi.U64, cabi.I8], nullable=[False, True])
     # filter + projection
-    pipe = ctx.pipe(["(col a)", "(+ (col a) (col b))"], predicate="(> (col b) (i8 10))", **kw)
-    outs = [ctx.column(cabi.U64, n), ctx.column(cabi.I64, n)]
+    pipe = ctx.pipe(["(col a)", "(* (col b) (i8 2))"], predicate="(> (col b) (i8 10))", **kw)
+    outs = [ctx.column(cabi.U64, n), ctx.column(cabi.I8, n)]
     ov = [None, ctx.column(cabi.BOOL, n)]
     pipe.launch_project(src, outs, n, out_valid=ov)
     sel, written = pipe.fetch_project()
     keep = yv & (y > 10)
     assert sel == written == int(keep.sum())
     assert np.array_equal(outs[0].to_numpy(written), x[keep])
-    assert np.array_equal(outs[1].to_numpy(written), (x[keep].astype(np.int64) + y[keep]))
+    assert np.array_equal(outs[1].to_numpy(written), (y[keep] * 2).astype(np.int8))   # Int8 * Int8 wraps
     assert ov[1].to_numpy(written).all()
     # projection only
     pipe = ctx.pipe(["(* (col a) (u64 3))"], **kw)
