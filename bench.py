@@ -337,6 +337,22 @@ def run_ours(args):
                 per_query.setdefault(name, {})[mode] = {"ms": round(q_ms, 4), "rows_per_s": n / (q_ms * 1e-3),
                                                         "gb_per_s": (0 if g else 8) * n / (q_ms * 1e-3) / 1e9}
                 p.destroy()
+        # BASELINE configs[0] (the reference's own CPU-runnable case: 80 MB, fits in L2 — a latency figure, not bandwidth)
+        n0 = min(n, 10_000_000)
+        for mode in ("materialised", "generated"):
+            g = mode == "generated"
+            if g is False and generated:
+                continue
+            s0 = cabi.make_source([] if g else [col], n0, generated=g, begin=begin)
+            p = ctx.pipe([f"(sum {NUM})"], aggregate=True, generated=g)
+            per_query.setdefault("cfg0: sum(number) @1e7 (L2-resident, launch-latency bound)", {})[mode] = time_launches(
+                torch, lambda: p.launch_aggregate(s0, stream=stream), n0, 0 if g else 8)
+            p.destroy()
+        # the Source itself: fq_numbers_fill materialising 10^9 rows (numbers_stream.rs:68-83), write-only
+        if col is not None:
+            per_query["source: fill 1e9 rows"] = {"materialised": time_launches(
+                torch, lambda: ctx.fill_numbers(col, begin, min(n, 1_000_000_000), stream),
+                min(n, 1_000_000_000), 8)}
         # BASELINE configs[1] and [2] on the first 10^9 rows of the shard
         n2 = min(n, 1_000_000_000)
         for mode in ("materialised", "generated"):
@@ -396,6 +412,16 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": rows / secs_cpu, "unit": "rows/s", "cores": min(8, os.cpu_count() or 1), "kind": "port",
                                    "sample": f"{rows} rows of the same query through the oracle's reference-shaped pipeline "
                                              f"(8 partitions, 10 000-row blocks, one pass per aggregate), {secs_cpu:.2f} s; cpu: {cpu_model()}"}
+            # the best a CPU could do with this query, NOT the reference's structure: one fused pass per
+            # thread over numbers generated in registers, all host threads.  Reported beside the baseline, not as it.
+            from oracle import binding as _o
+            nthreads = os.cpu_count() or 1
+            _o.fused_headline(1_000_000_000, nthreads)
+            secs_best, res_best = _o.fused_headline(TOTAL_ROWS, nthreads)
+            assert res_best == [(TOTAL_ROWS * (TOTAL_ROWS - 1) // 2) % (1 << 64), TOTAL_ROWS, TOTAL_ROWS - 1, 0], res_best
+            out["cpu_baseline"]["best_case_fused"] = {"value": TOTAL_ROWS / secs_best, "unit": "rows/s", "cores": nthreads,
+                                                      "note": "hand-fused single pass, generated in registers, vectorised by gcc -O3 -march=native; "
+                                                              "compare with per_query[...]['generated'], not with the materialised scan"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -251,6 +251,10 @@ class Context:
         self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
         return col
 
+    def fill_numbers(self, col: "Column", begin: int, n: int, stream: int = 0, row_offset: int = 0) -> None:
+        """col[row_offset : row_offset + n] = begin .. begin + n - 1 (NumbersStream::poll_next on the device)."""
+        self.check(lib().fq_numbers_fill(self._h, col._h, row_offset, begin, n, C.c_void_p(stream)))
+
     def from_numpy(self, a, valid=None, stream: int = 0) -> "Column":
         """Upload values; `valid` (bool / 0-1 array, one entry per row) attaches a validity column."""
         import numpy as np

@@ -133,7 +133,7 @@ struct Shapes {
   int tma_stages_env = 0;   // FQ_TUNE_TMA_STAGES: ring depth override (<= FQ_TMA_STAGES)
   int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
   int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
-  int selt_threads = FQ_SELT_THREADS, selt_unroll = FQ_SELT_UNROLL, selt_seg = FQ_SELT_SEG;
+  int selt_threads = FQ_SELT_THREADS, selt_unroll = FQ_SELT_UNROLL, selt_seg = FQ_SELT_SEG, selt_lag = FQ_SELT_LAG;
   int selt_stages_env = 0;  // FQ_TUNE_SELT_STAGES: ring depth override (<= FQ_SELT_STAGES)
   bool tuned = false;
   Shapes() {
@@ -147,18 +147,18 @@ struct Shapes {
     if (getenv("FQ_TUNE_TMA_STAGES") && atoi(getenv("FQ_TUNE_TMA_STAGES")) > 0) tma_stages_env = atoi(getenv("FQ_TUNE_TMA_STAGES"));
     env("FQ_TUNE_TMA_MIN_BLOCKS", &tma_min_blocks);
     env("FQ_TUNE_SEL_THREADS", &sel_threads); env("FQ_TUNE_SEL_MIN_BLOCKS", &sel_min_blocks); env("FQ_TUNE_SEL_UNROLL", &sel_unroll); env("FQ_TUNE_SEL_SEG", &sel_seg); env("FQ_TUNE_SEL_LOOK", &sel_look);
-    env("FQ_TUNE_SELT_THREADS", &selt_threads); env("FQ_TUNE_SELT_UNROLL", &selt_unroll); env("FQ_TUNE_SELT_SEG", &selt_seg);
+    env("FQ_TUNE_SELT_THREADS", &selt_threads); env("FQ_TUNE_SELT_UNROLL", &selt_unroll); env("FQ_TUNE_SELT_SEG", &selt_seg); env("FQ_TUNE_SELT_LAG", &selt_lag);
     if (getenv("FQ_TUNE_SELT_STAGES") && atoi(getenv("FQ_TUNE_SELT_STAGES")) > 0) selt_stages_env = atoi(getenv("FQ_TUNE_SELT_STAGES"));
     env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
   }
   std::string defines() const {
     char b[1536];
     snprintf(b, sizeof b,
-             "#define FQ_SELT_THREADS %d\n#define FQ_SELT_UNROLL %d\n#define FQ_SELT_SEG %d\n#define FQ_SELT_STAGES 8\n"
+             "#define FQ_SELT_THREADS %d\n#define FQ_SELT_UNROLL %d\n#define FQ_SELT_SEG %d\n#define FQ_SELT_STAGES 8\n#define FQ_SELT_LAG %d\n"
              "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_TMA_THREADS %d\n"
              "#define FQ_TMA_UNROLL %d\n#define FQ_TMA_STAGES %d\n#define FQ_TMA_MIN_BLOCKS %d\n#define FQ_SEL_THREADS %d\n"
              "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
-             selt_threads, selt_unroll, selt_seg, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
+             selt_threads, selt_unroll, selt_seg, selt_lag, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
     return b;
   }
 };
@@ -546,10 +546,11 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     } else if (gen.has_pred) {
       s2 = resolve_kernel(m, base + "_select", shapes().sel_threads + 32, &pipe->k_select);   // worker warps + one scan warp
       if (!s2 && gen.tma_ok) {
-        // staged variant: consumer warps + scan warp + producer warp; ring of ~128 KB per CTA, at least 2 tiles
+        // staged variant: consumer warps + scan warp + producer warp; ring of ~192 KB per CTA, at least 2 tiles
         const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
         const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.row_bytes;
-        unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (128u * 1024u) / tile_bytes;
+        // ~192 KB in flight per SM measured best here (1.19 -> 1.14 ms at 1e9 rows; the aggregate kernel peaks at 128 KB)
+        unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (192u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);
         if (stages * tile_bytes <= 200 * 1024) {
           s2 = resolve_kernel(m, base + "_select_tma", shapes().selt_threads + 64, &pipe->k_select_tma, stages * tile_bytes);

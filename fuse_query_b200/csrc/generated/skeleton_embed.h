@@ -57,7 +57,8 @@ typedef signed char fq_i8;
 #define FQ_SELT_THREADS 512  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp)
 #define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
 #define FQ_SELT_SEG 8        // tiles per segment (one look-back each): 256 KB of a UInt64 column
-#define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~128 KB in flight per SM)
+#define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~192 KB in flight per SM)
+#define FQ_SELT_LAG 3        // pass 2 runs this many segments behind pass 1
 #endif
 
 #define FQ_STATE_HDR 6        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned,
@@ -154,8 +155,8 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
-// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is t)FQSK"
-R"FQSK(hat wide.
+// Store V consecutive )FQSK"
+R"FQSK(values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
 // `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
 template <class T, int V>
 __device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
@@ -300,9 +301,9 @@ template <class T> __device__ __forceinline__ T fq_shfl_xor(T x, int m) {
 
 // ---------------------------------------------------------------------------------------------
 // block-level reduction of a generated accumulator:  registers -> warp shuffles -> shared -> warp 0
-// result valid in thread 0
-// -----------------------------------------------------------------)FQSK"
-R"FQSK(----------------------------
+// result valid in )FQSK"
+R"FQSK(thread 0
+// ---------------------------------------------------------------------------------------------
 template <class Q>
 __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &nsel, fq_u32 &err,
                                                 fq_u64 (*sm)[FQ_STATE_HDR + Q::NSLOTS]) {
@@ -495,11 +496,11 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   // remainder groups (< one chunk) and the scalar tail (< V rows), spread over the whole grid
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
-  for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
+  for (fq_u64 g = nfull * chunk + tid; g < n)FQSK"
+R"FQSK(vec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
-    fq_u3)FQSK"
-R"FQSK(2 kept = 0;
+    fq_u32 kept = 0;
 #pragma unroll
     for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
     if constexpr (Q::TRACK_BLOCKS) {
@@ -664,8 +665,8 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 // fq_select_kernel — fused predicate + order-preserving stream compaction + projection (+ limit).
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
-// (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at)FQSK"
-R"FQSK(
+// (tile = 32 * W)FQSK"
+R"FQSK( * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
 // tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are assigned round-robin to
 // the CTAs of a persistent, fully resident grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
@@ -805,8 +806,8 @@ __device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq
 // resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
 // and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
 // published prefix, prefixes are published only when a look-back ends, and with hundreds of segments in flight the
-// chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segme)FQSK"
-R"FQSK(nt per look-back latency).  Bounded by
+//)FQSK"
+R"FQSK( chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
 // the CTA's own history the walk is 1-2 polls of FQ_SEL_LOOK * 32 descriptors, independent of the others' progress.
 // A nearer published prefix still ends the walk early; the first segment of a CTA (prev_seg < 0) walks to one.
 __device__ __forceinline__ fq_u64 fq_sel_lookback(const fq_launch_params &p, fq_u64 seg, fq_u32 tot, fq_i64 prev_seg, fq_u64 prev_incl) {
@@ -971,9 +972,9 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   // segment has started and the look-back makes progress whatever else shares the GPU.  Claiming and observing the
   // early-exit flag happen together: a claimed segment is ALWAYS published (a successor may already be polling it); a CTA
   // that sees the flag publishes a saturated prefix for the segment it just claimed and leaves.
-  // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and hands it to the other warps through a
-  // shared-memory ring (s_ready[slot])FQSK"
-R"FQSK( == k + 2): no block-wide barrier per segment, warps run ahead on their own.
+  // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and)FQSK"
+R"FQSK( hands it to the other warps through a
+  // shared-memory ring (s_ready[slot] == k + 2): no block-wide barrier per segment, warps run ahead on their own.
   auto publish_claim = [&](int k, fq_u64 c, fq_u32 st) {   // claim of iteration k
     s_seg[k & 3] = c;
     s_stop[k & 3] = st;
@@ -1115,10 +1116,14 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   constexpr int V = Q::V;
   constexpr int BITS = U * V;
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
+  constexpr int LAG = FQ_SELT_LAG;            // pass 2 runs this many segments behind pass 1 (absorbs the skew between CTAs)
+  constexpr int R = LAG + 1;                  // ring of count / base slots and of FULL / DONE named barriers
+  constexpr int BAR_FULL = 2, BAR_DONE = 2 + R;
+  static_assert(2 + 2 * R <= 16, "named barriers");
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
-  __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];
-  __shared__ fq_u64 s_excl[FQ_SEL_RING];
-  __shared__ unsigned long long s_acc[FQ_SEL_RING];
+  __shared__ fq_u32 s_cnt[R][SEG][FQ_MAX_WARPS];
+  __shared__ fq_u64 s_excl[R];
+  __shared__ unsigned long long s_acc[R];
   __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
   __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
@@ -1129,7 +1134,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const bool is_scan = (int)threadIdx.x >= cthreads && (int)threadIdx.x < cthreads + 32;
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
-  const fq_u64 tile_rows = (fq_u64)tile_groups * V;
+  const fq_u64 tile_rows = (fq_u64)tile_groups * V)FQSK"
+R"FQSK(;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
@@ -1137,8 +1143,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   fq_u32 err = 0;
 
   if (threadIdx.x < FQ_SELT_CLAIMS) s_ready[threadIdx.x] = 0;
-  if (threadIdx.x < FQ_SEL_RING) s_acc[thre)FQSK"
-R"FQSK(adIdx.x] = 0ull;
+  if (threadIdx.x < R) s_acc[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; s++) {
       fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
@@ -1188,8 +1193,8 @@ R"FQSK(adIdx.x] = 0ull;
     fq_i64 prev_seg = -1;      // the segment this CTA resolved last and its inclusive prefix (see fq_sel_lookback)
     fq_u64 prev_incl = 0;
     for (int k = 0;; k++) {
-      const int b = k % FQ_SEL_RING;
-      fq_bar_sync(FQ_BAR_FULL + b, barthreads);
+      const int b = k % R;
+      fq_bar_sync(BAR_FULL + b, barthreads);
       const fq_u64 seg = s_seg[k % FQ_SELT_CLAIMS];
       if (!(seg < n_seg) || s_stop[k % FQ_SELT_CLAIMS]) break;
       const fq_u32 tot = fq_sel_scan_counts<SEG>(s_cnt[b], cwarps);
@@ -1206,22 +1211,24 @@ R"FQSK(adIdx.x] = 0ull;
         if (seg == n_seg - 1) atomicMax(p.result, incl);
       }
       __syncwarp();
-      fq_bar_arrive(FQ_BAR_DONE + b, barthreads);
+      fq_bar_arrive(BAR_DONE + b, barthreads);
     }
     return;
   }
 
   // ================= consumer warps =================
   auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
-    fq_bar_sync(FQ_BAR_DONE + sb, barthreads);
+    fq_bar_sync(BAR_DONE + sb, barthreads);
     fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, &err);
   };
-  fq_u64 keep1 = 0, seg1 = 0, keep2 = 0, seg2 = 0;
+  fq_u64 keepq[LAG], segq[LAG];   // segments streamed but not yet scattered, newest first (registers: constant indexes)
+#pragma unroll
+  for (int j = 0; j < LAG; j++) keepq[j] = segq[j] = 0;
   int pending = 0;
   int slot = 0;          // ring slot and round of the next staged tile (same count as the producer's)
   fq_u32 round = 0;
   for (int k = 0;; k++) {
-    const int b = k % FQ_SEL_RING;
+    const int b = k % R;
     if (lane == 0) {
       while (s_ready[k % FQ_SELT_CLAIMS] != k + 1) {}
     }
@@ -1262,20 +1269,22 @@ R"FQSK(adIdx.x] = 0ull;
       if (lane == 0) fq_sel_publish_agg(p, seg, &s_acc[b], wsum, cwarps);
     }
     __syncwarp();
-    fq_bar_arrive(FQ_BAR_FULL + b, barthreads);
+    fq_bar_arrive(BAR_FULL + b, barthreads);
 
-    if (pending == 2) {
-      scatter(seg2, keep2, (k + 1) % FQ_SEL_RING);
-      pending = 1;
+    if (pending == LAG) {   // the oldest: segment of iteration k - LAG
+      scatter(segq[LAG - 1], keepq[LAG - 1], (k + 1) % R);
+      pending = LAG - 1;
     }
-    if (!active) {
-      if (pending == 1) scatter(seg1, keep1, (k + 2) % FQ_SEL_RING);
+    if (!active) {          // drain, oldest first: entry j is the segment of iteration k - 1 - j
+#pragma unroll
+      for (int j = LAG - 2; j >= 0; j--)
+        if (j < pending) scatter(segq[j], keepq[j], (k - 1 - j) % R);
       break;
     }
-    keep2 = keep1;
-    seg2 = seg1;
-    keep1 = keepbits;
-    seg1 = seg;
+#pragma unroll
+    for (int j = LAG - 1; j > 0; j--) { keepq[j] = keepq[j - 1]; segq[j] = segq[j - 1]; }
+    keepq[0] = keepbits;
+    segq[0] = seg;
     pending += 1;
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
@@ -1321,7 +1330,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
         if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
     }
   }
-  for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
+  for (fq_u64 row = nvec * V + tid; row < p.n_row)FQSK"
+R"FQSK(s; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
     if (row < p.capacity) Q::emit(r, 0, p, row, err);

@@ -56,7 +56,8 @@ typedef signed char fq_i8;
 #define FQ_SELT_THREADS 512  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp)
 #define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
 #define FQ_SELT_SEG 8        // tiles per segment (one look-back each): 256 KB of a UInt64 column
-#define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~128 KB in flight per SM)
+#define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~192 KB in flight per SM)
+#define FQ_SELT_LAG 3        // pass 2 runs this many segments behind pass 1
 #endif
 
 #define FQ_STATE_HDR 6        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned,
@@ -1108,10 +1109,14 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   constexpr int V = Q::V;
   constexpr int BITS = U * V;
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
+  constexpr int LAG = FQ_SELT_LAG;            // pass 2 runs this many segments behind pass 1 (absorbs the skew between CTAs)
+  constexpr int R = LAG + 1;                  // ring of count / base slots and of FULL / DONE named barriers
+  constexpr int BAR_FULL = 2, BAR_DONE = 2 + R;
+  static_assert(2 + 2 * R <= 16, "named barriers");
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
-  __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];
-  __shared__ fq_u64 s_excl[FQ_SEL_RING];
-  __shared__ unsigned long long s_acc[FQ_SEL_RING];
+  __shared__ fq_u32 s_cnt[R][SEG][FQ_MAX_WARPS];
+  __shared__ fq_u64 s_excl[R];
+  __shared__ unsigned long long s_acc[R];
   __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
   __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
@@ -1130,7 +1135,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   fq_u32 err = 0;
 
   if (threadIdx.x < FQ_SELT_CLAIMS) s_ready[threadIdx.x] = 0;
-  if (threadIdx.x < FQ_SEL_RING) s_acc[threadIdx.x] = 0ull;
+  if (threadIdx.x < R) s_acc[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; s++) {
       fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
@@ -1180,8 +1185,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     fq_i64 prev_seg = -1;      // the segment this CTA resolved last and its inclusive prefix (see fq_sel_lookback)
     fq_u64 prev_incl = 0;
     for (int k = 0;; k++) {
-      const int b = k % FQ_SEL_RING;
-      fq_bar_sync(FQ_BAR_FULL + b, barthreads);
+      const int b = k % R;
+      fq_bar_sync(BAR_FULL + b, barthreads);
       const fq_u64 seg = s_seg[k % FQ_SELT_CLAIMS];
       if (!(seg < n_seg) || s_stop[k % FQ_SELT_CLAIMS]) break;
       const fq_u32 tot = fq_sel_scan_counts<SEG>(s_cnt[b], cwarps);
@@ -1198,22 +1203,24 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
         if (seg == n_seg - 1) atomicMax(p.result, incl);
       }
       __syncwarp();
-      fq_bar_arrive(FQ_BAR_DONE + b, barthreads);
+      fq_bar_arrive(BAR_DONE + b, barthreads);
     }
     return;
   }
 
   // ================= consumer warps =================
   auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
-    fq_bar_sync(FQ_BAR_DONE + sb, barthreads);
+    fq_bar_sync(BAR_DONE + sb, barthreads);
     fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, &err);
   };
-  fq_u64 keep1 = 0, seg1 = 0, keep2 = 0, seg2 = 0;
+  fq_u64 keepq[LAG], segq[LAG];   // segments streamed but not yet scattered, newest first (registers: constant indexes)
+#pragma unroll
+  for (int j = 0; j < LAG; j++) keepq[j] = segq[j] = 0;
   int pending = 0;
   int slot = 0;          // ring slot and round of the next staged tile (same count as the producer's)
   fq_u32 round = 0;
   for (int k = 0;; k++) {
-    const int b = k % FQ_SEL_RING;
+    const int b = k % R;
     if (lane == 0) {
       while (s_ready[k % FQ_SELT_CLAIMS] != k + 1) {}
     }
@@ -1254,20 +1261,22 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
       if (lane == 0) fq_sel_publish_agg(p, seg, &s_acc[b], wsum, cwarps);
     }
     __syncwarp();
-    fq_bar_arrive(FQ_BAR_FULL + b, barthreads);
+    fq_bar_arrive(BAR_FULL + b, barthreads);
 
-    if (pending == 2) {
-      scatter(seg2, keep2, (k + 1) % FQ_SEL_RING);
-      pending = 1;
+    if (pending == LAG) {   // the oldest: segment of iteration k - LAG
+      scatter(segq[LAG - 1], keepq[LAG - 1], (k + 1) % R);
+      pending = LAG - 1;
     }
-    if (!active) {
-      if (pending == 1) scatter(seg1, keep1, (k + 2) % FQ_SEL_RING);
+    if (!active) {          // drain, oldest first: entry j is the segment of iteration k - 1 - j
+#pragma unroll
+      for (int j = LAG - 2; j >= 0; j--)
+        if (j < pending) scatter(segq[j], keepq[j], (k - 1 - j) % R);
       break;
     }
-    keep2 = keep1;
-    seg2 = seg1;
-    keep1 = keepbits;
-    seg1 = seg;
+#pragma unroll
+    for (int j = LAG - 1; j > 0; j--) { keepq[j] = keepq[j - 1]; segq[j] = segq[j - 1]; }
+    keepq[0] = keepbits;
+    segq[0] = seg;
     pending += 1;
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);

@@ -530,6 +530,16 @@ class QueryResult:
         return [tuple(c[i] for c in cols) for i in range(self.n_rows)]
 
 
+def fused_headline(total: int, threads: int):
+    """Best-case CPU pass of the headline query (not the reference's structure): (seconds, [sum, count, max, min])."""
+    L = lib()
+    L.orc_fused_headline.argtypes = [C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+    L.orc_fused_headline.restype = C.c_double
+    out = (C.c_uint64 * 4)()
+    secs = L.orc_fused_headline(total, threads, out)
+    return secs, [int(x) for x in out]
+
+
 def run_query(exprs: Sequence[str], *, total: int = 10000, table: Optional[dict] = None, predicate: Optional[str] = None,
               is_aggregate: bool = False, limit: Optional[int] = None, worker_threads: int = 8, use_threads: bool = False,
               block_size: int = 10000, tail_quirk: bool = True) -> QueryResult:

@@ -15,7 +15,7 @@
  * numeric `cast` that yields null when out of range).
  *
  * Parity pin: every known-answer vector of the reference's own tests for this path is
- * extracted by tests/golden/extract_reference_vectors.py into tests/golden/*.json and
+ * extracted by tests/golden/extract_reference_vectors.py into the tests/golden JSON files and
  * replayed against this oracle by tests/test_oracle_golden.py.  Behaviours no reference
  * test pins (u64 sum wrap at 10^10 rows, the NumbersStream tail quirk, empty-block sum)
  * are listed as "unpinned" in DESIGN.md.
@@ -132,7 +132,7 @@ int32_t orc_fn_accumulate_result(const orc_fn *f, orc_value *out_struct, char *e
 int32_t orc_fn_merge_state(orc_fn *f, const orc_value *states_struct, char *err);
 int32_t orc_fn_merge_result(const orc_fn *f, orc_value *out, char *err);
 
-/* ---- pipeline (processors/pipeline_builder.rs:26-106 + transforms/*.rs) ---- */
+/* ---- pipeline (processors/pipeline_builder.rs:26-106 + transforms) ---- */
 typedef struct orc_query {
   /* source: system.numbers_mt(total) when table == NULL, else an in-memory table whose
    * rows are partitioned exactly like numbers_mt's (generate_parts over row indices) */
@@ -161,6 +161,12 @@ typedef struct orc_result {
 
 int32_t orc_query_run(const orc_query *q, orc_result *out, char *err);
 void orc_result_free(orc_result *r);
+
+/* Best-case CPU figure for bench.py, NOT the reference's structure: the headline query
+ * sum(number)/count(number), max(number), min(number) over numbers [0, total) as ONE fused pass per thread, numbers
+ * generated in registers, no blocks, no arrays, no per-node passes.  out[0..3] = wrapping sum, count, max, min.
+ * Returns the wall seconds of the pass. */
+double orc_fused_headline(uint64_t total, int32_t threads, uint64_t out[4]);
 
 #ifdef __cplusplus
 }
