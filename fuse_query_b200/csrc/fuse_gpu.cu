@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cinttypes>
 #include <cstdarg>
 #include <cstdio>
@@ -187,7 +188,7 @@ struct Module {  // one compiled specialisation, shared by every pipe with the s
 struct fq_ctx {
   int device = 0;
   int sm_count = 0;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::map<std::string, Module> modules;  // tag -> module
 };
@@ -382,7 +383,7 @@ void fq_ctx_destroy(fq_ctx *ctx) {
   delete ctx;
 }
 
-uint64_t fq_ctx_launch_count(const fq_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t fq_ctx_launch_count(const fq_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 int32_t fq_ctx_sm_count(const fq_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 // ---- columns ----

@@ -912,11 +912,17 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
           tot += __popc(bmask);
         }
         fq_u64 pos = pos0 + before;
+        if (tot == 32u * V && (pos0 % V) == 0 && pos + V <= p.capacity) {
+          // the warp kept the whole group (range predicates over sorted data: groups are all-or-nothing) and the
+          // output position keeps the vector alignment: one vector store per output column instead of V scalar ones
+          Q::emit_vec(rows[u], p, pos, err);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-          if ((keep >> (u * V + v)) & 1u) {
-            if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
-            pos++;
+          for (int v = 0; v < V; v++) {
+            if ((keep >> (u * V + v)) & 1u) {
+              if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+              pos++;
+            }
           }
         }
         pos0 += tot;
@@ -969,11 +975,11 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   fq_u32 err = 0;
 
   // Segments are claimed dynamically (atomicAdd): only running CTAs own segments, so every predecessor of a running
-  // segment has started and the look-back makes progress whatever else shares the GPU.  Claiming and observing the
+  // segment has started and t)FQSK"
+R"FQSK(he look-back makes progress whatever else shares the GPU.  Claiming and observing the
   // early-exit flag happen together: a claimed segment is ALWAYS published (a successor may already be polling it); a CTA
   // that sees the flag publishes a saturated prefix for the segment it just claimed and leaves.
-  // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and)FQSK"
-R"FQSK( hands it to the other warps through a
+  // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and hands it to the other warps through a
   // shared-memory ring (s_ready[slot] == k + 2): no block-wide barrier per segment, warps run ahead on their own.
   auto publish_claim = [&](int k, fq_u64 c, fq_u32 st) {   // claim of iteration k
     s_seg[k & 3] = c;
@@ -1129,13 +1135,13 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
   __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];   // full[0..STAGES), empty[0..STAGES)
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = thr)FQSK"
+R"FQSK(eadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cthreads = (int)blockDim.x - 64, cwarps = cthreads >> 5, barthreads = cthreads + 32;
   const bool is_scan = (int)threadIdx.x >= cthreads && (int)threadIdx.x < cthreads + 32;
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
-  const fq_u64 tile_rows = (fq_u64)tile_groups * V)FQSK"
-R"FQSK(;
+  const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
@@ -1318,7 +1324,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
     }
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
-  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  const fq_u64 nthreads = (fq_u64)gridDim.x )FQSK"
+R"FQSK(* blockDim.x;
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
@@ -1330,8 +1337,7 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
         if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
     }
   }
-  for (fq_u64 row = nvec * V + tid; row < p.n_row)FQSK"
-R"FQSK(s; row += nthreads) {
+  for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
     if (row < p.capacity) Q::emit(r, 0, p, row, err);

@@ -906,11 +906,17 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
           tot += __popc(bmask);
         }
         fq_u64 pos = pos0 + before;
+        if (tot == 32u * V && (pos0 % V) == 0 && pos + V <= p.capacity) {
+          // the warp kept the whole group (range predicates over sorted data: groups are all-or-nothing) and the
+          // output position keeps the vector alignment: one vector store per output column instead of V scalar ones
+          Q::emit_vec(rows[u], p, pos, err);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-          if ((keep >> (u * V + v)) & 1u) {
-            if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
-            pos++;
+          for (int v = 0; v < V; v++) {
+            if ((keep >> (u * V + v)) & 1u) {
+              if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+              pos++;
+            }
           }
         }
         pos0 += tot;

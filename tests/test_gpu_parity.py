@@ -428,3 +428,50 @@ def test_baseline_1e10_materialised_headline(ctx):
     assert rows == n and got == [13106511847580896768, n, n - 1, 0]
     assert got[0] // got[1] == 1310651184
     col.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY §8b "Threading": one context, many host threads (the reference runs one tokio task per pipe,
+# processor_merge.rs:46-62).  Compiles (NVRTC included), launches on per-thread streams and fetches run concurrently.
+# ---------------------------------------------------------------------------------------------
+def test_context_is_usable_from_many_host_threads(ctx):
+    import threading
+    import torch
+    n_threads, n = 8, 3_000_017
+    shards = [(t * n, n) for t in range(n_threads)]
+    cols = [ctx.numbers(b, m) for b, m in shards]
+    ctx.synchronize()
+    results, errors = [None] * n_threads, []
+
+    def work(t):
+        try:
+            stream = torch.cuda.Stream()
+            begin, m = shards[t]
+            # a different tree per thread: some precompiled, some through NVRTC, all at once
+            exprs = [f"(sum (+ {NUM} (u64 {t})))", f"(max {NUM})", f"(min (* {NUM} (u64 {t + 1})))", f"(count {NUM})"]
+            pipe = ctx.pipe(exprs, aggregate=True)
+            sel = ctx.pipe([f"(+ {NUM} (u64 {t}))"], predicate=f"(= (* (/ {NUM} (u64 1000)) (u64 1000)) {NUM})")
+            out = ctx.column(cabi.U64, m // 1000 + 2)
+            src = cabi.make_source([cols[t]], m)
+            for _ in range(5):
+                pipe.launch_aggregate(src, stream=stream.cuda_stream)
+                sel.launch_project(src, [out], m // 1000 + 2, stream=stream.cuda_stream)
+                states, rows = pipe.fetch_aggregate()
+                k, w = sel.fetch_project()
+            results[t] = ([v for _, v in states], rows, k, out.to_numpy(w, stream=stream.cuda_stream))
+        except Exception as e:   # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t, (begin, m) in enumerate(shards):
+        x = np.arange(begin, begin + m, dtype=np.uint64)
+        vals, rows, k, got = results[t]
+        assert rows == m
+        assert vals == [int((x + np.uint64(t)).sum(dtype=np.uint64)), int(x.max()), int((x * np.uint64(t + 1)).min()), m]
+        want = x[x % 1000 == 0] + np.uint64(t)
+        assert k == len(want) and np.array_equal(got, want)

@@ -71,6 +71,28 @@ def test_all_rows_kept_and_none_kept(ctx, variant, n):
     assert none.fetch_project() == (0, 0)
 
 
+@pytest.mark.parametrize("lo,hi", [(0, 2_500_001), (12_345, 4_000_000), (12_346, 5_000_000), (4_999_999, 5_000_001), (77, 78)])
+def test_range_predicates_keep_whole_groups(ctx, variant, lo, hi):
+    """Range predicates over sorted data keep vector groups all-or-nothing: pass 2 writes them with vector stores when
+    the output position keeps the alignment (even `lo`) and row by row when it does not (odd `lo`)."""
+    n = 5_000_001
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(PROJ + [NUM], predicate=f"(and (>= {NUM} (u64 {lo})) (< {NUM} (u64 {hi})))")
+    hi = min(hi, n)
+    k = hi - lo
+    for cap in (k, k - 1 if k > 1 else k, k + 7):
+        outs = [ctx.column(cabi.U64, cap) for _ in range(3)]
+        pipe.launch_project(cabi.make_source([col], n), outs, cap)
+        sel, written = pipe.fetch_project()
+        assert sel == k and written == min(k, cap)
+        want = np.arange(lo, lo + written, dtype=np.uint64)
+        assert np.array_equal(outs[0].to_numpy(written), want + 1)
+        assert np.array_equal(outs[1].to_numpy(written), want // 2)
+        assert np.array_equal(outs[2].to_numpy(written), want)
+        for c in outs:
+            c.free()
+
+
 @pytest.mark.parametrize("limit,early", [(3, False), (3, True), (1000, True), (0, False)])
 def test_readme_query_with_limit(ctx, variant, limit, early):
     n = 30_000_011
