@@ -160,7 +160,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = min(8, os.cpu_count() or 1)
-    rows = args.rows or cpu_sample_rows()
+    # bounded sample: the whole --steps/--warmup run stays within ~2.5 minutes whatever K the driver passes
+    rows = args.rows or cpu_sample_rows(max(0.5, min(8.0, 150.0 / max(1, args.steps + args.warmup))))
     times = []
     for i in range(args.warmup + args.steps):
         secs, res = cpu_reference_run(rows)

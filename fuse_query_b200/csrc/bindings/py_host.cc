@@ -372,6 +372,12 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def("execute", [](IExecutor &e) { return PyStream{e.execute()}; });
   struct ExecutorFactoryNS {};
   py::class_<ExecutorFactoryNS>(m, "ExecutorFactory").def_static("get", &ExecutorFactory::get);
+  m.def("mysql_result_set", [](std::vector<DataBlock> blocks) {
+    MySQLResultSet rs = MySQLStream::create(std::move(blocks)).execute();
+    py::list cols;
+    for (auto &c : rs.columns) cols.append(py::make_tuple(c.column, c.coltype));
+    return py::make_tuple(cols, rs.rows);
+  }, "servers/mysql/mysql_stream.rs: (columns [(name, MYSQL_TYPE_*)], rows of strings) for a list of result blocks");
   m.def("execute_sql", &execute_sql, "plan -> optimize -> execute -> drain (what the MySQL handler does per query)");
   m.def("numbers_cache_clear", &numbers_cache_clear);
 }

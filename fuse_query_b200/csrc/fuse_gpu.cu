@@ -24,6 +24,9 @@
 #include "kernels/fq_skeleton.cuh"
 #include "generated/skeleton_embed.h"  // static const char fq_skeleton_src[]
 
+#ifndef FQ_MAP_DEFAULT_VARIANT
+#define FQ_MAP_DEFAULT_VARIANT "tma"
+#endif
 #ifndef FQ_SEL_DEFAULT_VARIANT
 #define FQ_SEL_DEFAULT_VARIANT "tma"   // "tma": pass 1 of the select kernel staged by bulk copies
 #endif
@@ -204,7 +207,8 @@ struct fq_column {
 
 struct fq_pipe {
   fq::Generated gen;
-  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map;
+  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
+  unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
@@ -560,6 +564,15 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       }
     } else {
       s2 = resolve_kernel(m, base + "_map", shapes().map_threads, &pipe->k_map);
+      if (!s2 && gen.tma_ok) {
+        const unsigned tile_bytes = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec * gen.row_bytes;
+        unsigned stages = shapes().tma_stages_env > 0 ? (unsigned)shapes().tma_stages_env : (128u * 1024u) / tile_bytes;
+        stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_TMA_STAGES);
+        if (stages * tile_bytes <= 200 * 1024) {
+          s2 = resolve_kernel(m, base + "_map_tma", shapes().tma_threads + 32, &pipe->k_map_tma, stages * tile_bytes);
+          pipe->mapt_stages = stages;
+        }
+      }
     }
     if (s2) { delete pipe; return s2; }
   }
@@ -781,8 +794,12 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   } else {
-    const Kernel &k = pipe->k_map;
-    const uint64_t chunk_rows = (uint64_t)k.threads * shapes().map_unroll * pipe->gen.vec;
+    // FQ_MAP_VARIANT = tma (default: reads staged by bulk copies; needs every referenced column materialised) | ldg
+    const std::string variant = getenv("FQ_MAP_VARIANT") ? getenv("FQ_MAP_VARIANT") : FQ_MAP_DEFAULT_VARIANT;
+    const bool use_tma = variant == "tma" && pipe->k_map_tma.valid();
+    const Kernel &k = use_tma ? pipe->k_map_tma : pipe->k_map;
+    p.stages = pipe->mapt_stages;
+    const uint64_t chunk_rows = (uint64_t)(use_tma ? shapes().tma_threads * shapes().tma_unroll : k.threads * shapes().map_unroll) * pipe->gen.vec;
     const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;

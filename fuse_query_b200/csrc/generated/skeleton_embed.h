@@ -1345,5 +1345,96 @@ R"FQSK(* blockDim.x;
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
   if (tid == 0) p.result[0] = p.n_rows;
 }
+
+// ---------------------------------------------------------------------------------------------
+// fq_map_tma_kernel — fq_map_kernel with its reads staged by the bulk-copy engine (same ring as fq_agg_tma_kernel):
+// the loads in flight no longer compete with the output vectors for registers.  Consumers read a staged tile with
+// LDS.128, evaluate every select expression and write one vector store per output column per group.
+// ---------------------------------------------------------------------------------------------
+template <class Q, int U, int STAGES>
+__device__ __forceinline__ void fq_map_tma_kernel(const fq_launch_params &p) {
+  constexpr int V = Q::V;
+  extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
+  __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];
+  const int lane = threadIdx.x & 31;
+  const int cthreads = (int)blockDim.x - 32, cwarps = cthreads >> 5;
+  const bool is_producer = (int)threadIdx.x >= cthreads;
+  const fq_u32 tile_groups = (fq_u32)cthreads * U;
+  const fq_u64 tile_rows = (fq_u64)tile_groups * V;
+  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u64 n_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;
+  const int stages = (int)p.stages;
+  fq_u32 err = 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; s++) {
+      fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
+      fq_mbar_init(fq_smem_addr(&s_bars[STAGES + s]), cwarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (is_producer) {
+    if (lane == 0) {
+      int slot = 0;
+      fq_u32 round = 0;
+      for (fq_u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
+        const fq_u32 full = fq_smem_addr(&s_bars[slot]);
+        fq_mbar_expect_tx(full, stage_bytes);
+        Q::tma_issue(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, t, (fq_u32)tile_rows);
+        if (++slot == stages) { slot = 0; round++; }
+      }
+    }
+    return;
+  }
+  int slot = 0;
+  fq_u32 round = 0;
+  for (fq_u64 t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    fq_mbar_wait(fq_smem_addr(&s_bars[slot]), round & 1);
+    const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
+    typename Q::Rows rows[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(u * cthreads + (int)threadIdx.x));
+    __syncwarp();
+    if (lane == 0) fq_mbar_arrive(fq_smem_addr(&s_bars[STAGES + slot]));   // the tile is in registers: hand the slot back
+    if (++slot == stages) { slot = 0; round++; }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const fq_u64 row0 = (t * tile_groups + (fq_u64)u * cthreads + threadIdx.x) * V;
+      if (row0 + V <= p.capacity) {
+        Q::emit_vec(rows[u], p, row0, err);
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; v++)
+          if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+      }
+    }
+  }
+  // rows past the last full tile: plain loads, spread over the consumers of the whole grid
+  const fq_u64 ctid = (fq_u64)blockIdx.x * cthreads + threadIdx.x;
+  const fq_u64 cn = (fq_u64)gridDim.x * cthreads;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
+  for (fq_u64 g = n_tiles * tile_groups + ctid; g < nvec; g += cn) {
+    typename Q::Rows r;
+    Q::load(r, p, g);
+    if (g * V + V <= p.capacity) {
+      Q::emit_vec(r, p, g * V, err);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; v++)
+        if (g * V + v < p.capacity) Q::emit(r, v, p, g * V + v, err);
+    }
+  }
+  for (fq_u64 row = nvec * V + ctid; row < p.n_rows; row += cn) {
+    typename Q::Rows r;
+    Q::load1(r, p, row);
+    if (row < p.capacity) Q::emit(r, 0, p, row, err);
+  }
+  if (err) atomicOr((fq_u32 *)(p.result + 1), err);
+  if (ctid == 0) p.result[0] = p.n_rows;
+}
 )FQSK"
 ;

@@ -664,4 +664,22 @@ struct ExecutorFactory {   // executor_factory.rs:12-25
 // What mysql_handler.rs:52-75 does for one query, minus the wire protocol: plan, optimize, execute, drain.
 std::vector<DataBlock> execute_sql(FuseQueryContextRef ctx, const std::string &sql);
 
+// servers/mysql/mysql_stream.rs:12-86 minus the socket: the result set a MySQL client would be sent.  Column types
+// follow the reference's mapping (every integer -> MYSQL_TYPE_LONG, floats -> MYSQL_TYPE_FLOAT, Utf8 ->
+// MYSQL_TYPE_VARCHAR, anything else "Unsupported column type:<type>"); cells are arrow's array_value_to_string
+// (decimal integers, shortest round-trip floats without exponent, "" for NULL).  One D2H copy per column per block.
+struct MySQLColumn { std::string column; std::string coltype; };
+struct MySQLResultSet {
+  std::vector<MySQLColumn> columns;
+  std::vector<std::vector<std::string>> rows;
+};
+class MySQLStream {
+ public:
+  static MySQLStream create(std::vector<DataBlock> blocks) { return MySQLStream(std::move(blocks)); }
+  MySQLResultSet execute() const;
+ private:
+  explicit MySQLStream(std::vector<DataBlock> blocks) : blocks_(std::move(blocks)) {}
+  std::vector<DataBlock> blocks_;
+};
+
 }  // namespace fuse

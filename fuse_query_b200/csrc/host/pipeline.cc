@@ -6,6 +6,10 @@
 
 #include "host_internal.h"
 
+#include <charconv>
+#include <cmath>
+#include <type_traits>
+
 namespace fuse {
 
 // ---------------------------------------------------------------------------------------------
@@ -704,6 +708,80 @@ std::vector<DataBlock> execute_sql(FuseQueryContextRef ctx, const std::string &s
   std::vector<DataBlock> blocks;
   while (auto b = stream->next()) blocks.push_back(*b);
   return blocks;
+}
+
+
+// ---- servers/mysql/mysql_stream.rs ----
+namespace {
+template <class T> void cells_of(const DataArray &a, std::vector<std::string> *out) {
+  std::vector<T> v(a.len());
+  a.to_host(v.data());
+  std::vector<unsigned char> ok;
+  if (a.validity()) {
+    ok.resize(a.len());
+    a.validity()->to_host(ok.data());
+  }
+  out->reserve(v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    if (!ok.empty() && !ok[i]) { out->emplace_back(); continue; }   // arrow: a NULL slot prints as the empty string
+    if constexpr (std::is_floating_point<T>::value) {
+      if (std::isnan(v[i])) { out->emplace_back("NaN"); continue; }
+      if (std::isinf(v[i])) { out->emplace_back(v[i] < 0 ? "-inf" : "inf"); continue; }
+      char buf[400];
+      auto r = std::to_chars(buf, buf + sizeof buf, v[i], std::chars_format::fixed);   // Rust's Display: shortest, no exponent
+      out->emplace_back(buf, r.ptr);
+    } else {
+      out->push_back(std::to_string(v[i]));
+    }
+  }
+}
+}  // namespace
+
+MySQLResultSet MySQLStream::execute() const {
+  MySQLResultSet rs;
+  if (blocks_.empty()) return rs;   // writer.completed(0, 0)
+  const DataBlock &first = blocks_[0];
+  for (const DataField &f : first.schema()->fields) {
+    std::string t;
+    switch (f.data_type) {
+      case FQ_I8: case FQ_I16: case FQ_I32: case FQ_I64: case FQ_U8: case FQ_U16: case FQ_U32: case FQ_U64: t = "MYSQL_TYPE_LONG"; break;
+      case FQ_F32: case FQ_F64: t = "MYSQL_TYPE_FLOAT"; break;
+      case FQ_UTF8: t = "MYSQL_TYPE_VARCHAR"; break;
+      default: throw FuseQueryError::internal(std::string("Unsupported column type:") + data_type_name(f.data_type));
+    }
+    rs.columns.push_back({f.name, t});
+  }
+  const size_t ncols = first.num_columns();
+  if (ncols == 0) return rs;
+  for (const DataBlock &b : blocks_) {
+    std::vector<std::vector<std::string>> cols(ncols);
+    for (size_t c = 0; c < ncols; c++) {
+      const DataArray &a = *b.column(c);
+      switch (a.data_type()) {
+        case FQ_I8: cells_of<int8_t>(a, &cols[c]); break;
+        case FQ_I16: cells_of<int16_t>(a, &cols[c]); break;
+        case FQ_I32: cells_of<int32_t>(a, &cols[c]); break;
+        case FQ_I64: cells_of<int64_t>(a, &cols[c]); break;
+        case FQ_U8: cells_of<uint8_t>(a, &cols[c]); break;
+        case FQ_U16: cells_of<uint16_t>(a, &cols[c]); break;
+        case FQ_U32: cells_of<uint32_t>(a, &cols[c]); break;
+        case FQ_U64: cells_of<uint64_t>(a, &cols[c]); break;
+        case FQ_F32: cells_of<float>(a, &cols[c]); break;
+        case FQ_F64: cells_of<double>(a, &cols[c]); break;
+        case FQ_UTF8:
+          for (uint64_t i = 0; i < a.len(); i++) cols[c].push_back(a.value(i).s);
+          break;
+        default: throw FuseQueryError::internal(std::string("Unsupported column type:") + data_type_name(a.data_type()));
+      }
+    }
+    const size_t nrows = cols[0].size();
+    for (size_t r = 0; r < nrows; r++) {
+      std::vector<std::string> row(ncols);
+      for (size_t c = 0; c < ncols; c++) row[c] = std::move(cols[c][r]);
+      rs.rows.push_back(std::move(row));
+    }
+  }
+  return rs;
 }
 
 }  // namespace fuse

@@ -189,6 +189,30 @@ def test_unaligned_slices_fall_back_to_row_loads(ctx, variant, off):
         assert [v for _, v in states] == [int(x.sum(dtype=np.uint64)), int(y[yv].max()), n, int(x.min())]
 
 
+@pytest.mark.parametrize("map_variant", ["ldg", "tma"])
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 148 * 4096 + 5, 3_000_001])
+def test_projection_without_filter_both_variants(ctx, map_variant, n):
+    """ProjectionTransform alone (transform_projection.rs:45-56): every row, every expression, both load styles."""
+    os.environ["FQ_MAP_VARIANT"] = map_variant
+    try:
+        rng = np.random.default_rng(n)
+        a = rng.integers(0, 1 << 50, n, dtype=np.uint64)
+        b = rng.integers(-30000, 30000, n).astype(np.int16)
+        cols = [ctx.from_numpy(a), ctx.from_numpy(b)]
+        pipe = ctx.pipe(["(+ (col a) (u64 1))", "(/ (col a) (u64 2))", "(* (col b) (i16 3))", "(< (col b) (i16 0))"], columns=["a", "b"],
+                        dtypes=[cabi.U64, cabi.I16])
+        outs = [ctx.column(pipe.expr_dtype(i), n) for i in range(4)]
+        for cap in (n, max(1, n - 3)):
+            pipe.launch_project(cabi.make_source(cols, n), outs, cap)
+            assert pipe.fetch_project() == (n, cap)
+            assert np.array_equal(outs[0].to_numpy(cap), a[:cap] + 1)
+            assert np.array_equal(outs[1].to_numpy(cap), a[:cap] // 2)
+            assert np.array_equal(outs[2].to_numpy(cap), (b[:cap] * np.int16(3)).astype(np.int16))
+            assert np.array_equal(outs[3].to_numpy(cap).astype(bool), b[:cap] < 0)
+    finally:
+        os.environ.pop("FQ_MAP_VARIANT", None)
+
+
 def test_variants_launch_different_kernels(ctx):
     """The environment switch must really select another kernel (both are precompiled for the README pipe)."""
     pipe = ctx.pipe(PROJ, predicate=README_PRED)

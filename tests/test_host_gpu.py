@@ -451,6 +451,31 @@ def test_parquet_and_arrow_ipc_files_become_resident_tables(gpu, tmp_path):
         assert got == want.rows() and len(got) == 25
 
 
+def test_mysql_result_set_matches_the_reference_writer(gpu):
+    """servers/mysql/mysql_stream.rs:22-86: column types by data type, cells by arrow's array_value_to_string."""
+    import pyarrow as pa
+    from fuse_query_b200.tables import register_table
+    ctx = make_ctx(gpu, 1, fuse=True)
+    cols, rows = h.mysql_result_set(h.execute_sql(ctx, "select number + 1 as c1, number / 2 as c2 from system.numbers_mt(1000000) "
+                                                       "where (c1 + c2 + 1) < 100 limit 3"))
+    assert cols == [("c1", "MYSQL_TYPE_LONG"), ("c2", "MYSQL_TYPE_LONG")]
+    assert rows == [["1", "0"], ["2", "0"], ["3", "1"]]          # README.md:120-126
+    cols, rows = h.mysql_result_set(h.execute_sql(ctx, "select sum(number)/count(number), max(number) from system.numbers_mt(160000)"))
+    assert cols == [("Sum(number) / Count(number)", "MYSQL_TYPE_LONG"), ("Max(number)", "MYSQL_TYPE_LONG")]
+    assert rows == [["79999", "159999"]]
+    tbl = pa.table({"f": pa.array([1.0, 0.1, None, 1e21, -2.5e-7, 3.0000000000000004], type=pa.float64()),
+                    "i": pa.array([-3, 0, 7, None, 9, 10], type=pa.int16())})
+    register_table(ctx, gpu, "default", "m", tbl)
+    cols, rows = h.mysql_result_set(h.execute_sql(ctx, "select f, i, f * i from m"))
+    assert cols == [("f", "MYSQL_TYPE_FLOAT"), ("i", "MYSQL_TYPE_LONG"), ("f * i", "MYSQL_TYPE_FLOAT")]
+    assert rows == [["1", "-3", "-3"], ["0.1", "0", "0"], ["", "7", ""], ["1000000000000000000000", "", ""],
+                    ["-0.00000025", "9", "-0.00000225"], ["3.0000000000000004", "10", "30.000000000000004"]]
+    assert h.mysql_result_set([]) == ([], [])
+    with pytest.raises(h.FuseQueryError) as e:                       # a Boolean column has no MySQL type in the reference
+        h.mysql_result_set(h.execute_sql(ctx, "select number < 3 from system.numbers_mt(10)"))
+    assert str(e.value) == "Internal Error: Unsupported column type:Boolean"
+
+
 def test_pyarrow_table_with_nulls_registers_nullable_fields(gpu):
     import pyarrow as pa
     from fuse_query_b200.tables import register_table

@@ -25,4 +25,12 @@ for name, (pred, cap) in cases.items():
     for _ in range(5): run()
     b.record(); torch.cuda.synchronize()
     res.append(f"{name} {a.elapsed_time(b) / 5:.3f}")
+p = ctx.pipe(proj)
+run = lambda: p.launch_project(src, outs, n, stream=stream)
+for _ in range(2): run()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5): run()
+b.record(); torch.cuda.synchronize()
+res.append(f"map {a.elapsed_time(b) / 5:.3f}")
 print(os.environ.get("TAG", ""), "|", " | ".join(res))
