@@ -67,7 +67,8 @@ class FuseGpuError(Exception):
 
 EXPORTS = [
     "fq_abi_version", "fq_ctx_create", "fq_ctx_destroy", "fq_last_error", "fq_ctx_launch_count", "fq_ctx_sm_count",
-    "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free", "fq_column_dtype", "fq_column_len",
+    "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free",
+    "fq_column_upload_bits", "fq_column_download_bits", "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
@@ -99,6 +100,8 @@ def lib():
         "fq_column_set_validity": (i32, [vp, vp, vp]),
         "fq_column_validity": (vp, [vp]),
         "fq_column_free": (None, [vp, vp]),
+        "fq_column_upload_bits": (i32, [vp, vp, u64, vp, u64, u64, vp]),
+        "fq_column_download_bits": (i32, [vp, vp, u64, vp, u64, vp]),
         "fq_column_dtype": (i32, [vp]),
         "fq_column_len": (u64, [vp]),
         "fq_column_device_ptr": (vp, [vp]),
@@ -251,6 +254,15 @@ class Context:
         self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
         return col
 
+    def from_bitmap(self, bits, n: int, bit_offset: int = 0, stream: int = 0) -> "Column":
+        """Boolean column (values or validity) from an Arrow LSB-first bitmap (bytes / numpy uint8), expanded on the device."""
+        import numpy as np
+        b = np.ascontiguousarray(np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else bits)
+        col = self.column(BOOL, n)
+        self.check(lib().fq_column_upload_bits(self._h, col._h, 0, C.c_void_p(b.ctypes.data), bit_offset, n, C.c_void_p(stream)))
+        self.synchronize(stream)
+        return col
+
     def fill_numbers(self, col: "Column", begin: int, n: int, stream: int = 0, row_offset: int = 0) -> None:
         """col[row_offset : row_offset + n] = begin .. begin + n - 1 (NumbersStream::poll_next on the device)."""
         self.check(lib().fq_numbers_fill(self._h, col._h, row_offset, begin, n, C.c_void_p(stream)))
@@ -341,6 +353,16 @@ class Column:
         """The attached validity column (one BOOL byte per row, 1 = valid), or None for a NOT NULL column."""
         h = lib().fq_column_validity(self._h)
         return Column(self.ctx, h) if h else None
+
+    def to_bitmap(self, n: Optional[int] = None, stream: int = 0):
+        """Boolean column -> Arrow LSB-first bitmap (numpy uint8 of ceil(n / 8) bytes), packed on the device."""
+        import numpy as np
+        n = len(self) if n is None else n
+        out = np.zeros((n + 7) // 8, dtype=np.uint8)
+        if n:
+            self.ctx.check(lib().fq_column_download_bits(self.ctx._h, self._h, 0, C.c_void_p(out.ctypes.data), n, C.c_void_p(stream)))
+            self.ctx.synchronize(stream)
+        return out
 
     def to_numpy(self, n: Optional[int] = None, stream: int = 0):
         import numpy as np

@@ -170,6 +170,14 @@ PYBIND11_MODULE(_fuse_host, m) {
         arr->set_validity(DataArray::from_host(gpu, FQ_BOOL, v.data(), (uint64_t)v.size()));
         return arr;
       })
+      .def_static("from_arrow_bitmap", [](GpuContextRef gpu, uintptr_t address, uint64_t bit_offset, uint64_t len) {
+        return DataArray::from_arrow_bitmap(gpu, (const void *)address, bit_offset, len);
+      }, "Boolean array from an Arrow LSB-first bitmap at a host address (pyarrow Buffer.address), expanded on the device")
+      .def("to_arrow_bitmap", [](const DataArrayRef &a) {
+        auto v = a->to_arrow_bitmap();
+        return py::bytes((const char *)v.data(), v.size());
+      })
+      .def("set_validity", &DataArray::set_validity)
       .def("validity", &DataArray::validity)
       .def("null_count", &DataArray::null_count)
       .def_static("utf8", &DataArray::utf8)

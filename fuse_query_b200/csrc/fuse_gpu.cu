@@ -474,6 +474,70 @@ fq_status fq_column_download(fq_ctx *ctx, const fq_column *col, uint64_t row_off
   CUDA_TRY(cudaMemcpyAsync(host, (const char *)col->ptr + row_offset * w, n_rows * w, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return FQ_OK;
 }
+// ---- Arrow LSB-first bitmaps <-> one byte per row ----
+__global__ void __launch_bounds__(256) fq_bits_expand(fq_u8 *dst, const fq_u8 *bits, unsigned shift, fq_u64 n_rows) {
+  // thread i -> rows [8i, 8i + 8): source bits [shift + 8i, shift + 8i + 8) straddle bytes i and i + 1 (the staging buffer has one spare byte)
+  const fq_u64 groups = (n_rows + 7) / 8;
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (fq_u64)gridDim.x * blockDim.x) {
+    const unsigned w = ((unsigned)bits[i] | ((unsigned)bits[i + 1] << 8)) >> shift;
+    fq_u64 out = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) out |= (fq_u64)((w >> b) & 1u) << (8 * b);
+    if (8 * i + 8 <= n_rows && (((uintptr_t)dst) & 7) == 0) {
+      *(fq_u64 *)(dst + 8 * i) = out;
+    } else {
+      for (int b = 0; b < 8 && 8 * i + b < n_rows; b++) dst[8 * i + b] = (fq_u8)(out >> (8 * b));
+    }
+  }
+}
+__global__ void __launch_bounds__(256) fq_bits_pack(fq_u8 *bits, const fq_u8 *src, fq_u64 n_rows) {
+  const fq_u64 groups = (n_rows + 7) / 8;
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (fq_u64)gridDim.x * blockDim.x) {
+    unsigned w = 0;
+    for (int b = 0; b < 8 && 8 * i + b < n_rows; b++) w |= (src[8 * i + b] ? 1u : 0u) << b;
+    bits[i] = (fq_u8)w;
+  }
+}
+fq_status fq_column_upload_bits(fq_ctx *ctx, fq_column *col, uint64_t row_offset, const void *host_bits, uint64_t bit_offset,
+                                uint64_t n_rows, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || col->dtype != FQ_BOOL) return set_err(FQ_ERR_INVALID, "Internal Error: bitmap upload needs a Boolean column");
+  if (row_offset + n_rows > col->len) return set_err(FQ_ERR_INVALID, "Internal Error: upload out of range");
+  if (n_rows == 0) return FQ_OK;
+  if (!host_bits) return set_err(FQ_ERR_INVALID, "Internal Error: null bitmap");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t first = bit_offset / 8, nbytes = (bit_offset % 8 + n_rows + 7) / 8;
+  fq_u8 *stage = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&stage, nbytes + 1, s));
+  CUDA_TRY(cudaMemsetAsync(stage + nbytes, 0, 1, s));
+  CUDA_TRY(cudaMemcpyAsync(stage, (const char *)host_bits + first, nbytes, cudaMemcpyHostToDevice, s));
+  const uint64_t groups = (n_rows + 7) / 8;
+  const unsigned grid = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_bits_expand<<<grid, 256, 0, s>>>((fq_u8 *)col->ptr + row_offset, stage, (unsigned)(bit_offset % 8), n_rows);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaFreeAsync(stage, s));
+  return FQ_OK;
+}
+fq_status fq_column_download_bits(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host_bits, uint64_t n_rows,
+                                  void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || col->dtype != FQ_BOOL) return set_err(FQ_ERR_INVALID, "Internal Error: bitmap download needs a Boolean column");
+  if (row_offset + n_rows > col->len) return set_err(FQ_ERR_INVALID, "Internal Error: download out of range");
+  if (n_rows == 0) return FQ_OK;
+  if (!host_bits) return set_err(FQ_ERR_INVALID, "Internal Error: null bitmap");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t nbytes = (n_rows + 7) / 8;
+  fq_u8 *stage = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&stage, nbytes, s));
+  const unsigned grid = (unsigned)std::min<uint64_t>((nbytes + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_bits_pack<<<grid, 256, 0, s>>>(stage, (const fq_u8 *)col->ptr + row_offset, n_rows);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaMemcpyAsync(host_bits, stage, nbytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaFreeAsync(stage, s));
+  return FQ_OK;
+}
 fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream) {
   if (fq_status st = use(ctx)) return st;
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));

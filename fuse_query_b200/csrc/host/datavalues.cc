@@ -433,6 +433,23 @@ DataArrayRef DataArray::from_host(GpuContextRef ctx, DataType t, const void *dat
   }
   return a;
 }
+DataArrayRef DataArray::from_arrow_bitmap(GpuContextRef ctx, const void *bits, uint64_t bit_offset, uint64_t len) {
+  auto a = alloc(ctx, FQ_BOOL, len);
+  if (len) {
+    ctx->check(fq_column_upload_bits(ctx->raw(), a->col_, 0, bits, bit_offset, len, ctx->stream));
+    ctx->check(fq_stream_synchronize(ctx->raw(), ctx->stream));
+  }
+  return a;
+}
+std::vector<unsigned char> DataArray::to_arrow_bitmap() const {
+  if (dtype_ != FQ_BOOL) throw FuseQueryError::internal("to_arrow_bitmap on a non-Boolean array");
+  std::vector<unsigned char> out((len_ + 7) / 8);
+  if (len_) {
+    ctx_->check(fq_column_download_bits(ctx_->raw(), col_, 0, out.data(), len_, ctx_->stream));
+    ctx_->check(fq_stream_synchronize(ctx_->raw(), ctx_->stream));
+  }
+  return out;
+}
 void DataArray::set_validity(DataArrayRef validity) {
   if (is_utf8()) throw FuseQueryError::internal("validity on a Utf8 array is not supported");
   if (validity && (validity->data_type() != FQ_BOOL || validity->len() < len_)) throw FuseQueryError::internal("validity must be a Boolean array of the same length");

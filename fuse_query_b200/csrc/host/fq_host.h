@@ -95,6 +95,9 @@ class DataArray : public std::enable_shared_from_this<DataArray> {
   static std::shared_ptr<DataArray> device(GpuContextRef ctx, fq_column *col, std::shared_ptr<DataArray> parent = nullptr);
   static std::shared_ptr<DataArray> alloc(GpuContextRef ctx, DataType t, uint64_t len);
   static std::shared_ptr<DataArray> from_host(GpuContextRef ctx, DataType t, const void *data, uint64_t len);
+  // Arrow LSB-first bitmaps (BooleanArray values, validity buffers) <-> the device's byte per row
+  static std::shared_ptr<DataArray> from_arrow_bitmap(GpuContextRef ctx, const void *bits, uint64_t bit_offset, uint64_t len);
+  std::vector<unsigned char> to_arrow_bitmap() const;   // Boolean arrays only; ceil(len / 8) bytes
   // validity: a Boolean array of the same length (one byte per row, 1 = valid) or null for a NOT NULL array
   void set_validity(std::shared_ptr<DataArray> validity);
   const std::shared_ptr<DataArray> &validity() const { return validity_; }

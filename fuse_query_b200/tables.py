@@ -14,16 +14,16 @@ _TAG = {np.dtype(np.bool_): h.DataType.Boolean, np.dtype(np.int8): h.DataType.In
 
 
 def _arrow_column(col):
-    """pyarrow ChunkedArray/Array -> (values, validity bytes or None).  The arrow null bitmap (1 bit per row, LSB first)
-    becomes the device layout: one byte per row, 1 = valid."""
+    """pyarrow ChunkedArray/Array -> (values, validity or None).  The validity comes back as ("bitmap", buffer, bit
+    offset): the arrow null bitmap itself (1 bit per row, LSB first), which the device expands to its own layout (one
+    byte per row) — no host-side unpacking."""
     import pyarrow as pa
     arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
     if not arr.null_count:
         return arr.to_numpy(zero_copy_only=False), None
-    valid = np.asarray(arr.is_valid().to_numpy(zero_copy_only=False)).astype(np.uint8)
     zero = False if pa.types.is_boolean(arr.type) else 0
     values = arr.fill_null(zero).to_numpy(zero_copy_only=False)   # the payload of a NULL slot is never read as a value
-    return values, valid
+    return values, ("bitmap", arr.buffers()[0], arr.offset)
 
 
 def register_table(ctx, gpu, db: str, name: str, columns: Mapping[str, "np.ndarray"]):
@@ -48,7 +48,14 @@ def register_table(ctx, gpu, db: str, name: str, columns: Mapping[str, "np.ndarr
         if a.dtype not in _TAG:
             raise h.FuseQueryError(f"Internal Error: Unsupported on the device path: column {n} of dtype {a.dtype}")
         fields.append(h.DataField(n, _TAG[a.dtype], valid is not None))
-        arrays.append(h.DataArray.from_numpy(gpu, a) if valid is None else h.DataArray.from_numpy_masked(gpu, a, np.asarray(valid)))
+        if valid is None:
+            arrays.append(h.DataArray.from_numpy(gpu, a))
+        elif isinstance(valid, tuple) and valid[0] == "bitmap":
+            arr = h.DataArray.from_numpy(gpu, a)
+            arr.set_validity(h.DataArray.from_arrow_bitmap(gpu, valid[1].address, valid[2], len(a)))
+            arrays.append(arr)
+        else:
+            arrays.append(h.DataArray.from_numpy_masked(gpu, a, np.asarray(valid)))
     table = h.MemoryTable(db, name, h.DataSchema(fields), arrays)
     ds = ctx.datasource()
     ds.add_database(db) if not _has_db(ds, db) else None

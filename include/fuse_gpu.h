@@ -133,6 +133,16 @@ void *fq_column_device_ptr(const fq_column *col);
 /* async copies of `n_rows` values starting at row `row_offset`; host memory should be pinned */
 fq_status fq_column_upload(fq_ctx *ctx, fq_column *col, uint64_t row_offset, const void *host, uint64_t n_rows, void *stream);
 fq_status fq_column_download(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host, uint64_t n_rows, void *stream);
+/* Arrow bitmaps <-> the device's one byte per row.  The reference's BooleanArray values and every array's validity
+ * are LSB-first bitmaps (arrow 2.0.0 bitmap.rs / buffer.rs; `DataBlock` columns are arrow ArrayRef,
+ * datablocks/data_block.rs:10-14).  `col` must be a Boolean column (values, or the validity column of another).
+ * upload: rows [row_offset, row_offset + n_rows) = bits [bit_offset, bit_offset + n_rows) of `host_bits`, expanded by
+ * a kernel (one source byte -> one 8-byte store); download: the inverse, `host_bits` receives ceil(n_rows / 8)
+ * bytes starting at bit 0, padding bits zero.  Async on `stream` like the plain copies. */
+fq_status fq_column_upload_bits(fq_ctx *ctx, fq_column *col, uint64_t row_offset, const void *host_bits, uint64_t bit_offset,
+                                uint64_t n_rows, void *stream);
+fq_status fq_column_download_bits(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host_bits, uint64_t n_rows,
+                                  void *stream);
 fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream);
 /* pinned host staging memory */
 fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out);

@@ -242,3 +242,43 @@ def test_random_trees_over_nullable_columns(env, seed):
     pipe, got, gv, written = project(ctx, cols, exprs, p)
     assert written == want.n_rows
     check(pipe, got, gv, want, exprs)
+
+
+@pytest.mark.parametrize("n,bit_offset", [(1, 0), (7, 0), (8, 0), (9, 3), (64, 5), (1000, 7), (100_003, 0), (100_003, 13), (1_000_001, 6)])
+def test_arrow_bitmaps_expand_and_pack_on_the_device(env, n, bit_offset):
+    """include/fuse_gpu.h fq_column_upload_bits / _download_bits: arrow's LSB-first validity / Boolean bitmaps
+    (arrow 2.0.0 bitmap.rs) <-> one byte per row, against numpy's packbits / unpackbits (bitorder='little')."""
+    ctx, *_ = env
+    rng = np.random.default_rng(n + bit_offset)
+    bits = rng.integers(0, 256, (bit_offset + n + 7) // 8 + 2, dtype=np.uint8)
+    want = np.unpackbits(bits, bitorder="little")[bit_offset:bit_offset + n]
+    col = ctx.from_bitmap(bits, n, bit_offset)
+    assert np.array_equal(col.to_numpy(n), want)
+    packed = col.to_bitmap(n)
+    assert np.array_equal(packed, np.packbits(want, bitorder="little"))
+    # a slice that starts off the byte grid packs from its own row 0
+    if n > 11:
+        sl = col.slice(3, n - 11)
+        assert np.array_equal(sl.to_bitmap(), np.packbits(want[3:n - 8], bitorder="little"))
+
+
+def test_pyarrow_validity_bitmap_goes_to_the_device_unexpanded(env):
+    """tables.register_table hands arrow's own null bitmap (with the array's offset) to the device."""
+    import pyarrow as pa
+    from fuse_query_b200 import _fuse_host as h
+    from fuse_query_b200.tables import register_table
+    gpu = h.GpuContext.create(0)
+    fctx = h.FuseQueryContext.create_ctx(1, gpu)
+    n = 10_007
+    rng = np.random.default_rng(1)
+    vals = rng.integers(0, 1000, n)
+    mask = rng.random(n) < 0.3
+    arr = pa.array(vals, type=pa.int64(), mask=mask).slice(5, n - 9)      # a non-zero arrow offset
+    t = register_table(fctx, gpu, "default", "bm", {"x": arr, "y": np.arange(n - 9, dtype=np.uint64)})
+    assert t.schema().fields[0].nullable
+    got = h.execute_sql(fctx, "select x, y from bm")[0]
+    want = [None if m else int(v) for v, m in zip(vals[5:n - 4], mask[5:n - 4])]
+    assert got.column(0).to_list() == want
+    assert got.column(0).validity().to_arrow_bitmap() == np.packbits(~mask[5:n - 4], bitorder="little").tobytes()
+    (cnt,) = h.execute_sql(fctx, "select sum(x) from bm")[0].column(0).to_list()
+    assert cnt == int(vals[5:n - 4][~mask[5:n - 4]].sum())
