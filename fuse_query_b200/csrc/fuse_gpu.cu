@@ -751,8 +751,6 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
 
 static fq_status decode_err(uint64_t bits) {
   if (bits & FQ_E_DIVZERO) return set_err(FQ_ERR_DIVIDE_BY_ZERO, "Internal Error: Divide by zero error");
-  if (bits & FQ_E_CAST)
-    return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: a numeric cast went out of range (arrow yields NULL; nullable results are not carried yet)");
   return FQ_OK;
 }
 

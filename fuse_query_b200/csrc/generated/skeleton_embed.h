@@ -33,7 +33,6 @@ typedef unsigned char fq_u8;
 typedef signed char fq_i8;
 
 #define FQ_E_DIVZERO 1u  // arrow DivideByZero
-#define FQ_E_CAST 2u     // arrow cast would have produced a null (out-of-range numeric cast)
 
 // launch shapes (the host reads the same macros through fq_skeleton_config.h)
 #ifndef FQ_AGG_THREADS
@@ -155,9 +154,9 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
-// Store V consecutive )FQSK"
-R"FQSK(values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
-// `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
+// Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
+// `bas)FQSK"
+R"FQSK(e + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
 template <class T, int V>
 __device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
   constexpr int BYTES = V * (int)sizeof(T);
@@ -301,9 +300,9 @@ template <class T> __device__ __forceinline__ T fq_shfl_xor(T x, int m) {
 
 // ---------------------------------------------------------------------------------------------
 // block-level reduction of a generated accumulator:  registers -> warp shuffles -> shared -> warp 0
-// result valid in )FQSK"
-R"FQSK(thread 0
-// ---------------------------------------------------------------------------------------------
+// result valid in thread 0
+// ----------------------------------------------------------------------------------)FQSK"
+R"FQSK(-----------
 template <class Q>
 __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &nsel, fq_u32 &err,
                                                 fq_u64 (*sm)[FQ_STATE_HDR + Q::NSLOTS]) {
@@ -496,12 +495,12 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   // remainder groups (< one chunk) and the scalar tail (< V rows), spread over the whole grid
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
-  for (fq_u64 g = nfull * chunk + tid; g < n)FQSK"
-R"FQSK(vec; g += nthreads) {
+  for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);
     fq_u32 kept = 0;
-#pragma unroll
+#prag)FQSK"
+R"FQSK(ma unroll
     for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
     if constexpr (Q::TRACK_BLOCKS) {
       if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
@@ -665,22 +664,24 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 // fq_select_kernel — fused predicate + order-preserving stream compaction + projection (+ limit).
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
-// (tile = 32 * W)FQSK"
-R"FQSK( * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
-// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are assigned round-robin to
-// the CTAs of a persistent, fully resident grid.
+// (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
+// tile_base + w)FQSK"
+R"FQSK( * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are claimed dynamically
+// (atomicAdd) by the CTAs of a persistent grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
 //                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
-//   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
-//                     segment's global base by a decoupled look-back over 64-bit descriptors {flag:2, count:62};
-//   workers, pass 2   (one segment behind) warps that selected something in a tile re-read that tile (still in the
-//                     126 MB L2: <= resident CTAs * 2 * 128 KB are in flight), rank rows with __ballot_sync / __popc
-//                     of the lower-lane mask and write each selected row once, projected at scatter time.
-// The look-back of segment k (a chain of global round trips that also waits for the slowest predecessor)
-// overlaps the workers' pass 1 of segment k + 1: named barriers FULL[k&1] (workers arrive, scan waits) and
-// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
-// warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back per 16-KB tile cannot keep up
-// with HBM at all (0.7 TB/s measured).
+//                     the last warp to finish publishes the segment's aggregate descriptor (fq_sel_publish_agg);
+//   scan warp         turns the counts into exclusive offsets and resolves the segment's global base by a look-back
+//                     over 64-bit descriptors {flag:2, count:62} that stops at the CTA's own previous segment
+//                     (fq_sel_lookback), then publishes the inclusive prefix;
+//   workers, pass 2   (two segments behind) warps that selected something in a tile re-read those rows (still in
+//                     the 126 MB L2: <= resident CTAs * 3 * 128 KB are in flight), rank them with __ballot_sync /
+//                     __popc of the lower-lane mask and write each selected row once, projected at scatter time.
+// The look-back of segment k overlaps the workers' pass 1 of segments k + 1 and k + 2: named barriers FULL[k % 3]
+// (workers arrive, scan waits) and DONE[k % 3] (scan arrives, workers wait) form a three-slot ring.  With block-wide
+// barriers instead, ncu showed 16-25 warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back
+// per 16-KB tile cannot keep up with HBM at all (0.7 TB/s measured).  fq_select_tma_kernel below is the same
+// algorithm with pass 1 staged by bulk copies; this kernel serves generated sources (nothing to copy).
 // Rows beyond min(limit, capacity) are counted, not written.  Early exit: the segment that reaches `stop_after`
 // raises a flag; a CTA that sees it when claiming publishes a saturated prefix for the claimed segment and leaves.
 // Algorithmic traffic: sizeof(row) read per row from HBM + sum(sizeof(out_i)) written per selected row.
@@ -751,7 +752,7 @@ template <int V> struct fq_sel_shape {
   static constexpr int SEG = (FQ_SEL_SEG * U * V <= 64) ? FQ_SEL_SEG : (64 / (U * V));
 };
 
-enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2)
+enum { FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2; 0 is __syncthreads)
 
 // scan warp, step 1: per-(tile, worker warp) selected counts -> exclusive offsets inside the segment (in place,
 // (tile, warp) order); returns the segment total.  Called by all 32 lanes of the scan warp.
@@ -804,10 +805,10 @@ __device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq
 // A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  So when it
 // looks back from segment `seg` it already knows the inclusive prefix `prev_incl` of the segment `prev_seg` it
 // resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
-// and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
+// and never has to wait for anybody's PREFIX. )FQSK"
+R"FQSK( That matters: a classic decoupled look-back ends at the nearest
 // published prefix, prefixes are published only when a look-back ends, and with hundreds of segments in flight the
-//)FQSK"
-R"FQSK( chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
+// chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
 // the CTA's own history the walk is 1-2 polls of FQ_SEL_LOOK * 32 descriptors, independent of the others' progress.
 // A nearer published prefix still ends the walk early; the first segment of a CTA (prev_seg < 0) walks to one.
 __device__ __forceinline__ fq_u64 fq_sel_lookback(const fq_launch_params &p, fq_u64 seg, fq_u32 tot, fq_i64 prev_seg, fq_u64 prev_incl) {
@@ -971,12 +972,12 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   const int wthreads = (int)blockDim.x - 32, nwarps = wthreads >> 5, allthreads = (int)blockDim.x;
   const bool is_scan = (int)threadIdx.x >= wthreads;
   const fq_u32 lt_mask = (1u << lane) - 1u;
-  const fq_u64 n_seg = p.n_tiles;
+  const fq_u64 n_)FQSK"
+R"FQSK(seg = p.n_tiles;
   fq_u32 err = 0;
 
   // Segments are claimed dynamically (atomicAdd): only running CTAs own segments, so every predecessor of a running
-  // segment has started and t)FQSK"
-R"FQSK(he look-back makes progress whatever else shares the GPU.  Claiming and observing the
+  // segment has started and the look-back makes progress whatever else shares the GPU.  Claiming and observing the
   // early-exit flag happen together: a claimed segment is ALWAYS published (a successor may already be polling it); a CTA
   // that sees the flag publishes a saturated prefix for the segment it just claimed and leaves.
   // Thread 0 claims the segment of iteration k + 1 at the start of iteration k and hands it to the other warps through a
@@ -1131,12 +1132,12 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   __shared__ fq_u64 s_excl[R];
   __shared__ unsigned long long s_acc[R];
   __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
-  __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
+  __shared__ volatile fq_u32 s_stop[)FQSK"
+R"FQSK(FQ_SELT_CLAIMS];
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
   __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];   // full[0..STAGES), empty[0..STAGES)
 
-  const int lane = thr)FQSK"
-R"FQSK(eadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cthreads = (int)blockDim.x - 64, cwarps = cthreads >> 5, barthreads = cthreads + 32;
   const bool is_scan = (int)threadIdx.x >= cthreads && (int)threadIdx.x < cthreads + 32;
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
@@ -1319,13 +1320,13 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
       } else {
 #pragma unroll
         for (int v = 0; v < V; v++)
-          if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+          if (row0 + v )FQSK"
+R"FQSK(< p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
       }
     }
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
-  const fq_u64 nthreads = (fq_u64)gridDim.x )FQSK"
-R"FQSK(* blockDim.x;
+  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
   for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
     typename Q::Rows r;
     Q::load(r, p, g);

@@ -32,7 +32,6 @@ typedef unsigned char fq_u8;
 typedef signed char fq_i8;
 
 #define FQ_E_DIVZERO 1u  // arrow DivideByZero
-#define FQ_E_CAST 2u     // arrow cast would have produced a null (out-of-range numeric cast)
 
 // launch shapes (the host reads the same macros through fq_skeleton_config.h)
 #ifndef FQ_AGG_THREADS
@@ -662,20 +661,22 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
 // (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
-// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are assigned round-robin to
-// the CTAs of a persistent, fully resident grid.
+// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are claimed dynamically
+// (atomicAdd) by the CTAs of a persistent grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
 //                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
-//   scan warp         turns the counts into exclusive offsets, publishes the segment total and resolves the
-//                     segment's global base by a decoupled look-back over 64-bit descriptors {flag:2, count:62};
-//   workers, pass 2   (one segment behind) warps that selected something in a tile re-read that tile (still in the
-//                     126 MB L2: <= resident CTAs * 2 * 128 KB are in flight), rank rows with __ballot_sync / __popc
-//                     of the lower-lane mask and write each selected row once, projected at scatter time.
-// The look-back of segment k (a chain of global round trips that also waits for the slowest predecessor)
-// overlaps the workers' pass 1 of segment k + 1: named barriers FULL[k&1] (workers arrive, scan waits) and
-// DONE[k&1] (scan arrives, workers wait) form a two-slot ring.  With block-wide barriers instead, ncu showed 16-25
-// warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back per 16-KB tile cannot keep up
-// with HBM at all (0.7 TB/s measured).
+//                     the last warp to finish publishes the segment's aggregate descriptor (fq_sel_publish_agg);
+//   scan warp         turns the counts into exclusive offsets and resolves the segment's global base by a look-back
+//                     over 64-bit descriptors {flag:2, count:62} that stops at the CTA's own previous segment
+//                     (fq_sel_lookback), then publishes the inclusive prefix;
+//   workers, pass 2   (two segments behind) warps that selected something in a tile re-read those rows (still in
+//                     the 126 MB L2: <= resident CTAs * 3 * 128 KB are in flight), rank them with __ballot_sync /
+//                     __popc of the lower-lane mask and write each selected row once, projected at scatter time.
+// The look-back of segment k overlaps the workers' pass 1 of segments k + 1 and k + 2: named barriers FULL[k % 3]
+// (workers arrive, scan waits) and DONE[k % 3] (scan arrives, workers wait) form a three-slot ring.  With block-wide
+// barriers instead, ncu showed 16-25 warp-cycles of barrier stall per issued instruction and 2.1 TB/s; a look-back
+// per 16-KB tile cannot keep up with HBM at all (0.7 TB/s measured).  fq_select_tma_kernel below is the same
+// algorithm with pass 1 staged by bulk copies; this kernel serves generated sources (nothing to copy).
 // Rows beyond min(limit, capacity) are counted, not written.  Early exit: the segment that reaches `stop_after`
 // raises a flag; a CTA that sees it when claiming publishes a saturated prefix for the claimed segment and leaves.
 // Algorithmic traffic: sizeof(row) read per row from HBM + sum(sizeof(out_i)) written per selected row.
@@ -746,7 +747,7 @@ template <int V> struct fq_sel_shape {
   static constexpr int SEG = (FQ_SEL_SEG * U * V <= 64) ? FQ_SEL_SEG : (64 / (U * V));
 };
 
-enum { FQ_BAR_WORKERS = 1, FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2)
+enum { FQ_BAR_FULL = 2, FQ_BAR_DONE = 5, FQ_SEL_RING = 3 };  // named barrier ids (FULL/DONE take +0..+2; 0 is __syncthreads)
 
 // scan warp, step 1: per-(tile, worker warp) selected counts -> exclusive offsets inside the segment (in place,
 // (tile, warp) order); returns the segment total.  Called by all 32 lanes of the scan warp.
