@@ -16,7 +16,9 @@
  *     legacy default stream) and is asynchronous; results are read with the matching *_fetch call;
  *   - a context binds one CUDA device; calls set the device themselves, so any host thread may
  *     drive any context (the reference runs one tokio task per partition pipe,
- *     processors/processor_merge.rs:46-62).
+ *     processors/processor_merge.rs:46-62).  Contexts and columns may be shared between threads; a pipe
+ *     owns running state (aggregate state, result slots) and is driven by one thread at a time — the
+ *     reference clones its Function per pipe for the same reason (pipeline_builder.rs:50-65).
  */
 #ifndef FUSE_GPU_H
 #define FUSE_GPU_H
