@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[3], the README headline query):
     SELECT sum(number)/count(number), max(number), min(number) FROM system.numbers_mt(10_000_000_000)
 One "step" = one pass of the fused Source -> AggregatePartial kernel over every rank's shard of the
 10^10-row UInt64 column (materialised in HBM, 80 GB at N=1) + the merge of the per-rank partial states
-(NCCL all-gather of 64 bytes per rank when N > 1) — strong scaling: the 10^10 rows are partitioned
+(NCCL all-gather of the 80-byte state per rank when N > 1) — strong scaling: the 10^10 rows are partitioned
 across ranks exactly like the reference chunks its 8 partitions over workers
 (processors/pipeline_builder.rs:73-95).
 
@@ -399,7 +399,7 @@ def run_ours(args):
                        "partitioning": f"{8 // world if world <= 8 else 1} of the reference's 8 partitions per GPU",
                        "host_affinity": numa,
                        "l2": "inputs (>= 10 GB per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "merge": "nccl all_gather of the 64-byte state" if world > 1 else "single GPU",
+                       "merge": f"nccl all_gather of the {state_bytes}-byte state" if world > 1 else "single GPU",
                        "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
             "hbm_gb_per_s": row_bytes * total * args.steps / secs / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n, generated),
@@ -471,7 +471,7 @@ def run_sql_e2e(device, total):
 def run_e2e(args, ctx, torch, dist, rank, world, local):
     """Same query, inputs in HOST memory: each step copies this rank's share of an `e2e_rows`-row column
     from pinned memory in chunks (double-buffered against the kernel, which folds chunk after chunk into
-    the running state) and reads the 64-byte state back."""
+    the running state) and reads the state (80 bytes) back."""
     import ctypes as C
 
     import numpy as np
@@ -488,6 +488,7 @@ def run_e2e(args, ctx, torch, dist, rank, world, local):
     chunk = min(n, args.e2e_chunk_rows)
     bufs = [ctx.column(cabi.U64, chunk), ctx.column(cabi.U64, chunk)]
     pipe = ctx.pipe(HEADLINE, aggregate=True)
+    state_bytes = pipe.state_device()[1]
     copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
     free_ev = [torch.cuda.Event(), torch.cuda.Event()]
     full_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -507,7 +508,7 @@ def run_e2e(args, ctx, torch, dist, rank, world, local):
             pipe.launch_aggregate(cabi.make_source([bufs[b]], m), accumulate=k > 0, stream=comp_s.cuda_stream)
             free_ev[b].record(comp_s)
             h2d += m * 8
-            d2h += 64
+            d2h += state_bytes   # every launch queues the D2H copy of the running state behind the kernel
             k += 1
         return pipe.fetch_aggregate()  # waits for the last launch, D2H of the state
 
