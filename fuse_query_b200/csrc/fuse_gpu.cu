@@ -239,7 +239,19 @@ __global__ void __launch_bounds__(256) fq_fill_numbers(fq_u64 *dst, fq_u64 begin
   const bool aligned = (((fq_u64)dst) & 15) == 0;
   if (aligned) {
     const fq_u64 nvec = n / 2;
-    for (fq_u64 g = tid; g < nvec; g += nthreads) {
+    // each CTA writes contiguous 16-KB chunks: 4 independent 16-byte stores in flight per thread, every warp store one 512-B run
+    const fq_u64 chunk = 4ull * blockDim.x, nfull = nvec / chunk;
+    for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const fq_u64 g = c * chunk + (fq_u64)k * blockDim.x + threadIdx.x;
+        ulonglong2 v;
+        v.x = begin + 2 * g;
+        v.y = begin + 2 * g + 1;
+        reinterpret_cast<ulonglong2 *>(dst)[g] = v;
+      }
+    }
+    for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
       ulonglong2 v;
       v.x = begin + 2 * g;
       v.y = begin + 2 * g + 1;
