@@ -588,31 +588,41 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     s += "  }\n";
   }
   s += "};\n";
+  // kernel wrappers: the ahead-of-time build compiles all of them, a JIT build only the variant it will launch
+  std::vector<std::pair<std::string, std::string>> wrappers;
   if (d.kind == FQ_PIPE_AGGREGATE) {
-    s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS) fqk_@_agg_u4(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 4>(p); }\n";
+    wrappers.push_back({"_agg_u4", "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS) fqk_@_agg_u4(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 4>(p); }\n"});
     if (out->tma_ok)
-      s += "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_agg_tma(const __grid_constant__ fq_launch_params p) { fq_agg_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n";
+      wrappers.push_back({"_agg_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_agg_tma(const __grid_constant__ fq_launch_params p) { fq_agg_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n"});
+    wrappers.push_back({"_agg_u8", "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n"});
   } else if (out->has_pred) {
-    s += "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS + 32, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, fq_sel_shape<Q_@::V>::U, fq_sel_shape<Q_@::V>::SEG>(p); }\n";
+    wrappers.push_back({"_select", "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS + 32, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, fq_sel_shape<Q_@::V>::U, fq_sel_shape<Q_@::V>::SEG>(p); }\n"});
     if (out->tma_ok)
-      s += "extern \"C\" __global__ void __launch_bounds__(FQ_SELT_THREADS + 64, 1) fqk_@_select_tma(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_selt_shape<Q_@::V>::U, fq_selt_shape<Q_@::V>::SEG, FQ_SELT_STAGES>(p); }\n";
+      wrappers.push_back({"_select_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_SELT_THREADS + 64, 1) fqk_@_select_tma(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_selt_shape<Q_@::V>::U, fq_selt_shape<Q_@::V>::SEG, FQ_SELT_STAGES>(p); }\n"});
   } else {
-    s += "extern \"C\" __global__ void __launch_bounds__(FQ_MAP_THREADS, FQ_MAP_MIN_BLOCKS) fqk_@_map(const __grid_constant__ fq_launch_params p) { fq_map_kernel<Q_@, FQ_MAP_UNROLL>(p); }\n";
+    wrappers.push_back({"_map", "extern \"C\" __global__ void __launch_bounds__(FQ_MAP_THREADS, FQ_MAP_MIN_BLOCKS) fqk_@_map(const __grid_constant__ fq_launch_params p) { fq_map_kernel<Q_@, FQ_MAP_UNROLL>(p); }\n"});
     if (out->tma_ok)
-      s += "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_map_tma(const __grid_constant__ fq_launch_params p) { fq_map_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n";
+      wrappers.push_back({"_map_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_map_tma(const __grid_constant__ fq_launch_params p) { fq_map_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n"});
   }
+  const std::string struct_text = s;
+  for (auto &w : wrappers) s += w.second;
 
   if (g.status != FQ_OK) { *err = g.err; return g.status; }
   out->const_divide_by_zero = g.const_div0;
   char tag[32];
   snprintf(tag, sizeof tag, "%016" PRIx64, fnv1a(s));
   out->tag = tag;
-  std::string src;
-  for (size_t i = 0; i < s.size(); i++) {
-    if (s[i] == '@') src += out->tag; else src += s[i];
-  }
-  out->source = src;
+  auto with_tag = [&](const std::string &text) {
+    std::string src;
+    for (char c : text) {
+      if (c == '@') src += out->tag; else src += c;
+    }
+    return src;
+  };
+  out->source = with_tag(s);
+  out->struct_source = with_tag(struct_text);
+  out->kernels.clear();
+  for (auto &w : wrappers) out->kernels.push_back({w.first, with_tag(w.second)});
   out->node_dtypes = g.ty;
   return FQ_OK;
 }

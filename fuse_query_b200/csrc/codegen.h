@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/fuse_gpu.h"
@@ -11,7 +12,9 @@
 namespace fq {
 
 struct Generated {
-  std::string source;      // struct Q_<hash> + extern "C" kernel wrappers (skeleton not included)
+  std::string source;      // struct Q_<hash> + every extern "C" kernel wrapper (skeleton not included)
+  std::string struct_source;                                   // struct Q_<hash> alone
+  std::vector<std::pair<std::string, std::string>> kernels;   // (suffix such as "_agg_tma", wrapper source): a JIT build picks a subset
   std::string tag;         // 16 hex digits: FNV-1a of the specialised text, names the kernels
   int kind = 0;            // FQ_PIPE_*
   bool has_pred = false;

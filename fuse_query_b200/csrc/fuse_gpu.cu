@@ -182,6 +182,7 @@ struct Kernel {
 
 struct Module {  // one compiled specialisation, shared by every pipe with the same tag
   std::map<std::string, Kernel> kernels;
+  std::vector<std::string> built;   // JIT: suffixes of the kernel variants in the module
   bool precompiled = false;
   CUmodule_ mod = nullptr;
 };
@@ -263,10 +264,13 @@ __global__ void __launch_bounds__(256) fq_fill_numbers(fq_u64 *dst, fq_u64 begin
   }
 }
 
-fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m) {
+// `suffixes`: the kernel variants to build (empty = all of them)
+fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const std::vector<std::string> &suffixes) {
   if (!g_nvrtc.load()) return set_err(FQ_ERR_CUDA, "NVRTC unavailable: %s", g_nvrtc.why.c_str());
   if (!g_drv.load()) return set_err(FQ_ERR_CUDA, "CUDA driver unavailable: %s", g_drv.why.c_str());
-  std::string src = shapes().defines() + std::string(fq_skeleton_src) + "\n" + gen.source;
+  std::string src = shapes().defines() + std::string(fq_skeleton_src) + "\n" + gen.struct_source;
+  for (auto &k : gen.kernels)
+    if (suffixes.empty() || std::find(suffixes.begin(), suffixes.end(), k.first) != suffixes.end()) src += k.second;
   nvrtcProgram_ prog = nullptr;
   int r = g_nvrtc.nvrtcCreateProgram(&prog, src.c_str(), ("fq_" + gen.tag + ".cu").c_str(), 0, nullptr, nullptr);
   if (r) return set_err(FQ_ERR_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.nvrtcGetErrorString(r));
@@ -292,9 +296,11 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m) {
   return FQ_OK;
 }
 
+// A JIT module holds only the variants it was built with: a missing one leaves `out` invalid (the launch falls back).
 fq_status resolve_kernel(Module *m, const std::string &name, int threads, Kernel *out, unsigned smem = 0) {
   auto it = m->kernels.find(name);
   if (it != m->kernels.end()) { *out = it->second; return FQ_OK; }
+  if (!m->precompiled && std::find(m->built.begin(), m->built.end(), name.substr(name.find('_', 4))) == m->built.end()) return FQ_OK;
   Kernel k;
   k.threads = threads;
   k.smem = smem;
@@ -602,8 +608,24 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
         if (strncmp(fq_aot_table[i].name, probe.c_str(), probe.size()) == 0) mod.precompiled = true;
       if (getenv("FQ_FORCE_JIT") || shapes().tuned) mod.precompiled = false;
       if (!mod.precompiled) {
+        // NVRTC + ptxas cost about a second per kernel: build only the variant this pipe will launch (the staged one when
+        // its ring fits, else the LDG one; both handle ragged and unaligned sources).  FQ_JIT_ALL_VARIANTS=1 builds all.
+        std::vector<std::string> want;
+        if (!(getenv("FQ_JIT_ALL_VARIANTS") && atoi(getenv("FQ_JIT_ALL_VARIANTS")) != 0)) {
+          const bool agg = gen.kind == FQ_PIPE_AGGREGATE;
+          const int u = agg || !gen.has_pred ? shapes().tma_unroll : (shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec);
+          const unsigned tile_bytes = (unsigned)(agg || !gen.has_pred ? shapes().tma_threads : shapes().selt_threads) * u * gen.vec * gen.row_bytes;
+          const bool staged = gen.tma_ok && 2u * tile_bytes <= 200u * 1024u;
+          const std::string variant_env = getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT")
+                                              ? getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT") : "tma";
+          if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
+          else if (gen.has_pred) want.push_back(staged && variant_env == "tma" ? "_select_tma" : "_select");
+          else want.push_back(staged && variant_env == "tma" ? "_map_tma" : "_map");
+        }
         std::lock_guard<std::mutex> lk2(g_mu);
-        if (fq_status s2 = compile_jit(ctx, gen, &mod)) { delete pipe; return s2; }
+        if (fq_status s2 = compile_jit(ctx, gen, &mod, want)) { delete pipe; return s2; }
+        for (auto &k : gen.kernels)
+          if (want.empty() || std::find(want.begin(), want.end(), k.first) != want.end()) mod.built.push_back(k.first);
       }
       it = ctx->modules.emplace(gen.tag, mod).first;
     }
@@ -721,9 +743,11 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   if (fq_status st = bind_source(pipe, src, &p)) return st;
   // kernel variant: FQ_AGG_VARIANT = tma (default: bulk-copy staged; needs every referenced column materialised) | u4 | u8
   const std::string variant = getenv("FQ_AGG_VARIANT") ? getenv("FQ_AGG_VARIANT") : (getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8 ? "u8" : FQ_AGG_DEFAULT_VARIANT);
-  const bool use_tma = variant == "tma" && pipe->k_agg_tma.valid();
-  const bool want_u8 = variant == "u8";
+  // the preferred variant when the module holds it, else whichever it was built with
+  const bool use_tma = (variant == "tma" && pipe->k_agg_tma.valid()) || (!pipe->k_agg_u4.valid() && !pipe->k_agg_u8.valid());
+  const bool want_u8 = (variant == "u8" && pipe->k_agg_u8.valid()) || (!use_tma && !pipe->k_agg_u4.valid());
   const Kernel &k = use_tma ? pipe->k_agg_tma : want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
+  if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no aggregate kernel was built for this pipe");
   const int unroll = use_tma ? shapes().tma_unroll : want_u8 ? 8 : 4;
   // persistent grid: every resident CTA slot of every SM, fewer when the shard has fewer chunks
   const uint64_t chunk_rows = (uint64_t)(use_tma ? k.threads - 32 : k.threads) * unroll * pipe->gen.vec;
@@ -845,8 +869,9 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   } else if (pipe->gen.has_pred) {
     // kernel variant: FQ_SEL_VARIANT = tma (default: pass 1 staged by bulk copies; needs every referenced column materialised) | ldg
     const std::string variant = getenv("FQ_SEL_VARIANT") ? getenv("FQ_SEL_VARIANT") : FQ_SEL_DEFAULT_VARIANT;   // read per launch: tests switch it
-    const bool use_tma = variant == "tma" && pipe->k_select_tma.valid();
+    const bool use_tma = (variant == "tma" && pipe->k_select_tma.valid()) || !pipe->k_select.valid();
     const Kernel &k = use_tma ? pipe->k_select_tma : pipe->k_select;
+    if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no select kernel was built for this pipe");
     // work unit = segment of sel_seg tiles; p.n_tiles counts segments (one look-back descriptor each)
     const int vec = pipe->gen.vec;
     const int cfg_u = use_tma ? shapes().selt_unroll : shapes().sel_unroll, cfg_seg = use_tma ? shapes().selt_seg : shapes().sel_seg;
@@ -870,8 +895,9 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   } else {
     // FQ_MAP_VARIANT = tma (default: reads staged by bulk copies; needs every referenced column materialised) | ldg
     const std::string variant = getenv("FQ_MAP_VARIANT") ? getenv("FQ_MAP_VARIANT") : FQ_MAP_DEFAULT_VARIANT;
-    const bool use_tma = variant == "tma" && pipe->k_map_tma.valid();
+    const bool use_tma = (variant == "tma" && pipe->k_map_tma.valid()) || !pipe->k_map.valid();
     const Kernel &k = use_tma ? pipe->k_map_tma : pipe->k_map;
+    if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no projection kernel was built for this pipe");
     p.stages = pipe->mapt_stages;
     const uint64_t chunk_rows = (uint64_t)(use_tma ? shapes().tma_threads * shapes().tma_unroll : k.threads * shapes().map_unroll) * pipe->gen.vec;
     const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;

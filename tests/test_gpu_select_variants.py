@@ -16,6 +16,14 @@ README_PRED = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100)
 PROJ = [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def all_jit_variants():
+    """A JIT build normally holds only the kernel variant it will launch; this file switches variants per test."""
+    os.environ["FQ_JIT_ALL_VARIANTS"] = "1"
+    yield
+    os.environ.pop("FQ_JIT_ALL_VARIANTS", None)
+
+
 @pytest.fixture(params=["ldg", "tma"])
 def variant(request):
     old = os.environ.get("FQ_SEL_VARIANT")
