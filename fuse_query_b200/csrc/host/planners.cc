@@ -275,6 +275,24 @@ std::vector<Tok> lex(const std::string &sql) {
   return out;
 }
 
+// sqlparser's Display of an expression it parsed but sql_to_rex refuses (plan_parser.rs:262-265 formats the AST, not the
+// ExpressionPlan): binary operators without added parentheses, functions as name(args).  Parentheses of the original
+// text are not kept by this parser, so `NOT (a > 1)` prints as `NOT a > 1`.
+static std::string sql_display(const ExpressionPlan &e) {
+  switch (e.kind) {
+    case ExpressionPlan::Field: return e.name;
+    case ExpressionPlan::Constant: return e.value.data_type() == FQ_UTF8 ? "'" + e.value.to_string() + "'" : e.value.to_string();
+    case ExpressionPlan::BinaryExpression: return sql_display(e.args[0]) + " " + e.name + " " + sql_display(e.args[1]);
+    case ExpressionPlan::Function: {
+      std::string out = e.name + "(";
+      for (size_t i = 0; i < e.args.size(); i++) out += (i ? ", " : "") + sql_display(e.args[i]);
+      return out + ")";
+    }
+    case ExpressionPlan::Alias: return sql_display(e.args[0]) + " AS " + e.name;
+    default: return "*";
+  }
+}
+
 struct SqlParser {
   std::vector<Tok> t;
   size_t p = 0;
@@ -341,7 +359,12 @@ struct SqlParser {
     if (tok.k == Tok::Sym && (tok.text == "-" || tok.text == "+")) {   // UnaryOp: not handled by sql_to_rex
       p++;
       ExpressionPlan inner = expr(50);
-      throw FuseQueryError::plan("Unsupported ExpressionPlan: " + tok.text + " " + inner.to_string());
+      throw FuseQueryError::plan("Unsupported ExpressionPlan: " + tok.text + " " + sql_display(inner));
+    }
+    if (is_kw("NOT")) {   // UnaryOp { op: Not }: parsed by sqlparser, refused by sql_to_rex
+      p++;
+      ExpressionPlan inner = expr(15);   // NOT binds looser than the comparisons, tighter than AND / OR
+      throw FuseQueryError::plan("Unsupported ExpressionPlan: NOT " + sql_display(inner));
     }
     if (tok.k == Tok::Word && !reserved(tok.text)) {
       p++;

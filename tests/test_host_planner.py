@@ -101,6 +101,10 @@ def test_literal_typing_and_column_names(ctx):
     ("select sum(number), number from system.numbers_mt", "Error during plan: Projection references non-aggregate values"),
     ("select number from system.numbers_mt having number > 1", "Internal Error: HAVING is not implemented yet"),
     ("select number from system.numbers_mt where number > -1", "Error during plan: Unsupported ExpressionPlan: - 1"),
+    # UnaryOp { Not } parses in sqlparser 0.6 and falls into sql_to_rex's catch-all (plan_parser.rs:262-265), printed as SQL
+    ("select number from system.numbers_mt where not number > 3", "Error during plan: Unsupported ExpressionPlan: NOT number > 3"),
+    ("select number from system.numbers_mt where number > 1 and not max(number) = 'x'",
+     "Error during plan: Unsupported ExpressionPlan: NOT max(number) = 'x'"),
 ])
 def test_planner_errors(ctx, sql, err):
     with pytest.raises(h.FuseQueryError) as e:
