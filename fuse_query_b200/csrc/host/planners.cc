@@ -406,26 +406,39 @@ PlanNode select_to_plan(FuseQueryContextRef ctx, SqlParser &sp) {   // plan_pars
   // FROM: plan_tables_with_joins / create_relation, :155-213
   PlanNode plan = PlanBuilder::empty(true).build();
   if (sp.eat_kw("FROM")) {
-    if (sp.peek().k != Tok::Word) sp.expected("a table name");
-    std::string db = ctx->get_current_database(), table = sp.t[sp.p++].text;
-    if (sp.eat_sym(".")) {
-      db = table;
-      if (sp.peek().k != Tok::Word) sp.expected("a table name");
-      table = sp.t[sp.p++].text;
-    }
-    ITableRef tbl = ctx->get_table(db, table);
-    DataSchemaRef schema = tbl->schema();
-    std::optional<ExpressionPlan> table_args;
     if (sp.eat_sym("(")) {
-      if (!sp.eat_sym(")")) {
-        table_args = sp.expr();
-        while (sp.eat_sym(",")) sp.expr();   // only args[0] is used, :195-197
-        sp.expect_sym(")");
+      // TableFactor::Derived: the subquery's plan (a SelectPlan node) is the input, plan_parser.rs:206-208;
+      // children_to_plans flattens nested selects into one chain of transforms
+      plan = select_to_plan(ctx, sp);
+      sp.expect_sym(")");
+      if (sp.eat_kw("AS")) {
+        if (sp.peek().k != Tok::Word) sp.expected("an identifier after AS");
+        sp.p++;
+      } else if (sp.peek().k == Tok::Word && !SqlParser::reserved(sp.peek().text)) {
+        sp.p++;   // table alias: parsed, not used (columns are resolved by name only)
       }
+    } else {
+      if (sp.peek().k != Tok::Word) sp.expected("a table name");
+      std::string db = ctx->get_current_database(), table = sp.t[sp.p++].text;
+      if (sp.eat_sym(".")) {
+        db = table;
+        if (sp.peek().k != Tok::Word) sp.expected("a table name");
+        table = sp.t[sp.p++].text;
+      }
+      ITableRef tbl = ctx->get_table(db, table);
+      DataSchemaRef schema = tbl->schema();
+      std::optional<ExpressionPlan> table_args;
+      if (sp.eat_sym("(")) {
+        if (!sp.eat_sym(")")) {
+          table_args = sp.expr();
+          while (sp.eat_sym(",")) sp.expr();   // only args[0] is used, :195-197
+          sp.expect_sym(")");
+        }
+      }
+      PlanNode scan = PlanBuilder::scan(db, table, *schema, table_args).build();
+      plan = tbl->read_plan(scan);
     }
     if (sp.eat_sym(",") || sp.is_kw("JOIN")) throw FuseQueryError::internal("Cannot support JOIN clause");
-    PlanNode scan = PlanBuilder::scan(db, table, *schema, table_args).build();
-    plan = tbl->read_plan(scan);
   }
   // WHERE -> FilterPlan (below the projection), :265-276
   if (sp.eat_kw("WHERE")) plan = PlanBuilder::from(plan).filter(sp.expr()).build();

@@ -451,6 +451,36 @@ def test_parquet_and_arrow_ipc_files_become_resident_tables(gpu, tmp_path):
         assert got == want.rows() and len(got) == 25
 
 
+def test_derived_tables_chain_transforms_after_the_fused_pipe(gpu):
+    """FROM (subquery): plan_parser.rs:206-208 plans the subquery and PlanNode::children_to_plans flattens the nested
+    SelectPlan into one chain, so the outer Filter / Projection / Aggregate / Limit run as ordinary transforms after the
+    fused device pipe of the inner query.  Expected rows by hand (the oracle has no nested plans)."""
+    for workers, fuse in ((1, True), (0, True), (0, False)):
+        ctx = make_ctx(gpu, workers, fuse=fuse, block_rows=0 if fuse else 10000)
+        got = rows_of(h.execute_sql(ctx, "select number + 1 from (select number from system.numbers_mt(100000) where number > 2) where number < 8"))
+        assert got == [(4,), (5,), (6,), (7,), (8,)]
+        got = rows_of(h.execute_sql(ctx, "select max(x), count(x), min(x) from (select number * 2 as x from system.numbers_mt(100000) where number < 10) t"))
+        assert got == [(18, 10, 0)]
+        got = rows_of(h.execute_sql(ctx, "select sum(x) / count(x) from (select number * 2 as x from system.numbers_mt(160000))"))
+        assert got == [(159999,)]     # 160000 rows: partitions of whole 10 000-row blocks (no NumbersStream tail quirk, SURVEY F7)
+        # Sum over a filtered subquery meets the emptied blocks of partitions 1..7: the reference's poisoned state (SURVEY F8)
+        with pytest.raises(h.FuseQueryError) as e:
+            h.execute_sql(ctx, "select sum(x) from (select number * 2 as x from system.numbers_mt(100000) where number < 10) t")
+        assert str(e.value) == "Internal Error: DataValue to array cannot be NONE NULL"
+        got = rows_of(h.execute_sql(ctx, "select number from (select number from system.numbers_mt(100000) limit 5) as t where number > 1"))
+        assert got == [(2,), (3,), (4,)]
+        got = rows_of(h.execute_sql(ctx, "select count(number) from (select number from (select number from system.numbers_mt(100000) where number > 9) where number < 20)"))
+        assert got == [(10,)]
+        # the reference's alias rewrite (optimizer_filter_push_down.rs:66-78) turns the outer `x < 8` into `number < 8`, which the
+        # block below it (columns: x) cannot satisfy: the same arrow error
+        with pytest.raises(h.FuseQueryError) as e:
+            h.execute_sql(ctx, "select x from (select number as x from system.numbers_mt(100)) where x < 8")
+        assert 'Unable to get field named "number"' in str(e.value)
+    ctx = make_ctx(gpu, 8, fuse=True)
+    plan = h.Planner().build_from_sql(ctx, "select number + 1 from (select number from system.numbers_mt(100) where number > 2) where number < 8")
+    assert [p.name() for p in plan.children_to_plans()] == ["ReadSourcePlan", "FilterPlan", "ProjectionPlan", "FilterPlan", "ProjectionPlan"]
+
+
 def test_mysql_result_set_matches_the_reference_writer(gpu):
     """servers/mysql/mysql_stream.rs:22-86: column types by data type, cells by arrow's array_value_to_string."""
     import pyarrow as pa

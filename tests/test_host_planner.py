@@ -157,3 +157,21 @@ def test_merge_protocol_without_device():
     for js in ('{"Struct":[{"UInt64":10},{"UInt64":4}]}', '{"Struct":[{"UInt64":60},{"UInt64":24}]}'):
         f.merge_state(h.DataValue.from_json(js).value)
     assert f.merge_result() == h.DataValue(DT.UInt64, 2)   # 70 / 28, integer division (function_aggregator_test.rs:118-140)
+
+
+def test_derived_table_plans_flatten_like_the_reference(ctx):
+    """plan_parser.rs:206-208 + plan_node.rs:60-120: a subquery in FROM is planned on its own and its SelectPlan is skipped
+    when the plan is flattened, so the pipeline is one chain."""
+    plan = h.Planner().build_from_sql(ctx, "select sum(x) from (select number * 2 as x from system.numbers_mt(1000) where number < 10) t")
+    assert [p.name() for p in plan.children_to_plans()] == ["ReadSourcePlan", "FilterPlan", "ProjectionPlan", "AggregatePlan"]
+    pipeline = h.PipelineBuilder.create(ctx, h.Optimizer.create().optimize(plan)).build()
+    text = pipeline.display() if hasattr(pipeline, "display") else str(pipeline)
+    # this module's context builds the reference-shaped pipeline: one processor per plan node, in plan order
+    order = [line.strip().lstrip("└─ ") for line in text.splitlines() if line.strip()]
+    assert order == ["AggregateFinalTransform × 1 processor",
+                     "Merge (AggregatePartialTransform × 8 processors) to (MergeProcessor × 1)",
+                     "AggregatePartialTransform × 8 processors", "ProjectionTransform × 8 processors",
+                     "FilterTransform × 8 processors", "SourceTransform × 8 processors"]
+    with pytest.raises(h.FuseQueryError) as e:
+        h.Planner().build_from_sql(ctx, "select number from (select number from system.numbers_mt(10)) a, system.numbers_mt(5)")
+    assert str(e.value) == "Internal Error: Cannot support JOIN clause"
