@@ -427,6 +427,17 @@ def test_baseline_1e10_materialised_headline(ctx):
     got, rows = gpu_leaf_values(pipe, cabi.make_source([col], n))
     assert rows == n and got == [13106511847580896768, n, n - 1, 0]
     assert got[0] // got[1] == 1310651184
+    # filter + projection over the same shard: row indexes beyond 2^32 through segment claims, look-back and scatter
+    k = 1_000_000_007
+    for generated in (False, True):
+        src = cabi.make_source([] if generated else [col], n, generated=generated)
+        p = ctx.pipe([NUM, f"(+ {NUM} (u64 1))"], predicate=f"(= (* (/ {NUM} (u64 {k})) (u64 {k})) {NUM})", generated=generated)
+        sel, written, (c0, c1) = run_project(ctx, p, src, 2, capacity=16)
+        want = np.arange(0, n, k, dtype=np.uint64)
+        assert sel == written == len(want) == 10 and np.array_equal(c0, want) and np.array_equal(c1, want + 1)
+        p = ctx.pipe([NUM], predicate=f"(>= {NUM} (u64 {n - 7}))", generated=generated)
+        sel, written, (c0,) = run_project(ctx, p, src, 1, capacity=16)
+        assert sel == written == 7 and np.array_equal(c0, np.arange(n - 7, n, dtype=np.uint64))
     col.free()
 
 
