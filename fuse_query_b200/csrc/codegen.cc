@@ -84,6 +84,16 @@ struct Gen {
   bool const_div0 = false;
   int quiet_depth = 0;
 
+  // columns referenced below node i (any depth)
+  void cols_below(int i, std::set<int> *out, int depth = 0) const {
+    if (i < 0 || i >= d.n_nodes || depth > 130) return;
+    const fq_expr_node &n = d.nodes[i];
+    if (n.kind == FQ_EXPR_FIELD) { out->insert(n.column); return; }
+    if (n.kind == FQ_EXPR_CONSTANT) return;
+    cols_below(n.left, out, depth + 1);
+    if (n.kind != FQ_EXPR_ALIAS && n.kind != FQ_EXPR_AGGREGATOR) cols_below(n.right, out, depth + 1);
+  }
+
   bool trivial(int i) const {
     if (i < 0 || i >= d.n_nodes) return false;
     const fq_expr_node &n = d.nodes[i];
@@ -447,6 +457,61 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   for (int c : g.used_cols) s += fmt("    dst.c%d[v] = one.c%d[0];\n", c, c);
   for (int c : null_cols) s += fmt("    dst.k%d[v] = one.k%d[0];\n", c, c);
   s += "  }\n";
+  // Filter + projection pipes read only the predicate's columns in pass 1 (one streaming read of every row); the
+  // projection-only columns are read in pass 2, for the rows that were kept.
+  std::set<int> pred_cols;
+  if (d.kind == FQ_PIPE_PROJECT && out->has_pred) {
+    g.cols_below(d.predicate, &pred_cols);
+    std::vector<int> pred_null;
+    for (int c : pred_cols)
+      if (g.nullable_col(c)) pred_null.push_back(c);
+    out->pred_row_bytes = 0;
+    for (int c : pred_cols)
+      if (!(d.generated && c == 0)) out->pred_row_bytes += (int)dtype_size(g.col_dtype(c));
+    out->pred_row_bytes += (int)pred_null.size();
+    s += fmt("  static constexpr int PRED_ROW_BYTES = %d;\n", out->pred_row_bytes);
+    s += "  __device__ static __forceinline__ void load_pred(Rows &r, const fq_launch_params &p, fq_u64 g) {\n";
+    for (int c : pred_cols) {
+      if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
+      else s += fmt("    fq_load_vec<%s, V>(r.c%d, p.cols[%d], g);\n", ctype(g.col_dtype(c)), c, c);
+    }
+    for (int c : pred_null) s += fmt("    fq_load_vec<bool, V>(r.k%d, p.cols_valid[%d], g);\n", c, c);
+    s += "  }\n";
+    s += "  __device__ static __forceinline__ void load1_pred(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
+    for (int c : pred_cols) {
+      if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
+      else s += fmt("    r.c%d[0] = fq_ld1<%s>(p.cols[%d], row);\n", c, ctype(g.col_dtype(c)), c);
+    }
+    for (int c : pred_null) s += fmt("    r.k%d[0] = fq_ld1<bool>(p.cols_valid[%d], row);\n", c, c);
+    s += "  }\n";
+    out->sel_tma_ok = !pred_cols.empty() && !(d.generated && g.used_cols.count(0)) && !g.used_cols.empty();
+    if (out->sel_tma_ok) {
+      s += "  __device__ static __forceinline__ void tma_issue_pred(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
+      int prefix = 0;
+      for (int c : pred_cols) {
+        int w = (int)dtype_size(g.col_dtype(c));
+        s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
+        prefix += w;
+      }
+      for (int c : pred_null) {
+        s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
+        prefix += 1;
+      }
+      s += "  }\n";
+      s += "  __device__ static __forceinline__ void load_smem_pred(Rows &r, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group) {\n";
+      prefix = 0;
+      for (int c : pred_cols) {
+        int w = (int)dtype_size(g.col_dtype(c));
+        s += fmt("    fq_lds_vec<%s, V>(r.c%d, stage + (size_t)tile_rows * %d, group);\n", ctype(g.col_dtype(c)), c, prefix);
+        prefix += w;
+      }
+      for (int c : pred_null) {
+        s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
+        prefix += 1;
+      }
+      s += "  }\n";
+    }
+  }
   // staged (bulk-copy) access: every referenced column must be materialised; validity bytes are staged like a column
   out->tma_ok = !g.used_cols.empty() && !(d.generated && g.used_cols.count(0));
   out->row_bytes += (int)null_cols.size();
@@ -597,7 +662,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     wrappers.push_back({"_agg_u8", "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n"});
   } else if (out->has_pred) {
     wrappers.push_back({"_select", "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS + 32, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, fq_sel_shape<Q_@::V>::U, fq_sel_shape<Q_@::V>::SEG>(p); }\n"});
-    if (out->tma_ok)
+    if (out->sel_tma_ok)
       wrappers.push_back({"_select_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_SELT_THREADS + 64, 1) fqk_@_select_tma(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_selt_shape<Q_@::V>::U, fq_selt_shape<Q_@::V>::SEG, FQ_SELT_STAGES>(p); }\n"});
   } else {
     wrappers.push_back({"_map", "extern \"C\" __global__ void __launch_bounds__(FQ_MAP_THREADS, FQ_MAP_MIN_BLOCKS) fqk_@_map(const __grid_constant__ fq_launch_params p) { fq_map_kernel<Q_@, FQ_MAP_UNROLL>(p); }\n"});

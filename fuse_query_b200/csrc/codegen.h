@@ -21,6 +21,7 @@ struct Generated {
   bool generated_source = false;
   int vec = 2;             // rows per thread per vector load group (Q::V)
   int row_bytes = 0;       // bytes read per row (materialised columns actually referenced)
+  int pred_row_bytes = 0;  // filter + projection pipes: bytes per row of the predicate's columns (what pass 1 streams)
   std::vector<int> used_cols;
   std::vector<int> null_cols;           // referenced columns that carry validity
   // aggregate pipes: Aggregator leaves in node-index order
@@ -33,6 +34,7 @@ struct Generated {
   std::vector<int> expr_nullable;       // projection pipes: can select expression i yield NULL?
   std::vector<fq_dtype> node_dtypes;    // per node, FQ_NULL when not reachable
   bool tma_ok = false;                  // every referenced column is materialised: the bulk-copy staged kernel exists
+  bool sel_tma_ok = false;              // ... and the predicate reads at least one column: the staged select kernel exists
   bool track_blocks = false;            // aggregate pipe with a predicate and a Sum leaf: reference-block tracking compiled in
   bool const_divide_by_zero = false;    // a literal zero divisor is evaluated for every scanned row
 };

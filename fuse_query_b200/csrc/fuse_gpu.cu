@@ -614,8 +614,9 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
         if (!(getenv("FQ_JIT_ALL_VARIANTS") && atoi(getenv("FQ_JIT_ALL_VARIANTS")) != 0)) {
           const bool agg = gen.kind == FQ_PIPE_AGGREGATE;
           const int u = agg || !gen.has_pred ? shapes().tma_unroll : (shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec);
-          const unsigned tile_bytes = (unsigned)(agg || !gen.has_pred ? shapes().tma_threads : shapes().selt_threads) * u * gen.vec * gen.row_bytes;
-          const bool staged = gen.tma_ok && 2u * tile_bytes <= 200u * 1024u;
+          const unsigned tile_bytes = (unsigned)(agg || !gen.has_pred ? shapes().tma_threads : shapes().selt_threads) * u * gen.vec *
+                                      (agg || !gen.has_pred ? gen.row_bytes : gen.pred_row_bytes);
+          const bool staged = (agg || !gen.has_pred ? gen.tma_ok : gen.sel_tma_ok) && 2u * tile_bytes <= 200u * 1024u;
           const std::string variant_env = getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT")
                                               ? getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT") : "tma";
           if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
@@ -648,10 +649,10 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       }
     } else if (gen.has_pred) {
       s2 = resolve_kernel(m, base + "_select", shapes().sel_threads + 32, &pipe->k_select);   // worker warps + one scan warp
-      if (!s2 && gen.tma_ok) {
+      if (!s2 && gen.sel_tma_ok) {
         // staged variant: consumer warps + scan warp + producer warp; ring of ~192 KB per CTA, at least 2 tiles
         const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
-        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.row_bytes;
+        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
         // ~192 KB in flight per SM measured best here (1.19 -> 1.14 ms at 1e9 rows; the aggregate kernel peaks at 128 KB)
         unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (192u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);

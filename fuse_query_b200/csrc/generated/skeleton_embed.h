@@ -698,7 +698,8 @@ __device__ __forceinline__ void fq_bar_arrive(int id, int count) { asm volatile(
 // fq_tile_load only issues the loads (full tiles vectorised, the ragged last one row by row), fq_tile_pred
 // evaluates the predicate on rows that exist: bit (u * V + v) of the returned mask is set for kept rows.
 // `wthreads` = worker threads of the CTA (the tile geometry ignores the scan warp).
-template <class Q, int U>
+// PRED: only the predicate's columns (pass 1); otherwise every referenced column (pass 2 projects from them).
+template <class Q, int U, bool PRED = false>
 __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 tile, int wthreads, typename Q::Rows (&rows)[U]) {
   constexpr int V = Q::V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -706,7 +707,10 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
   const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
   if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
-    for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
+    for (int u = 0; u < U; u++) {
+      if constexpr (PRED) Q::load_pred(rows[u], p, g0 + 32ull * u);
+      else Q::load(rows[u], p, g0 + 32ull * u);
+    }
   } else if (tile * tile_groups * V < p.n_rows) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -715,7 +719,8 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
       for (int v = 0; v < V; v++) {
         if (row0 + v < p.n_rows) {
           typename Q::Rows one;
-          Q::load1(one, p, row0 + v);
+          if constexpr (PRED) Q::load1_pred(one, p, row0 + v);
+          else Q::load1(one, p, row0 + v);
           Q::copy_row(rows[u], v, one);
         }
       }
@@ -802,11 +807,11 @@ __device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq
 // scan warp, step 2: resolve the segment's exclusive global base by a look-back over the 64-bit descriptors
 // {flag:2, count:62} of its predecessors, publish the inclusive prefix.
 //
-// A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  So when it
+// A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  S)FQSK"
+R"FQSK(o when it
 // looks back from segment `seg` it already knows the inclusive prefix `prev_incl` of the segment `prev_seg` it
 // resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
-// and never has to wait for anybody's PREFIX. )FQSK"
-R"FQSK( That matters: a classic decoupled look-back ends at the nearest
+// and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
 // published prefix, prefixes are published only when a look-back ends, and with hundreds of segments in flight the
 // chain costs 7-10 us per segment per CTA (measured: the kernel ran at 1 segment per look-back latency).  Bounded by
 // the CTA's own history the walk is 1-2 polls of FQ_SEL_LOOK * 32 descriptors, independent of the others' progress.
@@ -967,13 +972,13 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   __shared__ unsigned long long s_acc[FQ_SEL_RING];         // {arrived worker warps, selected rows} of the segment being streamed
   __shared__ volatile fq_u64 s_seg[4];           // claimed segment ids: ring of 4 (the scan warp lags the workers by up to 2)
   __shared__ volatile fq_u32 s_stop[4];
-  __shared__ volatile int s_ready[4];
+  __shared__ volatile int s_)FQSK"
+R"FQSK(ready[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wthreads = (int)blockDim.x - 32, nwarps = wthreads >> 5, allthreads = (int)blockDim.x;
   const bool is_scan = (int)threadIdx.x >= wthreads;
   const fq_u32 lt_mask = (1u << lane) - 1u;
-  const fq_u64 n_)FQSK"
-R"FQSK(seg = p.n_tiles;
+  const fq_u64 n_seg = p.n_tiles;
   fq_u32 err = 0;
 
   // Segments are claimed dynamically (atomicAdd): only running CTAs own segments, so every predecessor of a running
@@ -1057,10 +1062,10 @@ R"FQSK(seg = p.n_tiles;
     if (active) {
       typename Q::Rows rows0[U], rows_n[U];
       fq_u32 wsum = 0;
-      fq_tile_load<Q, U>(p, seg * SEG, wthreads, rows0);
+      fq_tile_load<Q, U, true>(p, seg * SEG, wthreads, rows0);
 #pragma unroll
       for (int t = 0; t < SEG; t++) {
-        if (t + 1 < SEG) fq_tile_load<Q, U>(p, seg * SEG + t + 1, wthreads, rows_n);   // next tile's loads in flight
+        if (t + 1 < SEG) fq_tile_load<Q, U, true>(p, seg * SEG + t + 1, wthreads, rows_n);   // next tile's loads in flight
         const fq_u32 keep = fq_tile_pred<Q, U>(p, seg * SEG + t, wthreads, rows0, err);
         keepbits |= (fq_u64)keep << (t * BITS);
         const fq_u32 wcount = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
@@ -1126,14 +1131,14 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   constexpr int LAG = FQ_SELT_LAG;            // pass 2 runs this many segments behind pass 1 (absorbs the skew between CTAs)
   constexpr int R = LAG + 1;                  // ring of count / base slots and of FULL / DONE named barriers
   constexpr int BAR_FULL = 2, BAR_DONE = 2 + R;
-  static_assert(2 + 2 * R <= 16, "named barriers");
+  static_assert(2 + 2 * R <= )FQSK"
+R"FQSK(16, "named barriers");
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
   __shared__ fq_u32 s_cnt[R][SEG][FQ_MAX_WARPS];
   __shared__ fq_u64 s_excl[R];
   __shared__ unsigned long long s_acc[R];
   __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
-  __shared__ volatile fq_u32 s_stop[)FQSK"
-R"FQSK(FQ_SELT_CLAIMS];
+  __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
   __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];   // full[0..STAGES), empty[0..STAGES)
 
@@ -1143,7 +1148,7 @@ R"FQSK(FQ_SELT_CLAIMS];
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES;   // pass 1 stages the predicate's columns only
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
   const int stages = (int)p.stages;
@@ -1185,7 +1190,7 @@ R"FQSK(FQ_SELT_CLAIMS];
             if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
             const fq_u32 full = fq_smem_addr(&s_bars[slot]);
             fq_mbar_expect_tx(full, stage_bytes);
-            Q::tma_issue(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
+            Q::tma_issue_pred(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
             if (++slot == stages) { slot = 0; round++; }
           }
         }
@@ -1255,7 +1260,7 @@ R"FQSK(FQ_SELT_CLAIMS];
           const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
           typename Q::Rows rows[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
+          for (int u = 0; u < U; u++) Q::load_smem_pred(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
 #pragma unroll
           for (int u = 0; u < U; u++)
 #pragma unroll
@@ -1265,7 +1270,7 @@ R"FQSK(FQ_SELT_CLAIMS];
           if (++slot == stages) { slot = 0; round++; }
         } else {   // ragged or empty tile at the end of the source
           typename Q::Rows rows[U];
-          fq_tile_load<Q, U>(p, tile, cthreads, rows);
+          fq_tile_load<Q, U, true>(p, tile, cthreads, rows);
           keep = fq_tile_pred<Q, U>(p, tile, cthreads, rows, err);
         }
         keepbits |= (fq_u64)keep << (t * BITS);
@@ -1311,7 +1316,8 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
     const fq_u64 g0 = c * chunk + threadIdx.x;
     typename Q::Rows rows[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
+    for (int u = 0; u < UNROLL; u++) Q::load()FQSK"
+R"FQSK(rows[u], p, g0 + (fq_u64)u * blockDim.x);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const fq_u64 row0 = (g0 + (fq_u64)u * blockDim.x) * V;
@@ -1320,8 +1326,7 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
       } else {
 #pragma unroll
         for (int v = 0; v < V; v++)
-          if (row0 + v )FQSK"
-R"FQSK(< p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
+          if (row0 + v < p.capacity) Q::emit(rows[u], v, p, row0 + v, err);
       }
     }
   }

@@ -693,7 +693,8 @@ __device__ __forceinline__ void fq_bar_arrive(int id, int count) { asm volatile(
 // fq_tile_load only issues the loads (full tiles vectorised, the ragged last one row by row), fq_tile_pred
 // evaluates the predicate on rows that exist: bit (u * V + v) of the returned mask is set for kept rows.
 // `wthreads` = worker threads of the CTA (the tile geometry ignores the scan warp).
-template <class Q, int U>
+// PRED: only the predicate's columns (pass 1); otherwise every referenced column (pass 2 projects from them).
+template <class Q, int U, bool PRED = false>
 __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 tile, int wthreads, typename Q::Rows (&rows)[U]) {
   constexpr int V = Q::V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -701,7 +702,10 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
   const fq_u64 g0 = tile * tile_groups + (fq_u64)warp * 32 * U + lane;
   if ((tile + 1) * tile_groups * V <= p.n_rows && !p.unaligned) {
 #pragma unroll
-    for (int u = 0; u < U; u++) Q::load(rows[u], p, g0 + 32ull * u);
+    for (int u = 0; u < U; u++) {
+      if constexpr (PRED) Q::load_pred(rows[u], p, g0 + 32ull * u);
+      else Q::load(rows[u], p, g0 + 32ull * u);
+    }
   } else if (tile * tile_groups * V < p.n_rows) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -710,7 +714,8 @@ __device__ __forceinline__ void fq_tile_load(const fq_launch_params &p, fq_u64 t
       for (int v = 0; v < V; v++) {
         if (row0 + v < p.n_rows) {
           typename Q::Rows one;
-          Q::load1(one, p, row0 + v);
+          if constexpr (PRED) Q::load1_pred(one, p, row0 + v);
+          else Q::load1(one, p, row0 + v);
           Q::copy_row(rows[u], v, one);
         }
       }
@@ -1050,10 +1055,10 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
     if (active) {
       typename Q::Rows rows0[U], rows_n[U];
       fq_u32 wsum = 0;
-      fq_tile_load<Q, U>(p, seg * SEG, wthreads, rows0);
+      fq_tile_load<Q, U, true>(p, seg * SEG, wthreads, rows0);
 #pragma unroll
       for (int t = 0; t < SEG; t++) {
-        if (t + 1 < SEG) fq_tile_load<Q, U>(p, seg * SEG + t + 1, wthreads, rows_n);   // next tile's loads in flight
+        if (t + 1 < SEG) fq_tile_load<Q, U, true>(p, seg * SEG + t + 1, wthreads, rows_n);   // next tile's loads in flight
         const fq_u32 keep = fq_tile_pred<Q, U>(p, seg * SEG + t, wthreads, rows0, err);
         keepbits |= (fq_u64)keep << (t * BITS);
         const fq_u32 wcount = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
@@ -1135,7 +1140,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES;   // pass 1 stages the predicate's columns only
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
   const int stages = (int)p.stages;
@@ -1177,7 +1182,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
             if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
             const fq_u32 full = fq_smem_addr(&s_bars[slot]);
             fq_mbar_expect_tx(full, stage_bytes);
-            Q::tma_issue(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
+            Q::tma_issue_pred(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
             if (++slot == stages) { slot = 0; round++; }
           }
         }
@@ -1247,7 +1252,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
           const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
           typename Q::Rows rows[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
+          for (int u = 0; u < U; u++) Q::load_smem_pred(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
 #pragma unroll
           for (int u = 0; u < U; u++)
 #pragma unroll
@@ -1257,7 +1262,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
           if (++slot == stages) { slot = 0; round++; }
         } else {   // ragged or empty tile at the end of the source
           typename Q::Rows rows[U];
-          fq_tile_load<Q, U>(p, tile, cthreads, rows);
+          fq_tile_load<Q, U, true>(p, tile, cthreads, rows);
           keep = fq_tile_pred<Q, U>(p, tile, cthreads, rows, err);
         }
         keepbits |= (fq_u64)keep << (t * BITS);
