@@ -894,6 +894,13 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   } else {
+    // LIMIT without a filter: LimitStream stops pulling once `limit` rows went by (stream_limit.rs:28-31), so the reference
+    // evaluates only the 10 000-row blocks up to the one that completes the limit.  Same here: rows past that block are
+    // neither read nor evaluated (their divide-by-zero errors do not surface in the reference either).
+    if ((flags & FQ_RUN_LIMIT_EARLY_EXIT) && limit >= 0) {
+      const uint64_t blocks = ((uint64_t)limit + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS;
+      p.n_rows = std::min<uint64_t>(p.n_rows, std::max<uint64_t>(blocks, 1) * FQ_REF_BLOCK_ROWS);
+    }
     // FQ_MAP_VARIANT = tma (default: reads staged by bulk copies; needs every referenced column materialised) | ldg
     const std::string variant = getenv("FQ_MAP_VARIANT") ? getenv("FQ_MAP_VARIANT") : FQ_MAP_DEFAULT_VARIANT;
     const bool use_tma = (variant == "tma" && pipe->k_map_tma.valid()) || !pipe->k_map.valid();
@@ -901,7 +908,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no projection kernel was built for this pipe");
     p.stages = pipe->mapt_stages;
     const uint64_t chunk_rows = (uint64_t)(use_tma ? shapes().tma_threads * shapes().tma_unroll : k.threads * shapes().map_unroll) * pipe->gen.vec;
-    const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
+    const uint64_t chunks = (p.n_rows + chunk_rows - 1) / chunk_rows;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }

@@ -235,7 +235,8 @@ fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr,
  * out_cols[i] receives select expression i for the rows that pass the predicate, in row order
  * (arrow filter keeps order, transform_filter.rs:51-54).  At most min(limit, capacity) rows are
  * written (limit < 0 = none; stream_limit.rs:28-48); rows_selected reports every matching row
- * unless FQ_RUN_LIMIT_EARLY_EXIT let the scan stop once `limit` rows were found. */
+ * unless FQ_RUN_LIMIT_EARLY_EXIT let the scan stop once `limit` rows were found (without a predicate:
+ * after the 10 000-row reference block that completes the limit, like LimitStream stops pulling blocks). */
 /* out_valid[i] (FQ_BOOL, one byte per output row) is required for expressions fq_pipe_expr_nullable reports; the
  * array itself may be NULL when no expression is nullable. */
 fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols,

@@ -221,6 +221,30 @@ def test_projection_without_filter_both_variants(ctx, map_variant, n):
         os.environ.pop("FQ_MAP_VARIANT", None)
 
 
+def test_limit_without_filter_stops_after_the_block_that_completes_it(ctx):
+    """stream_limit.rs:28-31: LimitStream ends the pipe, so blocks after the one that completes the limit are never
+    evaluated — a zero divisor in row 10 000 does not surface with LIMIT 5."""
+    n = 50_000
+    x = np.ones(n, dtype=np.uint64)
+    x[10_000:] = 0
+    col = ctx.from_numpy(x)
+    pipe = ctx.pipe(["(/ (u64 10) (col x))"], columns=["x"], dtypes=[cabi.U64])
+    out = ctx.column(cabi.U64, 5)
+    pipe.launch_project(cabi.make_source([col], n), [out], 5, limit=5, early_exit=True)
+    sel, written = pipe.fetch_project()
+    assert written == 5 and sel == 10_000 and out.to_numpy(5).tolist() == [10] * 5
+    # without the early exit every row is counted; projection expressions are still evaluated only for rows that are
+    # written (DESIGN.md, known deviations), so the zero divisors beyond the limit stay silent
+    pipe.launch_project(cabi.make_source([col], n), [out], 5, limit=5, early_exit=False)
+    assert pipe.fetch_project() == (n, 5)
+    # ... and are an error as soon as such a row is written
+    out2 = ctx.column(cabi.U64, n)
+    pipe.launch_project(cabi.make_source([col], n), [out2], n)
+    with pytest.raises(cabi.FuseGpuError) as e:
+        pipe.fetch_project()
+    assert str(e.value) == "Internal Error: Divide by zero error"
+
+
 def test_variants_launch_different_kernels(ctx):
     """The environment switch must really select another kernel (both are precompiled for the README pipe)."""
     pipe = ctx.pipe(PROJ, predicate=README_PRED)
