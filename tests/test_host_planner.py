@@ -175,3 +175,29 @@ def test_derived_table_plans_flatten_like_the_reference(ctx):
     with pytest.raises(h.FuseQueryError) as e:
         h.Planner().build_from_sql(ctx, "select number from (select number from system.numbers_mt(10)) a, system.numbers_mt(5)")
     assert str(e.value) == "Internal Error: Cannot support JOIN clause"
+
+
+def test_planner_survives_token_soup(ctx):
+    """Robustness of the hand-written SQL front end: random token sequences only ever produce a plan or a FuseQueryError
+    (SQLParser / Plan / Internal, error.rs:10-20) — never another exception type, never a crash."""
+    import random
+    toks = ["select", "from", "where", "limit", "group", "by", "as", "and", "or", "not", "explain", "system", ".", "numbers_mt", "number",
+            "(", ")", ",", "*", "+", "-", "/", "%", "=", "<", ">", "<=", ">=", "<>", "!=", "1", "0", "10000", "1.5", "'a'", "sum", "count",
+            "max", "min", "avg", "x", "t", ";", "having", "order", "join", "union", "-1", "1e10", "99999999999999999999", '"q"', "`b`"]
+    rng = random.Random(20201)
+    planned = 0
+    for _ in range(4000):
+        k = rng.randint(1, 14)
+        if rng.random() < 0.5:
+            arg = rng.choice(["10", "0", "", "1,2", "number", "'a'", "-1", "1.5"])
+            q = "select " + " ".join(rng.choice(toks) for _ in range(k)) + f" from system.numbers_mt({arg}) " + \
+                " ".join(rng.choice(toks) for _ in range(rng.randint(0, 6)))
+        else:
+            q = " ".join(rng.choice(toks) for _ in range(k))
+        try:
+            plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, q))
+            h.PipelineBuilder.create(ctx, plan).build()
+            planned += 1
+        except h.FuseQueryError as e:
+            assert str(e).split(":")[0] in ("Internal Error", "SQLParser Error", "Error during plan"), (q, str(e))
+    assert planned > 0
