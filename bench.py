@@ -262,11 +262,38 @@ def run_ours(args):
     state_t = torch.as_tensor(DevPtr(state_ptr, n_slots), device=f"cuda:{local}")
     gathered = torch.zeros((world, n_slots), dtype=torch.int64, device=f"cuda:{local}")
 
+    # ---- merge point (processor_merge.rs:37-66) ----
+    # default for N > 1: fused into the aggregate kernel — its last CTA stores the state straight into every rank's gather
+    # buffer over NVLink peer memory (CUDA IPC), no collective call in the step.  --merge nccl (or an IPC failure) uses an
+    # NCCL all-gather of the same bytes after each launch instead.
+    merge = "single GPU"
+    gather_col, peer_ptrs = None, []
+    if world > 1:
+        merge = f"nccl all_gather of the {state_bytes}-byte state"
+        if args.merge == "peer":
+            try:
+                gather_col = ctx.column(cabi.U64, world * n_slots)
+                torch.as_tensor(DevPtr(gather_col.device_ptr, world * n_slots), device=f"cuda:{local}").zero_()
+                torch.cuda.synchronize()
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.ipc_export(gather_col))
+                peer_ptrs = [gather_col.device_ptr if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
+                ok = torch.ones(1, device=f"cuda:{local}")
+            except Exception as e:  # IPC not permitted in this container / no peer access: keep NCCL
+                sys.stderr.write(f"[bench] rank {rank}: peer-memory merge unavailable ({e}); using NCCL\n")
+                ok = torch.zeros(1, device=f"cuda:{local}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+            if ok.item() == 1:
+                pipe.set_peer_slots([ptr + rank * state_bytes for ptr in peer_ptrs])
+                gathered = torch.as_tensor(DevPtr(gather_col.device_ptr, world * n_slots), device=f"cuda:{local}").view(world, n_slots)
+                merge = f"in-kernel: the aggregate kernel's last CTA stores the {state_bytes}-byte state into every rank's gather buffer over NVLink peer memory"
+    use_nccl = world > 1 and not merge.startswith("in-kernel")
+
     def step():
         pipe.launch_aggregate(src, stream=stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), state_t)  # merge point (processor_merge.rs:37-66)
-        else:
+        if use_nccl:
+            dist.all_gather_into_tensor(gathered.view(-1), state_t)
+        elif world == 1:
             gathered[0].copy_(state_t, non_blocking=True)
 
     def barrier():
@@ -290,9 +317,9 @@ def run_ours(args):
         k_ev[i][0].record()
         pipe.launch_aggregate(src, stream=stream)
         k_ev[i][1].record()
-        if world > 1:
+        if use_nccl:
             dist.all_gather_into_tensor(gathered.view(-1), state_t)
-        else:
+        elif world == 1:
             gathered[0].copy_(state_t, non_blocking=True)
     e1.record()
     barrier()
@@ -399,7 +426,7 @@ def run_ours(args):
                        "partitioning": f"{8 // world if world <= 8 else 1} of the reference's 8 partitions per GPU",
                        "host_affinity": numa,
                        "l2": "inputs (>= 10 GB per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "merge": f"nccl all_gather of the {state_bytes}-byte state" if world > 1 else "single GPU",
+                       "merge": merge,
                        "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
             "hbm_gb_per_s": row_bytes * total * args.steps / secs / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n, generated),
@@ -552,6 +579,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="override the 10^10-row workload (debug)")
     ap.add_argument("--mode", default="materialised", choices=["materialised", "generated"])
+    ap.add_argument("--merge", choices=["peer", "nccl"], default="peer", help="N > 1: how the per-rank states meet")
     ap.add_argument("--e2e-rows", type=int, default=1_000_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 25)
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -68,7 +68,8 @@ class FuseGpuError(Exception):
 EXPORTS = [
     "fq_abi_version", "fq_ctx_create", "fq_ctx_destroy", "fq_last_error", "fq_ctx_launch_count", "fq_ctx_sm_count",
     "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free",
-    "fq_column_upload_bits", "fq_column_download_bits", "fq_column_dtype", "fq_column_len",
+    "fq_column_upload_bits", "fq_column_download_bits",
+    "fq_ipc_export", "fq_ipc_open", "fq_ipc_close", "fq_pipe_set_peer_slots", "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
@@ -100,6 +101,10 @@ def lib():
         "fq_column_set_validity": (i32, [vp, vp, vp]),
         "fq_column_validity": (vp, [vp]),
         "fq_column_free": (None, [vp, vp]),
+        "fq_ipc_export": (i32, [vp, vp, vp]),
+        "fq_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
+        "fq_ipc_close": (i32, [vp, vp]),
+        "fq_pipe_set_peer_slots": (i32, [vp, vp, C.POINTER(vp), i32]),
         "fq_column_upload_bits": (i32, [vp, vp, u64, vp, u64, u64, vp]),
         "fq_column_download_bits": (i32, [vp, vp, u64, vp, u64, vp]),
         "fq_column_dtype": (i32, [vp]),
@@ -254,6 +259,21 @@ class Context:
         self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
         return col
 
+    def ipc_export(self, col: "Column") -> bytes:
+        """64-byte CUDA IPC handle of a column's buffer (to be sent to the peer processes)."""
+        buf = C.create_string_buffer(64)
+        self.check(lib().fq_ipc_export(self._h, col._h, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        """Device address, in this process, of a peer's exported buffer."""
+        out = C.c_void_p()
+        self.check(lib().fq_ipc_open(self._h, C.c_char_p(handle), C.byref(out)))
+        return out.value
+
+    def ipc_close(self, ptr: int) -> None:
+        self.check(lib().fq_ipc_close(self._h, C.c_void_p(ptr)))
+
     def from_bitmap(self, bits, n: int, bit_offset: int = 0, stream: int = 0) -> "Column":
         """Boolean column (values or validity) from an Arrow LSB-first bitmap (bytes / numpy uint8), expanded on the device."""
         import numpy as np
@@ -405,6 +425,11 @@ class Pipe:
     @property
     def source(self) -> str:
         return lib().fq_pipe_source(self._h).decode()
+
+    def set_peer_slots(self, slots: Sequence[int]) -> None:
+        """Aggregate launches end by storing the running state to these device addresses (peer GPUs' gather rows)."""
+        arr = (C.c_void_p * max(1, len(slots)))(*[C.c_void_p(x) for x in slots])
+        self.ctx.check(lib().fq_pipe_set_peer_slots(self.ctx._h, self._h, arr, len(slots)))
 
     def expr_nullable(self, i: int) -> bool:
         out = C.c_int32()

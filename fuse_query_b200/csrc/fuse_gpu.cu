@@ -211,6 +211,8 @@ struct fq_pipe {
   Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
+  void *peer_slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0;
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
   uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
@@ -768,6 +770,8 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   p.ticket = (fq_u32 *)(pipe->d_ctl + 4);
   p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
   p.stages = pipe->tma_stages;
+  p.n_peers = (fq_u32)pipe->n_peers;
+  for (int r = 0; r < pipe->n_peers; r++) p.peer_slots[r] = (fq_u64 *)pipe->peer_slots[r];
   if ((flags & FQ_RUN_BLOCK_STATS) && pipe->gen.track_blocks && src->n_rows > 0) {
     const uint64_t words = ((src->n_rows + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS + 31) / 32;
     if (words > pipe->blocks_cap) {
@@ -829,6 +833,38 @@ fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks
   if (pipe->launched) CUDA_TRY(cudaEventSynchronize(pipe->ev));
   if (blocks) *blocks = pipe->launched ? pipe->h_state[4] : 0;
   if (empty_blocks) *empty_blocks = pipe->launched ? pipe->h_state[5] : 0;
+  return FQ_OK;
+}
+
+// ---- merge point over peer memory ----
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 opaque bytes");
+fq_status fq_ipc_export(fq_ctx *ctx, const fq_column *col, void *handle64) {
+  if (fq_status st = use(ctx)) return st;
+  if (!col || !handle64) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, col->ptr));
+  memcpy(handle64, &h, sizeof h);
+  return FQ_OK;
+}
+fq_status fq_ipc_open(fq_ctx *ctx, const void *handle64, void **dev_ptr) {
+  if (fq_status st = use(ctx)) return st;
+  if (!handle64 || !dev_ptr) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FQ_OK;
+}
+fq_status fq_ipc_close(fq_ctx *ctx, void *dev_ptr) {
+  if (fq_status st = use(ctx)) return st;
+  if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return FQ_OK;
+}
+fq_status fq_pipe_set_peer_slots(fq_ctx *ctx, fq_pipe *pipe, void *const *slots, int32_t n) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  if (n < 0 || n > 8 || (n > 0 && !slots)) return set_err(FQ_ERR_INVALID, "Internal Error: at most 8 peer slots");
+  for (int r = 0; r < 8; r++) pipe->peer_slots[r] = r < n ? slots[r] : nullptr;
+  pipe->n_peers = n;
   return FQ_OK;
 }
 

@@ -79,6 +79,10 @@ struct fq_launch_params {
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
+  // multi-GPU merge fused into the aggregate kernel: after the fold the last CTA also stores the running state into
+  // these remote slots (peer GPUs' memory over NVLink, or this GPU's own gather row); n_peers = 0: off
+  fq_u64 *peer_slots[8];
+  fq_u32 n_peers;
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -146,7 +150,8 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   } else if constexpr (BYTES == 4) {
     union { fq_u32 q; T t[V]; } u;
     u.q = __ldg((const fq_u32 *)p);
-#pragma unroll
+#pragma )FQSK"
+R"FQSK(unroll
     for (int k = 0; k < V; k++) dst[k] = u.t[k];
   } else {
 #pragma unroll
@@ -155,8 +160,7 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
 }
 
 // Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
-// `bas)FQSK"
-R"FQSK(e + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
+// `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
 template <class T, int V>
 __device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (&src)[V]) {
   constexpr int BYTES = V * (int)sizeof(T);
@@ -298,11 +302,11 @@ template <class T> __device__ __forceinline__ T fq_shfl_xor(T x, int m) {
   else return (T)__shfl_xor_sync(0xffffffffu, (fq_i32)x, m);
 }
 
-// ---------------------------------------------------------------------------------------------
+// --------------------------------------------)FQSK"
+R"FQSK(-------------------------------------------------
 // block-level reduction of a generated accumulator:  registers -> warp shuffles -> shared -> warp 0
 // result valid in thread 0
-// ----------------------------------------------------------------------------------)FQSK"
-R"FQSK(-----------
+// ---------------------------------------------------------------------------------------------
 template <class Q>
 __device__ __forceinline__ void fq_block_reduce(typename Q::Acc &acc, fq_u64 &nsel, fq_u32 &err,
                                                 fq_u64 (*sm)[FQ_STATE_HDR + Q::NSLOTS]) {
@@ -450,6 +454,17 @@ __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typenam
     p.state[5] = empty_blocks;
     Q::store(acc, p.state + FQ_STATE_HDR);
     *p.ticket = 0;
+    // the exchange step of the merge (processor_merge.rs:37-66), fused: S 8-byte stores per peer straight into the
+    // peers' gather buffers.  No wait on the device: readers synchronise with the launch (stream + cross-rank barrier).
+    if (p.n_peers) {
+      for (fq_u32 r = 0; r < p.n_peers; r++) {
+        fq_u64 *dst = p.peer_slots[r];
+        if (!dst) continue;
+#pragma unroll 1
+        for (int k = 0; k < S; k++) dst[k] = p.state[k];
+      }
+      __threadfence_system();
+    }
   }
 }
 
@@ -481,7 +496,8 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
     const fq_u64 g0 = c * chunk + threadIdx.x;
     typename Q::Rows rows[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
+    for (int u = 0; u < UNROLL; u)FQSK"
+R"FQSK(++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       fq_u32 kept = 0;
@@ -499,8 +515,7 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
     typename Q::Rows r;
     Q::load(r, p, g);
     fq_u32 kept = 0;
-#prag)FQSK"
-R"FQSK(ma unroll
+#pragma unroll
     for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
     if constexpr (Q::TRACK_BLOCKS) {
       if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
@@ -648,7 +663,8 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
         if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
       }
     }
-    for (fq_u64 row = nvec * V + ctid; row < p.n_rows; row += cn) {
+    for (fq_u64 row = nvec * V + ctid; row <)FQSK"
+R"FQSK( p.n_rows; row += cn) {
       typename Q::Rows r;
       Q::load1(r, p, row);
       const bool kept = Q::consume(acc, r, 0, nsel, err);
@@ -665,8 +681,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
 //
 // CTA = W worker warps + 1 scan warp (warp-specialised).  Work unit = SEGMENT of SEG consecutive tiles
 // (tile = 32 * W * U vector groups; worker warp w owns the contiguous run of 32 * U groups at
-// tile_base + w)FQSK"
-R"FQSK( * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are claimed dynamically
+// tile_base + w * 32 * U, so row order inside a tile is (warp, u, lane, v)).  Segments are claimed dynamically
 // (atomicAdd) by the CTAs of a persistent grid.
 //   workers, pass 1   stream the segment once from HBM, evaluate the predicate in registers, keep ONE BIT per
 //                     row (U * V * SEG <= 64 bits per thread) and per-(tile, warp) selected counts in shared memory;
@@ -795,7 +810,8 @@ __device__ __forceinline__ fq_u32 fq_sel_scan_counts(fq_u32 (*cnt)[FQ_MAX_WARPS]
 // prefix for segment 0).  The aggregate therefore becomes visible the moment the segment has been streamed and never
 // queues behind the scan warp, which may still be looking back for the previous segment — with the scan warp
 // publishing it, every look-back waited for the look-backs before it (a convoy: 7-10 us per segment per CTA).
-__device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
+__device__ __forceinline__ void fq_sel_pub)FQSK"
+R"FQSK(lish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
   const unsigned long long old = atomicAdd(acc, (1ull << 32) | (unsigned long long)wsum);
   if ((int)(old >> 32) == nwarps - 1) {
     const fq_u64 tot = (fq_u64)((fq_u32)old + wsum);
@@ -807,8 +823,7 @@ __device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq
 // scan warp, step 2: resolve the segment's exclusive global base by a look-back over the 64-bit descriptors
 // {flag:2, count:62} of its predecessors, publish the inclusive prefix.
 //
-// A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  S)FQSK"
-R"FQSK(o when it
+// A CTA claims segments in increasing order, and its scan warp resolves them one after the other.  So when it
 // looks back from segment `seg` it already knows the inclusive prefix `prev_incl` of the segment `prev_seg` it
 // resolved before: the walk only has to add the AGGREGATES of the segments in between (about one per resident CTA)
 // and never has to wait for anybody's PREFIX.  That matters: a classic decoupled look-back ends at the nearest
@@ -965,15 +980,15 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
 template <class Q, int U, int SEG>
 __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
-  constexpr int BITS = U * V;                 // predicate bits per thread per tile
+ )FQSK"
+R"FQSK( constexpr int BITS = U * V;                 // predicate bits per thread per tile
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
   __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
   __shared__ fq_u64 s_excl[FQ_SEL_RING];                    // global base of the segment in each ring slot
   __shared__ unsigned long long s_acc[FQ_SEL_RING];         // {arrived worker warps, selected rows} of the segment being streamed
   __shared__ volatile fq_u64 s_seg[4];           // claimed segment ids: ring of 4 (the scan warp lags the workers by up to 2)
   __shared__ volatile fq_u32 s_stop[4];
-  __shared__ volatile int s_)FQSK"
-R"FQSK(ready[4];
+  __shared__ volatile int s_ready[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wthreads = (int)blockDim.x - 32, nwarps = wthreads >> 5, allthreads = (int)blockDim.x;
   const bool is_scan = (int)threadIdx.x >= wthreads;
@@ -1119,7 +1134,8 @@ R"FQSK(ready[4];
 // ---------------------------------------------------------------------------------------------
 template <int V> struct fq_selt_shape {
   static constexpr int U = (FQ_SELT_UNROLL * V <= 32) ? FQ_SELT_UNROLL : (32 / V);
-  static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT_SEG : (64 / (U * V));
+  static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT)FQSK"
+R"FQSK(_SEG : (64 / (U * V));
 };
 #define FQ_SELT_CLAIMS 16   // claim ring: the producer runs at most stages/SEG + 1 segments ahead of pass 1, the scan warp 2 behind
 
@@ -1131,8 +1147,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   constexpr int LAG = FQ_SELT_LAG;            // pass 2 runs this many segments behind pass 1 (absorbs the skew between CTAs)
   constexpr int R = LAG + 1;                  // ring of count / base slots and of FULL / DONE named barriers
   constexpr int BAR_FULL = 2, BAR_DONE = 2 + R;
-  static_assert(2 + 2 * R <= )FQSK"
-R"FQSK(16, "named barriers");
+  static_assert(2 + 2 * R <= 16, "named barriers");
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
   __shared__ fq_u32 s_cnt[R][SEG][FQ_MAX_WARPS];
   __shared__ fq_u64 s_excl[R];
@@ -1302,7 +1317,8 @@ R"FQSK(16, "named barriers");
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
 
-// ---------------------------------------------------------------------------------------------
+// ---------------)FQSK"
+R"FQSK(------------------------------------------------------------------------------
 // fq_map_kernel — projection of every row (no predicate): out_i[row] = expr_i(row)
 // ---------------------------------------------------------------------------------------------
 template <class Q, int UNROLL>
@@ -1316,8 +1332,7 @@ __device__ __forceinline__ void fq_map_kernel(const fq_launch_params &p) {
     const fq_u64 g0 = c * chunk + threadIdx.x;
     typename Q::Rows rows[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) Q::load()FQSK"
-R"FQSK(rows[u], p, g0 + (fq_u64)u * blockDim.x);
+    for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const fq_u64 row0 = (g0 + (fq_u64)u * blockDim.x) * V;

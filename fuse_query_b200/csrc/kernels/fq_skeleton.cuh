@@ -78,6 +78,10 @@ struct fq_launch_params {
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
+  // multi-GPU merge fused into the aggregate kernel: after the fold the last CTA also stores the running state into
+  // these remote slots (peer GPUs' memory over NVLink, or this GPU's own gather row); n_peers = 0: off
+  fq_u64 *peer_slots[8];
+  fq_u32 n_peers;
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -447,6 +451,17 @@ __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typenam
     p.state[5] = empty_blocks;
     Q::store(acc, p.state + FQ_STATE_HDR);
     *p.ticket = 0;
+    // the exchange step of the merge (processor_merge.rs:37-66), fused: S 8-byte stores per peer straight into the
+    // peers' gather buffers.  No wait on the device: readers synchronise with the launch (stream + cross-rank barrier).
+    if (p.n_peers) {
+      for (fq_u32 r = 0; r < p.n_peers; r++) {
+        fq_u64 *dst = p.peer_slots[r];
+        if (!dst) continue;
+#pragma unroll 1
+        for (int k = 0; k < S; k++) dst[k] = p.state[k];
+      }
+      __threadfence_system();
+    }
   }
 }
 

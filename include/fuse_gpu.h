@@ -231,6 +231,19 @@ fq_status fq_pipe_aggregator_nodes(fq_ctx *ctx, const fq_pipe *pipe, int32_t *no
 #define FQ_STATE_HEADER_SLOTS 6
 fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes);
 
+/* ---- multi-GPU merge point (processors/processor_merge.rs:37-66) without a collective call ----
+ * One process per GPU.  Every rank owns a gather buffer (a UInt64 column of world * state_slots rows), exports it with
+ * fq_ipc_export (64-byte CUDA IPC handle, exchanged by the host however it likes) and opens its peers' buffers with
+ * fq_ipc_open.  fq_pipe_set_peer_slots(pipe, slots, n) then makes every aggregate launch of `pipe` finish by storing
+ * its running state (the bytes fq_pipe_state_device describes) to slots[r] for r < n (<= 8): the address, in GPU r's
+ * memory, of this rank's row of r's gather buffer (slots[own rank] may point into the local buffer).  The stores ride
+ * NVLink from the kernel's last CTA; nothing waits on the device.  A reader of a gather buffer must first order itself
+ * after the launches of all ranks (stream synchronisation + a cross-rank barrier).  n = 0 switches it off. */
+fq_status fq_ipc_export(fq_ctx *ctx, const fq_column *col, void *handle64);
+fq_status fq_ipc_open(fq_ctx *ctx, const void *handle64, void **dev_ptr);
+fq_status fq_ipc_close(fq_ctx *ctx, void *dev_ptr);
+fq_status fq_pipe_set_peer_slots(fq_ctx *ctx, fq_pipe *pipe, void *const *slots, int32_t n);
+
 /* ---- projection pipes: filter_record_batch + projection (+ LimitStream) in one pass ----
  * out_cols[i] receives select expression i for the rows that pass the predicate, in row order
  * (arrow filter keeps order, transform_filter.rs:51-54).  At most min(limit, capacity) rows are

@@ -4,6 +4,8 @@ Bit-exact for every integer / index result.  Floating-point sums are compared wi
 tolerance (the reduction order differs from the reference's sequential fold); float min/max and
 element-wise float arithmetic are exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -486,3 +488,35 @@ def test_context_is_usable_from_many_host_threads(ctx):
         assert vals == [int((x + np.uint64(t)).sum(dtype=np.uint64)), int(x.max()), int((x * np.uint64(t + 1)).min()), m]
         want = x[x % 1000 == 0] + np.uint64(t)
         assert k == len(want) and np.array_equal(got, want)
+
+
+def test_aggregate_kernel_publishes_its_state_to_peer_slots(ctx):
+    """fq_pipe_set_peer_slots: the launch ends by storing the running state (header + leaves) into every slot it was
+    given — the multi-GPU merge point without a collective call.  Here the "peers" are rows of a local gather buffer."""
+    n = 5_000_003
+    col = ctx.numbers(7, n)
+    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True)
+    ptr, nbytes = pipe.state_device()
+    slots = nbytes // 8
+    gather = ctx.from_numpy(np.zeros(3 * slots, dtype=np.uint64))
+    pipe.set_peer_slots([gather.device_ptr + r * nbytes for r in (0, 2)])       # rows 0 and 2; row 1 stays untouched
+    for variant in ("tma", "u4"):
+        os.environ["FQ_AGG_VARIANT"] = variant
+        try:
+            pipe.launch_aggregate(cabi.make_source([col], n))
+            states, rows = pipe.fetch_aggregate()
+        finally:
+            os.environ.pop("FQ_AGG_VARIANT", None)
+        g = gather.to_numpy().reshape(3, slots)
+        x = np.arange(7, 7 + n, dtype=np.uint64)
+        want_leaves = [int(x.sum(dtype=np.uint64)), n, int(x.max()), int(x.min())]
+        assert [s[1] for s in states] == want_leaves and rows == n
+        for r in (0, 2):
+            H = cabi.STATE_HEADER_SLOTS   # raw slots: Count(number) reads nothing, its value is the header's row count
+            assert g[r, 0] == n and g[r, 1] == 0 and g[r, 3] == n
+            assert [int(g[r, H]), int(g[r, H + 2]), int(g[r, H + 3])] == [want_leaves[0], want_leaves[2], want_leaves[3]]
+        assert not g[1].any()
+    pipe.set_peer_slots([])
+    pipe.launch_aggregate(cabi.make_source([col], 1000))
+    pipe.fetch_aggregate()
+    assert gather.to_numpy().reshape(3, slots)[0, 0] == n      # switched off: the slot keeps the previous launch
