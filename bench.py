@@ -452,6 +452,13 @@ def run_ours(args):
                                                               "compare with per_query[...]['generated'], not with the materialised scan"}
         print(json.dumps(out), flush=True)
     if world > 1:
+        if peer_ptrs:   # nobody may unmap a gather buffer while a peer could still store into it
+            pipe.set_peer_slots([])
+            barrier()
+            for r, ptr in enumerate(peer_ptrs):
+                if r != rank:
+                    ctx.ipc_close(ptr)
+            barrier()
         dist.destroy_process_group()
 
 
