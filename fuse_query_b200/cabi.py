@@ -71,7 +71,7 @@ EXPORTS = [
     "fq_column_upload_bits", "fq_column_download_bits",
     "fq_ipc_export", "fq_ipc_open", "fq_ipc_close", "fq_pipe_set_peer_slots", "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
-    "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_source",
+    "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_build_kind", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project",
 ]
@@ -119,6 +119,7 @@ def lib():
         "fq_pipe_compile": (i32, [vp, C.POINTER(PipeDesc), C.POINTER(vp)]),
         "fq_pipe_destroy": (None, [vp, vp]),
         "fq_pipe_is_precompiled": (i32, [vp]),
+        "fq_pipe_build_kind": (i32, [vp]),
         "fq_pipe_source": (C.c_char_p, [vp]),
         "fq_pipe_expr_dtype": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "fq_pipe_expr_nullable": (i32, [vp, vp, i32, C.POINTER(i32)]),
@@ -421,6 +422,11 @@ class Pipe:
     @property
     def precompiled(self) -> bool:
         return bool(lib().fq_pipe_is_precompiled(self._h))
+
+    @property
+    def build_kind(self) -> int:
+        """0 = precompiled table, 1 = NVRTC in this process, 2 = on-disk JIT cache."""
+        return lib().fq_pipe_build_kind(self._h)
 
     @property
     def source(self) -> str:

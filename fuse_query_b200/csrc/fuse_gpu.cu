@@ -6,9 +6,12 @@
 // machine without a GPU; every data-path entry point then fails loudly with FQ_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cinttypes>
 #include <cstdarg>
 #include <cstdio>
@@ -183,6 +186,7 @@ struct Kernel {
 struct Module {  // one compiled specialisation, shared by every pipe with the same tag
   std::map<std::string, Kernel> kernels;
   std::vector<std::string> built;   // JIT: suffixes of the kernel variants in the module
+  bool from_disk_cache = false;     // JIT: the cubin came from the on-disk cache instead of NVRTC
   bool precompiled = false;
   CUmodule_ mod = nullptr;
 };
@@ -211,6 +215,7 @@ struct fq_pipe {
   Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
+  int build_kind = 0;   // 0 precompiled, 1 NVRTC in this process, 2 on-disk JIT cache
   void *peer_slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_peers = 0;
   bool precompiled = false;
@@ -266,6 +271,62 @@ __global__ void __launch_bounds__(256) fq_fill_numbers(fq_u64 *dst, fq_u64 begin
   }
 }
 
+// ---- on-disk cache of JIT-built cubins ----
+// NVRTC + ptxas cost about a second per kernel; the cubin of a specialisation is a pure function of the program text, so
+// it is kept under $FQ_JIT_CACHE_DIR (default: .jit_cache next to libfuse_gpu.so) as <hash of the text>.cubin,
+// written to a temporary name and renamed (ranks and threads may race for the same entry).  FQ_JIT_CACHE=0 disables it.
+static uint64_t fnv1a64(const std::string &s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+static std::string jit_cache_dir() {
+  const char *off = getenv("FQ_JIT_CACHE");
+  if (off && atoi(off) == 0) return "";
+  std::string dir;
+  if (const char *d = getenv("FQ_JIT_CACHE_DIR")) {
+    dir = d;
+  } else {   // next to the library itself: <dir of libfuse_gpu.so>/.jit_cache
+    Dl_info info;
+    if (dladdr((const void *)&jit_cache_dir, &info) && info.dli_fname) {
+      dir = info.dli_fname;
+      const size_t slash = dir.rfind('/');
+      dir = (slash == std::string::npos ? std::string(".") : dir.substr(0, slash)) + "/.jit_cache";
+    }
+  }
+  if (dir.empty()) return "";
+  std::string cur;
+  for (size_t i = 0; i <= dir.size(); i++) {   // mkdir -p
+    if (i == dir.size() || dir[i] == '/') {
+      if (!cur.empty() && mkdir(cur.c_str(), 0755) != 0 && errno != EEXIST) return "";
+    }
+    if (i < dir.size()) cur += dir[i];
+  }
+  return dir;
+}
+static bool jit_cache_read(const std::string &path, std::vector<char> *out) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) {
+    out->resize((size_t)n);
+    ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n;
+  }
+  fclose(f);
+  return ok;
+}
+static void jit_cache_write(const std::string &path, const std::vector<char> &data) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid()) + "_" + std::to_string((unsigned long)(uintptr_t)&data);
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 // `suffixes`: the kernel variants to build (empty = all of them)
 fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const std::vector<std::string> &suffixes) {
   if (!g_nvrtc.load()) return set_err(FQ_ERR_CUDA, "NVRTC unavailable: %s", g_nvrtc.why.c_str());
@@ -273,6 +334,16 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const st
   std::string src = shapes().defines() + std::string(fq_skeleton_src) + "\n" + gen.struct_source;
   for (auto &k : gen.kernels)
     if (suffixes.empty() || std::find(suffixes.begin(), suffixes.end(), k.first) != suffixes.end()) src += k.second;
+  const std::string cache_dir = jit_cache_dir();
+  char key[40];
+  snprintf(key, sizeof key, "%016" PRIx64 "%08x", fnv1a64(src), (unsigned)src.size());
+  const std::string cache_path = cache_dir.empty() ? "" : cache_dir + "/" + key + ".sm_100a.cubin";
+  std::vector<char> cached;
+  if (!cache_path.empty() && jit_cache_read(cache_path, &cached)) {
+    cudaFree(nullptr);
+    if (g_drv.cuModuleLoadData(&m->mod, cached.data()) == 0) { m->from_disk_cache = true; return FQ_OK; }
+    remove(cache_path.c_str());   // unreadable entry (another driver / truncated): rebuild it
+  }
   nvrtcProgram_ prog = nullptr;
   int r = g_nvrtc.nvrtcCreateProgram(&prog, src.c_str(), ("fq_" + gen.tag + ".cu").c_str(), 0, nullptr, nullptr);
   if (r) return set_err(FQ_ERR_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.nvrtcGetErrorString(r));
@@ -291,6 +362,7 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const st
   std::vector<char> cubin(n);
   g_nvrtc.nvrtcGetCUBIN(prog, cubin.data());
   g_nvrtc.nvrtcDestroyProgram(&prog);
+  if (!cache_path.empty()) jit_cache_write(cache_path, cubin);
   cudaFree(nullptr);  // make sure the primary context exists and is current
   CUresult_ cr = g_drv.cuModuleLoadData(&m->mod, cubin.data());
   if (cr) return set_err(FQ_ERR_CUDA, "cuModuleLoadData: %s", g_drv.err(cr).c_str());
@@ -634,6 +706,7 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     }
     m = &it->second;
     pipe->precompiled = m->precompiled;
+    pipe->build_kind = m->precompiled ? 0 : m->from_disk_cache ? 2 : 1;
     fq_status s2 = FQ_OK;
     const std::string base = "fqk_" + gen.tag;
     if (gen.kind == FQ_PIPE_AGGREGATE) {
@@ -710,6 +783,7 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
 }
 
 int32_t fq_pipe_is_precompiled(const fq_pipe *pipe) { return pipe && pipe->precompiled; }
+int32_t fq_pipe_build_kind(const fq_pipe *pipe) { return pipe ? pipe->build_kind : 0; }
 const char *fq_pipe_source(const fq_pipe *pipe) { return pipe ? pipe->gen.source.c_str() : ""; }
 
 fq_status fq_pipe_expr_dtype(fq_ctx *, const fq_pipe *pipe, int32_t i, fq_dtype *out) {

@@ -196,6 +196,10 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out);
 void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe);
 /* 1 if the kernel came from the library's precompiled table, 0 if NVRTC built it */
 int32_t fq_pipe_is_precompiled(const fq_pipe *pipe);
+/* where the pipe's kernels came from: 0 = the library's precompiled table, 1 = built by NVRTC in this process,
+ * 2 = a cubin from the on-disk JIT cache ($FQ_JIT_CACHE_DIR, default .jit_cache next to the library; FQ_JIT_CACHE=0
+ * disables it) */
+int32_t fq_pipe_build_kind(const fq_pipe *pipe);
 /* generated CUDA source of the specialised part (diagnostics / DESIGN.md) */
 const char *fq_pipe_source(const fq_pipe *pipe);
 /* Function::return_type of select expression i over the pipe's schema (functions/function.rs:28-38) */

@@ -520,3 +520,38 @@ def test_aggregate_kernel_publishes_its_state_to_peer_slots(ctx):
     pipe.launch_aggregate(cabi.make_source([col], 1000))
     pipe.fetch_aggregate()
     assert gather.to_numpy().reshape(3, slots)[0, 0] == n      # switched off: the slot keeps the previous launch
+
+
+def test_jit_cubins_are_cached_on_disk(tmp_path):
+    """A specialisation outside the precompiled table is built by NVRTC once and then loaded from
+    $FQ_JIT_CACHE_DIR by every later context / process; FQ_JIT_CACHE=0 switches the cache off.  Same results either way."""
+    exprs = [f"(sum (* {NUM} (u64 31337)))", f"(max (+ {NUM} (u64 424242)))"]      # not in aot_pipes.txt
+    n = 1_000_003
+    x = np.arange(n, dtype=np.uint64)
+    want = [int((x * np.uint64(31337)).sum(dtype=np.uint64)), int(x.max()) + 424242]
+    old = {k: os.environ.get(k) for k in ("FQ_JIT_CACHE_DIR", "FQ_JIT_CACHE")}
+    os.environ["FQ_JIT_CACHE_DIR"] = str(tmp_path / "jit")
+    os.environ.pop("FQ_JIT_CACHE", None)
+    try:
+        kinds = []
+        for _ in range(2):                      # a context caches modules in memory, so use a fresh one each time
+            c = cabi.Context(0)
+            pipe = c.pipe(exprs, aggregate=True, generated=True)
+            pipe.launch_aggregate(cabi.make_source([], n, generated=True))
+            states, rows = pipe.fetch_aggregate()
+            assert [s[1] for s in states] == want and rows == n
+            kinds.append(pipe.build_kind)
+            c.close()
+        assert kinds == [1, 2]
+        assert len(list((tmp_path / "jit").glob("*.cubin"))) == 1
+        os.environ["FQ_JIT_CACHE"] = "0"
+        c = cabi.Context(0)
+        assert c.pipe(exprs, aggregate=True, generated=True).build_kind == 1
+        assert c.pipe(README_AGGS["headline"], aggregate=True).build_kind == 0
+        c.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
