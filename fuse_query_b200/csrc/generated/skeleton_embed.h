@@ -378,6 +378,17 @@ template <int V> __device__ __forceinline__ void fq_mark_blocks_warp(const fq_la
   }
 }
 
+// Out of line on purpose: inlined, the (cold) peer stores changed the register allocation and unrolling of the hot
+// loops of the ALU-bound generated-source kernels (sum(number) over 1e10 generated rows: 1.15 -> 1.70 ms).
+static __device__ __noinline__ void fq_publish_state(const fq_launch_params &p, int n_slots) {
+  for (fq_u32 r = 0; r < p.n_peers; r++) {
+    fq_u64 *dst = p.peer_slots[r];
+    if (!dst) continue;
+    for (int k = 0; k < n_slots; k++) dst[k] = p.state[k];
+  }
+  __threadfence_system();
+}
+
 // CTA partial -> global partial row -> last CTA (ticket) folds every partial into (or restarts) the running state
 template <class Q>
 __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typename Q::Acc &acc, fq_u64 &nsel, fq_u32 &err,
@@ -456,15 +467,7 @@ __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typenam
     *p.ticket = 0;
     // the exchange step of the merge (processor_merge.rs:37-66), fused: S 8-byte stores per peer straight into the
     // peers' gather buffers.  No wait on the device: readers synchronise with the launch (stream + cross-rank barrier).
-    if (p.n_peers) {
-      for (fq_u32 r = 0; r < p.n_peers; r++) {
-        fq_u64 *dst = p.peer_slots[r];
-        if (!dst) continue;
-#pragma unroll 1
-        for (int k = 0; k < S; k++) dst[k] = p.state[k];
-      }
-      __threadfence_system();
-    }
+    if (p.n_peers) fq_publish_state(p, S);
   }
 }
 
@@ -489,15 +492,15 @@ __device__ __forceinline__ void fq_agg_kernel(const fq_launch_params &p) {
   fq_u32 err = 0;
   fq_u64 nsel = 0;
 
-  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;   // unaligned slices: everything through the row-by-row tail
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;   // unaligned slices: everything thr)FQSK"
+R"FQSK(ough the row-by-row tail
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
   for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {
     const fq_u64 g0 = c * chunk + threadIdx.x;
     typename Q::Rows rows[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; u)FQSK"
-R"FQSK(++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
+    for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       fq_u32 kept = 0;
@@ -655,7 +658,8 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
     const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
     for (fq_u64 g = n_tiles * tile_groups + ctid; g < nvec; g += cn) {
       typename Q::Rows r;
-      Q::load(r, p, g);
+      Q::load()FQSK"
+R"FQSK(r, p, g);
       fq_u32 kept = 0;
 #pragma unroll
       for (int v = 0; v < V; v++) kept |= (Q::consume(acc, r, v, nsel, err) ? 1u : 0u) << v;
@@ -663,8 +667,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
         if (p.block_hit) fq_mark_blocks_lane<V>(p, g * V, kept);
       }
     }
-    for (fq_u64 row = nvec * V + ctid; row <)FQSK"
-R"FQSK( p.n_rows; row += cn) {
+    for (fq_u64 row = nvec * V + ctid; row < p.n_rows; row += cn) {
       typename Q::Rows r;
       Q::load1(r, p, row);
       const bool kept = Q::consume(acc, r, 0, nsel, err);
@@ -807,11 +810,11 @@ __device__ __forceinline__ fq_u32 fq_sel_scan_counts(fq_u32 (*cnt)[FQ_MAX_WARPS]
 
 // Workers, end of pass 1: lane 0 of every worker warp adds the warp's selected count of the segment to a packed
 // shared-memory word {arrivals:32, count:32}; the last warp to arrive publishes the segment's descriptor (aggregate;
-// prefix for segment 0).  The aggregate therefore becomes visible the moment the segment has been streamed and never
+// prefix for segment 0).  The aggregate therefore becomes visible the moment )FQSK"
+R"FQSK(the segment has been streamed and never
 // queues behind the scan warp, which may still be looking back for the previous segment — with the scan warp
 // publishing it, every look-back waited for the look-backs before it (a convoy: 7-10 us per segment per CTA).
-__device__ __forceinline__ void fq_sel_pub)FQSK"
-R"FQSK(lish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
+__device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
   const unsigned long long old = atomicAdd(acc, (1ull << 32) | (unsigned long long)wsum);
   if ((int)(old >> 32) == nwarps - 1) {
     const fq_u64 tot = (fq_u64)((fq_u32)old + wsum);
@@ -966,7 +969,8 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
 #pragma unroll
         for (int v = 0; v < V; v++) {
           if ((ku >> v) & 1u) {
-            if (pos < p.capacity) Q::emit(r, v, p, pos, err);
+          )FQSK"
+R"FQSK(  if (pos < p.capacity) Q::emit(r, v, p, pos, err);
             pos++;
           }
         }
@@ -980,8 +984,7 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
 template <class Q, int U, int SEG>
 __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
- )FQSK"
-R"FQSK( constexpr int BITS = U * V;                 // predicate bits per thread per tile
+  constexpr int BITS = U * V;                 // predicate bits per thread per tile
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
   __shared__ fq_u32 s_cnt[FQ_SEL_RING][SEG][FQ_MAX_WARPS];  // per (tile, worker warp): selected count, then exclusive offset in the segment
   __shared__ fq_u64 s_excl[FQ_SEL_RING];                    // global base of the segment in each ring slot
@@ -1130,12 +1133,12 @@ R"FQSK( constexpr int BITS = U * V;                 // predicate bits per thread
 // bit per row and per-(tile, warp) counts, and release the slot (one arrive per warp on empty[s]).  Scan warp,
 // look-back, named-barrier ring FULL/DONE and pass 2 (re-read of kept tiles from L2) are those of fq_select_kernel.
 // Tiles that are not entirely inside the source (the ragged end) are never staged: consumers load them with
-// fq_tile_load.  Producer and consumers count staged tiles with the same rule, so their slot/parity stay in step.
+// fq_tile_load.  Producer and consumers count staged tiles with the same rule, so their slot/pari)FQSK"
+R"FQSK(ty stay in step.
 // ---------------------------------------------------------------------------------------------
 template <int V> struct fq_selt_shape {
   static constexpr int U = (FQ_SELT_UNROLL * V <= 32) ? FQ_SELT_UNROLL : (32 / V);
-  static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT)FQSK"
-R"FQSK(_SEG : (64 / (U * V));
+  static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT_SEG : (64 / (U * V));
 };
 #define FQ_SELT_CLAIMS 16   // claim ring: the producer runs at most stages/SEG + 1 segments ahead of pass 1, the scan warp 2 behind
 
@@ -1305,7 +1308,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     if (!active) {          // drain, oldest first: entry j is the segment of iteration k - 1 - j
 #pragma unroll
       for (int j = LAG - 2; j >= 0; j--)
-        if (j < pending) scatter(segq[j], keepq[j], (k - 1 - j) % R);
+        if (j < pending) scatt)FQSK"
+R"FQSK(er(segq[j], keepq[j], (k - 1 - j) % R);
       break;
     }
 #pragma unroll
@@ -1317,8 +1321,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
 
-// ---------------)FQSK"
-R"FQSK(------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
 // fq_map_kernel — projection of every row (no predicate): out_i[row] = expr_i(row)
 // ---------------------------------------------------------------------------------------------
 template <class Q, int UNROLL>
