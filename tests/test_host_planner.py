@@ -201,3 +201,23 @@ def test_planner_survives_token_soup(ctx):
         except h.FuseQueryError as e:
             assert str(e).split(":")[0] in ("Internal Error", "SQLParser Error", "Error during plan"), (q, str(e))
     assert planned > 0
+
+
+def test_arrow_columns_hand_over_their_own_null_bitmap():
+    """tables._arrow_column: values with NULL slots zero-filled, validity as arrow's LSB-first bitmap + bit offset
+    (expanded on the device by fq_column_upload_bits); no validity at all for a column without NULLs."""
+    import numpy as np
+    import pyarrow as pa
+    from fuse_query_b200.tables import _arrow_column
+    vals, valid = _arrow_column(pa.array([1, 2, 3], type=pa.int32()))
+    assert valid is None and vals.dtype == np.int32 and vals.tolist() == [1, 2, 3]
+    arr = pa.array([5, None, 7, None, None, 11, 13, None, 17, 19], type=pa.uint64()).slice(3, 6)   # None None 11 13 None 17
+    vals, valid = _arrow_column(arr)
+    assert vals.dtype == np.uint64 and vals.tolist() == [0, 0, 11, 13, 0, 17]
+    kind, buf, off = valid
+    assert kind == "bitmap" and off == arr.offset
+    bits = np.unpackbits(np.frombuffer(buf, dtype=np.uint8), bitorder="little")[off:off + len(arr)]
+    assert bits.tolist() == [0, 0, 1, 1, 0, 1]
+    chunked = pa.chunked_array([pa.array([1.5, None]), pa.array([None, 4.0])])
+    vals, valid = _arrow_column(chunked)
+    assert vals.tolist() == [1.5, 0.0, 0.0, 4.0] and valid[0] == "bitmap"
