@@ -50,3 +50,23 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cc", ".cu", ".cuh", ".h", ".txt")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert not bad.search(text), f"{os.path.join(base, f)} reaches into the oracle"
+
+
+def test_generated_rust_bindings_match_the_header_and_the_exports():
+    """ffi/fuse-gpu-sys/src/lib.rs is generated from include/fuse_gpu.h (tools/gen_rust_bindings.py): it must be current
+    and declare every symbol the library exports — the reference-side binding of INTEGRATION.md, kept from drifting."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_bindings", os.path.join(root, "tools", "gen_rust_bindings.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    current = open(os.path.join(root, "ffi", "fuse-gpu-sys", "src", "lib.rs")).read()
+    assert current == gen.generate(), "run python tools/gen_rust_bindings.py"
+    declared = set(re.findall(r"pub fn (fq_\w+)\(", current))
+    from fuse_query_b200 import cabi
+    assert declared == set(cabi.EXPORTS)
+    # pointer constness follows the header
+    assert "pub fn fq_pipe_launch_project(ctx: *mut fq_ctx, pipe: *mut fq_pipe, src: *const fq_source, out_cols: *const *mut fq_column," in current
+    assert "pub fn fq_last_error(ctx: *const fq_ctx) -> *const c_char;" in current
