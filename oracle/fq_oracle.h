@@ -18,7 +18,9 @@
  * extracted by tests/golden/extract_reference_vectors.py into the tests/golden JSON files and
  * replayed against this oracle by tests/test_oracle_golden.py.  Behaviours no reference
  * test pins (u64 sum wrap at 10^10 rows, the NumbersStream tail quirk, empty-block sum)
- * are listed as "unpinned" in DESIGN.md.
+ * are listed as "unpinned" in DESIGN.md.  NULL propagation and wrapping at every
+ * numeric width, which those vectors do not exercise, are cross-checked against an
+ * independent Arrow implementation (pyarrow.compute) by tests/test_oracle_vs_pyarrow.py.
  */
 #ifndef FQ_ORACLE_H
 #define FQ_ORACLE_H
