@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[3], the README headline query):
     SELECT sum(number)/count(number), max(number), min(number) FROM system.numbers_mt(10_000_000_000)
 One "step" = one pass of the fused Source -> AggregatePartial kernel over every rank's shard of the
 10^10-row UInt64 column (materialised in HBM, 80 GB at N=1) + the merge of the per-rank partial states
-(NCCL all-gather of the 80-byte state per rank when N > 1) — strong scaling: the 10^10 rows are partitioned
+(N > 1: the kernel's last CTA stores the 80-byte state into every rank's gather buffer over NVLink peer memory;
+--merge nccl, or an IPC failure, all-gathers the same bytes with NCCL after each launch) — strong scaling: the 10^10 rows are partitioned
 across ranks exactly like the reference chunks its 8 partitions over workers
 (processors/pipeline_builder.rs:73-95).
 
