@@ -125,3 +125,35 @@ def test_pipeline_known_answers(case):
         assert [o.DTYPE_NAMES[c.dtype] for c in r.columns] == case["expect_dtypes"]
     if "expect_names" in case:
         assert r.names == case["expect_names"]
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties of the oracle itself (so that it can be trusted beyond the golden sizes)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("total", [80_000, 240_000, 1_600_000])
+def test_aggregates_do_not_depend_on_how_partitions_are_chunked(total):
+    """pipeline_builder.rs:75-84 chunks the 8 partitions over `worker_threads` pipes; partial states merge by wrapping add /
+    min / max (function_aggregator.rs:106-139), so every chunking gives the closed form."""
+    exprs = ["(/ (sum (col number)) (count (col number)))", "(max (+ (col number) (u64 1)))", "(min (col number))", "(count (col number))",
+             "(sum (* (col number) (col number)))"]
+    n = total
+    want = ((n * (n - 1) // 2) // n, n, 0, n, sum(i * i for i in range(n)) % (1 << 64))
+    for workers in (0, 1, 2, 3, 4, 8, 16):
+        for threads in (False, True):
+            r = o.run_query(exprs, total=total, is_aggregate=True, worker_threads=workers, use_threads=threads)
+            assert r.rows() == [want], (workers, threads)
+
+
+def test_tail_quirk_rows_match_the_block_formula():
+    """numbers_stream.rs:37-54: a partition of c >= 10000 rows, c % 10000 = r > 0, emits 10000 * (c / 10000 - 1) + r + 1 rows."""
+    for total in (80_008, 100_000, 123_456, 799_999):
+        parts = o.generate_parts(total)
+        expect = 0
+        for b, e in parts:
+            c = e - b + 1
+            nblk, rem = divmod(c, 10_000)
+            expect += c if (nblk == 0 or rem == 0) else 10_000 * (nblk - 1) + rem + 1
+        r = o.run_query(["(count (col number))"], total=total, is_aggregate=True, worker_threads=0)
+        assert r.rows() == [(expect,)]
+        fixed = o.run_query(["(count (col number))"], total=total, is_aggregate=True, worker_threads=0, tail_quirk=False)
+        assert fixed.rows() == [(total,)]
