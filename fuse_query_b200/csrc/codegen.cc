@@ -94,11 +94,11 @@ struct Gen {
     if (n.kind != FQ_EXPR_ALIAS && n.kind != FQ_EXPR_AGGREGATOR) cols_below(n.right, out, depth + 1);
   }
 
-  bool trivial(int i) const {
-    if (i < 0 || i >= d.n_nodes) return false;
+  bool trivial(int i, int depth = 0) const {
+    if (i < 0 || i >= d.n_nodes || depth > 130) return false;   // (an alias cycle is not trivial; infer() reports it)
     const fq_expr_node &n = d.nodes[i];
     if (n.kind == FQ_EXPR_FIELD || n.kind == FQ_EXPR_CONSTANT) return true;
-    return n.kind == FQ_EXPR_ALIAS && trivial(n.left);
+    return n.kind == FQ_EXPR_ALIAS && trivial(n.left, depth + 1);
   }
 
   explicit Gen(const fq_pipe_desc &desc) : d(desc), ty(desc.n_nodes, FQ_NULL), visited(desc.n_nodes, 0), scalar(desc.n_nodes, 0) {}
@@ -118,8 +118,20 @@ struct Gen {
     const fq_expr_node *n = node(i);
     if (!n) return false;
     if (depth > 128) return fail(FQ_ERR_PLAN, "Error during plan: expression depth more than 128");
-    if (visited[i]) return status == FQ_OK;
+    if (visited[i] == 2) return status == FQ_OK;   // typed before (a node shared by two parents)
+    if (visited[i] == 1)                            // still being typed: the "tree" has a cycle — every later walk would not end
+      return fail(FQ_ERR_INVALID, fmt("Internal Error: expression node %d is its own ancestor", i));
     visited[i] = 1;
+    const bool typed = infer_node(i, n, depth);
+    visited[i] = 2;
+    return typed;
+  }
+  bool infer_node(int i, const fq_expr_node *n, int depth) {
+    // operator codes index symbol tables below and in the emitter: refuse anything outside the enums up front
+    const int n_ops = n->kind == FQ_EXPR_ARITHMETIC ? 4 : n->kind == FQ_EXPR_COMPARISON ? 5 : n->kind == FQ_EXPR_LOGIC ? 2
+                      : n->kind == FQ_EXPR_AGGREGATOR ? 4 : 0;
+    if (n_ops && (n->op < 0 || n->op >= n_ops))
+      return fail(FQ_ERR_INVALID, fmt("Internal Error: operator code %d out of range for expression node kind %d", n->op, n->kind));
     switch (n->kind) {
       case FQ_EXPR_FIELD: {
         if (n->column < 0 || n->column >= d.n_cols)
