@@ -88,3 +88,29 @@ def test_code_generator_survives_malformed_pipe_descriptions(tmp_path):
         r = subprocess.run([exe, "15000", seed], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         assert "generated" in r.stdout and "rejected" in r.stdout
+
+
+def test_every_entry_point_survives_null_arguments():
+    """Handles are opaque pointers a host language can get wrong: every exported function called with NULL / 0 for every
+    argument returns (an error status, 0 or NULL) instead of crashing.  Run in a child process so that a crash is a test
+    failure, not the end of the test session.  No device is needed: nothing here reaches a kernel."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C
+from fuse_query_b200 import cabi
+L = cabi.lib()
+for name in cabi.EXPORTS:
+    fn = getattr(L, name)
+    args = []
+    for t in (fn.argtypes or []):
+        pointer = t in (C.c_void_p, C.c_char_p) or (hasattr(t, "_type_") and not isinstance(t._type_, str))
+        args.append(None if pointer else 0)
+    fn(*args)
+print("survived", len(cabi.EXPORTS))
+'''
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=root)
+    assert r.returncode == 0, (r.returncode, r.stderr[-1500:])
+    assert r.stdout.strip().startswith("survived")
