@@ -221,3 +221,33 @@ def test_arrow_columns_hand_over_their_own_null_bitmap():
     chunked = pa.chunked_array([pa.array([1.5, None]), pa.array([None, 4.0])])
     vals, valid = _arrow_column(chunked)
     assert vals.tolist() == [1.5, 0.0, 0.0, 4.0] and valid[0] == "bitmap"
+
+
+def test_partial_state_json_parser_survives_mutations():
+    """The merge point parses what the partial pipes serialise (transform_aggregate_final.rs:56-66 -> serde_json of
+    DataValue::Struct): mutated JSON either parses to a value that round-trips or raises FuseQueryError."""
+    import random
+    rng = random.Random(3)
+    seeds = ['{"Struct":[{"UInt64":4999},{"UInt64":null}]}', '"Null"', '{"Int64":-5}', '{"Float64":1.5e3}', '{"Utf8":"a\\\\"b"}',
+             '{"Boolean":true}', '{"Struct":[{"Struct":[{"UInt8":1}]},"Null"]}', '{"UInt64":18446744073709551615}', '{"Float32":null}']
+    alphabet = list('{}[]":,\\\\ntruefalsnul0123456789.-+eE ') + ['"UInt64"', '"Struct"', '"Null"', 'null', '{', '}', '[', ']']
+    parsed = 0
+    for _ in range(30000):
+        s = rng.choice(seeds)
+        for _ in range(rng.randint(0, 4)):
+            k, pos = rng.randint(0, 3), rng.randint(0, len(s))
+            if k == 0:
+                s = s[:pos] + rng.choice(alphabet) + s[pos:]
+            elif k == 1:
+                s = s[:pos] + s[pos + 1:]
+            elif k == 2:
+                s = s[:pos] + s[pos:][::-1][:rng.randint(0, 5)] + s[pos:]
+            else:
+                s = s[:pos]
+        try:
+            v = h.DataValue.from_json(s)
+        except h.FuseQueryError:
+            continue
+        assert h.DataValue.from_json(v.to_json()).to_json() == v.to_json(), s
+        parsed += 1
+    assert parsed > 1000
