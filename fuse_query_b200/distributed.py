@@ -37,7 +37,14 @@ def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_obj
     sel = plans[i]
     is_agg = sel.name() == "AggregatePlan"
     i += 1
-    limit = plans[i].n if i < len(plans) and plans[i].name() == "LimitPlan" else None
+    limit = None
+    if i < len(plans) and plans[i].name() == "LimitPlan":
+        limit = plans[i].n
+        i += 1
+    if i != len(plans) or sel.name() not in ("AggregatePlan", "ProjectionPlan"):
+        # e.g. a derived table: its outer Filter / Projection would have to run after the cross-rank merge
+        raise h.FuseQueryError("Internal Error: distributed execution supports ReadSource [Filter] (Projection | Aggregate) [Limit], got "
+                               + " -> ".join(p.name() for p in plans))
     parts = _my_partitions(list(src.partitions), rank, world)
     names = sel.schema().names()
     local_blocks = []

@@ -251,3 +251,20 @@ def test_partial_state_json_parser_survives_mutations():
         assert h.DataValue.from_json(v.to_json()).to_json() == v.to_json(), s
         parsed += 1
     assert parsed > 1000
+
+
+def test_distributed_execution_refuses_plan_shapes_it_cannot_split():
+    """distributed.execute_sql_distributed runs ReadSource [Filter] (Projection | Aggregate) [Limit] per rank and merges;
+    a derived table would need its outer stages after the merge and must be refused, not silently truncated."""
+    from fuse_query_b200.distributed import execute_sql_distributed
+    c = h.FuseQueryContext.create_ctx(8)
+    gather = lambda obj: [obj]
+    with pytest.raises(h.FuseQueryError) as e:
+        execute_sql_distributed(c, "select number + 1 from (select number from system.numbers_mt(100) where number > 2) where number < 8",
+                                0, 1, gather)
+    assert "distributed execution supports" in str(e.value) and "FilterPlan -> ProjectionPlan -> FilterPlan -> ProjectionPlan" in str(e.value)
+    # a plain select passes the shape check and only then misses the device this context does not have
+    for sql in ("select sum(number) from system.numbers_mt(1000)", "select number from system.numbers_mt(1000) where number > 3 limit 2"):
+        with pytest.raises(h.FuseQueryError) as e:
+            execute_sql_distributed(c, sql, 0, 1, gather)
+        assert "distributed execution supports" not in str(e.value)
