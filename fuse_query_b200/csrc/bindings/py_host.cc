@@ -164,7 +164,9 @@ PYBIND11_MODULE(_fuse_host, m) {
       })
       .def_static("from_numpy_masked", [](GpuContextRef gpu, py::array a, py::array valid) {
         py::array c = py::array::ensure(a, py::array::c_style);
-        py::array v = py::array::ensure(valid.attr("astype")("uint8"), py::array::c_style);
+        // canonical 0/1 bytes: the kernels load validity as `bool` and combine it bitwise, so a mask holding 2 or 255 must
+        // not reach the device unchanged
+        py::array v = py::array::ensure(valid.attr("__ne__")(0).attr("astype")("uint8"), py::array::c_style);
         if (v.size() != c.size()) throw FuseQueryError::internal("validity and values differ in length");
         auto arr = DataArray::from_host(gpu, dtype_of_numpy(c), c.data(), (uint64_t)c.size());
         arr->set_validity(DataArray::from_host(gpu, FQ_BOOL, v.data(), (uint64_t)v.size()));

@@ -110,6 +110,7 @@ struct Nvrtc {
   int (*nvrtcGetProgramLog)(nvrtcProgram_, char *) = nullptr;
   int (*nvrtcDestroyProgram)(nvrtcProgram_ *) = nullptr;
   const char *(*nvrtcGetErrorString)(int) = nullptr;
+  int (*nvrtcVersion)(int *, int *) = nullptr;
   std::string why;
   bool load() {
     if (h) return true;
@@ -122,7 +123,7 @@ struct Nvrtc {
     if (!h) { why = dlerror(); return false; }
 #define SYM(n) *(void **)(&n) = dlsym(h, #n)
     SYM(nvrtcCreateProgram); SYM(nvrtcCompileProgram); SYM(nvrtcGetCUBINSize); SYM(nvrtcGetCUBIN);
-    SYM(nvrtcGetProgramLogSize); SYM(nvrtcGetProgramLog); SYM(nvrtcDestroyProgram); SYM(nvrtcGetErrorString);
+    SYM(nvrtcGetProgramLogSize); SYM(nvrtcGetProgramLog); SYM(nvrtcDestroyProgram); SYM(nvrtcGetErrorString); SYM(nvrtcVersion);
 #undef SYM
     if (!nvrtcCreateProgram || !nvrtcCompileProgram || !nvrtcGetCUBIN) { why = "libnvrtc lacks required symbols"; return false; }
     return true;
@@ -327,6 +328,8 @@ static void jit_cache_write(const std::string &path, const std::vector<char> &da
   if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
 }
 
+static const char *const kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+
 // `suffixes`: the kernel variants to build (empty = all of them)
 fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const std::vector<std::string> &suffixes) {
   if (!g_nvrtc.load()) return set_err(FQ_ERR_CUDA, "NVRTC unavailable: %s", g_nvrtc.why.c_str());
@@ -335,8 +338,13 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const st
   for (auto &k : gen.kernels)
     if (suffixes.empty() || std::find(suffixes.begin(), suffixes.end(), k.first) != suffixes.end()) src += k.second;
   const std::string cache_dir = jit_cache_dir();
+  // key = program text + everything else the cubin depends on: NVRTC's version and the compile options
+  int nv_major = 0, nv_minor = 0;
+  if (g_nvrtc.nvrtcVersion) g_nvrtc.nvrtcVersion(&nv_major, &nv_minor);
+  std::string key_text = src + "\n//nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor);
+  for (const char *o : kNvrtcOpts) key_text += std::string(" ") + o;
   char key[40];
-  snprintf(key, sizeof key, "%016" PRIx64 "%08x", fnv1a64(src), (unsigned)src.size());
+  snprintf(key, sizeof key, "%016" PRIx64 "%08x", fnv1a64(key_text), (unsigned)key_text.size());
   const std::string cache_path = cache_dir.empty() ? "" : cache_dir + "/" + key + ".sm_100a.cubin";
   std::vector<char> cached;
   if (!cache_path.empty() && jit_cache_read(cache_path, &cached)) {
@@ -347,8 +355,7 @@ fq_status compile_jit(fq_ctx *ctx, const fq::Generated &gen, Module *m, const st
   nvrtcProgram_ prog = nullptr;
   int r = g_nvrtc.nvrtcCreateProgram(&prog, src.c_str(), ("fq_" + gen.tag + ".cu").c_str(), 0, nullptr, nullptr);
   if (r) return set_err(FQ_ERR_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.nvrtcGetErrorString(r));
-  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
-  r = g_nvrtc.nvrtcCompileProgram(prog, 3, opts);
+  r = g_nvrtc.nvrtcCompileProgram(prog, (int)(sizeof kNvrtcOpts / sizeof kNvrtcOpts[0]), kNvrtcOpts);
   if (r) {
     size_t n = 0;
     g_nvrtc.nvrtcGetProgramLogSize(prog, &n);

@@ -7,6 +7,7 @@
 // side); here it is C++ because no Rust toolchain exists in this image.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -295,14 +296,27 @@ struct ExpressionPlan {
   std::string name;   // alias / field / operator / function name
   DataValue value;
   std::vector<ExpressionPlan> args;   // Alias: [expr]; Binary: [left, right]; Function: args
+  int tree_depth = 1;                 // height of the tree below (and including) this node; the SQL front end bounds it
 
+  static constexpr int kMaxDepth = 128;   // deeper trees are refused: every later walk (to_function, lowering, codegen) recurses
   static ExpressionPlan field(const std::string &n) { ExpressionPlan e; e.kind = Field; e.name = n; return e; }
   static ExpressionPlan constant(const DataValue &v) { ExpressionPlan e; e.kind = Constant; e.value = v; return e; }
-  static ExpressionPlan alias(const std::string &a, ExpressionPlan x) { ExpressionPlan e; e.kind = Alias; e.name = a; e.args = {std::move(x)}; return e; }
-  static ExpressionPlan binary(ExpressionPlan l, const std::string &op, ExpressionPlan r) {
-    ExpressionPlan e; e.kind = BinaryExpression; e.name = op; e.args = {std::move(l), std::move(r)}; return e;
+  static ExpressionPlan alias(const std::string &a, ExpressionPlan x) {
+    ExpressionPlan e; e.kind = Alias; e.name = a; e.tree_depth = x.tree_depth + 1; e.args = {std::move(x)}; return checked(std::move(e));
   }
-  static ExpressionPlan function(const std::string &op, std::vector<ExpressionPlan> a) { ExpressionPlan e; e.kind = Function; e.name = op; e.args = std::move(a); return e; }
+  static ExpressionPlan binary(ExpressionPlan l, const std::string &op, ExpressionPlan r) {
+    ExpressionPlan e; e.kind = BinaryExpression; e.name = op; e.tree_depth = std::max(l.tree_depth, r.tree_depth) + 1;
+    e.args = {std::move(l), std::move(r)}; return checked(std::move(e));
+  }
+  static ExpressionPlan function(const std::string &op, std::vector<ExpressionPlan> a) {
+    ExpressionPlan e; e.kind = Function; e.name = op;
+    for (const auto &x : a) e.tree_depth = std::max(e.tree_depth, x.tree_depth + 1);
+    e.args = std::move(a); return checked(std::move(e));
+  }
+  static ExpressionPlan checked(ExpressionPlan e) {
+    if (e.tree_depth > kMaxDepth) throw FuseQueryError::plan("expression depth more than 128");
+    return e;
+  }
   static ExpressionPlan wildcard() { return ExpressionPlan(); }
 
   FunctionRef to_function(size_t depth = 0) const;                 // plan_expression.rs:40-75

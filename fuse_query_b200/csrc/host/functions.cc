@@ -84,6 +84,9 @@ fq_pipe_desc Lowering::desc(int kind, int predicate, const std::vector<int> &roo
   d.n_nodes = (int)nodes.size();
   d.predicate = predicate;
   d.kind = kind;
+  // fq_pipe_desc::exprs holds FQ_MAX_EXPRS roots; callers with more split them into several pipes (run_project) or refuse
+  if (roots.size() > (size_t)FQ_MAX_EXPRS)
+    throw FuseQueryError::internal("Unsupported on the device path: more than 8 select expressions in one pipe");
   d.n_exprs = (int)roots.size();
   for (size_t k = 0; k < roots.size(); k++) d.exprs[k] = roots[k];
   return d;
@@ -111,6 +114,19 @@ PipeRef compile_pipe(GpuContextRef ctx, const fq_pipe_desc &d) {
 // `limit` of them).  Used by Function::eval, the Filter/Projection transforms and GpuPipeTransform.
 ProjectResult run_project(GpuContextRef ctx, const DataBlock &block, const Function *predicate, const std::vector<const Function *> &funcs,
                           int64_t limit, bool early_exit) {
+  if (funcs.size() > (size_t)FQ_MAX_EXPRS) {
+    // a pipe holds at most FQ_MAX_EXPRS select expressions: wider projections (and filters over wide tables, which gather
+    // every column) run as several launches with the same predicate — the compaction is deterministic, so every launch
+    // keeps the same rows in the same order
+    ProjectResult all;
+    for (size_t b = 0; b < funcs.size(); b += FQ_MAX_EXPRS) {
+      std::vector<const Function *> part(funcs.begin() + b, funcs.begin() + std::min(funcs.size(), b + (size_t)FQ_MAX_EXPRS));
+      ProjectResult r = run_project(ctx, block, predicate, part, limit, early_exit);
+      if (b == 0) { all.rows_selected = r.rows_selected; all.rows_written = r.rows_written; }
+      for (auto &c : r.columns) all.columns.push_back(c);
+    }
+    return all;
+  }
   Lowering lw;
   // a generated block's column must be pipe column 0: touch it first
   if (block.generated) lw.column_of(block, block.schema()->fields[0].name);

@@ -472,52 +472,68 @@ SendableDataBlockStream GpuPipeTransform::execute() {
     for (auto &f : funcs) collect_leaves(*f, &ls);
     for (const Function *l : ls) track_blocks = track_blocks || l->op == FQ_AGG_SUM;
   }
-  GpuOptions saved = ctx_->options;
-  ctx_->options.block_rows = 0;
-  ctx_->options.align_runs = track_blocks;
-  SendableDataBlockStream source = table->read(ctx_, partitions_);
-  ctx_->options = saved;
+  // the pipe reads whole runs of partitions; the context's options are restored even when read() throws (bad partition name)
+  struct OptionsGuard {
+    FuseQueryContextRef c;
+    GpuOptions saved;
+    explicit OptionsGuard(FuseQueryContextRef ctx) : c(std::move(ctx)), saved(c->options) {}
+    ~OptionsGuard() { c->options = saved; }
+  };
+  SendableDataBlockStream source;
+  {
+    OptionsGuard guard(ctx_);
+    ctx_->options.block_rows = 0;
+    ctx_->options.align_runs = track_blocks;
+    source = table->read(ctx_, partitions_);
+  }
 
   if (is_aggregate_) {
-    PipeRef pipe;
-    Lowering lw;
+    // one fused pipe per FQ_MAX_EXPRS select expressions (almost always exactly one)
+    struct Part { PipeRef pipe; Lowering lw; std::vector<const Function *> funcs, leaves; };
+    std::vector<Part> parts((funcs.size() + FQ_MAX_EXPRS - 1) / FQ_MAX_EXPRS);
+    for (size_t i = 0; i < funcs.size(); i++) parts[i / FQ_MAX_EXPRS].funcs.push_back(funcs[i].get());
     std::vector<const Function *> leaves;
     for (auto &f : funcs) collect_leaves(*f, &leaves);
+    for (auto &pt : parts)
+      for (const Function *f : pt.funcs) collect_leaves(*f, &pt.leaves);
     int launches = 0;
     while (auto block = source->next()) {
-      if (!pipe) {
-        if (block->generated) lw.column_of(*block, block->schema()->fields[0].name);
-        int p = pred ? lw.lower(*pred, *block) : -1;
-        std::vector<int> roots;
-        for (auto &f : funcs) roots.push_back(lw.lower(*f, *block));
-        fq_pipe_desc d = lw.desc(FQ_PIPE_AGGREGATE, p, roots);
-        pipe = compile_pipe(gpu, d);
+      for (auto &pt : parts) {
+        if (!pt.pipe) {
+          if (block->generated) pt.lw.column_of(*block, block->schema()->fields[0].name);
+          int p = pred ? pt.lw.lower(*pred, *block) : -1;
+          std::vector<int> roots;
+          for (const Function *f : pt.funcs) roots.push_back(pt.lw.lower(*f, *block));
+          fq_pipe_desc d = pt.lw.desc(FQ_PIPE_AGGREGATE, p, roots);
+          pt.pipe = compile_pipe(gpu, d);
+        }
+        BoundSource bs;
+        bind_source(pt.lw, *block, &bs);
+        gpu->check(fq_pipe_launch_aggregate(gpu->raw(), pt.pipe->pipe, &bs.src,
+                                            (launches > 0 ? FQ_RUN_ACCUMULATE : 0) | (track_blocks ? FQ_RUN_BLOCK_STATS : 0), gpu->stream));
       }
-      BoundSource bs;
-      bind_source(lw, *block, &bs);
-      gpu->check(fq_pipe_launch_aggregate(gpu->raw(), pipe->pipe, &bs.src,
-                                          (launches > 0 ? FQ_RUN_ACCUMULATE : 0) | (track_blocks ? FQ_RUN_BLOCK_STATS : 0), gpu->stream));
       launches++;
     }
     std::map<const Function *, DataValue> leaf_state;
     for (const Function *l : leaves) leaf_state[l] = DataValue::Null();
-    if (pipe) {
-      std::vector<fq_value> st(leaves.size() + 1);
+    for (auto &pt : parts) {
+      if (!pt.pipe) continue;
+      std::vector<fq_value> st(pt.leaves.size() + 1);
       int32_t n = 0;
       uint64_t sel = 0;
-      gpu->check(fq_pipe_fetch_aggregate(gpu->raw(), pipe->pipe, st.data(), (int32_t)st.size(), &n, &sel));
+      gpu->check(fq_pipe_fetch_aggregate(gpu->raw(), pt.pipe->pipe, st.data(), (int32_t)st.size(), &n, &sel));
       if (track_blocks) {
         uint64_t blocks = 0, empty = 0;
-        gpu->check(fq_pipe_fetch_block_stats(gpu->raw(), pipe->pipe, &blocks, &empty));
+        gpu->check(fq_pipe_fetch_block_stats(gpu->raw(), pt.pipe->pipe, &blocks, &empty));
         // function_aggregator.rs:88-97: state = state + arrow_sum(block); the second block onwards goes through
         // DataValue::to_array, which refuses Type(None) (data_value.rs:104-109) — on either side of the add
         if (blocks >= 2 && empty > 0) throw FuseQueryError::internal("DataValue to array cannot be NONE NULL");
       }
-      std::vector<int32_t> nodes(leaves.size() + 1);
+      std::vector<int32_t> nodes(pt.leaves.size() + 1);
       int32_t nn = 0;
-      gpu->check(fq_pipe_aggregator_nodes(gpu->raw(), pipe->pipe, nodes.data(), (int32_t)nodes.size(), &nn));
-      for (const Function *l : leaves) {
-        int node = lw.node_of.at(l);
+      gpu->check(fq_pipe_aggregator_nodes(gpu->raw(), pt.pipe->pipe, nodes.data(), (int32_t)nodes.size(), &nn));
+      for (const Function *l : pt.leaves) {
+        int node = pt.lw.node_of.at(l);
         for (int k = 0; k < nn; k++)
           if (nodes[k] == node) leaf_state[l] = DataValue::from_abi(st[k]);
       }

@@ -296,6 +296,16 @@ static std::string sql_display(const ExpressionPlan &e) {
 struct SqlParser {
   std::vector<Tok> t;
   size_t p = 0;
+  // nesting of parentheses / function calls / derived tables currently open: the parser is recursive-descent, so a query
+  // of 20 000 opening parentheses would otherwise overflow the host stack long before any plan check runs
+  int nesting = 0;
+  struct Nest {
+    SqlParser &sp;
+    explicit Nest(SqlParser &s, const char *what) : sp(s) {
+      if (++sp.nesting > ExpressionPlan::kMaxDepth) { --sp.nesting; throw FuseQueryError::plan(std::string(what) + " depth more than 128"); }
+    }
+    ~Nest() { --sp.nesting; }
+  };
   const Tok &peek() const { return t[p]; }
   bool is_kw(const char *kw) const {
     if (peek().k != Tok::Word) return false;
@@ -352,23 +362,27 @@ struct SqlParser {
     if (tok.k == Tok::String) { p++; return ExpressionPlan::constant(DataValue::String(tok.text)); }
     if (tok.k == Tok::Sym && tok.text == "(") {   // Expr::Nested
       p++;
+      Nest nest(*this, "expression");
       ExpressionPlan e = expr();
       expect_sym(")");
       return e;
     }
     if (tok.k == Tok::Sym && (tok.text == "-" || tok.text == "+")) {   // UnaryOp: not handled by sql_to_rex
       p++;
+      Nest nest(*this, "expression");
       ExpressionPlan inner = expr(50);
       throw FuseQueryError::plan("Unsupported ExpressionPlan: " + tok.text + " " + sql_display(inner));
     }
     if (is_kw("NOT")) {   // UnaryOp { op: Not }: parsed by sqlparser, refused by sql_to_rex
       p++;
+      Nest nest(*this, "expression");
       ExpressionPlan inner = expr(15);   // NOT binds looser than the comparisons, tighter than AND / OR
       throw FuseQueryError::plan("Unsupported ExpressionPlan: NOT " + sql_display(inner));
     }
     if (tok.k == Tok::Word && !reserved(tok.text)) {
       p++;
       if (eat_sym("(")) {   // Expr::Function
+        Nest nest(*this, "expression");
         std::vector<ExpressionPlan> args;
         if (!eat_sym(")")) {
           do {
@@ -409,7 +423,10 @@ PlanNode select_to_plan(FuseQueryContextRef ctx, SqlParser &sp) {   // plan_pars
     if (sp.eat_sym("(")) {
       // TableFactor::Derived: the subquery's plan (a SelectPlan node) is the input, plan_parser.rs:206-208;
       // children_to_plans flattens nested selects into one chain of transforms
-      plan = select_to_plan(ctx, sp);
+      {
+        SqlParser::Nest nest(sp, "PlanNode");
+        plan = select_to_plan(ctx, sp);
+      }
       sp.expect_sym(")");
       if (sp.eat_kw("AS")) {
         if (sp.peek().k != Tok::Word) sp.expected("an identifier after AS");

@@ -553,3 +553,42 @@ def test_sum_with_where_reproduces_reference_block_poisoning(gpu, sql_where, pre
     keep = {"number >= 60000": x >= 60000, "number/10000*10000 = number": x % 10000 == 0, "number/20000*20000 = number": x % 20000 == 0,
             "number < 5": x < 5}[sql_where]
     assert rows_of(h.execute_sql(ctx, sql)) == [(int(x[keep].sum()), int(keep.sum()))]
+
+
+def test_more_than_eight_select_expressions_split_into_several_pipes(gpu):
+    """A pipe holds FQ_MAX_EXPRS = 8 select expressions: wider projections, wider aggregate lists and a WHERE over a table of
+    more than 8 columns (FilterTransform gathers every column) run as several launches and still match the oracle."""
+    from fuse_query_b200.tables import register_table
+    n = 80_000
+    items = [f"number + {i} as c{i}" for i in range(11)]
+    want = o.run_query([f"(alias c{i} (+ (col number) (u64 {i})))" for i in range(11)], total=n, predicate="(< (col number) (u64 7))",
+                       worker_threads=1)
+    for fuse in (True, False):
+        ctx = make_ctx(gpu, 1, fuse=fuse)
+        blocks = h.execute_sql(ctx, "select " + ", ".join(items) + f" from system.numbers_mt({n}) where number < 7")
+        assert rows_of(blocks) == want.rows() and blocks[0].schema().names() == want.names
+    aggs = [f"sum(number + {i})" for i in range(10)]
+    ctx = make_ctx(gpu, 1)
+    blocks = h.execute_sql(ctx, "select " + ", ".join(aggs) + f" from system.numbers_mt({n})")
+    want = o.run_query([f"(sum (+ (col number) (u64 {i})))" for i in range(10)], total=n, is_aggregate=True, worker_threads=1)
+    assert rows_of(blocks) == want.rows() and blocks[0].schema().names() == want.names
+    rng = np.random.default_rng(5)
+    data = {f"k{i}": rng.integers(0, 1000, 5000, dtype=np.uint64) for i in range(10)}
+    ctx = make_ctx(gpu, 1, fuse=False, block_rows=0)
+    register_table(ctx, gpu, "default", "wide", data)
+    blocks = h.execute_sql(ctx, "select k0, k9 from wide where k3 < 10")
+    keep = data["k3"] < 10
+    assert rows_of(blocks) == list(zip(data["k0"][keep].tolist(), data["k9"][keep].tolist()))
+
+
+def test_validity_masks_are_canonicalised_on_upload(gpu):
+    """register_table's (values, valid) pairs may hold any non-zero byte for "valid"; the device sees 0/1 only."""
+    from fuse_query_b200.tables import register_table
+    vals = np.arange(1, 9, dtype=np.int64)
+    valid = np.array([255, 0, 2, 1, 0, 128, 7, 0], dtype=np.uint8)
+    ctx = make_ctx(gpu, 1)
+    register_table(ctx, gpu, "default", "m", {"v": (vals, valid)})
+    blocks = h.execute_sql(ctx, "select sum(v), count(v), min(v), max(v) from m")
+    assert rows_of(blocks) == [(int(vals[valid != 0].sum()), 8, 1, 7)]
+    blocks = h.execute_sql(ctx, "select v + 1 as w from m where v > 0")
+    assert rows_of(blocks) == [(int(x) + 1,) for x in vals[valid != 0]]

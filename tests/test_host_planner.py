@@ -268,3 +268,33 @@ def test_distributed_execution_refuses_plan_shapes_it_cannot_split():
         with pytest.raises(h.FuseQueryError) as e:
             execute_sql_distributed(c, sql, 0, 1, gather)
         assert "distributed execution supports" not in str(e.value)
+
+
+def test_deeply_nested_sql_is_refused_not_crashed(ctx):
+    """A 40 KB query of nested parentheses, a 20 000-term sum or 5 000 nested derived tables must end in a
+    FuseQueryError — the recursive-descent parser counts its nesting and ExpressionPlan bounds its height at 128
+    (the same bound the code generator applies), instead of running the host stack out (exit 139)."""
+    deep = "(" * 20000 + "number" + ")" * 20000
+    for sql in (f"select {deep} from system.numbers_mt(10)",
+                "select " + "+".join(["number"] * 20000) + " from system.numbers_mt(10)",
+                "select " + "sum(" * 3000 + "number" + ")" * 3000 + " from system.numbers_mt(10)",
+                "select number from " + "(select number from " * 5000 + "system.numbers_mt(10)" + ")" * 5000,
+                "select " + "not " * 20000 + "number from system.numbers_mt(10)",
+                "select " + "- " * 20000 + "number from system.numbers_mt(10)"):
+        with pytest.raises(h.FuseQueryError) as e:
+            h.Planner().build_from_sql(ctx, sql)
+        assert "depth more than 128" in str(e.value), str(e.value)[:200]
+    # 100 levels are fine
+    ok = "(" * 100 + "number" + ")" * 100
+    h.Planner().build_from_sql(ctx, f"select {ok} from system.numbers_mt(10)")
+    h.Planner().build_from_sql(ctx, "select " + "+".join(["number"] * 100) + " from system.numbers_mt(10)")
+
+
+def test_more_than_eight_select_items_plan_without_a_device(ctx):
+    """fq_pipe_desc holds 8 roots; a 9+ item select list must never overrun it (stack-buffer-overflow in
+    Lowering::desc).  Without a device the query plans and builds its pipeline; executing throws a FuseQueryError."""
+    sql = "select " + ", ".join(f"number + {i} as c{i}" for i in range(12)) + " from system.numbers_mt(100)"
+    plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, sql))
+    assert len(plan.children_to_plans()[1].schema().names()) == 12
+    with pytest.raises(h.FuseQueryError):
+        h.execute_sql(ctx, sql)
