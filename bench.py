@@ -5,20 +5,25 @@
 
 Workload (BASELINE.json configs[3], the README headline query):
     SELECT sum(number)/count(number), max(number), min(number) FROM system.numbers_mt(10_000_000_000)
-One "step" = one pass of the fused Source -> AggregatePartial kernel over every rank's shard of the
-10^10-row UInt64 column (materialised in HBM, 80 GB at N=1) + the merge of the per-rank partial states
-(N > 1: the kernel's last CTA stores the 80-byte state into every rank's gather buffer over NVLink peer memory;
---merge nccl, or an IPC failure, all-gathers the same bytes with NCCL after each launch) — strong scaling: the 10^10 rows are partitioned
-across ranks exactly like the reference chunks its 8 partitions over workers
-(processors/pipeline_builder.rs:73-95).
+One "step" = one COMPLETE query over the 10^10-row UInt64 column (materialised in HBM, 80 GB at N=1): every rank runs the
+fused Source -> AggregatePartial kernel over its shard and the kernel itself finishes with the merge point
+(processors/processor_merge.rs:37-66 -> transforms/transform_aggregate_final.rs:50-78): its last CTA stores the 80-byte
+running state into every rank's exchange window over NVLink peer memory, waits for the states of all ranks of this step
+and folds them, so that when the step's kernel has ended EVERY rank holds the merged answer (copied to pinned host
+memory behind the kernel).  `--merge nccl` (or an IPC failure) does the same exchange with an NCCL all-gather + fold
+after each launch.  Strong scaling: the 10^10 rows are partitioned across ranks exactly like the reference chunks its 8
+partitions over workers (processors/pipeline_builder.rs:73-95).
 
-Prints ONE JSON line (see the contract in the task statement): `value` = whole-job rows/s with inputs
-resident in HBM; `e2e` = the same query through the C ABI with HOST (pinned) column buffers, H2D copies
-and the D2H state read inside the timed region; `roofline` for the aggregate kernel; `cpu_baseline` =
-the CPU oracle's reference-shaped pipeline timed on this box's host cores (rank 0, N=1 only).
+Prints ONE JSON line (see the contract in the task statement): `value` = whole-job rows/s with inputs resident in HBM,
+merge included; `throughput_no_merge` = back-to-back kernels without the cross-rank wait (round 1's figure); `e2e` = the
+same query through the C ABI with HOST (pinned) column buffers, H2D copies and the D2H state read inside the timed
+region, with `e2e.roofline` = the plain cudaMemcpyAsync rate of the same copies on all ranks at once; `roofline` for the
+aggregate kernel; `per_query` = every README query x {materialised, generated} as whole-job numbers at this N with the
+merged result verified against the closed form; `cpu_baseline` = the CPU oracle's reference-shaped pipeline timed on this
+box's host cores (rank 0, N=1 only).
 
---impl reference times the reference's CPU algorithm (oracle port; the reference itself is Rust and
-cannot be built in this image) with the 8-way parallelism the reference uses.
+--impl reference times the reference's CPU algorithm (oracle port; the reference itself is Rust and cannot be built in
+this image) with the 8-way parallelism the reference uses.
 """
 from __future__ import annotations
 
@@ -40,14 +45,29 @@ NUM = "(col number)"
 HEADLINE = [f"(/ (sum {NUM}) (count {NUM}))", f"(max {NUM})", f"(min {NUM})"]
 HEADLINE_SQL = "SELECT sum(number)/count(number), max(number), min(number) FROM system.numbers_mt(10000000000)"
 README_PUBLISHED_SECONDS = 6.40  # README.md:62 (8 vCPU KVM), BASELINE.md §1
+M64 = (1 << 64) - 1
+
+
+def _sum(n, b=0):     # wrapping sum of b .. b+n-1
+    return ((2 * b + n - 1) * n // 2) & M64
+
+
+# name -> (select expressions, expected Aggregator-leaf states in node order as functions of the row count, README seconds, note)
 README_QUERIES = {
-    "sum(number)": [f"(sum {NUM})"],
-    "max(number)": [f"(max {NUM})"],
-    "max(number+1)": [f"(max (+ {NUM} (u64 1)))"],
-    "count(number)": [f"(count {NUM})"],
-    "sum(number)/count(number)": [f"(/ (sum {NUM}) (count {NUM}))"],
-    "sum(number)/count(number),max(number),min(number)": HEADLINE,
+    "sum(number)": ([f"(sum {NUM})"], lambda n: [_sum(n)], 1.77, None),
+    "max(number)": ([f"(max {NUM})"], lambda n: [n - 1], 2.83, None),
+    "max(number+1)": ([f"(max (+ {NUM} (u64 1)))"], lambda n: [n], 6.13, None),
+    "count(number)": ([f"(count {NUM})"], lambda n: [n], 1.55,
+                      "metadata-only: Count of a bare column reads no data (the row count is known); no bytes, no GB/s"),
+    "count(number) [honest 8N scan]": ([f"(count (+ {NUM} (u64 0)))"], lambda n: [n], 1.55,
+                                       "Count(number + 0): the argument is evaluated for every row like the reference does "
+                                       "(function_aggregator.rs:58-59), so the column is streamed once"),
+    "sum(number)/count(number)": ([f"(/ (sum {NUM}) (count {NUM}))"], lambda n: [_sum(n), n], 2.04, None),
+    "sum(number)/count(number),max(number),min(number)": (HEADLINE, lambda n: [_sum(n), n, n - 1, 0], 6.40, None),
 }
+CFG1 = [f"(max (+ {NUM} (u64 1)))", f"(min {NUM})", f"(count {NUM})"]
+CFG2_PRED = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))"
+CFG2_PROJ = [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"]
 
 
 def agg_kernel_name(generated: bool) -> str:
@@ -59,13 +79,17 @@ def agg_kernel_name(generated: bool) -> str:
 
 def ncu_traffic(rows_per_launch: int, generated: bool):
     """dram__bytes_read.sum + dram__bytes_write.sum of the aggregate kernel from the committed ncu --set full capture of THIS
-    workload (profiles/r01_traffic_headline_1e10.json); None when the launch differs from the captured one."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_headline_1e10.json")
-    if generated or not os.path.exists(path):
+    workload (profiles/*traffic_headline_1e10.json, newest round first); None when the launch differs from the captured one."""
+    if generated:
         return None
-    with open(path) as f:
-        t = json.load(f)
-    return t["traffic"] if t["rows"] == rows_per_launch else None
+    for name in ("r02_traffic_headline_1e10.json", "r01_traffic_headline_1e10.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                t = json.load(f)
+            if t["rows"] == rows_per_launch:
+                return t["traffic"]
+    return None
 
 
 def peaks():
@@ -123,21 +147,14 @@ def shard_of(rank: int, world: int, total: int):
     return shard_for_rank(rank, world, total)
 
 
-def fold_states(rows):
-    """Merge per-rank raw state slots [6 header slots: rows_selected, err, folded, scanned, blocks, empty blocks | sum, count,
-    max, min] (AggregatorFunction::merge_state, function_aggregator.rs:106-139) and apply merge_result."""
-    M = (1 << 64) - 1
-    H = 6  # FQ_STATE_HEADER_SLOTS
-    s = sum(r[H] for r in rows) & M
-    c = sum(r[0] for r in rows) & M
-    mx = max(r[H + 2] for r in rows)
-    mn = min(r[H + 3] for r in rows)
-    return {"sum": s, "count": c, "avg": s // c, "max": mx, "min": mn}
-
-
 def expected(total: int):
-    return {"sum": (total * (total - 1) // 2) % (1 << 64), "count": total, "avg": ((total * (total - 1) // 2) % (1 << 64)) // total,
-            "max": total - 1, "min": 0}
+    return {"sum": _sum(total), "count": total, "avg": _sum(total) // total, "max": total - 1, "min": 0}
+
+
+def common_config(total: int):
+    """The part of `config` both arms print identically (the driver compares them)."""
+    sql = HEADLINE_SQL if total == TOTAL_ROWS else HEADLINE_SQL.replace("10000000000", str(total))
+    return {"workload": sql, "rows_total": total}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -172,13 +189,15 @@ def run_reference(args):
     value = rows * len(times) / t
     exp = expected(rows)
     assert list(res) == [exp["avg"], exp["max"], exp["min"]], (res, exp)
-    sample = (f"{rows} rows of numbers_mt per step (the 10^10-row workload is {TOTAL_ROWS // rows}x this; rows/s is size-independent), "
+    total = args.rows or TOTAL_ROWS
+    sample = (f"{rows} rows of numbers_mt per step (the {total}-row workload is {total / rows:.1f}x this; rows/s is size-independent), "
               f"8 partitions on {cores} threads, 10 000-row blocks, one Arrow-style pass per aggregate")
     out = {
         "impl": "reference", "metric": "rows_per_s", "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": value / (TOTAL_ROWS / README_PUBLISHED_SECONDS), "dtype": "u64", "data": "synthetic",
-        "config": {"workload": HEADLINE_SQL, "rows_per_step": rows, "note": "CPU oracle port of the reference pipeline (reference is Rust; no rustc in this image)"},
+        "config": common_config(total),
+        "note": "CPU oracle port of the reference pipeline (the reference is Rust; no rustc in this image), bounded sample per step",
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_model": cpu_model(),
@@ -200,30 +219,51 @@ def cpu_model():
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def bind_to_gpu_numa_node(local: int):
-    """Pin this process (and so the first-touch placement of its pinned host buffers) to the CPUs of the NUMA node
-    the GPU hangs off: with 8 ranks the e2e leg otherwise pulls half of its host column across the socket link.
-    Returns a short description for the JSON line; does nothing when sysfs does not say."""
+def _cpulist(text: str):
+    ids = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        ids.update(range(int(a), int(b or a) + 1))
+    return ids
+
+
+def bind_to_gpu_cpus(local: int):
+    """Pin this process (and so the placement of the pinned host buffers it allocates afterwards) to the CPUs next to its GPU:
+    with 8 ranks the e2e leg otherwise pulls part of its host column across the socket interconnect.  Sources, in order: the
+    PCI device's numa_node, its local_cpulist (present even where numa_node says -1).  Returns a description for the JSON line."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local).pci_bus_id
-        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
-        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
-        node = int(open(path).read().strip())
-        if node < 0:
-            return "numa: unknown"
-        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
-        ids = set()
-        for part in cpus.split(","):
-            a, _, b = part.partition("-")
-            ids.update(range(int(a), int(b or a) + 1))
-        allowed = ids & os.sched_getaffinity(0)
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-        return f"numa node {node} ({len(allowed)} cpus)"
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        allowed_now = os.sched_getaffinity(0)
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus, src = set(), ""
+        if node >= 0:
+            cpus, src = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()), f"numa node {node}"
+        else:
+            cpus, src = _cpulist(open(f"{base}/local_cpulist").read()), "pci local_cpulist (numa_node = -1)"
+        pick = cpus & allowed_now
+        n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+        if pick and len(pick) < len(allowed_now):
+            os.sched_setaffinity(0, pick)
+            return f"{bdf}: bound to {len(pick)} cpus of {src}; host has {n_nodes} numa node(s)"
+        return f"{bdf}: {src} covers every allowed cpu ({len(allowed_now)}): nothing to bind; host has {n_nodes} numa node(s)"
     except Exception as e:  # sysfs layout differs / container hides it: keep the default placement
-        return f"numa: not bound ({type(e).__name__})"
+        return f"not bound ({type(e).__name__}: {e})"
+
+
+def mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
 
 
 class DevPtr:
@@ -233,183 +273,206 @@ class DevPtr:
         self.__cuda_array_interface__ = {"shape": (n_u64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from fuse_query_b200 import cabi
+class Rig:
+    """Everything a measurement needs: context, stream, ranks, the group, max-over-ranks reductions."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from fuse_query_b200 import cabi
+        self.torch, self.dist, self.cabi, self.args = torch, dist, cabi, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else "numa: single rank, not bound"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = cabi.Context(local)
-    stream = torch.cuda.current_stream().cuda_stream
+        torch.cuda.set_device(self.local)
+        self.dev = f"cuda:{self.local}"
+        self.affinity = bind_to_gpu_cpus(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.ctx = cabi.Context(self.local)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.group, self.merge = None, "single GPU: the kernel's own fold is the final state"
+        if self.world > 1:
+            self.merge = "nccl all_gather of the running state + fold on the device after each launch"
+            if args.merge == "peer":
+                ok = torch.ones(1, device=self.dev)
+                try:
+                    g = self.ctx.group(self.rank, self.world)
+                    handles = [None] * self.world
+                    dist.all_gather_object(handles, g.handle())
+                    g.connect(handles)
+                    self.group = g
+                except Exception as e:  # IPC not permitted in this container / no peer access: keep NCCL
+                    sys.stderr.write(f"[bench] rank {self.rank}: peer-memory merge unavailable ({e}); using NCCL\n")
+                    ok = torch.zeros(1, device=self.dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+                if ok.item() != 1:
+                    self.group = None
+                else:
+                    self.merge = ("in-kernel: the aggregate kernel's last CTA stores its state into every rank's exchange window over NVLink "
+                                  "peer memory, waits for all ranks' states of the step and folds them (fq_group)")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        if self.world == 1:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+class MergedPipe:
+    """An aggregate pipe whose launch completes the query across ranks: in-kernel group merge, or NCCL all-gather + device fold."""
+
+    def __init__(self, rig: Rig, exprs, generated: bool, leaf_ops):
+        self.rig, self.leaf_ops = rig, leaf_ops
+        self.pipe = rig.ctx.pipe(exprs, aggregate=True, generated=generated)
+        self.use_nccl = rig.world > 1 and rig.group is None
+        if rig.group is not None:
+            self.pipe.set_group(rig.group)
+        if self.use_nccl:
+            t = rig.torch
+            ptr, nbytes = self.pipe.state_device()
+            self.n_slots = nbytes // 8
+            self.state_t = t.as_tensor(DevPtr(ptr, self.n_slots), device=rig.dev)
+            self.gathered = t.zeros((rig.world, self.n_slots), dtype=t.int64, device=rig.dev)
+            self.folded = t.zeros(self.n_slots, dtype=t.int64, device=rig.dev)
+            self.host = t.zeros(self.n_slots, dtype=t.int64).pin_memory()
+
+    def launch(self, src):
+        self.pipe.launch_aggregate(src, stream=self.rig.stream)
+        self.exchange()
+
+    def exchange(self):
+        """NCCL arm only: the collective part of the step (the in-kernel merge needs nothing after the launch)."""
+        if not self.use_nccl:
+            return
+        H = self.rig.cabi.STATE_HEADER_SLOTS
+        self.rig.dist.all_gather_into_tensor(self.gathered.view(-1), self.state_t)
+        self.folded[:H] = self.gathered[:, :H].sum(0)
+        for k, op in enumerate(self.leaf_ops):     # this workload's values stay below 2^63 for min/max; sums wrap like u64
+            col = self.gathered[:, H + k]
+            self.folded[H + k] = col.sum() if op in ("sum", "count") else (col.max() if op == "max" else col.min())
+        self.host.copy_(self.folded, non_blocking=True)
+
+    def result(self):
+        """-> (leaf values, rows) of the whole job, on this rank"""
+        if self.rig.world == 1:
+            states, rows = self.pipe.fetch_aggregate()
+        elif not self.use_nccl:
+            states, rows = self.pipe.fetch_merged()
+        else:
+            self.rig.torch.cuda.synchronize()
+            H = self.rig.cabi.STATE_HEADER_SLOTS
+            raw = [int(x) & M64 for x in self.host.tolist()]
+            return [raw[0] if op == "count" else raw[H + k] for k, op in enumerate(self.leaf_ops)], raw[0]
+        return [s[1] for s in states], rows
+
+    def destroy(self):
+        self.pipe.destroy()
+
+
+def leaf_ops_of(exprs):
+    """Aggregator leaves in node order (post-order of each expression in turn)."""
+    import re
+    ops = []
+    for e in exprs:
+        ops += re.findall(r"\((sum|count|max|min) ", e)
+    return ops
+
+
+def timed(rig: Rig, launch, reps: int, warm: int = 2):
+    """ms per call of `launch` on this rig's stream, max over ranks; ranks enter together."""
+    for _ in range(warm):
+        launch()
+    rig.barrier()
+    a, b = rig.event(), rig.event()
+    a.record()
+    for _ in range(reps):
+        launch()
+    b.record()
+    rig.torch.cuda.synchronize()
+    return rig.reduce([a.elapsed_time(b) / reps])[0]
+
+
+def run_ours(args):
+    rig = Rig(args)
+    torch, cabi, ctx, rank, world = rig.torch, rig.cabi, rig.ctx, rig.rank, rig.world
     total = args.rows or TOTAL_ROWS
     generated = args.mode == "generated"
     begin, n = shard_of(rank, world, total)
 
     # ---- resident shard (untimed): one fill kernel writes this rank's range into HBM ----
-    col = None if generated else ctx.numbers(begin, n, stream)
+    col = None if generated else ctx.numbers(begin, n, rig.stream)
     src = cabi.make_source([] if generated else [col], n, generated=generated, begin=begin)
-    pipe = ctx.pipe(HEADLINE, aggregate=True, generated=generated)
-    state_ptr, state_bytes = pipe.state_device()
-    n_slots = state_bytes // 8
-    state_t = torch.as_tensor(DevPtr(state_ptr, n_slots), device=f"cuda:{local}")
-    gathered = torch.zeros((world, n_slots), dtype=torch.int64, device=f"cuda:{local}")
+    head = MergedPipe(rig, HEADLINE, generated, leaf_ops_of(HEADLINE))
 
-    # ---- merge point (processor_merge.rs:37-66) ----
-    # default for N > 1: fused into the aggregate kernel — its last CTA stores the state straight into every rank's gather
-    # buffer over NVLink peer memory (CUDA IPC), no collective call in the step.  --merge nccl (or an IPC failure) uses an
-    # NCCL all-gather of the same bytes after each launch instead.
-    merge = "single GPU"
-    gather_col, peer_ptrs = None, []
-    if world > 1:
-        merge = f"nccl all_gather of the {state_bytes}-byte state"
-        if args.merge == "peer":
-            try:
-                gather_col = ctx.column(cabi.U64, world * n_slots)
-                torch.as_tensor(DevPtr(gather_col.device_ptr, world * n_slots), device=f"cuda:{local}").zero_()
-                torch.cuda.synchronize()
-                handles = [None] * world
-                dist.all_gather_object(handles, ctx.ipc_export(gather_col))
-                peer_ptrs = [gather_col.device_ptr if r == rank else ctx.ipc_open(handles[r]) for r in range(world)]
-                ok = torch.ones(1, device=f"cuda:{local}")
-            except Exception as e:  # IPC not permitted in this container / no peer access: keep NCCL
-                sys.stderr.write(f"[bench] rank {rank}: peer-memory merge unavailable ({e}); using NCCL\n")
-                ok = torch.zeros(1, device=f"cuda:{local}")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
-            if ok.item() == 1:
-                pipe.set_peer_slots([ptr + rank * state_bytes for ptr in peer_ptrs])
-                gathered = torch.as_tensor(DevPtr(gather_col.device_ptr, world * n_slots), device=f"cuda:{local}").view(world, n_slots)
-                merge = f"in-kernel: the aggregate kernel's last CTA stores the {state_bytes}-byte state into every rank's gather buffer over NVLink peer memory"
-    use_nccl = world > 1 and not merge.startswith("in-kernel")
-
-    def step():
-        pipe.launch_aggregate(src, stream=stream)
-        if use_nccl:
-            dist.all_gather_into_tensor(gathered.view(-1), state_t)
-        elif world == 1:
-            gathered[0].copy_(state_t, non_blocking=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- the timed region: K complete queries ----
     for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
+        head.launch(src)
+    rig.barrier()
+    sampler = ClockSampler(rig.local)
     sampler.start()
     time.sleep(0.25)
     launches0 = ctx.launch_count
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    k_ev = [(rig.event(), rig.event()) for _ in range(args.steps)]
+    e0, e1 = rig.event(), rig.event()
+    rig.barrier()
     wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         k_ev[i][0].record()
-        pipe.launch_aggregate(src, stream=stream)
+        head.pipe.launch_aggregate(src, stream=rig.stream)
         k_ev[i][1].record()
-        if use_nccl:
-            dist.all_gather_into_tensor(gathered.view(-1), state_t)
-        elif world == 1:
-            gathered[0].copy_(state_t, non_blocking=True)
+        head.exchange()
     e1.record()
-    barrier()
+    rig.barrier()
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1)
     launches = ctx.launch_count - launches0
     ms = e0.elapsed_time(e1)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
-    t = torch.tensor([ms, kernel_ms, float(launches)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, kernel_ms, launches = tmax[0].item(), tmax[1].item(), int(tsum[2].item())
-    # ---- validity: the merged result of the last step must be the reference's answer, bit-exact ----
-    rows_raw = [[int(x) & ((1 << 64) - 1) for x in r] for r in gathered.cpu().tolist()]
-    got, exp = fold_states(rows_raw), expected(total)
-    assert got == exp, f"result mismatch: {got} != {exp}"
+    ms, kernel_ms = rig.reduce([ms, kernel_ms])
+    launches = int(rig.reduce([float(launches)], "sum")[0])
+    # ---- validity: the merged result every rank holds after the last step must be the reference's answer, bit-exact ----
+    vals, rows = head.result()
+    exp = expected(total)
+    got = {"sum": vals[0], "count": vals[1], "avg": vals[0] // vals[1], "max": vals[2], "min": vals[3]}
+    assert got == exp and rows == total, f"rank {rank}: result mismatch: {got} != {exp}"
+
+    # ---- the same kernels back to back without the cross-rank merge (what round 1 reported as the step) ----
+    no_merge = None
+    if world > 1 and rig.group is not None:
+        head.pipe.set_group(None)
+        t_ms = timed(rig, lambda: head.pipe.launch_aggregate(src, stream=rig.stream), args.steps, warm=2)
+        head.pipe.set_group(rig.group)
+        no_merge = {"ms_per_step": t_ms, "rows_per_s": total / (t_ms * 1e-3),
+                    "note": "kernels back to back, no exchange and no wait for the other ranks: NOT a complete query"}
+
+    # ---- every README query x {materialised, generated}: whole-job numbers at this N, merged result verified ----
+    per_query = {}
+    if not args.no_query_table:
+        per_query = query_table(rig, col, begin, n, total, generated)
 
     # ---- e2e: host-resident (pinned) column -> H2D chunks overlapped with the kernel -> D2H state ----
-    e2e = run_e2e(args, ctx, torch, dist, rank, world, local)
+    e2e = run_e2e(rig, col, begin, n, total, generated)
 
-    # ---- per-README-query kernel table (rank-local shard; extra information, not the headline) ----
-    per_query = {}
-    if rank == 0 and not args.no_query_table:
-        for name, exprs in README_QUERIES.items():
-            for mode in ("materialised", "generated"):
-                g = mode == "generated"
-                if g is False and generated:
-                    continue
-                p = ctx.pipe(exprs, aggregate=True, generated=g)
-                s = cabi.make_source([] if g else [col], n, generated=g, begin=begin)
-                for _ in range(2):
-                    p.launch_aggregate(s, stream=stream)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(3):
-                    p.launch_aggregate(s, stream=stream)
-                b.record()
-                torch.cuda.synchronize()
-                q_ms = a.elapsed_time(b) / 3
-                per_query.setdefault(name, {})[mode] = {"ms": round(q_ms, 4), "rows_per_s": n / (q_ms * 1e-3),
-                                                        "gb_per_s": (0 if g else 8) * n / (q_ms * 1e-3) / 1e9}
-                p.destroy()
-        # BASELINE configs[0] (the reference's own CPU-runnable case: 80 MB, fits in L2 — a latency figure, not bandwidth)
-        n0 = min(n, 10_000_000)
-        for mode in ("materialised", "generated"):
-            g = mode == "generated"
-            if g is False and generated:
-                continue
-            s0 = cabi.make_source([] if g else [col], n0, generated=g, begin=begin)
-            p = ctx.pipe([f"(sum {NUM})"], aggregate=True, generated=g)
-            per_query.setdefault("cfg0: sum(number) @1e7 (L2-resident, launch-latency bound)", {})[mode] = time_launches(
-                torch, lambda: p.launch_aggregate(s0, stream=stream), n0, 0 if g else 8)
-            p.destroy()
-        # the Source itself: fq_numbers_fill materialising 10^9 rows (numbers_stream.rs:68-83), write-only
-        if col is not None:
-            per_query["source: fill 1e9 rows"] = {"materialised": time_launches(
-                torch, lambda: ctx.fill_numbers(col, begin, min(n, 1_000_000_000), stream),
-                min(n, 1_000_000_000), 8)}
-        # BASELINE configs[1] and [2] on the first 10^9 rows of the shard
-        n2 = min(n, 1_000_000_000)
-        for mode in ("materialised", "generated"):
-            g = mode == "generated"
-            if g is False and generated:
-                continue
-            s2 = cabi.make_source([] if g else [col], n2, generated=g, begin=begin)
-            p = ctx.pipe([f"(max (+ {NUM} (u64 1)))", f"(min {NUM})", f"(count {NUM})"], aggregate=True, generated=g)
-            per_query.setdefault("cfg1: max(number+1),min(number),count(number) @1e9", {})[mode] = time_launches(
-                torch, lambda: p.launch_aggregate(s2, stream=stream), n2, 0 if g else 8)
-            p.destroy()
-            pred = f"(< (+ (+ (+ {NUM} (u64 1)) (/ {NUM} (u64 2))) (u64 1)) (u64 100))"
-            p = ctx.pipe([f"(alias c1 (+ {NUM} (u64 1)))", f"(alias c2 (/ {NUM} (u64 2)))"], predicate=pred, generated=g)
-            outs = [ctx.column(cabi.U64, 3), ctx.column(cabi.U64, 3)]
-            for early in (False, True):
-                key = "cfg2: filter+projection+limit 3 @1e9" + (" (limit early exit)" if early else " (full scan)")
-                per_query.setdefault(key, {})[mode] = time_launches(
-                    torch, lambda: p.launch_project(s2, outs, 3, limit=3, early_exit=early, stream=stream), n2, 0 if g else 8)
-            sel, written = p.fetch_project()
-            assert written == 3 and outs[0].to_numpy(3).tolist() == [1, 2, 3] and outs[1].to_numpy(3).tolist() == [0, 0, 1]
-            p.destroy()
-    barrier()
+    rig.barrier()
     sql_e2e = None
     if rank == 0 and world == 1 and not args.no_query_table:
         if col is not None:
             col.free()
             col = None
-        sql_e2e = run_sql_e2e(local, total)
+        sql_e2e = run_sql_e2e(rig.local, total)
 
     if rank == 0:
         peak, which = peaks()
@@ -418,28 +481,33 @@ def run_ours(args):
         kernel_s = kernel_ms * 1e-3
         row_bytes = 0 if generated else 8
         achieved = row_bytes * n / kernel_s / 1e9
+        cfg = common_config(total)
         out = {
             "metric": "rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": value / (TOTAL_ROWS / README_PUBLISHED_SECONDS), "dtype": "u64", "data": "synthetic",
-            "config": {"workload": HEADLINE_SQL if total == TOTAL_ROWS else HEADLINE_SQL.replace("10000000000", str(total)),
-                       "rows_total": total, "rows_per_gpu": n, "source": args.mode,
-                       "partitioning": f"{8 // world if world <= 8 else 1} of the reference's 8 partitions per GPU",
-                       "host_affinity": numa,
-                       "l2": "inputs (>= 10 GB per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "merge": merge,
-                       "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
+            "config": cfg,
+            "setup": {"rows_per_gpu": n, "source": args.mode,
+                      "partitioning": f"{8 // world if world <= 8 else 1} of the reference's 8 partitions per GPU",
+                      "host_affinity": rig.affinity,
+                      "l2": "inputs (>= 10 GB per GPU) are far larger than the 126 MB L2; no flush needed",
+                      "merge": rig.merge,
+                      "step": "one complete query: every rank's kernel + the cross-rank merge; each rank holds the merged state when its kernel ends",
+                      "vs_baseline_ref": "README.md:62 FuseQuery 6.40 s for this query on an 8 vCPU KVM instance"},
             "hbm_gb_per_s": row_bytes * total * args.steps / secs / 1e9,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(n, generated),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(n, generated),
                          "kernel": agg_kernel_name(generated), "kernel_ms": kernel_ms, "peak_source": which,
-                         "algorithmic_bytes_per_launch": row_bytes * n},
+                         "algorithmic_bytes_per_launch": row_bytes * n,
+                         "note": "kernel_ms includes the in-kernel wait for the slowest rank when N > 1"},
+            "throughput_no_merge": no_merge,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "sql_e2e": sql_e2e,
         }
         if world == 1 and not args.no_cpu_baseline:
-            rows = cpu_sample_rows()
-            secs_cpu, _ = cpu_reference_run(rows)
-            out["cpu_baseline"] = {"value": rows / secs_cpu, "unit": "rows/s", "cores": min(8, os.cpu_count() or 1), "kind": "port",
-                                   "sample": f"{rows} rows of the same query through the oracle's reference-shaped pipeline "
+            rows_cpu = cpu_sample_rows()
+            secs_cpu, _ = cpu_reference_run(rows_cpu)
+            out["cpu_baseline"] = {"value": rows_cpu / secs_cpu, "unit": "rows/s", "cores": min(8, os.cpu_count() or 1), "kind": "port",
+                                   "sample": f"{rows_cpu} rows of the same query through the oracle's reference-shaped pipeline "
                                              f"(8 partitions, 10 000-row blocks, one pass per aggregate), {secs_cpu:.2f} s; cpu: {cpu_model()}"}
             # the best a CPU could do with this query, NOT the reference's structure: one fused pass per
             # thread over numbers generated in registers, all host threads.  Reported beside the baseline, not as it.
@@ -447,33 +515,117 @@ def run_ours(args):
             nthreads = os.cpu_count() or 1
             _o.fused_headline(1_000_000_000, nthreads)
             secs_best, res_best = _o.fused_headline(TOTAL_ROWS, nthreads)
-            assert res_best == [(TOTAL_ROWS * (TOTAL_ROWS - 1) // 2) % (1 << 64), TOTAL_ROWS, TOTAL_ROWS - 1, 0], res_best
+            assert res_best == [_sum(TOTAL_ROWS), TOTAL_ROWS, TOTAL_ROWS - 1, 0], res_best
             out["cpu_baseline"]["best_case_fused"] = {"value": TOTAL_ROWS / secs_best, "unit": "rows/s", "cores": nthreads,
                                                       "note": "hand-fused single pass, generated in registers, vectorised by gcc -O3 -march=native; "
                                                               "compare with per_query[...]['generated'], not with the materialised scan"}
         print(json.dumps(out), flush=True)
+    rig.barrier()
+    head.destroy()
+    if rig.group is not None:
+        rig.group.destroy()
     if world > 1:
-        if peer_ptrs:   # nobody may unmap a gather buffer while a peer could still store into it
-            pipe.set_peer_slots([])
-            barrier()
-            for r, ptr in enumerate(peer_ptrs):
-                if r != rank:
-                    ctx.ipc_close(ptr)
-            barrier()
-        dist.destroy_process_group()
+        rig.dist.destroy_process_group()
 
 
-def time_launches(torch, launch, rows, row_bytes, reps=3):
-    for _ in range(2):
-        launch()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        launch()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / reps
-    return {"ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3), "gb_per_s": row_bytes * rows / (ms * 1e-3) / 1e9}
+def query_table(rig: Rig, col, begin, n, total, generated_only):
+    """Whole-job time of every README query (and BASELINE configs 0-2) at this N: all ranks launch together, the launch ends
+    with the merged state on every rank, max over ranks, result asserted against the closed form on EVERY rank."""
+    cabi, ctx, world, rank = rig.cabi, rig.ctx, rig.world, rig.rank
+    per_query = {}
+    reps = 3
+
+    def record(name, mode, ms, rows, nbytes, extra=None):
+        d = {"ms": round(ms, 4), "rows_per_s": rows / (ms * 1e-3), "gb_per_s": (nbytes / (ms * 1e-3) / 1e9) if nbytes else None,
+             "verified": True, "n_gpus": world}
+        if extra:
+            d.update(extra)
+        per_query.setdefault(name, {})[mode] = d
+
+    for name, (exprs, want, readme_s, note) in README_QUERIES.items():
+        for mode in ("materialised", "generated"):
+            g = mode == "generated"
+            if not g and generated_only:
+                continue
+            mp = MergedPipe(rig, exprs, g, leaf_ops_of(exprs))
+            s = cabi.make_source([] if g else [col], n, generated=g, begin=begin)
+            ms = timed(rig, lambda: mp.launch(s), reps)
+            vals, rows = mp.result()
+            assert rows == total and vals == want(total), f"rank {rank}: {name} [{mode}]: {vals} != {want(total)}"
+            reads = (not g) and not name.startswith("count(number)") or (not g and "honest" in name)
+            extra = {"readme_seconds_8vcpu": readme_s}
+            if note:
+                extra["note"] = note
+            record(name, mode, ms, total, 8 * total if reads else 0, extra)
+            mp.destroy()
+
+    # BASELINE configs[0] (the reference's own CPU-runnable case: 80 MB per job, L2-resident — a latency figure, not bandwidth)
+    t0 = 10_000_000
+    b0, n0 = shard_of(rank, world, t0)
+    for mode in ("materialised", "generated"):
+        g = mode == "generated"
+        if not g and generated_only:
+            continue
+        if not g:
+            ctx.fill_numbers(col, b0, n0, rig.stream)
+        mp = MergedPipe(rig, [f"(sum {NUM})"], g, ["sum"])
+        s0 = cabi.make_source([] if g else [col], n0, generated=g, begin=b0)
+        ms = timed(rig, lambda: mp.launch(s0), 20, warm=5)
+        vals, rows = mp.result()
+        assert rows == t0 and vals == [_sum(t0)], (vals, rows)
+        record("cfg0: sum(number) @1e7", mode, ms, t0, 0, {"note": "80 MB per job: L2-resident and launch-latency bound; no bandwidth claim"})
+        mp.destroy()
+
+    # BASELINE configs[1] and [2] over numbers_mt(10^9), sharded like the headline
+    t2 = min(total, 1_000_000_000)
+    b2, n2 = shard_of(rank, world, t2)
+    if col is not None:
+        ctx.fill_numbers(col, b2, n2, rig.stream)      # this rank's shard of numbers_mt(10^9) (overwrites the head of the column)
+        ms = timed(rig, lambda: ctx.fill_numbers(col, b2, n2, rig.stream), reps)
+        record("source: fill numbers_mt(1e9)", "materialised", ms, t2, 8 * t2, {"note": "fq_fill_numbers, write-only"})
+    for mode in ("materialised", "generated"):
+        g = mode == "generated"
+        if not g and generated_only:
+            continue
+        s2 = cabi.make_source([] if g else [col], n2, generated=g, begin=b2)
+        mp = MergedPipe(rig, CFG1, g, leaf_ops_of(CFG1))
+        ms = timed(rig, lambda: mp.launch(s2), reps)
+        vals, rows = mp.result()
+        assert rows == t2 and vals == [t2, 0, t2], (vals, rows)
+        record("cfg1: max(number+1),min(number),count(number) @1e9", mode, ms, t2, 0 if g else 8 * t2)
+        mp.destroy()
+
+        # cfg2: every rank filters + projects its shard with LIMIT 3; the rows of all ranks meet in rank order and are cut
+        # at LIMIT 3 again (pipeline_builder.rs:31-41) — on the device, over the group's windows, when there is one
+        p = ctx.pipe(CFG2_PROJ, predicate=CFG2_PRED, generated=g)
+        outs = [ctx.column(cabi.U64, 3), ctx.column(cabi.U64, 3)]
+        fin = [ctx.column(cabi.U64, 3 * world), ctx.column(cabi.U64, 3 * world)]
+        for early in (False, True):
+            def one():
+                p.launch_project(s2, outs, 3, limit=3, early_exit=early, stream=rig.stream)
+                if rig.group is not None:
+                    rig.group.gather_project(p, outs, fin, limit=3, stream=rig.stream)
+            ms = timed(rig, one, reps)
+            if rig.group is not None:
+                sel, nfin = rig.group.fetch_gather()
+                rows_out = list(zip(fin[0].to_numpy(nfin).tolist(), fin[1].to_numpy(nfin).tolist()))
+            else:
+                sel, written = p.fetch_project()
+                mine = list(zip(outs[0].to_numpy(written).tolist(), outs[1].to_numpy(written).tolist()))
+                if world > 1:
+                    allrows = [None] * world
+                    rig.dist.all_gather_object(allrows, (sel, mine))
+                    sel, rows_out = sum(a for a, _ in allrows), [r for _, rr in allrows for r in rr][:3]
+                else:
+                    rows_out = mine
+            assert rows_out == [(1, 0), (2, 0), (3, 1)] and (early or sel == 66), (rows_out, sel)
+            key = "cfg2: filter+projection+limit 3 @1e9" + (" (limit early exit)" if early else " (full scan)")
+            record(key, mode, ms, t2, 0 if (g or early) else 8 * t2,
+                   {"note": "early exit: the scan stops once LIMIT rows were found; rows/s counts rows of the table, not rows read"} if early else None)
+        p.destroy()
+        for c in outs + fin:
+            c.free()
+    return per_query
 
 
 def run_sql_e2e(device, total):
@@ -503,35 +655,68 @@ def run_sql_e2e(device, total):
     return out
 
 
-def run_e2e(args, ctx, torch, dist, rank, world, local):
-    """Same query, inputs in HOST memory: each step copies this rank's share of an `e2e_rows`-row column
-    from pinned memory in chunks (double-buffered against the kernel, which folds chunk after chunk into
-    the running state) and reads the state (80 bytes) back."""
+def run_e2e(rig: Rig, col, begin_full, n_full, total_full, generated):
+    """Same query, inputs in HOST memory: each step copies this rank's share of the column from pinned memory in chunks
+    (double-buffered against the kernel, which folds chunk after chunk into the running state; the last chunk's launch
+    ends with the cross-rank merge) and reads the merged state back.  Also measured: the plain cudaMemcpyAsync rate of the
+    very same copies without any kernel, on all ranks at once — the roofline of this leg."""
     import ctypes as C
 
     import numpy as np
-    from fuse_query_b200 import cabi
+    args, torch, cabi, ctx, world, rank = rig.args, rig.torch, rig.cabi, rig.ctx, rig.world, rig.rank
     L = cabi.lib()
-    total = args.e2e_rows
-    begin, n = shard_of(rank, world, total)
+    # the headline's 10^10 rows when the host can pin them (80 GB at N=1), else --e2e-rows
+    total = args.e2e_rows or total_full
+    why = None
+    avail = -rig.reduce([-float(mem_available_bytes())])[0]      # min over ranks (they share the host)
+    if not args.e2e_rows and (8 * total * 1.25 + (24 << 30) > avail or generated):
+        total, why = min(total_full, 1_000_000_000), f"host MemAvailable {avail / 2**30:.0f} GiB cannot pin {8 * total_full / 2**30:.0f} GiB safely"
     hp = C.c_void_p()
-    ctx.check(L.fq_host_alloc(ctx._h, n * 8, C.byref(hp)))
-    host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(n,))
-    step = 1 << 24
-    for i in range(0, n, step):  # the host-side DataBlocks of the reference (numbers_stream.rs:68-83)
-        host[i:i + step] = np.arange(begin + i, begin + min(n, i + step), dtype=np.uint64)
-    chunk = min(n, args.e2e_chunk_rows)
+    while True:
+        begin, n = shard_of(rank, world, total)
+        t_pin = time.time()
+        ok = 1.0
+        try:
+            ctx.check(L.fq_host_alloc(ctx._h, max(n, 1) * 8, C.byref(hp)))
+        except cabi.FuseGpuError as e:
+            ok, why = 0.0, f"pinning {8 * n / 2**30:.0f} GiB failed ({e})"
+        t_pin = time.time() - t_pin
+        if -rig.reduce([-ok])[0] == 1.0:
+            break
+        if ok:
+            L.fq_host_free(ctx._h, hp)
+        if total <= 1_000_000_000:
+            raise SystemExit("cannot pin host memory for the e2e leg")
+        total = 1_000_000_000
+    # the host-side DataBlocks of the reference (numbers_stream.rs:68-83): written by D2H copies of the resident column where
+    # it holds exactly these numbers (fast), else by numpy
+    if col is not None and (begin, n) == (begin_full, n_full):
+        ctx.fill_numbers(col, begin, n, rig.stream)   # query_table may have overwritten the head of the column
+        step_rows = 1 << 27
+        for i in range(0, n, step_rows):
+            m = min(step_rows, n - i)
+            ctx.check(L.fq_column_download(ctx._h, col._h, i, C.c_void_p(hp.value + i * 8), m, C.c_void_p(rig.stream)))
+        ctx.synchronize(rig.stream)
+    else:
+        host = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint64)), shape=(max(n, 1),))
+        step_rows = 1 << 24
+        for i in range(0, n, step_rows):
+            host[i:i + step_rows] = np.arange(begin + i, begin + min(n, i + step_rows), dtype=np.uint64)
+    chunk = max(1, min(n, args.e2e_chunk_rows))
     bufs = [ctx.column(cabi.U64, chunk), ctx.column(cabi.U64, chunk)]
-    pipe = ctx.pipe(HEADLINE, aggregate=True)
+    mp = MergedPipe(rig, HEADLINE, False, leaf_ops_of(HEADLINE))
+    pipe = mp.pipe
+    if rig.group is not None:
+        pipe.set_group(None)      # only the last chunk's launch of a step merges across ranks
     state_bytes = pipe.state_device()[1]
     copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
     free_ev = [torch.cuda.Event(), torch.cuda.Event()]
     full_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    h2d = d2h = 0
+    n_chunks = (n + chunk - 1) // chunk
+    counts = {"h2d": 0, "d2h": 0}
 
-    def one():
-        nonlocal h2d, d2h
-        h2d = d2h = 0
+    def one(with_kernel=True):
+        counts["h2d"] = counts["d2h"] = 0
         k = 0
         for off in range(0, n, chunk):
             m = min(chunk, n - off)
@@ -539,43 +724,69 @@ def run_e2e(args, ctx, torch, dist, rank, world, local):
             copy_s.wait_event(free_ev[b])
             ctx.check(L.fq_column_upload(ctx._h, bufs[b]._h, 0, C.c_void_p(hp.value + off * 8), m, C.c_void_p(copy_s.cuda_stream)))
             full_ev[b].record(copy_s)
-            comp_s.wait_event(full_ev[b])
-            pipe.launch_aggregate(cabi.make_source([bufs[b]], m), accumulate=k > 0, stream=comp_s.cuda_stream)
-            free_ev[b].record(comp_s)
-            h2d += m * 8
-            d2h += state_bytes   # every launch queues the D2H copy of the running state behind the kernel
+            counts["h2d"] += m * 8
+            if with_kernel:
+                comp_s.wait_event(full_ev[b])
+                last = k == n_chunks - 1
+                if last and rig.group is not None:
+                    pipe.set_group(rig.group)
+                pipe.launch_aggregate(cabi.make_source([bufs[b]], m), accumulate=k > 0, stream=comp_s.cuda_stream)
+                if last and rig.group is not None:
+                    pipe.set_group(None)
+                free_ev[b].record(comp_s)
+                counts["d2h"] += state_bytes * (2 if last and rig.group is not None else 1)   # every launch queues the D2H of its state
+            else:
+                free_ev[b].record(copy_s)
             k += 1
-        return pipe.fetch_aggregate()  # waits for the last launch, D2H of the state
+        if not with_kernel:
+            copy_s.synchronize()
+            return None
+        if rig.group is not None:
+            return pipe.fetch_merged()
+        return pipe.fetch_aggregate()   # waits for the last launch, D2H of the state
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def measure(with_kernel, steps):
+        for _ in range(2 if with_kernel else 1):
+            one(with_kernel)
+        rig.barrier()
+        t0 = time.time()
+        for _ in range(steps):
+            res = one(with_kernel)
         torch.cuda.synchronize()
+        mine = time.time() - t0
+        rig.barrier()
+        return res, mine
 
-    for _ in range(2):
-        one()
-    barrier()
-    t0 = time.time()
-    for _ in range(args.e2e_steps):
-        states, rows = one()
-    barrier()
-    dt = time.time() - t0
-    t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        dt, h2d, d2h = tm[0].item(), ts[1].item(), ts[2].item()
+    res, dt_mine = measure(True, args.e2e_steps)
+    h2d, d2h = counts["h2d"], counts["d2h"]
+    dt = rig.reduce([dt_mine])[0]
+    h2d_all, d2h_all = rig.reduce([float(h2d), float(d2h)], "sum")
+    states, rows = res
     vals = [s[1] for s in states]
-    lo, hi = begin, begin + n - 1
-    assert rows == n and vals == [((lo + hi) * n // 2) % (1 << 64), n, hi, lo], (vals, rows)
+    if rig.group is not None or world == 1:
+        assert rows == total and vals == [_sum(total), total, total - 1, 0], (vals, rows)
+    else:
+        assert rows == n and vals == [_sum(n, begin), n, begin + n - 1, begin], (vals, rows)
+    # roofline of the leg: the same pinned -> device copies, one plain cudaMemcpyAsync per chunk, no kernel, all ranks at once
+    _, roof_mine = measure(False, args.e2e_steps)
+    roof_dt = rig.reduce([roof_mine])[0]
+    per_rank = [0.0] * world
+    per_rank[rank] = 8 * n * args.e2e_steps / roof_mine / 1e9
+    per_rank = rig.reduce(per_rank, "sum")
     for b in bufs:
         b.free()
-    pipe.destroy()
+    mp.destroy()
     L.fq_host_free(ctx._h, hp)
-    return {"value": total * args.e2e_steps / dt, "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "rows_per_step": total, "ms_per_step": 1e3 * dt / args.e2e_steps,
+    value = total * args.e2e_steps / dt
+    roof_gbs = 8 * total * args.e2e_steps / roof_dt / 1e9
+    return {"value": value, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+            "rows_per_step": total, "ms_per_step": 1e3 * dt / args.e2e_steps, "h2d_gb_per_s": 8 * value / 1e9,
+            "chunk_rows": chunk, "pinned_alloc_s": round(t_pin, 2),
+            "roofline": {"bound": "pcie", "achieved": 8 * value / 1e9, "peak": roof_gbs, "unit": "GB/s", "frac": 8 * value / 1e9 / roof_gbs,
+                         "per_gpu_gb_per_s": [round(x, 2) for x in per_rank],
+                         "how": "the same chunks copied pinned -> device with one cudaMemcpyAsync each (fq_column_upload), no kernel, "
+                                "all ranks concurrently; aggregate = bytes of all ranks / slowest rank's time"},
+            "rows_note": why or "the headline's own table (same_config)",
             "note": "host-resident UInt64 column in pinned memory, chunked H2D overlapped with the kernel; PCIe-bound"}
 
 
@@ -588,7 +799,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the 10^10-row workload (debug)")
     ap.add_argument("--mode", default="materialised", choices=["materialised", "generated"])
     ap.add_argument("--merge", choices=["peer", "nccl"], default="peer", help="N > 1: how the per-rank states meet")
-    ap.add_argument("--e2e-rows", type=int, default=1_000_000_000)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the host-buffer leg (default: the workload's, if the host can pin them)")
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 25)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

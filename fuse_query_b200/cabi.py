@@ -69,7 +69,9 @@ EXPORTS = [
     "fq_abi_version", "fq_ctx_create", "fq_ctx_destroy", "fq_last_error", "fq_ctx_launch_count", "fq_ctx_sm_count",
     "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free",
     "fq_column_upload_bits", "fq_column_download_bits",
-    "fq_ipc_export", "fq_ipc_open", "fq_ipc_close", "fq_pipe_set_peer_slots", "fq_column_dtype", "fq_column_len",
+    "fq_group_create", "fq_group_handle", "fq_group_window", "fq_group_connect", "fq_group_connect_ptrs", "fq_group_destroy",
+    "fq_pipe_set_group", "fq_pipe_fetch_merged", "fq_group_gather_project", "fq_group_fetch_gather", "fq_pipe_set_variant",
+    "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_build_kind", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
@@ -101,10 +103,17 @@ def lib():
         "fq_column_set_validity": (i32, [vp, vp, vp]),
         "fq_column_validity": (vp, [vp]),
         "fq_column_free": (None, [vp, vp]),
-        "fq_ipc_export": (i32, [vp, vp, vp]),
-        "fq_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
-        "fq_ipc_close": (i32, [vp, vp]),
-        "fq_pipe_set_peer_slots": (i32, [vp, vp, C.POINTER(vp), i32]),
+        "fq_group_create": (i32, [vp, i32, i32, u64, C.POINTER(vp)]),
+        "fq_group_handle": (i32, [vp, vp, vp]),
+        "fq_group_window": (i32, [vp, vp, C.POINTER(vp), C.POINTER(u64)]),
+        "fq_group_connect": (i32, [vp, vp, vp]),
+        "fq_group_connect_ptrs": (i32, [vp, vp, C.POINTER(vp)]),
+        "fq_group_destroy": (None, [vp, vp]),
+        "fq_pipe_set_group": (i32, [vp, vp, vp]),
+        "fq_pipe_fetch_merged": (i32, [vp, vp, C.POINTER(CValue), i32, C.POINTER(i32), C.POINTER(u64)]),
+        "fq_group_gather_project": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, vp]),
+        "fq_group_fetch_gather": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+        "fq_pipe_set_variant": (i32, [vp, vp, C.c_char_p]),
         "fq_column_upload_bits": (i32, [vp, vp, u64, vp, u64, u64, vp]),
         "fq_column_download_bits": (i32, [vp, vp, u64, vp, u64, vp]),
         "fq_column_dtype": (i32, [vp]),
@@ -260,20 +269,11 @@ class Context:
         self.check(lib().fq_numbers_fill(self._h, col._h, 0, begin, n, C.c_void_p(stream)))
         return col
 
-    def ipc_export(self, col: "Column") -> bytes:
-        """64-byte CUDA IPC handle of a column's buffer (to be sent to the peer processes)."""
-        buf = C.create_string_buffer(64)
-        self.check(lib().fq_ipc_export(self._h, col._h, buf))
-        return buf.raw
-
-    def ipc_open(self, handle: bytes) -> int:
-        """Device address, in this process, of a peer's exported buffer."""
-        out = C.c_void_p()
-        self.check(lib().fq_ipc_open(self._h, C.c_char_p(handle), C.byref(out)))
-        return out.value
-
-    def ipc_close(self, ptr: int) -> None:
-        self.check(lib().fq_ipc_close(self._h, C.c_void_p(ptr)))
+    def group(self, rank: int, world: int, row_bytes: int = 1 << 16) -> "Group":
+        """This rank's end of the cross-GPU merge point (exchange window in this GPU's memory)."""
+        h = C.c_void_p()
+        self.check(lib().fq_group_create(self._h, rank, world, row_bytes, C.byref(h)))
+        return Group(self, h, rank, world)
 
     def from_bitmap(self, bits, n: int, bit_offset: int = 0, stream: int = 0) -> "Column":
         """Boolean column (values or validity) from an Arrow LSB-first bitmap (bytes / numpy uint8), expanded on the device."""
@@ -397,6 +397,56 @@ class Column:
         return out
 
 
+class Group:
+    """fq_group: the merge point across GPUs over peer memory (one process per GPU; see include/fuse_gpu.h)."""
+
+    def __init__(self, ctx: Context, h, rank: int, world: int):
+        self.ctx, self._h, self.rank, self.world = ctx, h, rank, world
+
+    def handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's window (to be sent to the peer processes)."""
+        buf = C.create_string_buffer(64)
+        self.ctx.check(lib().fq_group_handle(self.ctx._h, self._h, buf))
+        return buf.raw
+
+    @property
+    def window(self) -> int:
+        p, n = C.c_void_p(), C.c_uint64()
+        self.ctx.check(lib().fq_group_window(self.ctx._h, self._h, C.byref(p), C.byref(n)))
+        return p.value
+
+    def connect(self, handles: Sequence[bytes]) -> None:
+        """handles[r] = rank r's handle() (own entry ignored)."""
+        blob = b"".join(bytes(h).ljust(64, b"\0")[:64] for h in handles)
+        self.ctx.check(lib().fq_group_connect(self.ctx._h, self._h, C.c_char_p(blob)))
+
+    def connect_ptrs(self, windows: Sequence[int]) -> None:
+        """Ranks living in one process: the device addresses of every rank's window."""
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(w) for w in windows])
+        self.ctx.check(lib().fq_group_connect_ptrs(self.ctx._h, self._h, arr))
+
+    def gather_project(self, pipe: "Pipe", local_cols: Sequence[Column], final_cols: Sequence[Column], *, limit: int = -1,
+                       local_valid: Optional[Sequence[Optional[Column]]] = None,
+                       final_valid: Optional[Sequence[Optional[Column]]] = None, stream: int = 0) -> None:
+        def arr(cols):
+            if cols is None:
+                return None
+            return (C.c_void_p * max(1, len(cols)))(*[None if c is None else c._h for c in cols])
+        self.ctx.check(lib().fq_group_gather_project(self.ctx._h, self._h, pipe._h, arr(local_cols), arr(local_valid), arr(final_cols),
+                                                      arr(final_valid), limit, C.c_void_p(stream)))
+
+    def fetch_gather(self) -> Tuple[int, int]:
+        """-> (rows selected by all ranks, rows in the final columns)"""
+        sel, fin = C.c_uint64(), C.c_uint64()
+        self.ctx.check(lib().fq_group_fetch_gather(self.ctx._h, self._h, C.byref(sel), C.byref(fin)))
+        return sel.value, fin.value
+
+    def destroy(self):
+        if self._h:
+            lib().fq_group_destroy(self.ctx._h, self._h)
+            self._h = None
+
+
 def make_source(cols: Sequence[Column], n_rows: int, *, generated: bool = False, begin: int = 0):
     arr = (C.c_void_p * max(1, len(cols)))(*[c._h for c in cols])
     s = Source()
@@ -432,10 +482,13 @@ class Pipe:
     def source(self) -> str:
         return lib().fq_pipe_source(self._h).decode()
 
-    def set_peer_slots(self, slots: Sequence[int]) -> None:
-        """Aggregate launches end by storing the running state to these device addresses (peer GPUs' gather rows)."""
-        arr = (C.c_void_p * max(1, len(slots)))(*[C.c_void_p(x) for x in slots])
-        self.ctx.check(lib().fq_pipe_set_peer_slots(self.ctx._h, self._h, arr, len(slots)))
+    def set_group(self, group: Optional["Group"]) -> None:
+        """Aggregate launches end with the in-kernel merge across the group's ranks (fetch_merged reads it)."""
+        self.ctx.check(lib().fq_pipe_set_group(self.ctx._h, self._h, group._h if group is not None else None))
+
+    def set_variant(self, variant: str) -> None:
+        """Kernel variant for the next launches: "tma" | "u4" | "u8" (aggregate), "tma" | "ldg" (select / projection)."""
+        self.ctx.check(lib().fq_pipe_set_variant(self.ctx._h, self._h, variant.encode()))
 
     def expr_nullable(self, i: int) -> bool:
         out = C.c_int32()
@@ -469,11 +522,16 @@ class Pipe:
         self.ctx.check(lib().fq_pipe_fetch_block_stats(self.ctx._h, self._h, C.byref(b), C.byref(e)))
         return b.value, e.value
 
-    def fetch_aggregate(self):
+    def fetch_merged(self):
+        """fetch_aggregate for the state merged over every rank of the pipe's group by the last launch."""
+        return self.fetch_aggregate(merged=True)
+
+    def fetch_aggregate(self, merged: bool = False):
         """-> (list of (dtype, value|None) per Aggregator leaf, or None for DataValue::Null; rows_selected)"""
         vals = (CValue * 64)()
         n, rows = C.c_int32(), C.c_uint64()
-        self.ctx.check(lib().fq_pipe_fetch_aggregate(self.ctx._h, self._h, vals, 64, C.byref(n), C.byref(rows)))
+        fetch = lib().fq_pipe_fetch_merged if merged else lib().fq_pipe_fetch_aggregate
+        self.ctx.check(fetch(self.ctx._h, self._h, vals, 64, C.byref(n), C.byref(rows)))
         out = []
         for i in range(n.value):
             v = vals[i]

@@ -211,14 +211,31 @@ struct fq_column {
   bool owns_validity = false;
 };
 
+// Exchange windows of a group of ranks (one process per GPU): the merge point across GPUs (processor_merge.rs:37-66).
+struct fq_group {
+  int rank = 0, world = 1;
+  uint32_t row_slots = 0;          // 8-byte slots per (parity, writer) row, slot 0 = epoch
+  uint64_t *window = nullptr;      // local: 2 * world * row_slots slots
+  uint64_t *windows[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ipc_opened[8] = {false, false, false, false, false, false, false, false};
+  bool connected = false;
+  uint64_t epoch = 0;              // one per group operation; every rank issues the same sequence of operations
+  uint64_t timeout_ns = 20ull * 1000 * 1000 * 1000;
+  uint64_t *d_result = nullptr, *h_result = nullptr;   // gather: [0] rows selected by all ranks, [1] final rows, [2] error bits
+  cudaEvent_t ev = nullptr;
+  bool gathered = false;
+};
+
 struct fq_pipe {
   fq::Generated gen;
   Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
   int build_kind = 0;   // 0 precompiled, 1 NVRTC in this process, 2 on-disk JIT cache
-  void *peer_slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int n_peers = 0;
+  std::string variant;  // kernel variant the launches prefer: FQ_{AGG,SEL,MAP}_VARIANT when the pipe was compiled, or fq_pipe_set_variant
+  fq_group *group = nullptr;   // aggregate launches end with the in-kernel cross-GPU merge when set
+  uint64_t *d_merged = nullptr, *h_merged = nullptr;
+  bool launched_merged = false;
   bool precompiled = false;
   int n_slots = 0;          // FQ_STATE_HDR + leaves
   uint64_t *d_state = nullptr, *d_partials = nullptr, *d_ctl = nullptr, *d_tiles = nullptr;
@@ -444,6 +461,16 @@ fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_param
     }
   }
   return FQ_OK;
+}
+
+// every group operation takes the next epoch; all ranks issue the same sequence of operations (like a communicator)
+void bind_group(fq_group *g, fq_launch_params *p) {
+  for (int r = 0; r < g->world; r++) p->group_windows[r] = (fq_u64 *)g->windows[r];
+  p->group_epoch = ++g->epoch;
+  p->group_timeout_ns = g->timeout_ns;
+  p->group_rank = (fq_u32)g->rank;
+  p->group_world = (fq_u32)g->world;
+  p->group_row_slots = g->row_slots;
 }
 
 }  // namespace
@@ -758,7 +785,23 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     if (s2) { delete pipe; return s2; }
   }
   pipe->n_slots = FQ_STATE_HDR + gen.n_slots;
+  {
+    // the environment is read here, once per pipe — never on the launch path
+    const char *name = gen.kind == FQ_PIPE_AGGREGATE ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT";
+    const char *dflt = gen.kind == FQ_PIPE_AGGREGATE ? FQ_AGG_DEFAULT_VARIANT : gen.has_pred ? FQ_SEL_DEFAULT_VARIANT : FQ_MAP_DEFAULT_VARIANT;
+    const char *v = getenv(name);
+    pipe->variant = v ? v : dflt;
+    if (!v && gen.kind == FQ_PIPE_AGGREGATE && getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8) pipe->variant = "u8";
+  }
   cudaError_t e = cudaMalloc(&pipe->d_state, sizeof(uint64_t) * pipe->n_slots);
+  if (e == cudaSuccess && gen.kind == FQ_PIPE_AGGREGATE) {
+    // one partial row per CTA of the largest persistent grid any variant can launch: no allocation on the launch path
+    int bps = 1;
+    for (const Kernel *k : {&pipe->k_agg_u4, &pipe->k_agg_u8, &pipe->k_agg_tma})
+      if (k->valid()) bps = std::max(bps, k->blocks_per_sm);
+    pipe->partials_cap = ctx->sm_count * bps;
+    e = cudaMalloc(&pipe->d_partials, sizeof(uint64_t) * pipe->n_slots * pipe->partials_cap);
+  }
   if (e == cudaSuccess) e = cudaMemset(pipe->d_state, 0, sizeof(uint64_t) * pipe->n_slots);
   if (e == cudaSuccess) e = cudaMalloc(&pipe->d_ctl, 64);
   if (e == cudaSuccess) e = cudaMemset(pipe->d_ctl, 0, 64);
@@ -783,12 +826,22 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
   cudaFree(pipe->d_ctl);
   cudaFree(pipe->d_tiles);
   cudaFree(pipe->d_blocks);
+  cudaFree(pipe->d_merged);
+  if (pipe->h_merged) cudaFreeHost(pipe->h_merged);
   if (pipe->h_state) cudaFreeHost(pipe->h_state);
   if (pipe->h_result) cudaFreeHost(pipe->h_result);
   if (pipe->ev) cudaEventDestroy(pipe->ev);
   delete pipe;
 }
 
+fq_status fq_pipe_set_variant(fq_ctx *, fq_pipe *pipe, const char *variant) {
+  if (!pipe || !variant) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  const std::string v = variant;
+  const bool ok = pipe->gen.kind == FQ_PIPE_AGGREGATE ? (v == "tma" || v == "u4" || v == "u8") : (v == "tma" || v == "ldg");
+  if (!ok) return set_err(FQ_ERR_INVALID, "Internal Error: unknown kernel variant %s", variant);
+  pipe->variant = v;
+  return FQ_OK;
+}
 int32_t fq_pipe_is_precompiled(const fq_pipe *pipe) { return pipe && pipe->precompiled; }
 int32_t fq_pipe_build_kind(const fq_pipe *pipe) { return pipe ? pipe->build_kind : 0; }
 const char *fq_pipe_source(const fq_pipe *pipe) { return pipe ? pipe->gen.source.c_str() : ""; }
@@ -825,8 +878,8 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   fq_launch_params p;
   memset(&p, 0, sizeof p);
   if (fq_status st = bind_source(pipe, src, &p)) return st;
-  // kernel variant: FQ_AGG_VARIANT = tma (default: bulk-copy staged; needs every referenced column materialised) | u4 | u8
-  const std::string variant = getenv("FQ_AGG_VARIANT") ? getenv("FQ_AGG_VARIANT") : (getenv("FQ_AGG_UNROLL") && atoi(getenv("FQ_AGG_UNROLL")) == 8 ? "u8" : FQ_AGG_DEFAULT_VARIANT);
+  // kernel variant: chosen when the pipe was compiled (FQ_AGG_VARIANT) or by fq_pipe_set_variant
+  const std::string &variant = pipe->variant;
   // the preferred variant when the module holds it, else whichever it was built with
   const bool use_tma = (variant == "tma" && pipe->k_agg_tma.valid()) || (!pipe->k_agg_u4.valid() && !pipe->k_agg_u8.valid());
   const bool want_u8 = (variant == "u8" && pipe->k_agg_u8.valid()) || (!use_tma && !pipe->k_agg_u4.valid());
@@ -839,20 +892,18 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   static const int bps_env = getenv("FQ_AGG_BLOCKS_PER_SM") ? atoi(getenv("FQ_AGG_BLOCKS_PER_SM")) : 0;
   const int bps = bps_env > 0 ? std::min(bps_env, k.blocks_per_sm) : k.blocks_per_sm;
   unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * bps, chunks));
-  if ((int)grid > pipe->partials_cap) {
-    cudaFree(pipe->d_partials);
-    pipe->d_partials = nullptr;
-    int cap = std::max<int>((int)grid, ctx->sm_count * k.blocks_per_sm);
-    CUDA_TRY(cudaMalloc(&pipe->d_partials, sizeof(uint64_t) * pipe->n_slots * cap));
-    pipe->partials_cap = cap;
-  }
+  if ((int)grid > pipe->partials_cap) return set_err(FQ_ERR_INTERNAL, "Internal Error: grid of %u CTAs exceeds the pipe's %d partial rows", grid, pipe->partials_cap);
   p.partials = (fq_u64 *)pipe->d_partials;
   p.state = (fq_u64 *)pipe->d_state;
   p.ticket = (fq_u32 *)(pipe->d_ctl + 4);
   p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
   p.stages = pipe->tma_stages;
-  p.n_peers = (fq_u32)pipe->n_peers;
-  for (int r = 0; r < pipe->n_peers; r++) p.peer_slots[r] = (fq_u64 *)pipe->peer_slots[r];
+  if (fq_group *g = pipe->group) {
+    if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the pipe's group is not connected to its peers");
+    if ((uint32_t)pipe->n_slots + 1 > g->row_slots) return set_err(FQ_ERR_INVALID, "Internal Error: group rows are too small for this pipe's state");
+    bind_group(g, &p);
+    p.merged = (fq_u64 *)pipe->d_merged;
+  }
   if ((flags & FQ_RUN_BLOCK_STATS) && pipe->gen.track_blocks && src->n_rows > 0) {
     const uint64_t words = ((src->n_rows + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS + 31) / 32;
     if (words > pipe->blocks_cap) {
@@ -866,33 +917,35 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   }
   if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   CUDA_TRY(cudaMemcpyAsync(pipe->h_state, pipe->d_state, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (pipe->group)
+    CUDA_TRY(cudaMemcpyAsync(pipe->h_merged, pipe->d_merged, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  pipe->launched_merged = pipe->group != nullptr;
   CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
   pipe->launched = true;
   return FQ_OK;
 }
 
 static fq_status decode_err(uint64_t bits) {
+  if (bits & FQ_E_MERGE_TIMEOUT) return set_err(FQ_ERR_CUDA, "CUDA error: a rank of the group did not publish its state in time (cross-GPU merge timed out)");
   if (bits & FQ_E_DIVZERO) return set_err(FQ_ERR_DIVIDE_BY_ZERO, "Internal Error: Divide by zero error");
   return FQ_OK;
 }
 
-fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
-                                  uint64_t *rows_selected) {
-  if (fq_status st = use(ctx)) return st;
-  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+// raw state slots -> the DataValues Function::accumulate_result / merge_result would hold
+static fq_status decode_states(const fq_pipe *pipe, const uint64_t *slots, bool launched, fq_value *states, int32_t cap, int32_t *n_states,
+                               uint64_t *rows_selected) {
   const int n = (int)pipe->gen.agg_nodes.size();
   if (n_states) *n_states = n;
-  if (pipe->launched) CUDA_TRY(cudaEventSynchronize(pipe->ev));
-  const uint64_t nsel = pipe->h_state[0], folded = pipe->h_state[2];
+  const uint64_t nsel = slots[0], folded = slots[2];
   if (rows_selected) *rows_selected = nsel;
-  if (fq_status st = decode_err(pipe->h_state[1])) return st;
+  if (fq_status st = decode_err(slots[1])) return st;
   for (int k = 0; k < n && k < cap && states; k++) {
     fq_value &v = states[k];
     memset(&v, 0, sizeof v);
-    if (!pipe->launched || folded == 0) { v.dtype = FQ_NULL; continue; }  // state still DataValue::Null
+    if (!launched || folded == 0) { v.dtype = FQ_NULL; continue; }  // state still DataValue::Null
     const int op = pipe->gen.agg_ops[k];
     const fq_dtype t = pipe->gen.agg_dtypes[k];
-    const uint64_t bits = pipe->h_state[FQ_STATE_HDR + k];
+    const uint64_t bits = slots[FQ_STATE_HDR + k];
     v.dtype = t;
     if (op == FQ_AGG_COUNT) {  // state (+) UInt64(rows) per block, function_aggregator.rs:61-66
       v.some = 1;
@@ -900,12 +953,29 @@ fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, 
       continue;
     }
     // arrow sum/min/max skip nulls and are None when no valid row was seen (empty input included)
-    v.some = pipe->gen.agg_count_slot[k] >= 0 ? pipe->h_state[FQ_STATE_HDR + pipe->gen.agg_count_slot[k]] > 0 : nsel > 0;
+    v.some = pipe->gen.agg_count_slot[k] >= 0 ? slots[FQ_STATE_HDR + pipe->gen.agg_count_slot[k]] > 0 : nsel > 0;
     if (!v.some) continue;
     if (t == FQ_F32 || t == FQ_F64) memcpy(&v.v.f, &bits, 8);
     else v.v.u = bits;
   }
   return FQ_OK;
+}
+
+fq_status fq_pipe_fetch_aggregate(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
+                                  uint64_t *rows_selected) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  if (pipe->launched) CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  return decode_states(pipe, pipe->h_state, pipe->launched, states, cap, n_states, rows_selected);
+}
+
+fq_status fq_pipe_fetch_merged(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
+                               uint64_t *rows_selected) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
+  if (!pipe->launched_merged) return set_err(FQ_ERR_INVALID, "Internal Error: the last launch of this pipe did not merge across a group");
+  CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  return decode_states(pipe, pipe->h_merged, true, states, cap, n_states, rows_selected);
 }
 
 fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks, uint64_t *empty_blocks) {
@@ -919,34 +989,247 @@ fq_status fq_pipe_fetch_block_stats(fq_ctx *ctx, fq_pipe *pipe, uint64_t *blocks
 
 // ---- merge point over peer memory ----
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 opaque bytes");
-fq_status fq_ipc_export(fq_ctx *ctx, const fq_column *col, void *handle64) {
+fq_status fq_group_create(fq_ctx *ctx, int32_t rank, int32_t world, uint64_t row_bytes, fq_group **out) {
   if (fq_status st = use(ctx)) return st;
-  if (!col || !handle64) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (!out) return set_err(FQ_ERR_INVALID, "Internal Error: null out pointer");
+  *out = nullptr;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return set_err(FQ_ERR_INVALID, "Internal Error: a group has 1..8 ranks");
+  if (row_bytes < 256 || row_bytes > (64u << 20)) return set_err(FQ_ERR_INVALID, "Internal Error: group rows hold 256 B .. 64 MB");
+  fq_group *g = new fq_group();
+  g->rank = rank;
+  g->world = world;
+  g->row_slots = (uint32_t)((row_bytes + 7) / 8);
+  if (const char *t = getenv("FQ_GROUP_TIMEOUT_MS")) {
+    if (atoll(t) > 0) g->timeout_ns = (uint64_t)atoll(t) * 1000000ull;
+  }
+  const size_t bytes = sizeof(uint64_t) * 2 * (size_t)world * g->row_slots;
+  cudaError_t e = cudaMalloc(&g->window, bytes);
+  if (e == cudaSuccess) e = cudaMemset(g->window, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_result, 64);
+  if (e == cudaSuccess) e = cudaMemset(g->d_result, 0, 64);
+  if (e == cudaSuccess) e = cudaHostAlloc(&g->h_result, 64, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    fq_group_destroy(ctx, g);
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (group buffers)", cudaGetErrorString(e));
+  }
+  g->windows[rank] = g->window;
+  g->connected = world == 1;
+  *out = g;
+  return FQ_OK;
+}
+fq_status fq_group_handle(fq_ctx *ctx, const fq_group *g, void *handle64) {
+  if (fq_status st = use(ctx)) return st;
+  if (!g || !handle64) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
   cudaIpcMemHandle_t h;
-  CUDA_TRY(cudaIpcGetMemHandle(&h, col->ptr));
+  CUDA_TRY(cudaIpcGetMemHandle(&h, g->window));
   memcpy(handle64, &h, sizeof h);
   return FQ_OK;
 }
-fq_status fq_ipc_open(fq_ctx *ctx, const void *handle64, void **dev_ptr) {
-  if (fq_status st = use(ctx)) return st;
-  if (!handle64 || !dev_ptr) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, sizeof h);
-  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+fq_status fq_group_window(fq_ctx *, const fq_group *g, void **dev_ptr, uint64_t *n_bytes) {
+  if (!g || !dev_ptr) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *dev_ptr = g->window;
+  if (n_bytes) *n_bytes = sizeof(uint64_t) * 2 * (uint64_t)g->world * g->row_slots;
   return FQ_OK;
 }
-fq_status fq_ipc_close(fq_ctx *ctx, void *dev_ptr) {
+fq_status fq_group_connect(fq_ctx *ctx, fq_group *g, const void *handles) {
   if (fq_status st = use(ctx)) return st;
-  if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  if (!g || !handles) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is already connected");
+  for (int r = 0; r < g->world; r++) {
+    if (r == g->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof h);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; q++)
+        if (g->ipc_opened[q]) { cudaIpcCloseMemHandle(g->windows[q]); g->ipc_opened[q] = false; g->windows[q] = nullptr; }
+      return set_err(FQ_ERR_CUDA, "CUDA error: %s (cudaIpcOpenMemHandle of rank %d's window)", cudaGetErrorString(e), r);
+    }
+    g->windows[r] = (uint64_t *)ptr;
+    g->ipc_opened[r] = true;
+  }
+  g->connected = true;
   return FQ_OK;
 }
-fq_status fq_pipe_set_peer_slots(fq_ctx *ctx, fq_pipe *pipe, void *const *slots, int32_t n) {
-  if (fq_status st = use(ctx)) return st;
-  if (!pipe || pipe->gen.kind != FQ_PIPE_AGGREGATE) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate pipe");
-  if (n < 0 || n > 8 || (n > 0 && !slots)) return set_err(FQ_ERR_INVALID, "Internal Error: at most 8 peer slots");
-  for (int r = 0; r < 8; r++) pipe->peer_slots[r] = r < n ? slots[r] : nullptr;
-  pipe->n_peers = n;
+fq_status fq_group_connect_ptrs(fq_ctx *ctx, fq_group *g, void *const *windows) {
+  if (!ctx || !g || !windows) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is already connected");
+  for (int r = 0; r < g->world; r++) {
+    if (r == g->rank) continue;
+    if (!windows[r]) return set_err(FQ_ERR_INVALID, "Internal Error: missing window of rank %d", r);
+    g->windows[r] = (uint64_t *)windows[r];
+  }
+  g->connected = true;
   return FQ_OK;
+}
+void fq_group_destroy(fq_ctx *ctx, fq_group *g) {
+  if (!g) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  for (int r = 0; r < 8; r++)
+    if (g->ipc_opened[r]) cudaIpcCloseMemHandle(g->windows[r]);
+  cudaFree(g->window);
+  cudaFree(g->d_result);
+  if (g->h_result) cudaFreeHost(g->h_result);
+  if (g->ev) cudaEventDestroy(g->ev);
+  delete g;
+}
+fq_status fq_pipe_set_group(fq_ctx *ctx, fq_pipe *pipe, fq_group *g) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe) return set_err(FQ_ERR_INVALID, "Internal Error: null pipe");
+  if (g && pipe->gen.kind == FQ_PIPE_AGGREGATE) {
+    if ((uint32_t)pipe->n_slots + 1 > g->row_slots) return set_err(FQ_ERR_INVALID, "Internal Error: group rows are too small for this pipe's state");
+    if (!pipe->d_merged) {
+      CUDA_TRY(cudaMalloc(&pipe->d_merged, sizeof(uint64_t) * pipe->n_slots));
+      CUDA_TRY(cudaMemset(pipe->d_merged, 0, sizeof(uint64_t) * pipe->n_slots));
+      CUDA_TRY(cudaHostAlloc(&pipe->h_merged, sizeof(uint64_t) * pipe->n_slots, cudaHostAllocDefault));
+      memset(pipe->h_merged, 0, sizeof(uint64_t) * pipe->n_slots);
+    }
+  }
+  pipe->group = g;
+  return FQ_OK;
+}
+
+// Ordered concatenation of every rank's filtered + projected rows, cut at `limit` — MergeProcessor + the LimitTransform
+// after it (processor_merge.rs:37-66, pipeline_builder.rs:31-41), ranks in partition order (a legal merge order).
+// One CTA: publish this rank's {selected, written, error bits, rows} into every rank's window, wait for all rows of
+// the epoch, copy the first `limit` rows in rank order into the final columns.
+struct fq_gather_params {
+  fq_launch_params g;          // group_* fields only
+  const void *src[2 * FQ_MAX_EXPRS];
+  void *dst[2 * FQ_MAX_EXPRS];
+  fq_u32 elem[2 * FQ_MAX_EXPRS];
+  fq_u32 col_slot[2 * FQ_MAX_EXPRS];   // first slot of column c inside a row's payload
+  fq_u32 n_cols;
+  const fq_u64 *local_result;  // the projection launch's result block: [0] rows selected, [1] error bits
+  fq_u64 cap_local;            // rows the local launch may have written
+  fq_u64 limit;                // final rows = min(limit, sum of written)
+  fq_u64 *out_result;          // [0] rows selected by all ranks, [1] final rows, [2] error bits
+};
+__global__ void __launch_bounds__(256) fq_group_gather_rows(const __grid_constant__ fq_gather_params a) {
+  const fq_launch_params &p = a.g;
+  __shared__ fq_u64 s_off[9], s_take[8], s_sel, s_err;
+  __shared__ int s_ok;
+  const fq_u64 selected = a.local_result[0];
+  const fq_u64 written = selected < a.cap_local ? selected : a.cap_local;
+  // payload into every rank's window: 8-byte words (columns are 256-byte padded, rows 8-byte slotted)
+  for (fq_u32 r = 0; r < p.group_world; r++) {
+    fq_u64 *row = fq_group_row(p, (int)r, (int)p.group_rank);
+    for (fq_u32 c = 0; c < a.n_cols; c++) {
+      const fq_u64 words = (written * a.elem[c] + 7) / 8;
+      const fq_u64 *src = (const fq_u64 *)a.src[c];
+      fq_u64 *dst = row + a.col_slot[c];
+      for (fq_u64 i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < p.group_world) {
+    fq_u64 *row = fq_group_row(p, (int)threadIdx.x, (int)p.group_rank);
+    row[1] = selected;
+    row[2] = written;
+    row[3] = a.local_result[1];
+    __threadfence_system();
+    fq_st_release_sys(row, p.group_epoch);
+  }
+  if (threadIdx.x < 32) {
+    const bool ok = fq_group_wait(p);
+    if (threadIdx.x == 0) {
+      s_ok = ok ? 1 : 0;
+      fq_u64 off = 0, sel = 0, err = ok ? 0 : FQ_E_MERGE_TIMEOUT;
+      for (fq_u32 r = 0; r < p.group_world; r++) {
+        const fq_u64 *row = fq_group_row(p, (int)p.group_rank, (int)r);
+        const fq_u64 w = ok ? fq_ld_cg(row + 2) : 0;
+        const fq_u64 take = off + w <= a.limit ? w : a.limit - off;
+        s_off[r] = off;
+        s_take[r] = take;
+        off += take;
+        sel += ok ? fq_ld_cg(row + 1) : 0;
+        err |= ok ? fq_ld_cg(row + 3) : 0;
+      }
+      s_off[p.group_world] = off;
+      s_sel = sel;
+      s_err = err;
+    }
+  }
+  __syncthreads();
+  for (fq_u32 r = 0; r < p.group_world; r++) {
+    const fq_u64 *row = fq_group_row(p, (int)p.group_rank, (int)r);
+    for (fq_u32 c = 0; c < a.n_cols; c++) {
+      const unsigned char *src = (const unsigned char *)(row + a.col_slot[c]);
+      unsigned char *dst = (unsigned char *)a.dst[c] + s_off[r] * a.elem[c];
+      const fq_u64 bytes = s_take[r] * a.elem[c];
+      if (a.elem[c] == 8) {
+        for (fq_u64 i = threadIdx.x; i < s_take[r]; i += blockDim.x) ((fq_u64 *)dst)[i] = fq_ld_cg((const fq_u64 *)src + i);
+      } else {
+        for (fq_u64 i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = *(const volatile unsigned char *)(src + i);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    a.out_result[0] = s_sel;
+    a.out_result[1] = s_off[p.group_world];
+    a.out_result[2] = s_err;
+  }
+}
+
+fq_status fq_group_gather_project(fq_ctx *ctx, fq_group *g, fq_pipe *pipe, fq_column *const *local_cols, fq_column *const *local_valid,
+                                  fq_column *const *final_cols, fq_column *const *final_valid, int64_t limit, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!g || !pipe || pipe->gen.kind != FQ_PIPE_PROJECT || !pipe->launched_project)
+    return set_err(FQ_ERR_INVALID, "Internal Error: gather needs a group and a projection pipe that was launched");
+  if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is not connected to its peers");
+  fq_gather_params a;
+  memset(&a, 0, sizeof a);
+  const int ne = (int)pipe->gen.expr_dtypes.size();
+  const uint64_t cap = pipe->capacity_eff;
+  const uint64_t lim = limit < 0 ? cap * (uint64_t)g->world : (uint64_t)limit;
+  uint64_t slot = 4;   // [0] epoch, [1] selected, [2] written, [3] error bits
+  for (int e = 0; e < ne; e++) {
+    for (int v = 0; v < 2; v++) {
+      const bool nullable = e < (int)pipe->gen.expr_nullable.size() && pipe->gen.expr_nullable[e];
+      if (v == 1 && !nullable) continue;
+      const fq_column *lc = v ? (local_valid ? local_valid[e] : nullptr) : (local_cols ? local_cols[e] : nullptr);
+      const fq_column *fc = v ? (final_valid ? final_valid[e] : nullptr) : (final_cols ? final_cols[e] : nullptr);
+      const fq_dtype want = v ? (fq_dtype)FQ_BOOL : pipe->gen.expr_dtypes[e];
+      if (!lc || !fc || lc->dtype != want || fc->dtype != want)
+        return set_err(FQ_ERR_INVALID, "Internal Error: gather column %d%s missing or of the wrong type", e, v ? " (validity)" : "");
+      if (lc->len < cap || fc->len < std::min<uint64_t>(lim, cap * (uint64_t)g->world))
+        return set_err(FQ_ERR_INVALID, "Internal Error: gather column %d is shorter than the rows it may receive", e);
+      const uint32_t w = (uint32_t)fq::dtype_size(want);
+      const int c = (int)a.n_cols++;
+      a.src[c] = lc->ptr;
+      a.dst[c] = fc->ptr;
+      a.elem[c] = w;
+      a.col_slot[c] = (fq_u32)slot;
+      slot += (cap * w + 7) / 8;
+    }
+  }
+  if (slot > g->row_slots)
+    return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: %" PRIu64 " rows per rank do not fit the group's %u-byte rows", cap,
+                   g->row_slots * 8u);
+  bind_group(g, &a.g);
+  a.local_result = (const fq_u64 *)pipe->d_ctl;
+  a.cap_local = cap;
+  a.limit = lim;
+  a.out_result = (fq_u64 *)g->d_result;
+  fq_group_gather_rows<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaMemcpyAsync(g->h_result, g->d_result, 24, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventRecord(g->ev, (cudaStream_t)stream));
+  g->gathered = true;
+  return FQ_OK;
+}
+fq_status fq_group_fetch_gather(fq_ctx *ctx, fq_group *g, uint64_t *rows_selected, uint64_t *rows_final) {
+  if (fq_status st = use(ctx)) return st;
+  if (!g || !g->gathered) return set_err(FQ_ERR_INVALID, "Internal Error: no gather to fetch");
+  CUDA_TRY(cudaEventSynchronize(g->ev));
+  if (rows_selected) *rows_selected = g->h_result[0];
+  if (rows_final) *rows_final = g->h_result[1];
+  return decode_err(g->h_result[2]);
 }
 
 fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, fq_column *const *out_cols,
@@ -986,7 +1269,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     pipe->skipped = true;
   } else if (pipe->gen.has_pred) {
     // kernel variant: FQ_SEL_VARIANT = tma (default: pass 1 staged by bulk copies; needs every referenced column materialised) | ldg
-    const std::string variant = getenv("FQ_SEL_VARIANT") ? getenv("FQ_SEL_VARIANT") : FQ_SEL_DEFAULT_VARIANT;   // read per launch: tests switch it
+    const std::string &variant = pipe->variant;
     const bool use_tma = (variant == "tma" && pipe->k_select_tma.valid()) || !pipe->k_select.valid();
     const Kernel &k = use_tma ? pipe->k_select_tma : pipe->k_select;
     if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no select kernel was built for this pipe");
@@ -1019,7 +1302,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
       p.n_rows = std::min<uint64_t>(p.n_rows, std::max<uint64_t>(blocks, 1) * FQ_REF_BLOCK_ROWS);
     }
     // FQ_MAP_VARIANT = tma (default: reads staged by bulk copies; needs every referenced column materialised) | ldg
-    const std::string variant = getenv("FQ_MAP_VARIANT") ? getenv("FQ_MAP_VARIANT") : FQ_MAP_DEFAULT_VARIANT;
+    const std::string &variant = pipe->variant;
     const bool use_tma = (variant == "tma" && pipe->k_map_tma.valid()) || !pipe->k_map.valid();
     const Kernel &k = use_tma ? pipe->k_map_tma : pipe->k_map;
     if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no projection kernel was built for this pipe");

@@ -78,10 +78,16 @@ struct fq_launch_params {
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
-  // multi-GPU merge fused into the aggregate kernel: after the fold the last CTA also stores the running state into
-  // these remote slots (peer GPUs' memory over NVLink, or this GPU's own gather row); n_peers = 0: off
-  fq_u64 *peer_slots[8];
-  fq_u32 n_peers;
+  // multi-GPU merge point fused into the aggregate kernel (fq_group, include/fuse_gpu.h): after the fold the last CTA
+  // stores the running state into its row of EVERY rank's exchange window (peer GPUs' memory over NVLink), waits until
+  // every rank's row of this epoch has arrived in its own window, folds them in rank order and writes `merged`.
+  // Window layout: [parity = epoch & 1][writer rank][group_row_slots] 8-byte slots, slot 0 of a row = the epoch it holds.
+  // group_world = 0: off
+  fq_u64 *group_windows[8];
+  fq_u64 group_epoch;
+  fq_u64 group_timeout_ns;
+  fq_u64 *merged;          // [FQ_STATE_HDR + Q::NSLOTS] merged state of all ranks (local)
+  fq_u32 group_rank, group_world, group_row_slots;
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -375,15 +381,86 @@ template <int V> __device__ __forceinline__ void fq_mark_blocks_warp(const fq_la
   }
 }
 
-// Out of line on purpose: inlined, the (cold) peer stores changed the register allocation and unrolling of the hot
-// loops of the ALU-bound generated-source kernels (sum(number) over 1e10 generated rows: 1.15 -> 1.70 ms).
-static __device__ __noinline__ void fq_publish_state(const fq_launch_params &p, int n_slots) {
-  for (fq_u32 r = 0; r < p.n_peers; r++) {
-    fq_u64 *dst = p.peer_slots[r];
-    if (!dst) continue;
-    for (int k = 0; k < n_slots; k++) dst[k] = p.state[k];
+#define FQ_E_MERGE_TIMEOUT 2u  // a rank's state did not arrive in the exchange window in time
+
+__device__ __forceinline__ void fq_st_release_sys(fq_u64 *p, fq_u64 v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ fq_u64 fq_ld_acquire_sys(const fq_u64 *p) {
+  fq_u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ fq_u64 fq_globaltimer() {
+  fq_u64 t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Row of `writer` in a window, for the epoch's parity.  A rank can be at most one epoch ahead of another (it cannot finish
+// epoch e + 1 before every rank has published e + 1, which they do after finishing e), so two row sets suffice.
+__device__ __forceinline__ fq_u64 *fq_group_row(const fq_launch_params &p, int window_of, int writer) {
+  return p.group_windows[window_of] + ((p.group_epoch & 1ull) * p.group_world + (fq_u64)writer) * p.group_row_slots;
+}
+// lanes 0 .. world-1 of one warp: lane r stores `n` payload slots into this rank's row of rank r's window, then the epoch
+// (release at system scope: the payload is visible to whoever acquires the epoch).  Returns after the stores were issued.
+__device__ __forceinline__ void fq_group_publish(const fq_launch_params &p, const fq_u64 *payload, int n) {
+  const int lane = threadIdx.x & 31;
+  if (lane < (int)p.group_world) {
+    fq_u64 *row = fq_group_row(p, lane, (int)p.group_rank);
+    for (int k = 0; k < n; k++) row[1 + k] = payload[k];
+    __threadfence_system();
+    fq_st_release_sys(row, p.group_epoch);
   }
-  __threadfence_system();
+}
+// lanes 0 .. world-1: lane r waits for rank r's row of this epoch in the LOCAL window; false on timeout (a dead peer must
+// not hang the GPU: the caller reports FQ_E_MERGE_TIMEOUT)
+__device__ __forceinline__ bool fq_group_wait(const fq_launch_params &p) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  if (lane < (int)p.group_world) {
+    const fq_u64 *row = fq_group_row(p, (int)p.group_rank, lane);
+    const fq_u64 t0 = fq_globaltimer();
+    while (fq_ld_acquire_sys(row) != p.group_epoch) {
+      if (fq_globaltimer() - t0 > p.group_timeout_ns) { ok = false; break; }
+    }
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+// The exchange + final fold of the merge point (processors/processor_merge.rs:37-66 feeding
+// transforms/transform_aggregate_final.rs:50-78), run by warp 0 of the aggregate kernel's last CTA.  Out of line on
+// purpose: inlined, this cold code changed the register allocation and unrolling of the hot loops of the ALU-bound
+// generated-source kernels (sum(number) over 1e10 generated rows: 1.15 -> 1.70 ms).
+template <class Q>
+static __device__ __noinline__ void fq_group_merge(const fq_launch_params &p) {
+  constexpr int S = FQ_STATE_HDR + Q::NSLOTS;
+  fq_group_publish(p, p.state, S);
+  const bool ok = fq_group_wait(p);
+  if ((threadIdx.x & 31) == 0) {
+    typename Q::Acc acc;
+    Q::init(acc);
+    fq_u64 hdr[FQ_STATE_HDR];
+#pragma unroll
+    for (int k = 0; k < FQ_STATE_HDR; k++) hdr[k] = 0;
+    for (int r = 0; r < (int)p.group_world; r++) {   // rank order = partition order: float sums fold deterministically
+      const fq_u64 *row = fq_group_row(p, (int)p.group_rank, r) + 1;
+      fq_u64 tmp[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
+#pragma unroll
+      for (int k = 0; k < Q::NSLOTS; k++) tmp[k] = fq_ld_cg(row + FQ_STATE_HDR + k);
+      typename Q::Acc o;
+      Q::unpack(o, tmp);
+      Q::merge(acc, o);
+#pragma unroll
+      for (int k = 0; k < FQ_STATE_HDR; k++) {
+        const fq_u64 x = fq_ld_cg(row + k);
+        hdr[k] = k == 1 ? (hdr[k] | x) : (hdr[k] + x);
+      }
+    }
+    if (!ok) hdr[1] |= FQ_E_MERGE_TIMEOUT;
+#pragma unroll
+    for (int k = 0; k < FQ_STATE_HDR; k++) p.merged[k] = hdr[k];
+    Q::store(acc, p.merged + FQ_STATE_HDR);
+  }
 }
 
 // CTA partial -> global partial row -> last CTA (ticket) folds every partial into (or restarts) the running state
@@ -462,9 +539,11 @@ __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typenam
     p.state[5] = empty_blocks;
     Q::store(acc, p.state + FQ_STATE_HDR);
     *p.ticket = 0;
-    // the exchange step of the merge (processor_merge.rs:37-66), fused: S 8-byte stores per peer straight into the
-    // peers' gather buffers.  No wait on the device: readers synchronise with the launch (stream + cross-rank barrier).
-    if (p.n_peers) fq_publish_state(p, S);
+  }
+  // the merge point across GPUs, fused: exchange over peer memory + final fold (see fq_group_merge)
+  if (p.group_world) {
+    __syncthreads();   // p.state is complete
+    if (threadIdx.x < 32) fq_group_merge<Q>(p);
   }
 }
 

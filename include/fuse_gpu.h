@@ -194,6 +194,10 @@ typedef struct fq_pipe fq_pipe;
 
 fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out);
 void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe);
+/* Kernel variant the pipe's launches prefer: aggregate pipes "tma" (bulk-copy staged, default) | "u4" | "u8" (LDG.128 x 4 / x 8),
+ * select and projection pipes "tma" | "ldg".  The default comes from FQ_AGG_VARIANT / FQ_SEL_VARIANT / FQ_MAP_VARIANT, read once
+ * when the pipe is compiled (never on the launch path).  A variant the pipe's module does not hold falls back to one it does. */
+fq_status fq_pipe_set_variant(fq_ctx *ctx, fq_pipe *pipe, const char *variant);
 /* 1 if the kernel came from the library's precompiled table, 0 if NVRTC built it */
 int32_t fq_pipe_is_precompiled(const fq_pipe *pipe);
 /* where the pipe's kernels came from: 0 = the library's precompiled table, 1 = built by NVRTC in this process,
@@ -235,18 +239,43 @@ fq_status fq_pipe_aggregator_nodes(fq_ctx *ctx, const fq_pipe *pipe, int32_t *no
 #define FQ_STATE_HEADER_SLOTS 6
 fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes);
 
-/* ---- multi-GPU merge point (processors/processor_merge.rs:37-66) without a collective call ----
- * One process per GPU.  Every rank owns a gather buffer (a UInt64 column of world * state_slots rows), exports it with
- * fq_ipc_export (64-byte CUDA IPC handle, exchanged by the host however it likes) and opens its peers' buffers with
- * fq_ipc_open.  fq_pipe_set_peer_slots(pipe, slots, n) then makes every aggregate launch of `pipe` finish by storing
- * its running state (the bytes fq_pipe_state_device describes) to slots[r] for r < n (<= 8): the address, in GPU r's
- * memory, of this rank's row of r's gather buffer (slots[own rank] may point into the local buffer).  The stores ride
- * NVLink from the kernel's last CTA; nothing waits on the device.  A reader of a gather buffer must first order itself
- * after the launches of all ranks (stream synchronisation + a cross-rank barrier).  n = 0 switches it off. */
-fq_status fq_ipc_export(fq_ctx *ctx, const fq_column *col, void *handle64);
-fq_status fq_ipc_open(fq_ctx *ctx, const void *handle64, void **dev_ptr);
-fq_status fq_ipc_close(fq_ctx *ctx, void *dev_ptr);
-fq_status fq_pipe_set_peer_slots(fq_ctx *ctx, fq_pipe *pipe, void *const *slots, int32_t n);
+/* ---- multi-GPU merge point (processors/processor_merge.rs:37-66 feeding transform_aggregate_final.rs:50-78 /
+ * the LimitTransform after the merge, pipeline_builder.rs:31-41) without a collective call ----
+ * One process per GPU.  A group is a set of 1..8 ranks, each owning an exchange window in its GPU's memory
+ * (2 parities x world rows of `row_bytes`).  Every rank creates its group, exports the window with fq_group_handle
+ * (64-byte CUDA IPC handle, exchanged by the host however it likes: torch.distributed, MPI, a socket) and hands the
+ * `world * 64` bytes of all handles, in rank order, to fq_group_connect (ranks in ONE process pass raw window addresses
+ * to fq_group_connect_ptrs instead: IPC handles cannot be opened by the process that made them).
+ *
+ * Aggregate pipes: after fq_pipe_set_group every fq_pipe_launch_aggregate ends with the merge point INSIDE the kernel —
+ * its last CTA stores the running state into its row of every rank's window over NVLink peer memory (release at system
+ * scope), waits until the rows of all ranks for this operation have arrived in its own window, folds them in rank order
+ * (wrapping add / min / max — the merge_state rules, function_aggregator.rs:106-139) and leaves the merged state of the
+ * whole group on every rank: fq_pipe_fetch_merged.  No host round trip, no collective library call.
+ * Projection pipes: fq_group_gather_project concatenates the rows every rank's launch wrote, in rank (= partition) order,
+ * cut at `limit`, into `final_cols` on every rank.
+ *
+ * Like a communicator, a group numbers its operations: every rank must issue the same sequence of group operations
+ * (launches of pipes bound to the group, gathers).  A rank that never shows up makes the others fail with FQ_ERR_CUDA
+ * after FQ_GROUP_TIMEOUT_MS (default 20 000) instead of hanging the GPU. */
+typedef struct fq_group fq_group;
+fq_status fq_group_create(fq_ctx *ctx, int32_t rank, int32_t world, uint64_t row_bytes, fq_group **out);
+fq_status fq_group_handle(fq_ctx *ctx, const fq_group *group, void *handle64);
+fq_status fq_group_window(fq_ctx *ctx, const fq_group *group, void **dev_ptr, uint64_t *n_bytes);
+fq_status fq_group_connect(fq_ctx *ctx, fq_group *group, const void *handles /* world x 64 bytes, rank order */);
+fq_status fq_group_connect_ptrs(fq_ctx *ctx, fq_group *group, void *const *windows /* world device addresses */);
+void fq_group_destroy(fq_ctx *ctx, fq_group *group);
+/* group == NULL detaches the pipe; the group must outlive the pipes bound to it */
+fq_status fq_pipe_set_group(fq_ctx *ctx, fq_pipe *pipe, fq_group *group);
+/* like fq_pipe_fetch_aggregate, for the state merged over all ranks by the last launch (Count = rows of all ranks) */
+fq_status fq_pipe_fetch_merged(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int32_t cap, int32_t *n_states,
+                               uint64_t *rows_selected);
+/* after fq_pipe_launch_project(pipe, ..., local_cols, local_valid, ...) on the same stream; final_* must hold
+ * min(limit, world * capacity) rows; limit < 0 = none */
+fq_status fq_group_gather_project(fq_ctx *ctx, fq_group *group, fq_pipe *pipe, fq_column *const *local_cols,
+                                  fq_column *const *local_valid, fq_column *const *final_cols, fq_column *const *final_valid,
+                                  int64_t limit, void *stream);
+fq_status fq_group_fetch_gather(fq_ctx *ctx, fq_group *group, uint64_t *rows_selected, uint64_t *rows_final);
 
 /* ---- projection pipes: filter_record_batch + projection (+ LimitStream) in one pass ----
  * out_cols[i] receives select expression i for the rows that pass the predicate, in row order

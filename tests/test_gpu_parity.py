@@ -490,36 +490,122 @@ def test_context_is_usable_from_many_host_threads(ctx):
         assert k == len(want) and np.array_equal(got, want)
 
 
-def test_aggregate_kernel_publishes_its_state_to_peer_slots(ctx):
-    """fq_pipe_set_peer_slots: the launch ends by storing the running state (header + leaves) into every slot it was
-    given — the multi-GPU merge point without a collective call.  Here the "peers" are rows of a local gather buffer."""
-    n = 5_000_003
-    col = ctx.numbers(7, n)
-    pipe = ctx.pipe(README_AGGS["headline"], aggregate=True)
-    ptr, nbytes = pipe.state_device()
-    slots = nbytes // 8
-    gather = ctx.from_numpy(np.zeros(3 * slots, dtype=np.uint64))
-    pipe.set_peer_slots([gather.device_ptr + r * nbytes for r in (0, 2)])       # rows 0 and 2; row 1 stays untouched
-    for variant in ("tma", "u4"):
-        os.environ["FQ_AGG_VARIANT"] = variant
-        try:
-            pipe.launch_aggregate(cabi.make_source([col], n))
-            states, rows = pipe.fetch_aggregate()
-        finally:
-            os.environ.pop("FQ_AGG_VARIANT", None)
-        g = gather.to_numpy().reshape(3, slots)
-        x = np.arange(7, 7 + n, dtype=np.uint64)
-        want_leaves = [int(x.sum(dtype=np.uint64)), n, int(x.max()), int(x.min())]
-        assert [s[1] for s in states] == want_leaves and rows == n
-        for r in (0, 2):
-            H = cabi.STATE_HEADER_SLOTS   # raw slots: Count(number) reads nothing, its value is the header's row count
-            assert g[r, 0] == n and g[r, 1] == 0 and g[r, 3] == n
-            assert [int(g[r, H]), int(g[r, H + 2]), int(g[r, H + 3])] == [want_leaves[0], want_leaves[2], want_leaves[3]]
-        assert not g[1].any()
-    pipe.set_peer_slots([])
-    pipe.launch_aggregate(cabi.make_source([col], 1000))
-    pipe.fetch_aggregate()
-    assert gather.to_numpy().reshape(3, slots)[0, 0] == n      # switched off: the slot keeps the previous launch
+def _streams(k):
+    import torch
+    return [torch.cuda.Stream(device=0) for _ in range(k)]
+
+
+def _local_groups(ctx, world, row_bytes=1 << 16):
+    """`world` ranks of one group living in this process on one GPU (each rank's kernels go to its own stream): the exchange
+    windows are plain device addresses instead of IPC mappings, the kernels are those of the multi-process path."""
+    groups = [ctx.group(r, world, row_bytes) for r in range(world)]
+    wins = [g.window for g in groups]
+    for g in groups:
+        g.connect_ptrs(wins)
+    return groups
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("variant", ["tma", "u4"])
+def test_aggregate_kernels_merge_their_states_across_a_group(ctx, world, variant):
+    """fq_pipe_set_group: every aggregate launch ends with the merge point inside the kernel (exchange of the running
+    states over peer memory + final fold in rank order, processor_merge.rs:37-66 -> transform_aggregate_final.rs:50-78).
+    Every rank ends up with the merged state of all ranks; several operations in a row reuse the two row parities."""
+    import torch
+    n_total = 8 * 625_003 + 5
+    groups = _local_groups(ctx, world)
+    streams = _streams(world)
+    bounds = [n_total * r // world for r in range(world + 1)]
+    bounds[1:-1] = [b // 2 * 2 for b in bounds[1:-1]]
+    cols = [ctx.numbers(11 + bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+    pipes = []
+    for r in range(world):
+        p = ctx.pipe(README_AGGS["headline"] + [f"(count {NUM})", f"(max (+ {NUM} (u64 1)))"], aggregate=True)
+        p.set_variant(variant)
+        p.set_group(groups[r])
+        pipes.append(p)
+    x = np.arange(11, 11 + n_total, dtype=np.uint64)
+    want = [int(x.sum(dtype=np.uint64)), n_total, int(x.max()), int(x.min()), n_total, int(x.max()) + 1]
+    for op in range(5):   # epochs 1..5: both parities, rows reused
+        for r in range(world):
+            pipes[r].launch_aggregate(cabi.make_source([cols[r]], bounds[r + 1] - bounds[r]), stream=streams[r].cuda_stream)
+        for r in range(world):
+            states, rows = pipes[r].fetch_merged()
+            assert rows == n_total and [s[1] for s in states] == want, (op, r)
+            local, lrows = pipes[r].fetch_aggregate()
+            assert lrows == bounds[r + 1] - bounds[r]
+    # a filtered Sum whose predicate keeps nothing on some ranks: Type(None) only if NO rank saw a row
+    pipes2 = []
+    for r in range(world):
+        p = ctx.pipe([f"(sum {NUM})", f"(min {NUM})"], predicate=f"(< {NUM} (u64 100))", aggregate=True)
+        p.set_group(groups[r])
+        pipes2.append(p)
+    for r in range(world):
+        pipes2[r].launch_aggregate(cabi.make_source([cols[r]], bounds[r + 1] - bounds[r]), stream=streams[r].cuda_stream)
+    for r in range(world):
+        states, rows = pipes2[r].fetch_merged()
+        assert rows == 89 and [s[1] for s in states] == [sum(range(11, 100)), 11]
+    torch.cuda.synchronize()
+    for p in pipes + pipes2:
+        p.destroy()
+    for g in groups:
+        g.destroy()
+
+
+def test_group_merge_reports_a_missing_rank_instead_of_hanging(ctx):
+    """A rank that never launches makes the others fail after FQ_GROUP_TIMEOUT_MS — never a hung GPU."""
+    os.environ["FQ_GROUP_TIMEOUT_MS"] = "200"
+    try:
+        groups = _local_groups(ctx, 2)
+    finally:
+        os.environ.pop("FQ_GROUP_TIMEOUT_MS", None)
+    col = ctx.numbers(0, 100_000)
+    p = ctx.pipe(README_AGGS["sum"], aggregate=True)
+    p.set_group(groups[0])
+    p.launch_aggregate(cabi.make_source([col], 100_000))
+    with pytest.raises(cabi.FuseGpuError) as e:
+        p.fetch_merged()
+    assert "merge timed out" in str(e.value)
+    states, rows = p.fetch_aggregate()      # the local state is intact
+    assert rows == 100_000 and states[0][1] == 100_000 * 99_999 // 2
+    p.destroy()
+    for g in groups:
+        g.destroy()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("limit", [3, 70, 1000, -1])
+def test_group_gathers_filtered_rows_in_rank_order(ctx, world, limit):
+    """fq_group_gather_project: MergeProcessor + the LimitTransform after it for projection pipes — every rank's kept rows,
+    ranks in partition order, cut at LIMIT (pipeline_builder.rs:31-41).  Checked against the oracle's single-pipe run."""
+    import torch
+    n_total = 1_600_000
+    per = n_total // world
+    groups = _local_groups(ctx, world)
+    streams = _streams(world)
+    pred = f"(= (* (/ {NUM} (u64 25000)) (u64 25000)) {NUM})"      # every 25 000th number: 64 rows, 64 / world per rank
+    exprs = [f"(alias c1 (+ {NUM} (u64 1)))", f"(alias small (< {NUM} (u64 800000)))"]
+    cap = 1000 if limit < 0 else limit
+    finals = []
+    for r in range(world):
+        col = ctx.numbers(r * per, per)
+        p = ctx.pipe(exprs, predicate=pred)
+        outs = [ctx.column(p.expr_dtype(i), cap) for i in range(2)]
+        fin = [ctx.column(p.expr_dtype(i), cap * world) for i in range(2)]
+        p.launch_project(cabi.make_source([col], per), outs, cap, limit=limit, stream=streams[r].cuda_stream)
+        groups[r].gather_project(p, outs, fin, limit=limit, stream=streams[r].cuda_stream)
+        finals.append(fin)
+    want = o.run_query(exprs, total=n_total, predicate=pred, limit=None if limit < 0 else limit, worker_threads=1, tail_quirk=False).rows()
+    for r in range(world):
+        sel, nfin = groups[r].fetch_gather()
+        assert nfin == len(want)
+        if limit < 0 or limit >= 64:
+            assert sel == 64
+        got = list(zip(finals[r][0].to_numpy(nfin).tolist(), [bool(b) for b in finals[r][1].to_numpy(nfin)]))
+        assert got == [(a, bool(b)) for a, b in want]
+    torch.cuda.synchronize()
+    for g in groups:
+        g.destroy()
 
 
 def test_jit_cubins_are_cached_on_disk(tmp_path):

@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box call: smoke + the -m gpu suite + a short bench + the host/PCIe topology, everything into gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh [tests|bench|topo|all] [extra bench args]'
+# Multi-GPU: gpurun --gpus N -- 'bash tools/gpu_check.sh benchN N'
+set -u
+mkdir -p gpurun_out
+what=${1:-all}
+shift || true
+topo() {
+  { echo "== nvidia-smi topo -m"; nvidia-smi topo -m; echo "== nvidia-smi -L"; nvidia-smi -L;
+    echo "== lscpu"; lscpu | head -30; echo "== numa nodes"; ls /sys/devices/system/node/ 2>/dev/null; cat /sys/devices/system/node/node*/cpulist 2>/dev/null;
+    echo "== meminfo"; head -5 /proc/meminfo; echo "== nproc"; nproc;
+    echo "== pci"; for d in /sys/bus/pci/devices/*; do c=$(cat $d/class 2>/dev/null); case $c in 0x0302*|0x0300*) echo "$d class=$c numa=$(cat $d/numa_node) local_cpulist=$(cat $d/local_cpulist) link=$(cat $d/current_link_speed 2>/dev/null) x$(cat $d/current_link_width 2>/dev/null)";; esac; done;
+    echo "== lspci -tv"; lspci -tv 2>/dev/null | head -80; } > gpurun_out/topology.txt 2>&1
+}
+case $what in
+  tests|all)
+    timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+    timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+    ;;&
+  bench|all)
+    timeout 900 python bench.py --steps 20 --warmup 5 "$@" > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_n1.err
+    head -c 1500 gpurun_out/bench_n1.json
+    ;;&
+  topo|all)
+    topo
+    ;;
+  benchN)
+    N=$1; shift
+    topo
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 "$@" > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$?"; tail -5 gpurun_out/bench_n$N.err
+    head -c 1500 gpurun_out/bench_n$N.json
+    ;;
+esac
