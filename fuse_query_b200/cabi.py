@@ -75,7 +75,7 @@ EXPORTS = [
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_build_kind", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
-    "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project",
+    "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project", "fq_pipe_fetch_limit_row",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def lib():
         "fq_pipe_state_device": (i32, [vp, vp, C.POINTER(vp), C.POINTER(u64)]),
         "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), C.POINTER(vp), u64, i64, u32, vp]),
         "fq_pipe_fetch_project": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+        "fq_pipe_fetch_limit_row": (i32, [vp, vp, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -556,6 +557,12 @@ class Pipe:
             varr = (C.c_void_p * max(1, len(outs)))(*[None if c is None else c._h for c in out_valid])
         self.ctx.check(lib().fq_pipe_launch_project(self.ctx._h, self._h, C.byref(source), arr, varr, capacity, limit,
                                                      RUN_LIMIT_EARLY_EXIT if early_exit else 0, C.c_void_p(stream)))
+
+    def fetch_limit_row(self) -> int:
+        """Source row that produced the last output row of a launch that filled its capacity (completes the LIMIT)."""
+        row = C.c_uint64()
+        self.ctx.check(lib().fq_pipe_fetch_limit_row(self.ctx._h, self._h, C.byref(row)))
+        return row.value
 
     def fetch_project(self) -> Tuple[int, int]:
         sel, wr = C.c_uint64(), C.c_uint64()

@@ -248,6 +248,7 @@ struct fq_pipe {
   bool launched = false, launched_project = false;
   uint64_t capacity_eff = 0;
   bool skipped = false;     // project launch over zero rows
+  bool project_has_pred_launch = false;
 };
 
 namespace {
@@ -1036,6 +1037,7 @@ fq_status fq_group_window(fq_ctx *, const fq_group *g, void **dev_ptr, uint64_t 
 fq_status fq_group_connect(fq_ctx *ctx, fq_group *g, const void *handles) {
   if (fq_status st = use(ctx)) return st;
   if (!g || !handles) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (g->world == 1) return FQ_OK;   // nothing to connect
   if (g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is already connected");
   for (int r = 0; r < g->world; r++) {
     if (r == g->rank) continue;
@@ -1056,6 +1058,7 @@ fq_status fq_group_connect(fq_ctx *ctx, fq_group *g, const void *handles) {
 }
 fq_status fq_group_connect_ptrs(fq_ctx *ctx, fq_group *g, void *const *windows) {
   if (!ctx || !g || !windows) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (g->world == 1) return FQ_OK;   // nothing to connect
   if (g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is already connected");
   for (int r = 0; r < g->world; r++) {
     if (r == g->rank) continue;
@@ -1263,8 +1266,9 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   p.tile_counter = (fq_u32 *)(pipe->d_ctl + 2);
   p.done = (fq_u32 *)(pipe->d_ctl + 3);
   p.stop_after = ((flags & FQ_RUN_LIMIT_EARLY_EXIT) && limit > 0) ? (uint64_t)limit : 0;
-  CUDA_TRY(cudaMemsetAsync(pipe->d_ctl, 0, 32, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemsetAsync(pipe->d_ctl, 0, 48, (cudaStream_t)stream));
   pipe->skipped = false;
+  pipe->project_has_pred_launch = false;
   if (src->n_rows == 0) {
     pipe->skipped = true;
   } else if (pipe->gen.has_pred) {
@@ -1293,6 +1297,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     const int sel_bps = (sel_bps_env > 0 && !use_tma) ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+    pipe->project_has_pred_launch = true;
   } else {
     // LIMIT without a filter: LimitStream stops pulling once `limit` rows went by (stream_limit.rs:28-31), so the reference
     // evaluates only the 10 000-row blocks up to the one that completes the limit.  Same here: rows past that block are
@@ -1312,7 +1317,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }
-  CUDA_TRY(cudaMemcpyAsync(pipe->h_result, pipe->d_ctl, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemcpyAsync(pipe->h_result, pipe->d_ctl, 48, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
   pipe->launched_project = true;
   return FQ_OK;
@@ -1326,6 +1331,17 @@ fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selec
   if (rows_selected) *rows_selected = sel;
   if (rows_written) *rows_written = std::min(sel, pipe->capacity_eff);
   return decode_err(pipe->h_result[1]);
+}
+
+
+fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row) {
+  if (fq_status st = use(ctx)) return st;
+  if (!pipe || !pipe->launched_project || !row) return set_err(FQ_ERR_INVALID, "Internal Error: no projection launch to fetch");
+  CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  const uint64_t sel = pipe->skipped ? 0 : pipe->h_result[0];
+  if (pipe->capacity_eff == 0 || sel < pipe->capacity_eff) return set_err(FQ_ERR_INVALID, "Internal Error: the launch did not fill its capacity");
+  *row = pipe->project_has_pred_launch ? pipe->h_result[5] : pipe->capacity_eff - 1;
+  return FQ_OK;
 }
 
 }  // extern "C"

@@ -113,7 +113,7 @@ PipeRef compile_pipe(GpuContextRef ctx, const fq_pipe_desc &d) {
 // One fused launch evaluating `funcs` over `block` (optionally only the rows passing `predicate`, at most
 // `limit` of them).  Used by Function::eval, the Filter/Projection transforms and GpuPipeTransform.
 ProjectResult run_project(GpuContextRef ctx, const DataBlock &block, const Function *predicate, const std::vector<const Function *> &funcs,
-                          int64_t limit, bool early_exit) {
+                          int64_t limit, bool early_exit, std::string *deferred_error) {
   if (funcs.size() > (size_t)FQ_MAX_EXPRS) {
     // a pipe holds at most FQ_MAX_EXPRS select expressions: wider projections (and filters over wide tables, which gather
     // every column) run as several launches with the same predicate — the compaction is deterministic, so every launch
@@ -121,8 +121,8 @@ ProjectResult run_project(GpuContextRef ctx, const DataBlock &block, const Funct
     ProjectResult all;
     for (size_t b = 0; b < funcs.size(); b += FQ_MAX_EXPRS) {
       std::vector<const Function *> part(funcs.begin() + b, funcs.begin() + std::min(funcs.size(), b + (size_t)FQ_MAX_EXPRS));
-      ProjectResult r = run_project(ctx, block, predicate, part, limit, early_exit);
-      if (b == 0) { all.rows_selected = r.rows_selected; all.rows_written = r.rows_written; }
+      ProjectResult r = run_project(ctx, block, predicate, part, limit, early_exit, deferred_error);
+      if (b == 0) { all.rows_selected = r.rows_selected; all.rows_written = r.rows_written; all.limit_reached = r.limit_reached; all.limit_row = r.limit_row; }
       for (auto &c : r.columns) all.columns.push_back(c);
     }
     return all;
@@ -155,7 +155,16 @@ ProjectResult run_project(GpuContextRef ctx, const DataBlock &block, const Funct
   bind_source(lw, block, &bs);
   ctx->check(fq_pipe_launch_project(ctx->raw(), pipe->pipe, &bs.src, outs.data(), outs_valid.data(), cap, limit,
                                     early_exit ? FQ_RUN_LIMIT_EARLY_EXIT : 0, ctx->stream));
-  ctx->check(fq_pipe_fetch_project(ctx->raw(), pipe->pipe, &res.rows_selected, &res.rows_written));
+  const fq_status fst = fq_pipe_fetch_project(ctx->raw(), pipe->pipe, &res.rows_selected, &res.rows_written);
+  if (fst != FQ_OK && deferred_error && fst == FQ_ERR_DIVIDE_BY_ZERO) {
+    if (deferred_error->empty()) *deferred_error = fq_last_error(ctx->raw());
+  } else {
+    ctx->check(fst);
+  }
+  if (limit > 0 && res.rows_written == (uint64_t)limit && res.rows_selected >= (uint64_t)limit) {
+    res.limit_reached = true;
+    ctx->check(fq_pipe_fetch_limit_row(ctx->raw(), pipe->pipe, &res.limit_row));
+  }
   for (size_t e = 0; e < funcs.size(); e++)
     if (valids[e]) res.columns[e]->set_validity(valids[e]);
   if (res.rows_written < cap)

@@ -435,6 +435,19 @@ std::string GpuPipeTransform::describe() const {
   return s;
 }
 
+// rows [off, off + rows) of a device block (a view; generated blocks just move their first number)
+static DataBlock slice_block(const DataBlock &b, uint64_t off, uint64_t rows) {
+  if (b.generated) {
+    DataBlock s = b;
+    s.numbers_begin = b.numbers_begin + off;
+    s.generated_rows = rows;
+    return s;
+  }
+  std::vector<DataArrayRef> cols;
+  for (size_t i = 0; i < b.num_columns(); i++) cols.push_back(b.column(i)->slice(off, rows));
+  return DataBlock(b.schema(), cols);
+}
+
 static void collect_leaves(const Function &f, std::vector<const Function *> *out);
 // states of one select expression in accumulate_result order (function_arithmetic.rs:69-75)
 static void collect_states(const Function &f, const std::map<const Function *, DataValue> &leaf, std::vector<DataValue> *out) {
@@ -483,7 +496,8 @@ SendableDataBlockStream GpuPipeTransform::execute() {
   {
     OptionsGuard guard(ctx_);
     ctx_->options.block_rows = 0;
-    ctx_->options.align_runs = track_blocks;
+    // runs keep the reference's block boundaries whenever they are observable: Sum under WHERE (F8), errors under LIMIT
+    ctx_->options.align_runs = track_blocks || (!is_aggregate_ && limit_ && ctx_->options.block_quirks);
     source = table->read(ctx_, partitions_);
   }
 
@@ -552,10 +566,26 @@ SendableDataBlockStream GpuPipeTransform::execute() {
   for (auto &f : funcs) raw.push_back(f.get());
   std::vector<DataBlock> out;
   size_t taken = 0;
+  const bool exact_errors = limit_ && ctx_->options.block_quirks;
   while (auto block = source->next()) {
     if (limit_ && taken == *limit_) break;   // LimitStream ends the pipe (stream_limit.rs:30-31)
     int64_t remaining = limit_ ? (int64_t)(*limit_ - taken) : -1;
-    ProjectResult r = run_project(gpu, *block, pred.get(), raw, remaining, ctx_->options.limit_early_exit);
+    std::string deferred;
+    ProjectResult r = run_project(gpu, *block, pred.get(), raw, remaining, ctx_->options.limit_early_exit, exact_errors ? &deferred : nullptr);
+    if (exact_errors) {
+      // The reference pulls this pipe's 10 000-row blocks one by one: FilterTransform evaluates the predicate over the whole
+      // block, ProjectionTransform every kept row of it (transform_projection.rs:45-56), and only then LimitStream cuts
+      // (stream_limit.rs:28-48) and stops pulling.  The fused kernel evaluates the predicate over rows the reference never
+      // pulls and projects only the rows it writes, so errors are settled here over exactly the reference's rows.
+      const uint64_t rows = block->rows();
+      const uint64_t blk_end = r.limit_reached ? std::min<uint64_t>(rows, (r.limit_row / 10000 + 1) * 10000) : rows;
+      if (!deferred.empty()) {
+        if (!r.limit_reached) throw FuseQueryError(FuseQueryError::Internal, deferred);
+        run_project(gpu, slice_block(*block, 0, blk_end), pred.get(), raw, -1, false);            // throws iff the error is inside
+      } else if (r.limit_reached && r.limit_row + 1 < blk_end) {
+        run_project(gpu, slice_block(*block, r.limit_row + 1, blk_end - r.limit_row - 1), pred.get(), raw, -1, false);
+      }
+    }
     taken += r.rows_written;
     out.push_back(DataBlock(schema_, r.columns));
   }

@@ -94,7 +94,7 @@ struct fq_launch_params {
   fq_u64 capacity;       // rows written are those with rank < capacity (min(limit, capacity) on the host)
   fq_u64 *tile_status;   // decoupled look-back descriptors, zeroed before the launch
   fq_u32 *tile_counter;  // dynamic tile ids (forward progress for the look-back), zeroed before the launch
-  fq_u64 *result;        // [0] rows selected, [1] error bits
+  fq_u64 *result;        // [0] rows selected, [1] error bits, [5] source row of output row capacity - 1 (the row that completes a LIMIT)
   fq_u64 n_tiles;
   fq_u64 stop_after;     // early exit: stop scanning once this many rows were selected (0 = never)
   fq_u32 *done;          // early-exit flag, zeroed before the launch
@@ -1009,15 +1009,20 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
           tot += __popc(bmask);
         }
         fq_u64 pos = pos0 + before;
+        const fq_u64 row0 = (((sseg * SEG + t) * (fq_u64)wthreads + (fq_u64)warp * 32) * U + lane + 32ull * u) * V;   // first row of this group
         if (tot == 32u * V && (pos0 % V) == 0 && pos + V <= p.capacity) {
           // the warp kept the whole group (range predicates over sorted data: groups are all-or-nothing) and the
           // output position keeps the vector alignment: one vector store per output column instead of V scalar ones
           Q::emit_vec(rows[u], p, pos, err);
+          if (pos + V == p.capacity) p.result[5] = row0 + V - 1;
         } else {
 #pragma unroll
           for (int v = 0; v < V; v++) {
             if ((keep >> (u * V + v)) & 1u) {
-              if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+              if (pos < p.capacity) {
+                Q::emit(rows[u], v, p, pos, err);
+                if (pos + 1 == p.capacity) p.result[5] = row0 + v;
+              }
               pos++;
             }
           }
@@ -1039,10 +1044,14 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
           tot += __popc(bmask);
         }
         fq_u64 pos = pos0 + before;
+        const fq_u64 row0 = (((sseg * SEG + t) * (fq_u64)wthreads + (fq_u64)warp * 32) * U + lane + 32ull * u) * V;
 #pragma unroll
         for (int v = 0; v < V; v++) {
           if ((ku >> v) & 1u) {
-            if (pos < p.capacity) Q::emit(r, v, p, pos, err);
+            if (pos < p.capacity) {
+              Q::emit(r, v, p, pos, err);
+              if (pos + 1 == p.capacity) p.result[5] = row0 + v;
+            }
             pos++;
           }
         }

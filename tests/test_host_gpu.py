@@ -592,3 +592,50 @@ def test_validity_masks_are_canonicalised_on_upload(gpu):
     assert rows_of(blocks) == [(int(vals[valid != 0].sum()), 8, 1, 7)]
     blocks = h.execute_sql(ctx, "select v + 1 as w from m where v > 0")
     assert rows_of(blocks) == [(int(x) + 1,) for x in vals[valid != 0]]
+
+
+@pytest.mark.parametrize("generated", [False, True])
+def test_projection_errors_beyond_the_limit_follow_the_reference_blocks(gpu, generated):
+    """The reference projects every kept row of a 10 000-row block before LimitStream cuts it and stops pulling
+    (transform_projection.rs:45-56, stream_limit.rs:28-48): a zero divisor in a kept row AFTER the LIMIT-th row but in the
+    same block is an error; in a later block it is never evaluated.  The fused kernel only projects the rows it writes,
+    so GpuPipeTransform settles the errors over exactly the reference's rows (block_quirks, default on); with the option
+    off the launch's own outcome stands."""
+    from fuse_query_b200.tables import register_table
+    n = 80_000                                    # one source pipe (workers = 1): eight 10 000-row blocks
+    cases = [(50, True), (9_999, True), (10_000, False), (10_050, False), (3, True)]     # zero divisor at row -> error?
+    for row, want_error in cases:
+        d = np.ones(n, dtype=np.uint64)
+        d[row] = 0
+        x = np.arange(n, dtype=np.uint64)
+        table = {"x": o.from_numpy(x), "d": o.from_numpy(d)}
+        for pred_sql, pred in ((" where x >= 0", "(>= (col x) (u64 0))"), ("", None)):
+            def oracle():
+                return o.run_query(["(alias q (/ (col x) (col d)))"], table=table, predicate=pred, limit=5, worker_threads=1, tail_quirk=False)
+            ctx = make_ctx(gpu, 1)
+            register_table(ctx, gpu, "default", "t", {"x": x, "d": d})
+            sql = f"select x / d as q from t{pred_sql} limit 5"
+            if want_error:
+                with pytest.raises(o.OracleError) as oe:
+                    oracle()
+                with pytest.raises(h.FuseQueryError) as e:
+                    h.execute_sql(ctx, sql)
+                assert str(e.value) == str(oe.value) == "Internal Error: Divide by zero error"
+            else:
+                assert rows_of(h.execute_sql(ctx, sql)) == oracle().rows()
+            # quirk off: only rows that are written are evaluated -> an error only if the zero divisor is among the first 5 rows
+            ctx.options.block_quirks = False
+            if row < 5:
+                with pytest.raises(h.FuseQueryError):
+                    h.execute_sql(ctx, sql)
+            else:
+                assert rows_of(h.execute_sql(ctx, sql)) == [(i,) for i in range(5)]
+    # the predicate itself: evaluated over whole blocks up to the one completing the limit, never beyond
+    ctx = make_ctx(gpu, 1)
+    ctx.options.generated = generated
+    sql = "select number from system.numbers_mt(80000) where 100 / (number - 20000) < 1000 limit 5"     # zero divisor at row 20 000
+    want = o.run_query(["(col number)"], total=80_000, predicate="(< (/ (u64 100) (- (col number) (u64 20000))) (u64 1000))", limit=5,
+                       worker_threads=1)
+    assert rows_of(h.execute_sql(ctx, sql)) == want.rows() and len(want.rows()) == 5
+    ctx.options.limit_early_exit = False         # full scan: the kernel sees the zero divisor, the reference never pulls that block
+    assert rows_of(h.execute_sql(ctx, sql)) == want.rows()
