@@ -231,6 +231,7 @@ struct fq_pipe {
   Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
+  bool selt_stage2 = false;   // staged select kernel: pass 2 of dense segments staged as well
   int build_kind = 0;   // 0 precompiled, 1 NVRTC in this process, 2 on-disk JIT cache
   std::string variant;  // kernel variant the launches prefer: FQ_{AGG,SEL,MAP}_VARIANT when the pipe was compiled, or fq_pipe_set_variant
   fq_group *group = nullptr;   // aggregate launches end with the in-kernel cross-GPU merge when set
@@ -762,7 +763,13 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       if (!s2 && gen.sel_tma_ok) {
         // staged variant: consumer warps + scan warp + producer warp; ring of ~192 KB per CTA, at least 2 tiles
         const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
-        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
+        unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
+        // pass 2 of dense segments is staged too when a slot can hold a tile of EVERY referenced column and the ring still has
+        // three of them (FQ_SELT_STAGE2=0 switches it off: pass 2 then re-reads kept rows from L2 with plain loads)
+        const unsigned all_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.row_bytes;
+        static const bool stage2_env = !(getenv("FQ_SELT_STAGE2") && atoi(getenv("FQ_SELT_STAGE2")) == 0);
+        pipe->selt_stage2 = stage2_env && 3u * all_bytes <= 200u * 1024u;
+        if (pipe->selt_stage2) tile_bytes = all_bytes;
         // ~192 KB in flight per SM measured best here (1.19 -> 1.14 ms at 1e9 rows; the aggregate kernel peaks at 128 KB)
         unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (192u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);
@@ -1284,6 +1291,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     const int sel_seg = cfg_seg * sel_u * vec <= 64 ? cfg_seg : 64 / (sel_u * vec);  // ...::SEG
     const uint64_t tile_rows = (uint64_t)(k.threads - (use_tma ? 64 : 32)) * sel_u * vec * sel_seg;
     p.stages = pipe->selt_stages;
+    p.stages2 = (use_tma && pipe->selt_stage2) ? 1u : 0u;
     p.n_tiles = (src->n_rows + tile_rows - 1) / tile_rows;
     if (p.n_tiles > pipe->tiles_cap) {
       cudaFree(pipe->d_tiles);
@@ -1299,9 +1307,10 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
     pipe->project_has_pred_launch = true;
   } else {
-    // LIMIT without a filter: LimitStream stops pulling once `limit` rows went by (stream_limit.rs:28-31), so the reference
-    // evaluates only the 10 000-row blocks up to the one that completes the limit.  Same here: rows past that block are
-    // neither read nor evaluated (their divide-by-zero errors do not surface in the reference either).
+    // LIMIT without a filter: rows past the 10 000-row block that completes the limit are neither read nor evaluated.
+    // (The reference's LimitStream polls its input once more before it ends, stream_limit.rs:58-62, so it still evaluates
+    // the FOLLOWING block: a caller that wants the reference's errors checks the rows up to the end of that block itself —
+    // fq_pipe_fetch_limit_row tells where; the host mirror's GpuPipeTransform does.)
     if ((flags & FQ_RUN_LIMIT_EARLY_EXIT) && limit >= 0) {
       const uint64_t blocks = ((uint64_t)limit + FQ_REF_BLOCK_ROWS - 1) / FQ_REF_BLOCK_ROWS;
       p.n_rows = std::min<uint64_t>(p.n_rows, std::max<uint64_t>(blocks, 1) * FQ_REF_BLOCK_ROWS);

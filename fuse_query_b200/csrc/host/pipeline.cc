@@ -575,10 +575,13 @@ SendableDataBlockStream GpuPipeTransform::execute() {
     if (exact_errors) {
       // The reference pulls this pipe's 10 000-row blocks one by one: FilterTransform evaluates the predicate over the whole
       // block, ProjectionTransform every kept row of it (transform_projection.rs:45-56), and only then LimitStream cuts
-      // (stream_limit.rs:28-48) and stops pulling.  The fused kernel evaluates the predicate over rows the reference never
-      // pulls and projects only the rows it writes, so errors are settled here over exactly the reference's rows.
+      // (stream_limit.rs:28-48).  LimitStream::poll_next polls its input BEFORE it looks at its counter (:58-62), so the
+      // block after the one that completes the limit is still pulled — filtered, projected, and its error passed on —
+      // before the stream ends.  The fused kernel evaluates the predicate over rows the reference never pulls and projects
+      // only the rows it writes, so errors are settled here over exactly the reference's rows: everything up to the end of
+      // the block FOLLOWING the one that holds the limit-th kept row.
       const uint64_t rows = block->rows();
-      const uint64_t blk_end = r.limit_reached ? std::min<uint64_t>(rows, (r.limit_row / 10000 + 1) * 10000) : rows;
+      const uint64_t blk_end = r.limit_reached ? std::min<uint64_t>(rows, (r.limit_row / 10000 + 2) * 10000) : rows;
       if (!deferred.empty()) {
         if (!r.limit_reached) throw FuseQueryError(FuseQueryError::Internal, deferred);
         run_project(gpu, slice_block(*block, 0, blk_end), pred.get(), raw, -1, false);            // throws iff the error is inside

@@ -77,6 +77,7 @@ struct fq_launch_params {
   fq_u32 accumulate;
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
+  fq_u32 stages2;        // staged select kernel: != 0 when pass 2 of dense segments is staged too (slots hold every referenced column)
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
   // multi-GPU merge point fused into the aggregate kernel (fq_group, include/fuse_gpu.h): after the fold the last CTA
   // stores the running state into its row of EVERY rank's exchange window (peer GPUs' memory over NVLink), waits until
@@ -887,13 +888,18 @@ __device__ __forceinline__ fq_u32 fq_sel_scan_counts(fq_u32 (*cnt)[FQ_MAX_WARPS]
 // prefix for segment 0).  The aggregate therefore becomes visible the moment the segment has been streamed and never
 // queues behind the scan warp, which may still be looking back for the previous segment — with the scan warp
 // publishing it, every look-back waited for the look-backs before it (a convoy: 7-10 us per segment per CTA).
-__device__ __forceinline__ void fq_sel_publish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps) {
+// Returns true in the warp that arrived last, with the segment total in *tot_out.
+__device__ __forceinline__ bool fq_sel_publish_agg(const fq_launch_params &p, fq_u64 seg, unsigned long long *acc, fq_u32 wsum, int nwarps,
+                                                   fq_u32 *tot_out = nullptr) {
   const unsigned long long old = atomicAdd(acc, (1ull << 32) | (unsigned long long)wsum);
   if ((int)(old >> 32) == nwarps - 1) {
     const fq_u64 tot = (fq_u64)((fq_u32)old + wsum);
     *acc = 0ull;   // the slot is reused three segments later, after two named barriers
     fq_st_volatile(p.tile_status + seg, (seg == 0 ? FQ_TILE_PREFIX : FQ_TILE_AGG) | tot);
+    if (tot_out) *tot_out = (fq_u32)tot;
+    return true;
   }
+  return false;
 }
 
 // scan warp, step 2: resolve the segment's exclusive global base by a look-back over the 64-bit descriptors
@@ -975,19 +981,119 @@ __device__ __forceinline__ void fq_group_load(const fq_launch_params &p, fq_u64 
   }
 }
 
-// Pass 2 of one segment (kept out of line: it runs once per 128 KB and would otherwise double the register
-// pressure of the streaming loop).  `cnt` = this segment's ring slot of exclusive offsets, `base` its global base.
-// Dense tiles (the warp kept at least 1/8 of its rows) re-read the warp's whole run with all loads in flight; sparse
-// tiles load only the vector groups of the threads that kept something (a 1/1024 selection re-reads 3 % of the tile
-// instead of 25 %).  Per-thread predicated loads for both cases were measured slower on dense selections (7.9 vs
-// 5.9 ms for all of 1e9 rows).  The re-reads hit L2: at most resident CTAs * 3 segments are between the passes.
+// The (tile, worker warp) run that holds output row capacity - 1 records which source row produced it (result[5],
+// fq_pipe_fetch_limit_row): one run per launch at most, so the ranking is simply redone here, off the hot path.
+template <class Q, int U>
+__device__ __noinline__ void fq_note_limit_row(const fq_launch_params &p, fq_u64 tile, int wthreads, fq_u32 keep, fq_u64 pos0) {
+  constexpr int V = Q::V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u32 lt_mask = (1u << lane) - 1u;
+  for (int u = 0; u < U; u++) {
+    fq_u32 before = 0, tot = 0;
+    for (int v = 0; v < V; v++) {
+      const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
+      before += __popc(bmask & lt_mask);
+      tot += __popc(bmask);
+    }
+    fq_u64 pos = pos0 + before;
+    const fq_u64 row0 = ((tile * (fq_u64)wthreads + (fq_u64)warp * 32) * U + lane + 32ull * u) * V;   // first row of this group
+    for (int v = 0; v < V; v++) {
+      if ((keep >> (u * V + v)) & 1u) {
+        if (pos + 1 == p.capacity) p.result[5] = row0 + v;
+        pos++;
+      }
+    }
+    pos0 += tot;
+  }
+}
+
+// Scatter of one (tile, worker warp) run whose rows are in registers (loaded from L2 or from a staged tile): rank every
+// kept row with ballots over the warp, project at scatter time.  `pos0` = output position of the run's first kept row.
+template <class Q, int U>
+__device__ __forceinline__ void fq_scatter_rows(const fq_launch_params &p, fq_u64 tile, int wthreads, fq_u32 keep, fq_u64 pos0,
+                                                const typename Q::Rows (&rows)[U], fq_u32 &err) {
+  constexpr int V = Q::V;
+  const int lane = threadIdx.x & 31;
+  const fq_u32 lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    fq_u32 before = 0, tot = 0;
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
+      before += __popc(bmask & lt_mask);
+      tot += __popc(bmask);
+    }
+    fq_u64 pos = pos0 + before;
+    if (tot == 32u * V && (pos0 % V) == 0 && pos + V <= p.capacity) {
+      // the warp kept the whole group (range predicates over sorted data: groups are all-or-nothing) and the
+      // output position keeps the vector alignment: one vector store per output column instead of V scalar ones
+      Q::emit_vec(rows[u], p, pos, err);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        if ((keep >> (u * V + v)) & 1u) {
+          if (pos < p.capacity) Q::emit(rows[u], v, p, pos, err);
+          pos++;
+        }
+      }
+    }
+    pos0 += tot;
+  }
+}
+
+// Pass 2 of one (tile, worker warp) run from global memory (L2).  Dense runs (the warp kept at least 1/8 of its rows)
+// re-read the warp's whole run with all loads in flight; sparse runs load only the vector groups of the threads that kept
+// something (a 1/1024 selection re-reads 3 % of the tile instead of 25 %).  Per-thread predicated loads for both cases
+// were measured slower on dense selections (7.9 vs 5.9 ms for all of 1e9 rows).
+template <class Q, int U>
+__device__ __forceinline__ void fq_scatter_tile_global(const fq_launch_params &p, fq_u64 tile, int wthreads, fq_u32 keep, fq_u32 wkept,
+                                                       fq_u64 pos0, fq_u32 &err) {
+  constexpr int V = Q::V;
+  constexpr int BITS = U * V;
+  const int lane = threadIdx.x & 31;
+  const fq_u32 lt_mask = (1u << lane) - 1u;
+  if (pos0 < p.capacity && p.capacity <= pos0 + wkept) fq_note_limit_row<Q, U>(p, tile, wthreads, keep, pos0);
+  if (wkept * 8 >= 32 * BITS) {
+    typename Q::Rows rows[U];
+    fq_tile_load<Q, U>(p, tile, wthreads, rows);   // L2 hit
+    fq_scatter_rows<Q, U>(p, tile, wthreads, keep, pos0, rows, err);
+  } else {
+#pragma unroll 1
+    for (int u = 0; u < U; u++) {
+      const fq_u32 ku = (keep >> (u * V)) & ((1u << V) - 1u);
+      if (__ballot_sync(0xffffffffu, ku != 0) == 0) continue;
+      typename Q::Rows r;
+      if (ku) fq_group_load<Q, U>(p, tile, wthreads, u, r);
+      fq_u32 before = 0, tot = 0;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const fq_u32 bmask = __ballot_sync(0xffffffffu, (ku >> v) & 1u);
+        before += __popc(bmask & lt_mask);
+        tot += __popc(bmask);
+      }
+      fq_u64 pos = pos0 + before;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        if ((ku >> v) & 1u) {
+          if (pos < p.capacity) Q::emit(r, v, p, pos, err);
+          pos++;
+        }
+      }
+      pos0 += tot;
+    }
+  }
+}
+
+// Pass 2 of one segment from global memory (kept out of line: it runs once per segment and would otherwise double the
+// register pressure of the streaming loop).  `cnt` = this segment's ring slot of exclusive offsets, `base` its global
+// base.  The re-reads hit L2: at most resident CTAs * LAG segments are between the passes.
 template <class Q, int U, int SEG>
 __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64 sseg, fq_u64 skeep, const fq_u32 (*cnt)[FQ_MAX_WARPS],
                                                fq_u64 base, int wthreads, fq_u32 *err_out) {
   constexpr int V = Q::V;
   constexpr int BITS = U * V;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const fq_u32 lt_mask = (1u << lane) - 1u;
+  const int warp = threadIdx.x >> 5;
   fq_u32 err = 0;
   if (base >= p.capacity) return;
 #pragma unroll
@@ -995,70 +1101,56 @@ __device__ __noinline__ void fq_select_scatter(const fq_launch_params &p, fq_u64
     const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
     const fq_u32 wkept = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
     if (wkept == 0) continue;
-    fq_u64 pos0 = base + cnt[t][warp];
-    if (wkept * 8 >= 32 * BITS) {
-      typename Q::Rows rows[U];
-      fq_tile_load<Q, U>(p, sseg * SEG + t, wthreads, rows);   // L2 hit
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        fq_u32 before = 0, tot = 0;
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const fq_u32 bmask = __ballot_sync(0xffffffffu, (keep >> (u * V + v)) & 1u);
-          before += __popc(bmask & lt_mask);
-          tot += __popc(bmask);
-        }
-        fq_u64 pos = pos0 + before;
-        const fq_u64 row0 = (((sseg * SEG + t) * (fq_u64)wthreads + (fq_u64)warp * 32) * U + lane + 32ull * u) * V;   // first row of this group
-        if (tot == 32u * V && (pos0 % V) == 0 && pos + V <= p.capacity) {
-          // the warp kept the whole group (range predicates over sorted data: groups are all-or-nothing) and the
-          // output position keeps the vector alignment: one vector store per output column instead of V scalar ones
-          Q::emit_vec(rows[u], p, pos, err);
-          if (pos + V == p.capacity) p.result[5] = row0 + V - 1;
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            if ((keep >> (u * V + v)) & 1u) {
-              if (pos < p.capacity) {
-                Q::emit(rows[u], v, p, pos, err);
-                if (pos + 1 == p.capacity) p.result[5] = row0 + v;
-              }
-              pos++;
-            }
-          }
-        }
-        pos0 += tot;
-      }
-    } else {
+    fq_scatter_tile_global<Q, U>(p, sseg * SEG + t, wthreads, keep, wkept, base + cnt[t][warp], err);
+  }
+  if (err) *err_out |= err;
+}
+
+// Pass 2 of one DENSE segment of the staged select kernel: the producer staged the segment's full tiles again (every
+// referenced column).  Every consumer warp takes every slot (work or not), copies its rows to registers, hands the slot
+// back and then ranks + writes.  sr = {ring slot, round} of the next staged tile, updated.  Out of line like
+// fq_select_scatter, for the same reason.
+template <class Q, int U, int SEG, int STAGES>
+__device__ __noinline__ void fq_select_scatter_staged(const fq_launch_params &p, fq_u64 sseg, fq_u64 skeep, const fq_u32 (*cnt)[FQ_MAX_WARPS],
+                                                      fq_u64 base, int cthreads, fq_u64 *bars, fq_u32 stage_bytes, fq_u64 n_full_tiles,
+                                                      fq_u32 (&sr)[2], fq_u32 *err_out) {
+  constexpr int V = Q::V;
+  constexpr int BITS = U * V;
+  extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const fq_u32 tile_rows = (fq_u32)cthreads * U * V;
+  const int stages = (int)p.stages;
+  int slot = (int)sr[0];
+  fq_u32 round = sr[1];
+  fq_u32 err = 0;
+  const bool live = base < p.capacity;
 #pragma unroll 1
-      for (int u = 0; u < U; u++) {
-        const fq_u32 ku = (keep >> (u * V)) & ((1u << V) - 1u);
-        if (__ballot_sync(0xffffffffu, ku != 0) == 0) continue;
-        typename Q::Rows r;
-        if (ku) fq_group_load<Q, U>(p, sseg * SEG + t, wthreads, u, r);
-        fq_u32 before = 0, tot = 0;
+  for (int t = 0; t < SEG; t++) {
+    const fq_u64 tile = sseg * SEG + t;
+    const fq_u32 keep = (fq_u32)(skeep >> (t * BITS)) & (BITS >= 32 ? 0xffffffffu : ((1u << (BITS & 31)) - 1u));
+    const fq_u32 wkept = __reduce_add_sync(0xffffffffu, (fq_u32)__popc(keep));
+    const fq_u64 pos0 = base + cnt[t][warp];
+    if (tile < n_full_tiles) {
+      fq_mbar_wait(fq_smem_addr(&bars[slot]), round & 1);
+      typename Q::Rows rows[U];
+      if (live && wkept) {
+        const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
 #pragma unroll
-        for (int v = 0; v < V; v++) {
-          const fq_u32 bmask = __ballot_sync(0xffffffffu, (ku >> v) & 1u);
-          before += __popc(bmask & lt_mask);
-          tot += __popc(bmask);
-        }
-        fq_u64 pos = pos0 + before;
-        const fq_u64 row0 = (((sseg * SEG + t) * (fq_u64)wthreads + (fq_u64)warp * 32) * U + lane + 32ull * u) * V;
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          if ((ku >> v) & 1u) {
-            if (pos < p.capacity) {
-              Q::emit(r, v, p, pos, err);
-              if (pos + 1 == p.capacity) p.result[5] = row0 + v;
-            }
-            pos++;
-          }
-        }
-        pos0 += tot;
+        for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
       }
+      __syncwarp();
+      if (lane == 0) fq_mbar_arrive(fq_smem_addr(&bars[STAGES + slot]));   // the rows are in registers: hand the slot back
+      if (++slot == stages) { slot = 0; round++; }
+      if (live && wkept) {
+        if (pos0 < p.capacity && p.capacity <= pos0 + wkept) fq_note_limit_row<Q, U>(p, tile, cthreads, keep, pos0);
+        fq_scatter_rows<Q, U>(p, tile, cthreads, keep, pos0, rows, err);
+      }
+    } else if (live && wkept) {
+      fq_scatter_tile_global<Q, U>(p, tile, cthreads, keep, wkept, pos0, err);
     }
   }
+  sr[0] = (fq_u32)slot;
+  sr[1] = round;
   if (err) *err_out |= err;
 }
 
@@ -1203,18 +1295,29 @@ __device__ __forceinline__ void fq_select_kernel(const fq_launch_params &p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fq_select_tma_kernel — the select kernel with pass 1 staged by the bulk-copy engine.
+// fq_select_tma_kernel — the select kernel with BOTH passes staged by the bulk-copy engine.
 //
 // One CTA per SM = C consumer warps + 1 scan warp + 1 producer warp.  The producer lane claims segments
 // (atomicAdd), hands the ids to the other warps through a shared-memory ring and keeps a ring of `stages` tiles
-// in flight with cp.async.bulk (one copy per referenced column per tile, completion on full[s]); bytes in flight per
-// SM are therefore independent of the consumers' registers and of the time they spend in pass 2.  Consumers read
-// each staged tile with LDS.128 (lane l of warp w, group u: vector group w * 32U + 32u + l — the row order of
-// fq_tile_load, so pass 2 and the ranking code are shared with fq_select_kernel), evaluate the predicate, keep one
-// bit per row and per-(tile, warp) counts, and release the slot (one arrive per warp on empty[s]).  Scan warp,
-// look-back, named-barrier ring FULL/DONE and pass 2 (re-read of kept tiles from L2) are those of fq_select_kernel.
-// Tiles that are not entirely inside the source (the ragged end) are never staged: consumers load them with
-// fq_tile_load.  Producer and consumers count staged tiles with the same rule, so their slot/parity stay in step.
+// in flight with cp.async.bulk (one copy per column per tile, completion on full[s]); bytes in flight per
+// SM are therefore independent of the consumers' registers and of the time they spend in pass 2.
+//   pass 1   consumers read each staged tile (the predicate's columns) with LDS.128 (lane l of warp w, group u: vector
+//            group w * 32U + 32u + l — the row order of fq_tile_load, so the ranking code is shared with
+//            fq_select_kernel), evaluate the predicate, keep one bit per row and per-(tile, warp) counts, and release
+//            the slot (one arrive per warp on empty[s]).  The warp that finishes a segment last publishes its
+//            aggregate and decides whether the segment is DENSE (>= 1/8 of its rows kept and the output not yet full).
+//   pass 2   LAG segments later, when the scan warp has resolved the segment's base.  Sparse segments: the warps that
+//            kept something re-read just those vector groups from L2 (fq_scatter_tile_global).  Dense segments: the
+//            producer stages the segment's tiles AGAIN (every referenced column this time; an L2 hit when LAG * SEG
+//            tiles per SM fit) behind the pass-1 tiles of the current segment, so the re-read is as asynchronous as the
+//            first read: consumers find the rows in shared memory, copy them to registers, release the slot, rank with
+//            ballots and write.  With per-thread L2 re-reads instead (round 1) the L2 latency was exposed once per
+//            tile and a selection keeping every row ran at 0.70 of the copy peak.
+// Producer and consumers walk the same sequence of staged tiles: per iteration k the full tiles of the claimed segment,
+// then, if the segment of iteration k - LAG is dense, its full tiles again; at the end the pending segments oldest
+// first.  Tiles that are not entirely inside the source (the ragged end) are never staged: consumers load them with
+// fq_tile_load.  Scan warp, look-back and the named-barrier ring FULL/DONE are those of fq_select_kernel.
+// p.stages2 != 0 switches the staged pass 2 on (the host does when a stage of all referenced columns fits the ring).
 // ---------------------------------------------------------------------------------------------
 template <int V> struct fq_selt_shape {
   static constexpr int U = (FQ_SELT_UNROLL * V <= 32) ? FQ_SELT_UNROLL : (32 / V);
@@ -1231,6 +1334,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   constexpr int R = LAG + 1;                  // ring of count / base slots and of FULL / DONE named barriers
   constexpr int BAR_FULL = 2, BAR_DONE = 2 + R;
   static_assert(2 + 2 * R <= 16, "named barriers");
+  static_assert(LAG + 1 <= FQ_SELT_CLAIMS, "claim ring");
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
   __shared__ fq_u32 s_cnt[R][SEG][FQ_MAX_WARPS];
   __shared__ fq_u64 s_excl[R];
@@ -1238,6 +1342,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   __shared__ volatile fq_u64 s_seg[FQ_SELT_CLAIMS];
   __shared__ volatile fq_u32 s_stop[FQ_SELT_CLAIMS];
   __shared__ volatile int s_ready[FQ_SELT_CLAIMS];
+  __shared__ volatile int s_p1[R];            // iteration k finished pass 1: (k + 1) << 1 | dense
+  __shared__ volatile fq_u64 s_lastbase;      // base of the segment this CTA resolved last (monotone)
   __shared__ __align__(8) fq_u64 s_bars[2 * STAGES];   // full[0..STAGES), empty[0..STAGES)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1246,15 +1352,19 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES;   // pass 1 stages the predicate's columns only
+  const bool stage2 = p.stages2 != 0;
+  // one slot holds a pass-1 tile (the predicate's columns) or, with the staged pass 2, a tile of every referenced column
+  const fq_u32 pred_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES, all_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 stage_bytes = stage2 ? all_bytes : pred_bytes;
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
   const int stages = (int)p.stages;
   fq_u32 err = 0;
 
   if (threadIdx.x < FQ_SELT_CLAIMS) s_ready[threadIdx.x] = 0;
-  if (threadIdx.x < R) s_acc[threadIdx.x] = 0ull;
+  if (threadIdx.x < R) { s_acc[threadIdx.x] = 0ull; s_p1[threadIdx.x] = 0; }
   if (threadIdx.x == 0) {
+    s_lastbase = 0;
     for (int s = 0; s < stages; s++) {
       fq_mbar_init(fq_smem_addr(&s_bars[s]), 1);
       fq_mbar_init(fq_smem_addr(&s_bars[STAGES + s]), cwarps);
@@ -1269,6 +1379,31 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     if (lane == 0) {
       int slot = 0;          // ring slot and round of the next staged tile (no 64-bit divisions in the loop)
       fq_u32 round = 0;
+      fq_u64 hist[R];        // segments of the last iterations (registers: constant indexes after unrolling)
+#pragma unroll
+      for (int j = 0; j < R; j++) hist[j] = 0;
+      auto stage_tile = [&](fq_u64 tile, bool all_cols) {
+        if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
+        const fq_u32 full = fq_smem_addr(&s_bars[slot]);
+        const fq_u32 dst = fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes);
+        if (all_cols) {
+          fq_mbar_expect_tx(full, all_bytes);
+          Q::tma_issue(p, dst, full, tile, (fq_u32)tile_rows);
+        } else {
+          fq_mbar_expect_tx(full, pred_bytes);
+          Q::tma_issue_pred(p, dst, full, tile, (fq_u32)tile_rows);
+        }
+        if (++slot == stages) { slot = 0; round++; }
+      };
+      // pass 2 of iteration j (segment sj): staged again when the consumers found it dense
+      auto stage_pass2 = [&](int j, fq_u64 sj) {
+        int v;
+        while (((v = s_p1[j % R]) >> 1) != j + 1) {}
+        if (!(v & 1)) return;
+#pragma unroll 1
+        for (int t = 0; t < SEG; t++)
+          if (sj * SEG + t < n_full_tiles) stage_tile(sj * SEG + t, true);
+      };
       fq_u64 c = atomicAdd(p.tile_counter, 1u);
       for (int k = 0;; k++) {
         const fq_u32 st = (p.stop_after != 0 && fq_ld_volatile32(p.done) != 0) ? 1u : 0u;
@@ -1278,20 +1413,25 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
         s_stop[k % FQ_SELT_CLAIMS] = st;
         __threadfence_block();
         s_ready[k % FQ_SELT_CLAIMS] = k + 1;
-        if (!(c < n_seg) || st) break;
+        if (!(c < n_seg) || st) {
+          if (stage2) {   // drain: the consumers scatter what is pending, oldest first
+#pragma unroll
+            for (int a = LAG; a >= 1; a--)
+              if (k - a >= 0) stage_pass2(k - a, hist[a - 1]);
+          }
+          break;
+        }
         // the next claim's round trip to L2 overlaps the copies of this segment (its value is first used next iteration)
         const fq_u64 c_next = atomicAdd(p.tile_counter, 1u);
 #pragma unroll 1
         for (int t = 0; t < SEG; t++) {
           const fq_u64 tile = c * SEG + t;
-          if (tile < n_full_tiles) {
-            if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
-            const fq_u32 full = fq_smem_addr(&s_bars[slot]);
-            fq_mbar_expect_tx(full, stage_bytes);
-            Q::tma_issue_pred(p, fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes), full, tile, (fq_u32)tile_rows);
-            if (++slot == stages) { slot = 0; round++; }
-          }
+          if (tile < n_full_tiles) stage_tile(tile, false);
         }
+        if (stage2 && k >= LAG) stage_pass2(k - LAG, hist[LAG - 1]);
+#pragma unroll
+        for (int j = R - 1; j > 0; j--) hist[j] = hist[j - 1];
+        hist[0] = c;          // hist[a - 1] = segment of iteration k - a at the next iteration
         c = c_next;
       }
     }
@@ -1313,6 +1453,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
       prev_incl = excl + tot;
       if (lane == 0) {
         s_excl[b] = excl;
+        s_lastbase = excl;
         const fq_u64 incl = excl + tot;
         if (p.stop_after != 0 && incl >= p.stop_after) {
           *(volatile fq_u32 *)p.done = 1u;
@@ -1327,16 +1468,24 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   }
 
   // ================= consumer warps =================
+  int slot = 0;          // ring slot and round of the next staged tile (same count as the producer's)
+  fq_u32 round = 0;
   auto scatter = [&](fq_u64 sseg, fq_u64 skeep, int sb) {
     fq_bar_sync(BAR_DONE + sb, barthreads);
-    fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, &err);
+    if (!(stage2 && (s_p1[sb] & 1))) {
+      fq_select_scatter<Q, U, SEG>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, &err);
+      return;
+    }
+    // dense segment: its full tiles were staged again (every referenced column) — consume every slot, work or not
+    fq_u32 sr[2] = {(fq_u32)slot, round};
+    fq_select_scatter_staged<Q, U, SEG, STAGES>(p, sseg, skeep, s_cnt[sb], s_excl[sb], cthreads, s_bars, stage_bytes, n_full_tiles, sr, &err);
+    slot = (int)sr[0];
+    round = sr[1];
   };
   fq_u64 keepq[LAG], segq[LAG];   // segments streamed but not yet scattered, newest first (registers: constant indexes)
 #pragma unroll
   for (int j = 0; j < LAG; j++) keepq[j] = segq[j] = 0;
   int pending = 0;
-  int slot = 0;          // ring slot and round of the next staged tile (same count as the producer's)
-  fq_u32 round = 0;
   for (int k = 0;; k++) {
     const int b = k % R;
     if (lane == 0) {
@@ -1376,7 +1525,15 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
         if (lane == 0) s_cnt[b][t][warp] = wcount;
         wsum += wcount;
       }
-      if (lane == 0) fq_sel_publish_agg(p, seg, &s_acc[b], wsum, cwarps);
+      if (lane == 0) {
+        fq_u32 tot = 0;
+        if (fq_sel_publish_agg(p, seg, &s_acc[b], wsum, cwarps, &tot)) {
+          // last warp of the segment: dense segments get their pass 2 staged (producer and consumers read this one flag)
+          const bool dense = stage2 && (fq_u64)tot * 8 >= tile_rows * SEG && s_lastbase < p.capacity;
+          __threadfence_block();
+          s_p1[b] = ((k + 1) << 1) | (dense ? 1 : 0);
+        }
+      }
     }
     __syncwarp();
     fq_bar_arrive(BAR_FULL + b, barthreads);

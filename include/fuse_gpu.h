@@ -289,9 +289,10 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
                                  fq_column *const *out_valid, uint64_t capacity, int64_t limit, uint32_t flags, void *stream);
 fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selected, uint64_t *rows_written);
 /* When the last launch filled min(limit, capacity) output rows: the source row (index into the launch's source) that
- * produced the LAST of them — the row that completes the LIMIT.  The reference evaluates the projection over every kept
- * row of the 10 000-row block holding that row before LimitStream cuts it (transform_projection.rs:45-56 runs before
- * stream_limit.rs:28-48), so a caller that wants the reference's errors re-checks the rest of that block. */
+ * produced the LAST of them — the row that completes the LIMIT.  The reference evaluates predicate and projection over
+ * every row of the 10 000-row block holding that row before LimitStream cuts it (transform_projection.rs:45-56 runs
+ * before stream_limit.rs:28-48), and of the block after it (LimitStream polls its input before it checks its counter,
+ * :58-62); a caller that wants exactly the reference's errors evaluates up to the end of that block and no further. */
 fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row);
 
 #ifdef __cplusplus

@@ -596,14 +596,15 @@ def test_validity_masks_are_canonicalised_on_upload(gpu):
 
 @pytest.mark.parametrize("generated", [False, True])
 def test_projection_errors_beyond_the_limit_follow_the_reference_blocks(gpu, generated):
-    """The reference projects every kept row of a 10 000-row block before LimitStream cuts it and stops pulling
-    (transform_projection.rs:45-56, stream_limit.rs:28-48): a zero divisor in a kept row AFTER the LIMIT-th row but in the
-    same block is an error; in a later block it is never evaluated.  The fused kernel only projects the rows it writes,
-    so GpuPipeTransform settles the errors over exactly the reference's rows (block_quirks, default on); with the option
-    off the launch's own outcome stands."""
+    """The reference projects every kept row of a 10 000-row block before LimitStream cuts it, and LimitStream polls its
+    input once more before it notices that the limit is complete (transform_projection.rs:45-56, stream_limit.rs:28-62): a
+    zero divisor in a kept row AFTER the LIMIT-th row is an error when it sits in the same block or in the next one; two
+    blocks on it is never evaluated.  The fused kernel only projects the rows it writes, so GpuPipeTransform settles the
+    errors over exactly the reference's rows (block_quirks, default on); with the option off the launch's own outcome
+    stands."""
     from fuse_query_b200.tables import register_table
     n = 80_000                                    # one source pipe (workers = 1): eight 10 000-row blocks
-    cases = [(50, True), (9_999, True), (10_000, False), (10_050, False), (3, True)]     # zero divisor at row -> error?
+    cases = [(50, True), (9_999, True), (10_000, True), (19_999, True), (20_000, False), (30_050, False), (3, True)]   # zero divisor at row -> error?
     for row, want_error in cases:
         d = np.ones(n, dtype=np.uint64)
         d[row] = 0
@@ -633,7 +634,7 @@ def test_projection_errors_beyond_the_limit_follow_the_reference_blocks(gpu, gen
     # the predicate itself: evaluated over whole blocks up to the one completing the limit, never beyond
     ctx = make_ctx(gpu, 1)
     ctx.options.generated = generated
-    sql = "select number from system.numbers_mt(80000) where 100 / (number - 20000) < 1000 limit 5"     # zero divisor at row 20 000
+    sql = "select number from system.numbers_mt(80000) where 100 / (number - 20000) < 1000 limit 5"     # zero divisor at row 20 000: block 2
     want = o.run_query(["(col number)"], total=80_000, predicate="(< (/ (u64 100) (- (col number) (u64 20000))) (u64 1000))", limit=5,
                        worker_threads=1)
     assert rows_of(h.execute_sql(ctx, sql)) == want.rows() and len(want.rows()) == 5
