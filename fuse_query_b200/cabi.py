@@ -19,12 +19,13 @@ DTYPE_NAMES = ["Null", "Boolean", "Int8", "Int16", "Int32", "Int64", "UInt8", "U
                "Float32", "Float64", "Utf8", "Struct"]
 DTYPE_SIZE = {BOOL: 1, I8: 1, I16: 2, I32: 4, I64: 8, U8: 1, U16: 2, U32: 4, U64: 8, F32: 4, F64: 8}
 
-OK, ERR_INTERNAL, ERR_PLAN, ERR_DIVIDE_BY_ZERO, ERR_UNSUPPORTED, ERR_CUDA, ERR_INVALID = range(7)
+OK, ERR_INTERNAL, ERR_PLAN, ERR_DIVIDE_BY_ZERO, ERR_UNSUPPORTED, ERR_CUDA, ERR_INVALID, ERR_CAPACITY = range(8)
 EXPR_ALIAS, EXPR_CONSTANT, EXPR_FIELD, EXPR_ARITHMETIC, EXPR_COMPARISON, EXPR_LOGIC, EXPR_AGGREGATOR = range(7)
-PIPE_PROJECT, PIPE_AGGREGATE = 0, 1
+PIPE_PROJECT, PIPE_AGGREGATE, PIPE_GROUPBY = 0, 1, 2
 RUN_ACCUMULATE, RUN_LIMIT_EARLY_EXIT, RUN_BLOCK_STATS = 1, 2, 4
 STATE_HEADER_SLOTS = 6   # FQ_STATE_HEADER_SLOTS
 MAX_COLS = MAX_EXPRS = 8
+MAX_KEYS = 4
 
 AGG = {"min": 0, "max": 1, "sum": 2, "count": 3}
 CMP = {"=": 0, "<": 1, "<=": 2, ">": 3, ">=": 4}
@@ -55,7 +56,7 @@ class Source(C.Structure):
 class PipeDesc(C.Structure):
     _fields_ = [("n_cols", C.c_int32), ("col_dtypes", C.c_int32 * MAX_COLS), ("col_nullable", C.c_int32 * MAX_COLS), ("generated", C.c_int32),
                 ("nodes", C.POINTER(ExprNode)), ("n_nodes", C.c_int32), ("predicate", C.c_int32), ("kind", C.c_int32),
-                ("n_exprs", C.c_int32), ("exprs", C.c_int32 * MAX_EXPRS)]
+                ("n_exprs", C.c_int32), ("exprs", C.c_int32 * MAX_EXPRS), ("n_keys", C.c_int32), ("keys", C.c_int32 * MAX_KEYS)]
 
 
 class FuseGpuError(Exception):
@@ -76,6 +77,8 @@ EXPORTS = [
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_build_kind", "fq_pipe_source",
     "fq_pipe_expr_dtype", "fq_pipe_expr_nullable", "fq_pipe_launch_aggregate", "fq_pipe_fetch_aggregate", "fq_pipe_fetch_block_stats", "fq_pipe_aggregator_nodes",
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project", "fq_pipe_fetch_limit_row",
+    "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
+    "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
 ]
 
 _lib = None
@@ -140,6 +143,15 @@ def lib():
         "fq_pipe_launch_project": (i32, [vp, vp, C.POINTER(Source), C.POINTER(vp), C.POINTER(vp), u64, i64, u32, vp]),
         "fq_pipe_fetch_project": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "fq_pipe_fetch_limit_row": (i32, [vp, vp, C.POINTER(u64)]),
+        "fq_pipe_key_dtype": (i32, [vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "fq_pipe_leaf_dtype": (i32, [vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]),
+        "fq_pipe_groupby_reserve": (i32, [vp, vp, u64]),
+        "fq_pipe_launch_groupby": (i32, [vp, vp, C.POINTER(Source), u32, vp]),
+        "fq_pipe_fetch_groupby": (i32, [vp, vp, C.POINTER(u64)]),
+        "fq_pipe_export_groups": (i32, [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64, vp]),
+        "fq_pipe_group_entry_slots": (i32, [vp, vp, C.POINTER(i32)]),
+        "fq_pipe_export_partials": (i32, [vp, vp, i32, vp, C.POINTER(u64), vp]),
+        "fq_pipe_merge_partials": (i32, [vp, vp, vp, u64, u32, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -318,10 +330,12 @@ class Context:
     # ---- pipes ----
     def pipe(self, exprs: Sequence[str], *, columns: Sequence[str] = ("number",), dtypes: Sequence[int] = (U64,),
              predicate: Optional[str] = None, aggregate: bool = False, generated: bool = False,
-             nullable: Sequence[bool] = ()) -> "Pipe":
+             nullable: Sequence[bool] = (), keys: Sequence[str] = ()) -> "Pipe":
+        """`keys` (GROUP BY expressions) makes it a hash-aggregation pipe; `exprs` are then the aggregate expressions."""
         b = ExprBuilder(columns)
         pred = b.add(predicate) if predicate else -1
         roots = [b.add(e) for e in exprs]
+        key_roots = [b.add(k) for k in keys]
         d = PipeDesc()
         d.n_cols = len(columns)
         for i, t in enumerate(dtypes):
@@ -333,13 +347,18 @@ class Context:
         d.nodes = C.cast(nodes, C.POINTER(ExprNode))
         d.n_nodes = len(b.nodes)
         d.predicate = pred
-        d.kind = PIPE_AGGREGATE if aggregate else PIPE_PROJECT
+        d.kind = PIPE_GROUPBY if key_roots else (PIPE_AGGREGATE if aggregate else PIPE_PROJECT)
         d.n_exprs = len(roots)
         for i, r in enumerate(roots):
             d.exprs[i] = r
+        d.n_keys = len(key_roots)
+        for i, r in enumerate(key_roots):
+            d.keys[i] = r
         h = C.c_void_p()
         self.check(lib().fq_pipe_compile(self._h, C.byref(d), C.byref(h)))
-        return Pipe(self, h, b, roots, aggregate, generated)
+        p = Pipe(self, h, b, roots, aggregate or bool(key_roots), generated)
+        p.n_keys = len(key_roots)
+        return p
 
 
 class Column:
@@ -547,6 +566,75 @@ class Pipe:
             else:
                 out.append((v.dtype, v.v.i))
         return out, rows.value
+
+    # ---- group by ----
+    def key_dtype(self, j: int) -> Tuple[int, bool]:
+        t, nl = C.c_int32(), C.c_int32()
+        self.ctx.check(lib().fq_pipe_key_dtype(self.ctx._h, self._h, j, C.byref(t), C.byref(nl)))
+        return t.value, bool(nl.value)
+
+    def leaf_dtype(self, k: int) -> Tuple[int, bool]:
+        t, nl = C.c_int32(), C.c_int32()
+        self.ctx.check(lib().fq_pipe_leaf_dtype(self.ctx._h, self._h, k, C.byref(t), C.byref(nl)))
+        return t.value, bool(nl.value)
+
+    def groupby_reserve(self, groups: int) -> None:
+        self.ctx.check(lib().fq_pipe_groupby_reserve(self.ctx._h, self._h, groups))
+
+    def launch_groupby(self, source: Source, *, accumulate: bool = False, stream: int = 0) -> None:
+        self.ctx.check(lib().fq_pipe_launch_groupby(self.ctx._h, self._h, C.byref(source), RUN_ACCUMULATE if accumulate else 0, C.c_void_p(stream)))
+
+    def fetch_groupby(self) -> int:
+        n = C.c_uint64()
+        self.ctx.check(lib().fq_pipe_fetch_groupby(self.ctx._h, self._h, C.byref(n)))
+        return n.value
+
+    def run_groupby(self, source: Source, *, groups_hint: int = 1 << 16, stream: int = 0) -> int:
+        """reserve -> launch -> fetch, growing the table until the groups fit; returns the number of groups."""
+        hint = groups_hint
+        while True:
+            self.groupby_reserve(hint)
+            self.launch_groupby(source, stream=stream)
+            try:
+                return self.fetch_groupby()
+            except FuseGpuError as e:
+                if e.status != ERR_CAPACITY:
+                    raise
+                hint *= 8
+
+    def export_groups(self, n_groups: int, stream: int = 0):
+        """-> (key columns, key validity columns or None, leaf columns, leaf validity columns or None), device-resident"""
+        ctx = self.ctx
+        n_leaves = len(self.aggregator_nodes())
+        keys, kval, leaves, lval = [], [], [], []
+        for j in range(self.n_keys):
+            t, nl = self.key_dtype(j)
+            keys.append(ctx.column(t, max(1, n_groups)))
+            kval.append(ctx.column(BOOL, max(1, n_groups)) if nl else None)
+        for k in range(n_leaves):
+            t, nl = self.leaf_dtype(k)
+            leaves.append(ctx.column(t, max(1, n_groups)))
+            lval.append(ctx.column(BOOL, max(1, n_groups)) if nl else None)
+
+        def arr(cols):
+            return (C.c_void_p * max(1, len(cols)))(*[None if c is None else c._h for c in cols])
+        ctx.check(lib().fq_pipe_export_groups(ctx._h, self._h, arr(keys), arr(kval), arr(leaves), arr(lval), n_groups, C.c_void_p(stream)))
+        ctx.synchronize(stream)
+        return keys, kval, leaves, lval
+
+    def group_entry_slots(self) -> int:
+        n = C.c_int32()
+        self.ctx.check(lib().fq_pipe_group_entry_slots(self.ctx._h, self._h, C.byref(n)))
+        return n.value
+
+    def export_partials(self, world: int, entries: "Column", stream: int = 0) -> List[int]:
+        counts = (C.c_uint64 * 8)()
+        self.ctx.check(lib().fq_pipe_export_partials(self.ctx._h, self._h, world, entries._h, counts, C.c_void_p(stream)))
+        return [counts[i] for i in range(world)]
+
+    def merge_partials(self, entries: Optional["Column"], n_entries: int, *, accumulate: bool = False, stream: int = 0) -> None:
+        self.ctx.check(lib().fq_pipe_merge_partials(self.ctx._h, self._h, entries._h if entries is not None else None, n_entries,
+                                                     RUN_ACCUMULATE if accumulate else 0, C.c_void_p(stream)))
 
     # ---- projection / filter ----
     def launch_project(self, source: Source, outs: Sequence[Column], capacity: int, *, limit: int = -1, early_exit: bool = False,

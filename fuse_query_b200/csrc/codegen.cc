@@ -153,7 +153,7 @@ struct Gen {
       case FQ_EXPR_AGGREGATOR: {
         // Count(arg) evaluates and discards its argument (function_aggregator.rs:58-66).  A bare column or literal cannot
         // fail, so nothing has to be read for it: the column is typed but not marked as used.
-        const bool quiet = n->kind == FQ_EXPR_AGGREGATOR && n->op == FQ_AGG_COUNT && trivial(n->left) && d.kind == FQ_PIPE_AGGREGATE;
+        const bool quiet = n->kind == FQ_EXPR_AGGREGATOR && n->op == FQ_AGG_COUNT && trivial(n->left) && d.kind != FQ_PIPE_PROJECT;
         if (quiet) quiet_depth++;
         const bool ok = infer(n->left, depth + 1);
         if (quiet) quiet_depth--;
@@ -351,8 +351,18 @@ std::string identity_of(int op, fq_dtype t) {
 
 int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   *out = Generated();
-  if (d.n_cols < 0 || d.n_cols > FQ_MAX_COLS || d.n_exprs < 1 || d.n_exprs > FQ_MAX_EXPRS || !d.nodes || d.n_nodes < 1) {
+  const bool groupby = d.kind == FQ_PIPE_GROUPBY;
+  const bool agg_like = d.kind == FQ_PIPE_AGGREGATE || groupby;   // select expressions are trees over Aggregator leaves
+  if (d.n_cols < 0 || d.n_cols > FQ_MAX_COLS || d.n_exprs < (groupby ? 0 : 1) || d.n_exprs > FQ_MAX_EXPRS || !d.nodes || d.n_nodes < 1) {
     *err = "Error during plan: pipe needs 1..8 select expressions over at most 8 input columns";
+    return FQ_ERR_PLAN;
+  }
+  if (d.kind != FQ_PIPE_PROJECT && d.kind != FQ_PIPE_AGGREGATE && !groupby) {
+    *err = "Error during plan: unknown pipe kind";
+    return FQ_ERR_PLAN;
+  }
+  if (groupby ? (d.n_keys < 1 || d.n_keys > FQ_MAX_KEYS) : d.n_keys != 0) {
+    *err = groupby ? "Error during plan: a GROUP BY pipe needs 1..4 key expressions" : "Error during plan: only GROUP BY pipes take key expressions";
     return FQ_ERR_PLAN;
   }
   if (d.generated && d.n_cols < 1) {
@@ -375,8 +385,38 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   out->has_pred = d.predicate >= 0;
   out->generated_source = d.generated != 0;
 
+  // GROUP BY keys: typed like any expression; no aggregates, no bare constants
+  struct KeyInfo { int node; fq_dtype t; bool nullable; int shift, bits; };
+  std::vector<KeyInfo> keys;
+  if (groupby) {
+    int shift = 0;
+    for (int k = 0; k < d.n_keys; k++) {
+      if (!g.infer(d.keys[k])) { *err = g.err; return g.status; }
+      std::set<int> inner;
+      g.collect_aggs(d.keys[k], inner);
+      if (!inner.empty()) { *err = "Internal Error: Aggregate function is found in GROUP BY in query"; return FQ_ERR_INTERNAL; }
+      if (g.scalar[d.keys[k]]) { *err = "Unsupported on the device path: a constant GROUP BY expression"; return FQ_ERR_UNSUPPORTED; }
+      KeyInfo ki;
+      ki.node = d.keys[k];
+      ki.t = g.ty[d.keys[k]];
+      ki.nullable = g.maybe_null(d.keys[k]);
+      ki.bits = (int)dtype_size(ki.t) * 8;
+      ki.shift = shift;
+      shift += ki.bits + (ki.nullable ? 1 : 0);
+      keys.push_back(ki);
+      out->key_dtypes.push_back(ki.t);
+      out->key_nullable.push_back(ki.nullable ? 1 : 0);
+      out->key_shift.push_back(ki.shift);
+      out->key_bits.push_back(ki.bits);
+    }
+    if (shift > 64) {
+      *err = fmt("Unsupported on the device path: GROUP BY keys of %d bits (values plus one bit per nullable key) do not pack into 64", shift);
+      return FQ_ERR_UNSUPPORTED;
+    }
+  }
+
   std::set<int> aggs;
-  if (d.kind == FQ_PIPE_AGGREGATE) {
+  if (agg_like) {
     for (int e = 0; e < d.n_exprs; e++) g.collect_aggs(d.exprs[e], aggs);
     for (int a : aggs) {
       const fq_expr_node &n = d.nodes[a];
@@ -444,7 +484,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   s += "struct Q_@ {\n";
   bool has_sum = false;
   for (int op : out->agg_ops) has_sum = has_sum || op == FQ_AGG_SUM;
-  out->track_blocks = out->has_pred && has_sum;   // only Sum is poisoned by an empty block
+  out->track_blocks = out->has_pred && has_sum && !groupby;   // only Sum is poisoned by an empty block
   s += fmt("  static constexpr int V = %d;\n  static constexpr int NSLOTS = %d;\n  static constexpr bool HAS_PRED = %s;\n"
            "  static constexpr bool TRACK_BLOCKS = %s;\n", V, n_slots, out->has_pred ? "true" : "false", out->track_blocks ? "true" : "false");
   s += "  struct Rows {";
@@ -564,7 +604,92 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     s += "    return true;\n  }\n";
   }
 
-  if (d.kind == FQ_PIPE_AGGREGATE) {
+  if (groupby) {
+    // ---- hash aggregation: per row the packed key and the encoded value of every leaf; per group G 8-byte slots ----
+    const int n = n_leaves;
+    auto is_f = [&](int k) { return is_float(out->agg_dtypes[k]); };
+    auto is_s = [&](int k) { return is_signed_int(out->agg_dtypes[k]); };
+    s += fmt("  static constexpr int G = %d;\n", 1 + n_slots);
+    s += "  __device__ static __forceinline__ bool gb_row(const Rows &r, int v, fq_u32 &err, fq_u64 &key, fq_u64 (&val)[NSLOTS > 0 ? NSLOTS : 1], fq_u32 &vmask) {\n";
+    if (out->has_pred) s += "    if (!pred(r, v, err)) return false;\n";
+    {
+      Gen::Emitter e(g, "    ");
+      std::string st = "    key = 0ull;\n    vmask = 0u;\n";
+      for (const KeyInfo &ki : keys) {
+        e.node(ki.node);
+        std::string bits;
+        const std::string &x = e.val[ki.node];
+        switch (ki.t) {
+          case FQ_F32: bits = "(fq_u64)__float_as_uint(" + x + ")"; break;
+          case FQ_F64: bits = "(fq_u64)__double_as_longlong(" + x + ")"; break;
+          case FQ_BOOL: bits = "(fq_u64)((" + x + ") ? 1u : 0u)"; break;
+          default: bits = fmt("(fq_u64)(fq_traits<%s>::unsigned_t)(", ctype(ki.t)) + x + ")";
+        }
+        if (ki.nullable) st += fmt("    key |= (%s) ? (%s << %d) : (1ull << %d);\n", e.ok[ki.node].c_str(), bits.c_str(), ki.shift, ki.shift + ki.bits);
+        else st += fmt("    key |= %s << %d;\n", bits.c_str(), ki.shift);
+      }
+      for (int k = 0; k < n; k++) {
+        const fq_expr_node &an = d.nodes[out->agg_nodes[k]];
+        if (an.op == FQ_AGG_COUNT) {
+          // Count evaluates (and discards) its argument, function_aggregator.rs:58-66: only its error checks remain
+          if (!g.trivial(an.left)) { e.node(an.left); st += "    (void)" + e.val[an.left] + ";\n"; }
+          st += fmt("    val[%d] = 0ull;\n", k);
+          continue;
+        }
+        e.node(an.left);
+        const std::string &x = e.val[an.left];
+        std::string enc;
+        if (is_f(k)) enc = an.op == FQ_AGG_SUM ? "(fq_u64)__double_as_longlong((double)(" + x + "))" : "fq_f64_ordered((double)(" + x + "))";
+        else if (is_s(k)) enc = "(fq_u64)(fq_i64)(" + x + ")";
+        else enc = "(fq_u64)(" + x + ")";
+        st += fmt("    val[%d] = %s;\n", k, enc.c_str());
+        if (leaf_counted[k]) st += fmt("    vmask |= (%s) ? %uu : 0u;\n", e.ok[an.left].c_str(), 1u << k);
+      }
+      s += e.body + st;
+    }
+    s += "    return true;\n  }\n";
+    // identities of a fresh group
+    s += "  __device__ static __forceinline__ void gb_init(fq_u64 *slots) {\n    slots[0] = 0ull;\n";
+    for (int k = 0; k < n; k++) {
+      const int op = out->agg_ops[k];
+      const char *idn = (op == FQ_AGG_SUM || op == FQ_AGG_COUNT) ? "0ull"
+                        : op == FQ_AGG_MIN ? (is_s(k) ? "(fq_u64)9223372036854775807ll" : "~0ull")
+                                           : (is_s(k) ? "(fq_u64)(-9223372036854775807ll - 1)" : "0ull");
+      s += fmt("    slots[%d] = %s;\n", 1 + k, idn);
+      if (leaf_counted[k]) s += fmt("    slots[%d] = 0ull;\n", 1 + out->agg_count_slot[k]);
+    }
+    s += "  }\n";
+    // one row into a group (ROW = true) or a partial group state into a group (ROW = false): atomics on generic addresses
+    for (int pass = 0; pass < 2; pass++) {
+      const bool row = pass == 0;
+      s += row ? "  __device__ static __forceinline__ void gb_apply(fq_u64 *slots, const fq_u64 (&val)[NSLOTS > 0 ? NSLOTS : 1], fq_u32 vmask) {\n"
+                 "    atomicAdd((unsigned long long *)slots, 1ull);\n"
+               : "  __device__ static __forceinline__ void gb_merge(fq_u64 *slots, const fq_u64 *src) {\n"
+                 "    atomicAdd((unsigned long long *)slots, (unsigned long long)src[0]);\n";
+      for (int k = 0; k < n; k++) {
+        const int op = out->agg_ops[k];
+        if (op == FQ_AGG_COUNT) continue;
+        const std::string x = row ? fmt("val[%d]", k) : fmt("src[%d]", 1 + k);
+        std::string stmt;
+        if (op == FQ_AGG_SUM) {
+          stmt = is_f(k) ? fmt("atomicAdd((double *)(slots + %d), __longlong_as_double((fq_i64)%s));", 1 + k, x.c_str())
+                         : fmt("atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)%s);", 1 + k, x.c_str());
+        } else {
+          const char *f = op == FQ_AGG_MIN ? "atomicMin" : "atomicMax";
+          stmt = is_s(k) ? fmt("%s((long long *)(slots + %d), (long long)%s);", f, 1 + k, x.c_str())
+                         : fmt("%s((unsigned long long *)(slots + %d), (unsigned long long)%s);", f, 1 + k, x.c_str());
+        }
+        if (leaf_counted[k]) {
+          const int cs = 1 + out->agg_count_slot[k];
+          if (row) s += fmt("    if (vmask & %uu) { %s atomicAdd((unsigned long long *)(slots + %d), 1ull); }\n", 1u << k, stmt.c_str(), cs);
+          else s += fmt("    if (src[%d]) { %s atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)src[%d]); }\n", cs, stmt.c_str(), cs, cs);
+        } else {
+          s += "    " + stmt + "\n";
+        }
+      }
+      s += "  }\n";
+    }
+  } else if (d.kind == FQ_PIPE_AGGREGATE) {
     const int n = n_leaves;
     s += "  struct Acc {";
     for (int k = 0; k < n; k++) s += fmt(" %s a%d;", ctype(out->agg_dtypes[k]), k);
@@ -667,7 +792,10 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   s += "};\n";
   // kernel wrappers: the ahead-of-time build compiles all of them, a JIT build only the variant it will launch
   std::vector<std::pair<std::string, std::string>> wrappers;
-  if (d.kind == FQ_PIPE_AGGREGATE) {
+  if (groupby) {
+    wrappers.push_back({"_groupby", "extern \"C\" __global__ void __launch_bounds__(FQ_GB_THREADS, FQ_GB_MIN_BLOCKS) fqk_@_groupby(const __grid_constant__ fq_launch_params p) { fq_groupby_kernel<Q_@, FQ_GB_UNROLL>(p); }\n"});
+    wrappers.push_back({"_gbmerge", "extern \"C\" __global__ void __launch_bounds__(256) fqk_@_gbmerge(const __grid_constant__ fq_launch_params p) { fq_groupby_merge_kernel<Q_@>(p); }\n"});
+  } else if (d.kind == FQ_PIPE_AGGREGATE) {
     wrappers.push_back({"_agg_u4", "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS) fqk_@_agg_u4(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 4>(p); }\n"});
     if (out->tma_ok)
       wrappers.push_back({"_agg_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_TMA_THREADS + 32, FQ_TMA_MIN_BLOCKS) fqk_@_agg_tma(const __grid_constant__ fq_launch_params p) { fq_agg_tma_kernel<Q_@, FQ_TMA_UNROLL, FQ_TMA_STAGES>(p); }\n"});

@@ -228,7 +228,14 @@ struct fq_group {
 
 struct fq_pipe {
   fq::Generated gen;
-  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma;
+  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma, k_groupby, k_gbmerge;
+  // GROUP BY: the hash table in HBM
+  uint64_t *gb_keys = nullptr, *gb_slots = nullptr;
+  uint64_t gb_cap = 0;
+  uint32_t *gb_flags = nullptr;      // [0] overflow, [1] EMPTY-valued key seen, [2..3] group count (u64), [4..5] error bits
+  uint64_t *h_gb = nullptr;          // pinned mirror of gb_flags (4 x u64)
+  unsigned gb_smem_cap = 0;
+  bool launched_groupby = false;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
   bool selt_stage2 = false;   // staged select kernel: pass 2 of dense segments staged as well
@@ -729,7 +736,8 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
           const bool staged = (agg || !gen.has_pred ? gen.tma_ok : gen.sel_tma_ok) && 2u * tile_bytes <= 200u * 1024u;
           const std::string variant_env = getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT")
                                               ? getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT") : "tma";
-          if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
+          if (gen.kind == FQ_PIPE_GROUPBY) { want.push_back("_groupby"); want.push_back("_gbmerge"); }
+          else if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
           else if (gen.has_pred) want.push_back(staged && variant_env == "tma" ? "_select_tma" : "_select");
           else want.push_back(staged && variant_env == "tma" ? "_map_tma" : "_map");
         }
@@ -745,7 +753,17 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     pipe->build_kind = m->precompiled ? 0 : m->from_disk_cache ? 2 : 1;
     fq_status s2 = FQ_OK;
     const std::string base = "fqk_" + gen.tag;
-    if (gen.kind == FQ_PIPE_AGGREGATE) {
+    if (gen.kind == FQ_PIPE_GROUPBY) {
+      // shared-memory table of the CTA: the largest power of two of (key + state) slots within 96 KB (two CTAs per SM)
+      const unsigned entry = 8u * (2u + (unsigned)gen.n_slots);
+      unsigned cap = 1;
+      while (cap * 2 * entry <= 96u * 1024u) cap *= 2;
+      static const int smem_env = getenv("FQ_GB_SMEM_SLOTS") ? atoi(getenv("FQ_GB_SMEM_SLOTS")) : -1;
+      if (smem_env >= 0) { cap = 1; while ((int)cap * 2 <= smem_env) cap *= 2; if (smem_env == 0) cap = 0; }
+      pipe->gb_smem_cap = cap;
+      s2 = resolve_kernel(m, base + "_groupby", FQ_GB_THREADS, &pipe->k_groupby, cap * entry);
+      if (!s2) s2 = resolve_kernel(m, base + "_gbmerge", 256, &pipe->k_gbmerge);
+    } else if (gen.kind == FQ_PIPE_AGGREGATE) {
       s2 = resolve_kernel(m, base + "_agg_u4", shapes().agg_threads, &pipe->k_agg_u4);
       if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", shapes().agg_threads, &pipe->k_agg_u8);
       if (!s2 && gen.tma_ok) {
@@ -835,6 +853,10 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
   cudaFree(pipe->d_tiles);
   cudaFree(pipe->d_blocks);
   cudaFree(pipe->d_merged);
+  cudaFree(pipe->gb_keys);
+  cudaFree(pipe->gb_slots);
+  cudaFree(pipe->gb_flags);
+  if (pipe->h_gb) cudaFreeHost(pipe->h_gb);
   if (pipe->h_merged) cudaFreeHost(pipe->h_merged);
   if (pipe->h_state) cudaFreeHost(pipe->h_state);
   if (pipe->h_result) cudaFreeHost(pipe->h_result);
@@ -1351,6 +1373,362 @@ fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row) {
   if (pipe->capacity_eff == 0 || sel < pipe->capacity_eff) return set_err(FQ_ERR_INVALID, "Internal Error: the launch did not fill its capacity");
   *row = pipe->project_has_pred_launch ? pipe->h_result[5] : pipe->capacity_eff - 1;
   return FQ_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// GROUP BY pipes (hash aggregation)
+// =============================================================================================
+namespace {
+__global__ void __launch_bounds__(256) fq_gb_fill(fq_u64 *keys, fq_u64 *slots, fq_u64 n_entries, int G, const fq_u64 *identity) {
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (fq_u64)gridDim.x * blockDim.x;
+  for (fq_u64 i = tid; i < n_entries; i += nthreads) keys[i] = FQ_GB_EMPTY;
+  for (fq_u64 i = tid; i < n_entries * (fq_u64)G; i += nthreads) slots[i] = identity[i % (fq_u64)G];
+}
+__device__ __forceinline__ bool fq_gb_occupied(const fq_u64 *keys, fq_u64 cap, const fq_u32 *flags, fq_u64 i) {
+  return i < cap ? keys[i] != FQ_GB_EMPTY : (i == cap && flags[1] != 0);
+}
+__global__ void __launch_bounds__(256) fq_gb_count(const fq_u64 *keys, fq_u64 cap, fq_u32 *flags) {
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (fq_u64)gridDim.x * blockDim.x;
+  fq_u64 n = 0;
+  for (fq_u64 i = tid; i <= cap; i += nthreads) n += fq_gb_occupied(keys, cap, flags, i) ? 1 : 0;
+  for (int m = 16; m > 0; m >>= 1) n += __shfl_xor_sync(0xffffffffu, n, m);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd((unsigned long long *)(flags + 2), (unsigned long long)n);
+}
+struct fq_gb_export_params {
+  const fq_u64 *keys, *slots;
+  fq_u64 cap;
+  const fq_u32 *flags;
+  int G, n_keys, n_leaves;
+  int key_shift[FQ_MAX_KEYS], key_bits[FQ_MAX_KEYS], key_nullable[FQ_MAX_KEYS];
+  void *key_out[FQ_MAX_KEYS], *key_valid[FQ_MAX_KEYS];
+  int leaf_op[16], leaf_dtype[16], leaf_count_slot[16];
+  void *leaf_out[16], *leaf_valid[16];
+  fq_u64 capacity;
+  fq_u64 *counter;
+};
+__device__ __forceinline__ void fq_store_low(void *base, fq_u64 idx, int bytes, fq_u64 v) {
+  switch (bytes) {
+    case 1: ((fq_u8 *)base)[idx] = (fq_u8)v; break;
+    case 2: ((fq_u16 *)base)[idx] = (fq_u16)v; break;
+    case 4: ((fq_u32 *)base)[idx] = (fq_u32)v; break;
+    default: ((fq_u64 *)base)[idx] = v;
+  }
+}
+__global__ void __launch_bounds__(256) fq_gb_export(const __grid_constant__ fq_gb_export_params a) {
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (fq_u64)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const fq_u64 rounds = (a.cap + 1 + nthreads - 1) / nthreads;
+  for (fq_u64 k = 0; k < rounds; k++) {
+    const fq_u64 i = k * nthreads + tid;
+    const bool occ = i <= a.cap && fq_gb_occupied(a.keys, a.cap, a.flags, i);
+    const fq_u32 m = __ballot_sync(0xffffffffu, occ);
+    if (!m) continue;
+    fq_u64 base = 0;
+    if (lane == 0) base = atomicAdd((unsigned long long *)a.counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!occ) continue;
+    const fq_u64 pos = base + __popc(m & ((1u << lane) - 1u));
+    if (pos >= a.capacity) continue;
+    const fq_u64 key = i < a.cap ? a.keys[i] : FQ_GB_EMPTY;
+    for (int j = 0; j < a.n_keys; j++) {
+      const fq_u64 bits = a.key_bits[j] >= 64 ? key : ((key >> a.key_shift[j]) & ((1ull << a.key_bits[j]) - 1ull));
+      fq_store_low(a.key_out[j], pos, a.key_bits[j] / 8, bits);
+      if (a.key_nullable[j]) ((fq_u8 *)a.key_valid[j])[pos] = (fq_u8)(((key >> (a.key_shift[j] + a.key_bits[j])) & 1ull) ? 0 : 1);
+    }
+    const fq_u64 *st = a.slots + i * (fq_u64)a.G;
+    for (int l = 0; l < a.n_leaves; l++) {
+      const int op = a.leaf_op[l], t = a.leaf_dtype[l];
+      fq_u64 x = op == FQ_AGG_COUNT ? st[0] : st[1 + l];
+      if (t == FQ_F32 || t == FQ_F64) {
+        const double d = op == FQ_AGG_SUM ? __longlong_as_double((fq_i64)x) : fq_f64_unordered(x);
+        if (t == FQ_F32) ((float *)a.leaf_out[l])[pos] = (float)d;
+        else ((double *)a.leaf_out[l])[pos] = d;
+      } else {
+        fq_store_low(a.leaf_out[l], pos, t == FQ_BOOL || t == FQ_I8 || t == FQ_U8 ? 1 : t == FQ_I16 || t == FQ_U16 ? 2 : t == FQ_I32 || t == FQ_U32 ? 4 : 8, x);
+      }
+      if (a.leaf_count_slot[l] >= 0 && a.leaf_valid[l]) ((fq_u8 *)a.leaf_valid[l])[pos] = st[1 + a.leaf_count_slot[l]] > 0 ? 1 : 0;
+    }
+  }
+}
+// partial groups ordered by owner rank: pass 0 counts (cursor[d] += ...), pass 1 writes entries at cursor positions
+__global__ void __launch_bounds__(256) fq_gb_partials(const fq_u64 *keys, const fq_u64 *slots, fq_u64 cap, const fq_u32 *flags, int G, int world,
+                                                      unsigned long long *cursor, fq_u64 *entries, int pass) {
+  __shared__ fq_u32 cnt[8], base_lo[8];
+  __shared__ unsigned long long base[8];
+  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  const fq_u64 rounds = (cap + 1 + nthreads - 1) / nthreads;
+  (void)base_lo;
+  for (fq_u64 k = 0; k < rounds; k++) {
+    const fq_u64 i = (k * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const bool occ = i <= cap && fq_gb_occupied(keys, cap, flags, i);
+    const fq_u64 key = occ && i < cap ? keys[i] : FQ_GB_EMPTY;
+    const int dest = (int)((fq_gb_hash(key) >> 40) % (fq_u64)world);
+    fq_u32 r = 0;
+    if (occ) r = atomicAdd(&cnt[dest], 1u);
+    __syncthreads();
+    if ((int)threadIdx.x < world && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, (unsigned long long)cnt[threadIdx.x]);
+    __syncthreads();
+    if (occ && pass == 1) {
+      fq_u64 *e = entries + (base[dest] + r) * (fq_u64)(1 + G);
+      e[0] = key;
+      for (int s = 0; s < G; s++) e[1 + s] = slots[i * (fq_u64)G + s];
+    }
+    __syncthreads();
+  }
+}
+__global__ void fq_gb_prefix(unsigned long long *cursor, unsigned long long *counts_out, int world) {
+  unsigned long long run = 0;
+  for (int d = 0; d < world; d++) {
+    const unsigned long long c = cursor[d];
+    counts_out[d] = c;
+    cursor[d] = run;
+    run += c;
+  }
+}
+
+std::vector<uint64_t> gb_identity(const fq::Generated &gen) {
+  std::vector<uint64_t> idn(1 + gen.n_slots, 0);
+  for (size_t k = 0; k < gen.agg_ops.size(); k++) {
+    const int op = gen.agg_ops[k];
+    const fq_dtype t = gen.agg_dtypes[k];
+    const bool sgn = t >= FQ_I8 && t <= FQ_I64;
+    if (op == FQ_AGG_MIN) idn[1 + k] = sgn ? (uint64_t)INT64_MAX : ~0ull;
+    else if (op == FQ_AGG_MAX) idn[1 + k] = sgn ? (uint64_t)INT64_MIN : 0ull;
+  }
+  return idn;
+}
+fq_status gb_check(const fq_pipe *pipe) {
+  if (!pipe || pipe->gen.kind != FQ_PIPE_GROUPBY) return set_err(FQ_ERR_INVALID, "Internal Error: not a GROUP BY pipe");
+  return FQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+fq_status fq_pipe_key_dtype(fq_ctx *, const fq_pipe *pipe, int32_t j, fq_dtype *out, int32_t *nullable) {
+  if (fq_status st = gb_check(pipe)) return st;
+  if (j < 0 || j >= (int)pipe->gen.key_dtypes.size() || !out) return set_err(FQ_ERR_INVALID, "Internal Error: bad key index");
+  *out = pipe->gen.key_dtypes[j];
+  if (nullable) *nullable = pipe->gen.key_nullable[j];
+  return FQ_OK;
+}
+fq_status fq_pipe_leaf_dtype(fq_ctx *, const fq_pipe *pipe, int32_t k, fq_dtype *out, int32_t *nullable) {
+  if (!pipe || pipe->gen.kind == FQ_PIPE_PROJECT) return set_err(FQ_ERR_INVALID, "Internal Error: not an aggregate or GROUP BY pipe");
+  if (k < 0 || k >= (int)pipe->gen.agg_dtypes.size() || !out) return set_err(FQ_ERR_INVALID, "Internal Error: bad leaf index");
+  *out = pipe->gen.agg_dtypes[k];
+  if (nullable) *nullable = pipe->gen.agg_count_slot[k] >= 0 ? 1 : 0;
+  return FQ_OK;
+}
+fq_status fq_pipe_group_entry_slots(fq_ctx *, const fq_pipe *pipe, int32_t *slots) {
+  if (fq_status st = gb_check(pipe)) return st;
+  if (!slots) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *slots = 2 + pipe->gen.n_slots;
+  return FQ_OK;
+}
+
+fq_status fq_pipe_groupby_reserve(fq_ctx *ctx, fq_pipe *pipe, uint64_t groups) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  uint64_t cap = 1024;
+  while (cap < groups * 2 && cap < (1ull << 40)) cap *= 2;   // load factor <= 1/2
+  const int G = 1 + pipe->gen.n_slots;
+  if (cap != pipe->gb_cap) {
+    cudaFree(pipe->gb_keys);
+    cudaFree(pipe->gb_slots);
+    pipe->gb_keys = pipe->gb_slots = nullptr;
+    pipe->gb_cap = 0;
+    cudaError_t e = cudaMalloc(&pipe->gb_keys, sizeof(uint64_t) * (cap + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&pipe->gb_slots, sizeof(uint64_t) * (cap + 1) * G);
+    if (e != cudaSuccess) {
+      cudaFree(pipe->gb_keys);
+      pipe->gb_keys = nullptr;
+      return set_err(FQ_ERR_CUDA, "CUDA error: %s (GROUP BY table of %" PRIu64 " slots)", cudaGetErrorString(e), cap);
+    }
+    pipe->gb_cap = cap;
+  }
+  if (!pipe->gb_flags) {
+    CUDA_TRY(cudaMalloc(&pipe->gb_flags, 64));
+    CUDA_TRY(cudaHostAlloc(&pipe->h_gb, 64, cudaHostAllocDefault));
+  }
+  // clear: keys = EMPTY, states = the aggregates' identities
+  const std::vector<uint64_t> idn = gb_identity(pipe->gen);
+  uint64_t *d_idn = nullptr;
+  CUDA_TRY(cudaMalloc(&d_idn, sizeof(uint64_t) * idn.size()));
+  CUDA_TRY(cudaMemcpy(d_idn, idn.data(), sizeof(uint64_t) * idn.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(pipe->gb_flags, 0, 64));
+  const unsigned grid = (unsigned)std::min<uint64_t>((cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_gb_fill<<<grid, 256>>>((fq_u64 *)pipe->gb_keys, (fq_u64 *)pipe->gb_slots, cap + 1, G, (const fq_u64 *)d_idn);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaFree(d_idn);
+  pipe->launched_groupby = false;
+  return FQ_OK;
+}
+
+static fq_status gb_after_launch(fq_ctx *ctx, fq_pipe *pipe, cudaStream_t s) {
+  // count the groups, mirror {overflow, count, error bits} to the host
+  CUDA_TRY(cudaMemsetAsync(pipe->gb_flags + 2, 0, 8, s));
+  const unsigned grid = (unsigned)std::min<uint64_t>((pipe->gb_cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_gb_count<<<grid, 256, 0, s>>>((const fq_u64 *)pipe->gb_keys, pipe->gb_cap, (fq_u32 *)pipe->gb_flags);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaMemcpyAsync(pipe->h_gb, pipe->gb_flags, 32, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(pipe->ev, s));
+  pipe->launched_groupby = true;
+  return FQ_OK;
+}
+
+fq_status fq_pipe_launch_groupby(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, uint32_t flags, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  if (!pipe->gb_cap) return set_err(FQ_ERR_INVALID, "Internal Error: fq_pipe_groupby_reserve was not called");
+  if (!(flags & FQ_RUN_ACCUMULATE) && pipe->launched_groupby) {
+    if (fq_status st = fq_pipe_groupby_reserve(ctx, pipe, pipe->gb_cap / 2)) return st;   // restart from an empty table
+  }
+  fq_launch_params p;
+  memset(&p, 0, sizeof p);
+  if (fq_status st = bind_source(pipe, src, &p)) return st;
+  p.gb_keys = (fq_u64 *)pipe->gb_keys;
+  p.gb_slots = (fq_u64 *)pipe->gb_slots;
+  p.gb_cap = pipe->gb_cap;
+  p.gb_flags = (fq_u32 *)pipe->gb_flags;
+  p.gb_smem_cap = pipe->gb_smem_cap;
+  p.result = (fq_u64 *)(pipe->gb_flags + 2);   // [0] = count (u64 at flags[2..3]), [1] = error bits (flags[4..5])
+  const Kernel &k = pipe->k_groupby;
+  if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no GROUP BY kernel was built for this pipe");
+  if (src->n_rows > 0) {
+    const uint64_t chunk_rows = (uint64_t)k.threads * FQ_GB_UNROLL * pipe->gen.vec;
+    const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
+    if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+  }
+  return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
+}
+
+fq_status fq_pipe_fetch_groupby(fq_ctx *ctx, fq_pipe *pipe, uint64_t *n_groups) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  if (!pipe->launched_groupby) return set_err(FQ_ERR_INVALID, "Internal Error: no GROUP BY launch to fetch");
+  CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  const uint32_t *f = (const uint32_t *)pipe->h_gb;
+  if (n_groups) *n_groups = pipe->h_gb[1];
+  if (f[0]) return set_err(FQ_ERR_CAPACITY, "Internal Error: GROUP BY met more groups than the %" PRIu64 " reserved: reserve more and relaunch", pipe->gb_cap / 2);
+  return decode_err(pipe->h_gb[2]);
+}
+
+fq_status fq_pipe_export_groups(fq_ctx *ctx, fq_pipe *pipe, fq_column *const *key_cols, fq_column *const *key_valid,
+                                fq_column *const *leaf_cols, fq_column *const *leaf_valid, uint64_t capacity, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  if (!pipe->gb_cap) return set_err(FQ_ERR_INVALID, "Internal Error: fq_pipe_groupby_reserve was not called");
+  const fq::Generated &gen = pipe->gen;
+  fq_gb_export_params a;
+  memset(&a, 0, sizeof a);
+  a.keys = (const fq_u64 *)pipe->gb_keys;
+  a.slots = (const fq_u64 *)pipe->gb_slots;
+  a.cap = pipe->gb_cap;
+  a.flags = (const fq_u32 *)pipe->gb_flags;
+  a.G = 1 + gen.n_slots;
+  a.n_keys = (int)gen.key_dtypes.size();
+  a.n_leaves = (int)gen.agg_nodes.size();
+  if (a.n_leaves > 16) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: more than 16 aggregates in a GROUP BY");
+  for (int j = 0; j < a.n_keys; j++) {
+    const fq_column *c = key_cols ? key_cols[j] : nullptr;
+    if (!c || c->dtype != gen.key_dtypes[j] || c->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: key output column %d missing, mistyped or short", j);
+    a.key_out[j] = c->ptr;
+    a.key_shift[j] = gen.key_shift[j];
+    a.key_bits[j] = gen.key_bits[j];
+    a.key_nullable[j] = gen.key_nullable[j];
+    if (gen.key_nullable[j]) {
+      const fq_column *v = key_valid ? key_valid[j] : nullptr;
+      if (!v || v->dtype != FQ_BOOL || v->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: key %d can be NULL: a Boolean validity output column is required", j);
+      a.key_valid[j] = v->ptr;
+    }
+  }
+  for (int l = 0; l < a.n_leaves; l++) {
+    const fq_column *c = leaf_cols ? leaf_cols[l] : nullptr;
+    if (!c || c->dtype != gen.agg_dtypes[l] || c->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: leaf output column %d missing, mistyped or short", l);
+    a.leaf_out[l] = c->ptr;
+    a.leaf_op[l] = gen.agg_ops[l];
+    a.leaf_dtype[l] = gen.agg_dtypes[l];
+    a.leaf_count_slot[l] = gen.agg_count_slot[l];
+    if (gen.agg_count_slot[l] >= 0) {
+      const fq_column *v = leaf_valid ? leaf_valid[l] : nullptr;
+      if (!v || v->dtype != FQ_BOOL || v->len < capacity) return set_err(FQ_ERR_INVALID, "Internal Error: aggregate %d can be NULL: a Boolean validity output column is required", l);
+      a.leaf_valid[l] = v->ptr;
+    }
+  }
+  a.capacity = capacity;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(pipe->gb_flags + 6, 0, 8, s));
+  a.counter = (fq_u64 *)(pipe->gb_flags + 6);
+  const unsigned grid = (unsigned)std::min<uint64_t>((pipe->gb_cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_gb_export<<<grid, 256, 0, s>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return FQ_OK;
+}
+
+fq_status fq_pipe_export_partials(fq_ctx *ctx, fq_pipe *pipe, int32_t world, fq_column *entries, uint64_t *counts, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  if (world < 1 || world > 8 || !counts) return set_err(FQ_ERR_INVALID, "Internal Error: 1..8 ranks and a counts array");
+  if (!pipe->launched_groupby) return set_err(FQ_ERR_INVALID, "Internal Error: no GROUP BY launch to export");
+  CUDA_TRY(cudaEventSynchronize(pipe->ev));
+  const uint64_t n_groups = pipe->h_gb[1];
+  const int G = 1 + pipe->gen.n_slots;
+  if (!entries || entries->dtype != FQ_U64 || entries->len < n_groups * (uint64_t)(1 + G))
+    return set_err(FQ_ERR_INVALID, "Internal Error: the entries column must be UInt64 with groups x %d rows", 1 + G);
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long *cursor = nullptr;
+  CUDA_TRY(cudaMalloc(&cursor, 16 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(cursor, 0, 16 * sizeof(unsigned long long), s));
+  const unsigned grid = (unsigned)std::min<uint64_t>((pipe->gb_cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_gb_partials<<<grid, 256, 0, s>>>((const fq_u64 *)pipe->gb_keys, (const fq_u64 *)pipe->gb_slots, pipe->gb_cap, (const fq_u32 *)pipe->gb_flags, G,
+                                      world, cursor, nullptr, 0);
+  fq_gb_prefix<<<1, 1, 0, s>>>(cursor, cursor + 8, world);
+  fq_gb_partials<<<grid, 256, 0, s>>>((const fq_u64 *)pipe->gb_keys, (const fq_u64 *)pipe->gb_slots, pipe->gb_cap, (const fq_u32 *)pipe->gb_flags, G,
+                                      world, cursor, (fq_u64 *)entries->ptr, 1);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 3;
+  unsigned long long h[8];
+  CUDA_TRY(cudaMemcpyAsync(h, cursor + 8, sizeof h, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  cudaFree(cursor);
+  for (int d = 0; d < world; d++) counts[d] = h[d];
+  return FQ_OK;
+}
+
+fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *entries, uint64_t n_entries, uint32_t flags, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = gb_check(pipe)) return st;
+  if (!pipe->gb_cap) return set_err(FQ_ERR_INVALID, "Internal Error: fq_pipe_groupby_reserve was not called");
+  const int G = 1 + pipe->gen.n_slots;
+  if (n_entries && (!entries || entries->dtype != FQ_U64 || entries->len < n_entries * (uint64_t)(1 + G)))
+    return set_err(FQ_ERR_INVALID, "Internal Error: the entries column must be UInt64 with entries x %d rows", 1 + G);
+  if (!(flags & FQ_RUN_ACCUMULATE) && pipe->launched_groupby) {
+    if (fq_status st = fq_pipe_groupby_reserve(ctx, pipe, pipe->gb_cap / 2)) return st;
+  }
+  if (n_entries) {
+    fq_launch_params p;
+    memset(&p, 0, sizeof p);
+    p.n_rows = n_entries;
+    p.gb_keys = (fq_u64 *)pipe->gb_keys;
+    p.gb_slots = (fq_u64 *)pipe->gb_slots;
+    p.gb_cap = pipe->gb_cap;
+    p.gb_flags = (fq_u32 *)pipe->gb_flags;
+    p.gb_entries = (const fq_u64 *)entries->ptr;
+    const Kernel &k = pipe->k_gbmerge;
+    if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no GROUP BY merge kernel was built for this pipe");
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)ctx->sm_count * 8));
+    if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+  }
+  return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -51,6 +51,12 @@ typedef signed char fq_i8;
 #define FQ_MAP_MIN_BLOCKS 4
 #define FQ_MAP_UNROLL 4
 #endif
+#ifndef FQ_GB_THREADS
+#define FQ_GB_THREADS 256    // GROUP BY kernel
+#define FQ_GB_MIN_BLOCKS 2
+#define FQ_GB_UNROLL 4
+#define FQ_GB_SMEM_PROBES 4  // linear probes in the CTA's shared-memory table before a row goes to the table in HBM
+#endif
 #ifndef FQ_SELT_THREADS
 #define FQ_SELT_THREADS 512  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp)
 #define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
@@ -89,6 +95,13 @@ struct fq_launch_params {
   fq_u64 group_timeout_ns;
   fq_u64 *merged;          // [FQ_STATE_HDR + Q::NSLOTS] merged state of all ranks (local)
   fq_u32 group_rank, group_world, group_row_slots;
+  // group by: open-addressing table in HBM, gb_cap (a power of two) slots + 1 for the key that equals the EMPTY mark
+  fq_u64 *gb_keys;        // [gb_cap + 1] packed keys, FQ_GB_EMPTY = free
+  fq_u64 *gb_slots;       // [gb_cap + 1][Q::G] group states
+  fq_u64 gb_cap;
+  fq_u32 *gb_flags;       // [0] != 0: the table overflowed (results void), [1] != 0: the EMPTY-valued key occurred
+  fq_u32 gb_smem_cap;     // slots of the CTA's shared-memory table (a power of two, 0 = none)
+  const fq_u64 *gb_entries;  // merge kernel: n_rows partial entries of 1 + Q::G slots each (packed key, state)
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -1555,6 +1568,140 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     pending += 1;
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fq_groupby_kernel — hash aggregation (GROUP BY), one pass over the source.
+//
+// The reference plans GROUP BY but never executes it (pipeline_builder.rs:50-65 uses only aggr_expr); this is the
+// operator AggregatePlan{group_expr, aggr_expr} describes, with the aggregate protocol of function_aggregator.rs:57-100
+// applied per group.  Generated code (codegen.cc) supplies, per row, the 64-bit packed key and the encoded value of every
+// Aggregator leaf (Q::gb_row), and the atomics that fold a row / a partial state into a group's Q::G slots.
+// Two levels of open-addressing tables: every CTA aggregates into a table in shared memory first (gb_smem_cap slots,
+// FQ_GB_SMEM_PROBES linear probes) — with few distinct keys nothing but the final flush leaves the SM; a row whose key
+// finds no room there goes straight to the table in HBM (atomicCAS on the key, then atomics on the state).  At the end the
+// CTA flushes its shared-memory groups into the HBM table.  A table that runs full raises gb_flags[0]: the host reserves
+// a bigger one and relaunches.  Algorithmic traffic: sizeof(row) read per row + the table.
+// ---------------------------------------------------------------------------------------------
+#define FQ_GB_EMPTY 0xffffffffffffffffull
+
+// order-preserving 64-bit code of a double (min / max of float columns through integer atomics)
+__device__ __forceinline__ fq_u64 fq_f64_ordered(double x) {
+  const fq_u64 b = (fq_u64)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | (1ull << 63));
+}
+__device__ __forceinline__ double fq_f64_unordered(fq_u64 c) {
+  return __longlong_as_double((fq_i64)((c >> 63) ? (c & ~(1ull << 63)) : ~c));
+}
+__device__ __forceinline__ fq_u64 fq_gb_hash(fq_u64 k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+// slot of `key` in the HBM table (claimed on the spot when new); gb_cap for the key that equals the EMPTY mark; -1 = full
+__device__ __forceinline__ fq_i64 fq_gb_find(const fq_launch_params &p, fq_u64 key, fq_u64 h) {
+  if (key == FQ_GB_EMPTY) {
+    if (*(volatile fq_u32 *)(p.gb_flags + 1) == 0) p.gb_flags[1] = 1u;
+    return (fq_i64)p.gb_cap;
+  }
+  const fq_u64 mask = p.gb_cap - 1;
+  const fq_u64 limit = p.gb_cap < 4096 ? p.gb_cap : 4096;   // a table that needs longer chains is as good as full
+  for (fq_u64 probe = 0; probe < limit; probe++) {
+    const fq_u64 i = (h + probe) & mask;
+    fq_u64 cur = fq_ld_volatile(p.gb_keys + i);
+    if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(p.gb_keys + i), FQ_GB_EMPTY, (unsigned long long)key);
+    if (cur == FQ_GB_EMPTY || cur == key) return (fq_i64)i;
+  }
+  if (*(volatile fq_u32 *)p.gb_flags == 0) p.gb_flags[0] = 1u;
+  return -1;
+}
+
+template <class Q>
+__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, const typename Q::Rows &r, int v, fq_u32 &err) {
+  fq_u64 key, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
+  fq_u32 vmask;
+  if (!Q::gb_row(r, v, err, key, val, vmask)) return;
+  const fq_u64 h = fq_gb_hash(key);
+  if (p.gb_smem_cap && key != FQ_GB_EMPTY) {
+    const fq_u32 smask = p.gb_smem_cap - 1;
+#pragma unroll 1
+    for (int probe = 0; probe < FQ_GB_SMEM_PROBES; probe++) {
+      const fq_u32 i = ((fq_u32)(h >> 32) + probe) & smask;
+      fq_u64 cur = *(volatile fq_u64 *)(skeys + i);
+      if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
+      if (cur == FQ_GB_EMPTY || cur == key) {
+        Q::gb_apply(sslots + (size_t)i * Q::G, val, vmask);
+        return;
+      }
+    }
+  }
+  const fq_i64 slot = fq_gb_find(p, key, h);
+  if (slot >= 0) Q::gb_apply(p.gb_slots + (fq_u64)slot * Q::G, val, vmask);
+}
+
+template <class Q, int UNROLL>
+__device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
+  constexpr int V = Q::V;
+  extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
+  fq_u64 *skeys = (fq_u64 *)fq_dyn_smem;
+  fq_u64 *sslots = skeys + p.gb_smem_cap;
+  for (fq_u32 i = threadIdx.x; i < p.gb_smem_cap; i += blockDim.x) {
+    skeys[i] = FQ_GB_EMPTY;
+    Q::gb_init(sslots + (size_t)i * Q::G);
+  }
+  __syncthreads();
+  fq_u32 err = 0;
+  const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
+  const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
+  const fq_u64 nfull = nvec / chunk;
+  for (fq_u64 c = blockIdx.x; c < nfull; c += gridDim.x) {
+    const fq_u64 g0 = c * chunk + threadIdx.x;
+    typename Q::Rows rows[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) Q::load(rows[u], p, g0 + (fq_u64)u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, rows[u], v, err);
+  }
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  for (fq_u64 g = nfull * chunk + tid; g < nvec; g += nthreads) {
+    typename Q::Rows r;
+    Q::load(r, p, g);
+#pragma unroll
+    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, r, v, err);
+  }
+  for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
+    typename Q::Rows r;
+    Q::load1(r, p, row);
+    fq_gb_row<Q>(p, skeys, sslots, r, 0, err);
+  }
+  __syncthreads();
+  // flush the CTA's groups into the table in HBM
+  for (fq_u32 i = threadIdx.x; i < p.gb_smem_cap; i += blockDim.x) {
+    const fq_u64 key = skeys[i];
+    if (key == FQ_GB_EMPTY) continue;
+    const fq_i64 slot = fq_gb_find(p, key, fq_gb_hash(key));
+    if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, sslots + (size_t)i * Q::G);
+  }
+  if (err) atomicOr((fq_u32 *)(p.result + 1), err);
+}
+
+// partial groups (entries of 1 + Q::G slots: packed key, state — what fq_pipe_export_partials writes) folded into the table
+template <class Q>
+__device__ __forceinline__ void fq_groupby_merge_kernel(const fq_launch_params &p) {
+  const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  for (fq_u64 e = tid; e < p.n_rows; e += nthreads) {
+    const fq_u64 *ent = p.gb_entries + e * (1 + Q::G);
+    const fq_u64 key = ent[0];
+    const fq_i64 slot = fq_gb_find(p, key, fq_gb_hash(key));
+    if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, ent + 1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

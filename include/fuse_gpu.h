@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FQ_ABI_VERSION 1
+#define FQ_ABI_VERSION 2
 
 /* status codes; FQ_ERR_INTERNAL/FQ_ERR_PLAN map onto FuseQueryError::{Internal,Plan} (error.rs:10-20) */
 typedef int32_t fq_status;
@@ -41,7 +41,8 @@ enum {
   FQ_ERR_DIVIDE_BY_ZERO = 3, /* arrow DivideByZero -> "Internal Error: Divide by zero error" */
   FQ_ERR_UNSUPPORTED = 4,    /* well-formed request the device path does not implement (never a silent fallback) */
   FQ_ERR_CUDA = 5,           /* CUDA runtime / driver / NVRTC failure */
-  FQ_ERR_INVALID = 6         /* bad handle / argument */
+  FQ_ERR_INVALID = 6,        /* bad handle / argument */
+  FQ_ERR_CAPACITY = 7        /* a GROUP BY pipe met more groups than its table was reserved for: reserve more and relaunch */
 };
 
 /* DataType / DataValue tags in the declaration order of datavalues/data_value.rs:19-35 */
@@ -173,8 +174,9 @@ typedef struct fq_source {
  * ------------------------------------------------------------------------------------------- */
 #define FQ_MAX_COLS 8
 #define FQ_MAX_EXPRS 8
+#define FQ_MAX_KEYS 4
 
-enum { FQ_PIPE_PROJECT = 0, FQ_PIPE_AGGREGATE = 1 };
+enum { FQ_PIPE_PROJECT = 0, FQ_PIPE_AGGREGATE = 1, FQ_PIPE_GROUPBY = 2 };
 
 typedef struct fq_pipe_desc {
   int32_t n_cols;                   /* input schema */
@@ -188,6 +190,8 @@ typedef struct fq_pipe_desc {
                                        (transform_aggregate_partial.rs:50-78) */
   int32_t n_exprs;
   int32_t exprs[FQ_MAX_EXPRS];      /* roots of the select expressions */
+  int32_t n_keys;                   /* FQ_PIPE_GROUPBY: GROUP BY expressions (plan_parser.rs:279-308), else 0 */
+  int32_t keys[FQ_MAX_KEYS];        /* their roots; `exprs` are the aggregate expressions (AggregatePlan.aggr_expr) */
 } fq_pipe_desc;
 
 typedef struct fq_pipe fq_pipe;
@@ -238,6 +242,40 @@ fq_status fq_pipe_aggregator_nodes(fq_ctx *ctx, const fq_pipe *pipe, int32_t *no
  * that merge states on the device (ncclAllGather of n_bytes) */
 #define FQ_STATE_HEADER_SLOTS 6
 fq_status fq_pipe_state_device(fq_ctx *ctx, const fq_pipe *pipe, void **dev_ptr, uint64_t *n_bytes);
+
+/* ---- GROUP BY pipes: hash aggregation ----
+ * The reference plans GROUP BY (plan_parser.rs:279-308: AggregatePlan{group_expr, aggr_expr}, schema = the group fields
+ * followed by the aggregate fields) but its pipeline builder only ever uses aggr_expr (pipeline_builder.rs:50-65): the
+ * operator is not executed there.  This is the operator the plan describes, with the reference's own aggregate protocol
+ * applied per group: one output row per distinct tuple of key values (a NULL key is a group of its own); Sum / Min / Max
+ * skip NULL slots and are Type(None) for a group without a valid row, Count is the group's row count
+ * (function_aggregator.rs:57-100, data_array_aggregate.rs:29); integer sums wrap.  Row order of the result is unspecified.
+ *
+ * A FQ_PIPE_GROUPBY pipe keeps an open-addressing hash table in HBM: 64-bit packed keys (the key expressions' value bits,
+ * plus one bit per nullable key: at most 64 bits in all) and one 8-byte state per Aggregator leaf per group, updated with
+ * atomics; every CTA pre-aggregates in a shared-memory table first, so low-cardinality keys never leave the SM.
+ * fq_pipe_groupby_reserve sizes (and clears) the table; a launch that meets more groups than reserved makes
+ * fq_pipe_fetch_groupby return FQ_ERR_CAPACITY (reserve more, relaunch).  FQ_RUN_ACCUMULATE keeps the table between launches.
+ * fq_pipe_export_groups writes the groups, in table order, to dense columns: key_cols[j] (+ key_valid[j] for nullable
+ * keys, one byte per row) and one column per Aggregator leaf in fq_pipe_aggregator_nodes order (+ leaf_valid[k] for
+ * leaves fq_pipe_leaf_nullable reports) — the caller evaluates arithmetic over aggregates (sum(x) / count(x)) as an
+ * ordinary projection over those columns, exactly like merge_result re-applies it (function_arithmetic.rs:82-88). */
+fq_status fq_pipe_key_dtype(fq_ctx *ctx, const fq_pipe *pipe, int32_t j, fq_dtype *out, int32_t *nullable);
+fq_status fq_pipe_leaf_dtype(fq_ctx *ctx, const fq_pipe *pipe, int32_t k, fq_dtype *out, int32_t *nullable);
+fq_status fq_pipe_groupby_reserve(fq_ctx *ctx, fq_pipe *pipe, uint64_t groups);
+fq_status fq_pipe_launch_groupby(fq_ctx *ctx, fq_pipe *pipe, const fq_source *src, uint32_t flags, void *stream);
+fq_status fq_pipe_fetch_groupby(fq_ctx *ctx, fq_pipe *pipe, uint64_t *n_groups);
+fq_status fq_pipe_export_groups(fq_ctx *ctx, fq_pipe *pipe, fq_column *const *key_cols, fq_column *const *key_valid,
+                                fq_column *const *leaf_cols, fq_column *const *leaf_valid, uint64_t capacity, void *stream);
+/* Multi-GPU exchange of partial groups (one process per GPU).  fq_pipe_export_partials writes this rank's groups as raw
+ * table entries — `entries` is a UInt64 column of n_groups x fq_pipe_group_entry_slots rows: the packed key, then the
+ * state slots — ordered by owner rank = hash(key) mod world, and reports how many go to each rank (counts[world], host
+ * memory, valid after fq_stream_synchronize).  The host moves the runs to their owners (NCCL all-to-all over NVLink);
+ * fq_pipe_merge_partials folds received entries into this pipe's table with the merge_state rules.  Afterwards every rank
+ * owns a disjoint set of complete groups and exports them with fq_pipe_export_groups. */
+fq_status fq_pipe_group_entry_slots(fq_ctx *ctx, const fq_pipe *pipe, int32_t *slots);
+fq_status fq_pipe_export_partials(fq_ctx *ctx, fq_pipe *pipe, int32_t world, fq_column *entries, uint64_t *counts, void *stream);
+fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *entries, uint64_t n_entries, uint32_t flags, void *stream);
 
 /* ---- multi-GPU merge point (processors/processor_merge.rs:37-66 feeding transform_aggregate_final.rs:50-78 /
  * the LimitTransform after the merge, pipeline_builder.rs:31-41) without a collective call ----

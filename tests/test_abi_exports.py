@@ -23,7 +23,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fuse_gpu.h but not exported"
     assert sorted(cabi.EXPORTS) == names   # the ctypes layer binds exactly the declared surface
-    assert lib.fq_abi_version() == 1
+    assert lib.fq_abi_version() == 2
 
 
 def test_no_cpu_fallback():
