@@ -316,7 +316,8 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def_readwrite("block_rows", &GpuOptions::block_rows)
       .def_readwrite("tail_quirk", &GpuOptions::tail_quirk)
       .def_readwrite("limit_early_exit", &GpuOptions::limit_early_exit)
-      .def_readwrite("block_quirks", &GpuOptions::block_quirks);
+      .def_readwrite("block_quirks", &GpuOptions::block_quirks)
+      .def_readwrite("group_by", &GpuOptions::group_by);
   py::class_<FuseQueryContext, FuseQueryContextRef>(m, "FuseQueryContext")
       .def_static("create_ctx", [](size_t workers, GpuContextRef gpu) { return FuseQueryContext::create_ctx(workers, nullptr, gpu); },
                   py::arg("worker_threads"), py::arg("gpu") = nullptr)

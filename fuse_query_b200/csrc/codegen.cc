@@ -538,15 +538,15 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     s += "  }\n";
     out->sel_tma_ok = !pred_cols.empty() && !(d.generated && g.used_cols.count(0)) && !g.used_cols.empty();
     if (out->sel_tma_ok) {
-      s += "  __device__ static __forceinline__ void tma_issue_pred(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
+      s += "  template <int HINT = 0> __device__ static __forceinline__ void tma_issue_pred(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
       int prefix = 0;
       for (int c : pred_cols) {
         int w = (int)dtype_size(g.col_dtype(c));
-        s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
+        s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
         prefix += w;
       }
       for (int c : pred_null) {
-        s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
+        s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
         prefix += 1;
       }
       s += "  }\n";
@@ -569,15 +569,15 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   out->row_bytes += (int)null_cols.size();
   s += fmt("  static constexpr int ROW_BYTES = %d;\n", out->row_bytes);
   if (out->tma_ok) {
-    s += "  __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
+    s += "  template <int HINT = 0> __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
     int prefix = 0;
     for (int c : g.used_cols) {
       int w = (int)dtype_size(g.col_dtype(c));
-      s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
+      s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols[%d] + tile * tile_rows * %dull, tile_rows * %du, bar);\n", prefix, c, w, w);
       prefix += w;
     }
     for (int c : null_cols) {
-      s += fmt("    fq_bulk_g2s(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
+      s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
       prefix += 1;
     }
     s += "  }\n";
@@ -757,8 +757,8 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       for (int x = 0; x < d.n_exprs; x++) {
         fq_dtype t = out->expr_dtypes[x];
         e.node(d.exprs[x]);
-        st += fmt("    ((%s *)p.outs[%d])[pos] = ", t == FQ_BOOL ? "fq_u8" : ctype(t), x) + e.val[d.exprs[x]] + ";\n";
-        if (out->expr_nullable[x]) st += fmt("    ((fq_u8 *)p.outs_valid[%d])[pos] = ", x) + e.ok[d.exprs[x]] + ";\n";
+        st += fmt("    fq_st1<%s>(p.outs[%d], pos, ", t == FQ_BOOL ? "fq_u8" : ctype(t), x) + e.val[d.exprs[x]] + ");\n";
+        if (out->expr_nullable[x]) st += fmt("    fq_st1<fq_u8>(p.outs_valid[%d], pos, ", x) + e.ok[d.exprs[x]] + ");\n";
       }
       s += e.body + st;
     }

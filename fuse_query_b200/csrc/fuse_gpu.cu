@@ -158,6 +158,7 @@ struct Shapes {
     env("FQ_TUNE_SELT_THREADS", &selt_threads); env("FQ_TUNE_SELT_UNROLL", &selt_unroll); env("FQ_TUNE_SELT_SEG", &selt_seg); env("FQ_TUNE_SELT_LAG", &selt_lag);
     if (getenv("FQ_TUNE_SELT_STAGES") && atoi(getenv("FQ_TUNE_SELT_STAGES")) > 0) selt_stages_env = atoi(getenv("FQ_TUNE_SELT_STAGES"));
     env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
+    if (getenv("FQ_TUNE_EXTRA")) tuned = true;
   }
   std::string defines() const {
     char b[1536];
@@ -167,7 +168,14 @@ struct Shapes {
              "#define FQ_TMA_UNROLL %d\n#define FQ_TMA_STAGES %d\n#define FQ_TMA_MIN_BLOCKS %d\n#define FQ_SEL_THREADS %d\n"
              "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
              selt_threads, selt_unroll, selt_seg, selt_lag, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
-    return b;
+    std::string out = b;
+    // FQ_TUNE_EXTRA: raw preprocessor text for A/B experiments, ';' separates lines ("#define FQ_STORE_CS 0;#define FQ_L2_HINTS 0")
+    if (const char *x = getenv("FQ_TUNE_EXTRA")) {
+      std::string t = x;
+      for (char &c : t) if (c == ';') c = '\n';
+      out += t + "\n";
+    }
+    return out;
   }
 };
 const Shapes &shapes() {

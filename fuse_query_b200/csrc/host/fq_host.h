@@ -447,6 +447,7 @@ struct GpuOptions {
   bool block_quirks = true;      // fused aggregate pipes reproduce SURVEY F8: with a WHERE clause, a Sum whose predicate
                                  // empties one of the reference's 10 000-row blocks fails like the reference does
                                  // ("DataValue to array cannot be NONE NULL"); false = return the merged sum instead
+  bool group_by = true;          // execute GROUP BY (hash aggregation); false = ignore it like the reference's pipeline builder
   bool align_runs = false;       // internal: only merge partitions into one device block when block boundaries line up
 };
 class FuseQueryContext : public std::enable_shared_from_this<FuseQueryContext> {
@@ -615,6 +616,30 @@ class GpuPipeTransform : public IProcessor {
   DataSchemaRef schema_;
   std::vector<ExpressionPlan> exprs_;
   std::optional<size_t> limit_;
+};
+
+// GROUP BY.  The reference plans AggregatePlan{group_expr, aggr_expr} (plan_parser.rs:279-308) but
+// PipelineBuilder only uses aggr_expr (pipeline_builder.rs:50-65): a GROUP BY query there returns the un-grouped aggregate.
+// With GpuOptions.group_by (default on) the plan is executed as written: ONE processor over all partitions — the hash
+// table in HBM is the merge point — emitting one block with the plan's schema: the group fields, then the aggregate
+// fields, one row per group (row order unspecified).  Arithmetic over aggregates is applied per group exactly like
+// merge_result does (function_arithmetic.rs:82-88), as a projection over the exported leaf columns.
+class GpuGroupByTransform : public IProcessor {
+ public:
+  GpuGroupByTransform(FuseQueryContextRef ctx, std::string db, std::string table, Partitions partitions,
+                      std::optional<ExpressionPlan> predicate, DataSchemaRef schema, std::vector<ExpressionPlan> group_expr,
+                      std::vector<ExpressionPlan> aggr_expr);
+  std::string name() const override { return "GpuGroupByTransform"; }
+  void connect_to(IProcessorRef) override;
+  SendableDataBlockStream execute() override;
+
+ private:
+  FuseQueryContextRef ctx_;
+  std::string db_, table_;
+  Partitions partitions_;
+  std::optional<ExpressionPlan> predicate_;
+  DataSchemaRef schema_;
+  std::vector<ExpressionPlan> group_expr_, aggr_expr_;
 };
 
 // processors/pipeline.rs:13-135

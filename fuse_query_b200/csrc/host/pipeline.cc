@@ -596,6 +596,150 @@ SendableDataBlockStream GpuPipeTransform::execute() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// GpuGroupByTransform
+// ---------------------------------------------------------------------------------------------
+GpuGroupByTransform::GpuGroupByTransform(FuseQueryContextRef ctx, std::string db, std::string table, Partitions partitions,
+                                         std::optional<ExpressionPlan> predicate, DataSchemaRef schema, std::vector<ExpressionPlan> group_expr,
+                                         std::vector<ExpressionPlan> aggr_expr)
+    : ctx_(std::move(ctx)), db_(std::move(db)), table_(std::move(table)), partitions_(std::move(partitions)), predicate_(std::move(predicate)),
+      schema_(std::move(schema)), group_expr_(std::move(group_expr)), aggr_expr_(std::move(aggr_expr)) {
+  if (predicate_ && predicate_->is_aggregate())
+    throw FuseQueryError::internal("Aggregate function " + predicate_->to_string() + " is found in WHERE in query");
+  for (const auto &k : group_expr_)
+    if (k.is_aggregate()) throw FuseQueryError::internal("Aggregate function " + k.to_string() + " is found in GROUP BY in query");
+  if (group_expr_.size() > (size_t)FQ_MAX_KEYS) throw FuseQueryError::internal("Unsupported on the device path: more than 4 GROUP BY expressions");
+  if (aggr_expr_.size() > (size_t)FQ_MAX_EXPRS) throw FuseQueryError::internal("Unsupported on the device path: more than 8 aggregate expressions in a GROUP BY");
+}
+void GpuGroupByTransform::connect_to(IProcessorRef) { throw FuseQueryError::internal("Cannot call GpuGroupByTransform connect_to"); }
+
+// the select expression with every Aggregator leaf replaced by a field of the exported leaf block
+static FunctionRef over_leaves(const Function &f, const std::map<const Function *, std::string> &leaf_name) {
+  switch (f.kind) {
+    case Function::Aggregator: return Function::FieldFunction(leaf_name.at(&f));
+    case Function::Alias: return over_leaves(*f.left, leaf_name);
+    case Function::Constant: return Function::ConstantFunction(f.value);
+    case Function::Arithmetic: return Function::ArithmeticFunction(f.op, {over_leaves(*f.left, leaf_name), over_leaves(*f.right, leaf_name)});
+    case Function::Variable: throw FuseQueryError::internal("Unsupported aggregate operation for function field");
+    case Function::Comparison:
+      throw FuseQueryError::internal(std::string("Unsupported aggregate operation for function ") + (const char *[]){"=", "<", "<=", ">", ">="}[f.op % 5]);
+    default: throw FuseQueryError::internal(std::string("Unsupported aggregate operation for function ") + (f.op == FQ_LG_AND ? "and" : "or"));
+  }
+}
+
+SendableDataBlockStream GpuGroupByTransform::execute() {
+  GpuContextRef gpu = ctx_->gpu();
+  ITableRef table = ctx_->get_table(db_, table_);
+  FunctionRef pred = predicate_ ? predicate_->to_function() : nullptr;
+  std::vector<FunctionRef> keys, funcs;
+  for (const auto &e : group_expr_) keys.push_back(e.to_function());
+  for (const auto &e : aggr_expr_) funcs.push_back(e.to_function());
+  std::vector<const Function *> leaves;
+  for (auto &f : funcs) collect_leaves(*f, &leaves);
+
+  PipeRef pipe;
+  Lowering lw;
+  uint64_t hint = 1 << 16, n_groups = 0;
+  for (;;) {   // the table is grown until the groups fit (a full re-scan: cardinality is unknown up front)
+    struct OptionsGuard {
+      FuseQueryContextRef c;
+      GpuOptions saved;
+      explicit OptionsGuard(FuseQueryContextRef ctx) : c(std::move(ctx)), saved(c->options) {}
+      ~OptionsGuard() { c->options = saved; }
+    };
+    SendableDataBlockStream source;
+    {
+      OptionsGuard guard(ctx_);
+      ctx_->options.block_rows = 0;
+      ctx_->options.align_runs = false;
+      source = table->read(ctx_, partitions_);
+    }
+    int launches = 0;
+    while (auto block = source->next()) {
+      if (!pipe) {
+        if (block->generated) lw.column_of(*block, block->schema()->fields[0].name);
+        const int p = pred ? lw.lower(*pred, *block) : -1;
+        std::vector<int> roots, key_roots;
+        for (auto &f : funcs) roots.push_back(lw.lower(*f, *block));
+        for (auto &k : keys) key_roots.push_back(lw.lower(*k, *block));
+        fq_pipe_desc d = lw.desc(FQ_PIPE_GROUPBY, p, roots);
+        d.n_keys = (int)key_roots.size();
+        for (size_t k = 0; k < key_roots.size(); k++) d.keys[k] = key_roots[k];
+        pipe = compile_pipe(gpu, d);
+      }
+      if (launches == 0) gpu->check(fq_pipe_groupby_reserve(gpu->raw(), pipe->pipe, hint));
+      BoundSource bs;
+      bind_source(lw, *block, &bs);
+      gpu->check(fq_pipe_launch_groupby(gpu->raw(), pipe->pipe, &bs.src, launches > 0 ? FQ_RUN_ACCUMULATE : 0, gpu->stream));
+      launches++;
+    }
+    if (!pipe) break;   // no rows at all: no groups
+    const fq_status st = fq_pipe_fetch_groupby(gpu->raw(), pipe->pipe, &n_groups);
+    if (st == FQ_ERR_CAPACITY) { hint *= 8; continue; }
+    gpu->check(st);
+    break;
+  }
+
+  std::vector<DataArrayRef> out;
+  if (!pipe || n_groups == 0) {   // an empty result still carries the plan's schema
+    for (const auto &f : schema_->fields) out.push_back(DataArray::alloc(gpu, f.data_type == FQ_UTF8 ? (DataType)FQ_U8 : f.data_type, 0));
+    return std::make_unique<DataBlockStream>(std::vector<DataBlock>{DataBlock(schema_, out)});
+  }
+  // export: key columns, then one column per Aggregator leaf
+  std::vector<DataArrayRef> key_arrays, key_valid, leaf_arrays, leaf_valid;
+  std::vector<fq_column *> kc, kv, lc, lv;
+  for (size_t j = 0; j < keys.size(); j++) {
+    fq_dtype t;
+    int32_t nullable = 0;
+    gpu->check(fq_pipe_key_dtype(gpu->raw(), pipe->pipe, (int)j, &t, &nullable));
+    key_arrays.push_back(DataArray::alloc(gpu, t, n_groups));
+    key_valid.push_back(nullable ? DataArray::alloc(gpu, FQ_BOOL, n_groups) : nullptr);
+    kc.push_back(key_arrays.back()->column());
+    kv.push_back(nullable ? key_valid.back()->column() : nullptr);
+  }
+  std::vector<int32_t> nodes(leaves.size() + 1);
+  int32_t n_leaves = 0;
+  gpu->check(fq_pipe_aggregator_nodes(gpu->raw(), pipe->pipe, nodes.data(), (int32_t)nodes.size(), &n_leaves));
+  for (int k = 0; k < n_leaves; k++) {
+    fq_dtype t;
+    int32_t nullable = 0;
+    gpu->check(fq_pipe_leaf_dtype(gpu->raw(), pipe->pipe, k, &t, &nullable));
+    leaf_arrays.push_back(DataArray::alloc(gpu, t, n_groups));
+    leaf_valid.push_back(nullable ? DataArray::alloc(gpu, FQ_BOOL, n_groups) : nullptr);
+    lc.push_back(leaf_arrays.back()->column());
+    lv.push_back(nullable ? leaf_valid.back()->column() : nullptr);
+  }
+  gpu->check(fq_pipe_export_groups(gpu->raw(), pipe->pipe, kc.data(), kv.data(), lc.data(), lv.data(), n_groups, gpu->stream));
+  gpu->check(fq_stream_synchronize(gpu->raw(), gpu->stream));
+  for (size_t j = 0; j < keys.size(); j++) {
+    if (key_valid[j]) key_arrays[j]->set_validity(key_valid[j]);
+    out.push_back(key_arrays[j]);
+  }
+  // the leaf block and the select expressions over it
+  auto leaf_schema = std::make_shared<DataSchema>();
+  std::map<const Function *, std::string> leaf_name;
+  for (int k = 0; k < n_leaves; k++) {
+    if (leaf_valid[k]) leaf_arrays[k]->set_validity(leaf_valid[k]);
+    leaf_schema->fields.push_back({"__leaf" + std::to_string(k), leaf_arrays[k]->data_type(), leaf_valid[k] != nullptr});
+  }
+  for (const Function *l : leaves) {
+    const int node = lw.node_of.at(l);
+    for (int k = 0; k < n_leaves; k++)
+      if (nodes[k] == node) leaf_name[l] = "__leaf" + std::to_string(k);
+  }
+  DataBlock leaf_block(leaf_schema, leaf_arrays);
+  std::vector<FunctionRef> finals;
+  std::vector<const Function *> raw;
+  for (auto &f : funcs) finals.push_back(over_leaves(*f, leaf_name));
+  for (auto &f : finals) raw.push_back(f.get());
+  if (!raw.empty()) {
+    if (n_leaves == 0) throw FuseQueryError::internal("Unsupported on the device path: GROUP BY select expressions without an aggregate");
+    ProjectResult r = run_project(gpu, leaf_block, nullptr, raw, -1, false);
+    for (auto &c : r.columns) out.push_back(c);
+  }
+  return std::make_unique<DataBlockStream>(std::vector<DataBlock>{DataBlock(schema_, out)});
+}
+
+// ---------------------------------------------------------------------------------------------
 // Pipeline — processors/pipeline.rs
 // ---------------------------------------------------------------------------------------------
 void Pipeline::add_source(IProcessorRef source) {
@@ -663,7 +807,13 @@ Pipeline PipelineBuilder::build() const {
     size_t j = 1;
     std::optional<ExpressionPlan> pred;
     if (j < plans.size() && plans[j].kind == PlanNode::Filter) pred = plans[j++].predicate;
-    if (j < plans.size() && (plans[j].kind == PlanNode::Projection || plans[j].kind == PlanNode::Aggregate)) {
+    if (j < plans.size() && plans[j].kind == PlanNode::Aggregate && !plans[j].group_expr.empty() && ctx->options.group_by) {
+      // GROUP BY: one hash-aggregation processor over every partition (the table in HBM is the merge point)
+      const PlanNode &src = plans[0];
+      const PlanNode &sel = plans[j];
+      pipeline.add_source(std::make_shared<GpuGroupByTransform>(ctx, src.db, src.table, src.partitions, pred, sel.schema(), sel.group_expr, sel.expr));
+      i = j + 1;
+    } else if (j < plans.size() && (plans[j].kind == PlanNode::Projection || plans[j].kind == PlanNode::Aggregate)) {
       const PlanNode &src = plans[0];
       const PlanNode &sel = plans[j];
       const bool is_agg = sel.kind == PlanNode::Aggregate;

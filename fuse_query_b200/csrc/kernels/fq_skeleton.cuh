@@ -58,8 +58,9 @@ typedef signed char fq_i8;
 #define FQ_GB_SMEM_PROBES 4  // linear probes in the CTA's shared-memory table before a row goes to the table in HBM
 #endif
 #ifndef FQ_SELT_THREADS
-#define FQ_SELT_THREADS 512  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp)
-#define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
+#define FQ_SELT_THREADS 448  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp) = 16 warps, 4 per SM
+                             // sub-partition: 128 registers per thread (18 warps put 5 on one sub-partition: 96, and spills)
+#define FQ_SELT_UNROLL 4     // tile = 448 * 4 vector groups = 28 KB of a UInt64 column per bulk copy
 #define FQ_SELT_SEG 8        // tiles per segment (one look-back each): 256 KB of a UInt64 column
 #define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~192 KB in flight per SM)
 #define FQ_SELT_LAG 3        // pass 2 runs this many segments behind pass 1
@@ -177,6 +178,18 @@ __device__ __forceinline__ void fq_load_vec(T (&dst)[V], const void *base, fq_u6
   }
 }
 
+// Outputs are written once and never read by the kernel: streaming stores (.cs: evict-first) keep them from pushing the
+// input lines that pass 2 of the select kernel will read again out of L2.
+#ifndef FQ_STORE_CS
+#define FQ_STORE_CS 1
+#endif
+template <class T> __device__ __forceinline__ void fq_st1(void *base, fq_u64 idx, T v) {
+#if FQ_STORE_CS
+  __stcs((T *)base + idx, v);
+#else
+  ((T *)base)[idx] = v;
+#endif
+}
 // Store V consecutive values (the mirror of fq_load_vec): one 16/8/4/2-byte store when the run is that wide.
 // `base + first` is aligned to V * sizeof(T) because vector groups start at multiples of V rows.
 template <class T, int V>
@@ -188,8 +201,13 @@ __device__ __forceinline__ void fq_store_vec(void *base, fq_u64 first, const T (
 #pragma unroll
     for (int k = 0; k < V; k++) u.t[k] = src[k];
 #pragma unroll
-    for (int k = 0; k < BYTES / 16; k++)
+    for (int k = 0; k < BYTES / 16; k++) {
+#if FQ_STORE_CS
+      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16 * k), "r"(u.q[k].x), "r"(u.q[k].y), "r"(u.q[k].z), "r"(u.q[k].w) : "memory");
+#else
       asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p + 16 * k), "r"(u.q[k].x), "r"(u.q[k].y), "r"(u.q[k].z), "r"(u.q[k].w) : "memory");
+#endif
+    }
   } else if constexpr (BYTES == 8) {
     union { fq_u64 q; T t[V]; } u;
 #pragma unroll
@@ -654,10 +672,24 @@ __device__ __forceinline__ void fq_mbar_wait(fq_u32 bar, fq_u32 parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
-// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted in bytes on `bar`
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted in bytes on `bar`.
+// HINT: L2 eviction priority of the lines the copy touches — 0 default, 1 evict_last (they will be read again: pass 1 of
+// the select kernel), 2 evict_first (last use: its pass 2).
+#ifndef FQ_L2_HINTS
+#define FQ_L2_HINTS 1
+#endif
+template <int HINT = 0>
 __device__ __forceinline__ void fq_bulk_g2s(fq_u32 dst, const void *src, fq_u32 bytes, fq_u32 bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  if constexpr (HINT == 0 || !FQ_L2_HINTS) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  } else {
+    fq_u64 pol;
+    if constexpr (HINT == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+  }
 }
 // V consecutive values of one staged column from shared memory
 template <class T, int V>
@@ -1401,10 +1433,11 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
         const fq_u32 dst = fq_smem_addr(fq_dyn_smem + (size_t)slot * stage_bytes);
         if (all_cols) {
           fq_mbar_expect_tx(full, all_bytes);
-          Q::tma_issue(p, dst, full, tile, (fq_u32)tile_rows);
+          Q::template tma_issue<2>(p, dst, full, tile, (fq_u32)tile_rows);          // last use of these lines
         } else {
           fq_mbar_expect_tx(full, pred_bytes);
-          Q::tma_issue_pred(p, dst, full, tile, (fq_u32)tile_rows);
+          if (stage2) Q::template tma_issue_pred<1>(p, dst, full, tile, (fq_u32)tile_rows);   // dense segments read them again
+          else Q::template tma_issue_pred<0>(p, dst, full, tile, (fq_u32)tile_rows);
         }
         if (++slot == stages) { slot = 0; round++; }
       };

@@ -640,3 +640,52 @@ def test_projection_errors_beyond_the_limit_follow_the_reference_blocks(gpu, gen
     assert rows_of(h.execute_sql(ctx, sql)) == want.rows() and len(want.rows()) == 5
     ctx.options.limit_early_exit = False         # full scan: the kernel sees the zero divisor, the reference never pulls that block
     assert rows_of(h.execute_sql(ctx, sql)) == want.rows()
+
+
+def test_group_by_through_sql_matches_the_group_by_oracle(gpu):
+    """AggregatePlan{group_expr, aggr_expr} executed as planned (plan_parser.rs:279-308; the reference's pipeline builder
+    drops group_expr, pipeline_builder.rs:50-65): schema = group fields then aggregate fields (plan_builder.rs:63-83), one
+    row per group, arithmetic over aggregates applied per group.  Oracle-anchored (oracle/groupby.py); order unspecified."""
+    from fuse_query_b200.tables import register_table
+    from oracle.groupby import run_group_by
+    n = 160_000
+    key = "(- (col number) (* (/ (col number) (u64 7)) (u64 7)))"
+    aggs = ["(sum (col number))", "(count (col number))", "(/ (sum (col number)) (count (col number)))", "(max (+ (col number) (u64 1)))"]
+    sql = ("select number - number / 7 * 7, sum(number), count(number), sum(number) / count(number), max(number + 1) "
+           f"from system.numbers_mt({n}) where number >= 10 group by number - number / 7 * 7")
+    names, want = run_group_by([key], aggs, total=n, predicate="(>= (col number) (u64 10))")
+    for generated in (False, True):
+        for workers in (0, 1):
+            ctx = make_ctx(gpu, workers)
+            ctx.options.generated = generated
+            blocks = h.execute_sql(ctx, sql)
+            assert blocks[0].schema().names() == names == ["number - number / 7 * 7", "Sum(number)", "Count(number)", "Sum(number) / Count(number)",
+                                                           "Max(number + 1)"]
+            assert sorted(rows_of(blocks)) == want
+    # select list order does not matter: the plan's schema is group fields first (the reference's own rule)
+    ctx = make_ctx(gpu, 1)
+    blocks = h.execute_sql(ctx, f"select count(number), number / 40000 from system.numbers_mt({n}) group by number / 40000")
+    assert blocks[0].schema().names() == ["number / 40000", "Count(number)"] and sorted(rows_of(blocks)) == [(i, 40000) for i in range(4)]
+    # keys only (DISTINCT), and a table with NULL keys / NULL values
+    blocks = h.execute_sql(ctx, f"select number / 50000 from system.numbers_mt({n}) group by number / 50000")
+    assert sorted(rows_of(blocks)) == [(0,), (1,), (2,), (3,)]
+    rng = np.random.default_rng(3)
+    m = 50_000
+    k = rng.integers(0, 20, m).astype(np.int16)
+    k_ok = rng.random(m) > 0.1
+    v = rng.integers(-500, 500, m).astype(np.int64)
+    v_ok = rng.random(m) > 0.3
+    register_table(ctx, gpu, "default", "g", {"k": (k, k_ok), "v": (v, v_ok)})
+    blocks = h.execute_sql(ctx, "select k, sum(v), min(v), count(v), sum(v) / count(v) from g group by k")
+    table = {"k": o.Array(o.I16, k, k_ok.astype(np.uint8)), "v": o.Array(o.I64, v, v_ok.astype(np.uint8))}
+    _, want = run_group_by(["(col k)"], ["(sum (col v))", "(min (col v))", "(count (col v))", "(/ (sum (col v)) (count (col v)))"], table=table)
+    got = rows_of(blocks)
+    assert sorted(got, key=lambda r: (r[0] is not None, r[0])) == want and len(want) == 21
+    # the reference's own behaviour (GROUP BY planned, then ignored) stays available
+    ctx.options.group_by = False
+    blocks = h.execute_sql(ctx, f"select number / 40000, count(number) from system.numbers_mt({n}) group by number / 40000")
+    assert rows_of(blocks) == [(n,)]
+    # errors: an aggregate as a key, more key bits than the table key holds
+    ctx.options.group_by = True
+    with pytest.raises(h.FuseQueryError):
+        h.execute_sql(ctx, f"select sum(number), count(number) from system.numbers_mt({n}) group by sum(number)")
