@@ -460,8 +460,11 @@ def run_ours(args):
 
     # ---- every README query x {materialised, generated}: whole-job numbers at this N, merged result verified ----
     per_query = {}
+    group_by = None
     if not args.no_query_table:
         per_query = query_table(rig, col, begin, n, total, generated)
+        if col is not None:
+            group_by = group_by_table(rig, col)
 
     # ---- e2e: host-resident (pinned) column -> H2D chunks overlapped with the kernel -> D2H state ----
     e2e = run_e2e(rig, col, begin, n, total, generated)
@@ -501,7 +504,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": row_bytes * n,
                          "note": "kernel_ms includes the in-kernel wait for the slowest rank when N > 1"},
             "throughput_no_merge": no_merge,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "sql_e2e": sql_e2e,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "group_by": group_by,
+            "sql_e2e": sql_e2e,
         }
         if world == 1 and not args.no_cpu_baseline:
             rows_cpu = cpu_sample_rows()
@@ -626,6 +630,84 @@ def query_table(rig: Rig, col, begin, n, total, generated_only):
         for c in outs + fin:
             c.free()
     return per_query
+
+
+def group_by_table(rig: Rig, col):
+    """GROUP BY hash aggregation over numbers_mt(10^9): SELECT number % k, sum, count, min, max ... GROUP BY
+    number % k (written number - number / k * k: the reference has no % operator).  Whole-job time at this N: every rank
+    aggregates its shard into its own hash table; at N > 1 the partial groups then travel to their owner rank
+    (hash(key) mod N) with one NCCL all-to-all over NVLink and are folded there (fq_pipe_export_partials /
+    fq_pipe_merge_partials).  Verified: number of groups, and the column sums of count / sum / min / max against closed forms."""
+    cabi, ctx, world, rank, torch, dist = rig.cabi, rig.ctx, rig.world, rig.rank, rig.torch, rig.dist
+    total = 1_000_000_000
+    b, n = shard_of(rank, world, total)
+    ctx.fill_numbers(col, b, n, rig.stream)
+    src = cabi.make_source([col], n)
+    out = {}
+    aggs = [f"(sum {NUM})", f"(count {NUM})", f"(min {NUM})", f"(max {NUM})"]
+    for k in (7, 1000, 1_000_000, 100_000_000):
+        key = f"(- {NUM} (* (/ {NUM} (u64 {k})) (u64 {k})))"
+        pipe = ctx.pipe(aggs, keys=[key])
+        owner = ctx.pipe(aggs, keys=[key]) if world > 1 else None
+        slots = pipe.group_entry_slots()
+        local_groups = min(k, n)
+        pipe.groupby_reserve(local_groups)
+        if owner is not None:
+            owner.groupby_reserve(k // world + k // (4 * world) + 1024)
+        ent = ctx.column(cabi.U64, local_groups * slots) if world > 1 else None
+        recv = None
+
+        def one():
+            nonlocal recv
+            pipe.launch_groupby(src, stream=rig.stream)
+            if world == 1:
+                return
+            g = pipe.fetch_groupby()
+            counts = pipe.export_partials(world, ent, stream=rig.stream)
+            send_counts = torch.tensor(counts, dtype=torch.int64, device=rig.dev)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            rc = recv_counts.tolist()
+            send_t = torch.as_tensor(DevPtr(ent.device_ptr, g * slots), device=rig.dev)
+            if recv is None or recv[1] < sum(rc) * slots:
+                recv = (ctx.column(cabi.U64, max(1, sum(rc) * slots)), sum(rc) * slots)
+            recv_t = torch.as_tensor(DevPtr(recv[0].device_ptr, max(1, sum(rc) * slots)), device=rig.dev)[:sum(rc) * slots]
+            dist.all_to_all_single(recv_t, send_t[:g * slots], [c * slots for c in rc], [c * slots for c in counts])
+            torch.cuda.current_stream().synchronize()
+            owner.merge_partials(recv[0], sum(rc), stream=rig.stream)
+
+        reps = 2 if k >= 1_000_000 else 3
+        ms = timed(rig, one, reps, warm=1)
+        final = owner if owner is not None else pipe
+        groups = final.fetch_groupby()
+        keys, kval, leaves, lval = final.export_groups(groups)
+        lv = [torch.as_tensor(DevPtr(c.device_ptr, max(1, groups)), device=rig.dev)[:groups] for c in leaves]
+        # checks that need no sort: totals over all groups (and all ranks)
+        sums = [int(lv[0].sum().item()) & M64, int(lv[1].sum().item()), int(lv[2].sum().item()) & M64, int(lv[3].sum().item()) & M64, groups]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, sums)
+            sums = [sum(x[i] for x in gathered) & M64 for i in range(5)]
+        kk = min(k, total)
+        # group r's max is the largest number below `total` congruent to r
+        max_sum = (kk * (total - kk) + _sum(kk)) if total % kk == 0 else sum(((total - 1 - r) // kk) * kk + r for r in range(kk))
+        want = [_sum(total), total, _sum(kk), max_sum & M64, kk]
+        assert sums == want, f"group by k={k}: {sums} != {want}"
+        table_bytes = (2 * local_groups) * 8 * slots
+        out[f"number % {k}"] = {"ms": round(ms, 4), "rows_per_s": total / (ms * 1e-3), "groups": kk, "verified": True, "n_gpus": world,
+                                "read_gb_per_s": 8 * total / (ms * 1e-3) / 1e9,
+                                "bytes": {"column_read": 8 * total, "table_per_gpu_at_least": table_bytes},
+                                "note": "whole job: scan + hash aggregation" + (" + all-to-all of partial groups + merge" if world > 1 else "")}
+        for c in keys + leaves:
+            c.free()
+        pipe.destroy()
+        if owner is not None:
+            owner.destroy()
+        if ent is not None:
+            ent.free()
+        if recv is not None:
+            recv[0].free()
+    return out
 
 
 def run_sql_e2e(device, total):

@@ -242,6 +242,7 @@ struct fq_pipe {
   uint64_t gb_cap = 0;
   uint32_t *gb_flags = nullptr;      // [0] overflow, [1] EMPTY-valued key seen, [2..3] group count (u64), [4..5] error bits
   uint64_t *h_gb = nullptr;          // pinned mirror of gb_flags (4 x u64)
+  uint64_t *gb_identity = nullptr;   // device copy of a fresh group's state
   unsigned gb_smem_cap = 0;
   bool launched_groupby = false;
   unsigned mapt_stages = 0;
@@ -864,6 +865,7 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
   cudaFree(pipe->gb_keys);
   cudaFree(pipe->gb_slots);
   cudaFree(pipe->gb_flags);
+  cudaFree(pipe->gb_identity);
   if (pipe->h_gb) cudaFreeHost(pipe->h_gb);
   if (pipe->h_merged) cudaFreeHost(pipe->h_merged);
   if (pipe->h_state) cudaFreeHost(pipe->h_state);
@@ -1513,6 +1515,17 @@ fq_status gb_check(const fq_pipe *pipe) {
   if (!pipe || pipe->gen.kind != FQ_PIPE_GROUPBY) return set_err(FQ_ERR_INVALID, "Internal Error: not a GROUP BY pipe");
   return FQ_OK;
 }
+// empty table on `stream`: keys = EMPTY, states = the aggregates' identities, flags = 0
+fq_status gb_clear(fq_ctx *ctx, fq_pipe *pipe, cudaStream_t s) {
+  const int G = 1 + pipe->gen.n_slots;
+  CUDA_TRY(cudaMemsetAsync(pipe->gb_flags, 0, 64, s));
+  const unsigned grid = (unsigned)std::min<uint64_t>((pipe->gb_cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_gb_fill<<<grid, 256, 0, s>>>((fq_u64 *)pipe->gb_keys, (fq_u64 *)pipe->gb_slots, pipe->gb_cap + 1, G, (const fq_u64 *)pipe->gb_identity);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  pipe->launched_groupby = false;
+  return FQ_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1562,19 +1575,13 @@ fq_status fq_pipe_groupby_reserve(fq_ctx *ctx, fq_pipe *pipe, uint64_t groups) {
     CUDA_TRY(cudaMalloc(&pipe->gb_flags, 64));
     CUDA_TRY(cudaHostAlloc(&pipe->h_gb, 64, cudaHostAllocDefault));
   }
-  // clear: keys = EMPTY, states = the aggregates' identities
-  const std::vector<uint64_t> idn = gb_identity(pipe->gen);
-  uint64_t *d_idn = nullptr;
-  CUDA_TRY(cudaMalloc(&d_idn, sizeof(uint64_t) * idn.size()));
-  CUDA_TRY(cudaMemcpy(d_idn, idn.data(), sizeof(uint64_t) * idn.size(), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(pipe->gb_flags, 0, 64));
-  const unsigned grid = (unsigned)std::min<uint64_t>((cap + 256) / 256, (uint64_t)ctx->sm_count * 8);
-  fq_gb_fill<<<grid, 256>>>((fq_u64 *)pipe->gb_keys, (fq_u64 *)pipe->gb_slots, cap + 1, G, (const fq_u64 *)d_idn);
-  CUDA_TRY(cudaGetLastError());
-  ctx->launches++;
+  if (!pipe->gb_identity) {
+    const std::vector<uint64_t> idn = gb_identity(pipe->gen);
+    CUDA_TRY(cudaMalloc(&pipe->gb_identity, sizeof(uint64_t) * idn.size()));
+    CUDA_TRY(cudaMemcpy(pipe->gb_identity, idn.data(), sizeof(uint64_t) * idn.size(), cudaMemcpyHostToDevice));
+  }
+  if (fq_status st = gb_clear(ctx, pipe, nullptr)) return st;
   CUDA_TRY(cudaDeviceSynchronize());
-  cudaFree(d_idn);
-  pipe->launched_groupby = false;
   return FQ_OK;
 }
 
@@ -1596,7 +1603,7 @@ fq_status fq_pipe_launch_groupby(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   if (fq_status st = gb_check(pipe)) return st;
   if (!pipe->gb_cap) return set_err(FQ_ERR_INVALID, "Internal Error: fq_pipe_groupby_reserve was not called");
   if (!(flags & FQ_RUN_ACCUMULATE) && pipe->launched_groupby) {
-    if (fq_status st = fq_pipe_groupby_reserve(ctx, pipe, pipe->gb_cap / 2)) return st;   // restart from an empty table
+    if (fq_status st = gb_clear(ctx, pipe, (cudaStream_t)stream)) return st;   // restart from an empty table
   }
   fq_launch_params p;
   memset(&p, 0, sizeof p);
@@ -1720,7 +1727,7 @@ fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *en
   if (n_entries && (!entries || entries->dtype != FQ_U64 || entries->len < n_entries * (uint64_t)(1 + G)))
     return set_err(FQ_ERR_INVALID, "Internal Error: the entries column must be UInt64 with entries x %d rows", 1 + G);
   if (!(flags & FQ_RUN_ACCUMULATE) && pipe->launched_groupby) {
-    if (fq_status st = fq_pipe_groupby_reserve(ctx, pipe, pipe->gb_cap / 2)) return st;
+    if (fq_status st = gb_clear(ctx, pipe, (cudaStream_t)stream)) return st;
   }
   if (n_entries) {
     fq_launch_params p;

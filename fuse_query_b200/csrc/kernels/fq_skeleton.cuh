@@ -1424,9 +1424,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     if (lane == 0) {
       int slot = 0;          // ring slot and round of the next staged tile (no 64-bit divisions in the loop)
       fq_u32 round = 0;
-      fq_u64 hist[R];        // segments of the last iterations (registers: constant indexes after unrolling)
-#pragma unroll
-      for (int j = 0; j < R; j++) hist[j] = 0;
+      fq_u64 hist[1] = {0};  // segment of the previous iteration
       auto stage_tile = [&](fq_u64 tile, bool all_cols) {
         if (round >= 1) fq_mbar_wait(fq_smem_addr(&s_bars[STAGES + slot]), (round - 1) & 1);
         const fq_u32 full = fq_smem_addr(&s_bars[slot]);
@@ -1460,11 +1458,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
         __threadfence_block();
         s_ready[k % FQ_SELT_CLAIMS] = k + 1;
         if (!(c < n_seg) || st) {
-          if (stage2) {   // drain: the consumers scatter what is pending, oldest first
-#pragma unroll
-            for (int a = LAG; a >= 1; a--)
-              if (k - a >= 0) stage_pass2(k - a, hist[a - 1]);
-          }
+          if (stage2 && k >= 1) stage_pass2(k - 1, hist[0]);   // drain: only the last segment can still be waiting for its pass 2
           break;
         }
         // the next claim's round trip to L2 overlaps the copies of this segment (its value is first used next iteration)
@@ -1474,10 +1468,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
           const fq_u64 tile = c * SEG + t;
           if (tile < n_full_tiles) stage_tile(tile, false);
         }
-        if (stage2 && k >= LAG) stage_pass2(k - LAG, hist[LAG - 1]);
-#pragma unroll
-        for (int j = R - 1; j > 0; j--) hist[j] = hist[j - 1];
-        hist[0] = c;          // hist[a - 1] = segment of iteration k - a at the next iteration
+        if (stage2 && k >= 1) stage_pass2(k - 1, hist[0]);   // a dense segment is staged again right behind its successor
+        hist[0] = c;          // segment of iteration k - 1 at the next iteration
         c = c_next;
       }
     }
@@ -1528,10 +1520,16 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     slot = (int)sr[0];
     round = sr[1];
   };
-  fq_u64 keepq[LAG], segq[LAG];   // segments streamed but not yet scattered, newest first (registers: constant indexes)
+  // Segments streamed but not yet scattered, newest first (registers: constant indexes): entry j = iteration k - 1 - j,
+  // valid when bit j of `pend` is set.  A DENSE segment is scattered one iteration after its pass 1 (its tiles come
+  // through the ring again right behind the next segment's: the shorter the distance, the more of the re-read hits L2 —
+  // at LAG = 3 the 148 SMs hold 100 MB between the passes and every re-read went to HBM); a SPARSE one LAG iterations
+  // after, when its look-back has long finished (waiting for it any earlier stalls the streaming: 1.2 -> 1.5 ms on the
+  // README predicate), re-reading the few kept groups with plain loads.
+  fq_u64 keepq[LAG], segq[LAG];
 #pragma unroll
   for (int j = 0; j < LAG; j++) keepq[j] = segq[j] = 0;
-  int pending = 0;
+  fq_u32 pend = 0;
   for (int k = 0;; k++) {
     const int b = k % R;
     if (lane == 0) {
@@ -1584,21 +1582,33 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
     __syncwarp();
     fq_bar_arrive(BAR_FULL + b, barthreads);
 
-    if (pending == LAG) {   // the oldest: segment of iteration k - LAG
+    // the previous segment, if dense: its tiles are next in the ring
+    if ((pend & 1u) && stage2) {
+      if (lane == 0) {
+        while ((s_p1[(k - 1) % R] >> 1) != k) {}   // every warp finished its pass 1 (the flag is written by the last one)
+      }
+      __syncwarp();
+      if (s_p1[(k - 1) % R] & 1) {
+        scatter(segq[0], keepq[0], (k - 1) % R);
+        pend &= ~1u;
+      }
+    }
+    // the segment of iteration k - LAG, if it is still waiting (sparse)
+    if (pend & (1u << (LAG - 1))) {
       scatter(segq[LAG - 1], keepq[LAG - 1], (k + 1) % R);
-      pending = LAG - 1;
+      pend &= ~(1u << (LAG - 1));
     }
     if (!active) {          // drain, oldest first: entry j is the segment of iteration k - 1 - j
 #pragma unroll
       for (int j = LAG - 2; j >= 0; j--)
-        if (j < pending) scatter(segq[j], keepq[j], (k - 1 - j) % R);
+        if (pend & (1u << j)) scatter(segq[j], keepq[j], (k - 1 - j) % R);
       break;
     }
 #pragma unroll
     for (int j = LAG - 1; j > 0; j--) { keepq[j] = keepq[j - 1]; segq[j] = segq[j - 1]; }
     keepq[0] = keepbits;
     segq[0] = seg;
-    pending += 1;
+    pend = (pend << 1) | 1u;
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }

@@ -134,3 +134,31 @@ def test_sql_front_end_survives_fuzzing_under_sanitizers(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     planned = int(r.stdout.split("planner_fuzz:")[1].split("planned")[0])
     assert planned > 500      # the generator does reach the optimizer and the pipeline builder
+
+
+def _build_abi_sequence(tmp_path):
+    import subprocess
+    exe = tmp_path / "abi_sequence"
+    pkg = os.path.join(ROOT, "fuse_query_b200")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi_sequence.c"),
+           "-L", pkg, "-l:libfuse_gpu.so", f"-Wl,-rpath,{pkg}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+
+
+def test_plain_c_program_links_the_abi_and_fails_loudly_without_a_device(tmp_path):
+    """tests/abi_sequence.c = the call sequence of the Rust safe wrapper (ffi/fuse-gpu), in C11 with gcc: the header is
+    valid C, the library links without CUDA installed on the include path, and without a device the first call says so
+    (exit 77) — there is no CPU fallback to fall into."""
+    r = _build_abi_sequence(tmp_path)
+    assert r.returncode in (0, 77), (r.returncode, r.stdout, r.stderr)
+    if r.returncode == 77:
+        assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_program_runs_the_whole_call_sequence_on_the_device(tmp_path):
+    r = _build_abi_sequence(tmp_path)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "abi sequence ok" in r.stdout
