@@ -126,7 +126,7 @@ unsafe impl Sync for GpuContext {}
 
 impl GpuContext {
     pub fn try_create(device: i32) -> FuseQueryResult<Arc<Self>> {
-        if unsafe { sys::fq_abi_version() } != sys::FQ_ABI_VERSION {
+        if unsafe { sys::fq_abi_version() } != sys::FQ_ABI_VERSION as u32 {
             return Err(FuseQueryError::Internal("libfuse_gpu.so has another ABI version than these bindings".to_string()));
         }
         let mut raw = ptr::null_mut();
