@@ -802,8 +802,11 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     wrappers.push_back({"_agg_u8", "extern \"C\" __global__ void __launch_bounds__(FQ_AGG_THREADS, FQ_AGG_MIN_BLOCKS_U8) fqk_@_agg_u8(const __grid_constant__ fq_launch_params p) { fq_agg_kernel<Q_@, 8>(p); }\n"});
   } else if (out->has_pred) {
     wrappers.push_back({"_select", "extern \"C\" __global__ void __launch_bounds__(FQ_SEL_THREADS + 32, FQ_SEL_MIN_BLOCKS) fqk_@_select(const __grid_constant__ fq_launch_params p) { fq_select_kernel<Q_@, fq_sel_shape<Q_@::V>::U, fq_sel_shape<Q_@::V>::SEG>(p); }\n"});
-    if (out->sel_tma_ok)
-      wrappers.push_back({"_select_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_SELT_THREADS + 64, 1) fqk_@_select_tma(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_selt_shape<Q_@::V>::U, fq_selt_shape<Q_@::V>::SEG, FQ_SELT_STAGES>(p); }\n"});
+    if (out->sel_tma_ok) {
+      wrappers.push_back({"_select_tma", "extern \"C\" __global__ void __launch_bounds__(FQ_SELT_THREADS + 64, 1) fqk_@_select_tma(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_selt_shape<Q_@::V>::U, fq_selt_shape<Q_@::V>::SEG, FQ_SELT_STAGES, false>(p); }\n"});
+      wrappers.push_back({"_select_dense", "extern \"C\" __global__ void __launch_bounds__(FQ_SELD_THREADS + 64, 1) fqk_@_select_dense(const __grid_constant__ fq_launch_params p) { fq_select_tma_kernel<Q_@, fq_seld_shape<Q_@::V>::U, fq_seld_shape<Q_@::V>::SEG, 16, true>(p); }\n"});
+      wrappers.push_back({"_select_probe", "extern \"C\" __global__ void __launch_bounds__(128) fqk_@_select_probe(const __grid_constant__ fq_launch_params p) { fq_select_probe_kernel<Q_@>(p); }\n"});
+    }
   } else {
     wrappers.push_back({"_map", "extern \"C\" __global__ void __launch_bounds__(FQ_MAP_THREADS, FQ_MAP_MIN_BLOCKS) fqk_@_map(const __grid_constant__ fq_launch_params p) { fq_map_kernel<Q_@, FQ_MAP_UNROLL>(p); }\n"});
     if (out->tma_ok)

@@ -142,6 +142,7 @@ struct Shapes {
   int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
   int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
   int selt_threads = FQ_SELT_THREADS, selt_unroll = FQ_SELT_UNROLL, selt_seg = FQ_SELT_SEG, selt_lag = FQ_SELT_LAG;
+  int seld_threads = FQ_SELD_THREADS, seld_unroll = FQ_SELD_UNROLL, seld_seg = FQ_SELD_SEG, seld_stages = 8;
   int selt_stages_env = 0;  // FQ_TUNE_SELT_STAGES: ring depth override (<= FQ_SELT_STAGES)
   bool tuned = false;
   Shapes() {
@@ -157,17 +158,19 @@ struct Shapes {
     env("FQ_TUNE_SEL_THREADS", &sel_threads); env("FQ_TUNE_SEL_MIN_BLOCKS", &sel_min_blocks); env("FQ_TUNE_SEL_UNROLL", &sel_unroll); env("FQ_TUNE_SEL_SEG", &sel_seg); env("FQ_TUNE_SEL_LOOK", &sel_look);
     env("FQ_TUNE_SELT_THREADS", &selt_threads); env("FQ_TUNE_SELT_UNROLL", &selt_unroll); env("FQ_TUNE_SELT_SEG", &selt_seg); env("FQ_TUNE_SELT_LAG", &selt_lag);
     if (getenv("FQ_TUNE_SELT_STAGES") && atoi(getenv("FQ_TUNE_SELT_STAGES")) > 0) selt_stages_env = atoi(getenv("FQ_TUNE_SELT_STAGES"));
+    env("FQ_TUNE_SELD_THREADS", &seld_threads); env("FQ_TUNE_SELD_UNROLL", &seld_unroll); env("FQ_TUNE_SELD_SEG", &seld_seg); env("FQ_TUNE_SELD_STAGES", &seld_stages);
     env("FQ_TUNE_MAP_THREADS", &map_threads); env("FQ_TUNE_MAP_MIN_BLOCKS", &map_min_blocks); env("FQ_TUNE_MAP_UNROLL", &map_unroll);
     if (getenv("FQ_TUNE_EXTRA")) tuned = true;
   }
   std::string defines() const {
-    char b[1536];
+    char b[2048];
     snprintf(b, sizeof b,
+             "#define FQ_SELD_THREADS %d\n#define FQ_SELD_UNROLL %d\n#define FQ_SELD_SEG %d\n#define FQ_SELD_PROBE_ROWS 512\n"
              "#define FQ_SELT_THREADS %d\n#define FQ_SELT_UNROLL %d\n#define FQ_SELT_SEG %d\n#define FQ_SELT_STAGES 8\n#define FQ_SELT_LAG %d\n"
              "#define FQ_AGG_THREADS %d\n#define FQ_AGG_MIN_BLOCKS %d\n#define FQ_AGG_MIN_BLOCKS_U8 %d\n#define FQ_TMA_THREADS %d\n"
              "#define FQ_TMA_UNROLL %d\n#define FQ_TMA_STAGES %d\n#define FQ_TMA_MIN_BLOCKS %d\n#define FQ_SEL_THREADS %d\n"
              "#define FQ_SEL_MIN_BLOCKS %d\n#define FQ_SEL_UNROLL %d\n#define FQ_SEL_SEG %d\n#define FQ_SEL_LOOK %d\n#define FQ_MAP_THREADS %d\n#define FQ_MAP_MIN_BLOCKS %d\n#define FQ_MAP_UNROLL %d\n",
-             selt_threads, selt_unroll, selt_seg, selt_lag, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
+             seld_threads, seld_unroll, seld_seg, selt_threads, selt_unroll, selt_seg, selt_lag, agg_threads, agg_min_blocks, agg_min_blocks_u8, tma_threads, tma_unroll, tma_stages, tma_min_blocks, sel_threads, sel_min_blocks, sel_unroll, sel_seg, sel_look, map_threads, map_min_blocks, map_unroll);
     std::string out = b;
     // FQ_TUNE_EXTRA: raw preprocessor text for A/B experiments, ';' separates lines ("#define FQ_STORE_CS 0;#define FQ_L2_HINTS 0")
     if (const char *x = getenv("FQ_TUNE_EXTRA")) {
@@ -236,7 +239,8 @@ struct fq_group {
 
 struct fq_pipe {
   fq::Generated gen;
-  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_map, k_map_tma, k_groupby, k_gbmerge;
+  Kernel k_agg_u4, k_agg_u8, k_agg_tma, k_select, k_select_tma, k_select_dense, k_select_probe, k_map, k_map_tma, k_groupby, k_gbmerge;
+  unsigned seld_stages = 0;
   // GROUP BY: the hash table in HBM
   uint64_t *gb_keys = nullptr, *gb_slots = nullptr;
   uint64_t gb_cap = 0;
@@ -247,7 +251,7 @@ struct fq_pipe {
   bool launched_groupby = false;
   unsigned mapt_stages = 0;
   unsigned tma_stages = 0, selt_stages = 0;
-  bool selt_stage2 = false;   // staged select kernel: pass 2 of dense segments staged as well
+
   int build_kind = 0;   // 0 precompiled, 1 NVRTC in this process, 2 on-disk JIT cache
   std::string variant;  // kernel variant the launches prefer: FQ_{AGG,SEL,MAP}_VARIANT when the pipe was compiled, or fq_pipe_set_variant
   fq_group *group = nullptr;   // aggregate launches end with the in-kernel cross-GPU merge when set
@@ -747,7 +751,10 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
                                               ? getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT") : "tma";
           if (gen.kind == FQ_PIPE_GROUPBY) { want.push_back("_groupby"); want.push_back("_gbmerge"); }
           else if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
-          else if (gen.has_pred) want.push_back(staged && variant_env == "tma" ? "_select_tma" : "_select");
+          else if (gen.has_pred) {
+            if (staged && variant_env != "ldg") { want.push_back("_select_tma"); want.push_back("_select_dense"); want.push_back("_select_probe"); }
+            else want.push_back("_select");
+          }
           else want.push_back(staged && variant_env == "tma" ? "_map_tma" : "_map");
         }
         std::lock_guard<std::mutex> lk2(g_mu);
@@ -790,19 +797,24 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       if (!s2 && gen.sel_tma_ok) {
         // staged variant: consumer warps + scan warp + producer warp; ring of ~192 KB per CTA, at least 2 tiles
         const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
-        unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
-        // pass 2 of dense segments is staged too when a slot can hold a tile of EVERY referenced column and the ring still has
-        // three of them (FQ_SELT_STAGE2=0 switches it off: pass 2 then re-reads kept rows from L2 with plain loads)
-        const unsigned all_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.row_bytes;
-        static const bool stage2_env = !(getenv("FQ_SELT_STAGE2") && atoi(getenv("FQ_SELT_STAGE2")) == 0);
-        pipe->selt_stage2 = stage2_env && 3u * all_bytes <= 200u * 1024u;
-        if (pipe->selt_stage2) tile_bytes = all_bytes;
+        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
         // ~192 KB in flight per SM measured best here (1.19 -> 1.14 ms at 1e9 rows; the aggregate kernel peaks at 128 KB)
         unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (192u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);
         if (stages * tile_bytes <= 200 * 1024) {
           s2 = resolve_kernel(m, base + "_select_tma", shapes().selt_threads + 64, &pipe->k_select_tma, stages * tile_bytes);
           pipe->selt_stages = stages;
+        }
+        // the dense-tuned build: both passes staged, so a slot holds a tile of EVERY referenced column; small tiles and a
+        // ring of ~112 KB (FQ_SELT_STAGE2=0 leaves it out: dense selections then re-read kept rows from L2 with plain loads)
+        const int ud = shapes().seld_unroll * gen.vec <= 32 ? shapes().seld_unroll : 32 / gen.vec;   // fq_seld_shape<V>::U
+        const unsigned all_bytes = (unsigned)shapes().seld_threads * ud * gen.vec * gen.row_bytes;
+        static const bool stage2_env = !(getenv("FQ_SELT_STAGE2") && atoi(getenv("FQ_SELT_STAGE2")) == 0);
+        const unsigned dstages = std::min<unsigned>(std::max<unsigned>((unsigned)shapes().seld_stages, 3), 16);
+        if (!s2 && pipe->k_select_tma.valid() && stage2_env && dstages * all_bytes <= 200u * 1024u) {
+          s2 = resolve_kernel(m, base + "_select_dense", shapes().seld_threads + 64, &pipe->k_select_dense, dstages * all_bytes);
+          if (!s2) s2 = resolve_kernel(m, base + "_select_probe", 128, &pipe->k_select_probe);
+          pipe->seld_stages = dstages;
         }
       }
     } else {
@@ -877,7 +889,8 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
 fq_status fq_pipe_set_variant(fq_ctx *, fq_pipe *pipe, const char *variant) {
   if (!pipe || !variant) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
   const std::string v = variant;
-  const bool ok = pipe->gen.kind == FQ_PIPE_AGGREGATE ? (v == "tma" || v == "u4" || v == "u8") : (v == "tma" || v == "ldg");
+  const bool ok = pipe->gen.kind == FQ_PIPE_AGGREGATE ? (v == "tma" || v == "u4" || v == "u8")
+                                                       : (v == "tma" || v == "ldg" || v == "sparse" || v == "dense");
   if (!ok) return set_err(FQ_ERR_INVALID, "Internal Error: unknown kernel variant %s", variant);
   pipe->variant = v;
   return FQ_OK;
@@ -1305,38 +1318,68 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   p.tile_counter = (fq_u32 *)(pipe->d_ctl + 2);
   p.done = (fq_u32 *)(pipe->d_ctl + 3);
   p.stop_after = ((flags & FQ_RUN_LIMIT_EARLY_EXIT) && limit > 0) ? (uint64_t)limit : 0;
-  CUDA_TRY(cudaMemsetAsync(pipe->d_ctl, 0, 48, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemsetAsync(pipe->d_ctl, 0, 64, (cudaStream_t)stream));
   pipe->skipped = false;
   pipe->project_has_pred_launch = false;
   if (src->n_rows == 0) {
     pipe->skipped = true;
   } else if (pipe->gen.has_pred) {
     // kernel variant: FQ_SEL_VARIANT = tma (default: pass 1 staged by bulk copies; needs every referenced column materialised) | ldg
+    // kernel variant: FQ_SEL_VARIANT / fq_pipe_set_variant = tma (default: staged by bulk copies; the dense-tuned build when a
+    // density probe says so) | sparse | dense (force one staged build) | ldg (worker-warp loads; generated sources)
     const std::string &variant = pipe->variant;
-    const bool use_tma = (variant == "tma" && pipe->k_select_tma.valid()) || !pipe->k_select.valid();
-    const Kernel &k = use_tma ? pipe->k_select_tma : pipe->k_select;
-    if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no select kernel was built for this pipe");
-    // work unit = segment of sel_seg tiles; p.n_tiles counts segments (one look-back descriptor each)
+    const bool staged_ok = pipe->k_select_tma.valid();
+    const bool use_tma = (variant != "ldg" && staged_ok) || !pipe->k_select.valid();
     const int vec = pipe->gen.vec;
-    const int cfg_u = use_tma ? shapes().selt_unroll : shapes().sel_unroll, cfg_seg = use_tma ? shapes().selt_seg : shapes().sel_seg;
-    const int sel_u = cfg_u * vec <= 32 ? cfg_u : 32 / vec;                        // fq_sel_shape<V>::U / fq_selt_shape<V>::U
-    const int sel_seg = cfg_seg * sel_u * vec <= 64 ? cfg_seg : 64 / (sel_u * vec);  // ...::SEG
-    const uint64_t tile_rows = (uint64_t)(k.threads - (use_tma ? 64 : 32)) * sel_u * vec * sel_seg;
-    p.stages = pipe->selt_stages;
-    p.stages2 = (use_tma && pipe->selt_stage2) ? 1u : 0u;
-    p.n_tiles = (src->n_rows + tile_rows - 1) / tile_rows;
-    if (p.n_tiles > pipe->tiles_cap) {
+    auto seg_rows = [&](int threads, int cfg_u, int cfg_seg) {
+      const int u = cfg_u * vec <= 32 ? cfg_u : 32 / vec;
+      const int seg = cfg_seg * u * vec <= 64 ? cfg_seg : 64 / (u * vec);
+      return (uint64_t)threads * u * vec * seg;
+    };
+    const uint64_t rows_sparse = use_tma ? seg_rows(shapes().selt_threads, shapes().selt_unroll, shapes().selt_seg)
+                                         : seg_rows(pipe->k_select.threads - 32, shapes().sel_unroll, shapes().sel_seg);
+    const uint64_t rows_dense = seg_rows(shapes().seld_threads, shapes().seld_unroll, shapes().seld_seg);
+    // the dense-tuned build pays off when a good part of the rows is written: outputs of at least 1/16 of a large source
+    const bool dense_ok = use_tma && pipe->k_select_dense.valid() && pipe->k_select_probe.valid() && !p.unaligned;
+    const bool force_dense = dense_ok && variant == "dense";
+    const bool probe = dense_ok && variant == "tma" && src->n_rows >= (4u << 20) && cap >= src->n_rows / 16 && p.stop_after == 0;
+    const uint64_t segs_sparse = (src->n_rows + rows_sparse - 1) / rows_sparse, segs_dense = (src->n_rows + rows_dense - 1) / rows_dense;
+    const uint64_t segs_max = (probe || force_dense) ? std::max(segs_sparse, segs_dense) : segs_sparse;
+    if (segs_max > pipe->tiles_cap) {
       cudaFree(pipe->d_tiles);
       pipe->d_tiles = nullptr;
-      CUDA_TRY(cudaMalloc(&pipe->d_tiles, sizeof(uint64_t) * p.n_tiles));
-      pipe->tiles_cap = p.n_tiles;
+      CUDA_TRY(cudaMalloc(&pipe->d_tiles, sizeof(uint64_t) * segs_max));
+      pipe->tiles_cap = segs_max;
     }
     p.tile_status = (fq_u64 *)pipe->d_tiles;
-    CUDA_TRY(cudaMemsetAsync(pipe->d_tiles, 0, sizeof(uint64_t) * p.n_tiles, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(pipe->d_tiles, 0, sizeof(uint64_t) * segs_max, (cudaStream_t)stream));
     static const int sel_bps_env = getenv("FQ_SEL_BLOCKS_PER_SM") ? atoi(getenv("FQ_SEL_BLOCKS_PER_SM")) : 0;
-    const int sel_bps = (sel_bps_env > 0 && !use_tma) ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
-    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, p.n_tiles));
-    if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+    fq_u32 *probe_words = (fq_u32 *)(pipe->d_ctl + 6);   // [0] sampled, [1] kept, [2] mode, [3] CTA ticket
+    if (probe) {
+      fq_launch_params pp = p;
+      pp.probe = probe_words;
+      if (fq_status st = launch(ctx, pipe->k_select_probe, (unsigned)ctx->sm_count, pp, stream)) return st;
+      p.sel_mode = probe_words + 2;
+    }
+    if (!force_dense) {   // the sparse-tuned build (or the LDG kernel)
+      const Kernel &k = use_tma ? pipe->k_select_tma : pipe->k_select;
+      if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no select kernel was built for this pipe");
+      fq_launch_params ps = p;
+      ps.stages = pipe->selt_stages;
+      ps.stages2 = 0;
+      ps.n_tiles = segs_sparse;
+      const int sel_bps = (sel_bps_env > 0 && !use_tma) ? std::min(sel_bps_env, k.blocks_per_sm) : k.blocks_per_sm;
+      const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * sel_bps, ps.n_tiles));
+      if (fq_status st = launch(ctx, k, grid, ps, stream)) return st;
+    }
+    if (probe || force_dense) {   // the dense-tuned build: returns at once when the probe chose the other one
+      fq_launch_params pd = p;
+      pd.stages = pipe->seld_stages;
+      pd.stages2 = 1;
+      pd.n_tiles = segs_dense;
+      const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, pd.n_tiles));
+      if (fq_status st = launch(ctx, pipe->k_select_dense, grid, pd, stream)) return st;
+    }
     pipe->project_has_pred_launch = true;
   } else {
     // LIMIT without a filter: rows past the 10 000-row block that completes the limit are neither read nor evaluated.

@@ -58,12 +58,21 @@ typedef signed char fq_i8;
 #define FQ_GB_SMEM_PROBES 4  // linear probes in the CTA's shared-memory table before a row goes to the table in HBM
 #endif
 #ifndef FQ_SELT_THREADS
-#define FQ_SELT_THREADS 448  // staged select kernel: consumer threads (+32 scan warp, +32 producer warp) = 16 warps, 4 per SM
-                             // sub-partition: 128 registers per thread (18 warps put 5 on one sub-partition: 96, and spills)
-#define FQ_SELT_UNROLL 4     // tile = 448 * 4 vector groups = 28 KB of a UInt64 column per bulk copy
+#define FQ_SELT_THREADS 512  // staged select kernel, sparse-tuned build: consumer threads (+32 scan warp, +32 producer warp)
+#define FQ_SELT_UNROLL 4     // tile = 512 * 4 vector groups = 32 KB of a UInt64 column per bulk copy
 #define FQ_SELT_SEG 8        // tiles per segment (one look-back each): 256 KB of a UInt64 column
 #define FQ_SELT_STAGES 8     // upper bound of the ring; the host picks the depth (~192 KB in flight per SM)
-#define FQ_SELT_LAG 3        // pass 2 runs this many segments behind pass 1
+#define FQ_SELT_LAG 3        // pass 2 of SPARSE segments runs this many segments behind pass 1 (dense ones: 1)
+#endif
+// The dense-tuned build of the staged select kernel (fqk_*_select_dense): both passes through the ring, smaller tiles and
+// segments so that what lies between a tile's two reads (one segment + the read-ahead, times 148 SMs) stays near 35 MB and
+// the second read hits L2 (measured with ncu on 1e9 rows, every row kept: 14.2 GB from HBM for the 8 GB column with 28-KB
+// tiles x 8, 8.2 GB with 14-KB tiles x 8).  The sparse-tuned build (fqk_*_select_tma) has no staged pass 2 compiled in.
+#ifndef FQ_SELD_THREADS
+#define FQ_SELD_THREADS 448  // + scan warp + producer warp = 16 warps: 128 registers per thread
+#define FQ_SELD_UNROLL 2     // tile = 448 * 2 vector groups = 14 KB of a UInt64 column
+#define FQ_SELD_SEG 8        // 112-KB segments
+#define FQ_SELD_PROBE_ROWS 512   // rows per CTA of the density probe
 #endif
 
 #define FQ_STATE_HDR 6        // state / partial slots: [0] rows selected, [1] error bits, [2] launches folded, [3] rows scanned,
@@ -85,6 +94,8 @@ struct fq_launch_params {
   fq_u32 *block_hit;     // one bit per reference block of this launch (zeroed before it), or null: block tracking off
   fq_u32 stages;         // bulk-copy staged kernel: ring depth actually used (<= its STAGES template bound)
   fq_u32 stages2;        // staged select kernel: != 0 when pass 2 of dense segments is staged too (slots hold every referenced column)
+  const fq_u32 *sel_mode; // null, or which build of the staged select kernel runs: 0 sparse-tuned, 1 dense-tuned (written by the probe)
+  fq_u32 *probe;          // density probe: [0] rows sampled, [1] rows kept, [2] = the mode it decided
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
   // multi-GPU merge point fused into the aggregate kernel (fq_group, include/fuse_gpu.h): after the fold the last CTA
   // stores the running state into its row of EVERY rank's exchange window (peer GPUs' memory over NVLink), waits until
@@ -1368,11 +1379,53 @@ template <int V> struct fq_selt_shape {
   static constexpr int U = (FQ_SELT_UNROLL * V <= 32) ? FQ_SELT_UNROLL : (32 / V);
   static constexpr int SEG = (FQ_SELT_SEG * U * V <= 64) ? FQ_SELT_SEG : (64 / (U * V));
 };
+template <int V> struct fq_seld_shape {
+  static constexpr int U = (FQ_SELD_UNROLL * V <= 32) ? FQ_SELD_UNROLL : (32 / V);
+  static constexpr int SEG = (FQ_SELD_SEG * U * V <= 64) ? FQ_SELD_SEG : (64 / (U * V));
+};
+// Density probe: every CTA evaluates the predicate over FQ_SELD_PROBE_ROWS rows at an evenly spaced position of the source;
+// the last CTA decides the build (dense when at least 1/16 of the sampled rows are kept) — on the device, so that no host
+// round trip sits between the probe and the two launches that follow it (the build that is not chosen returns at once).
+template <class Q>
+__device__ __forceinline__ void fq_select_probe_kernel(const fq_launch_params &p) {
+  constexpr int V = Q::V;
+  __shared__ fq_u32 s_kept;
+  if (threadIdx.x == 0) s_kept = 0;
+  __syncthreads();
+  const fq_u64 groups_total = p.n_rows / V;
+  const fq_u64 per_cta = FQ_SELD_PROBE_ROWS / V;
+  fq_u32 err = 0, kept = 0, sampled = 0;
+  if (groups_total >= per_cta * gridDim.x && !p.unaligned) {
+    const fq_u64 g0 = (groups_total / gridDim.x) * blockIdx.x;
+    for (fq_u64 g = threadIdx.x; g < per_cta; g += blockDim.x) {
+      typename Q::Rows r;
+      Q::load_pred(r, p, g0 + g);
+#pragma unroll
+      for (int v = 0; v < V; v++) kept += Q::pred(r, v, err) ? 1u : 0u;
+      sampled += V;
+    }
+  }
+  kept = __reduce_add_sync(0xffffffffu, kept);
+  sampled = __reduce_add_sync(0xffffffffu, sampled);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(p.probe, sampled);
+    atomicAdd(p.probe + 1, kept);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(p.probe + 3, 1u) == gridDim.x - 1) {
+    __threadfence();
+    const fq_u32 n = *(volatile fq_u32 *)p.probe, k = *(volatile fq_u32 *)(p.probe + 1);
+    p.probe[2] = (n > 0 && (fq_u64)k * 16 >= n) ? 1u : 0u;
+  }
+}
 #define FQ_SELT_CLAIMS 16   // claim ring: the producer runs at most stages/SEG + 1 segments ahead of pass 1, the scan warp 2 behind
 
-template <class Q, int U, int SEG, int STAGES>
+template <class Q, int U, int SEG, int STAGES, bool STAGE2>
 __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
+  // two builds share the launch parameters; the density probe (or the host) says which one runs this launch
+  if (p.sel_mode && *(volatile const fq_u32 *)p.sel_mode != (STAGE2 ? 1u : 0u)) return;
   constexpr int BITS = U * V;
   static_assert(BITS <= 32 && BITS * SEG <= 64, "one keep bit per row must fit two registers");
   constexpr int LAG = FQ_SELT_LAG;            // pass 2 runs this many segments behind pass 1 (absorbs the skew between CTAs)
@@ -1397,7 +1450,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const bool is_producer = (int)threadIdx.x >= cthreads + 32;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const bool stage2 = p.stages2 != 0;
+  const bool stage2 = STAGE2 && p.stages2 != 0;
   // one slot holds a pass-1 tile (the predicate's columns) or, with the staged pass 2, a tile of every referenced column
   const fq_u32 pred_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES, all_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
   const fq_u32 stage_bytes = stage2 ? all_bytes : pred_bytes;

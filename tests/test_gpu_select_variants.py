@@ -24,7 +24,7 @@ def all_jit_variants():
     os.environ.pop("FQ_JIT_ALL_VARIANTS", None)
 
 
-@pytest.fixture(params=["ldg", "tma"])
+@pytest.fixture(params=["ldg", "tma", "dense"])
 def variant(request):
     old = os.environ.get("FQ_SEL_VARIANT")
     os.environ["FQ_SEL_VARIANT"] = request.param     # read by the library at every launch
