@@ -79,6 +79,7 @@ EXPORTS = [
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project", "fq_pipe_fetch_limit_row",
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
+    "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
 ]
 
 _lib = None
@@ -152,6 +153,12 @@ def lib():
         "fq_pipe_group_entry_slots": (i32, [vp, vp, C.POINTER(i32)]),
         "fq_pipe_export_partials": (i32, [vp, vp, i32, vp, C.POINTER(u64), vp]),
         "fq_pipe_merge_partials": (i32, [vp, vp, vp, u64, u32, vp]),
+        "fq_utf8_create": (i32, [vp, vp, vp, u64, vp, vp, C.POINTER(vp)]),
+        "fq_utf8_free": (None, [vp, vp]),
+        "fq_utf8_len": (u64, [vp]),
+        "fq_utf8_compare": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        "fq_utf8_compare_scalar": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
+        "fq_utf8_minmax": (i32, [vp, i32, vp, C.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -327,6 +334,25 @@ class Context:
     def synchronize(self, stream: int = 0):
         self.check(lib().fq_stream_synchronize(self._h, C.c_void_p(stream)))
 
+    # ---- Utf8 arrays ----
+    def utf8(self, values: Sequence[Optional[str]], stream: int = 0) -> "Utf8Array":
+        """Arrow string array on the device from python strings (None = NULL)."""
+        import numpy as np
+        raw = [b"" if v is None else v.encode() for v in values]
+        offsets = np.zeros(len(raw) + 1, dtype=np.int32)
+        if raw:
+            offsets[1:] = np.cumsum([len(b) for b in raw])
+        data = b"".join(raw)
+        valid = None
+        if any(v is None for v in values):
+            valid = self.from_numpy(np.array([v is not None for v in values], dtype=np.uint8).view(np.uint8))
+            valid = self.from_numpy(np.array([0 if v is None else 1 for v in values], dtype=np.uint8))
+        h = C.c_void_p()
+        buf = C.create_string_buffer(data, max(1, len(data)))
+        self.check(lib().fq_utf8_create(self._h, C.c_void_p(offsets.ctypes.data), buf, len(raw), valid._h if valid is not None else None,
+                                        C.c_void_p(stream), C.byref(h)))
+        return Utf8Array(self, h, valid)
+
     # ---- pipes ----
     def pipe(self, exprs: Sequence[str], *, columns: Sequence[str] = ("number",), dtypes: Sequence[int] = (U64,),
              predicate: Optional[str] = None, aggregate: bool = False, generated: bool = False,
@@ -415,6 +441,46 @@ class Column:
             self.ctx.check(lib().fq_column_download(self.ctx._h, self._h, 0, C.c_void_p(out.ctypes.data), n, C.c_void_p(stream)))
             self.ctx.synchronize(stream)
         return out
+
+
+class Utf8Array:
+    """fq_utf8: Arrow string layout on the device (offsets + bytes, optional validity)."""
+
+    def __init__(self, ctx: Context, h, valid: Optional[Column]):
+        self.ctx, self._h, self._valid = ctx, h, valid
+
+    def __len__(self) -> int:
+        return lib().fq_utf8_len(self._h)
+
+    def compare(self, op: str, other, stream: int = 0):
+        """-> list of bool / None per row; `other` is another Utf8Array or a python string (array (op) scalar)"""
+        n = len(self)
+        out = self.ctx.column(BOOL, max(1, n))
+        nullable = self._valid is not None or (isinstance(other, Utf8Array) and other._valid is not None)
+        out_valid = self.ctx.column(BOOL, max(1, n)) if nullable else None
+        ov = out_valid._h if out_valid is not None else None
+        if isinstance(other, Utf8Array):
+            self.ctx.check(lib().fq_utf8_compare(self.ctx._h, CMP[op], self._h, other._h, out._h, ov, C.c_void_p(stream)))
+        else:
+            b = other.encode()
+            self.ctx.check(lib().fq_utf8_compare_scalar(self.ctx._h, CMP[op], self._h, C.create_string_buffer(b, max(1, len(b))), len(b), out._h, ov,
+                                                         C.c_void_p(stream)))
+        vals = [bool(x) for x in out.to_numpy(n, stream)]
+        if out_valid is not None:
+            ok = out_valid.to_numpy(n, stream)
+            vals = [v if f else None for v, f in zip(vals, ok)]
+        return vals
+
+    def minmax(self, op: str, stream: int = 0) -> int:
+        """row index of the min / max valid string (first occurrence), -1 when there is none"""
+        row = C.c_int64()
+        self.ctx.check(lib().fq_utf8_minmax(self.ctx._h, AGG[op], self._h, C.byref(row), C.c_void_p(stream)))
+        return row.value
+
+    def free(self):
+        if self._h:
+            lib().fq_utf8_free(self.ctx._h, self._h)
+            self._h = None
 
 
 class Group:

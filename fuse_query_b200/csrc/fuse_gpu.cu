@@ -142,7 +142,7 @@ struct Shapes {
   int sel_threads = FQ_SEL_THREADS, sel_min_blocks = FQ_SEL_MIN_BLOCKS, sel_unroll = FQ_SEL_UNROLL, sel_seg = FQ_SEL_SEG, sel_look = FQ_SEL_LOOK;
   int map_threads = FQ_MAP_THREADS, map_min_blocks = FQ_MAP_MIN_BLOCKS, map_unroll = FQ_MAP_UNROLL;
   int selt_threads = FQ_SELT_THREADS, selt_unroll = FQ_SELT_UNROLL, selt_seg = FQ_SELT_SEG, selt_lag = FQ_SELT_LAG;
-  int seld_threads = FQ_SELD_THREADS, seld_unroll = FQ_SELD_UNROLL, seld_seg = FQ_SELD_SEG, seld_stages = 8;
+  int seld_threads = FQ_SELD_THREADS, seld_unroll = FQ_SELD_UNROLL, seld_seg = FQ_SELD_SEG, seld_stages = 12;   // 12 x 14 KB in flight: 4.04 ms for a selection that keeps all of 1e9 rows (8 stages: 4.33)
   int selt_stages_env = 0;  // FQ_TUNE_SELT_STAGES: ring depth override (<= FQ_SELT_STAGES)
   bool tuned = false;
   Shapes() {
@@ -1787,6 +1787,184 @@ fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *en
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }
   return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Utf8 arrays
+// =============================================================================================
+struct fq_utf8 {
+  uint64_t len = 0;
+  int32_t *offsets = nullptr;   // device, len + 1
+  unsigned char *data = nullptr;
+  const fq_column *validity = nullptr;
+};
+
+namespace {
+// bytewise order, shorter string first on a common prefix (Rust str / arrow)
+__device__ __forceinline__ int fq_utf8_cmp(const unsigned char *a, fq_u32 la, const unsigned char *b, fq_u32 lb) {
+  const fq_u32 n = la < lb ? la : lb;
+  for (fq_u32 i = 0; i < n; i++) {
+    const int d = (int)a[i] - (int)b[i];
+    if (d) return d;
+  }
+  return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+__device__ __forceinline__ bool fq_cmp_holds(int op, int c) {
+  switch (op) {
+    case FQ_CMP_EQ: return c == 0;
+    case FQ_CMP_LT: return c < 0;
+    case FQ_CMP_LTEQ: return c <= 0;
+    case FQ_CMP_GT: return c > 0;
+    default: return c >= 0;
+  }
+}
+__global__ void __launch_bounds__(256) fq_utf8_compare_kernel(int op, const int32_t *lo, const unsigned char *ld, const fq_u8 *lv, const int32_t *ro,
+                                                             const unsigned char *rd, const fq_u8 *rv, fq_u32 scalar_len, fq_u64 n, fq_u8 *out,
+                                                             fq_u8 *out_valid) {
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (fq_u64)gridDim.x * blockDim.x) {
+    const unsigned char *a = ld + lo[i];
+    const fq_u32 la = (fq_u32)(lo[i + 1] - lo[i]);
+    const unsigned char *b = ro ? rd + ro[i] : rd;       // ro == null: the right side is one scalar
+    const fq_u32 lb = ro ? (fq_u32)(ro[i + 1] - ro[i]) : scalar_len;
+    const bool ok = (!lv || lv[i]) && (!rv || rv[i]);
+    out[i] = (ok && fq_cmp_holds(op, fq_utf8_cmp(a, la, b, lb))) ? 1 : 0;
+    if (out_valid) out_valid[i] = ok ? 1 : 0;
+  }
+}
+// better(i, j): does row i beat row j for op?  ties keep the smaller row index (first occurrence)
+__device__ __forceinline__ long long fq_utf8_pick(int op, const int32_t *o, const unsigned char *d, long long i, long long j) {
+  if (i < 0) return j;
+  if (j < 0) return i;
+  const int c = fq_utf8_cmp(d + o[i], (fq_u32)(o[i + 1] - o[i]), d + o[j], (fq_u32)(o[j + 1] - o[j]));
+  const bool i_wins = op == FQ_AGG_MIN ? (c < 0 || (c == 0 && i < j)) : (c > 0 || (c == 0 && i < j));
+  return i_wins ? i : j;
+}
+__global__ void __launch_bounds__(256) fq_utf8_minmax_kernel(int op, const int32_t *o, const unsigned char *d, const fq_u8 *valid, fq_u64 n,
+                                                            long long *partials, fq_u32 *ticket, long long *result) {
+  __shared__ long long s_best[256];
+  __shared__ fq_u32 s_last;
+  long long best = -1;
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (fq_u64)gridDim.x * blockDim.x)
+    if (!valid || valid[i]) best = fq_utf8_pick(op, o, d, best, (long long)i);
+  s_best[threadIdx.x] = best;
+  __syncthreads();
+  for (int m = 128; m > 0; m >>= 1) {
+    if ((int)threadIdx.x < m) s_best[threadIdx.x] = fq_utf8_pick(op, o, d, s_best[threadIdx.x], s_best[threadIdx.x + m]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = s_best[0];
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  best = -1;
+  for (fq_u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) best = fq_utf8_pick(op, o, d, best, *(volatile long long *)(partials + b));
+  s_best[threadIdx.x] = best;
+  __syncthreads();
+  for (int m = 128; m > 0; m >>= 1) {
+    if ((int)threadIdx.x < m) s_best[threadIdx.x] = fq_utf8_pick(op, o, d, s_best[threadIdx.x], s_best[threadIdx.x + m]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *result = s_best[0]; *ticket = 0; }
+}
+}  // namespace
+
+extern "C" {
+
+fq_status fq_utf8_create(fq_ctx *ctx, const int32_t *offsets, const void *data, uint64_t len, const fq_column *validity, void *stream,
+                         fq_utf8 **out) {
+  if (fq_status st = use(ctx)) return st;
+  if (!out || (len && !offsets)) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  *out = nullptr;
+  const uint64_t bytes = len ? (uint64_t)offsets[len] - (uint64_t)offsets[0] : 0;
+  if (len && (offsets[0] != 0 || offsets[len] < 0)) return set_err(FQ_ERR_INVALID, "Internal Error: Utf8 offsets must start at 0 and stay within int32");
+  if (validity && (validity->dtype != FQ_BOOL || validity->len < len)) return set_err(FQ_ERR_INVALID, "Internal Error: validity must be a Boolean column as long as the array");
+  if (bytes && !data) return set_err(FQ_ERR_INVALID, "Internal Error: null value buffer");
+  fq_utf8 *a = new fq_utf8();
+  a->len = len;
+  a->validity = validity;
+  cudaError_t e = cudaMalloc(&a->offsets, sizeof(int32_t) * (len + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&a->data, bytes ? bytes : 1);
+  static const int32_t zero = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(a->offsets, len ? offsets : &zero, sizeof(int32_t) * (len + 1), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(a->data, data, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // the host buffers may go away after the call
+  if (e != cudaSuccess) {
+    fq_utf8_free(ctx, a);
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (Utf8 array of %" PRIu64 " rows)", cudaGetErrorString(e), len);
+  }
+  *out = a;
+  return FQ_OK;
+}
+void fq_utf8_free(fq_ctx *ctx, fq_utf8 *a) {
+  if (!a) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(a->offsets);
+  cudaFree(a->data);
+  delete a;
+}
+uint64_t fq_utf8_len(const fq_utf8 *a) { return a ? a->len : 0; }
+
+static fq_status utf8_compare(fq_ctx *ctx, int32_t op, const fq_utf8 *l, const fq_utf8 *r, const unsigned char *scalar_dev, uint32_t scalar_len,
+                              fq_column *out, fq_column *out_valid, void *stream) {
+  if (op < FQ_CMP_EQ || op > FQ_CMP_GTEQ) return set_err(FQ_ERR_INVALID, "Internal Error: operator code %d out of range", op);
+  if (!l || !out || out->dtype != FQ_BOOL || out->len < l->len) return set_err(FQ_ERR_INVALID, "Internal Error: a Boolean output column as long as the arrays is required");
+  if (r && r->len != l->len) return set_err(FQ_ERR_INTERNAL, "Internal Error: Compute error: Cannot perform comparison operation on arrays of different length");
+  const bool nullable = l->validity || (r && r->validity);
+  if (nullable && (!out_valid || out_valid->dtype != FQ_BOOL || out_valid->len < l->len))
+    return set_err(FQ_ERR_INVALID, "Internal Error: the operands carry validity: a Boolean validity output column is required");
+  if (l->len == 0) return FQ_OK;
+  const unsigned grid = (unsigned)std::min<uint64_t>((l->len + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_utf8_compare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(op, l->offsets, l->data, l->validity ? (const fq_u8 *)l->validity->ptr : nullptr,
+                                                               r ? r->offsets : nullptr, r ? r->data : scalar_dev,
+                                                               r && r->validity ? (const fq_u8 *)r->validity->ptr : nullptr, scalar_len, l->len,
+                                                               (fq_u8 *)out->ptr, out_valid ? (fq_u8 *)out_valid->ptr : nullptr);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return FQ_OK;
+}
+fq_status fq_utf8_compare(fq_ctx *ctx, int32_t op, const fq_utf8 *l, const fq_utf8 *r, fq_column *out, fq_column *out_valid, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!r) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  return utf8_compare(ctx, op, l, r, nullptr, 0, out, out_valid, stream);
+}
+fq_status fq_utf8_compare_scalar(fq_ctx *ctx, int32_t op, const fq_utf8 *l, const void *scalar, uint64_t scalar_len, fq_column *out,
+                                 fq_column *out_valid, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (scalar_len && !scalar) return set_err(FQ_ERR_INVALID, "Internal Error: null scalar");
+  unsigned char *dev = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&dev, scalar_len ? scalar_len : 1, (cudaStream_t)stream));
+  if (scalar_len) CUDA_TRY(cudaMemcpyAsync(dev, scalar, scalar_len, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  const fq_status st = utf8_compare(ctx, op, l, nullptr, dev, (uint32_t)scalar_len, out, out_valid, stream);
+  cudaFreeAsync(dev, (cudaStream_t)stream);
+  if (st == FQ_OK) CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // `scalar` may go away after the call
+  return st;
+}
+fq_status fq_utf8_minmax(fq_ctx *ctx, int32_t op, const fq_utf8 *a, int64_t *row, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!a || !row || (op != FQ_AGG_MIN && op != FQ_AGG_MAX)) return set_err(FQ_ERR_INVALID, "Internal Error: Min or Max over a Utf8 array");
+  *row = -1;
+  if (a->len == 0) return FQ_OK;
+  const unsigned grid = (unsigned)std::min<uint64_t>((a->len + 255) / 256, (uint64_t)ctx->sm_count * 4);
+  long long *scratch = nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMallocAsync((void **)&scratch, sizeof(long long) * (grid + 2), s));
+  CUDA_TRY(cudaMemsetAsync(scratch + grid, 0, sizeof(long long) * 2, s));
+  fq_utf8_minmax_kernel<<<grid, 256, 0, s>>>(op, a->offsets, a->data, a->validity ? (const fq_u8 *)a->validity->ptr : nullptr, a->len, scratch,
+                                            (fq_u32 *)(scratch + grid), scratch + grid + 1);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  long long h = -1;
+  CUDA_TRY(cudaMemcpyAsync(&h, scratch + grid + 1, sizeof h, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  cudaFreeAsync(scratch, s);
+  *row = h;
+  return FQ_OK;
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 // `Aggregator(arg)` into one single-pass reduction kernel.  State plumbing (accumulate_result /
 // merge_state / merge_result, depth indexing) is host logic restated 1:1.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 #include "host_internal.h"
@@ -308,6 +309,21 @@ DataColumnarValue Function::eval(GpuContextRef ctx, const DataBlock &block) {
       if (!block.generated) return DataColumnarValue::Array(block.column_by_name(name));  // function_field.rs:43-47
       [[fallthrough]];
     default: {
+      if (kind == Comparison && !block.generated) {
+        // string comparisons go to the *_utf8 kernels (datavalues/macros.rs:29-36, 102-113): operands are a Utf8 column or literal
+        auto is_utf8 = [&](const Function &f) {
+          const Function *g = &f;
+          while (g->kind == Alias) g = g->left.get();
+          if (g->kind == Constant) return g->value.tag == FQ_UTF8;
+          if (g->kind == Variable) {
+            const int i = block.schema()->index_of(g->name);
+            return block.column((size_t)i)->is_utf8();
+          }
+          return false;
+        };
+        if (is_utf8(*left) || is_utf8(*right))
+          return DataColumnarValue::Array(data_array_comparison_op(ctx, op, left->eval(ctx, block), right->eval(ctx, block)));
+      }
       ProjectResult r = run_project(ctx, block, nullptr, {this}, -1, false);
       return DataColumnarValue::Array(r.columns[0]);
     }
@@ -421,8 +437,52 @@ static DataArrayRef binary_array_op(GpuContextRef ctx, Function::Kind kind, int 
 DataArrayRef data_array_arithmetic_op(GpuContextRef ctx, int op, const DataColumnarValue &l, const DataColumnarValue &r) {
   return binary_array_op(std::move(ctx), Function::Arithmetic, op, l, r);
 }
+// A Utf8 DataArray keeps its strings on the host; for a kernel it is packed into Arrow's offsets + bytes and uploaded.
+namespace {
+struct DeviceUtf8 {
+  GpuContextRef ctx;
+  fq_utf8 *raw = nullptr;
+  DeviceUtf8(GpuContextRef c, const DataArray &a) : ctx(std::move(c)) {
+    const auto &strs = a.strings();
+    std::vector<int32_t> offsets(strs.size() + 1, 0);
+    std::string data;
+    for (size_t i = 0; i < strs.size(); i++) {
+      data += strs[i];
+      if (data.size() > (size_t)INT32_MAX) throw FuseQueryError::internal("Utf8 array exceeds 2 GiB of values");
+      offsets[i + 1] = (int32_t)data.size();
+    }
+    ctx->check(fq_utf8_create(ctx->raw(), offsets.data(), data.data(), strs.size(), nullptr, ctx->stream, &raw));
+  }
+  ~DeviceUtf8() { fq_utf8_free(ctx->raw(), raw); }
+  DeviceUtf8(const DeviceUtf8 &) = delete;
+  DeviceUtf8 &operator=(const DeviceUtf8 &) = delete;
+};
+}  // namespace
+
 DataArrayRef data_array_comparison_op(GpuContextRef ctx, int op, const DataColumnarValue &l, const DataColumnarValue &r) {
-  return binary_array_op(std::move(ctx), Function::Comparison, op, l, r);
+  const bool l8 = l.data_type() == FQ_UTF8, r8 = r.data_type() == FQ_UTF8;
+  if (!l8 && !r8) return binary_array_op(std::move(ctx), Function::Comparison, op, l, r);
+  // data_array_comparison.rs:14-94 with a Utf8 side: equal_coercion only accepts Utf8 (op) Utf8
+  static const char *sym[] = {"=", "<", "<=", ">", ">="};
+  if (!(l8 && r8)) numerical_coercion(sym[op % 5], l.data_type(), r.data_type());   // throws "Unsupported (..) = (..)"
+  if (l.is_scalar && r.is_scalar)   // :87-92
+    throw FuseQueryError::internal(std::string("Cannot do data_array ") + sym[op % 5] + ", left:Utf8, right:Utf8");
+  static const int flipped[] = {FQ_CMP_EQ, FQ_CMP_GT, FQ_CMP_GTEQ, FQ_CMP_LT, FQ_CMP_LTEQ};   // scalar (op) array = array (flipped op) scalar, :75-85
+  const DataArrayRef &arr = l.is_scalar ? r.array : l.array;
+  DataArrayRef out = DataArray::alloc(ctx, FQ_BOOL, arr->len());
+  DeviceUtf8 a(ctx, *arr);
+  if (l.is_scalar || r.is_scalar) {
+    const DataValue &sc = l.is_scalar ? l.scalar : r.scalar;
+    if (!sc.some) throw FuseQueryError::internal("DataValue to array cannot be NONE " + sc.to_string());
+    ctx->check(fq_utf8_compare_scalar(ctx->raw(), l.is_scalar ? flipped[op % 5] : op, a.raw, sc.s.data(), sc.s.size(), out->column(), nullptr, ctx->stream));
+  } else {
+    if (l.array->len() != r.array->len())
+      throw FuseQueryError::internal("Compute error: Cannot perform comparison operation on arrays of different length");
+    DeviceUtf8 b(ctx, *r.array);
+    ctx->check(fq_utf8_compare(ctx->raw(), op, a.raw, b.raw, out->column(), nullptr, ctx->stream));
+    ctx->check(fq_stream_synchronize(ctx->raw(), ctx->stream));
+  }
+  return out;
 }
 DataArrayRef data_array_logic_op(GpuContextRef ctx, int op, const DataColumnarValue &l, const DataColumnarValue &r) {
   return binary_array_op(std::move(ctx), Function::Logic, op, l, r);
@@ -432,6 +492,13 @@ DataValue data_array_aggregate_op(GpuContextRef ctx, int op, const DataArrayRef 
   schema->fields.push_back({"a", a->data_type(), false});
   DataBlock block(schema, {a});
   if (op == FQ_AGG_COUNT) return DataValue::UInt64(a->len());  // data_array_aggregate.rs:113
+  if (a->is_utf8()) {   // min_string / max_string, data_array_aggregate.rs:139-154 (macros.rs:162)
+    if (op == FQ_AGG_SUM) throw FuseQueryError::internal("Unsupported data_array_sum for data type: Utf8");
+    DeviceUtf8 d(ctx, *a);
+    int64_t row = -1;
+    ctx->check(fq_utf8_minmax(ctx->raw(), op, d.raw, &row, ctx->stream));
+    return row < 0 ? DataValue::None(FQ_UTF8) : DataValue::String(a->strings()[(size_t)row]);
+  }
   auto f = Function::AggregatorFunction(op, {Function::FieldFunction("a")});
   if (a->len() == 0) return DataValue::None(a->data_type());
   f->accumulate(ctx, block);

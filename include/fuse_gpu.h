@@ -152,6 +152,29 @@ fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out);
 void fq_host_free(fq_ctx *ctx, void *p);
 
 /* ---------------------------------------------------------------------------------------------
+ * Utf8 arrays — Arrow string layout on the device: int32 offsets[len + 1] + the value bytes (+ an optional validity column,
+ * one byte per row).  What the reference does with strings on this path: the *_utf8 comparison kernels for array (op) array
+ * and array (op) scalar (datavalues/macros.rs:29-36, 102-113 <- data_array_comparison.rs:29-85), min_string / max_string
+ * (macros.rs:162 <- data_array_aggregate.rs:139-154) and count.  Strings compare bytewise (Rust `str` ordering, which
+ * arrow's comparison kernels use).  Results are ordinary Boolean columns, so they feed filters like any predicate.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fq_utf8 fq_utf8;
+/* copies offsets (len + 1 entries, host) and the value bytes (offsets[len] bytes, host) to the device; `validity` (FQ_BOOL,
+ * borrowed, may be NULL) marks NULL slots */
+fq_status fq_utf8_create(fq_ctx *ctx, const int32_t *offsets, const void *data, uint64_t len, const fq_column *validity, void *stream,
+                         fq_utf8 **out);
+void fq_utf8_free(fq_ctx *ctx, fq_utf8 *a);
+uint64_t fq_utf8_len(const fq_utf8 *a);
+/* out[row] = l[row] op r[row] (op in FQ_CMP_*), out_valid[row] = both valid; out_valid may be NULL when neither side
+ * carries validity.  Arrays must have the same length. */
+fq_status fq_utf8_compare(fq_ctx *ctx, int32_t op, const fq_utf8 *l, const fq_utf8 *r, fq_column *out, fq_column *out_valid, void *stream);
+fq_status fq_utf8_compare_scalar(fq_ctx *ctx, int32_t op, const fq_utf8 *l, const void *scalar, uint64_t scalar_len, fq_column *out,
+                                 fq_column *out_valid, void *stream);
+/* row index of the smallest (FQ_AGG_MIN) / largest (FQ_AGG_MAX) valid string, first occurrence; -1 when there is none
+ * (arrow min_string / max_string return None).  Waits for the result. */
+fq_status fq_utf8_minmax(fq_ctx *ctx, int32_t op, const fq_utf8 *a, int64_t *row, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Source — system.numbers_mt shards.  Replaces NumbersStream::poll_next materialising 10 000-row
  * UInt64Arrays (datasources/system/numbers_stream.rs:68-83): one fill kernel writes the whole
  * shard [begin, end] (inclusive, like the partition names of numbers_table.rs:29-55) into HBM.
