@@ -290,6 +290,8 @@ class Rig:
         self.dev = f"cuda:{self.local}"
         self.affinity = bind_to_gpu_cpus(self.local)
         if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self.ctx = cabi.Context(self.local)
         self.stream = torch.cuda.current_stream().cuda_stream

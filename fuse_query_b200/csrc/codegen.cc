@@ -675,9 +675,13 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
           stmt = is_f(k) ? fmt("atomicAdd((double *)(slots + %d), __longlong_as_double((fq_i64)%s));", 1 + k, x.c_str())
                          : fmt("atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)%s);", 1 + k, x.c_str());
         } else {
+          // after the first rows of a group a new minimum / maximum is rare: look before paying for the atomic
           const char *f = op == FQ_AGG_MIN ? "atomicMin" : "atomicMax";
-          stmt = is_s(k) ? fmt("%s((long long *)(slots + %d), (long long)%s);", f, 1 + k, x.c_str())
-                         : fmt("%s((unsigned long long *)(slots + %d), (unsigned long long)%s);", f, 1 + k, x.c_str());
+          const char *cmp = op == FQ_AGG_MIN ? "<" : ">";
+          stmt = is_s(k) ? fmt("if ((long long)%s %s *(volatile long long *)(slots + %d)) %s((long long *)(slots + %d), (long long)%s);", x.c_str(), cmp,
+                               1 + k, f, 1 + k, x.c_str())
+                         : fmt("if ((unsigned long long)%s %s *(volatile unsigned long long *)(slots + %d)) %s((unsigned long long *)(slots + %d), (unsigned long long)%s);",
+                               x.c_str(), cmp, 1 + k, f, 1 + k, x.c_str());
         }
         if (leaf_counted[k]) {
           const int cs = 1 + out->agg_count_slot[k];

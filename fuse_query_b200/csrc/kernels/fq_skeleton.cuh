@@ -42,7 +42,7 @@ typedef signed char fq_i8;
 #define FQ_TMA_UNROLL 8      // tile = 256 * 8 vector groups = 32 KB of a UInt64 column per bulk copy
 #define FQ_TMA_STAGES 8      // upper bound of the ring; the host picks stages so that ~128 KB are in flight per SM
 #define FQ_TMA_MIN_BLOCKS 1
-#define FQ_SEL_THREADS 384
+#define FQ_SEL_THREADS 352
 #define FQ_SEL_MIN_BLOCKS 2
 #define FQ_SEL_UNROLL 4
 #define FQ_SEL_SEG 8

@@ -61,10 +61,15 @@ DV = golden("ref_datavalues.json")
 
 @pytest.mark.parametrize("case", [c for c in DV if c["kind"] in ("array_arithmetic", "array_comparison", "array_logic")], ids=ident)
 def test_data_array_ops(gpu, case):
-    if has_utf8(case) and not case["error"]:
-        pytest.skip("Utf8 arrays are outside the device path (SURVEY §8f rank 1)")
     fn = {"array_arithmetic": h.data_array_arithmetic_op, "array_comparison": h.data_array_comparison_op,
           "array_logic": h.data_array_logic_op}[case["kind"]]
+    if has_utf8(case) and not case["error"]:
+        # the *_utf8 comparison kernels (datavalues/macros.rs:29-36): strings go to the device as Arrow offsets + bytes
+        def utf8_operand(spec):
+            return h.DataColumnarValue.Array(h.DataArray.utf8(spec["values"])) if "array" in spec else h.DataColumnarValue.Scalar(h.DataValue(TAG["Utf8"], spec["v"]))
+        got = fn(gpu, OPS[case["op"]], utf8_operand(case["left"]), utf8_operand(case["right"]))
+        assert h.data_type_name(got.data_type()) == "Boolean" and got.to_list() == case["expect"]["values"]
+        return
     if has_utf8(case):
         # the reference's error text is still reproduced by the typing rules before anything reaches the device
         with pytest.raises(h.FuseQueryError) as e:
@@ -77,8 +82,17 @@ def test_data_array_ops(gpu, case):
     assert got.to_list() == np.asarray(exp["values"], dtype=NP[exp["array"]]).tolist()
 
 
-@pytest.mark.parametrize("case", [c for c in DV if c["kind"] == "array_aggregate" and not has_utf8(c)], ids=ident)
+@pytest.mark.parametrize("case", [c for c in DV if c["kind"] == "array_aggregate"], ids=ident)
 def test_data_array_aggregate(gpu, case):
+    if has_utf8(case):   # min_string / max_string on the device (data_array_aggregate.rs:139-154); Sum keeps the reference's error
+        arr = h.DataArray.utf8(case["array"]["values"])
+        if case["error"]:
+            with pytest.raises(h.FuseQueryError) as e:
+                h.data_array_aggregate_op(gpu, OPS[case["op"]], arr)
+            assert str(e.value) == case["error"]
+        else:
+            assert h.data_array_aggregate_op(gpu, OPS[case["op"]], arr) == h.DataValue(TAG["Utf8"], case["expect"]["v"])
+        return
     got = h.data_array_aggregate_op(gpu, OPS[case["op"]], to_array(gpu, case["array"]))
     assert got == to_value(case["expect"])
 
@@ -689,3 +703,41 @@ def test_group_by_through_sql_matches_the_group_by_oracle(gpu):
     ctx.options.group_by = True
     with pytest.raises(h.FuseQueryError):
         h.execute_sql(ctx, f"select sum(number), count(number) from system.numbers_mt({n}) group by sum(number)")
+
+
+def test_utf8_arrays_on_the_device(gpu):
+    """Arrow string arrays on the device (fq_utf8): every comparison operator array/array, array/scalar and scalar/array
+    (flipped like data_array_comparison.rs:75-85), NULL slots, min / max with ties and empties — against python's own
+    bytewise string order (Rust str ordering, which arrow's *_utf8 kernels use)."""
+    from fuse_query_b200 import cabi
+    import random
+    rng = random.Random(7)
+    alphabet = ["", "a", "ab", "abc", "b", "ba", "x1", "x2", "é", "zz", "Zebra", "a\u00e9", "日本"]
+    n = 5000
+    left = [rng.choice(alphabet) + rng.choice(alphabet) for _ in range(n)]
+    right = [rng.choice(alphabet) + rng.choice(alphabet) for _ in range(n)]
+    left_n = [None if rng.random() < 0.1 else v for v in left]
+    ctx = cabi.Context(0)
+    L, R, LN = ctx.utf8(left), ctx.utf8(right), ctx.utf8(left_n)
+    key = lambda s: s.encode()
+    ops = {"=": lambda a, b: key(a) == key(b), "<": lambda a, b: key(a) < key(b), "<=": lambda a, b: key(a) <= key(b),
+           ">": lambda a, b: key(a) > key(b), ">=": lambda a, b: key(a) >= key(b)}
+    for op, f in ops.items():
+        assert L.compare(op, R) == [f(a, b) for a, b in zip(left, right)]
+        assert L.compare(op, "ab") == [f(a, "ab") for a in left]
+        assert LN.compare(op, R) == [None if a is None else f(a, b) for a, b in zip(left_n, right)]
+    valid = [v for v in left_n if v is not None]
+    assert left_n[LN.minmax("min")] == min(valid, key=key) and LN.minmax("min") == left_n.index(min(valid, key=key))
+    assert left_n[LN.minmax("max")] == max(valid, key=key) and LN.minmax("max") == left_n.index(max(valid, key=key))
+    assert ctx.utf8([]).minmax("min") == -1 and ctx.utf8([None, None]).minmax("max") == -1
+    # through the host mirror: scalar (op) array flips the operator; a WHERE over a Utf8 column filters on the device result
+    arr = h.DataColumnarValue.Array(h.DataArray.utf8(left))
+    sc = h.DataColumnarValue.Scalar(h.DataValue(TAG["Utf8"], "b"))
+    assert h.data_array_comparison_op(gpu, OPS["Lt"], sc, arr).to_list() == [key("b") < key(a) for a in left]
+    with pytest.raises(h.FuseQueryError) as e:
+        h.data_array_comparison_op(gpu, OPS["Eq"], sc, sc)
+    assert str(e.value) == "Internal Error: Cannot do data_array =, left:Utf8, right:Utf8"
+    with pytest.raises(h.FuseQueryError) as e:
+        h.data_array_comparison_op(gpu, OPS["Eq"], arr, h.DataColumnarValue.Scalar(h.DataValue(TAG["Int8"], 1)))
+    assert str(e.value) == "Internal Error: Unsupported (Utf8) = (Int8)"
+    ctx.close()

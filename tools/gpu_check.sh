@@ -33,6 +33,23 @@ case $what in
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:select --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_select_$c -f python tools/prof_select.py 1000000000 $c > gpurun_out/ncu_select_$c.log 2>&1; echo "ncu $c rc=$?"
     done
     ;;
+  profiles)
+    # ncu captures for profiles/: every kernel of the path, --set full, one launch each after warm-up
+    cap() { name=$1; regex=$2; shift 2; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_$name -f "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?"; }
+    cap agg_headline_1e10 agg_tma python tools/prof_agg.py 10000000000 headline
+    cap agg_headline_gen_1e10 "_agg_" python tools/prof_agg.py 10000000000 headline gen
+    cap agg_nullable_1e9 "_agg_" python tools/prof_agg.py 1000000000 nullable
+    cap select_readme_1e9 select_tma python tools/prof_select.py 1000000000 readme
+    cap select_all_1e9 select_dense python tools/prof_select.py 1000000000 all
+    cap select_third_1e9 select_dense python tools/prof_select.py 1000000000 third
+    cap select_1024_1e9 select_tma python tools/prof_select.py 1000000000 1024
+    cap map_1e9 map_tma python tools/prof_select.py 1000000000 map
+    timeout 600 ncu --set full --clock-control none -k regex:fq_fill_numbers --launch-count 1 -o gpurun_out/ncu_fill_1e9 -f python tools/prof_select.py 1000000000 map > gpurun_out/ncu_fill_1e9.log 2>&1; echo "ncu fill rc=$?"
+    cap groupby_k7_1e9 groupby python tools/prof_groupby.py 1000000000 7
+    cap groupby_k1000_1e9 groupby python tools/prof_groupby.py 1000000000 1000
+    cap groupby_k1e6_1e9 groupby python tools/prof_groupby.py 1000000000 1000000
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-query-table --e2e-rows 1000000000 > gpurun_out/launches_bench.log 2>&1; echo "launch list rc=$?"
+    ;;
   benchN)
     N=$1; shift
     topo
