@@ -79,7 +79,7 @@ EXPORTS = [
     "fq_pipe_state_device", "fq_pipe_launch_project", "fq_pipe_fetch_project", "fq_pipe_fetch_limit_row",
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
-    "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
+    "fq_column_set_validity_bitmap", "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def lib():
         "fq_column_wrap": (i32, [vp, i32, u64, vp, C.POINTER(vp)]),
         "fq_column_slice": (i32, [vp, vp, u64, u64, C.POINTER(vp)]),
         "fq_column_set_validity": (i32, [vp, vp, vp]),
+        "fq_column_set_validity_bitmap": (i32, [vp, vp, vp, u64]),
         "fq_column_validity": (vp, [vp]),
         "fq_column_free": (None, [vp, vp]),
         "fq_group_create": (i32, [vp, i32, i32, u64, C.POINTER(vp)]),
@@ -308,9 +309,16 @@ class Context:
         """col[row_offset : row_offset + n] = begin .. begin + n - 1 (NumbersStream::poll_next on the device)."""
         self.check(lib().fq_numbers_fill(self._h, col._h, row_offset, begin, n, C.c_void_p(stream)))
 
-    def from_numpy(self, a, valid=None, stream: int = 0) -> "Column":
-        """Upload values; `valid` (bool / 0-1 array, one entry per row) attaches a validity column."""
+    def from_numpy(self, a, valid=None, stream: int = 0, *, valid_bitmap=None, bit_offset: int = 0) -> "Column":
+        """Upload values; `valid` (bool / 0-1 array, one entry per row) attaches a byte-per-row validity column,
+        `valid_bitmap` (numpy uint8: an Arrow LSB-first bitmap, row 0 = bit `bit_offset`) attaches it bit-packed."""
         import numpy as np
+        if valid_bitmap is not None:
+            col = self.from_numpy(a, None, stream)
+            bits = self.from_numpy(np.ascontiguousarray(np.asarray(valid_bitmap, dtype=np.uint8)), None, stream)
+            self.check(lib().fq_column_set_validity_bitmap(self._h, col._h, bits._h, bit_offset))
+            col._validity = bits
+            return col
         if valid is not None:
             col = self.from_numpy(a, None, stream)
             v = np.ascontiguousarray(np.asarray(valid).astype(np.uint8))
@@ -345,8 +353,10 @@ class Context:
         data = b"".join(raw)
         valid = None
         if any(v is None for v in values):
-            valid = self.from_numpy(np.array([v is not None for v in values], dtype=np.uint8).view(np.uint8))
-            valid = self.from_numpy(np.array([0 if v is None else 1 for v in values], dtype=np.uint8))
+            flags = np.array([0 if v is None else 1 for v in values], dtype=np.uint8)
+            valid = self.column(BOOL, len(flags))
+            self.check(lib().fq_column_upload(self._h, valid._h, 0, C.c_void_p(flags.ctypes.data), len(flags), C.c_void_p(stream)))
+            self.synchronize(stream)
         h = C.c_void_p()
         buf = C.create_string_buffer(data, max(1, len(data)))
         self.check(lib().fq_utf8_create(self._h, C.c_void_p(offsets.ctypes.data), buf, len(raw), valid._h if valid is not None else None,
@@ -367,7 +377,7 @@ class Context:
         for i, t in enumerate(dtypes):
             d.col_dtypes[i] = t
         for i, f in enumerate(nullable):
-            d.col_nullable[i] = int(bool(f))
+            d.col_nullable[i] = int(f) if int(f) in (0, 1, 2) else 1      # 1: byte validity, 2: Arrow bitmap validity
         d.generated = int(generated)
         nodes = b.array()
         d.nodes = C.cast(nodes, C.POINTER(ExprNode))

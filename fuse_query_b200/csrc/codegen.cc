@@ -220,6 +220,7 @@ struct Gen {
     }
   }
   bool nullable_col(int c) const { return !(d.generated && c == 0) && d.col_nullable[c] != 0; }
+  bool bitmap_col(int c) const { return nullable_col(c) && d.col_nullable[c] == 2; }   // validity = Arrow LSB-first bitmap
   // arrow cast S -> T yields NULL for values T cannot represent (num::cast): can that happen at all?
   static bool cast_fallible(fq_dtype from, fq_dtype to) {
     if (from == to || is_float(to) || from == FQ_BOOL || to == FQ_BOOL) return false;
@@ -476,6 +477,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     if (leaf_counted[k]) out->agg_count_slot[k] = n_slots++;
   out->n_slots = n_slots;
   out->null_cols = null_cols;
+  for (int c : null_cols) out->null_kind.push_back(g.bitmap_col(c) ? 2 : 1);
   out->expr_nullable.assign(d.n_exprs, 0);
   if (d.kind == FQ_PIPE_PROJECT)
     for (int e = 0; e < d.n_exprs; e++) out->expr_nullable[e] = g.maybe_null(d.exprs[e]) ? 1 : 0;
@@ -496,14 +498,22 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
     else s += fmt("    fq_load_vec<%s, V>(r.c%d, p.cols[%d], g);\n", ctype(g.col_dtype(c)), c, c);
   }
-  for (int c : null_cols) s += fmt("    fq_load_vec<bool, V>(r.k%d, p.cols_valid[%d], g);\n", c, c);
+  auto valid_vec = [&](int c) {
+    return g.bitmap_col(c) ? fmt("    fq_load_bits<V>(r.k%d, p.cols_valid[%d], p.cols_valid_bit0[%d] + g * V);\n", c, c, c)
+                           : fmt("    fq_load_vec<bool, V>(r.k%d, p.cols_valid[%d], g);\n", c, c);
+  };
+  auto valid_one = [&](int c) {
+    return g.bitmap_col(c) ? fmt("    r.k%d[0] = fq_ld_bit(p.cols_valid[%d], p.cols_valid_bit0[%d] + row);\n", c, c, c)
+                           : fmt("    r.k%d[0] = fq_ld1<bool>(p.cols_valid[%d], row);\n", c, c);
+  };
+  for (int c : null_cols) s += valid_vec(c);
   s += "  }\n";
   s += "  __device__ static __forceinline__ void load1(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
   for (int c : g.used_cols) {
     if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
     else s += fmt("    r.c%d[0] = fq_ld1<%s>(p.cols[%d], row);\n", c, ctype(g.col_dtype(c)), c);
   }
-  for (int c : null_cols) s += fmt("    r.k%d[0] = fq_ld1<bool>(p.cols_valid[%d], row);\n", c, c);
+  for (int c : null_cols) s += valid_one(c);
   s += "  }\n";
   s += "  __device__ static __forceinline__ void copy_row(Rows &dst, int v, const Rows &one) {\n";
   for (int c : g.used_cols) s += fmt("    dst.c%d[v] = one.c%d[0];\n", c, c);
@@ -520,21 +530,22 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     out->pred_row_bytes = 0;
     for (int c : pred_cols)
       if (!(d.generated && c == 0)) out->pred_row_bytes += (int)dtype_size(g.col_dtype(c));
-    out->pred_row_bytes += (int)pred_null.size();
+    for (int c : pred_null)
+      if (!g.bitmap_col(c)) out->pred_row_bytes += 1;   // byte validity is staged like a column; bitmaps are read in place
     s += fmt("  static constexpr int PRED_ROW_BYTES = %d;\n", out->pred_row_bytes);
     s += "  __device__ static __forceinline__ void load_pred(Rows &r, const fq_launch_params &p, fq_u64 g) {\n";
     for (int c : pred_cols) {
       if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
       else s += fmt("    fq_load_vec<%s, V>(r.c%d, p.cols[%d], g);\n", ctype(g.col_dtype(c)), c, c);
     }
-    for (int c : pred_null) s += fmt("    fq_load_vec<bool, V>(r.k%d, p.cols_valid[%d], g);\n", c, c);
+    for (int c : pred_null) s += valid_vec(c);
     s += "  }\n";
     s += "  __device__ static __forceinline__ void load1_pred(Rows &r, const fq_launch_params &p, fq_u64 row) {\n";
     for (int c : pred_cols) {
       if (d.generated && c == 0) s += "    r.c0[0] = p.numbers_begin + row;\n";
       else s += fmt("    r.c%d[0] = fq_ld1<%s>(p.cols[%d], row);\n", c, ctype(g.col_dtype(c)), c);
     }
-    for (int c : pred_null) s += fmt("    r.k%d[0] = fq_ld1<bool>(p.cols_valid[%d], row);\n", c, c);
+    for (int c : pred_null) s += valid_one(c);
     s += "  }\n";
     out->sel_tma_ok = !pred_cols.empty() && !(d.generated && g.used_cols.count(0)) && !g.used_cols.empty();
     if (out->sel_tma_ok) {
@@ -546,11 +557,12 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         prefix += w;
       }
       for (int c : pred_null) {
+        if (g.bitmap_col(c)) continue;
         s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
         prefix += 1;
       }
       s += "  }\n";
-      s += "  __device__ static __forceinline__ void load_smem_pred(Rows &r, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group) {\n";
+      s += "  __device__ static __forceinline__ void load_smem_pred(Rows &r, const fq_launch_params &p, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group, fq_u64 g) {\n";
       prefix = 0;
       for (int c : pred_cols) {
         int w = (int)dtype_size(g.col_dtype(c));
@@ -558,6 +570,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         prefix += w;
       }
       for (int c : pred_null) {
+        if (g.bitmap_col(c)) { s += valid_vec(c); continue; }   // `g` = the group's index in the source
         s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
         prefix += 1;
       }
@@ -566,7 +579,8 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   }
   // staged (bulk-copy) access: every referenced column must be materialised; validity bytes are staged like a column
   out->tma_ok = !g.used_cols.empty() && !(d.generated && g.used_cols.count(0));
-  out->row_bytes += (int)null_cols.size();
+  for (int c : null_cols)
+    if (!g.bitmap_col(c)) out->row_bytes += 1;
   s += fmt("  static constexpr int ROW_BYTES = %d;\n", out->row_bytes);
   if (out->tma_ok) {
     s += "  template <int HINT = 0> __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
@@ -577,11 +591,12 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       prefix += w;
     }
     for (int c : null_cols) {
+      if (g.bitmap_col(c)) continue;
       s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
       prefix += 1;
     }
     s += "  }\n";
-    s += "  __device__ static __forceinline__ void load_smem(Rows &r, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group) {\n";
+    s += "  __device__ static __forceinline__ void load_smem(Rows &r, const fq_launch_params &p, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group, fq_u64 g) {\n";
     prefix = 0;
     for (int c : g.used_cols) {
       int w = (int)dtype_size(g.col_dtype(c));
@@ -589,6 +604,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       prefix += w;
     }
     for (int c : null_cols) {
+      if (g.bitmap_col(c)) { s += valid_vec(c); continue; }
       s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
       prefix += 1;
     }

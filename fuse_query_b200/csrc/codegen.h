@@ -24,6 +24,7 @@ struct Generated {
   int pred_row_bytes = 0;  // filter + projection pipes: bytes per row of the predicate's columns (what pass 1 streams)
   std::vector<int> used_cols;
   std::vector<int> null_cols;           // referenced columns that carry validity
+  std::vector<int> null_kind;           // per entry of null_cols: 1 = one byte per row, 2 = Arrow LSB-first bitmap
   // aggregate pipes: Aggregator leaves in node-index order
   std::vector<int> agg_nodes, agg_ops;
   std::vector<fq_dtype> agg_dtypes;     // state type of each leaf (Count -> UInt64)

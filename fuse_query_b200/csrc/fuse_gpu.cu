@@ -220,6 +220,8 @@ struct fq_column {
   bool owned = false;
   const fq_column *validity = nullptr;   // FQ_BOOL, one byte per row; borrowed unless owns_validity (slices)
   bool owns_validity = false;
+  const fq_column *validity_bits = nullptr;   // or: FQ_U8 column holding an Arrow LSB-first bitmap (borrowed), row 0 = bit validity_bit0
+  uint64_t validity_bit0 = 0;
 };
 
 // Exchange windows of a group of ranks (one process per GPU): the merge point across GPUs (processor_merge.rs:37-66).
@@ -472,13 +474,21 @@ fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_param
     if (col->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: column %d has %" PRIu64 " rows, source says %" PRIu64, c, col->len, src->n_rows);
     if (((uintptr_t)col->ptr & 15) != 0) p->unaligned = 1;   // a slice off the 16-byte grid: the kernels read it row by row
     p->cols[c] = col->ptr;
-    const bool want_valid = std::find(pipe->gen.null_cols.begin(), pipe->gen.null_cols.end(), c) != pipe->gen.null_cols.end();
-    if (want_valid) {
+    const auto nit = std::find(pipe->gen.null_cols.begin(), pipe->gen.null_cols.end(), c);
+    const bool want_valid = nit != pipe->gen.null_cols.end();
+    const int want_kind = want_valid ? pipe->gen.null_kind[(size_t)(nit - pipe->gen.null_cols.begin())] : 0;
+    if (want_kind == 2) {
+      if (!col->validity_bits) return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a bitmap-validity column %d but the column carries no validity bitmap", c);
+      if (col->validity_bits->len * 8 < col->validity_bit0 + src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: validity bitmap of column %d is shorter than the source", c);
+      if (col->validity_bit0 % (uint64_t)pipe->gen.vec != 0) p->unaligned = 1;   // a thread's V bits would straddle its byte: row-by-row path
+      p->cols_valid[c] = col->validity_bits->ptr;
+      p->cols_valid_bit0[c] = col->validity_bit0;
+    } else if (want_valid) {
       if (!col->validity) return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a nullable column %d but the column carries no validity", c);
       if (col->validity->len < src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: validity of column %d is shorter than the source", c);
       if (((uintptr_t)col->validity->ptr & 15) != 0) p->unaligned = 1;
       p->cols_valid[c] = col->validity->ptr;
-    } else if (col->validity) {
+    } else if (col->validity || col->validity_bits) {
       return set_err(FQ_ERR_INVALID, "Internal Error: column %d carries validity but the pipe was compiled for a NOT NULL column", c);
     }
   }
@@ -581,6 +591,8 @@ fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset,
     c->validity = v;
     c->owns_validity = true;
   }
+  c->validity_bits = parent->validity_bits;
+  c->validity_bit0 = parent->validity_bit0 + offset;
   *out = c;
   return FQ_OK;
 }
@@ -591,6 +603,19 @@ fq_status fq_column_set_validity(fq_ctx *ctx, fq_column *col, const fq_column *v
   if (col->owns_validity && col->validity) fq_column_free(ctx, const_cast<fq_column *>(col->validity));
   col->validity = validity;
   col->owns_validity = false;
+  col->validity_bits = nullptr;
+  col->validity_bit0 = 0;
+  return FQ_OK;
+}
+fq_status fq_column_set_validity_bitmap(fq_ctx *ctx, fq_column *col, const fq_column *bitmap, uint64_t bit_offset) {
+  if (!ctx || !col) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (bitmap && (bitmap->dtype != FQ_U8 || bitmap->len * 8 < bit_offset + col->len))
+    return set_err(FQ_ERR_INVALID, "Internal Error: the validity bitmap must be a UInt8 column of at least ceil((offset + rows) / 8) bytes");
+  if (col->owns_validity && col->validity) fq_column_free(ctx, const_cast<fq_column *>(col->validity));
+  col->validity = nullptr;
+  col->owns_validity = false;
+  col->validity_bits = bitmap;
+  col->validity_bit0 = bitmap ? bit_offset : 0;
   return FQ_OK;
 }
 const fq_column *fq_column_validity(const fq_column *col) { return col ? col->validity : nullptr; }

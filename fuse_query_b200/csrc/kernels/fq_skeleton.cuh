@@ -84,7 +84,9 @@ typedef signed char fq_i8;
 struct fq_launch_params {
   fq_u64 n_rows;
   const void *cols[8];
-  const void *cols_valid[8];  // per input column: one byte per row (1 = valid) or null when the column is NOT NULL
+  const void *cols_valid[8];  // per input column: validity — one byte per row (1 = valid), or an Arrow LSB-first bitmap (the pipe is
+                              // compiled for one or the other), or null when the column is NOT NULL
+  fq_u64 cols_valid_bit0[8];  // bitmap validity: bit of row 0 of the source
   fq_u64 numbers_begin;  // generated mode: column 0 = numbers_begin + row
   // aggregate
   fq_u64 *partials;      // [gridDim.x][FQ_STATE_HDR + Q::NSLOTS]
@@ -156,6 +158,29 @@ __device__ __forceinline__ fq_u64 fq_ld_cg(const fq_u64 *p) {
   fq_u64 v;
   asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
+}
+
+// Arrow validity bitmaps, read in place (datablocks/data_block.rs:10-14 columns are arrow arrays: LSB-first, bit = 1 valid).
+// A thread owns V consecutive rows, i.e. V consecutive bits: one byte (two for V = 16) that the neighbouring lanes share,
+// so a warp load touches 32 * V / 8 bytes of the bitmap — 1/64 of the traffic of a UInt64 column, 1/8 of a UInt8 one,
+// instead of one validity BYTE per row.  `bit` is a multiple of V on the vector path (the host routes anything else
+// through the row-by-row path).
+__device__ __forceinline__ bool fq_ld_bit(const void *bitmap, fq_u64 bit) {
+  return (__ldg((const fq_u8 *)bitmap + (bit >> 3)) >> (bit & 7)) & 1u;
+}
+template <int V> __device__ __forceinline__ void fq_load_bits(bool (&dst)[V], const void *bitmap, fq_u64 bit) {
+  if constexpr (V <= 8) {
+    const fq_u32 w = (fq_u32)__ldg((const fq_u8 *)bitmap + (bit >> 3)) >> (bit & 7);
+#pragma unroll
+    for (int v = 0; v < V; v++) dst[v] = (w >> v) & 1u;
+  } else {
+#pragma unroll
+    for (int b = 0; b < V / 8; b++) {
+      const fq_u32 w = __ldg((const fq_u8 *)bitmap + (bit >> 3) + b);
+#pragma unroll
+      for (int v = 0; v < 8; v++) dst[8 * b + v] = (w >> v) & 1u;
+    }
+  }
 }
 
 // one value (scalar tails, ragged last tile)
@@ -771,7 +796,8 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
       const unsigned char *stage = fq_dyn_smem + (size_t)s * stage_bytes;
       typename Q::Rows rows[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(u * cthreads + (int)threadIdx.x));
+      for (int u = 0; u < U; u++)
+        Q::load_smem(rows[u], p, stage, (fq_u32)tile_rows, (fq_u32)(u * cthreads + (int)threadIdx.x), t * tile_groups + (fq_u64)u * cthreads + threadIdx.x);
 #pragma unroll
       for (int u = 0; u < U; u++) {
         fq_u32 kept = 0;
@@ -1192,7 +1218,8 @@ __device__ __noinline__ void fq_select_scatter_staged(const fq_launch_params &p,
       if (live && wkept) {
         const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
 #pragma unroll
-        for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
+        for (int u = 0; u < U; u++)
+          Q::load_smem(rows[u], p, stage, tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane), tile * ((fq_u64)cthreads * U) + (fq_u64)(warp * 32 * U + 32 * u + lane));
       }
       __syncwarp();
       if (lane == 0) fq_mbar_arrive(fq_smem_addr(&bars[STAGES + slot]));   // the rows are in registers: hand the slot back
@@ -1604,7 +1631,8 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
           const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
           typename Q::Rows rows[U];
 #pragma unroll
-          for (int u = 0; u < U; u++) Q::load_smem_pred(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane));
+          for (int u = 0; u < U; u++)
+            Q::load_smem_pred(rows[u], p, stage, (fq_u32)tile_rows, (fq_u32)(warp * 32 * U + 32 * u + lane), tile * tile_groups + (fq_u64)(warp * 32 * U + 32 * u + lane));
 #pragma unroll
           for (int u = 0; u < U; u++)
 #pragma unroll
@@ -1900,7 +1928,8 @@ __device__ __forceinline__ void fq_map_tma_kernel(const fq_launch_params &p) {
     const unsigned char *stage = fq_dyn_smem + (size_t)slot * stage_bytes;
     typename Q::Rows rows[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) Q::load_smem(rows[u], stage, (fq_u32)tile_rows, (fq_u32)(u * cthreads + (int)threadIdx.x));
+    for (int u = 0; u < U; u++)
+      Q::load_smem(rows[u], p, stage, (fq_u32)tile_rows, (fq_u32)(u * cthreads + (int)threadIdx.x), t * tile_groups + (fq_u64)u * cthreads + threadIdx.x);
     __syncwarp();
     if (lane == 0) fq_mbar_arrive(fq_smem_addr(&s_bars[STAGES + slot]));   // the tile is in registers: hand the slot back
     if (++slot == stages) { slot = 0; round++; }

@@ -128,6 +128,11 @@ fq_status fq_column_slice(fq_ctx *ctx, const fq_column *parent, uint64_t offset,
 /* attach (validity != NULL) or detach a validity column; it is borrowed and must outlive `col`; slices of `col`
  * made afterwards slice it too */
 fq_status fq_column_set_validity(fq_ctx *ctx, fq_column *col, const fq_column *validity);
+/* The same with Arrow's own validity buffer, left bit-packed: `bitmap` is an FQ_U8 column holding the LSB-first bitmap
+ * (bit = 1: valid), row 0 of `col` = bit `bit_offset` (arrow's array offset).  Pipes compiled with col_nullable = 2 read
+ * the bits in place: 1 bit of validity traffic per row instead of 1 byte (12.5 % -> 1.6 % on a UInt64 column, 100 % ->
+ * 12.5 % on a UInt8 one).  Borrowed like a byte validity column; slices of `col` keep it with a moved offset. */
+fq_status fq_column_set_validity_bitmap(fq_ctx *ctx, fq_column *col, const fq_column *bitmap, uint64_t bit_offset);
 const fq_column *fq_column_validity(const fq_column *col);
 void fq_column_free(fq_ctx *ctx, fq_column *col);
 fq_dtype fq_column_dtype(const fq_column *col);
@@ -204,7 +209,8 @@ enum { FQ_PIPE_PROJECT = 0, FQ_PIPE_AGGREGATE = 1, FQ_PIPE_GROUPBY = 2 };
 typedef struct fq_pipe_desc {
   int32_t n_cols;                   /* input schema */
   fq_dtype col_dtypes[FQ_MAX_COLS];
-  int32_t col_nullable[FQ_MAX_COLS]; /* 1: the column carries validity (fq_column_set_validity) */
+  int32_t col_nullable[FQ_MAX_COLS]; /* 1: the column carries validity, one byte per row (fq_column_set_validity);
+                                        2: validity is an Arrow bitmap (fq_column_set_validity_bitmap) */
   int32_t generated;                /* specialise for fq_source.generated (column 0 = UInt64 numbers) */
   const fq_expr_node *nodes;
   int32_t n_nodes;

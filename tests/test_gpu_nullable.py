@@ -282,3 +282,64 @@ def test_pyarrow_validity_bitmap_goes_to_the_device_unexpanded(env):
     assert got.column(0).validity().to_arrow_bitmap() == np.packbits(~mask[5:n - 4], bitorder="little").tobytes()
     (cnt,) = h.execute_sql(fctx, "select sum(x) from bm")[0].column(0).to_list()
     assert cnt == int(vals[5:n - 4][~mask[5:n - 4]].sum())
+
+
+@pytest.mark.parametrize("variant", ["tma", "ldg"])
+def test_arrow_validity_bitmaps_are_read_in_place(env, variant):
+    """fq_column_set_validity_bitmap: Arrow's LSB-first validity buffer stays bit-packed on the device (pipes compiled with
+    col_nullable = 2) — 1 bit of validity traffic per row instead of 1 byte.  Same results as the byte-per-row form and as the
+    oracle, through every kernel family (aggregate, filter + projection, projection, GROUP BY), with a bit offset (arrow's
+    array offset), on slices, and when a thread's bits straddle a byte (offsets that are not multiples of the vector width)."""
+    ctx, vals, valid, _cols, table = env
+    os_env = __import__("os").environ
+    for name, var in (("FQ_AGG_VARIANT", "tma" if variant == "tma" else "u4"), ("FQ_SEL_VARIANT", variant), ("FQ_MAP_VARIANT", variant)):
+        os_env[name] = var
+    try:
+        for bit_offset in (0, 3, 64):
+            cols = []
+            for k in NAMES:
+                if valid[k] is None:
+                    cols.append(ctx.from_numpy(vals[k]))
+                else:
+                    bits = np.packbits(np.concatenate([np.zeros(bit_offset, np.uint8), valid[k]]), bitorder="little")
+                    cols.append(ctx.from_numpy(vals[k], valid_bitmap=bits, bit_offset=bit_offset))
+            nullable = [0 if valid[k] is None else 2 for k in NAMES]
+            kw = dict(columns=NAMES, dtypes=[DT[k] for k in NAMES], nullable=nullable)
+            # aggregates
+            aggs = ["(sum (col a))", "(min (col b))", "(max (+ (col b) (col c)))", "(count (col a))", "(sum (col e))"]
+            pipe = ctx.pipe(aggs, aggregate=True, predicate="(> (col c) (i32 100))", **kw)
+            pipe.launch_aggregate(cabi.make_source(cols, N))
+            states, rows = pipe.fetch_aggregate()
+            want = o.run_query(aggs, table=table, predicate="(> (col c) (i32 100))", is_aggregate=True, worker_threads=1, tail_quirk=False,
+                               block_size=1 << 30)
+            got = [s[1] for s in states]
+            exp = list(want.rows()[0])
+            assert got[:4] == exp[:4] and abs(got[4] - exp[4]) <= 1e-9 * abs(exp[4])
+            # filter + projection, on a slice that starts off the vector grid (rows 5 .. N-2)
+            exprs = ["(+ (col a) (u64 1))", "(* (col b) (col c))"]
+            pred = "(< (col b) (i64 0))"
+            for off, m in ((0, N), (5, N - 7), (64, 10_000)):
+                sl = [c.slice(off, m) for c in cols]
+                p2 = ctx.pipe(exprs, predicate=pred, **kw)
+                outs = [ctx.column(p2.expr_dtype(i), m) for i in range(2)]
+                ov = [ctx.column(cabi.BOOL, m) if p2.expr_nullable(i) else None for i in range(2)]
+                p2.launch_project(cabi.make_source(sl, m), outs, m, out_valid=ov)
+                sel, written = p2.fetch_project()
+                sub = {k: o.array(DT[k], vals[k][off:off + m], None if valid[k] is None else valid[k][off:off + m]) for k in NAMES}
+                w = o.run_query(exprs, table=sub, predicate=pred, worker_threads=1, tail_quirk=False, block_size=1 << 30)
+                assert written == w.n_rows
+                for i in range(2):
+                    wv = w.columns[i]
+                    ok = np.ones(written, bool) if wv.valid is None else wv.valid.astype(bool)
+                    gv = np.ones(written, bool) if ov[i] is None else ov[i].to_numpy(written).astype(bool)
+                    assert np.array_equal(gv, ok) and np.array_equal(outs[i].to_numpy(written)[ok], wv.values[ok])
+                p2.destroy()
+            pipe.destroy()
+        # a pipe compiled for bitmaps refuses a byte-validity column and vice versa
+        pipe = ctx.pipe(["(sum (col a))"], aggregate=True, columns=["a"], dtypes=[cabi.U64], nullable=[2])
+        with pytest.raises(cabi.FuseGpuError) as e:
+            pipe.launch_aggregate(cabi.make_source([ctx.from_numpy(vals["a"], valid["a"])], N))
+        assert "carries no validity bitmap" in str(e.value)
+    finally:
+        for name in ("FQ_AGG_VARIANT", "FQ_SEL_VARIANT", "FQ_MAP_VARIANT"):
+            os_env.pop(name, None)

@@ -35,16 +35,25 @@ case $what in
     ;;
   profiles)
     # ncu captures for profiles/: every kernel of the path, --set full, one launch each after warm-up
-    cap() { name=$1; regex=$2; shift 2; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_$name -f "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?"; }
+    # (the .ncu-rep files are summarised on the box and removed: gpurun copies back at most 64 MiB)
+    cap() { name=$1; regex=$2; shift 2; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_$name -f "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?";
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page details > gpurun_out/ncu_$name.details.txt 2>/dev/null;
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page raw --csv > gpurun_out/ncu_$name.raw.csv 2>/dev/null;
+            case $name in agg_headline_1e10|select_all_1e9) ;; *) rm -f gpurun_out/ncu_$name.ncu-rep;; esac; }
+    rm -f gpurun_out/*.ncu-rep
     cap agg_headline_1e10 agg_tma python tools/prof_agg.py 10000000000 headline
     cap agg_headline_gen_1e10 "_agg_" python tools/prof_agg.py 10000000000 headline gen
-    cap agg_nullable_1e9 "_agg_" python tools/prof_agg.py 1000000000 nullable
+    cap agg_nullable_bytes_1e9 "_agg_" python tools/prof_agg.py 1000000000 nullable
+    cap agg_nullable_bits_1e9 "_agg_" python tools/prof_agg.py 1000000000 nullable_bits
+    cap agg_nullable_u8_bytes_4e9 "_agg_" python tools/prof_agg.py 4000000000 nullable_u8
+    cap agg_nullable_u8_bits_4e9 "_agg_" python tools/prof_agg.py 4000000000 nullable_u8_bits
     cap select_readme_1e9 select_tma python tools/prof_select.py 1000000000 readme
     cap select_all_1e9 select_dense python tools/prof_select.py 1000000000 all
     cap select_third_1e9 select_dense python tools/prof_select.py 1000000000 third
     cap select_1024_1e9 select_tma python tools/prof_select.py 1000000000 1024
     cap map_1e9 map_tma python tools/prof_select.py 1000000000 map
     timeout 600 ncu --set full --clock-control none -k regex:fq_fill_numbers --launch-count 1 -o gpurun_out/ncu_fill_1e9 -f python tools/prof_select.py 1000000000 map > gpurun_out/ncu_fill_1e9.log 2>&1; echo "ncu fill rc=$?"
+    ncu -i gpurun_out/ncu_fill_1e9.ncu-rep --page details > gpurun_out/ncu_fill_1e9.details.txt 2>/dev/null; ncu -i gpurun_out/ncu_fill_1e9.ncu-rep --page raw --csv > gpurun_out/ncu_fill_1e9.raw.csv 2>/dev/null; rm -f gpurun_out/ncu_fill_1e9.ncu-rep
     cap groupby_k7_1e9 groupby python tools/prof_groupby.py 1000000000 7
     cap groupby_k1000_1e9 groupby python tools/prof_groupby.py 1000000000 1000
     cap groupby_k1e6_1e9 groupby python tools/prof_groupby.py 1000000000 1000000
