@@ -993,10 +993,10 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
     CUDA_TRY(cudaMemsetAsync(pipe->d_blocks, 0, sizeof(uint32_t) * words, (cudaStream_t)stream));
     p.block_hit = pipe->d_blocks;
   }
+  // the kernel's last CTA writes state (and merged state) straight into the pinned host mirrors: nothing is queued behind it
+  p.host_state = (fq_u64 *)pipe->h_state;
+  p.host_merged = pipe->group ? (fq_u64 *)pipe->h_merged : nullptr;
   if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
-  CUDA_TRY(cudaMemcpyAsync(pipe->h_state, pipe->d_state, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  if (pipe->group)
-    CUDA_TRY(cudaMemcpyAsync(pipe->h_merged, pipe->d_merged, sizeof(uint64_t) * pipe->n_slots, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   pipe->launched_merged = pipe->group != nullptr;
   CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
   pipe->launched = true;

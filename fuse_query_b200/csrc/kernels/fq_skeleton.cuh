@@ -108,6 +108,8 @@ struct fq_launch_params {
   fq_u64 group_epoch;
   fq_u64 group_timeout_ns;
   fq_u64 *merged;          // [FQ_STATE_HDR + Q::NSLOTS] merged state of all ranks (local)
+  fq_u64 *host_state;      // pinned host mirrors of `state` / `merged`, written by the kernel itself (no copy operation queued
+  fq_u64 *host_merged;     // behind the launch: a 10^7-row query is launch-latency bound and the copy cost as much as the kernel)
   fq_u32 group_rank, group_world, group_row_slots;
   // group by: open-addressing table in HBM, gb_cap (a power of two) slots + 1 for the key that equals the EMPTY mark
   fq_u64 *gb_keys;        // [gb_cap + 1] packed keys, FQ_GB_EMPTY = free
@@ -451,6 +453,13 @@ template <int V> __device__ __forceinline__ void fq_mark_blocks_warp(const fq_la
 
 #define FQ_E_MERGE_TIMEOUT 2u  // a rank's state did not arrive in the exchange window in time
 
+// Out of line (see fq_group_merge): the running state into its pinned host mirror, posted writes over PCIe
+static __device__ __noinline__ void fq_mirror_state(fq_u64 *host, const fq_u64 *dev, int n) {
+  for (int k = 0; k < n; k++) host[k] = dev[k];
+  __threadfence_system();
+}
+
+
 __device__ __forceinline__ void fq_st_release_sys(fq_u64 *p, fq_u64 v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -528,6 +537,7 @@ static __device__ __noinline__ void fq_group_merge(const fq_launch_params &p) {
 #pragma unroll
     for (int k = 0; k < FQ_STATE_HDR; k++) p.merged[k] = hdr[k];
     Q::store(acc, p.merged + FQ_STATE_HDR);
+    if (p.host_merged) fq_mirror_state(p.host_merged, p.merged, S);
   }
 }
 
@@ -607,6 +617,7 @@ __device__ __forceinline__ void fq_agg_finish(const fq_launch_params &p, typenam
     p.state[5] = empty_blocks;
     Q::store(acc, p.state + FQ_STATE_HDR);
     *p.ticket = 0;
+    if (p.host_state) fq_mirror_state(p.host_state, p.state, S);
   }
   // the merge point across GPUs, fused: exchange over peer memory + final fold (see fq_group_merge)
   if (p.group_world) {
@@ -1743,11 +1754,35 @@ __device__ __forceinline__ fq_i64 fq_gb_find(const fq_launch_params &p, fq_u64 k
   return -1;
 }
 
+// Folds over the lanes of `mask` (the lanes of a warp that hold the same key), with the warp-reduce unit (REDUX.SYNC, 32-bit):
+// a wrapping 64-bit sum as three pieces of at most 22 bits (32 lanes x 2^22 fits 32 bits, no carry is lost), 64-bit
+// min / max as the high words first and then the low words of the lanes that tie on the high word.
+__device__ __forceinline__ fq_u64 fq_redux_add64(fq_u32 mask, fq_u64 x) {
+  const fq_u32 a = __reduce_add_sync(mask, (fq_u32)(x & 0x3fffffu));
+  const fq_u32 b = __reduce_add_sync(mask, (fq_u32)((x >> 22) & 0x3fffffu));
+  const fq_u32 c = __reduce_add_sync(mask, (fq_u32)(x >> 44));
+  return (fq_u64)a + ((fq_u64)b << 22) + ((fq_u64)c << 44);
+}
+__device__ __forceinline__ fq_u64 fq_redux_max64(fq_u32 mask, fq_u64 x) {
+  const fq_u32 hi = __reduce_max_sync(mask, (fq_u32)(x >> 32));
+  const fq_u32 lo = __reduce_max_sync(mask, (fq_u32)(x >> 32) == hi ? (fq_u32)x : 0u);
+  return ((fq_u64)hi << 32) | lo;
+}
+__device__ __forceinline__ fq_u64 fq_redux_min64(fq_u32 mask, fq_u64 x) {
+  const fq_u32 hi = __reduce_min_sync(mask, (fq_u32)(x >> 32));
+  const fq_u32 lo = __reduce_min_sync(mask, (fq_u32)(x >> 32) == hi ? (fq_u32)x : 0xffffffffu);
+  return ((fq_u64)hi << 32) | lo;
+}
+// float sums have no REDUX: the lanes of the group are added in lane order (= row order inside the warp)
+__device__ __forceinline__ fq_u64 fq_redux_addf64(fq_u32 mask, fq_u64 bits) {
+  double acc = 0.0;
+  for (fq_u32 m = mask; m; m &= m - 1) acc += __longlong_as_double((fq_i64)__shfl_sync(mask, bits, __ffs(m) - 1));
+  return (fq_u64)__double_as_longlong(acc);
+}
+
+// one group state (Q::G slots: rows, leaves, valid counts) into the CTA's shared-memory table or the table in HBM
 template <class Q>
-__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, const typename Q::Rows &r, int v, fq_u32 &err) {
-  fq_u64 key, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
-  fq_u32 vmask;
-  if (!Q::gb_row(r, v, err, key, val, vmask)) return;
+__device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u64 key, const fq_u64 *st) {
   const fq_u64 h = fq_gb_hash(key);
   if (p.gb_smem_cap && key != FQ_GB_EMPTY) {
     const fq_u32 smask = p.gb_smem_cap - 1;
@@ -1757,13 +1792,39 @@ __device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *ske
       fq_u64 cur = *(volatile fq_u64 *)(skeys + i);
       if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
       if (cur == FQ_GB_EMPTY || cur == key) {
-        Q::gb_apply(sslots + (size_t)i * Q::G, val, vmask);
+        Q::gb_merge(sslots + (size_t)i * Q::G, st);
         return;
       }
     }
   }
   const fq_i64 slot = fq_gb_find(p, key, h);
-  if (slot >= 0) Q::gb_apply(p.gb_slots + (fq_u64)slot * Q::G, val, vmask);
+  if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, st);
+}
+
+// One row per lane.  Lanes of the warp that hold the same key fold their rows first (Q::gb_fold: REDUX over the match
+// group) and one of them updates the table: with few distinct keys that turns 32 conflicting atomics per aggregate into
+// one per distinct key.  `agg` is the thread's running verdict on whether that pays (keys that never repeat inside a
+// warp only pay for the MATCH): after 32 rows without a single shared key the warp stops trying.
+template <class Q>
+__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, const typename Q::Rows &r, int v, fq_u32 &err,
+                                          int &agg) {
+  fq_u64 key, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
+  fq_u32 vmask;
+  if (!Q::gb_row(r, v, err, key, val, vmask)) return;
+  fq_u64 st[Q::G];
+  if (agg > 0) {
+    const fq_u32 live = __activemask();
+    const fq_u32 peers = __match_any_sync(live, key);
+    const bool shared = __any_sync(live, (peers & (peers - 1)) != 0);
+    agg = shared ? 32 : agg - 1;
+    if (peers & (peers - 1)) {
+      Q::gb_fold(st, val, vmask, peers);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) fq_gb_put<Q>(p, skeys, sslots, key, st);
+      return;
+    }
+  }
+  Q::gb_one(st, val, vmask);
+  fq_gb_put<Q>(p, skeys, sslots, key, st);
 }
 
 template <class Q, int UNROLL>
@@ -1778,6 +1839,7 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
   }
   __syncthreads();
   fq_u32 err = 0;
+  int agg = 32;
   const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
@@ -1789,7 +1851,7 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, rows[u], v, err);
+      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, rows[u], v, err, agg);
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
@@ -1797,12 +1859,12 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
     typename Q::Rows r;
     Q::load(r, p, g);
 #pragma unroll
-    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, r, v, err);
+    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, r, v, err, agg);
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
-    fq_gb_row<Q>(p, skeys, sslots, r, 0, err);
+    fq_gb_row<Q>(p, skeys, sslots, r, 0, err, agg);
   }
   __syncthreads();
   // flush the CTA's groups into the table in HBM
