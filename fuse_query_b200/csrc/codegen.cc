@@ -533,6 +533,11 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
     for (int c : pred_null)
       if (!g.bitmap_col(c)) out->pred_row_bytes += 1;   // byte validity is staged like a column; bitmaps are read in place
     s += fmt("  static constexpr int PRED_ROW_BYTES = %d;\n", out->pred_row_bytes);
+    {
+      int nb = 0;
+      for (int c : pred_null) nb += g.bitmap_col(c) ? 1 : 0;
+      s += fmt("  __device__ static constexpr fq_u32 pred_stage_bytes(fq_u32 tile_rows) { return tile_rows * %du + %du * (tile_rows >> 3); }\n", out->pred_row_bytes, nb);
+    }
     s += "  __device__ static __forceinline__ void load_pred(Rows &r, const fq_launch_params &p, fq_u64 g) {\n";
     for (int c : pred_cols) {
       if (d.generated && c == 0) s += "#pragma unroll\n    for (int v = 0; v < V; v++) r.c0[v] = p.numbers_begin + g * V + v;\n";
@@ -561,6 +566,16 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
         prefix += 1;
       }
+      {   // validity bitmaps: tile_rows / 8 bytes each, behind the byte columns (the host stages only 128-row aligned bitmaps)
+        int j = 0;
+        for (int c : pred_null)
+          if (g.bitmap_col(c)) {
+            s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du + %du * (tile_rows >> 3), (const char *)p.cols_valid[%d] + ((p.cols_valid_bit0[%d] + tile * tile_rows) >> 3), tile_rows >> 3, bar);\n",
+                     out->pred_row_bytes, j, c, c);
+            j++;
+          }
+        out->pred_row_bitmaps = j;
+      }
       s += "  }\n";
       s += "  __device__ static __forceinline__ void load_smem_pred(Rows &r, const fq_launch_params &p, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group, fq_u64 g) {\n";
       prefix = 0;
@@ -569,10 +584,16 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         s += fmt("    fq_lds_vec<%s, V>(r.c%d, stage + (size_t)tile_rows * %d, group);\n", ctype(g.col_dtype(c)), c, prefix);
         prefix += w;
       }
-      for (int c : pred_null) {
-        if (g.bitmap_col(c)) { s += valid_vec(c); continue; }   // `g` = the group's index in the source
-        s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
-        prefix += 1;
+      {
+        int j = 0;
+        for (int c : pred_null) {
+          if (g.bitmap_col(c)) {
+            s += fmt("    fq_lds_bits<V>(r.k%d, stage + (size_t)tile_rows * %d + %d * (tile_rows >> 3), group);\n", c, out->pred_row_bytes, j++);
+            continue;
+          }
+          s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
+          prefix += 1;
+        }
       }
       s += "  }\n";
     }
@@ -582,6 +603,8 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
   for (int c : null_cols)
     if (!g.bitmap_col(c)) out->row_bytes += 1;
   s += fmt("  static constexpr int ROW_BYTES = %d;\n", out->row_bytes);
+  for (int c : null_cols) out->row_bitmaps += g.bitmap_col(c) ? 1 : 0;
+  s += fmt("  __device__ static constexpr fq_u32 stage_bytes(fq_u32 tile_rows) { return tile_rows * %du + %du * (tile_rows >> 3); }\n", out->row_bytes, out->row_bitmaps);
   if (out->tma_ok) {
     s += "  template <int HINT = 0> __device__ static __forceinline__ void tma_issue(const fq_launch_params &p, fq_u32 stage, fq_u32 bar, fq_u64 tile, fq_u32 tile_rows) {\n";
     int prefix = 0;
@@ -595,6 +618,13 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du, (const char *)p.cols_valid[%d] + tile * tile_rows, tile_rows, bar);\n", prefix, c);
       prefix += 1;
     }
+    {
+      int j = 0;
+      for (int c : null_cols)
+        if (g.bitmap_col(c))
+          s += fmt("    fq_bulk_g2s<HINT>(stage + tile_rows * %du + %du * (tile_rows >> 3), (const char *)p.cols_valid[%d] + ((p.cols_valid_bit0[%d] + tile * tile_rows) >> 3), tile_rows >> 3, bar);\n",
+                   out->row_bytes, j++, c, c);
+    }
     s += "  }\n";
     s += "  __device__ static __forceinline__ void load_smem(Rows &r, const fq_launch_params &p, const unsigned char *stage, fq_u32 tile_rows, fq_u32 group, fq_u64 g) {\n";
     prefix = 0;
@@ -603,10 +633,16 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       s += fmt("    fq_lds_vec<%s, V>(r.c%d, stage + (size_t)tile_rows * %d, group);\n", ctype(g.col_dtype(c)), c, prefix);
       prefix += w;
     }
-    for (int c : null_cols) {
-      if (g.bitmap_col(c)) { s += valid_vec(c); continue; }
-      s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
-      prefix += 1;
+    {
+      int j = 0;
+      for (int c : null_cols) {
+        if (g.bitmap_col(c)) {
+          s += fmt("    fq_lds_bits<V>(r.k%d, stage + (size_t)tile_rows * %d + %d * (tile_rows >> 3), group);\n", c, out->row_bytes, j++);
+          continue;
+        }
+        s += fmt("    fq_lds_vec<bool, V>(r.k%d, stage + (size_t)tile_rows * %d, group);\n", c, prefix);
+        prefix += 1;
+      }
     }
     s += "  }\n";
   }

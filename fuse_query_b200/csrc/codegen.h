@@ -22,6 +22,7 @@ struct Generated {
   int vec = 2;             // rows per thread per vector load group (Q::V)
   int row_bytes = 0;       // bytes read per row (materialised columns actually referenced)
   int pred_row_bytes = 0;  // filter + projection pipes: bytes per row of the predicate's columns (what pass 1 streams)
+  int row_bitmaps = 0, pred_row_bitmaps = 0;   // validity bitmaps staged behind them: tile_rows / 8 bytes each
   std::vector<int> used_cols;
   std::vector<int> null_cols;           // referenced columns that carry validity
   std::vector<int> null_kind;           // per entry of null_cols: 1 = one byte per row, 2 = Arrow LSB-first bitmap

@@ -481,6 +481,7 @@ fq_status bind_source(const fq_pipe *pipe, const fq_source *src, fq_launch_param
       if (!col->validity_bits) return set_err(FQ_ERR_INVALID, "Internal Error: pipe was compiled for a bitmap-validity column %d but the column carries no validity bitmap", c);
       if (col->validity_bits->len * 8 < col->validity_bit0 + src->n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: validity bitmap of column %d is shorter than the source", c);
       if (col->validity_bit0 % (uint64_t)pipe->gen.vec != 0) p->unaligned = 1;   // a thread's V bits would straddle its byte: row-by-row path
+      if (col->validity_bit0 % 128 != 0) p->bits_unstaged = 1;   // a tile's bitmap bytes would not start on a 16-byte boundary: no bulk copies
       p->cols_valid[c] = col->validity_bits->ptr;
       p->cols_valid_bit0[c] = col->validity_bit0;
     } else if (want_valid) {
@@ -769,11 +770,14 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
         if (!(getenv("FQ_JIT_ALL_VARIANTS") && atoi(getenv("FQ_JIT_ALL_VARIANTS")) != 0)) {
           const bool agg = gen.kind == FQ_PIPE_AGGREGATE;
           const int u = agg || !gen.has_pred ? shapes().tma_unroll : (shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec);
-          const unsigned tile_bytes = (unsigned)(agg || !gen.has_pred ? shapes().tma_threads : shapes().selt_threads) * u * gen.vec *
-                                      (agg || !gen.has_pred ? gen.row_bytes : gen.pred_row_bytes);
+          const unsigned trows = (unsigned)(agg || !gen.has_pred ? shapes().tma_threads : shapes().selt_threads) * u * gen.vec;
+          const unsigned tile_bytes = agg || !gen.has_pred ? trows * gen.row_bytes + gen.row_bitmaps * (trows / 8)
+                                                           : trows * gen.pred_row_bytes + gen.pred_row_bitmaps * (trows / 8);
           const bool staged = (agg || !gen.has_pred ? gen.tma_ok : gen.sel_tma_ok) && 2u * tile_bytes <= 200u * 1024u;
           const std::string variant_env = getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT")
                                               ? getenv(agg ? "FQ_AGG_VARIANT" : gen.has_pred ? "FQ_SEL_VARIANT" : "FQ_MAP_VARIANT") : "tma";
+          // a validity bitmap that starts off the 128-row grid (a slice) cannot be bulk-copied: such pipes also get the LDG kernel
+          if (gen.row_bitmaps > 0 && gen.kind != FQ_PIPE_GROUPBY) want.push_back(agg ? "_agg_u4" : gen.has_pred ? "_select" : "_map");
           if (gen.kind == FQ_PIPE_GROUPBY) { want.push_back("_groupby"); want.push_back("_gbmerge"); }
           else if (agg) want.push_back(staged && variant_env == "tma" ? "_agg_tma" : variant_env == "u8" ? "_agg_u8" : "_agg_u4");
           else if (gen.has_pred) {
@@ -809,7 +813,8 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       if (!s2) s2 = resolve_kernel(m, base + "_agg_u8", shapes().agg_threads, &pipe->k_agg_u8);
       if (!s2 && gen.tma_ok) {
         // ring depth: as many tiles as fit ~128 KB per CTA (measured optimum on B200), at least 2, at most the template bound
-        const unsigned tile_bytes = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec * gen.row_bytes;
+        const unsigned trows = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec;
+        const unsigned tile_bytes = trows * gen.row_bytes + gen.row_bitmaps * (trows / 8);
         unsigned stages = shapes().tma_stages_env > 0 ? (unsigned)shapes().tma_stages_env : (128u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_TMA_STAGES);
         if (stages * tile_bytes <= 200 * 1024) {
@@ -822,7 +827,8 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
       if (!s2 && gen.sel_tma_ok) {
         // staged variant: consumer warps + scan warp + producer warp; ring of ~192 KB per CTA, at least 2 tiles
         const int u = shapes().selt_unroll * gen.vec <= 32 ? shapes().selt_unroll : 32 / gen.vec;   // fq_selt_shape<V>::U
-        const unsigned tile_bytes = (unsigned)shapes().selt_threads * u * gen.vec * gen.pred_row_bytes;   // pass 1 stages the predicate's columns
+        const unsigned trows_s = (unsigned)shapes().selt_threads * u * gen.vec;
+        const unsigned tile_bytes = trows_s * gen.pred_row_bytes + gen.pred_row_bitmaps * (trows_s / 8);   // pass 1 stages the predicate's columns
         // ~192 KB in flight per SM measured best here (1.19 -> 1.14 ms at 1e9 rows; the aggregate kernel peaks at 128 KB)
         unsigned stages = shapes().selt_stages_env > 0 ? (unsigned)shapes().selt_stages_env : (192u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_SELT_STAGES);
@@ -833,7 +839,8 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
         // the dense-tuned build: both passes staged, so a slot holds a tile of EVERY referenced column; small tiles and a
         // ring of ~112 KB (FQ_SELT_STAGE2=0 leaves it out: dense selections then re-read kept rows from L2 with plain loads)
         const int ud = shapes().seld_unroll * gen.vec <= 32 ? shapes().seld_unroll : 32 / gen.vec;   // fq_seld_shape<V>::U
-        const unsigned all_bytes = (unsigned)shapes().seld_threads * ud * gen.vec * gen.row_bytes;
+        const unsigned trows_d = (unsigned)shapes().seld_threads * ud * gen.vec;
+        const unsigned all_bytes = trows_d * gen.row_bytes + gen.row_bitmaps * (trows_d / 8);
         static const bool stage2_env = !(getenv("FQ_SELT_STAGE2") && atoi(getenv("FQ_SELT_STAGE2")) == 0);
         const unsigned dstages = std::min<unsigned>(std::max<unsigned>((unsigned)shapes().seld_stages, 3), 16);
         if (!s2 && pipe->k_select_tma.valid() && stage2_env && dstages * all_bytes <= 200u * 1024u) {
@@ -845,7 +852,8 @@ fq_status fq_pipe_compile(fq_ctx *ctx, const fq_pipe_desc *desc, fq_pipe **out) 
     } else {
       s2 = resolve_kernel(m, base + "_map", shapes().map_threads, &pipe->k_map);
       if (!s2 && gen.tma_ok) {
-        const unsigned tile_bytes = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec * gen.row_bytes;
+        const unsigned trows = (unsigned)shapes().tma_threads * shapes().tma_unroll * gen.vec;
+        const unsigned tile_bytes = trows * gen.row_bytes + gen.row_bitmaps * (trows / 8);
         unsigned stages = shapes().tma_stages_env > 0 ? (unsigned)shapes().tma_stages_env : (128u * 1024u) / tile_bytes;
         stages = std::min<unsigned>(std::max<unsigned>(stages, 2), FQ_TMA_STAGES);
         if (stages * tile_bytes <= 200 * 1024) {
@@ -959,7 +967,9 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   // kernel variant: chosen when the pipe was compiled (FQ_AGG_VARIANT) or by fq_pipe_set_variant
   const std::string &variant = pipe->variant;
   // the preferred variant when the module holds it, else whichever it was built with
-  const bool use_tma = (variant == "tma" && pipe->k_agg_tma.valid()) || (!pipe->k_agg_u4.valid() && !pipe->k_agg_u8.valid());
+  if (p.bits_unstaged && !pipe->k_agg_u4.valid() && !pipe->k_agg_u8.valid())
+    return set_err(FQ_ERR_INTERNAL, "Internal Error: validity bitmap off the 128-row grid needs the LDG kernel, which this pipe was not built with");
+  const bool use_tma = !p.bits_unstaged && ((variant == "tma" && pipe->k_agg_tma.valid()) || (!pipe->k_agg_u4.valid() && !pipe->k_agg_u8.valid()));
   const bool want_u8 = (variant == "u8" && pipe->k_agg_u8.valid()) || (!use_tma && !pipe->k_agg_u4.valid());
   const Kernel &k = use_tma ? pipe->k_agg_tma : want_u8 ? pipe->k_agg_u8 : pipe->k_agg_u4;
   if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no aggregate kernel was built for this pipe");
@@ -1354,7 +1364,9 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     // density probe says so) | sparse | dense (force one staged build) | ldg (worker-warp loads; generated sources)
     const std::string &variant = pipe->variant;
     const bool staged_ok = pipe->k_select_tma.valid();
-    const bool use_tma = (variant != "ldg" && staged_ok) || !pipe->k_select.valid();
+    if (p.bits_unstaged && !pipe->k_select.valid())
+      return set_err(FQ_ERR_INTERNAL, "Internal Error: validity bitmap off the 128-row grid needs the LDG kernel, which this pipe was not built with");
+    const bool use_tma = !p.bits_unstaged && ((variant != "ldg" && staged_ok) || !pipe->k_select.valid());
     const int vec = pipe->gen.vec;
     auto seg_rows = [&](int threads, int cfg_u, int cfg_seg) {
       const int u = cfg_u * vec <= 32 ? cfg_u : 32 / vec;
@@ -1417,7 +1429,9 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     }
     // FQ_MAP_VARIANT = tma (default: reads staged by bulk copies; needs every referenced column materialised) | ldg
     const std::string &variant = pipe->variant;
-    const bool use_tma = (variant == "tma" && pipe->k_map_tma.valid()) || !pipe->k_map.valid();
+    if (p.bits_unstaged && !pipe->k_map.valid())
+      return set_err(FQ_ERR_INTERNAL, "Internal Error: validity bitmap off the 128-row grid needs the LDG kernel, which this pipe was not built with");
+    const bool use_tma = !p.bits_unstaged && ((variant == "tma" && pipe->k_map_tma.valid()) || !pipe->k_map.valid());
     const Kernel &k = use_tma ? pipe->k_map_tma : pipe->k_map;
     if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no projection kernel was built for this pipe");
     p.stages = pipe->mapt_stages;

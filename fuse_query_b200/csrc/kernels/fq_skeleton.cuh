@@ -55,7 +55,8 @@ typedef signed char fq_i8;
 #define FQ_GB_THREADS 256    // GROUP BY kernel
 #define FQ_GB_MIN_BLOCKS 2
 #define FQ_GB_UNROLL 4
-#define FQ_GB_SMEM_PROBES 4  // linear probes in the CTA's shared-memory table before a row goes to the table in HBM
+#define FQ_GB_SMEM_PROBES 32 // linear probes in the CTA's shared-memory table before a row goes to the table in HBM: a key that
+                             // misses here sends ALL its rows to one address in HBM (k = 1000 with 4 probes: 46 GB of atomic traffic)
 #endif
 #ifndef FQ_SELT_THREADS
 #define FQ_SELT_THREADS 512  // staged select kernel, sparse-tuned build: consumer threads (+32 scan warp, +32 producer warp)
@@ -98,6 +99,7 @@ struct fq_launch_params {
   fq_u32 stages2;        // staged select kernel: != 0 when pass 2 of dense segments is staged too (slots hold every referenced column)
   const fq_u32 *sel_mode; // null, or which build of the staged select kernel runs: 0 sparse-tuned, 1 dense-tuned (written by the probe)
   fq_u32 *probe;          // density probe: [0] rows sampled, [1] rows kept, [2] = the mode it decided
+  fq_u32 bits_unstaged;  // a validity bitmap starts off the 128-row grid: the host launches the LDG variant (no bulk copies)
   fq_u32 unaligned;      // some input column (a slice) does not start on a 16-byte boundary: no vector / bulk loads, every row by fq_ld1
   // multi-GPU merge point fused into the aggregate kernel (fq_group, include/fuse_gpu.h): after the fold the last CTA
   // stores the running state into its row of EVERY rank's exchange window (peer GPUs' memory over NVLink), waits until
@@ -754,6 +756,23 @@ __device__ __forceinline__ void fq_lds_vec(T (&dst)[V], const unsigned char *col
   }
 }
 
+// V consecutive validity bits of a staged bitmap (tile-relative bit = group * V)
+template <int V> __device__ __forceinline__ void fq_lds_bits(bool (&dst)[V], const unsigned char *bits, fq_u32 group) {
+  const fq_u32 bit = group * V;
+  if constexpr (V <= 8) {
+    const fq_u32 w = (fq_u32)bits[bit >> 3] >> (bit & 7);
+#pragma unroll
+    for (int v = 0; v < V; v++) dst[v] = (w >> v) & 1u;
+  } else {
+#pragma unroll
+    for (int b = 0; b < V / 8; b++) {
+      const fq_u32 w = bits[(bit >> 3) + b];
+#pragma unroll
+      for (int v = 0; v < 8; v++) dst[8 * b + v] = (w >> v) & 1u;
+    }
+  }
+}
+
 template <class Q, int U, int STAGES>
 __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
   constexpr int V = Q::V;
@@ -769,7 +788,7 @@ __device__ __forceinline__ void fq_agg_tma_kernel(const fq_launch_params &p) {
   const bool is_producer = (int)threadIdx.x >= cthreads;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 stage_bytes = Q::stage_bytes((fq_u32)tile_rows);
   const fq_u64 n_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // full tiles only (none when a column is an unaligned slice)
   const int stages = (int)p.stages;
 
@@ -1490,7 +1509,7 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
   const bool stage2 = STAGE2 && p.stages2 != 0;
   // one slot holds a pass-1 tile (the predicate's columns) or, with the staged pass 2, a tile of every referenced column
-  const fq_u32 pred_bytes = (fq_u32)tile_rows * Q::PRED_ROW_BYTES, all_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 pred_bytes = Q::pred_stage_bytes((fq_u32)tile_rows), all_bytes = Q::stage_bytes((fq_u32)tile_rows);
   const fq_u32 stage_bytes = stage2 ? all_bytes : pred_bytes;
   const fq_u64 n_full_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;   // staged tiles; the others go through fq_tile_load
   const fq_u64 n_seg = p.n_tiles;
@@ -1954,7 +1973,7 @@ __device__ __forceinline__ void fq_map_tma_kernel(const fq_launch_params &p) {
   const bool is_producer = (int)threadIdx.x >= cthreads;
   const fq_u32 tile_groups = (fq_u32)cthreads * U;
   const fq_u64 tile_rows = (fq_u64)tile_groups * V;
-  const fq_u32 stage_bytes = (fq_u32)tile_rows * Q::ROW_BYTES;
+  const fq_u32 stage_bytes = Q::stage_bytes((fq_u32)tile_rows);
   const fq_u64 n_tiles = p.unaligned ? 0 : p.n_rows / tile_rows;
   const int stages = (int)p.stages;
   fq_u32 err = 0;
