@@ -196,11 +196,12 @@ impl Column {
             check(ctx.raw, unsafe { sys::fq_column_upload(ctx.raw, col.raw, 0, bytes as *const c_void, len, stream) })?;
         }
         if let Some(bitmap) = data.null_bitmap() {
-            let v = Column::alloc(ctx, sys::FQ_BOOL, len)?;
-            check(ctx.raw, unsafe {
-                sys::fq_column_upload_bits(ctx.raw, v.raw, 0, bitmap.buffer_ref().raw_data() as *const c_void, data.offset() as u64, len, stream)
-            })?;
-            check(ctx.raw, unsafe { sys::fq_column_set_validity(ctx.raw, col.raw, v.raw) })?;
+            // arrow's validity buffer goes over as it is and STAYS bit-packed: pipes compiled with col_nullable = 2 read the
+            // bits in place (1 bit of validity traffic per row); the array offset becomes the bit offset
+            let bytes = bitmap.buffer_ref().len() as u64;
+            let v = Column::alloc(ctx, sys::FQ_U8, bytes)?;
+            check(ctx.raw, unsafe { sys::fq_column_upload(ctx.raw, v.raw, 0, bitmap.buffer_ref().raw_data() as *const c_void, bytes, stream) })?;
+            check(ctx.raw, unsafe { sys::fq_column_set_validity_bitmap(ctx.raw, col.raw, v.raw, data.offset() as u64) })?;
             col.validity = Some(Box::new(v));
         }
         ctx.synchronize(stream)?;

@@ -56,7 +56,7 @@ impl Lowering {
         let field = schema.field(bi);
         self.block_cols.push(bi);
         self.col_dtypes.push(dtype_tag(field.data_type())?);
-        self.col_nullable.push(field.is_nullable() as i32);
+        self.col_nullable.push(if field.is_nullable() { 2 } else { 0 });   // 2: validity = arrow's bitmap, read in place
         Ok(self.block_cols.len() as i32 - 1)
     }
 
