@@ -736,18 +736,26 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       if (leaf_counted[k]) s += fmt("    st[%d] = (fq_u64)__popc(__ballot_sync(peers, (vmask >> %d) & 1u) & peers);\n", 1 + out->agg_count_slot[k], k);
     }
     s += "  }\n";
-    // a group state into a group of a table: atomics on generic addresses (shared memory or HBM)
-    {
-      s += "  __device__ static __forceinline__ void gb_merge(fq_u64 *slots, const fq_u64 *src) {\n"
-           "    atomicAdd((unsigned long long *)slots, (unsigned long long)src[0]);\n";
+    // a group state into a group of a table.  gb_merge: the table in HBM (native 64-bit ATOMG).  gb_merge_s: the CTA's table
+    // in shared memory — sm_100a has no 64-bit shared-memory atomics (the compiler emits ATOMS.CAST.SPIN loops, which under
+    // contention cost hundreds of instructions per row), so counts and wrapping integer sums go through native 32-bit
+    // atomics: low word first, and whoever sees it wrap carries one into the high word (exact mod 2^64 in any order).
+    for (int pass = 0; pass < 2; pass++) {
+      const bool shared = pass == 1;
+      s += shared ? "  __device__ static __forceinline__ void gb_merge_s(fq_u64 *slots, const fq_u64 *src) {\n"
+                  : "  __device__ static __forceinline__ void gb_merge(fq_u64 *slots, const fq_u64 *src) {\n";
+      auto add64 = [&](int slot, const std::string &x) {
+        return shared ? fmt("fq_atom_add64_s(slots + %d, %s);", slot, x.c_str())
+                      : fmt("atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)%s);", slot, x.c_str());
+      };
+      s += "    " + add64(0, "src[0]") + "\n";
       for (int k = 0; k < n; k++) {
         const int op = out->agg_ops[k];
         if (op == FQ_AGG_COUNT) continue;
         const std::string x = fmt("src[%d]", 1 + k);
         std::string stmt;
         if (op == FQ_AGG_SUM) {
-          stmt = is_f(k) ? fmt("atomicAdd((double *)(slots + %d), __longlong_as_double((fq_i64)%s));", 1 + k, x.c_str())
-                         : fmt("atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)%s);", 1 + k, x.c_str());
+          stmt = is_f(k) ? fmt("atomicAdd((double *)(slots + %d), __longlong_as_double((fq_i64)%s));", 1 + k, x.c_str()) : add64(1 + k, x);
         } else {
           // after the first rows of a group a new minimum / maximum is rare: look before paying for the atomic
           const char *f = op == FQ_AGG_MIN ? "atomicMin" : "atomicMax";
@@ -759,7 +767,7 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
         }
         if (leaf_counted[k]) {
           const int cs = 1 + out->agg_count_slot[k];
-          s += fmt("    if (src[%d]) { %s atomicAdd((unsigned long long *)(slots + %d), (unsigned long long)src[%d]); }\n", cs, stmt.c_str(), cs, cs);
+          s += fmt("    if (src[%d]) { %s %s }\n", cs, stmt.c_str(), add64(cs, fmt("src[%d]", cs)).c_str());
         } else {
           s += "    " + stmt + "\n";
         }

@@ -1798,6 +1798,18 @@ __device__ __forceinline__ fq_u64 fq_redux_addf64(fq_u32 mask, fq_u64 bits) {
   return (fq_u64)__double_as_longlong(acc);
 }
 
+// wrapping 64-bit add on a shared-memory slot with two native 32-bit atomics (low word, then the carry into the high word)
+__device__ __forceinline__ void fq_atom_add64_s(fq_u64 *slot, fq_u64 x) {
+  fq_u32 *w = (fq_u32 *)slot;
+  const fq_u32 lo = (fq_u32)x, hi = (fq_u32)(x >> 32);
+  fq_u32 carry = 0;
+  if (lo) {
+    const fq_u32 old = atomicAdd(w, lo);
+    carry = (old + lo < old) ? 1u : 0u;
+  }
+  if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
 // one group state (Q::G slots: rows, leaves, valid counts) into the CTA's shared-memory table or the table in HBM.
 // Finding the slot and updating it are kept apart: the probe loop diverges (lanes find their keys at different depths)
 // and everything inside it is executed once per distinct trip count — with the five atomics inside, ncu counted 230
@@ -1824,7 +1836,7 @@ __device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *ske
   }
   fq_i64 slot = -1;
   if (!in_smem) slot = fq_gb_find(p, key, h);
-  if (in_smem) Q::gb_merge(sslots + (size_t)i * Q::G, st);
+  if (in_smem) Q::gb_merge_s(sslots + (size_t)i * Q::G, st);
   else if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, st);
 }
 
