@@ -71,7 +71,7 @@ EXPORTS = [
     "fq_column_alloc", "fq_column_wrap", "fq_column_slice", "fq_column_set_validity", "fq_column_validity", "fq_column_free",
     "fq_column_upload_bits", "fq_column_download_bits",
     "fq_group_create", "fq_group_handle", "fq_group_window", "fq_group_connect", "fq_group_connect_ptrs", "fq_group_destroy",
-    "fq_pipe_set_group", "fq_pipe_fetch_merged", "fq_group_gather_project", "fq_group_fetch_gather", "fq_pipe_set_variant",
+    "fq_pipe_set_group", "fq_pipe_fetch_merged", "fq_group_gather_project", "fq_group_gather_columns", "fq_group_fetch_gather", "fq_pipe_set_variant",
     "fq_column_dtype", "fq_column_len",
     "fq_column_device_ptr", "fq_column_upload", "fq_column_download", "fq_stream_synchronize", "fq_host_alloc",
     "fq_host_free", "fq_numbers_fill", "fq_pipe_compile", "fq_pipe_destroy", "fq_pipe_is_precompiled", "fq_pipe_build_kind", "fq_pipe_source",
@@ -117,6 +117,7 @@ def lib():
         "fq_pipe_set_group": (i32, [vp, vp, vp]),
         "fq_pipe_fetch_merged": (i32, [vp, vp, C.POINTER(CValue), i32, C.POINTER(i32), C.POINTER(u64)]),
         "fq_group_gather_project": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64, vp]),
+        "fq_group_gather_columns": (i32, [vp, vp, C.POINTER(vp), C.POINTER(vp), i32, u64, u64, u64, C.POINTER(vp), C.POINTER(vp), i64, vp]),
         "fq_group_fetch_gather": (i32, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
         "fq_pipe_set_variant": (i32, [vp, vp, C.c_char_p]),
         "fq_column_upload_bits": (i32, [vp, vp, u64, vp, u64, u64, vp]),

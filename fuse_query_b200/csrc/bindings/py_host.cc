@@ -157,6 +157,23 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def_property_readonly("device", &GpuContext::device)
       .def("set_stream", [](GpuContext &g, uintptr_t s) { g.stream = (void *)s; });
 
+  py::class_<GpuGroup, std::shared_ptr<GpuGroup>>(m, "GpuGroup")
+      .def(py::init([](GpuContextRef gpu, int rank, int world, uint64_t row_bytes) { return std::make_shared<GpuGroup>(gpu, rank, world, row_bytes); }),
+           py::arg("gpu"), py::arg("rank"), py::arg("world"), py::arg("row_bytes") = 1u << 16)
+      .def("handle", [](const GpuGroup &g) { return py::bytes(g.handle()); })
+      .def("connect", [](GpuGroup &g, const std::vector<py::bytes> &hs) {
+        std::vector<std::string> v;
+        for (const auto &h : hs) v.push_back(std::string(h));
+        g.connect(v);
+      })
+      .def("gather", [](GpuGroup &g, const std::vector<DataArrayRef> &cols, const std::vector<int> &types, uint64_t rows, uint64_t selected,
+                        uint64_t capacity, int64_t limit) {
+        std::vector<DataType> t(types.begin(), types.end());
+        return g.gather(cols, t, rows, selected, capacity, limit);
+      })
+      .def_property_readonly("rank", &GpuGroup::rank)
+      .def_property_readonly("world", &GpuGroup::world);
+
   py::class_<DataArray, DataArrayRef>(m, "DataArray")
       .def_static("from_numpy", [](GpuContextRef gpu, py::array a) {
         py::array c = py::array::ensure(a, py::array::c_style);

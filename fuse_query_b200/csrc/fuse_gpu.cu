@@ -1193,6 +1193,8 @@ struct fq_gather_params {
   fq_u32 elem[2 * FQ_MAX_EXPRS];
   fq_u32 col_slot[2 * FQ_MAX_EXPRS];   // first slot of column c inside a row's payload
   fq_u32 n_cols;
+  fq_u64 local_selected, local_rows;   // used instead of local_result when use_imm != 0 (columns of any producer)
+  fq_u32 use_imm;
   const fq_u64 *local_result;  // the projection launch's result block: [0] rows selected, [1] error bits
   fq_u64 cap_local;            // rows the local launch may have written
   fq_u64 limit;                // final rows = min(limit, sum of written)
@@ -1202,8 +1204,8 @@ __global__ void __launch_bounds__(256) fq_group_gather_rows(const __grid_constan
   const fq_launch_params &p = a.g;
   __shared__ fq_u64 s_off[9], s_take[8], s_sel, s_err;
   __shared__ int s_ok;
-  const fq_u64 selected = a.local_result[0];
-  const fq_u64 written = selected < a.cap_local ? selected : a.cap_local;
+  const fq_u64 selected = a.use_imm ? a.local_selected : a.local_result[0];
+  const fq_u64 written = a.use_imm ? a.local_rows : (selected < a.cap_local ? selected : a.cap_local);
   // payload into every rank's window: 8-byte words (columns are 256-byte padded, rows 8-byte slotted)
   for (fq_u32 r = 0; r < p.group_world; r++) {
     fq_u64 *row = fq_group_row(p, (int)r, (int)p.group_rank);
@@ -1220,7 +1222,7 @@ __global__ void __launch_bounds__(256) fq_group_gather_rows(const __grid_constan
     fq_u64 *row = fq_group_row(p, (int)threadIdx.x, (int)p.group_rank);
     row[1] = selected;
     row[2] = written;
-    row[3] = a.local_result[1];
+    row[3] = a.use_imm ? 0ull : a.local_result[1];
     __threadfence_system();
     fq_st_release_sys(row, p.group_epoch);
   }
@@ -1303,6 +1305,53 @@ fq_status fq_group_gather_project(fq_ctx *ctx, fq_group *g, fq_pipe *pipe, fq_co
   bind_group(g, &a.g);
   a.local_result = (const fq_u64 *)pipe->d_ctl;
   a.cap_local = cap;
+  a.limit = lim;
+  a.out_result = (fq_u64 *)g->d_result;
+  fq_group_gather_rows<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  CUDA_TRY(cudaMemcpyAsync(g->h_result, g->d_result, 24, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventRecord(g->ev, (cudaStream_t)stream));
+  g->gathered = true;
+  return FQ_OK;
+}
+fq_status fq_group_gather_columns(fq_ctx *ctx, fq_group *g, const fq_column *const *local_cols, const fq_column *const *local_valid,
+                                  int32_t n_cols, uint64_t rows_local, uint64_t rows_selected_local, uint64_t capacity,
+                                  fq_column *const *final_cols, fq_column *const *final_valid, int64_t limit, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!g || !local_cols || !final_cols || n_cols < 1 || n_cols > FQ_MAX_EXPRS) return set_err(FQ_ERR_INVALID, "Internal Error: gather needs a group and 1..8 columns");
+  if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is not connected to its peers");
+  if (rows_local > capacity) return set_err(FQ_ERR_INVALID, "Internal Error: more local rows than the capacity every rank agreed on");
+  fq_gather_params a;
+  memset(&a, 0, sizeof a);
+  const uint64_t lim = limit < 0 ? capacity * (uint64_t)g->world : (uint64_t)limit;
+  uint64_t slot = 4;
+  for (int e = 0; e < n_cols; e++) {
+    for (int v = 0; v < 2; v++) {
+      const fq_column *lc = v ? (local_valid ? local_valid[e] : nullptr) : local_cols[e];
+      const fq_column *fc = v ? (final_valid ? final_valid[e] : nullptr) : final_cols[e];
+      if (v == 1 && !fc) continue;    // this column has no validity (every rank must agree)
+      if (!fc || (rows_local && !lc) || (lc && lc->dtype != fc->dtype) || (v == 1 && fc->dtype != FQ_BOOL))
+        return set_err(FQ_ERR_INVALID, "Internal Error: gather column %d%s missing or of the wrong type", e, v ? " (validity)" : "");
+      if ((lc && lc->len < rows_local) || fc->len < std::min<uint64_t>(lim, capacity * (uint64_t)g->world))
+        return set_err(FQ_ERR_INVALID, "Internal Error: gather column %d is shorter than the rows it may receive", e);
+      const uint32_t w = (uint32_t)fq::dtype_size(fc->dtype);
+      const int c = (int)a.n_cols++;
+      a.src[c] = lc ? lc->ptr : fc->ptr;   // (no local rows: never read)
+      a.dst[c] = fc->ptr;
+      a.elem[c] = w;
+      a.col_slot[c] = (fq_u32)slot;
+      slot += (capacity * w + 7) / 8;
+    }
+  }
+  if (slot > g->row_slots)
+    return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: %" PRIu64 " rows per rank do not fit the group's %u-byte rows", capacity,
+                   g->row_slots * 8u);
+  bind_group(g, &a.g);
+  a.use_imm = 1;
+  a.local_selected = rows_selected_local;
+  a.local_rows = rows_local;
+  a.cap_local = capacity;
   a.limit = lim;
   a.out_result = (fq_u64 *)g->d_result;
   fq_group_gather_rows<<<1, 256, 0, (cudaStream_t)stream>>>(a);

@@ -548,4 +548,45 @@ DataArrayRef DataColumnarValue::to_array(GpuContextRef ctx, uint64_t size) const
   return DataArray::from_host(std::move(ctx), scalar.tag, host.data(), size);
 }
 
+// ---------------------------------------------------------------------------------------------
+// GpuGroup
+// ---------------------------------------------------------------------------------------------
+GpuGroup::GpuGroup(GpuContextRef gpu, int rank, int world, uint64_t row_bytes) : gpu_(std::move(gpu)), rank_(rank), world_(world) {
+  gpu_->check(fq_group_create(gpu_->raw(), rank, world, row_bytes, &raw_));
+}
+GpuGroup::~GpuGroup() { fq_group_destroy(gpu_->raw(), raw_); }
+std::string GpuGroup::handle() const {
+  std::string h(64, '\0');
+  gpu_->check(fq_group_handle(gpu_->raw(), raw_, &h[0]));
+  return h;
+}
+void GpuGroup::connect(const std::vector<std::string> &handles) {
+  if ((int)handles.size() != world_) throw FuseQueryError::internal("group of " + std::to_string(world_) + " ranks got " + std::to_string(handles.size()) + " handles");
+  std::string blob;
+  for (const auto &h : handles) {
+    std::string x = h;
+    x.resize(64, '\0');
+    blob += x;
+  }
+  gpu_->check(fq_group_connect(gpu_->raw(), raw_, blob.data()));
+}
+std::pair<std::vector<DataArrayRef>, uint64_t> GpuGroup::gather(const std::vector<DataArrayRef> &cols, const std::vector<DataType> &types, uint64_t rows,
+                                                                uint64_t selected_local, uint64_t capacity, int64_t limit) {
+  const uint64_t out_rows = limit >= 0 ? std::min<uint64_t>((uint64_t)limit, capacity * (uint64_t)world_) : capacity * (uint64_t)world_;
+  std::vector<DataArrayRef> finals;
+  std::vector<const fq_column *> lc;
+  std::vector<fq_column *> fc;
+  for (size_t i = 0; i < types.size(); i++) {
+    finals.push_back(DataArray::alloc(gpu_, types[i], std::max<uint64_t>(out_rows, 1)));
+    fc.push_back(finals.back()->column());
+    lc.push_back(i < cols.size() && cols[i] ? cols[i]->column() : nullptr);
+  }
+  gpu_->check(fq_group_gather_columns(gpu_->raw(), raw_, lc.data(), nullptr, (int32_t)types.size(), rows, selected_local, capacity, fc.data(), nullptr,
+                                      limit, gpu_->stream));
+  uint64_t selected = 0, n = 0;
+  gpu_->check(fq_group_fetch_gather(gpu_->raw(), raw_, &selected, &n));
+  for (auto &a : finals) a = a->slice(0, n);
+  return {finals, selected};
+}
+
 }  // namespace fuse

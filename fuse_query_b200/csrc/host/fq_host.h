@@ -190,6 +190,29 @@ class GpuContext : public std::enable_shared_from_this<GpuContext> {
   int device_ = 0;
 };
 
+// The merge point across GPUs (processors/processor_merge.rs:37-66) for rows: every rank's blocks meet, in rank order, on the
+// device (fq_group).  One process per GPU; `handle` travels to the peers by whatever the deployment has.
+class GpuGroup {
+ public:
+  GpuGroup(GpuContextRef gpu, int rank, int world, uint64_t row_bytes);
+  ~GpuGroup();
+  GpuGroup(const GpuGroup &) = delete;
+  GpuGroup &operator=(const GpuGroup &) = delete;
+  std::string handle() const;                             // 64 bytes
+  void connect(const std::vector<std::string> &handles);  // handles[r] = rank r's
+  // every rank's columns (same types, `rows` local rows, at most `capacity` on any rank) concatenated in rank order and cut at
+  // `limit` (-1: none) -> (columns, rows selected by all ranks as reported in `selected_local`)
+  std::pair<std::vector<DataArrayRef>, uint64_t> gather(const std::vector<DataArrayRef> &cols, const std::vector<DataType> &types, uint64_t rows,
+                                                        uint64_t selected_local, uint64_t capacity, int64_t limit);
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+
+ private:
+  GpuContextRef gpu_;
+  fq_group *raw_ = nullptr;
+  int rank_, world_;
+};
+
 // ---------------------------------------------------------------------------------------------
 // functions — enum Function (functions/function.rs:16-146)
 // ---------------------------------------------------------------------------------------------

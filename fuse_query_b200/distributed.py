@@ -21,9 +21,10 @@ def _my_partitions(parts: list, rank: int, world: int) -> list:
     return parts[rank * per:(rank + 1) * per] if rank < world - 1 else parts[rank * per:]
 
 
-def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_object) -> Tuple[List[str], List[tuple]]:
+def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_object, gpu=None) -> Tuple[List[str], List[tuple]]:
     """Returns (column names, rows) on every rank.  `all_gather_object(obj) -> list` is the collective
-    (torch.distributed.all_gather_object bound to a group)."""
+    (torch.distributed.all_gather_object bound to a group).  With `gpu` (the rank's GpuContext) the rows of a LIMIT query
+    meet on the device (fq_group) instead of travelling through the host."""
     plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, sql))
     plans = plan.children_to_plans()
     src = plans[0]
@@ -63,6 +64,27 @@ def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_obj
         if limit is not None:
             rows = rows[:limit]
         return names, rows
+    n_cols = len(names)
+    if limit is not None and gpu is not None and world > 1:
+        # MergeProcessor + the LimitTransform after it (processor_merge.rs:37-66, pipeline_builder.rs:31-41) on the device: every
+        # rank's rows meet in every rank's exchange window over peer memory and the first `limit` rows, in rank (= partition)
+        # order, are copied out — nothing but the 64-byte window handles ever crosses the host.
+        group = _group_for(gpu, rank, world, all_gather_object)
+        cols = [None] * n_cols
+        rows_local = 0
+        if local_blocks:                       # a fused pipe with a LIMIT yields at most `limit` rows, usually in one block
+            merged = [b for b in local_blocks if b.num_rows() > 0]
+            if len(merged) > 1:                # several runs of partitions: concatenate on the host side of this rank only
+                mine = [np.concatenate([b.column(c).to_numpy() for b in merged])[:limit] for c in range(n_cols)]
+                cols = [h.DataArray.from_numpy(gpu, a) for a in mine]
+                rows_local = len(mine[0])
+            elif merged:
+                rows_local = min(merged[0].num_rows(), limit)
+                cols = [merged[0].column(c).slice(0, rows_local) for c in range(n_cols)]
+        types = [f.data_type for f in sel.schema().fields]
+        finals, _selected = group.gather(cols, types, rows_local, rows_local, max(limit, 1), limit)
+        rows = list(zip(*[a.to_list() for a in finals])) if finals and len(finals[0]) else []
+        return names, rows
     mine = [[b.column(c).to_numpy() for c in range(b.num_columns())] for b in local_blocks]
     gathered = all_gather_object(mine)
     rows: List[tuple] = []
@@ -72,3 +94,16 @@ def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_obj
     if limit is not None:                                               # LimitTransform x 1 after the merge
         rows = rows[:limit]
     return names, rows
+
+
+_GROUPS = {}
+
+
+def _group_for(gpu, rank: int, world: int, all_gather_object):
+    """One exchange window per (device context, world): created on first use, handles exchanged once."""
+    key = (id(gpu), rank, world)
+    if key not in _GROUPS:
+        g = h.GpuGroup(gpu, rank, world, 1 << 20)
+        g.connect(all_gather_object(g.handle()))
+        _GROUPS[key] = g
+    return _GROUPS[key]

@@ -342,6 +342,11 @@ fq_status fq_pipe_fetch_merged(fq_ctx *ctx, fq_pipe *pipe, fq_value *states, int
 fq_status fq_group_gather_project(fq_ctx *ctx, fq_group *group, fq_pipe *pipe, fq_column *const *local_cols,
                                   fq_column *const *local_valid, fq_column *const *final_cols, fq_column *const *final_valid,
                                   int64_t limit, void *stream);
+/* the same for columns the caller already holds (any producer): `rows_local` rows of `local_cols` (and `local_valid`, entries
+ * may be NULL), `capacity` = the most rows any rank brings (the same value on every rank: it fixes the window layout) */
+fq_status fq_group_gather_columns(fq_ctx *ctx, fq_group *group, const fq_column *const *local_cols, const fq_column *const *local_valid,
+                                  int32_t n_cols, uint64_t rows_local, uint64_t rows_selected_local, uint64_t capacity,
+                                  fq_column *const *final_cols, fq_column *const *final_valid, int64_t limit, void *stream);
 fq_status fq_group_fetch_gather(fq_ctx *ctx, fq_group *group, uint64_t *rows_selected, uint64_t *rows_final);
 
 /* ---- projection pipes: filter_record_batch + projection (+ LimitStream) in one pass ----

@@ -335,14 +335,17 @@ def _dist_worker(rank, world, port, sqls, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fuse_query_b200 import _fuse_host as hh
     from fuse_query_b200.distributed import execute_sql_distributed
-    ctx = hh.FuseQueryContext.create_ctx(1, hh.GpuContext.create(0))
+    gpu = hh.GpuContext.create(0)
+    ctx = hh.FuseQueryContext.create_ctx(1, gpu)
 
     def gather(obj):
         res = [None] * world
         dist.all_gather_object(res, obj)
         return res
 
-    results = [execute_sql_distributed(ctx, s, rank, world, gather) for s in sqls]
+    # with `gpu` the rows of LIMIT queries meet in the ranks' exchange windows on the device (two processes, one GPU here: CUDA IPC)
+    results = [execute_sql_distributed(ctx, s, rank, world, gather, gpu=gpu) for s in sqls]
+    results += [execute_sql_distributed(ctx, s, rank, world, gather) for s in sqls[1:2]]      # the host path, for comparison
     if rank == 0:
         out.put(results)
     dist.barrier()
@@ -355,7 +358,8 @@ def test_two_rank_distributed_sql(gpu):
     n = 16_000_000
     sqls = [f"select sum(number)/count(number), max(number), min(number) from system.numbers_mt({n})",
             f"select (number+1) as c1, number/2 as c2 from system.numbers_mt({n}) where (c1+c2+1) < 100 limit 3",
-            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number"]
+            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number",
+            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number limit 5"]
     mpctx = mp.get_context("spawn")
     q = mpctx.Queue()
     port = 29800 + (os.getpid() % 150)
@@ -370,6 +374,7 @@ def test_two_rank_distributed_sql(gpu):
     assert got[0] == (["Sum(number) / Count(number)", "Max(number)", "Min(number)"], [(s // n, n - 1, 0)])
     assert got[1] == (["c1", "c2"], [(1, 0), (2, 0), (3, 1)])
     assert got[2] == (["number"], [(k * 1000000,) for k in range(16)])
+    assert got[3] == (["number"], [(k * 1000000,) for k in range(5)]) and got[4] == got[1]
 
 
 # ---------------------------------------------------------------------------------------------
