@@ -55,7 +55,6 @@ typedef signed char fq_i8;
 #define FQ_GB_THREADS 256    // GROUP BY kernel
 #define FQ_GB_MIN_BLOCKS 2
 #define FQ_GB_UNROLL 4
-#define FQ_GB_SMEM_PROBES 8  // linear probes in the CTA's shared-memory table before a row goes to the table in HBM
 #endif
 #ifndef FQ_SELT_THREADS
 #define FQ_SELT_THREADS 512  // staged select kernel, sparse-tuned build: consumer threads (+32 scan warp, +32 producer warp)
@@ -1816,20 +1815,29 @@ __device__ __forceinline__ void fq_atom_add64_s(fq_u64 *slot, fq_u64 x) {
 // (k = 7) to 735 (k = 1000) warp instructions per 32 rows.  The loop now only looks; the warp reconverges and issues the
 // atomics once, ATOMS for the lanes that found room in shared memory and ATOMG for the others.
 template <class Q>
-__device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u64 key, const fq_u64 *st, int &smem_try) {
+__device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used, fq_u64 key, const fq_u64 *st,
+                                          int &smem_try) {
   const fq_u64 h = fq_gb_hash(key);
   bool in_smem = false;
   fq_u32 i = 0;
-  // smem_try: the thread's patience with the shared-memory table — once its keys have found no room there 64 times (a
-  // cardinality far beyond the table) it goes to HBM directly instead of probing eight full slots first
+  // The shared-memory table is searched like any linear-probing table: until the key or a free slot turns up.  A key that
+  // fits there must NEVER be sent to HBM: all its rows would hit one L2 line (measured: one such key among 1000 costs 40 ms
+  // per 1e9 rows).  New keys are admitted until the table is 3/4 full (s_used), which keeps the searches short; after that
+  // unknown keys go to HBM.  smem_try is the thread's patience: after 64 misses in a row (a cardinality far beyond the
+  // table) it stops looking here at all.
   if (p.gb_smem_cap && key != FQ_GB_EMPTY && smem_try > 0) {
     const fq_u32 smask = p.gb_smem_cap - 1;
     i = (fq_u32)(h >> 32) & smask;
 #pragma unroll 1
-    for (int probe = 0; probe < FQ_GB_SMEM_PROBES; probe++) {
+    for (fq_u32 probe = 0; probe < p.gb_smem_cap; probe++) {
       fq_u64 cur = *(volatile fq_u64 *)(skeys + i);
-      if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
-      if (cur == FQ_GB_EMPTY || cur == key) { in_smem = true; break; }
+      if (cur == key) { in_smem = true; break; }
+      if (cur == FQ_GB_EMPTY) {
+        if (*(volatile fq_u32 *)s_used >= p.gb_smem_cap - p.gb_smem_cap / 4) break;
+        cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
+        if (cur == FQ_GB_EMPTY) atomicAdd(s_used, 1u);
+        if (cur == FQ_GB_EMPTY || cur == key) { in_smem = true; break; }
+      }
       i = (i + 1) & smask;
     }
     smem_try = in_smem ? 64 : smem_try - 1;
@@ -1845,8 +1853,8 @@ __device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *ske
 // one per distinct key.  `agg` is the thread's running verdict on whether that pays (keys that never repeat inside a
 // warp only pay for the MATCH): after 32 rows without a single shared key the warp stops trying.
 template <class Q>
-__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, const typename Q::Rows &r, int v, fq_u32 &err,
-                                          int &agg, int &smem_try) {
+__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used, const typename Q::Rows &r, int v,
+                                          fq_u32 &err, int &agg, int &smem_try) {
   fq_u64 key, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
   fq_u32 vmask;
   if (!Q::gb_row(r, v, err, key, val, vmask)) return;
@@ -1858,12 +1866,12 @@ __device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *ske
     agg = shared ? 32 : agg - 1;
     if (peers & (peers - 1)) {
       Q::gb_fold(st, val, vmask, peers);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) fq_gb_put<Q>(p, skeys, sslots, key, st, smem_try);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) fq_gb_put<Q>(p, skeys, sslots, s_used, key, st, smem_try);
       return;
     }
   }
   Q::gb_one(st, val, vmask);
-  fq_gb_put<Q>(p, skeys, sslots, key, st, smem_try);
+  fq_gb_put<Q>(p, skeys, sslots, s_used, key, st, smem_try);
 }
 
 template <class Q, int UNROLL>
@@ -1872,6 +1880,8 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
   extern __shared__ __align__(128) unsigned char fq_dyn_smem[];
   fq_u64 *skeys = (fq_u64 *)fq_dyn_smem;
   fq_u64 *sslots = skeys + p.gb_smem_cap;
+  __shared__ fq_u32 s_used;   // keys admitted to the shared-memory table
+  if (threadIdx.x == 0) s_used = 0;
   for (fq_u32 i = threadIdx.x; i < p.gb_smem_cap; i += blockDim.x) {
     skeys[i] = FQ_GB_EMPTY;
     Q::gb_init(sslots + (size_t)i * Q::G);
@@ -1896,7 +1906,7 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, rows[u], v, err, agg, smem_try);
+      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, &s_used, rows[u], v, err, agg, smem_try);
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
@@ -1904,12 +1914,12 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
     typename Q::Rows r;
     Q::load(r, p, g);
 #pragma unroll
-    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, r, v, err, agg, smem_try);
+    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, &s_used, r, v, err, agg, smem_try);
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
-    fq_gb_row<Q>(p, skeys, sslots, r, 0, err, agg, smem_try);
+    fq_gb_row<Q>(p, skeys, sslots, &s_used, r, 0, err, agg, smem_try);
   }
   __syncthreads();
   // flush the CTA's groups into the table in HBM
