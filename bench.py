@@ -647,7 +647,7 @@ def group_by_table(rig: Rig, col):
     src = cabi.make_source([col], n)
     out = {}
     aggs = [f"(sum {NUM})", f"(count {NUM})", f"(min {NUM})", f"(max {NUM})"]
-    for k in (7, 1000, 1_000_000, 100_000_000):
+    for k in (7, 1000, 5000, 1_000_000, 100_000_000):
         key = f"(- {NUM} (* (/ {NUM} (u64 {k})) (u64 {k})))"
         pipe = ctx.pipe(aggs, keys=[key])
         owner = ctx.pipe(aggs, keys=[key]) if world > 1 else None

@@ -711,29 +711,11 @@ int generate(const fq_pipe_desc &d, Generated *out, std::string *err) {
       if (leaf_counted[k]) s += fmt("    slots[%d] = 0ull;\n", 1 + out->agg_count_slot[k]);
     }
     s += "  }\n";
-    // a row (gb_one) or the rows of the lanes of a match group (gb_fold) as a group state st[G]: rows, leaves, valid counts
+    // a row as a group state st[G]: rows, leaves, valid counts
     s += "  __device__ static __forceinline__ void gb_one(fq_u64 (&st)[G], const fq_u64 (&val)[NSLOTS > 0 ? NSLOTS : 1], fq_u32 vmask) {\n    st[0] = 1ull;\n";
     for (int k = 0; k < n; k++) {
       s += fmt("    st[%d] = val[%d];\n", 1 + k, k);
       if (leaf_counted[k]) s += fmt("    st[%d] = (vmask >> %d) & 1u;\n", 1 + out->agg_count_slot[k], k);
-    }
-    s += "  }\n";
-    s += "  __device__ static __forceinline__ void gb_fold(fq_u64 (&st)[G], const fq_u64 (&val)[NSLOTS > 0 ? NSLOTS : 1], fq_u32 vmask, fq_u32 peers) {\n"
-         "    st[0] = (fq_u64)__popc(peers);\n";
-    for (int k = 0; k < n; k++) {
-      const int op = out->agg_ops[k];
-      if (op == FQ_AGG_COUNT) { s += fmt("    st[%d] = 0ull;\n", 1 + k); continue; }
-      // a NULL argument contributes the identity
-      std::string idn = op == FQ_AGG_SUM ? "0ull" : op == FQ_AGG_MIN ? (is_s(k) ? "(fq_u64)9223372036854775807ll" : "~0ull")
-                                                                   : (is_s(k) ? "(fq_u64)(-9223372036854775807ll - 1)" : "0ull");
-      std::string x = leaf_counted[k] ? fmt("((vmask >> %d) & 1u ? val[%d] : %s)", k, k, idn.c_str()) : fmt("val[%d]", k);
-      std::string red;
-      if (op == FQ_AGG_SUM) red = is_f(k) ? "fq_redux_addf64(peers, " + x + ")" : "fq_redux_add64(peers, " + x + ")";
-      else if (is_s(k))   // signed order = unsigned order with the sign bit flipped
-        red = std::string(op == FQ_AGG_MIN ? "fq_redux_min64" : "fq_redux_max64") + "(peers, " + x + " ^ (1ull << 63)) ^ (1ull << 63)";
-      else red = std::string(op == FQ_AGG_MIN ? "fq_redux_min64" : "fq_redux_max64") + "(peers, " + x + ")";
-      s += fmt("    st[%d] = %s;\n", 1 + k, red.c_str());
-      if (leaf_counted[k]) s += fmt("    st[%d] = (fq_u64)__popc(__ballot_sync(peers, (vmask >> %d) & 1u) & peers);\n", 1 + out->agg_count_slot[k], k);
     }
     s += "  }\n";
     // a group state into a group of a table.  gb_merge: the table in HBM (native 64-bit ATOMG).  gb_merge_s: the CTA's table

@@ -245,6 +245,9 @@ struct fq_pipe {
   unsigned seld_stages = 0;
   // GROUP BY: the hash table in HBM
   uint64_t *gb_keys = nullptr, *gb_slots = nullptr;
+  uint64_t *gb_rep_keys = nullptr, *gb_rep_slots = nullptr;   // gb_reps - 1 more tables of gb_cap + 1 slots (see fq_groupby_kernel)
+  unsigned gb_reps = 1;
+  bool gb_reps_dirty = false;        // freshly allocated replicas: fill them once; afterwards the fold leaves them empty
   uint64_t gb_cap = 0;
   uint32_t *gb_flags = nullptr;      // [0] overflow, [1] EMPTY-valued key seen, [2..3] group count (u64), [4..5] error bits
   uint64_t *h_gb = nullptr;          // pinned mirror of gb_flags (4 x u64)
@@ -909,6 +912,8 @@ void fq_pipe_destroy(fq_ctx *ctx, fq_pipe *pipe) {
   cudaFree(pipe->d_merged);
   cudaFree(pipe->gb_keys);
   cudaFree(pipe->gb_slots);
+  cudaFree(pipe->gb_rep_keys);
+  cudaFree(pipe->gb_rep_slots);
   cudaFree(pipe->gb_flags);
   cudaFree(pipe->gb_identity);
   if (pipe->h_gb) cudaFreeHost(pipe->h_gb);
@@ -1654,6 +1659,14 @@ fq_status gb_clear(fq_ctx *ctx, fq_pipe *pipe, cudaStream_t s) {
   fq_gb_fill<<<grid, 256, 0, s>>>((fq_u64 *)pipe->gb_keys, (fq_u64 *)pipe->gb_slots, pipe->gb_cap + 1, G, (const fq_u64 *)pipe->gb_identity);
   CUDA_TRY(cudaGetLastError());
   ctx->launches++;
+  if (pipe->gb_reps > 1 && pipe->gb_reps_dirty) {
+    const uint64_t n = (pipe->gb_cap + 1) * (pipe->gb_reps - 1);
+    const unsigned g2 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    fq_gb_fill<<<g2, 256, 0, s>>>((fq_u64 *)pipe->gb_rep_keys, (fq_u64 *)pipe->gb_rep_slots, n, G, (const fq_u64 *)pipe->gb_identity);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    pipe->gb_reps_dirty = false;
+  }
   pipe->launched_groupby = false;
   return FQ_OK;
 }
@@ -1688,19 +1701,38 @@ fq_status fq_pipe_groupby_reserve(fq_ctx *ctx, fq_pipe *pipe, uint64_t groups) {
   uint64_t cap = 1024;
   while (cap < groups * 2 && cap < (1ull << 40)) cap *= 2;   // load factor <= 1/2
   const int G = 1 + pipe->gen.n_slots;
-  if (cap != pipe->gb_cap) {
+  // Replicas of a small table (CTA b aggregates into replica b % reps, folded into the table after the scan): as many as
+  // fit FQ_GB_REPLICA_BYTES (default 32 MB, a quarter of L2), at most 32.  A table beyond that budget has enough slots that
+  // the CTAs rarely meet on one line and stays single.
+  uint64_t budget = 32ull << 20;
+  unsigned max_reps = 32;
+  if (const char *e = getenv("FQ_GB_REPLICA_BYTES")) budget = strtoull(e, nullptr, 10);
+  if (const char *e = getenv("FQ_GB_REPLICAS")) max_reps = (unsigned)std::max(1, atoi(e));
+  unsigned reps = 1;
+  while (reps * 2 <= max_reps && (uint64_t)(reps * 2) * (cap + 1) * 8 * (1 + G) <= budget) reps *= 2;
+  if (cap != pipe->gb_cap || reps != pipe->gb_reps) {
     cudaFree(pipe->gb_keys);
     cudaFree(pipe->gb_slots);
-    pipe->gb_keys = pipe->gb_slots = nullptr;
+    cudaFree(pipe->gb_rep_keys);
+    cudaFree(pipe->gb_rep_slots);
+    pipe->gb_keys = pipe->gb_slots = pipe->gb_rep_keys = pipe->gb_rep_slots = nullptr;
     pipe->gb_cap = 0;
+    pipe->gb_reps = 1;
     cudaError_t e = cudaMalloc(&pipe->gb_keys, sizeof(uint64_t) * (cap + 1));
     if (e == cudaSuccess) e = cudaMalloc(&pipe->gb_slots, sizeof(uint64_t) * (cap + 1) * G);
+    if (e == cudaSuccess && reps > 1) e = cudaMalloc(&pipe->gb_rep_keys, sizeof(uint64_t) * (cap + 1) * (reps - 1));
+    if (e == cudaSuccess && reps > 1) e = cudaMalloc(&pipe->gb_rep_slots, sizeof(uint64_t) * (cap + 1) * G * (reps - 1));
     if (e != cudaSuccess) {
       cudaFree(pipe->gb_keys);
-      pipe->gb_keys = nullptr;
+      cudaFree(pipe->gb_slots);
+      cudaFree(pipe->gb_rep_keys);
+      cudaFree(pipe->gb_rep_slots);
+      pipe->gb_keys = pipe->gb_slots = pipe->gb_rep_keys = pipe->gb_rep_slots = nullptr;
       return set_err(FQ_ERR_CUDA, "CUDA error: %s (GROUP BY table of %" PRIu64 " slots)", cudaGetErrorString(e), cap);
     }
     pipe->gb_cap = cap;
+    pipe->gb_reps = reps;
+    pipe->gb_reps_dirty = true;
   }
   if (!pipe->gb_flags) {
     CUDA_TRY(cudaMalloc(&pipe->gb_flags, 64));
@@ -1744,6 +1776,9 @@ fq_status fq_pipe_launch_groupby(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
   p.gb_cap = pipe->gb_cap;
   p.gb_flags = (fq_u32 *)pipe->gb_flags;
   p.gb_smem_cap = pipe->gb_smem_cap;
+  p.gb_rep_keys = (fq_u64 *)pipe->gb_rep_keys;
+  p.gb_rep_slots = (fq_u64 *)pipe->gb_rep_slots;
+  p.gb_reps = pipe->gb_reps;
   p.result = (fq_u64 *)(pipe->gb_flags + 2);   // [0] = count (u64 at flags[2..3]), [1] = error bits (flags[4..5])
   const Kernel &k = pipe->k_groupby;
   if (!k.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no GROUP BY kernel was built for this pipe");
@@ -1751,7 +1786,18 @@ fq_status fq_pipe_launch_groupby(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     const uint64_t chunk_rows = (uint64_t)k.threads * FQ_GB_UNROLL * pipe->gen.vec;
     const uint64_t chunks = (src->n_rows + chunk_rows - 1) / chunk_rows;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count * k.blocks_per_sm, chunks));
+    if (grid < p.gb_reps) p.gb_reps = 1;   // a small scan: every CTA on the table itself, nothing to fold
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
+    if (p.gb_reps > 1) {
+      // fold the replicas into the table (and leave them empty): the merge kernel without an entry list
+      const Kernel &km = pipe->k_gbmerge;
+      if (!km.valid()) return set_err(FQ_ERR_INTERNAL, "Internal Error: no GROUP BY merge kernel was built for this pipe");
+      fq_launch_params q = p;
+      q.n_rows = (pipe->gb_cap + 1) * (uint64_t)(pipe->gb_reps - 1);
+      q.gb_entries = nullptr;
+      const unsigned g2 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((q.n_rows + 255) / 256, (uint64_t)ctx->sm_count * 8));
+      if (fq_status st = launch(ctx, km, g2, q, stream)) return st;
+    }
   }
   return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
 }

@@ -54,7 +54,12 @@ typedef signed char fq_i8;
 #ifndef FQ_GB_THREADS
 #define FQ_GB_THREADS 256    // GROUP BY kernel
 #define FQ_GB_MIN_BLOCKS 2
+#endif
+#ifndef FQ_GB_UNROLL
 #define FQ_GB_UNROLL 4
+#endif
+#ifndef FQ_GB_ADMIT_SHIFT
+#define FQ_GB_ADMIT_SHIFT 2  // the CTA's shared-memory table admits new keys until it is 1 - 2^-SHIFT full
 #endif
 #ifndef FQ_SELT_THREADS
 #define FQ_SELT_THREADS 512  // staged select kernel, sparse-tuned build: consumer threads (+32 scan warp, +32 producer warp)
@@ -118,6 +123,9 @@ struct fq_launch_params {
   fq_u32 *gb_flags;       // [0] != 0: the table overflowed (results void), [1] != 0: the EMPTY-valued key occurred
   fq_u32 gb_smem_cap;     // slots of the CTA's shared-memory table (a power of two, 0 = none)
   const fq_u64 *gb_entries;  // merge kernel: n_rows partial entries of 1 + Q::G slots each (packed key, state)
+  fq_u64 *gb_rep_keys;    // [gb_reps - 1][gb_cap + 1] replicas of the table: CTA b aggregates into replica b % gb_reps (0 = the
+  fq_u64 *gb_rep_slots;   // table itself), the merge kernel folds them into the table and leaves them empty again
+  fq_u32 gb_reps;         // >= 1
   // select / map
   void *outs[8];
   void *outs_valid[8];   // per select expression that can yield NULL: one byte per output row
@@ -1729,10 +1737,12 @@ __device__ __forceinline__ void fq_select_tma_kernel(const fq_launch_params &p) 
 // operator AggregatePlan{group_expr, aggr_expr} describes, with the aggregate protocol of function_aggregator.rs:57-100
 // applied per group.  Generated code (codegen.cc) supplies, per row, the 64-bit packed key and the encoded value of every
 // Aggregator leaf (Q::gb_row), and the atomics that fold a row / a partial state into a group's Q::G slots.
-// Two levels of open-addressing tables: every CTA aggregates into a table in shared memory first (gb_smem_cap slots,
-// FQ_GB_SMEM_PROBES linear probes) — with few distinct keys nothing but the final flush leaves the SM; a row whose key
-// finds no room there goes straight to the table in HBM (atomicCAS on the key, then atomics on the state).  At the end the
-// CTA flushes its shared-memory groups into the HBM table.  A table that runs full raises gb_flags[0]: the host reserves
+// Two levels of open-addressing tables: every CTA aggregates into a table in shared memory first (gb_smem_cap slots, new
+// keys admitted until it is 3/4 full) — with few distinct keys nothing but the final flush leaves the SM; a row whose key
+// is not admitted there goes straight to the table in HBM (atomicCAS on the key, then atomics on the state).  At the end
+// the CTA flushes its shared-memory groups into the HBM table.  Both searches keep the warp together (one probe step per
+// trip, the trip count is the warp's longest chain): the atomics that follow are issued once per warp, not once per chain
+// length.  A table that runs full raises gb_flags[0]: the host reserves
 // a bigger one and relaunches.  Algorithmic traffic: sizeof(row) read per row + the table.
 // ---------------------------------------------------------------------------------------------
 #define FQ_GB_EMPTY 0xffffffffffffffffull
@@ -1754,47 +1764,38 @@ __device__ __forceinline__ fq_u64 fq_gb_hash(fq_u64 k) {
   return k;
 }
 // slot of `key` in the HBM table (claimed on the spot when new); gb_cap for the key that equals the EMPTY mark; -1 = full
-__device__ __forceinline__ fq_i64 fq_gb_find(const fq_launch_params &p, fq_u64 key, fq_u64 h) {
-  if (key == FQ_GB_EMPTY) {
+// or not wanted.  Called by every lane that is active at the call site, `want` says which of them search.  The loop's exit
+// is a warp vote, so the lanes leave it together whatever their chain lengths: with an early `return slot` the compiler
+// threads each exit straight into the caller's atomics and they run once per distinct chain length (ncu: 25 instead of
+// 5 atomic instructions per 32 rows at 1000 keys).
+__device__ __forceinline__ fq_i64 fq_gb_find(const fq_launch_params &p, fq_u64 *tkeys, fq_u64 key, fq_u64 h, bool want) {
+  const fq_u32 warp = __activemask();
+  fq_i64 slot = -1;
+  if (want && key == FQ_GB_EMPTY) {
     if (*(volatile fq_u32 *)(p.gb_flags + 1) == 0) p.gb_flags[1] = 1u;
-    return (fq_i64)p.gb_cap;
+    slot = (fq_i64)p.gb_cap;
+    want = false;
   }
   const fq_u64 mask = p.gb_cap - 1;
-  const fq_u64 limit = p.gb_cap < 4096 ? p.gb_cap : 4096;   // a table that needs longer chains is as good as full
-  for (fq_u64 probe = 0; probe < limit; probe++) {
-    const fq_u64 i = (h + probe) & mask;
-    fq_u64 cur = fq_ld_volatile(p.gb_keys + i);
-    if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(p.gb_keys + i), FQ_GB_EMPTY, (unsigned long long)key);
-    if (cur == FQ_GB_EMPTY || cur == key) return (fq_i64)i;
+  const fq_u32 limit = p.gb_cap < 4096 ? (fq_u32)p.gb_cap : 4096u;   // a table that needs longer chains is as good as full
+  fq_u64 i = h & mask;
+  fq_u32 probe = 0;
+  while (__any_sync(warp, want)) {
+    if (want) {
+      fq_u64 cur = fq_ld_volatile(tkeys + i);
+      if (cur == FQ_GB_EMPTY) cur = atomicCAS((unsigned long long *)(tkeys + i), FQ_GB_EMPTY, (unsigned long long)key);
+      if (cur == FQ_GB_EMPTY || cur == key) {
+        slot = (fq_i64)i;
+        want = false;
+      } else if (++probe >= limit) {
+        if (*(volatile fq_u32 *)p.gb_flags == 0) p.gb_flags[0] = 1u;
+        want = false;
+      } else {
+        i = (i + 1) & mask;
+      }
+    }
   }
-  if (*(volatile fq_u32 *)p.gb_flags == 0) p.gb_flags[0] = 1u;
-  return -1;
-}
-
-// Folds over the lanes of `mask` (the lanes of a warp that hold the same key), with the warp-reduce unit (REDUX.SYNC, 32-bit):
-// a wrapping 64-bit sum as three pieces of at most 22 bits (32 lanes x 2^22 fits 32 bits, no carry is lost), 64-bit
-// min / max as the high words first and then the low words of the lanes that tie on the high word.
-__device__ __forceinline__ fq_u64 fq_redux_add64(fq_u32 mask, fq_u64 x) {
-  const fq_u32 a = __reduce_add_sync(mask, (fq_u32)(x & 0x3fffffu));
-  const fq_u32 b = __reduce_add_sync(mask, (fq_u32)((x >> 22) & 0x3fffffu));
-  const fq_u32 c = __reduce_add_sync(mask, (fq_u32)(x >> 44));
-  return (fq_u64)a + ((fq_u64)b << 22) + ((fq_u64)c << 44);
-}
-__device__ __forceinline__ fq_u64 fq_redux_max64(fq_u32 mask, fq_u64 x) {
-  const fq_u32 hi = __reduce_max_sync(mask, (fq_u32)(x >> 32));
-  const fq_u32 lo = __reduce_max_sync(mask, (fq_u32)(x >> 32) == hi ? (fq_u32)x : 0u);
-  return ((fq_u64)hi << 32) | lo;
-}
-__device__ __forceinline__ fq_u64 fq_redux_min64(fq_u32 mask, fq_u64 x) {
-  const fq_u32 hi = __reduce_min_sync(mask, (fq_u32)(x >> 32));
-  const fq_u32 lo = __reduce_min_sync(mask, (fq_u32)(x >> 32) == hi ? (fq_u32)x : 0xffffffffu);
-  return ((fq_u64)hi << 32) | lo;
-}
-// float sums have no REDUX: the lanes of the group are added in lane order (= row order inside the warp)
-__device__ __forceinline__ fq_u64 fq_redux_addf64(fq_u32 mask, fq_u64 bits) {
-  double acc = 0.0;
-  for (fq_u32 m = mask; m; m &= m - 1) acc += __longlong_as_double((fq_i64)__shfl_sync(mask, bits, __ffs(m) - 1));
-  return (fq_u64)__double_as_longlong(acc);
+  return slot;
 }
 
 // wrapping 64-bit add on a shared-memory slot with two native 32-bit atomics (low word, then the carry into the high word)
@@ -1809,69 +1810,71 @@ __device__ __forceinline__ void fq_atom_add64_s(fq_u64 *slot, fq_u64 x) {
   if (hi + carry) atomicAdd(w + 1, hi + carry);
 }
 
-// one group state (Q::G slots: rows, leaves, valid counts) into the CTA's shared-memory table or the table in HBM.
-// Finding the slot and updating it are kept apart: the probe loop diverges (lanes find their keys at different depths)
-// and everything inside it is executed once per distinct trip count — with the five atomics inside, ncu counted 230
-// (k = 7) to 735 (k = 1000) warp instructions per 32 rows.  The loop now only looks; the warp reconverges and issues the
-// atomics once, ATOMS for the lanes that found room in shared memory and ATOMG for the others.
+// one group state (Q::G slots: rows, leaves, valid counts) into the CTA's shared-memory table or the table in HBM; called by
+// every active lane, `live` says which of them hold a row.  Finding the slot and updating it are kept apart and the search
+// keeps the warp together (see fq_gb_find): the warp issues the atomics once, ATOMS for the lanes whose key lives in shared
+// memory and ATOMG for the others.
+//
+// The shared-memory table is searched like any linear-probing table: until the key or a free slot turns up.  A key that
+// fits there must NEVER be sent to HBM: all its rows would hit one L2 line (measured: one such key among 1000 costs 40 ms
+// per 1e9 rows).  New keys are admitted until the table is 3/4 full (s_used), which keeps the chains short; after that
+// unknown keys go to HBM.  smem_try is the lane's patience, +1 per hit and -1 per miss from 64: once fewer than half of
+// its rows find their key here, a lane stops looking (an unsuccessful search of a 3/4-full table costs more than the HBM
+// atomics it tries to avoid — 1e9 rows, 5000 keys: 53 ms with the search, 33 ms without).
 template <class Q>
-__device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used, fq_u64 key, const fq_u64 *st,
-                                          int &smem_try) {
+__device__ __forceinline__ void fq_gb_put(const fq_launch_params &p, fq_u64 *tkeys, fq_u64 *tslots, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used,
+                                          fq_u64 key, const fq_u64 *st, bool live, int &smem_try) {
+  const fq_u32 warp = __activemask();
   const fq_u64 h = fq_gb_hash(key);
+  const fq_u32 smask = p.gb_smem_cap - 1;
+  const fq_u32 admit = p.gb_smem_cap - (p.gb_smem_cap >> FQ_GB_ADMIT_SHIFT);
   bool in_smem = false;
-  fq_u32 i = 0;
-  // The shared-memory table is searched like any linear-probing table: until the key or a free slot turns up.  A key that
-  // fits there must NEVER be sent to HBM: all its rows would hit one L2 line (measured: one such key among 1000 costs 40 ms
-  // per 1e9 rows).  New keys are admitted until the table is 3/4 full (s_used), which keeps the searches short; after that
-  // unknown keys go to HBM.  smem_try is the thread's patience: after 64 misses in a row (a cardinality far beyond the
-  // table) it stops looking here at all.
-  if (p.gb_smem_cap && key != FQ_GB_EMPTY && smem_try > 0) {
-    const fq_u32 smask = p.gb_smem_cap - 1;
-    i = (fq_u32)(h >> 32) & smask;
-#pragma unroll 1
-    for (fq_u32 probe = 0; probe < p.gb_smem_cap; probe++) {
+  bool look = live && p.gb_smem_cap && key != FQ_GB_EMPTY && smem_try > 0;
+  const bool looked = look;
+  // double hashing (an odd step walks the whole power-of-two table): no primary clustering, so the longest chain among the
+  // warp's 32 lanes — the loop's trip count — stays short even at 3/4 load
+  const fq_u32 step = ((fq_u32)(h >> 12) | 1u) & smask;
+  fq_u32 i = (fq_u32)(h >> 32) & smask, probe = 0;
+  while (__any_sync(warp, look)) {
+    if (look) {
       fq_u64 cur = *(volatile fq_u64 *)(skeys + i);
-      if (cur == key) { in_smem = true; break; }
       if (cur == FQ_GB_EMPTY) {
-        if (*(volatile fq_u32 *)s_used >= p.gb_smem_cap - p.gb_smem_cap / 4) break;
-        cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
-        if (cur == FQ_GB_EMPTY) atomicAdd(s_used, 1u);
-        if (cur == FQ_GB_EMPTY || cur == key) { in_smem = true; break; }
+        if (*(volatile fq_u32 *)s_used >= admit) {
+          look = false;          // not admitted: this key lives in HBM
+        } else {
+          cur = atomicCAS((unsigned long long *)(skeys + i), FQ_GB_EMPTY, (unsigned long long)key);
+          if (cur == FQ_GB_EMPTY) atomicAdd(s_used, 1u);
+        }
       }
-      i = (i + 1) & smask;
+      if (look) {
+        if (cur == FQ_GB_EMPTY || cur == key) {
+          in_smem = true;
+          look = false;
+        } else if (++probe >= p.gb_smem_cap) {
+          look = false;          // admissions race past 3/4 on a tiny table: full
+        } else {
+          i = (i + step) & smask;
+        }
+      }
     }
-    smem_try = in_smem ? 64 : smem_try - 1;
   }
-  fq_i64 slot = -1;
-  if (!in_smem) slot = fq_gb_find(p, key, h);
+  if (looked) smem_try = in_smem ? (smem_try < 64 ? smem_try + 1 : 64) : smem_try - 1;
+  const fq_i64 slot = fq_gb_find(p, tkeys, key, h, live && !in_smem);
   if (in_smem) Q::gb_merge_s(sslots + (size_t)i * Q::G, st);
-  else if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, st);
+  else if (slot >= 0) Q::gb_merge(tslots + (fq_u64)slot * Q::G, st);
 }
 
-// One row per lane.  Lanes of the warp that hold the same key fold their rows first (Q::gb_fold: REDUX over the match
-// group) and one of them updates the table: with few distinct keys that turns 32 conflicting atomics per aggregate into
-// one per distinct key.  `agg` is the thread's running verdict on whether that pays (keys that never repeat inside a
-// warp only pay for the MATCH): after 32 rows without a single shared key the warp stops trying.
+// One row per lane.  (Folding the lanes of a warp that share a key first — MATCH.ANY + REDUX over the match groups — was
+// measured on 1e9 rows, number % 7: 42 ms against 8.2 ms with plain native shared-memory atomics, and removed.)
 template <class Q>
-__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used, const typename Q::Rows &r, int v,
-                                          fq_u32 &err, int &agg, int &smem_try) {
-  fq_u64 key, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1];
-  fq_u32 vmask;
-  if (!Q::gb_row(r, v, err, key, val, vmask)) return;
+__device__ __forceinline__ void fq_gb_row(const fq_launch_params &p, fq_u64 *tkeys, fq_u64 *tslots, fq_u64 *skeys, fq_u64 *sslots, fq_u32 *s_used,
+                                          const typename Q::Rows &r, int v, fq_u32 &err, int &smem_try) {
+  fq_u64 key = 0, val[Q::NSLOTS > 0 ? Q::NSLOTS : 1] = {};
+  fq_u32 vmask = 0;
+  const bool live = Q::gb_row(r, v, err, key, val, vmask);
   fq_u64 st[Q::G];
-  if (agg > 0) {
-    const fq_u32 live = __activemask();
-    const fq_u32 peers = __match_any_sync(live, key);
-    const bool shared = __any_sync(live, (peers & (peers - 1)) != 0);
-    agg = shared ? 32 : agg - 1;
-    if (peers & (peers - 1)) {
-      Q::gb_fold(st, val, vmask, peers);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) fq_gb_put<Q>(p, skeys, sslots, s_used, key, st, smem_try);
-      return;
-    }
-  }
   Q::gb_one(st, val, vmask);
-  fq_gb_put<Q>(p, skeys, sslots, s_used, key, st, smem_try);
+  fq_gb_put<Q>(p, tkeys, tslots, skeys, sslots, s_used, key, st, live, smem_try);
 }
 
 template <class Q, int UNROLL>
@@ -1887,14 +1890,18 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
     Q::gb_init(sslots + (size_t)i * Q::G);
   }
   __syncthreads();
+  // this CTA's table in HBM: replica blockIdx % gb_reps.  A key that overflows the shared-memory table is hit by every CTA
+  // on the same few L2 lines; with replicas only the CTAs that share one collide (1e9 rows, 5000 keys: 117 ms with one table)
+  fq_u64 *tkeys = p.gb_keys, *tslots = p.gb_slots;
+  if (p.gb_reps > 1) {
+    const fq_u32 rep = blockIdx.x % p.gb_reps;
+    if (rep) {
+      tkeys = p.gb_rep_keys + (fq_u64)(rep - 1) * (p.gb_cap + 1);
+      tslots = p.gb_rep_slots + (fq_u64)(rep - 1) * (p.gb_cap + 1) * Q::G;
+    }
+  }
   fq_u32 err = 0;
-  // Warp-level pre-aggregation (MATCH.ANY + REDUX over the match groups) is compiled in but off: measured on 1e9 rows,
-  // number % 7, it costs 42 ms against 8.2 ms with plain native shared-memory atomics (FQ_GB_WARP_AGG=1 to try it).
-#ifdef FQ_GB_WARP_AGG
-  int agg = 32, smem_try = 64;
-#else
-  int agg = 0, smem_try = 64;
-#endif
+  int smem_try = 64;
   const fq_u64 nvec = p.unaligned ? 0 : p.n_rows / V;
   const fq_u64 chunk = (fq_u64)blockDim.x * UNROLL;
   const fq_u64 nfull = nvec / chunk;
@@ -1906,7 +1913,7 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, &s_used, rows[u], v, err, agg, smem_try);
+      for (int v = 0; v < V; v++) fq_gb_row<Q>(p, tkeys, tslots, skeys, sslots, &s_used, rows[u], v, err, smem_try);
   }
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
@@ -1914,34 +1921,51 @@ __device__ __forceinline__ void fq_groupby_kernel(const fq_launch_params &p) {
     typename Q::Rows r;
     Q::load(r, p, g);
 #pragma unroll
-    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, skeys, sslots, &s_used, r, v, err, agg, smem_try);
+    for (int v = 0; v < V; v++) fq_gb_row<Q>(p, tkeys, tslots, skeys, sslots, &s_used, r, v, err, smem_try);
   }
   for (fq_u64 row = nvec * V + tid; row < p.n_rows; row += nthreads) {
     typename Q::Rows r;
     Q::load1(r, p, row);
-    fq_gb_row<Q>(p, skeys, sslots, &s_used, r, 0, err, agg, smem_try);
+    fq_gb_row<Q>(p, tkeys, tslots, skeys, sslots, &s_used, r, 0, err, smem_try);
   }
   __syncthreads();
   // flush the CTA's groups into the table in HBM
   for (fq_u32 i = threadIdx.x; i < p.gb_smem_cap; i += blockDim.x) {
     const fq_u64 key = skeys[i];
-    if (key == FQ_GB_EMPTY) continue;
-    const fq_i64 slot = fq_gb_find(p, key, fq_gb_hash(key));
-    if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, sslots + (size_t)i * Q::G);
+    const fq_i64 slot = fq_gb_find(p, tkeys, key, fq_gb_hash(key), key != FQ_GB_EMPTY);
+    if (slot >= 0) Q::gb_merge(tslots + (fq_u64)slot * Q::G, sslots + (size_t)i * Q::G);
   }
   if (err) atomicOr((fq_u32 *)(p.result + 1), err);
 }
 
-// partial groups (entries of 1 + Q::G slots: packed key, state — what fq_pipe_export_partials writes) folded into the table
+// partial groups folded into the table.  With gb_entries: n_rows entries of 1 + Q::G slots (packed key, state — what
+// fq_pipe_export_partials writes).  Without: the (gb_reps - 1) replicas the aggregation kernel filled, n_rows =
+// (gb_reps - 1) * (gb_cap + 1) of their slots; every group met is folded into the table and its replica slot is reset, so
+// the replicas are empty again when the kernel ends.
 template <class Q>
 __device__ __forceinline__ void fq_groupby_merge_kernel(const fq_launch_params &p) {
   const fq_u64 tid = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x;
   const fq_u64 nthreads = (fq_u64)gridDim.x * blockDim.x;
+  if (p.gb_entries) {
+    for (fq_u64 e = tid; e < p.n_rows; e += nthreads) {
+      const fq_u64 *ent = p.gb_entries + e * (1 + Q::G);
+      const fq_u64 key = ent[0];
+      const fq_i64 slot = fq_gb_find(p, p.gb_keys, key, fq_gb_hash(key), true);
+      if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, ent + 1);
+    }
+    return;
+  }
   for (fq_u64 e = tid; e < p.n_rows; e += nthreads) {
-    const fq_u64 *ent = p.gb_entries + e * (1 + Q::G);
-    const fq_u64 key = ent[0];
-    const fq_i64 slot = fq_gb_find(p, key, fq_gb_hash(key));
-    if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, ent + 1);
+    const bool special = e % (p.gb_cap + 1) == p.gb_cap;   // the slot of the key that equals the EMPTY mark
+    const fq_u64 key = special ? FQ_GB_EMPTY : p.gb_rep_keys[e];
+    fq_u64 *from = p.gb_rep_slots + e * Q::G;
+    const bool occupied = special ? from[0] != 0 : key != FQ_GB_EMPTY;   // from[0] = the group's row count
+    const fq_i64 slot = fq_gb_find(p, p.gb_keys, key, fq_gb_hash(key), occupied);
+    if (slot >= 0) Q::gb_merge(p.gb_slots + (fq_u64)slot * Q::G, from);
+    if (occupied) {
+      if (!special) p.gb_rep_keys[e] = FQ_GB_EMPTY;
+      Q::gb_init(from);
+    }
   }
 }
 

@@ -181,6 +181,28 @@ def test_accumulate_across_launches_and_partial_exchange(ctx):
     pipe.destroy()
 
 
+@pytest.mark.parametrize("replicas", ["1", "4", None])
+def test_table_replicas_fold_into_one_table_and_are_left_empty(ctx, monkeypatch, replicas):
+    """CTA b aggregates into replica b % reps of the HBM table and a fold kernel merges them afterwards (FQ_GB_REPLICAS,
+    read at reserve): the result is independent of the number of replicas, and a relaunch starts from empty replicas."""
+    if replicas is None:
+        monkeypatch.delenv("FQ_GB_REPLICAS", raising=False)
+    else:
+        monkeypatch.setenv("FQ_GB_REPLICAS", replicas)
+    n, k = 700_001, 4001                       # more keys than the shared-memory table admits: rows reach the HBM tables
+    col = ctx.numbers(0, n)
+    pipe = ctx.pipe(LEAVES, keys=[mod(k)])
+    pipe.groupby_reserve(k)
+    src = cabi.make_source([col], n)
+    _, want = run_group_by([mod(k)], LEAVES, total=n)
+    for _ in range(3):                         # every launch restarts: stale replica contents would double the counts
+        pipe.launch_groupby(src)
+        assert pipe.fetch_groupby() == k
+        assert fetch_rows(pipe, k) == want
+    pipe.destroy()
+    col.free()
+
+
 def test_group_by_errors(ctx):
     kw = dict(columns=["a", "b"], dtypes=[cabi.U64, cabi.I64], nullable=[False, True])
     with pytest.raises(cabi.FuseGpuError) as e:

@@ -33,6 +33,15 @@ case $what in
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:select --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_select_$c -f python tools/prof_select.py 1000000000 $c > gpurun_out/ncu_select_$c.log 2>&1; echo "ncu $c rc=$?"
     done
     ;;
+  recapture)
+    # the captures that changed after the main `profiles` pass: final GROUP BY kernels, validity bitmaps staged through the ring
+    cap() { name=$1; regex=$2; shift 2; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 2 --launch-count 1 -o gpurun_out/ncu_$name -f "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?";
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page details > gpurun_out/ncu_$name.details.txt 2>/dev/null;
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page raw --csv > gpurun_out/ncu_$name.raw.csv 2>/dev/null; rm -f gpurun_out/ncu_$name.ncu-rep; }
+    cap agg_nullable_bits_1e9 "_agg_" python tools/prof_agg.py 1000000000 nullable_bits
+    cap agg_nullable_u8_bits_4e9 "_agg_" python tools/prof_agg.py 4000000000 nullable_u8_bits
+    for k in 7 1000 5000 1000000; do cap groupby_k${k}_1e9 groupby python tools/prof_groupby.py 1000000000 $k; done
+    ;;
   profiles)
     # ncu captures for profiles/: every kernel of the path, --set full, one launch each after warm-up
     # (the .ncu-rep files are summarised on the box and removed: gpurun copies back at most 64 MiB)
