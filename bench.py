@@ -537,7 +537,7 @@ def run_ours(args):
 def query_table(rig: Rig, col, begin, n, total, generated_only):
     """Whole-job time of every README query (and BASELINE configs 0-2) at this N: all ranks launch together, the launch ends
     with the merged state on every rank, max over ranks, result asserted against the closed form on EVERY rank."""
-    cabi, ctx, world, rank = rig.cabi, rig.ctx, rig.world, rig.rank
+    cabi, ctx, world, rank, torch = rig.cabi, rig.ctx, rig.world, rig.rank, rig.torch
     per_query = {}
     reps = 3
 
@@ -628,6 +628,24 @@ def query_table(rig: Rig, col, begin, n, total, generated_only):
             key = "cfg2: filter+projection+limit 3 @1e9" + (" (limit early exit)" if early else " (full scan)")
             record(key, mode, ms, t2, 0 if (g or early) else 8 * t2,
                    {"note": "early exit: the scan stops once LIMIT rows were found; rows/s counts rows of the table, not rows read"} if early else None)
+        if rig.group is None and world == 1:
+            # the same query as a prepared statement: its launches (memset, kernel, copy-back of the counters) recorded once
+            # as a CUDA graph and replayed (fq_graph_*), next to direct launches of the same pipe on the same stream
+            torch.cuda.synchronize()
+            gs = torch.cuda.Stream()
+            with torch.cuda.stream(gs):
+                ctx.graph_begin(gs.cuda_stream)
+                p.launch_project(s2, outs, 3, limit=3, early_exit=True, stream=gs.cuda_stream)
+                graph = ctx.graph_end(gs.cuda_stream)
+                ms_direct = timed(rig, lambda: p.launch_project(s2, outs, 3, limit=3, early_exit=True, stream=gs.cuda_stream), 50, warm=5)
+                ms = timed(rig, lambda: graph.launch(gs.cuda_stream), 50, warm=5)
+                sel, written = p.fetch_project()
+                got = list(zip(outs[0].to_numpy(written, stream=gs.cuda_stream).tolist(), outs[1].to_numpy(written, stream=gs.cuda_stream).tolist()))
+            assert got == [(1, 0), (2, 0), (3, 1)], got
+            record("cfg2: filter+projection+limit 3 @1e9 (limit early exit, graph replay)", mode, ms, t2, 0,
+                   {"direct_launch_ms": round(ms_direct, 5),
+                    "note": "launch-latency figure: one cudaGraphLaunch per query instead of one launch per memset / kernel / copy"})
+            graph.destroy()
         p.destroy()
         for c in outs + fin:
             c.free()

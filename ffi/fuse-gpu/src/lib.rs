@@ -146,6 +146,17 @@ impl GpuContext {
     pub fn synchronize(&self, stream: *mut c_void) -> FuseQueryResult<()> {
         check(self.raw, unsafe { sys::fq_stream_synchronize(self.raw, stream) })
     }
+
+    /// A non-blocking stream on this context's device (the crate has no CUDA bindings of its own); pair with `stream_destroy`.
+    pub fn stream_create(&self) -> FuseQueryResult<*mut c_void> {
+        let mut s = ptr::null_mut();
+        check(self.raw, unsafe { sys::fq_stream_create(self.raw, &mut s) })?;
+        Ok(s)
+    }
+
+    pub fn stream_destroy(&self, stream: *mut c_void) {
+        unsafe { sys::fq_stream_destroy(self.raw, stream) }
+    }
 }
 
 impl Drop for GpuContext {

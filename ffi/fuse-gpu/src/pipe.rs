@@ -368,3 +368,40 @@ impl Drop for Pipe {
         unsafe { sys::fq_pipe_destroy(self.ctx.raw, self.raw) }
     }
 }
+
+/// A prepared statement: the launches issued between `Graph::record`'s begin and end, replayed with one graph launch
+/// (fq_graph_*).  The pipes launched inside must outlive it; their fetch_* calls work after every replay as after a direct launch.
+pub struct Graph {
+    ctx: Arc<GpuContext>,
+    raw: *mut sys::fq_graph,
+}
+
+unsafe impl Send for Graph {}
+
+impl Graph {
+    /// Records what `launches` issues on `stream` (an explicit stream; nothing runs) and instantiates it.
+    pub fn record(ctx: &Arc<GpuContext>, stream: *mut c_void, launches: impl FnOnce() -> FuseQueryResult<()>) -> FuseQueryResult<Self> {
+        check(ctx.raw, unsafe { sys::fq_graph_begin(ctx.raw, stream) })?;
+        let issued = launches();
+        let mut raw = ptr::null_mut();
+        let ended = check(ctx.raw, unsafe { sys::fq_graph_end(ctx.raw, stream, &mut raw) });
+        if let Err(e) = issued {
+            if !raw.is_null() {
+                unsafe { sys::fq_graph_destroy(ctx.raw, raw) }
+            }
+            return Err(e);
+        }
+        ended?;
+        Ok(Graph { ctx: ctx.clone(), raw })
+    }
+
+    pub fn launch(&self, stream: *mut c_void) -> FuseQueryResult<()> {
+        check(self.ctx.raw, unsafe { sys::fq_graph_launch(self.ctx.raw, self.raw, stream) })
+    }
+}
+
+impl Drop for Graph {
+    fn drop(&mut self) {
+        unsafe { sys::fq_graph_destroy(self.ctx.raw, self.raw) }
+    }
+}

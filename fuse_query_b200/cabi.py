@@ -80,6 +80,7 @@ EXPORTS = [
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
     "fq_column_set_validity_bitmap", "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
+    "fq_graph_begin", "fq_graph_end", "fq_graph_launch", "fq_graph_destroy", "fq_stream_create", "fq_stream_destroy",
 ]
 
 _lib = None
@@ -161,6 +162,12 @@ def lib():
         "fq_utf8_compare": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "fq_utf8_compare_scalar": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
         "fq_utf8_minmax": (i32, [vp, i32, vp, C.POINTER(i64), vp]),
+        "fq_stream_create": (i32, [vp, C.POINTER(vp)]),
+        "fq_stream_destroy": (None, [vp, vp]),
+        "fq_graph_begin": (i32, [vp, vp]),
+        "fq_graph_end": (i32, [vp, vp, C.POINTER(vp)]),
+        "fq_graph_launch": (i32, [vp, vp, vp]),
+        "fq_graph_destroy": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -343,6 +350,25 @@ class Context:
     def synchronize(self, stream: int = 0):
         self.check(lib().fq_stream_synchronize(self._h, C.c_void_p(stream)))
 
+    def stream_create(self) -> int:
+        """a non-blocking stream on this context's device (callers with CUDA bindings of their own pass their streams)"""
+        s = C.c_void_p()
+        self.check(lib().fq_stream_create(self._h, C.byref(s)))
+        return s.value
+
+    def stream_destroy(self, stream: int) -> None:
+        lib().fq_stream_destroy(self._h, C.c_void_p(stream))
+
+    # ---- recorded launches (CUDA graph) ----
+    def graph_begin(self, stream: int) -> None:
+        """Start recording: fq_pipe_launch_* calls on `stream` are recorded, not run, until graph_end."""
+        self.check(lib().fq_graph_begin(self._h, C.c_void_p(stream)))
+
+    def graph_end(self, stream: int) -> "Graph":
+        g = C.c_void_p()
+        self.check(lib().fq_graph_end(self._h, C.c_void_p(stream), C.byref(g)))
+        return Graph(self, g)
+
     # ---- Utf8 arrays ----
     def utf8(self, values: Sequence[Optional[str]], stream: int = 0) -> "Utf8Array":
         """Arrow string array on the device from python strings (None = NULL)."""
@@ -452,6 +478,21 @@ class Column:
             self.ctx.check(lib().fq_column_download(self.ctx._h, self._h, 0, C.c_void_p(out.ctypes.data), n, C.c_void_p(stream)))
             self.ctx.synchronize(stream)
         return out
+
+
+class Graph:
+    """fq_graph: the launches of one or more pipes, replayed with one graph launch; fetch from the pipes as usual."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self._h = ctx, handle
+
+    def launch(self, stream: int) -> None:
+        self.ctx.check(lib().fq_graph_launch(self.ctx._h, self._h, C.c_void_p(stream)))
+
+    def destroy(self) -> None:
+        if self._h:
+            lib().fq_graph_destroy(self.ctx._h, self._h)
+            self._h = None
 
 
 class Utf8Array:

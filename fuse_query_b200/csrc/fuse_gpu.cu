@@ -205,12 +205,23 @@ struct Module {  // one compiled specialisation, shared by every pipe with the s
 
 }  // namespace
 
+// launches recorded between fq_graph_begin and fq_graph_end
+struct fq_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaEvent_t> done;   // the "results are ready" events of the pipes launched inside, recorded after every replay
+  uint64_t launches = 0;           // kernels per replay (fq_ctx_launch_count)
+};
+
 struct fq_ctx {
   int device = 0;
   int sm_count = 0;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::map<std::string, Module> modules;  // tag -> module
+  fq_graph *recording = nullptr;          // set between fq_graph_begin and fq_graph_end
+  cudaStream_t recording_stream = nullptr;
+  uint64_t recording_launches0 = 0;
 };
 
 struct fq_column {
@@ -461,6 +472,18 @@ fq_status launch(fq_ctx *ctx, const Kernel &k, unsigned grid, const fq_launch_pa
     if (cr) return set_err(FQ_ERR_CUDA, "cuLaunchKernel: %s", g_drv.err(cr).c_str());
   }
   ctx->launches++;
+  return FQ_OK;
+}
+
+// "the results of this launch are ready" for the fetch calls: an event on the stream, or — while a graph is being recorded
+// — a note to record it after every replay (an event recorded into a capturing stream cannot be waited for)
+fq_status mark_done(fq_ctx *ctx, cudaEvent_t ev, cudaStream_t s) {
+  if (ctx->recording && s == ctx->recording_stream) {
+    std::vector<cudaEvent_t> &d = ctx->recording->done;
+    if (std::find(d.begin(), d.end(), ev) == d.end()) d.push_back(ev);
+    return FQ_OK;
+  }
+  CUDA_TRY(cudaEventRecord(ev, s));
   return FQ_OK;
 }
 
@@ -719,6 +742,19 @@ fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream) {
   if (fq_status st = use(ctx)) return st;
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return FQ_OK;
+}
+fq_status fq_stream_create(fq_ctx *ctx, void **stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!stream) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  cudaStream_t s = nullptr;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void *)s;
+  return FQ_OK;
+}
+void fq_stream_destroy(fq_ctx *ctx, void *stream) {
+  if (!stream) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaStreamDestroy((cudaStream_t)stream);
 }
 fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out) {
   if (fq_status st = use(ctx)) return st;
@@ -992,6 +1028,7 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   p.accumulate = (flags & FQ_RUN_ACCUMULATE) ? 1u : 0u;
   p.stages = pipe->tma_stages;
   if (fq_group *g = pipe->group) {
+    if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a pipe with a group attached cannot be recorded into a graph (the merge epoch advances per launch)");
     if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the pipe's group is not connected to its peers");
     if ((uint32_t)pipe->n_slots + 1 > g->row_slots) return set_err(FQ_ERR_INVALID, "Internal Error: group rows are too small for this pipe's state");
     bind_group(g, &p);
@@ -1013,7 +1050,7 @@ fq_status fq_pipe_launch_aggregate(fq_ctx *ctx, fq_pipe *pipe, const fq_source *
   p.host_merged = pipe->group ? (fq_u64 *)pipe->h_merged : nullptr;
   if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   pipe->launched_merged = pipe->group != nullptr;
-  CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
+  if (fq_status st = mark_done(ctx, pipe->ev, (cudaStream_t)stream)) return st;
   pipe->launched = true;
   return FQ_OK;
 }
@@ -1278,6 +1315,7 @@ fq_status fq_group_gather_project(fq_ctx *ctx, fq_group *g, fq_pipe *pipe, fq_co
   if (!g || !pipe || pipe->gen.kind != FQ_PIPE_PROJECT || !pipe->launched_project)
     return set_err(FQ_ERR_INVALID, "Internal Error: gather needs a group and a projection pipe that was launched");
   if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is not connected to its peers");
+  if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a group operation cannot be recorded into a graph (its epoch advances per call)");
   fq_gather_params a;
   memset(&a, 0, sizeof a);
   const int ne = (int)pipe->gen.expr_dtypes.size();
@@ -1327,6 +1365,7 @@ fq_status fq_group_gather_columns(fq_ctx *ctx, fq_group *g, const fq_column *con
   if (!g || !local_cols || !final_cols || n_cols < 1 || n_cols > FQ_MAX_EXPRS) return set_err(FQ_ERR_INVALID, "Internal Error: gather needs a group and 1..8 columns");
   if (!g->connected) return set_err(FQ_ERR_INVALID, "Internal Error: the group is not connected to its peers");
   if (rows_local > capacity) return set_err(FQ_ERR_INVALID, "Internal Error: more local rows than the capacity every rank agreed on");
+  if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a group operation cannot be recorded into a graph (its epoch advances per call)");
   fq_gather_params a;
   memset(&a, 0, sizeof a);
   const uint64_t lim = limit < 0 ? capacity * (uint64_t)g->world : (uint64_t)limit;
@@ -1495,7 +1534,7 @@ fq_status fq_pipe_launch_project(fq_ctx *ctx, fq_pipe *pipe, const fq_source *sr
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }
   CUDA_TRY(cudaMemcpyAsync(pipe->h_result, pipe->d_ctl, 48, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  CUDA_TRY(cudaEventRecord(pipe->ev, (cudaStream_t)stream));
+  if (fq_status st = mark_done(ctx, pipe->ev, (cudaStream_t)stream)) return st;
   pipe->launched_project = true;
   return FQ_OK;
 }
@@ -1756,7 +1795,7 @@ static fq_status gb_after_launch(fq_ctx *ctx, fq_pipe *pipe, cudaStream_t s) {
   CUDA_TRY(cudaGetLastError());
   ctx->launches++;
   CUDA_TRY(cudaMemcpyAsync(pipe->h_gb, pipe->gb_flags, 32, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaEventRecord(pipe->ev, s));
+  if (fq_status st = mark_done(ctx, pipe->ev, s)) return st;
   pipe->launched_groupby = true;
   return FQ_OK;
 }
@@ -1921,6 +1960,58 @@ fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *en
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }
   return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
+}
+
+// ---- recorded launches (CUDA graph) ----
+fq_status fq_graph_begin(fq_ctx *ctx, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a graph is already being recorded on this context");
+  if (!stream) return set_err(FQ_ERR_INVALID, "Internal Error: a graph is recorded on an explicit stream, not the default stream");
+  // relaxed mode: a pipe may grow a scratch buffer (cudaMalloc) on its first launch inside the recording
+  CUDA_TRY(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+  ctx->recording = new fq_graph();
+  ctx->recording_stream = (cudaStream_t)stream;
+  ctx->recording_launches0 = ctx->launches.load();
+  return FQ_OK;
+}
+
+fq_status fq_graph_end(fq_ctx *ctx, void *stream, fq_graph **out) {
+  if (fq_status st = use(ctx)) return st;
+  if (!ctx->recording || (cudaStream_t)stream != ctx->recording_stream || !out)
+    return set_err(FQ_ERR_INVALID, "Internal Error: fq_graph_end without a matching fq_graph_begin on this stream");
+  fq_graph *g = ctx->recording;
+  ctx->recording = nullptr;
+  ctx->recording_stream = nullptr;
+  g->launches = ctx->launches.load() - ctx->recording_launches0;
+  ctx->launches -= g->launches;   // nothing ran yet
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    cudaGetLastError();
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (recording a graph)", cudaGetErrorString(e));
+  }
+  *out = g;
+  return FQ_OK;
+}
+
+fq_status fq_graph_launch(fq_ctx *ctx, fq_graph *graph, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!graph || !graph->exec) return set_err(FQ_ERR_INVALID, "Internal Error: null graph");
+  if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a graph cannot be launched while another is being recorded");
+  CUDA_TRY(cudaGraphLaunch(graph->exec, (cudaStream_t)stream));
+  for (cudaEvent_t ev : graph->done) CUDA_TRY(cudaEventRecord(ev, (cudaStream_t)stream));
+  ctx->launches += graph->launches;
+  return FQ_OK;
+}
+
+void fq_graph_destroy(fq_ctx *ctx, fq_graph *graph) {
+  if (!graph) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (graph->exec) cudaGraphExecDestroy(graph->exec);
+  if (graph->graph) cudaGraphDestroy(graph->graph);
+  delete graph;
 }
 
 }  // extern "C"

@@ -152,6 +152,10 @@ fq_status fq_column_upload_bits(fq_ctx *ctx, fq_column *col, uint64_t row_offset
 fq_status fq_column_download_bits(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host_bits, uint64_t n_rows,
                                   void *stream);
 fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream);
+/* `stream` arguments are cudaStream_t handles of the caller (NULL = the default stream).  A host without CUDA bindings of
+ * its own gets one here: a non-blocking stream on the context's device. */
+fq_status fq_stream_create(fq_ctx *ctx, void **stream);
+void fq_stream_destroy(fq_ctx *ctx, void *stream);
 /* pinned host staging memory */
 fq_status fq_host_alloc(fq_ctx *ctx, uint64_t bytes, void **out);
 void fq_host_free(fq_ctx *ctx, void *p);
@@ -366,6 +370,20 @@ fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selec
  * before stream_limit.rs:28-48), and of the block after it (LimitStream polls its input before it checks its counter,
  * :58-62); a caller that wants exactly the reference's errors evaluates up to the end of that block and no further. */
 fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row);
+
+/* ---- replaying a query: the launches of one or more pipes recorded once as a CUDA graph ----
+ * The reference rebuilds its pipeline for every query (interpreter_select.rs:27-40); a prepared statement that is executed
+ * again and again pays here only one graph launch instead of one launch per memset / probe / kernel / copy-back.
+ *   fq_graph_begin(ctx, stream);  fq_pipe_launch_*(..., stream) ...;  fq_graph_end(ctx, stream, &g);
+ *   for every execution: fq_graph_launch(ctx, g, stream);  fq_pipe_fetch_*(...) as after a direct launch.
+ * Sources, output columns, limits and flags are frozen as recorded.  Between begin and end nothing runs; only launches
+ * on `stream` belong to the recording, one recording at a time per context.  A pipe with a group attached is refused
+ * (its merge carries an epoch that advances with every execution). */
+typedef struct fq_graph fq_graph;
+fq_status fq_graph_begin(fq_ctx *ctx, void *stream);
+fq_status fq_graph_end(fq_ctx *ctx, void *stream, fq_graph **out);
+fq_status fq_graph_launch(fq_ctx *ctx, fq_graph *graph, void *stream);
+void fq_graph_destroy(fq_ctx *ctx, fq_graph *graph);
 
 #ifdef __cplusplus
 }

@@ -155,6 +155,26 @@ int main(void) {
   st = fq_pipe_fetch_aggregate(ctx, bad, states, 8, &n_states, &rows);
   EXPECT(st == FQ_ERR_DIVIDE_BY_ZERO && strcmp(fq_last_error(ctx), "Internal Error: Divide by zero error") == 0);
 
+  /* a prepared statement: the select and the GROUP BY recorded once on a stream of the library's, replayed twice */
+  void *stream = NULL;
+  fq_graph *graph = NULL;
+  CHECK(fq_stream_create(ctx, &stream));
+  CHECK(fq_graph_begin(ctx, stream));
+  CHECK(fq_pipe_launch_project(ctx, sel, &src, outs, NULL, 3, 3, FQ_RUN_LIMIT_EARLY_EXIT, stream));
+  CHECK(fq_pipe_launch_groupby(ctx, gb, &src, 0, stream));
+  CHECK(fq_graph_end(ctx, stream, &graph));
+  for (int rep = 0; rep < 2; rep++) {
+    CHECK(fq_graph_launch(ctx, graph, stream));
+    CHECK(fq_pipe_fetch_project(ctx, sel, &selected, &written));
+    CHECK(fq_pipe_fetch_groupby(ctx, gb, &groups));
+    EXPECT(written == 3 && groups == 4);
+    CHECK(fq_column_download(ctx, outs[0], 0, a, 3, stream));
+    CHECK(fq_stream_synchronize(ctx, stream));
+    EXPECT(a[0] == 1 && a[1] == 2 && a[2] == 3);
+  }
+  fq_graph_destroy(ctx, graph);
+  fq_stream_destroy(ctx, stream);
+
   fq_pipe_destroy(ctx, bad);
   fq_pipe_destroy(ctx, gb);
   fq_pipe_destroy(ctx, sel);
