@@ -665,6 +665,12 @@ def group_by_table(rig: Rig, col):
     src = cabi.make_source([col], n)
     out = {}
     aggs = [f"(sum {NUM})", f"(count {NUM})", f"(min {NUM})", f"(max {NUM})"]
+    if world > 1:
+        # NCCL opens its peer-to-peer channels on first use per pair: a full all-to-all now, so that the first timed key count
+        # (7 groups: most pairs exchange nothing) does not pay for connections the later ones need
+        w = torch.ones(world * 16, dtype=torch.int64, device=rig.dev)
+        dist.all_to_all_single(torch.empty_like(w), w)
+        torch.cuda.synchronize()
     for k in (7, 1000, 5000, 1_000_000, 100_000_000):
         key = f"(- {NUM} (* (/ {NUM} (u64 {k})) (u64 {k})))"
         pipe = ctx.pipe(aggs, keys=[key])
