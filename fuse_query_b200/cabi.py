@@ -80,6 +80,7 @@ EXPORTS = [
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
     "fq_column_set_validity_bitmap", "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
+    "fq_sort_indices", "fq_column_take",
     "fq_graph_begin", "fq_graph_end", "fq_graph_launch", "fq_graph_destroy", "fq_stream_create", "fq_stream_destroy",
 ]
 
@@ -162,6 +163,8 @@ def lib():
         "fq_utf8_compare": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "fq_utf8_compare_scalar": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
         "fq_utf8_minmax": (i32, [vp, i32, vp, C.POINTER(i64), vp]),
+        "fq_sort_indices": (i32, [vp, vp, vp, i32, u64, vp, vp]),
+        "fq_column_take": (i32, [vp, vp, vp, u64, vp, vp, vp]),
         "fq_stream_create": (i32, [vp, C.POINTER(vp)]),
         "fq_stream_destroy": (None, [vp, vp]),
         "fq_graph_begin": (i32, [vp, vp]),
@@ -349,6 +352,26 @@ class Context:
 
     def synchronize(self, stream: int = 0):
         self.check(lib().fq_stream_synchronize(self._h, C.c_void_p(stream)))
+
+    # ---- ORDER BY ----
+    def sort_indices(self, keys: Sequence["Column"], n: int, descending: Optional[Sequence[bool]] = None, stream: int = 0) -> "Column":
+        """Row indexes (UInt32) that put `keys` in order: lexicographic, keys[0] most significant, NULLs first, stable."""
+        out = self.column(U32, max(1, n))
+        arr = (C.c_void_p * len(keys))(*[k._h for k in keys])
+        desc = (C.c_uint8 * len(keys))(*[1 if (descending and descending[j]) else 0 for j in range(len(keys))])
+        self.check(lib().fq_sort_indices(self._h, arr, desc, len(keys), n, out._h, C.c_void_p(stream)))
+        return out
+
+    def take(self, src: "Column", rows: "Column", n: int, stream: int = 0) -> "Column":
+        """out[i] = src[rows[i]]; the result carries byte validity when the source has validity of either form."""
+        out = self.column(src.dtype, max(1, n))
+        nullable = src.validity is not None or getattr(src, "_validity", None) is not None
+        valid = self.column(BOOL, max(1, n)) if nullable else None
+        self.check(lib().fq_column_take(self._h, src._h, rows._h, n, out._h, valid._h if valid is not None else None, C.c_void_p(stream)))
+        if valid is not None:
+            self.check(lib().fq_column_set_validity(self._h, out._h, valid._h))
+            out._validity = valid
+        return out
 
     def stream_create(self) -> int:
         """a non-blocking stream on this context's device (callers with CUDA bindings of their own pass their streams)"""

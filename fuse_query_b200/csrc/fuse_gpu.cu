@@ -25,6 +25,7 @@
 #include "../../include/fuse_gpu.h"
 #include "codegen.h"
 #include "kernels/fq_skeleton.cuh"
+#include "kernels/fq_sort.cuh"
 #include "generated/skeleton_embed.h"  // static const char fq_skeleton_src[]
 
 #ifndef FQ_MAP_DEFAULT_VARIANT
@@ -1960,6 +1961,138 @@ fq_status fq_pipe_merge_partials(fq_ctx *ctx, fq_pipe *pipe, const fq_column *en
     if (fq_status st = launch(ctx, k, grid, p, stream)) return st;
   }
   return gb_after_launch(ctx, pipe, (cudaStream_t)stream);
+}
+
+// ---- ORDER BY: stable radix sort of row indexes, and the gather that applies them (kernels/fq_sort.cuh) ----
+namespace {
+// exclusive scan of m u32 counters in place; `sums` holds ceil(m / FQ_SCAN_TILE) scratch words
+fq_status sort_scan(fq_ctx *ctx, fq_u32 *a, uint64_t m, fq_u32 *sums, cudaStream_t s) {
+  const unsigned nb = (unsigned)((m + FQ_SCAN_TILE - 1) / FQ_SCAN_TILE);
+  fq_scan_tile_sums<<<nb, FQ_SCAN_THREADS, 0, s>>>(a, m, sums);
+  fq_scan_sums<<<1, FQ_SCAN_THREADS, 0, s>>>(sums, nb);
+  fq_scan_tiles<<<nb, FQ_SCAN_THREADS, 0, s>>>(a, m, sums);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 3;
+  return FQ_OK;
+}
+}  // namespace
+
+fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
+                          fq_column *indices, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!keys || n_keys < 1 || !indices) return set_err(FQ_ERR_INVALID, "Internal Error: sort needs at least one key column and an index column");
+  if (indices->dtype != FQ_U32 || indices->len < n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: the index column must be UInt32 with at least n_rows slots");
+  if (n_rows >= (1ull << 32)) return set_err(FQ_ERR_INVALID, "Internal Error: sort handles fewer than 2^32 rows per call");
+  if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a sort cannot be recorded into a graph (its passes depend on the data)");
+  for (int j = 0; j < n_keys; j++) {
+    if (!keys[j] || keys[j]->len < n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: sort key %d is shorter than n_rows", j);
+    if (keys[j]->dtype == FQ_NULL || keys[j]->dtype == FQ_UTF8) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: sort key of type %s", fq::dtype_name(keys[j]->dtype));
+  }
+  if (n_rows == 0) return FQ_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint64_t n = n_rows;
+  const unsigned n_tiles = (unsigned)((n + FQ_SORT_TILE - 1) / FQ_SORT_TILE);
+  const uint64_t hist_len = 256ull * n_tiles;
+  const unsigned scan_blocks = (unsigned)((hist_len + FQ_SCAN_TILE - 1) / FQ_SCAN_TILE);
+  fq_u64 *code[2] = {nullptr, nullptr}, *and_or = nullptr;
+  fq_u32 *idx[2] = {nullptr, nullptr}, *hist = nullptr, *sums = nullptr;
+  auto release = [&]() {
+    for (void *p : {(void *)code[0], (void *)code[1], (void *)idx[0], (void *)idx[1], (void *)hist, (void *)sums, (void *)and_or})
+      if (p) cudaFreeAsync(p, s);
+  };
+  cudaError_t e = cudaMallocAsync((void **)&code[0], 8 * n, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&code[1], 8 * n, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&idx[0], 4 * n, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&idx[1], 4 * n, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&hist, 4 * hist_len, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&sums, 4 * (uint64_t)scan_blocks, s);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&and_or, 16, s);
+  if (e != cudaSuccess) {
+    release();
+    cudaGetLastError();
+    return set_err(FQ_ERR_CUDA, "CUDA error: %s (sort scratch for %" PRIu64 " rows)", cudaGetErrorString(e), n);
+  }
+  int cur = 0;             // code[cur] / idx[cur] hold the pairs in their current order
+  bool have_perm = false;  // false until the first key was encoded (identity order)
+  const unsigned enc_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+  fq_status status = FQ_OK;
+  // one stable sort per key, last key first; inside a key: its value digits, then (nullable keys) the NULLs-first bit
+  for (int j = n_keys - 1; j >= 0 && status == FQ_OK; j--) {
+    const fq_column *k = keys[j];
+    const bool nullable = k->validity || k->validity_bits;
+    for (int phase = 0; phase < (nullable ? 2 : 1) && status == FQ_OK; phase++) {
+      static const uint64_t init[2] = {~0ull, 0ull};
+      if (cudaMemcpyAsync(and_or, init, 16, cudaMemcpyHostToDevice, s) != cudaSuccess) { status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(cudaGetLastError())); break; }
+      fq_sort_encode_params a;
+      memset(&a, 0, sizeof a);
+      a.col = k->ptr;
+      a.valid_bytes = k->validity ? (const fq_u8 *)k->validity->ptr : nullptr;
+      a.valid_bits = (!k->validity && k->validity_bits) ? k->validity_bits->ptr : nullptr;
+      a.valid_bit0 = k->validity_bit0;
+      a.perm = have_perm ? idx[cur] : nullptr;
+      a.code_out = code[cur];
+      a.idx_out = idx[cur];
+      a.and_or = and_or;
+      a.n = n;
+      a.dtype = (int)k->dtype;
+      a.bits = 8 * (int)fq::dtype_size(k->dtype);
+      a.descending = (descending && descending[j]) ? 1 : 0;
+      a.flags_only = phase;
+      fq_sort_encode<<<enc_grid, 256, 0, s>>>(a);
+      ctx->launches++;
+      have_perm = true;
+      uint64_t h_and_or[2];
+      cudaError_t ce = cudaMemcpyAsync(h_and_or, and_or, 16, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+      if (ce != cudaSuccess) { status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(ce)); break; }
+      const uint64_t varying = h_and_or[0] ^ h_and_or[1];   // bits that differ between some two codes
+      const int digits = phase ? 1 : a.bits / 8;
+      for (int d = 0; d < digits; d++) {
+        if (((varying >> (8 * d)) & 255) == 0) continue;    // every row has the same digit: the pass would be the identity
+        fq_sort_hist<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], n, n_tiles, 8 * d, hist);
+        ctx->launches++;
+        if ((status = sort_scan(ctx, hist, hist_len, sums, s)) != FQ_OK) break;
+        fq_sort_scatter<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], idx[cur], code[cur ^ 1], idx[cur ^ 1], hist, n, n_tiles, 8 * d);
+        ctx->launches++;
+        cur ^= 1;
+      }
+    }
+  }
+  if (status == FQ_OK) {
+    cudaError_t ce = cudaMemcpyAsync(indices->ptr, idx[cur], 4 * n, cudaMemcpyDeviceToDevice, s);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(ce));
+  }
+  release();
+  return status;
+}
+
+fq_status fq_column_take(fq_ctx *ctx, const fq_column *src, const fq_column *rows, uint64_t n, fq_column *out, fq_column *out_valid,
+                         void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!src || !rows || !out) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (rows->dtype != FQ_U32 || rows->len < n) return set_err(FQ_ERR_INVALID, "Internal Error: row indexes must be a UInt32 column with at least n slots");
+  if (out->dtype != src->dtype || out->len < n) return set_err(FQ_ERR_INVALID, "Internal Error: the output column must have the source's type and at least n slots");
+  const bool nullable = src->validity || src->validity_bits;
+  if (nullable && (!out_valid || out_valid->dtype != FQ_BOOL || out_valid->len < n))
+    return set_err(FQ_ERR_INVALID, "Internal Error: the source has validity: a Boolean output validity column is required");
+  if (n == 0) return FQ_OK;
+  fq_take_params a;
+  memset(&a, 0, sizeof a);
+  a.src = src->ptr;
+  a.out = out->ptr;
+  a.rows = (const fq_u32 *)rows->ptr;
+  a.n = n;
+  a.width = (int)fq::dtype_size(src->dtype);
+  a.valid_bytes = src->validity ? (const fq_u8 *)src->validity->ptr : nullptr;
+  a.valid_bits = (!src->validity && src->validity_bits) ? src->validity_bits->ptr : nullptr;
+  a.valid_bit0 = src->validity_bit0;
+  a.out_valid = out_valid ? (fq_u8 *)out_valid->ptr : nullptr;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+  fq_take_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return FQ_OK;
 }
 
 // ---- recorded launches (CUDA graph) ----

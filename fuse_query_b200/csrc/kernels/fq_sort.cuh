@@ -1,0 +1,252 @@
+// fq_sort.cuh — ORDER BY on the device: a stable LSD radix sort of row indexes.
+//
+// The reference lists sorting as not implemented (README.md:28 "[ ] Sorting"; sqlparser accepts ORDER BY and
+// plan_parser.rs never reads `query.order_by`), so the semantics are stated here and in oracle/sort.py: keys are
+// compared as arrow's sort kernels compare them with the crate's default SortOptions — ascending unless DESC, NULLs first
+// — ties keep their input order (stable), floats are ordered by IEEE total order (-NaN < -inf < ... < -0 < +0 < ... < +inf
+// < +NaN).  Several keys are sorted last key first, each sort stable, which is the lexicographic order.
+//
+// What is sorted are (code, row) pairs: `code` is an order-preserving unsigned image of the key (fq_sort_code), `row` a
+// 32-bit row index — the payload columns are gathered once at the end (fq_take_kernel), they never ride through the passes.
+// One pass handles one 8-bit digit: per-tile digit histograms, one exclusive scan over all (digit, tile) counters in
+// digit-major order, and a scatter in which every warp ranks its rows with MATCH.ANY (lanes holding the same digit) against
+// per-warp digit counters in shared memory: stable by construction, no atomics.  Digits whose bits are the same in
+// every code (AND == OR, folded during encoding) are skipped: numbers below 2^32 cost four passes, not eight.
+// Bound: HBM; per pass 12 B read twice (histogram, scatter; the second read hits L2 for small inputs) + 12 B written per row.
+#pragma once
+
+#define FQ_SORT_THREADS 256
+#define FQ_SORT_ITEMS 16
+#define FQ_SORT_TILE (FQ_SORT_THREADS * FQ_SORT_ITEMS)        // pairs per CTA
+#define FQ_SORT_WARPS (FQ_SORT_THREADS / 32)
+#define FQ_SORT_WARP_ITEMS (FQ_SORT_TILE / FQ_SORT_WARPS)     // consecutive pairs owned by one warp
+#define FQ_SCAN_THREADS 1024
+#define FQ_SCAN_ITEMS 8
+#define FQ_SCAN_TILE (FQ_SCAN_THREADS * FQ_SCAN_ITEMS)
+
+// order-preserving unsigned code of slot `i` of a column (dtype tags of fuse_gpu.h)
+__device__ __forceinline__ fq_u64 fq_sort_code(const void *col, int dtype, fq_u64 i) {
+  switch (dtype) {
+    case FQ_BOOL:
+    case FQ_U8: return ((const fq_u8 *)col)[i];
+    case FQ_U16: return ((const unsigned short *)col)[i];
+    case FQ_U32: return ((const fq_u32 *)col)[i];
+    case FQ_U64: return ((const fq_u64 *)col)[i];
+    case FQ_I8: return (fq_u8)(((const signed char *)col)[i]) ^ 0x80u;
+    case FQ_I16: return (unsigned short)(((const short *)col)[i]) ^ 0x8000u;
+    case FQ_I32: return (fq_u32)(((const int *)col)[i]) ^ 0x80000000u;
+    case FQ_I64: return (fq_u64)(((const fq_i64 *)col)[i]) ^ (1ull << 63);
+    case FQ_F32: {
+      const fq_u32 b = ((const fq_u32 *)col)[i];
+      return (b >> 31) ? (fq_u32)~b : (b | 0x80000000u);
+    }
+    case FQ_F64: {
+      const fq_u64 b = ((const fq_u64 *)col)[i];
+      return (b >> 63) ? ~b : (b | (1ull << 63));
+    }
+  }
+  return 0;
+}
+
+struct fq_sort_encode_params {
+  const void *col;          // key column (values); nullptr with flags_only
+  const fq_u8 *valid_bytes; // validity, one byte per row, or
+  const void *valid_bits;   // an Arrow bitmap with row 0 at bit valid_bit0, or neither
+  fq_u64 valid_bit0;
+  const fq_u32 *perm;       // rows in their current order (nullptr = identity, and idx_out is written)
+  fq_u64 *code_out;
+  fq_u32 *idx_out;
+  fq_u64 *and_or;           // [0] &= every code, [1] |= every code
+  fq_u64 n;
+  int dtype, bits;          // bits of the code that carry the key (8 * width)
+  int descending;
+  int flags_only;           // code = 1 for a valid slot, 0 for NULL (the NULLs-first pass)
+};
+
+__global__ void __launch_bounds__(256) fq_sort_encode(const __grid_constant__ fq_sort_encode_params a) {
+  fq_u64 m_and = ~0ull, m_or = 0ull;
+  const fq_u64 mask = a.bits >= 64 ? ~0ull : ((1ull << a.bits) - 1);
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (fq_u64)gridDim.x * blockDim.x) {
+    const fq_u64 row = a.perm ? a.perm[i] : i;
+    fq_u64 code;
+    if (a.flags_only) {
+      code = a.valid_bytes ? (a.valid_bytes[row] ? 1u : 0u) : (fq_ld_bit(a.valid_bits, a.valid_bit0 + row) ? 1u : 0u);
+    } else {
+      code = fq_sort_code(a.col, a.dtype, row);
+      if (a.descending) code = ~code & mask;
+      // a NULL slot's value bytes are arbitrary: give all NULLs one code so that they keep their input order
+      const bool ok = a.valid_bytes ? a.valid_bytes[row] != 0 : (a.valid_bits ? fq_ld_bit(a.valid_bits, a.valid_bit0 + row) : true);
+      if (!ok) code = 0;
+    }
+    a.code_out[i] = code;
+    if (!a.perm) a.idx_out[i] = (fq_u32)i;
+    m_and &= code;
+    m_or |= code;
+  }
+  for (int o = 16; o; o >>= 1) {
+    m_and &= __shfl_xor_sync(0xffffffffu, m_and, o);
+    m_or |= __shfl_xor_sync(0xffffffffu, m_or, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAnd((unsigned long long *)a.and_or, (unsigned long long)m_and);
+    atomicOr((unsigned long long *)(a.and_or + 1), (unsigned long long)m_or);
+  }
+}
+
+// per-warp digit counts of this CTA's tile: cnt[w][d] = rows of warp w's run whose digit is d
+__device__ __forceinline__ void fq_sort_count(fq_u32 (*cnt)[256], const fq_u64 *code, fq_u64 n, fq_u64 base, int shift) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < FQ_SORT_WARPS * 256; i += FQ_SORT_THREADS) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+#pragma unroll 4
+  for (int r = 0; r < FQ_SORT_WARP_ITEMS / 32; r++) {
+    const fq_u64 i = base + (fq_u64)warp * FQ_SORT_WARP_ITEMS + r * 32 + lane;
+    const bool in = i < n;
+    const fq_u32 digit = in ? (fq_u32)(code[i] >> shift) & 255u : 256u;
+    const fq_u32 peers = __match_any_sync(0xffffffffu, digit);
+    if (in && lane == __ffs(peers) - 1) cnt[warp][digit] += __popc(peers);   // one lane per digit per round: no atomics
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// hist[d * n_tiles + tile] = rows of the tile whose digit is d (digit-major: one scan gives every (digit, tile) its base)
+__global__ void __launch_bounds__(FQ_SORT_THREADS) fq_sort_hist(const fq_u64 *code, fq_u64 n, fq_u32 n_tiles, int shift, fq_u32 *hist) {
+  __shared__ fq_u32 cnt[FQ_SORT_WARPS][256];
+  fq_sort_count(cnt, code, n, (fq_u64)blockIdx.x * FQ_SORT_TILE, shift);
+  fq_u32 c = 0;
+#pragma unroll
+  for (int w = 0; w < FQ_SORT_WARPS; w++) c += cnt[w][threadIdx.x];
+  hist[(fq_u64)threadIdx.x * n_tiles + blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(FQ_SORT_THREADS) fq_sort_scatter(const fq_u64 *code, const fq_u32 *idx, fq_u64 *code_out, fq_u32 *idx_out,
+                                                                   const fq_u32 *hist_scanned, fq_u64 n, fq_u32 n_tiles, int shift) {
+  __shared__ fq_u32 cnt[FQ_SORT_WARPS][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const fq_u64 base = (fq_u64)blockIdx.x * FQ_SORT_TILE;
+  fq_sort_count(cnt, code, n, base, shift);
+  {  // thread d: where the tile's rows of digit d go, then where each warp's share of them starts
+    fq_u32 run = hist_scanned[(fq_u64)threadIdx.x * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < FQ_SORT_WARPS; w++) {
+      const fq_u32 c = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int r = 0; r < FQ_SORT_WARP_ITEMS / 32; r++) {
+    const fq_u64 i = base + (fq_u64)warp * FQ_SORT_WARP_ITEMS + r * 32 + lane;
+    const bool in = i < n;
+    const fq_u64 c = in ? code[i] : 0;
+    const fq_u32 digit = in ? (fq_u32)(c >> shift) & 255u : 256u;
+    const fq_u32 peers = __match_any_sync(0xffffffffu, digit);
+    if (in) {
+      const fq_u32 at = cnt[warp][digit] + __popc(peers & ((1u << lane) - 1));   // lanes in row order: stable
+      code_out[at] = c;
+      idx_out[at] = idx[i];
+    }
+    __syncwarp();
+    if (in && lane == __ffs(peers) - 1) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// ---- exclusive scan of a u32 array (the digit-major histogram), in place: tile sums, scan of the sums, tile scans ----
+__device__ __forceinline__ fq_u32 fq_block_exclusive_scan(fq_u32 x, fq_u32 *warp_sums /* [32] shared */, fq_u32 &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  fq_u32 inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const fq_u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    fq_u32 s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const fq_u32 y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    warp_sums[lane] = s;   // inclusive over warps
+  }
+  __syncthreads();
+  total = warp_sums[31];
+  const fq_u32 before = warp ? warp_sums[warp - 1] : 0;
+  __syncthreads();
+  return before + inc - x;
+}
+
+__global__ void __launch_bounds__(FQ_SCAN_THREADS) fq_scan_tile_sums(const fq_u32 *a, fq_u64 m, fq_u32 *sums) {
+  __shared__ fq_u32 ws[32];
+  const fq_u64 base = (fq_u64)blockIdx.x * FQ_SCAN_TILE + (fq_u64)threadIdx.x * FQ_SCAN_ITEMS;
+  fq_u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < FQ_SCAN_ITEMS; k++) s += base + k < m ? a[base + k] : 0;
+  fq_u32 total;
+  fq_block_exclusive_scan(s, ws, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// one CTA: sums[] -> exclusive prefix, in place
+__global__ void __launch_bounds__(FQ_SCAN_THREADS) fq_scan_sums(fq_u32 *sums, fq_u32 nb) {
+  __shared__ fq_u32 ws[32];
+  fq_u32 carry = 0;
+  for (fq_u32 b0 = 0; b0 < nb; b0 += FQ_SCAN_THREADS) {
+    const fq_u32 i = b0 + threadIdx.x;
+    const fq_u32 x = i < nb ? sums[i] : 0;
+    fq_u32 total;
+    const fq_u32 ex = fq_block_exclusive_scan(x, ws, total);
+    if (i < nb) sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(FQ_SCAN_THREADS) fq_scan_tiles(fq_u32 *a, fq_u64 m, const fq_u32 *sums) {
+  __shared__ fq_u32 ws[32];
+  const fq_u64 base = (fq_u64)blockIdx.x * FQ_SCAN_TILE + (fq_u64)threadIdx.x * FQ_SCAN_ITEMS;
+  fq_u32 v[FQ_SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int k = 0; k < FQ_SCAN_ITEMS; k++) {
+    v[k] = base + k < m ? a[base + k] : 0;
+    s += v[k];
+  }
+  fq_u32 total;
+  fq_u32 run = sums[blockIdx.x] + fq_block_exclusive_scan(s, ws, total);
+#pragma unroll
+  for (int k = 0; k < FQ_SCAN_ITEMS; k++) {
+    if (base + k < m) a[base + k] = run;
+    run += v[k];
+  }
+}
+
+// ---- gather: out[i] = src[rows[i]] (values of `width` bytes; validity bytes or bits -> validity bytes) ----
+struct fq_take_params {
+  const void *src;
+  void *out;
+  const fq_u32 *rows;
+  fq_u64 n;
+  int width;
+  const fq_u8 *valid_bytes;
+  const void *valid_bits;
+  fq_u64 valid_bit0;
+  fq_u8 *out_valid;
+};
+
+__global__ void __launch_bounds__(256) fq_take_kernel(const __grid_constant__ fq_take_params a) {
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (fq_u64)gridDim.x * blockDim.x) {
+    const fq_u64 row = a.rows[i];
+    switch (a.width) {
+      case 1: ((fq_u8 *)a.out)[i] = ((const fq_u8 *)a.src)[row]; break;
+      case 2: ((unsigned short *)a.out)[i] = ((const unsigned short *)a.src)[row]; break;
+      case 4: ((fq_u32 *)a.out)[i] = ((const fq_u32 *)a.src)[row]; break;
+      default: ((fq_u64 *)a.out)[i] = ((const fq_u64 *)a.src)[row]; break;
+    }
+    if (a.out_valid)
+      a.out_valid[i] = a.valid_bytes ? (a.valid_bytes[row] ? 1 : 0) : (a.valid_bits ? (fq_ld_bit(a.valid_bits, a.valid_bit0 + row) ? 1 : 0) : 1);
+  }
+}

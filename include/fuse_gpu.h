@@ -371,6 +371,18 @@ fq_status fq_pipe_fetch_project(fq_ctx *ctx, fq_pipe *pipe, uint64_t *rows_selec
  * :58-62); a caller that wants exactly the reference's errors evaluates up to the end of that block and no further. */
 fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row);
 
+/* ---- ORDER BY ----
+ * The reference lists sorting as not implemented (README.md:28; plan_parser.rs never reads `query.order_by`); the order is
+ * arrow's with the crate's default SortOptions: ascending unless descending[j], NULLs first, ties in input order (stable),
+ * floats by IEEE total order.  Several keys: lexicographic, keys[0] most significant.
+ * fq_sort_indices writes the permutation (row indexes in sorted order, UInt32, so fewer than 2^32 rows) and fq_column_take
+ * applies it to a column: out[i] = src[rows[i]], validity (bytes or bitmap) gathered into out_valid when the source has one.
+ * Stable LSD radix sort, one pass per 8-bit digit that differs between some two rows; scratch is 24 bytes per row. */
+fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
+                          fq_column *indices, void *stream);
+fq_status fq_column_take(fq_ctx *ctx, const fq_column *src, const fq_column *rows, uint64_t n, fq_column *out, fq_column *out_valid,
+                         void *stream);
+
 /* ---- replaying a query: the launches of one or more pipes recorded once as a CUDA graph ----
  * The reference rebuilds its pipeline for every query (interpreter_select.rs:27-40); a prepared statement that is executed
  * again and again pays here only one graph launch instead of one launch per memset / probe / kernel / copy-back.
