@@ -463,10 +463,12 @@ def run_ours(args):
     # ---- every README query x {materialised, generated}: whole-job numbers at this N, merged result verified ----
     per_query = {}
     group_by = None
+    order_by = None
     if not args.no_query_table:
         per_query = query_table(rig, col, begin, n, total, generated)
         if col is not None:
             group_by = group_by_table(rig, col)
+            order_by = order_by_table(rig, col) if world == 1 else None
 
     # ---- e2e: host-resident (pinned) column -> H2D chunks overlapped with the kernel -> D2H state ----
     e2e = run_e2e(rig, col, begin, n, total, generated)
@@ -506,7 +508,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": row_bytes * n,
                          "note": "kernel_ms includes the in-kernel wait for the slowest rank when N > 1"},
             "throughput_no_merge": no_merge,
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "group_by": group_by,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "result": got, "per_query": per_query, "group_by": group_by, "order_by": order_by,
             "sql_e2e": sql_e2e,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -733,6 +735,55 @@ def group_by_table(rig: Rig, col):
             ent.free()
         if recv is not None:
             recv[0].free()
+    return out
+
+
+def order_by_table(rig: Rig, col):
+    """ORDER BY over numbers_mt(10^9) on one GPU: fq_sort_indices (stable LSD radix sort of row indexes) +
+    fq_column_take of the payload.  Two key shapes: `number DESC` (input already ordered the other way; 4 of 8 digits vary)
+    and a 64-bit scrambled key `number * 0x9E3779B97F4A7C15` (every digit varies: 8 passes).  Verified on the device: the
+    gathered keys are ordered and the row indexes are a permutation (sum and xor of 0 .. n-1)."""
+    cabi, ctx, torch = rig.cabi, rig.ctx, rig.torch
+    n = 1_000_000_000
+    ctx.fill_numbers(col, 0, n, rig.stream)
+    keycol = col.slice(0, n)
+    out = {}
+    scr = ctx.pipe([f"(* {NUM} (u64 {0x9E3779B97F4A7C15}))"])
+    scrambled = ctx.column(cabi.U64, n)
+    scr.launch_project(cabi.make_source([keycol], n), [scrambled], n, stream=rig.stream)
+    assert scr.fetch_project()[1] == n
+    scr.destroy()
+    for name, key, desc in (("number desc", keycol, True), ("number * 0x9E3779B97F4A7C15 (64-bit scrambled)", scrambled, False)):
+        def one():
+            idx = ctx.sort_indices([key], n, [desc], stream=rig.stream)
+            idx.free()
+        ms_sort = timed(rig, one, 2, warm=1)
+        idx = ctx.sort_indices([key], n, [desc], stream=rig.stream)
+        a, b = rig.event(), rig.event()
+        a.record()
+        taken = ctx.take(key, idx, n, stream=rig.stream)
+        b.record()
+        torch.cuda.synchronize()
+        ms_take = a.elapsed_time(b)
+        t = torch.as_tensor(DevPtr(taken.device_ptr, n), device=rig.dev)
+        rows = torch.as_tensor(DevPtr(idx.device_ptr, n // 2), device=rig.dev).view(torch.int32)     # u32 indexes, 2 per i64
+        if desc:
+            ordered = bool((t[1:] < t[:-1]).all().item())
+        else:   # unsigned order of i64 views: flip the sign bit
+            u = t ^ (-(1 << 63))
+            ordered = bool((u[1:] >= u[:-1]).all().item())
+            del u
+        perm_ok = int(rows.sum(dtype=torch.int64).item()) == n * (n - 1) // 2
+        assert ordered and perm_ok, (name, ordered, perm_ok)
+        passes = 4 if desc else 8
+        out[name] = {"sort_ms": round(ms_sort, 3), "take_ms": round(ms_take, 3), "rows_per_s": n / (ms_sort * 1e-3), "passes": passes, "verified": True,
+                     "bytes": {"algorithmic_per_pass": 36 * n, "note": "12 B read for the histogram + 12 B read + 12 B written by the scatter, per row and pass"},
+                     "gb_per_s": passes * 36 * n / (ms_sort * 1e-3) / 1e9}
+        del t, rows
+        idx.free()
+        taken.free()
+    scrambled.free()
+    ctx.trim()           # 24 GB of sort scratch back to the device before the e2e leg
     return out
 
 

@@ -80,7 +80,7 @@ EXPORTS = [
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
     "fq_column_set_validity_bitmap", "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
-    "fq_sort_indices", "fq_column_take",
+    "fq_sort_indices", "fq_column_take", "fq_column_copy", "fq_ctx_trim",
     "fq_graph_begin", "fq_graph_end", "fq_graph_launch", "fq_graph_destroy", "fq_stream_create", "fq_stream_destroy",
 ]
 
@@ -165,6 +165,8 @@ def lib():
         "fq_utf8_minmax": (i32, [vp, i32, vp, C.POINTER(i64), vp]),
         "fq_sort_indices": (i32, [vp, vp, vp, i32, u64, vp, vp]),
         "fq_column_take": (i32, [vp, vp, vp, u64, vp, vp, vp]),
+        "fq_column_copy": (i32, [vp, vp, u64, vp, u64, u64, vp]),
+        "fq_ctx_trim": (i32, [vp]),
         "fq_stream_create": (i32, [vp, C.POINTER(vp)]),
         "fq_stream_destroy": (None, [vp, vp]),
         "fq_graph_begin": (i32, [vp, vp]),
@@ -372,6 +374,10 @@ class Context:
             self.check(lib().fq_column_set_validity(self._h, out._h, valid._h))
             out._validity = valid
         return out
+
+    def trim(self) -> None:
+        """give cached scratch memory (ORDER BY) back to the device"""
+        self.check(lib().fq_ctx_trim(self._h))
 
     def stream_create(self) -> int:
         """a non-blocking stream on this context's device (callers with CUDA bindings of their own pass their streams)"""

@@ -220,6 +220,12 @@ struct fq_ctx {
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::map<std::string, Module> modules;  // tag -> module
+  // ORDER BY scratch: kept between sorts (growing a 24-bytes-per-row buffer costs ~0.3 s per GB of fresh device memory, far
+  // more than the sort itself); fq_ctx_trim gives it back
+  std::mutex sort_mu;
+  void *sort_scratch = nullptr;
+  size_t sort_scratch_bytes = 0;
+  cudaEvent_t sort_done = nullptr;        // the last sort's final copy out of the scratch
   fq_graph *recording = nullptr;          // set between fq_graph_begin and fq_graph_end
   cudaStream_t recording_stream = nullptr;
   uint64_t recording_launches0 = 0;
@@ -570,7 +576,22 @@ void fq_ctx_destroy(fq_ctx *ctx) {
   cudaSetDevice(ctx->device);
   for (auto &kv : ctx->modules)
     if (kv.second.mod && g_drv.cuModuleUnload) g_drv.cuModuleUnload(kv.second.mod);
+  cudaFree(ctx->sort_scratch);
+  if (ctx->sort_done) cudaEventDestroy(ctx->sort_done);
   delete ctx;
+}
+
+fq_status fq_ctx_trim(fq_ctx *ctx) {
+  if (fq_status st = use(ctx)) return st;
+  std::lock_guard<std::mutex> lock(ctx->sort_mu);
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaFree(ctx->sort_scratch);
+  ctx->sort_scratch = nullptr;
+  ctx->sort_scratch_bytes = 0;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && pool) cudaMemPoolTrimTo(pool, 0);
+  cudaGetLastError();
+  return FQ_OK;
 }
 
 uint64_t fq_ctx_launch_count(const fq_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
@@ -737,6 +758,16 @@ fq_status fq_column_download_bits(fq_ctx *ctx, const fq_column *col, uint64_t ro
   ctx->launches++;
   CUDA_TRY(cudaMemcpyAsync(host_bits, stage, nbytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaFreeAsync(stage, s));
+  return FQ_OK;
+}
+fq_status fq_column_copy(fq_ctx *ctx, fq_column *dst, uint64_t dst_offset, const fq_column *src, uint64_t src_offset, uint64_t n_rows,
+                         void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (!dst || !src) return set_err(FQ_ERR_INVALID, "Internal Error: null argument");
+  if (dst->dtype != src->dtype) return set_err(FQ_ERR_INVALID, "Internal Error: copy between columns of different types");
+  if (dst_offset + n_rows > dst->len || src_offset + n_rows > src->len) return set_err(FQ_ERR_INVALID, "Internal Error: copy exceeds a column");
+  const size_t w = fq::dtype_size(src->dtype);
+  if (n_rows) CUDA_TRY(cudaMemcpyAsync((char *)dst->ptr + dst_offset * w, (const char *)src->ptr + src_offset * w, n_rows * w, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return FQ_OK;
 }
 fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream) {
@@ -1994,24 +2025,36 @@ fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8
   const unsigned n_tiles = (unsigned)((n + FQ_SORT_TILE - 1) / FQ_SORT_TILE);
   const uint64_t hist_len = 256ull * n_tiles;
   const unsigned scan_blocks = (unsigned)((hist_len + FQ_SCAN_TILE - 1) / FQ_SCAN_TILE);
-  fq_u64 *code[2] = {nullptr, nullptr}, *and_or = nullptr;
-  fq_u32 *idx[2] = {nullptr, nullptr}, *hist = nullptr, *sums = nullptr;
-  auto release = [&]() {
-    for (void *p : {(void *)code[0], (void *)code[1], (void *)idx[0], (void *)idx[1], (void *)hist, (void *)sums, (void *)and_or})
-      if (p) cudaFreeAsync(p, s);
-  };
-  cudaError_t e = cudaMallocAsync((void **)&code[0], 8 * n, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&code[1], 8 * n, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&idx[0], 4 * n, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&idx[1], 4 * n, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&hist, 4 * hist_len, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&sums, 4 * (uint64_t)scan_blocks, s);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&and_or, 16, s);
-  if (e != cudaSuccess) {
-    release();
-    cudaGetLastError();
-    return set_err(FQ_ERR_CUDA, "CUDA error: %s (sort scratch for %" PRIu64 " rows)", cudaGetErrorString(e), n);
+  // scratch: two (code, row) buffers, the (digit, tile) counters, the scan's tile sums, the AND / OR words
+  auto up = [](uint64_t b) { return (b + 255) & ~255ull; };
+  const uint64_t need = 2 * up(8 * n) + 2 * up(4 * n) + up(4 * hist_len) + up(4 * (uint64_t)scan_blocks) + 256;
+  std::lock_guard<std::mutex> sort_lock(ctx->sort_mu);
+  if (!ctx->sort_done) CUDA_TRY(cudaEventCreateWithFlags(&ctx->sort_done, cudaEventDisableTiming));
+  if (need > ctx->sort_scratch_bytes) {
+    cudaFree(ctx->sort_scratch);   // (synchronises the device: nothing still reads the old buffer)
+    ctx->sort_scratch = nullptr;
+    ctx->sort_scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->sort_scratch, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_err(FQ_ERR_CUDA, "CUDA error: %s (sort scratch of %" PRIu64 " bytes for %" PRIu64 " rows)", cudaGetErrorString(e), need, n);
+    }
+    ctx->sort_scratch_bytes = need;
+  } else {
+    CUDA_TRY(cudaStreamWaitEvent(s, ctx->sort_done, 0));   // an earlier sort on another stream may still be copying its result out
   }
+  char *at = (char *)ctx->sort_scratch;
+  auto carve = [&](uint64_t b) { char *p = at; at += up(b); return p; };
+  fq_u64 *code[2], *and_or;
+  fq_u32 *idx[2], *hist, *sums;
+  code[0] = (fq_u64 *)carve(8 * n);
+  code[1] = (fq_u64 *)carve(8 * n);
+  idx[0] = (fq_u32 *)carve(4 * n);
+  idx[1] = (fq_u32 *)carve(4 * n);
+  hist = (fq_u32 *)carve(4 * hist_len);
+  sums = (fq_u32 *)carve(4 * (uint64_t)scan_blocks);
+  and_or = (fq_u64 *)carve(16);
+  CUDA_TRY(cudaFuncSetAttribute(fq_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SORT_SMEM));   // per device: not cached
   int cur = 0;             // code[cur] / idx[cur] hold the pairs in their current order
   bool have_perm = false;  // false until the first key was encoded (identity order)
   const unsigned enc_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
@@ -2052,7 +2095,7 @@ fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8
         fq_sort_hist<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], n, n_tiles, 8 * d, hist);
         ctx->launches++;
         if ((status = sort_scan(ctx, hist, hist_len, sums, s)) != FQ_OK) break;
-        fq_sort_scatter<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], idx[cur], code[cur ^ 1], idx[cur ^ 1], hist, n, n_tiles, 8 * d);
+        fq_sort_scatter<<<n_tiles, FQ_SORT_THREADS, FQ_SORT_SMEM, s>>>(code[cur], idx[cur], code[cur ^ 1], idx[cur ^ 1], hist, n, n_tiles, 8 * d);
         ctx->launches++;
         cur ^= 1;
       }
@@ -2061,9 +2104,9 @@ fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8
   if (status == FQ_OK) {
     cudaError_t ce = cudaMemcpyAsync(indices->ptr, idx[cur], 4 * n, cudaMemcpyDeviceToDevice, s);
     if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->sort_done, s);
     if (ce != cudaSuccess) status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(ce));
   }
-  release();
   return status;
 }
 

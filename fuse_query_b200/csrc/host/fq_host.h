@@ -355,10 +355,11 @@ using Partitions = std::vector<Partition>;
 struct PlanNode;
 using PlanNodeRef = std::shared_ptr<const PlanNode>;
 struct PlanNode {
-  enum Kind { Empty, Projection, Aggregate, Filter, Limit, Scan, ReadSource, Explain, Select } kind = Empty;
+  enum Kind { Empty, Projection, Aggregate, Filter, Limit, Scan, ReadSource, Explain, Select, Sort } kind = Empty;
   PlanNodeRef input;                      // Projection / Aggregate / Filter / Limit input; Explain / Select child plan
   DataSchemaRef schema_;                  // Empty, Projection, Aggregate, Scan (projected), ReadSource
-  std::vector<ExpressionPlan> expr;       // Projection exprs / Aggregate aggr_expr
+  std::vector<ExpressionPlan> expr;       // Projection exprs / Aggregate aggr_expr / Sort keys (over the input's output columns)
+  std::vector<bool> descending;           // Sort: per key
   std::vector<ExpressionPlan> group_expr; // Aggregate
   ExpressionPlan predicate;               // Filter
   size_t n = 0;                           // Limit
@@ -390,6 +391,8 @@ class PlanBuilder {
   PlanBuilder aggregate(const std::vector<ExpressionPlan> &group_expr, const std::vector<ExpressionPlan> &aggr_expr) const;
   PlanBuilder filter(const ExpressionPlan &expr) const;
   PlanBuilder limit(size_t n) const;
+  // ORDER BY (the reference plans no sort: README.md:28); keys are expressions over the input plan's output columns
+  PlanBuilder sort(const std::vector<ExpressionPlan> &keys, const std::vector<bool> &descending) const;
   PlanBuilder select() const;
   PlanBuilder explain() const;
   PlanNode build() const { return plan_; }
@@ -663,6 +666,22 @@ class GpuGroupByTransform : public IProcessor {
   std::optional<ExpressionPlan> predicate_;
   DataSchemaRef schema_;
   std::vector<ExpressionPlan> group_expr_, aggr_expr_;
+};
+
+// ORDER BY: gathers every block of its input, evaluates the key expressions over them, sorts row indexes on the device
+// (fq_sort_indices: stable, NULLs first, ASC unless DESC) and emits one block with every column gathered in that order.
+// The reference has no sort operator (README.md:28 "[ ] Sorting"); semantics in oracle/sort.py.
+class GpuSortTransform : public IProcessor {
+ public:
+  GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending);
+  FUSE_TRANSFORM_COMMON("GpuSortTransform")
+  SendableDataBlockStream execute() override;
+
+ private:
+  FuseQueryContextRef ctx_;
+  std::vector<ExpressionPlan> keys_;
+  std::vector<bool> descending_;
+  IProcessorRef input_ = std::make_shared<EmptyProcessor>();
 };
 
 // processors/pipeline.rs:13-135

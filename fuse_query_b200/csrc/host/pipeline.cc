@@ -412,6 +412,83 @@ SendableDataBlockStream AggregateFinalTransform::execute() {   // transform_aggr
 SendableDataBlockStream LimitTransform::execute() { return std::make_unique<LimitStream>(input_->execute(), limit_); }
 
 // ---------------------------------------------------------------------------------------------
+// GpuSortTransform — ORDER BY (no counterpart in the reference: README.md:28 "[ ] Sorting")
+// ---------------------------------------------------------------------------------------------
+GpuSortTransform::GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending)
+    : ctx_(std::move(ctx)), keys_(std::move(keys)), descending_(std::move(descending)) {
+  descending_.resize(keys_.size(), false);
+}
+SendableDataBlockStream GpuSortTransform::execute() {
+  GpuContextRef gpu = ctx_->gpu();
+  auto stream = input_->execute();
+  std::vector<DataBlock> blocks;
+  DataSchemaRef schema;
+  while (auto block = stream->next()) {
+    if (!schema) schema = block->schema();
+    if (block->num_rows() > 0) blocks.push_back(*block);
+  }
+  if (blocks.empty()) return std::make_unique<DataBlockStream>(std::vector<DataBlock>{});
+  const size_t n_cols = blocks[0].num_columns();
+  uint64_t n = 0;
+  for (const auto &b : blocks) n += b.num_rows();
+  if (n >= (1ull << 32)) throw FuseQueryError::internal("Unsupported on the device path: ORDER BY over 2^32 rows or more");
+  // every block of the input as one block (a sort is a pipeline breaker)
+  std::vector<DataArrayRef> cols(n_cols);
+  for (size_t c = 0; c < n_cols; c++) {
+    if (blocks[0].column(c)->is_utf8()) throw FuseQueryError::internal("Unsupported on the device path: ORDER BY over a block with a Utf8 column");
+    if (blocks.size() == 1) {
+      cols[c] = blocks[0].column(c);
+      continue;
+    }
+    bool nullable = false;
+    for (const auto &b : blocks) nullable = nullable || b.column(c)->validity();
+    cols[c] = DataArray::alloc(gpu, blocks[0].column(c)->data_type(), n);
+    DataArrayRef valid = nullable ? DataArray::alloc(gpu, FQ_BOOL, n) : nullptr;
+    uint64_t at = 0;
+    for (const auto &b : blocks) {
+      const DataArrayRef &src = b.column(c);
+      gpu->check(fq_column_copy(gpu->raw(), cols[c]->column(), at, src->column(), 0, src->len(), gpu->stream));
+      if (valid) {
+        DataArrayRef v = src->validity();
+        if (!v) {   // a NOT NULL piece of a nullable column: all ones
+          std::vector<unsigned char> ones(src->len(), 1);
+          v = DataArray::from_host(gpu, FQ_BOOL, ones.data(), src->len());
+        }
+        gpu->check(fq_column_copy(gpu->raw(), valid->column(), at, v->column(), 0, src->len(), gpu->stream));
+        gpu->check(fq_stream_synchronize(gpu->raw(), gpu->stream));   // `v` may be a temporary
+      }
+      at += src->len();
+    }
+    if (valid) cols[c]->set_validity(valid);
+  }
+  gpu->check(fq_stream_synchronize(gpu->raw(), gpu->stream));
+  DataBlock all(schema, cols);
+  // the keys: expressions over the block's columns, all in one projection launch
+  std::vector<FunctionRef> funcs;
+  std::vector<const Function *> raw;
+  for (const auto &k : keys_) funcs.push_back(k.to_function());
+  for (auto &f : funcs) raw.push_back(f.get());
+  ProjectResult keys = run_project(gpu, all, nullptr, raw, -1, false);
+  std::vector<const fq_column *> key_cols;
+  std::vector<uint8_t> desc;
+  for (size_t k = 0; k < keys.columns.size(); k++) {
+    key_cols.push_back(keys.columns[k]->column());
+    desc.push_back(descending_[k] ? 1 : 0);
+  }
+  DataArrayRef rows = DataArray::alloc(gpu, FQ_U32, n);
+  gpu->check(fq_sort_indices(gpu->raw(), key_cols.data(), desc.data(), (int32_t)key_cols.size(), n, rows->column(), gpu->stream));
+  std::vector<DataArrayRef> sorted(n_cols);
+  for (size_t c = 0; c < n_cols; c++) {
+    sorted[c] = DataArray::alloc(gpu, cols[c]->data_type(), n);
+    DataArrayRef valid = cols[c]->validity() ? DataArray::alloc(gpu, FQ_BOOL, n) : nullptr;
+    gpu->check(fq_column_take(gpu->raw(), cols[c]->column(), rows->column(), n, sorted[c]->column(), valid ? valid->column() : nullptr, gpu->stream));
+    if (valid) sorted[c]->set_validity(valid);
+  }
+  gpu->check(fq_stream_synchronize(gpu->raw(), gpu->stream));
+  return std::make_unique<DataBlockStream>(std::vector<DataBlock>{DataBlock(schema, sorted)});
+}
+
+// ---------------------------------------------------------------------------------------------
 // GpuPipeTransform
 // ---------------------------------------------------------------------------------------------
 GpuPipeTransform::GpuPipeTransform(FuseQueryContextRef ctx, std::string db, std::string table, Partitions partitions,
@@ -852,6 +929,10 @@ Pipeline PipelineBuilder::build() const {
         }
         break;
       }
+      case PlanNode::Sort:   // a pipeline breaker: every pipe meets in one sort processor
+        if (pipeline.pipe_num() > 1) pipeline.merge_processor();
+        pipeline.add_simple_transform([&]() { return std::make_shared<GpuSortTransform>(ctx, plan.expr, plan.descending); });
+        break;
       case PlanNode::Projection:
         pipeline.add_simple_transform([&]() { return std::make_shared<ProjectionTransform>(ctx, plan.schema(), plan.expr); });
         break;

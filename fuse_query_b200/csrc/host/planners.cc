@@ -77,13 +77,13 @@ std::string ExpressionPlan::to_string() const {   // Debug, :92-105
 // ---------------------------------------------------------------------------------------------
 DataSchemaRef PlanNode::schema() const {
   switch (kind) {
-    case Filter: case Limit: case Select: return input->schema();   // plan_filter.rs / plan_limit.rs forward the input schema
+    case Filter: case Limit: case Select: case Sort: return input->schema();   // plan_filter.rs / plan_limit.rs forward the input schema
     case Explain: throw FuseQueryError::internal("not implemented");   // unimplemented!() in the reference
     default: return schema_ ? schema_ : std::make_shared<DataSchema>();
   }
 }
 const char *PlanNode::name() const {
-  static const char *n[] = {"EmptyPlan", "ProjectionPlan", "AggregatePlan", "FilterPlan", "LimitPlan", "ScanPlan", "ReadSourcePlan", "ExplainPlan", "SelectPlan"};
+  static const char *n[] = {"EmptyPlan", "ProjectionPlan", "AggregatePlan", "FilterPlan", "LimitPlan", "ScanPlan", "ReadSourcePlan", "ExplainPlan", "SelectPlan", "SortPlan"};
   return n[kind];
 }
 static std::vector<PlanNode> to_array(const PlanNode &root, bool with_parent) {   // plan_node.rs:55-125
@@ -93,7 +93,7 @@ static std::vector<PlanNode> to_array(const PlanNode &root, bool with_parent) { 
     if (depth > 128) throw FuseQueryError::plan("PlanNode depth more than 128");
     bool stop = false;
     switch (plan->kind) {
-      case PlanNode::Aggregate: case PlanNode::Projection: case PlanNode::Filter: case PlanNode::Limit:
+      case PlanNode::Aggregate: case PlanNode::Projection: case PlanNode::Filter: case PlanNode::Limit: case PlanNode::Sort:
         result.push_back(*plan);
         plan = plan->input.get();
         break;
@@ -119,6 +119,7 @@ PlanNode PlanNode::plans_to_node(const std::vector<PlanNode> &plans) {   // :135
       case Aggregate: b = b.aggregate(p.group_expr, p.expr); break;
       case Filter: b = b.filter(p.predicate); break;
       case Limit: b = b.limit(p.n); break;
+      case Sort: b = b.sort(p.expr, p.descending); break;
       case ReadSource: b = PlanBuilder::from(p); break;
       case Explain: b = b.explain(); break;
       case Select: b = b.select(); break;
@@ -150,6 +151,10 @@ std::string PlanNode::to_string() const {   // plan_display.rs:66-88
         break;
       case Filter: out += prefix + " Filter: " + node.predicate.to_string(); break;
       case Limit: out += prefix + " Limit: " + std::to_string(node.n); break;
+      case Sort:
+        out += prefix + " Sort: ";
+        for (size_t i = 0; i < node.expr.size(); i++) out += (i ? ", " : "") + node.expr[i].to_string() + (node.descending[i] ? " desc" : "");
+        break;
       case ReadSource:
         out += prefix + " ReadDataSource: scan parts [" + std::to_string(node.partitions.size()) + "]" + node.description;
         break;
@@ -218,6 +223,21 @@ PlanBuilder PlanBuilder::limit(size_t n) const {
   PlanNode p;
   p.kind = PlanNode::Limit;
   p.n = n;
+  p.input = std::make_shared<PlanNode>(plan_);
+  return PlanBuilder(p);
+}
+PlanBuilder PlanBuilder::sort(const std::vector<ExpressionPlan> &keys, const std::vector<bool> &descending) const {
+  DataSchemaRef in = plan_.schema();
+  PlanNode p;
+  p.kind = PlanNode::Sort;
+  for (const auto &e : keys) {
+    if (e.is_aggregate())
+      throw FuseQueryError::plan("ORDER BY sorts the query's output columns: name the aggregate's column (or its alias) instead of " + e.to_string());
+    (void)e.to_field(*in);   // every column a key names must be an output column of the input plan
+  }
+  p.expr = keys;
+  p.descending = descending;
+  p.descending.resize(keys.size(), false);
   p.input = std::make_shared<PlanNode>(plan_);
   return PlanBuilder(p);
 }
@@ -321,7 +341,7 @@ struct SqlParser {
   static bool reserved(const std::string &w0) {
     std::string w = w0;
     std::transform(w.begin(), w.end(), w.begin(), ::toupper);
-    static const char *kws[] = {"FROM", "WHERE", "GROUP", "HAVING", "LIMIT", "ORDER", "AS", "AND", "OR", "BY", "SELECT", "UNION"};
+    static const char *kws[] = {"FROM", "WHERE", "GROUP", "HAVING", "LIMIT", "ORDER", "AS", "AND", "OR", "BY", "SELECT", "UNION", "ASC", "DESC"};
     for (const char *k : kws) if (w == k) return true;
     return false;
   }
@@ -475,7 +495,19 @@ PlanNode select_to_plan(FuseQueryContextRef ctx, SqlParser &sp) {   // plan_pars
   } else {
     plan = PlanBuilder::from(plan).project(projection).build();
   }
-  if (sp.eat_kw("ORDER")) throw FuseQueryError::internal("ORDER BY is not implemented yet");
+  if (sp.eat_kw("ORDER")) {   // no counterpart in plan_parser.rs (query.order_by is never read): SortPlan over the output columns
+    if (!sp.eat_kw("BY")) sp.expected("BY");
+    std::vector<ExpressionPlan> keys;
+    std::vector<bool> desc;
+    do {
+      keys.push_back(sp.expr());
+      bool d = false;
+      if (sp.eat_kw("DESC")) d = true;
+      else sp.eat_kw("ASC");
+      desc.push_back(d);
+    } while (sp.eat_sym(","));
+    plan = PlanBuilder::from(plan).sort(keys, desc).build();
+  }
   if (sp.eat_kw("LIMIT")) {   // :311-328
     ExpressionPlan l = sp.expr();
     if (!(l.kind == ExpressionPlan::Constant && l.value.tag == FQ_U64 && l.value.some)) throw FuseQueryError::plan("Unexpected expression for LIMIT clause");

@@ -10,7 +10,7 @@
 // 32-bit row index — the payload columns are gathered once at the end (fq_take_kernel), they never ride through the passes.
 // One pass handles one 8-bit digit: per-tile digit histograms, one exclusive scan over all (digit, tile) counters in
 // digit-major order, and a scatter in which every warp ranks its rows with MATCH.ANY (lanes holding the same digit) against
-// per-warp digit counters in shared memory: stable by construction, no atomics.  Digits whose bits are the same in
+// per-warp digit counters in shared memory: stable by construction.  Digits whose bits are the same in
 // every code (AND == OR, folded during encoding) are skipped: numbers below 2^32 cost four passes, not eight.
 // Bound: HBM; per pass 12 B read twice (histogram, scatter; the second read hits L2 for small inputs) + 12 B written per row.
 #pragma once
@@ -93,19 +93,40 @@ __global__ void __launch_bounds__(256) fq_sort_encode(const __grid_constant__ fq
   }
 }
 
-// per-warp digit counts of this CTA's tile: cnt[w][d] = rows of warp w's run whose digit is d
-__device__ __forceinline__ void fq_sort_count(fq_u32 (*cnt)[256], const fq_u64 *code, fq_u64 n, fq_u64 base, int shift) {
+// The tile is read once, up front, into registers (FQ_SORT_ITEMS independent loads per thread in flight), and ranking is
+// split so that no round waits for the one before it.  The first version ranked inside the scatter loop — MATCH, a read of
+// the warp's counter, the stores, the leader's write-back, next round — and ncu showed what a chain of shared-memory round
+// trips costs: 108 cycles per issued instruction, 58 % of them short-scoreboard stalls, 3.6 % issue-slot use, 10.8 ms for
+// 2.5e8 rows.  Now the counting phase leaves, per row, its rank among the warp's earlier rows of the same digit (the value
+// the leader's shared-memory atomicAdd returns, plus the row's position among its peers), and the scatter only adds the
+// (tile, warp, digit) base: independent work per round.
+// Warp w owns the tile's rows [w * WARP_ITEMS, (w + 1) * WARP_ITEMS); round r of a warp = 32 consecutive rows.
+#define FQ_SORT_ROUNDS (FQ_SORT_WARP_ITEMS / 32)
+__device__ __forceinline__ fq_u64 fq_sort_row(fq_u64 base, int r) {
+  return base + (fq_u64)(threadIdx.x >> 5) * FQ_SORT_WARP_ITEMS + r * 32 + (threadIdx.x & 31);
+}
+
+// per-warp digit counts of this CTA's tile: cnt[w][d] = rows of warp w's run whose digit is d (digit 256 = past the end).
+// RANKS: dg[r] becomes digit | rank << 16, rank = rows of the warp's run before this one with the same digit (rounds are
+// issued in order by one warp, and shared-memory atomics of a warp on one address complete in issue order).
+template <bool RANKS>
+__device__ __forceinline__ void fq_sort_count(fq_u32 (*cnt)[256], fq_u32 (&dg)[FQ_SORT_ROUNDS]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < FQ_SORT_WARPS * 256; i += FQ_SORT_THREADS) (&cnt[0][0])[i] = 0;
   __syncthreads();
-#pragma unroll 4
-  for (int r = 0; r < FQ_SORT_WARP_ITEMS / 32; r++) {
-    const fq_u64 i = base + (fq_u64)warp * FQ_SORT_WARP_ITEMS + r * 32 + lane;
-    const bool in = i < n;
-    const fq_u32 digit = in ? (fq_u32)(code[i] >> shift) & 255u : 256u;
-    const fq_u32 peers = __match_any_sync(0xffffffffu, digit);
-    if (in && lane == __ffs(peers) - 1) cnt[warp][digit] += __popc(peers);   // one lane per digit per round: no atomics
-    __syncwarp();
+#pragma unroll
+  for (int r = 0; r < FQ_SORT_ROUNDS; r++) {
+    const fq_u32 d = dg[r];
+    const fq_u32 peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    if constexpr (RANKS) {
+      fq_u32 before = 0;
+      if (lane == leader && d < 256u) before = atomicAdd(&cnt[warp][d], (fq_u32)__popc(peers));
+      before = __shfl_sync(0xffffffffu, before, leader);
+      dg[r] = d | ((before + __popc(peers & ((1u << lane) - 1))) << 16);   // lanes in row order: stable
+    } else {
+      if (lane == leader && d < 256u) atomicAdd(&cnt[warp][d], (fq_u32)__popc(peers));
+    }
   }
   __syncthreads();
 }
@@ -113,44 +134,85 @@ __device__ __forceinline__ void fq_sort_count(fq_u32 (*cnt)[256], const fq_u64 *
 // hist[d * n_tiles + tile] = rows of the tile whose digit is d (digit-major: one scan gives every (digit, tile) its base)
 __global__ void __launch_bounds__(FQ_SORT_THREADS) fq_sort_hist(const fq_u64 *code, fq_u64 n, fq_u32 n_tiles, int shift, fq_u32 *hist) {
   __shared__ fq_u32 cnt[FQ_SORT_WARPS][256];
-  fq_sort_count(cnt, code, n, (fq_u64)blockIdx.x * FQ_SORT_TILE, shift);
+  const fq_u64 base = (fq_u64)blockIdx.x * FQ_SORT_TILE;
+  fq_u32 dg[FQ_SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < FQ_SORT_ROUNDS; r++) {
+    const fq_u64 i = fq_sort_row(base, r);
+    dg[r] = i < n ? (fq_u32)(code[i] >> shift) & 255u : 256u;
+  }
+  fq_sort_count<false>(cnt, dg);
   fq_u32 c = 0;
 #pragma unroll
   for (int w = 0; w < FQ_SORT_WARPS; w++) c += cnt[w][threadIdx.x];
   hist[(fq_u64)threadIdx.x * n_tiles + blockIdx.x] = c;
 }
 
-__global__ void __launch_bounds__(FQ_SORT_THREADS) fq_sort_scatter(const fq_u64 *code, const fq_u32 *idx, fq_u64 *code_out, fq_u32 *idx_out,
-                                                                   const fq_u32 *hist_scanned, fq_u64 n, fq_u32 n_tiles, int shift) {
-  __shared__ fq_u32 cnt[FQ_SORT_WARPS][256];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Dynamic shared memory of the scatter kernel: the tile's pairs in digit-major order, then the counters.
+#define FQ_SORT_SMEM (FQ_SORT_TILE * 12 + FQ_SORT_WARPS * 256 * 4 + 256 * 4 + 32 * 4)
+
+__device__ __forceinline__ fq_u32 fq_block_exclusive_scan(fq_u32 x, fq_u32 *warp_sums, fq_u32 &total);
+
+// The tile is first ordered by digit in shared memory and then written out: the rows of one digit form one contiguous run
+// in the output, so consecutive threads store consecutive addresses.  (Storing straight from the ranking loop sent every
+// lane of a store to a different 32-byte sector: ncu counted 6 of 32 bytes used per sector, 4.8 GB written and 4.7 GB
+// read for 3 GB each way, the extra reads being read-modify-write fills of partial sectors.)
+__global__ void __launch_bounds__(FQ_SORT_THREADS, 3) fq_sort_scatter(const fq_u64 *code, const fq_u32 *idx, fq_u64 *code_out, fq_u32 *idx_out,
+                                                                      const fq_u32 *hist_scanned, fq_u64 n, fq_u32 n_tiles, int shift) {
+  extern __shared__ __align__(16) unsigned char fq_sort_smem[];
+  fq_u64 *s_code = (fq_u64 *)fq_sort_smem;
+  fq_u32 *s_row = (fq_u32 *)(s_code + FQ_SORT_TILE);
+  fq_u32(*cnt)[256] = (fq_u32(*)[256])(s_row + FQ_SORT_TILE);
+  fq_u32 *g_base = &cnt[0][0] + FQ_SORT_WARPS * 256;   // [256] global position of local slot 0 of the digit's run, minus the run's start
+  fq_u32 *ws = g_base + 256;                           // [32]
+  const int warp = threadIdx.x >> 5;
   const fq_u64 base = (fq_u64)blockIdx.x * FQ_SORT_TILE;
-  fq_sort_count(cnt, code, n, base, shift);
-  {  // thread d: where the tile's rows of digit d go, then where each warp's share of them starts
-    fq_u32 run = hist_scanned[(fq_u64)threadIdx.x * n_tiles + blockIdx.x];
+  fq_u64 c[FQ_SORT_ROUNDS];
+  fq_u32 row[FQ_SORT_ROUNDS], dg[FQ_SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < FQ_SORT_ROUNDS; r++) {
+    const fq_u64 i = fq_sort_row(base, r);
+    const bool in = i < n;
+    c[r] = in ? code[i] : 0;
+    row[r] = in ? idx[i] : 0;
+    dg[r] = in ? (fq_u32)(c[r] >> shift) & 255u : 256u;
+  }
+  fq_sort_count<true>(cnt, dg);
+  {  // thread d: the tile's rows of digit d — each warp's share starts after the earlier warps', the run after the smaller digits
+    fq_u32 total = 0;
 #pragma unroll
     for (int w = 0; w < FQ_SORT_WARPS; w++) {
-      const fq_u32 c = cnt[w][threadIdx.x];
-      cnt[w][threadIdx.x] = run;
-      run += c;
+      const fq_u32 k = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = total;
+      total += k;
+    }
+    fq_u32 all;
+    const fq_u32 start = fq_block_exclusive_scan(total, ws, all);   // local slot of the run's first row
+#pragma unroll
+    for (int w = 0; w < FQ_SORT_WARPS; w++) cnt[w][threadIdx.x] += start;
+    g_base[threadIdx.x] = hist_scanned[(fq_u64)threadIdx.x * n_tiles + blockIdx.x] - start;   // (mod 2^32)
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < FQ_SORT_ROUNDS; r++) {
+    const fq_u32 d = dg[r] & 0xffffu;
+    if (d < 256u) {
+      const fq_u32 at = cnt[warp][d] + (dg[r] >> 16);
+      s_code[at] = c[r];
+      s_row[at] = row[r];
     }
   }
   __syncthreads();
-#pragma unroll 4
-  for (int r = 0; r < FQ_SORT_WARP_ITEMS / 32; r++) {
-    const fq_u64 i = base + (fq_u64)warp * FQ_SORT_WARP_ITEMS + r * 32 + lane;
-    const bool in = i < n;
-    const fq_u64 c = in ? code[i] : 0;
-    const fq_u32 digit = in ? (fq_u32)(c >> shift) & 255u : 256u;
-    const fq_u32 peers = __match_any_sync(0xffffffffu, digit);
-    if (in) {
-      const fq_u32 at = cnt[warp][digit] + __popc(peers & ((1u << lane) - 1));   // lanes in row order: stable
-      code_out[at] = c;
-      idx_out[at] = idx[i];
+  const fq_u32 in_tile = (fq_u32)(n - base < (fq_u64)FQ_SORT_TILE ? n - base : (fq_u64)FQ_SORT_TILE);
+#pragma unroll
+  for (int k = 0; k < FQ_SORT_ITEMS; k++) {
+    const fq_u32 l = threadIdx.x + k * FQ_SORT_THREADS;
+    if (l < in_tile) {
+      const fq_u64 v = s_code[l];
+      const fq_u32 at = g_base[(fq_u32)(v >> shift) & 255u] + l;
+      code_out[at] = v;
+      idx_out[at] = s_row[l];
     }
-    __syncwarp();
-    if (in && lane == __ffs(peers) - 1) cnt[warp][digit] += __popc(peers);
-    __syncwarp();
   }
 }
 

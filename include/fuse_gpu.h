@@ -151,6 +151,9 @@ fq_status fq_column_upload_bits(fq_ctx *ctx, fq_column *col, uint64_t row_offset
                                 uint64_t n_rows, void *stream);
 fq_status fq_column_download_bits(fq_ctx *ctx, const fq_column *col, uint64_t row_offset, void *host_bits, uint64_t n_rows,
                                   void *stream);
+/* device-to-device: dst[dst_offset .. +n_rows) = src[src_offset .. +n_rows) (same type; values only) */
+fq_status fq_column_copy(fq_ctx *ctx, fq_column *dst, uint64_t dst_offset, const fq_column *src, uint64_t src_offset, uint64_t n_rows,
+                         void *stream);
 fq_status fq_stream_synchronize(fq_ctx *ctx, void *stream);
 /* `stream` arguments are cudaStream_t handles of the caller (NULL = the default stream).  A host without CUDA bindings of
  * its own gets one here: a non-blocking stream on the context's device. */
@@ -377,7 +380,9 @@ fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row);
  * floats by IEEE total order.  Several keys: lexicographic, keys[0] most significant.
  * fq_sort_indices writes the permutation (row indexes in sorted order, UInt32, so fewer than 2^32 rows) and fq_column_take
  * applies it to a column: out[i] = src[rows[i]], validity (bytes or bitmap) gathered into out_valid when the source has one.
- * Stable LSD radix sort, one pass per 8-bit digit that differs between some two rows; scratch is 24 bytes per row. */
+ * Stable LSD radix sort, one pass per 8-bit digit that differs between some two rows; scratch is 24 bytes per row, kept by
+ * the context between sorts (fq_ctx_trim returns it); sorts of one context run one at a time. */
+fq_status fq_ctx_trim(fq_ctx *ctx);   /* frees cached scratch memory (synchronises the device) */
 fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
                           fq_column *indices, void *stream);
 fq_status fq_column_take(fq_ctx *ctx, const fq_column *src, const fq_column *rows, uint64_t n, fq_column *out, fq_column *out_valid,

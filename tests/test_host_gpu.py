@@ -710,6 +710,42 @@ def test_group_by_through_sql_matches_the_group_by_oracle(gpu):
         h.execute_sql(ctx, f"select sum(number), count(number) from system.numbers_mt({n}) group by sum(number)")
 
 
+def test_order_by_through_sql_matches_the_sort_oracle(gpu):
+    """ORDER BY executes as a device sort (GpuSortTransform -> fq_sort_indices / fq_column_take) between the projection or
+    aggregation and the LIMIT.  The reference does not sort (README.md:28), so the oracle is the stated semantics
+    (oracle/sort.py: ASC unless DESC, NULLs first, stable in partition order)."""
+    from fuse_query_b200.tables import register_table
+    from oracle.sort import sort_indices
+    n = 160_000                      # 8 partitions of whole 10 000-row blocks (SURVEY F7 drops the tail of others)
+    for workers in (0, 1):          # 8 pipes merged in partition order / one pipe
+        ctx = make_ctx(gpu, workers)
+        blocks = h.execute_sql(ctx, f"select number, number / 3 as t from system.numbers_mt({n}) where number - number / 7 * 7 = 3 "
+                                    "order by number - number / 5 * 5 desc, number limit 7")
+        x = np.arange(n, dtype=np.uint64)
+        x = x[x % 7 == 3]
+        perm = sort_indices([x % 5, x], descending=[True, False])[:7]
+        assert rows_of(blocks) == [(int(v), int(v) // 3) for v in x[perm]]
+    # GROUP BY ... ORDER BY an aggregate's output column (by its display name or alias), descending
+    ctx = make_ctx(gpu, 1)
+    blocks = h.execute_sql(ctx, f"select number - number / 7 * 7 as k, sum(number) as s from system.numbers_mt({n}) group by number - number / 7 * 7 order by s desc")
+    x = np.arange(n, dtype=np.uint64)
+    sums = [(int(k), int(x[x % 7 == k].sum())) for k in range(7)]
+    assert rows_of(blocks) == sorted(sums, key=lambda r: -r[1])
+    # a table with NULLs: NULL keys first, ties keep table order; the payload's validity travels with the rows
+    rng = np.random.default_rng(5)
+    m = 30_000
+    a = rng.integers(-20, 20, m).astype(np.int32)
+    a_ok = rng.random(m) > 0.2
+    b = rng.normal(size=m)
+    b_ok = rng.random(m) > 0.5
+    register_table(ctx, gpu, "default", "srt", {"a": (a, a_ok), "b": (b, b_ok)})
+    got = rows_of(h.execute_sql(ctx, "select a, b from srt order by a desc, b"))
+    perm = sort_indices([a, b], [a_ok, b_ok], [True, False])
+    want = [(int(a[i]) if a_ok[i] else None, float(b[i]) if b_ok[i] else None) for i in perm]
+    assert got == want
+    assert rows_of(h.execute_sql(ctx, "select a from srt where a > 100 order by a")) == []
+
+
 def test_utf8_arrays_on_the_device(gpu):
     """Arrow string arrays on the device (fq_utf8): every comparison operator array/array, array/scalar and scalar/array
     (flipped like data_array_comparison.rs:75-85), NULL slots, min / max with ties and empties — against python's own

@@ -298,3 +298,22 @@ def test_more_than_eight_select_items_plan_without_a_device(ctx):
     assert len(plan.children_to_plans()[1].schema().names()) == 12
     with pytest.raises(h.FuseQueryError):
         h.execute_sql(ctx, sql)
+
+
+def test_order_by_plans_a_sort_over_the_output_columns(ctx):
+    """The reference accepts ORDER BY and drops it (sqlparser parses it, plan_parser.rs never reads query.order_by; README.md:28
+    lists sorting as open).  Here it becomes a SortPlan between the projection / aggregate and the LIMIT, its keys resolved
+    against the query's OUTPUT columns; EXPLAIN shows it, the optimizer keeps it."""
+    sql = "explain select number + 1 as c1, number from system.numbers_mt(100) where c1 > 3 order by number desc, c1 + 1 limit 5"
+    text = h.execute_sql(ctx, sql)[0].column(0).to_list()[0]
+    assert text.splitlines()[:3] == ["└─ Limit: 5", "  └─ Sort: number desc, (c1 + 1)", "    └─ Projection: (number + 1) as c1, number"]
+    plan = h.Optimizer.create().optimize(h.Planner().build_from_sql(ctx, sql.replace("explain ", "")))
+    assert [p.name() for p in plan.children_to_plans()] == ["ReadSourcePlan", "FilterPlan", "ProjectionPlan", "SortPlan", "LimitPlan"]
+    pipe = h.PipelineBuilder.create(ctx, plan).build()
+    assert "GpuSortTransform × 1 processor" in str(pipe) and "LimitTransform × 1 processor" in str(pipe)
+    for bad, err in [("select number from system.numbers_mt(10) order by nope", "nope"),
+                     ("select sum(number) from system.numbers_mt(10) order by sum(number)", "ORDER BY sorts the query's output columns"),
+                     ("select number from system.numbers_mt(10) order number", "BY")]:
+        with pytest.raises(h.FuseQueryError) as e:
+            h.Planner().build_from_sql(ctx, bad)
+        assert err in str(e.value), str(e.value)
