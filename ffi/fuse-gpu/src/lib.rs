@@ -231,6 +231,29 @@ impl Column {
         unsafe { sys::fq_column_dtype(self.raw) }
     }
 
+    /// ORDER BY: the row indexes (UInt32) that put `keys` in order — lexicographic, keys[0] most significant, ascending unless
+    /// `descending[j]`, NULLs first, ties in input order (fq_sort_indices; the reference has no sort, README.md:28).
+    pub fn sort_indices(ctx: &Arc<GpuContext>, keys: &[&Column], descending: &[bool], n_rows: u64, stream: *mut c_void) -> FuseQueryResult<Column> {
+        let out = Column::alloc(ctx, sys::FQ_U32, n_rows.max(1))?;
+        let raw: Vec<*const sys::fq_column> = keys.iter().map(|k| k.raw as *const sys::fq_column).collect();
+        let desc: Vec<u8> = (0..keys.len()).map(|j| descending.get(j).copied().unwrap_or(false) as u8).collect();
+        check(ctx.raw, unsafe { sys::fq_sort_indices(ctx.raw, raw.as_ptr(), desc.as_ptr(), raw.len() as i32, n_rows, out.raw, stream) })?;
+        Ok(out)
+    }
+
+    /// out[i] = self[rows[i]] for the first `n` row indexes; the validity (bytes or bitmap) travels into a byte validity column.
+    pub fn take(&self, rows: &Column, n: u64, nullable: bool, stream: *mut c_void) -> FuseQueryResult<Column> {
+        let mut out = Column::alloc(&self.ctx, self.dtype(), n.max(1))?;
+        let valid = if nullable { Some(Box::new(Column::alloc(&self.ctx, sys::FQ_BOOL, n.max(1))?)) } else { None };
+        let vraw = valid.as_ref().map(|v| v.raw).unwrap_or(ptr::null_mut());
+        check(self.ctx.raw, unsafe { sys::fq_column_take(self.ctx.raw, self.raw, rows.raw, n, out.raw, vraw, stream) })?;
+        if let Some(v) = valid {
+            check(self.ctx.raw, unsafe { sys::fq_column_set_validity(self.ctx.raw, out.raw, v.raw) })?;
+            out.validity = Some(v);
+        }
+        Ok(out)
+    }
+
     pub fn slice(self: &Arc<Self>, offset: u64, len: u64) -> FuseQueryResult<Column> {
         let mut raw = ptr::null_mut();
         check(self.ctx.raw, unsafe { sys::fq_column_slice(self.ctx.raw, self.raw, offset, len, &mut raw) })?;

@@ -42,6 +42,14 @@ case $what in
     cap agg_nullable_u8_bits_4e9 "_agg_" python tools/prof_agg.py 4000000000 nullable_u8_bits
     for k in 7 1000 5000 1000000; do cap groupby_k${k}_1e9 groupby python tools/prof_groupby.py 1000000000 $k; done
     ;;
+  sortcap)
+    # ORDER BY kernels: the scatter and the histogram of one pass over 2.5e8 scrambled 64-bit keys
+    cap() { name=$1; regex=$2; shift 2; timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 3 --launch-count 1 -o gpurun_out/ncu_$name -f "$@" > gpurun_out/ncu_$name.log 2>&1; echo "ncu $name rc=$?";
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page details > gpurun_out/ncu_$name.details.txt 2>/dev/null;
+            ncu -i gpurun_out/ncu_$name.ncu-rep --page raw --csv > gpurun_out/ncu_$name.raw.csv 2>/dev/null; rm -f gpurun_out/ncu_$name.ncu-rep; }
+    cap sort_scatter_2.5e8 fq_sort_scatter python tools/prof_sort.py 250000000 scrambled
+    cap sort_hist_2.5e8 fq_sort_hist python tools/prof_sort.py 250000000 scrambled
+    ;;
   profiles)
     # ncu captures for profiles/: every kernel of the path, --set full, one launch each after warm-up
     # (the .ncu-rep files are summarised on the box and removed: gpurun copies back at most 64 MiB)
