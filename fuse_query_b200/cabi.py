@@ -356,9 +356,10 @@ class Context:
         self.check(lib().fq_stream_synchronize(self._h, C.c_void_p(stream)))
 
     # ---- ORDER BY ----
-    def sort_indices(self, keys: Sequence["Column"], n: int, descending: Optional[Sequence[bool]] = None, stream: int = 0) -> "Column":
+    def sort_indices(self, keys: Sequence["Column"], n: int, descending: Optional[Sequence[bool]] = None, stream: int = 0,
+                     out: Optional["Column"] = None) -> "Column":
         """Row indexes (UInt32) that put `keys` in order: lexicographic, keys[0] most significant, NULLs first, stable."""
-        out = self.column(U32, max(1, n))
+        out = out if out is not None else self.column(U32, max(1, n))
         arr = (C.c_void_p * len(keys))(*[k._h for k in keys])
         desc = (C.c_uint8 * len(keys))(*[1 if (descending and descending[j]) else 0 for j in range(len(keys))])
         self.check(lib().fq_sort_indices(self._h, arr, desc, len(keys), n, out._h, C.c_void_p(stream)))
