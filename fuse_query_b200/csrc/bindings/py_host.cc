@@ -295,6 +295,7 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def_readonly("expr", &PlanNode::expr)
       .def_readonly("predicate", &PlanNode::predicate)
       .def_readonly("n", &PlanNode::n)
+      .def_readonly("descending", &PlanNode::descending)
       .def_property_readonly("input", [](const PlanNode &p) { return *p.input; })
       .def("__str__", &PlanNode::to_string)
       .def("__repr__", &PlanNode::to_string);
@@ -366,6 +367,10 @@ PYBIND11_MODULE(_fuse_host, m) {
       .def_static("try_create", [](FuseQueryContextRef c, std::shared_ptr<DataSchema> s, const std::vector<ExpressionPlan> &e) { return std::make_shared<ProjectionTransform>(c, s, e); });
   py::class_<AggregatePartialTransform, IProcessor, std::shared_ptr<AggregatePartialTransform>>(m, "AggregatePartialTransform")
       .def_static("try_create", [](FuseQueryContextRef c, std::shared_ptr<DataSchema> s, const std::vector<ExpressionPlan> &e) { return std::make_shared<AggregatePartialTransform>(c, s, e); });
+  py::class_<GpuSortTransform, IProcessor, std::shared_ptr<GpuSortTransform>>(m, "GpuSortTransform")
+      .def_static("try_create", [](FuseQueryContextRef c, const std::vector<ExpressionPlan> &keys, const std::vector<bool> &desc) {
+        return std::make_shared<GpuSortTransform>(c, keys, desc);
+      });
   py::class_<AggregateFinalTransform, IProcessor, std::shared_ptr<AggregateFinalTransform>>(m, "AggregateFinalTransform")
       .def_static("try_create", [](FuseQueryContextRef c, std::shared_ptr<DataSchema> s, const std::vector<ExpressionPlan> &e) { return std::make_shared<AggregateFinalTransform>(c, s, e); });
   py::class_<LimitTransform, IProcessor, std::shared_ptr<LimitTransform>>(m, "LimitTransform")

@@ -4,7 +4,8 @@ The reference runs one pipe per chunk of partitions and merges them at MergeProc
 (processors/pipeline_builder.rs:73-95, processor_merge.rs:37-66).  Here each rank runs the fused GpuPipeTransform
 over ITS consecutive partitions; what crosses ranks is exactly what crosses the reference's merge channel:
 the partial-state block (one Utf8/JSON row per aggregate expression, transform_aggregate_partial.rs:61-72) or the
-filtered + projected rows.  The final stage (AggregateFinalTransform / LimitTransform) is the unchanged host logic.
+filtered + projected rows.  The final stage (AggregateFinalTransform / LimitTransform) is the unchanged host logic; an
+ORDER BY (GpuSortTransform, no counterpart in the reference) runs on every rank over the merged rows.
 torch.distributed is plumbing: NCCL (or gloo) carries a few hundred bytes per rank.
 """
 from __future__ import annotations
@@ -38,21 +39,48 @@ def execute_sql_distributed(ctx, sql: str, rank: int, world: int, all_gather_obj
     sel = plans[i]
     is_agg = sel.name() == "AggregatePlan"
     i += 1
+    sort = None
+    if i < len(plans) and plans[i].name() == "SortPlan":
+        sort = plans[i]
+        i += 1
     limit = None
     if i < len(plans) and plans[i].name() == "LimitPlan":
         limit = plans[i].n
         i += 1
     if i != len(plans) or sel.name() not in ("AggregatePlan", "ProjectionPlan"):
         # e.g. a derived table: its outer Filter / Projection would have to run after the cross-rank merge
-        raise h.FuseQueryError("Internal Error: distributed execution supports ReadSource [Filter] (Projection | Aggregate) [Limit], got "
+        raise h.FuseQueryError("Internal Error: distributed execution supports ReadSource [Filter] (Projection | Aggregate) [Sort] [Limit], got "
                                + " -> ".join(p.name() for p in plans))
+    if sort is not None and (sel.name() != "ProjectionPlan" or gpu is None):
+        raise h.FuseQueryError("Internal Error: distributed ORDER BY needs a projection query and the rank's device context")
     parts = _my_partitions(list(src.partitions), rank, world)
     names = sel.schema().names()
     local_blocks = []
     if parts:
         pipe = h.GpuPipeTransform.try_create(ctx, src.db, src.table, parts, pred, is_agg, sel.schema(), sel.expr,
-                                             None if is_agg else limit)
+                                             None if (is_agg or sort is not None) else limit)
         local_blocks = pipe.execute().collect()
+    if sort is not None:
+        # A sort is a pipeline breaker: every rank's rows meet (rank order = partition order, so ties keep the order one
+        # process would give them) and every rank sorts the whole on its device.  Merge-then-sort: right, not scalable — a
+        # range-partitioned sort (sample, all-to-all, local sorts) is what a large result would need.
+        mine = [[b.column(c).to_numpy() for c in range(b.num_columns())] for b in local_blocks if b.num_rows() > 0]
+        valid = [[(b.column(c).validity().to_numpy() if b.column(c).validity() is not None else None) for c in range(b.num_columns())]
+                 for b in local_blocks if b.num_rows() > 0]
+        gathered = all_gather_object((mine, valid))
+        blocks = []
+        for per_rank, per_rank_valid in gathered:
+            for cols, vals in zip(per_rank, per_rank_valid):
+                arrays = [h.DataArray.from_numpy(gpu, np.ascontiguousarray(a)) if v is None else h.DataArray.from_numpy_masked(gpu, np.ascontiguousarray(a), np.asarray(v) != 0)
+                          for a, v in zip(cols, vals)]
+                blocks.append(h.DataBlock.create(sel.schema(), arrays))
+        if not blocks:
+            return names, []
+        srt = h.GpuSortTransform.try_create(ctx, sort.expr, list(sort.descending))
+        srt.connect_to(h.DataBlockSource(blocks))
+        out = srt.execute().collect()
+        rows = [r for b in out for r in zip(*[b.column(c).to_list() for c in range(b.num_columns())])]
+        return names, rows[:limit] if limit is not None else rows
     if is_agg:
         mine = [b.column(0).to_list() for b in local_blocks]            # JSON rows of this rank's partial block(s)
         gathered = all_gather_object(mine)

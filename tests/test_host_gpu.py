@@ -359,7 +359,8 @@ def test_two_rank_distributed_sql(gpu):
     sqls = [f"select sum(number)/count(number), max(number), min(number) from system.numbers_mt({n})",
             f"select (number+1) as c1, number/2 as c2 from system.numbers_mt({n}) where (c1+c2+1) < 100 limit 3",
             f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number",
-            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number limit 5"]
+            f"select number from system.numbers_mt({n}) where number/1000000*1000000 = number limit 5",
+            f"select number, number - number/7*7 as m from system.numbers_mt({n}) where number/1000000*1000000 = number order by m desc, number limit 6"]
     mpctx = mp.get_context("spawn")
     q = mpctx.Queue()
     port = 29800 + (os.getpid() % 150)
@@ -374,7 +375,10 @@ def test_two_rank_distributed_sql(gpu):
     assert got[0] == (["Sum(number) / Count(number)", "Max(number)", "Min(number)"], [(s // n, n - 1, 0)])
     assert got[1] == (["c1", "c2"], [(1, 0), (2, 0), (3, 1)])
     assert got[2] == (["number"], [(k * 1000000,) for k in range(16)])
-    assert got[3] == (["number"], [(k * 1000000,) for k in range(5)]) and got[4] == got[1]
+    assert got[3] == (["number"], [(k * 1000000,) for k in range(5)]) and got[5] == got[1]
+    # ORDER BY across ranks: every rank's rows meet in partition order, then one device sort (NULLs first, stable) and the LIMIT
+    want = sorted([(k * 1000000, (k * 1000000) % 7) for k in range(16)], key=lambda r: (-r[1], r[0]))[:6]
+    assert got[4] == (["number", "m"], want)
 
 
 # ---------------------------------------------------------------------------------------------
