@@ -173,6 +173,24 @@ int main(void) {
     EXPECT(a[0] == 1 && a[1] == 2 && a[2] == 3);
   }
   fq_graph_destroy(ctx, graph);
+
+  /* ORDER BY number DESC LIMIT 3 over the first million rows: permutation, gather, copy (fq_sort_indices / fq_column_take / fq_column_copy) */
+  const uint64_t m = 1000000;
+  fq_column *head = NULL, *perm = NULL, *sorted = NULL, *top = NULL;
+  CHECK(fq_column_slice(ctx, col, 0, m, &head));
+  CHECK(fq_column_alloc(ctx, FQ_U32, m, &perm));
+  CHECK(fq_column_alloc(ctx, FQ_U64, m, &sorted));
+  CHECK(fq_column_alloc(ctx, FQ_U64, 3, &top));
+  const fq_column *keys[1] = {head};
+  const uint8_t desc[1] = {1};
+  CHECK(fq_sort_indices(ctx, keys, desc, 1, m, perm, stream));
+  CHECK(fq_column_take(ctx, head, perm, m, sorted, NULL, stream));
+  CHECK(fq_column_copy(ctx, top, 0, sorted, 0, 3, stream));
+  CHECK(fq_column_download(ctx, top, 0, a, 3, stream));
+  CHECK(fq_stream_synchronize(ctx, stream));
+  EXPECT(a[0] == m - 1 && a[1] == m - 2 && a[2] == m - 3);
+  CHECK(fq_ctx_trim(ctx));
+  fq_column_free(ctx, top); fq_column_free(ctx, sorted); fq_column_free(ctx, perm); fq_column_free(ctx, head);
   fq_stream_destroy(ctx, stream);
 
   fq_pipe_destroy(ctx, bad);
