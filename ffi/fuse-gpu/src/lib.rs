@@ -241,6 +241,17 @@ impl Column {
         Ok(out)
     }
 
+    /// ORDER BY ... LIMIT: the first min(limit, n_rows) indexes of the same order (radix select when one NOT NULL key decides).
+    pub fn sort_indices_limit(ctx: &Arc<GpuContext>, keys: &[&Column], descending: &[bool], n_rows: u64, limit: u64, stream: *mut c_void)
+                              -> FuseQueryResult<(Column, u64)> {
+        let out = Column::alloc(ctx, sys::FQ_U32, limit.min(n_rows).max(1))?;
+        let raw: Vec<*const sys::fq_column> = keys.iter().map(|k| k.raw as *const sys::fq_column).collect();
+        let desc: Vec<u8> = (0..keys.len()).map(|j| descending.get(j).copied().unwrap_or(false) as u8).collect();
+        let mut count = 0u64;
+        check(ctx.raw, unsafe { sys::fq_sort_indices_limit(ctx.raw, raw.as_ptr(), desc.as_ptr(), raw.len() as i32, n_rows, limit, out.raw, &mut count, stream) })?;
+        Ok((out, count))
+    }
+
     /// out[i] = self[rows[i]] for the first `n` row indexes; the validity (bytes or bitmap) travels into a byte validity column.
     pub fn take(&self, rows: &Column, n: u64, nullable: bool, stream: *mut c_void) -> FuseQueryResult<Column> {
         let mut out = Column::alloc(&self.ctx, self.dtype(), n.max(1))?;

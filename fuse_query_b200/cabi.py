@@ -80,7 +80,7 @@ EXPORTS = [
     "fq_pipe_key_dtype", "fq_pipe_leaf_dtype", "fq_pipe_groupby_reserve", "fq_pipe_launch_groupby", "fq_pipe_fetch_groupby",
     "fq_pipe_export_groups", "fq_pipe_group_entry_slots", "fq_pipe_export_partials", "fq_pipe_merge_partials",
     "fq_column_set_validity_bitmap", "fq_utf8_create", "fq_utf8_free", "fq_utf8_len", "fq_utf8_compare", "fq_utf8_compare_scalar", "fq_utf8_minmax",
-    "fq_sort_indices", "fq_column_take", "fq_column_copy", "fq_ctx_trim",
+    "fq_sort_indices", "fq_sort_indices_limit", "fq_column_take", "fq_column_copy", "fq_ctx_trim",
     "fq_graph_begin", "fq_graph_end", "fq_graph_launch", "fq_graph_destroy", "fq_stream_create", "fq_stream_destroy",
 ]
 
@@ -164,6 +164,7 @@ def lib():
         "fq_utf8_compare_scalar": (i32, [vp, i32, vp, vp, u64, vp, vp, vp]),
         "fq_utf8_minmax": (i32, [vp, i32, vp, C.POINTER(i64), vp]),
         "fq_sort_indices": (i32, [vp, vp, vp, i32, u64, vp, vp]),
+        "fq_sort_indices_limit": (i32, [vp, vp, vp, i32, u64, u64, vp, C.POINTER(u64), vp]),
         "fq_column_take": (i32, [vp, vp, vp, u64, vp, vp, vp]),
         "fq_column_copy": (i32, [vp, vp, u64, vp, u64, u64, vp]),
         "fq_ctx_trim": (i32, [vp]),
@@ -364,6 +365,16 @@ class Context:
         desc = (C.c_uint8 * len(keys))(*[1 if (descending and descending[j]) else 0 for j in range(len(keys))])
         self.check(lib().fq_sort_indices(self._h, arr, desc, len(keys), n, out._h, C.c_void_p(stream)))
         return out
+
+    def sort_indices_limit(self, keys: Sequence["Column"], n: int, limit: int, descending: Optional[Sequence[bool]] = None,
+                           stream: int = 0) -> Tuple["Column", int]:
+        """ORDER BY ... LIMIT: the first min(limit, n) row indexes of the order sort_indices gives -> (column, count)."""
+        out = self.column(U32, max(1, min(limit, n)))
+        arr = (C.c_void_p * len(keys))(*[k._h for k in keys])
+        desc = (C.c_uint8 * len(keys))(*[1 if (descending and descending[j]) else 0 for j in range(len(keys))])
+        count = C.c_uint64()
+        self.check(lib().fq_sort_indices_limit(self._h, arr, desc, len(keys), n, limit, out._h, C.byref(count), C.c_void_p(stream)))
+        return out, count.value
 
     def take(self, src: "Column", rows: "Column", n: int, stream: int = 0) -> "Column":
         """out[i] = src[rows[i]]; the result carries byte validity when the source has validity of either form."""

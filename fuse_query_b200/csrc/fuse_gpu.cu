@@ -2008,106 +2008,203 @@ fq_status sort_scan(fq_ctx *ctx, fq_u32 *a, uint64_t m, fq_u32 *sums, cudaStream
 }
 }  // namespace
 
-fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
-                          fq_column *indices, void *stream) {
-  if (fq_status st = use(ctx)) return st;
+namespace {
+// One ORDER BY over the context's scratch (held under ctx->sort_mu by the caller): (code, row) pairs in code[cur] / idx[cur].
+struct SortJob {
+  fq_ctx *ctx;
+  cudaStream_t s;
+  fq_u64 *code[2] = {nullptr, nullptr}, *and_or = nullptr;
+  fq_u32 *idx[2] = {nullptr, nullptr}, *hist = nullptr, *sums = nullptr, *small = nullptr;   // small: 256 + 2 counters (radix select)
+  int cur = 0;
+
+  // scratch for n rows: two (code, row) buffers, the (digit, tile) counters, the scan's tile sums, a few words
+  fq_status acquire(uint64_t n) {
+    const uint64_t n_tiles = (n + FQ_SORT_TILE - 1) / FQ_SORT_TILE, hist_len = 256 * n_tiles;
+    const uint64_t scan_blocks = (hist_len + FQ_SCAN_TILE - 1) / FQ_SCAN_TILE;
+    auto up = [](uint64_t b) { return (b + 255) & ~255ull; };
+    const uint64_t need = 2 * up(8 * n) + 2 * up(4 * n) + up(4 * hist_len) + up(4 * scan_blocks) + 256 + 2048;
+    if (!ctx->sort_done) CUDA_TRY(cudaEventCreateWithFlags(&ctx->sort_done, cudaEventDisableTiming));
+    if (need > ctx->sort_scratch_bytes) {
+      cudaFree(ctx->sort_scratch);   // (synchronises the device: nothing still reads the old buffer)
+      ctx->sort_scratch = nullptr;
+      ctx->sort_scratch_bytes = 0;
+      cudaError_t e = cudaMalloc(&ctx->sort_scratch, need);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(FQ_ERR_CUDA, "CUDA error: %s (sort scratch of %" PRIu64 " bytes for %" PRIu64 " rows)", cudaGetErrorString(e), need, n);
+      }
+      ctx->sort_scratch_bytes = need;
+    } else {
+      CUDA_TRY(cudaStreamWaitEvent(s, ctx->sort_done, 0));   // an earlier sort on another stream may still be copying its result out
+    }
+    char *at = (char *)ctx->sort_scratch;
+    auto carve = [&](uint64_t b) { char *p = at; at += up(b); return p; };
+    code[0] = (fq_u64 *)carve(8 * n);
+    code[1] = (fq_u64 *)carve(8 * n);
+    idx[0] = (fq_u32 *)carve(4 * n);
+    idx[1] = (fq_u32 *)carve(4 * n);
+    hist = (fq_u32 *)carve(4 * hist_len);
+    sums = (fq_u32 *)carve(4 * scan_blocks);
+    and_or = (fq_u64 *)carve(16);
+    small = (fq_u32 *)carve(2048);
+    CUDA_TRY(cudaFuncSetAttribute(fq_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SORT_SMEM));   // per device: not cached
+    return FQ_OK;
+  }
+
+  // one stable pass over digit d of the first m pairs
+  fq_status radix_pass(uint64_t m, int d) {
+    const unsigned n_tiles = (unsigned)((m + FQ_SORT_TILE - 1) / FQ_SORT_TILE);
+    fq_sort_hist<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], m, n_tiles, 8 * d, hist);
+    ctx->launches++;
+    if (fq_status st = sort_scan(ctx, hist, 256ull * n_tiles, sums, s)) return st;
+    fq_sort_scatter<<<n_tiles, FQ_SORT_THREADS, FQ_SORT_SMEM, s>>>(code[cur], idx[cur], code[cur ^ 1], idx[cur ^ 1], hist, m, n_tiles, 8 * d);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    cur ^= 1;
+    return FQ_OK;
+  }
+
+  // codes of one key (phase 0: values, phase 1: the NULLs-first flag) for the first m pairs, through idx[cur] when have_perm;
+  // *varying = the bits that differ between some two codes
+  fq_status encode(const fq_column *k, bool desc, int phase, bool have_perm, uint64_t m, uint64_t *varying) {
+    static const uint64_t init[2] = {~0ull, 0ull};
+    CUDA_TRY(cudaMemcpyAsync(and_or, init, 16, cudaMemcpyHostToDevice, s));
+    fq_sort_encode_params a;
+    memset(&a, 0, sizeof a);
+    a.col = k->ptr;
+    a.valid_bytes = k->validity ? (const fq_u8 *)k->validity->ptr : nullptr;
+    a.valid_bits = (!k->validity && k->validity_bits) ? k->validity_bits->ptr : nullptr;
+    a.valid_bit0 = k->validity_bit0;
+    a.perm = have_perm ? idx[cur] : nullptr;
+    a.code_out = code[cur];
+    a.idx_out = idx[cur];
+    a.and_or = and_or;
+    a.n = m;
+    a.dtype = (int)k->dtype;
+    a.bits = 8 * (int)fq::dtype_size(k->dtype);
+    a.descending = desc ? 1 : 0;
+    a.flags_only = phase;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m + 255) / 256, (uint64_t)ctx->sm_count * 8));
+    fq_sort_encode<<<grid, 256, 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    uint64_t h[2];
+    CUDA_TRY(cudaMemcpyAsync(h, and_or, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *varying = h[0] ^ h[1];
+    return FQ_OK;
+  }
+
+  // one stable sort per key, last key first; inside a key: its value digits, then (nullable keys) the NULLs-first bit
+  fq_status sort_by_keys(const fq_column *const *keys, const uint8_t *descending, int n_keys, uint64_t m, bool have_perm) {
+    for (int j = n_keys - 1; j >= 0; j--) {
+      const fq_column *k = keys[j];
+      const bool nullable = k->validity || k->validity_bits;
+      for (int phase = 0; phase < (nullable ? 2 : 1); phase++) {
+        uint64_t varying = 0;
+        if (fq_status st = encode(k, descending && descending[j], phase, have_perm, m, &varying)) return st;
+        have_perm = true;
+        const int digits = phase ? 1 : (int)fq::dtype_size(k->dtype);
+        for (int d = 0; d < digits; d++) {
+          if (((varying >> (8 * d)) & 255) == 0) continue;   // every row has the same digit: the pass would be the identity
+          if (fq_status st = radix_pass(m, d)) return st;
+        }
+      }
+    }
+    return FQ_OK;
+  }
+
+  fq_status finish(fq_column *indices, uint64_t count) {
+    if (count) CUDA_TRY(cudaMemcpyAsync(indices->ptr, idx[cur], 4 * count, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaEventRecord(ctx->sort_done, s));
+    return FQ_OK;
+  }
+
+  // ORDER BY one NOT NULL key LIMIT `limit` (limit < n): radix select, then a sort of what is left
+  fq_status top_k(const fq_column *key, bool desc, uint64_t n, uint64_t limit, fq_column *indices) {
+    uint64_t varying = 0;
+    if (fq_status st = encode(key, desc, 0, false, n, &varying)) return st;   // code[cur] = codes, idx[cur] = 0 .. n-1
+    if (varying == 0) return finish(indices, limit);   // every key is the same: the first rows, in input order
+    uint64_t m = n, need = limit, winners = 0;
+    fq_u32 *win = (fq_u32 *)indices->ptr;   // winners collect in the result column (fewer than `limit` of them), unordered
+    for (int d = (int)fq::dtype_size(key->dtype) - 1; d >= 0; d--) {
+      if (((varying >> (8 * d)) & 255) == 0) continue;
+      if (m <= std::max<uint64_t>(4 * need, 1ull << 16)) break;   // small enough to sort
+      CUDA_TRY(cudaMemsetAsync(small, 0, 4 * 258, s));
+      const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((m + 255) / 256, (uint64_t)ctx->sm_count * 8));
+      fq_topk_hist<<<grid, 256, 0, s>>>(code[cur], m, 8 * d, small);
+      CUDA_TRY(cudaGetLastError());
+      ctx->launches++;
+      uint32_t h[256];
+      CUDA_TRY(cudaMemcpyAsync(h, small, sizeof h, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      uint64_t below = 0;
+      unsigned bucket = 0;
+      for (; bucket < 255 && below + h[bucket] < need; bucket++) below += h[bucket];   // the bucket that holds the need-th smallest
+      fq_topk_partition<<<grid, 256, 0, s>>>(code[cur], idx[cur], m, 8 * d, bucket, win + winners, code[cur ^ 1], idx[cur ^ 1], small + 256);
+      CUDA_TRY(cudaGetLastError());
+      ctx->launches++;
+      winners += below;
+      need -= below;
+      m = h[bucket];
+      cur ^= 1;
+    }
+    // what is left: the winners and the last candidates, first in input order, then (stable) by key
+    if (winners) CUDA_TRY(cudaMemcpyAsync(idx[cur] + m, win, 4 * winners, cudaMemcpyDeviceToDevice, s));
+    const uint64_t t = m + winners;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((t + 255) / 256, (uint64_t)ctx->sm_count * 8));
+    fq_sort_rows_as_codes<<<grid, 256, 0, s>>>(idx[cur], code[cur], t);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    for (int d = 0; d < 4; d++)
+      if (((n - 1) >> (8 * d)) != 0)
+        if (fq_status st = radix_pass(t, d)) return st;
+    const uint8_t dflag = desc ? 1 : 0;
+    if (fq_status st = sort_by_keys(&key, &dflag, 1, t, true)) return st;
+    return finish(indices, std::min(limit, t));
+  }
+};
+
+fq_status sort_check(fq_ctx *ctx, const fq_column *const *keys, int32_t n_keys, uint64_t n_rows, uint64_t slots, const fq_column *indices) {
   if (!keys || n_keys < 1 || !indices) return set_err(FQ_ERR_INVALID, "Internal Error: sort needs at least one key column and an index column");
-  if (indices->dtype != FQ_U32 || indices->len < n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: the index column must be UInt32 with at least n_rows slots");
+  if (indices->dtype != FQ_U32 || indices->len < slots) return set_err(FQ_ERR_INVALID, "Internal Error: the index column must be UInt32 with a slot per result row");
   if (n_rows >= (1ull << 32)) return set_err(FQ_ERR_INVALID, "Internal Error: sort handles fewer than 2^32 rows per call");
   if (ctx->recording) return set_err(FQ_ERR_INVALID, "Internal Error: a sort cannot be recorded into a graph (its passes depend on the data)");
   for (int j = 0; j < n_keys; j++) {
     if (!keys[j] || keys[j]->len < n_rows) return set_err(FQ_ERR_INVALID, "Internal Error: sort key %d is shorter than n_rows", j);
     if (keys[j]->dtype == FQ_NULL || keys[j]->dtype == FQ_UTF8) return set_err(FQ_ERR_UNSUPPORTED, "Unsupported on the device path: sort key of type %s", fq::dtype_name(keys[j]->dtype));
   }
+  return FQ_OK;
+}
+}  // namespace
+
+fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
+                          fq_column *indices, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  if (fq_status st = sort_check(ctx, keys, n_keys, n_rows, n_rows, indices)) return st;
   if (n_rows == 0) return FQ_OK;
-  cudaStream_t s = (cudaStream_t)stream;
-  const uint64_t n = n_rows;
-  const unsigned n_tiles = (unsigned)((n + FQ_SORT_TILE - 1) / FQ_SORT_TILE);
-  const uint64_t hist_len = 256ull * n_tiles;
-  const unsigned scan_blocks = (unsigned)((hist_len + FQ_SCAN_TILE - 1) / FQ_SCAN_TILE);
-  // scratch: two (code, row) buffers, the (digit, tile) counters, the scan's tile sums, the AND / OR words
-  auto up = [](uint64_t b) { return (b + 255) & ~255ull; };
-  const uint64_t need = 2 * up(8 * n) + 2 * up(4 * n) + up(4 * hist_len) + up(4 * (uint64_t)scan_blocks) + 256;
   std::lock_guard<std::mutex> sort_lock(ctx->sort_mu);
-  if (!ctx->sort_done) CUDA_TRY(cudaEventCreateWithFlags(&ctx->sort_done, cudaEventDisableTiming));
-  if (need > ctx->sort_scratch_bytes) {
-    cudaFree(ctx->sort_scratch);   // (synchronises the device: nothing still reads the old buffer)
-    ctx->sort_scratch = nullptr;
-    ctx->sort_scratch_bytes = 0;
-    cudaError_t e = cudaMalloc(&ctx->sort_scratch, need);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return set_err(FQ_ERR_CUDA, "CUDA error: %s (sort scratch of %" PRIu64 " bytes for %" PRIu64 " rows)", cudaGetErrorString(e), need, n);
-    }
-    ctx->sort_scratch_bytes = need;
-  } else {
-    CUDA_TRY(cudaStreamWaitEvent(s, ctx->sort_done, 0));   // an earlier sort on another stream may still be copying its result out
-  }
-  char *at = (char *)ctx->sort_scratch;
-  auto carve = [&](uint64_t b) { char *p = at; at += up(b); return p; };
-  fq_u64 *code[2], *and_or;
-  fq_u32 *idx[2], *hist, *sums;
-  code[0] = (fq_u64 *)carve(8 * n);
-  code[1] = (fq_u64 *)carve(8 * n);
-  idx[0] = (fq_u32 *)carve(4 * n);
-  idx[1] = (fq_u32 *)carve(4 * n);
-  hist = (fq_u32 *)carve(4 * hist_len);
-  sums = (fq_u32 *)carve(4 * (uint64_t)scan_blocks);
-  and_or = (fq_u64 *)carve(16);
-  CUDA_TRY(cudaFuncSetAttribute(fq_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, FQ_SORT_SMEM));   // per device: not cached
-  int cur = 0;             // code[cur] / idx[cur] hold the pairs in their current order
-  bool have_perm = false;  // false until the first key was encoded (identity order)
-  const unsigned enc_grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
-  fq_status status = FQ_OK;
-  // one stable sort per key, last key first; inside a key: its value digits, then (nullable keys) the NULLs-first bit
-  for (int j = n_keys - 1; j >= 0 && status == FQ_OK; j--) {
-    const fq_column *k = keys[j];
-    const bool nullable = k->validity || k->validity_bits;
-    for (int phase = 0; phase < (nullable ? 2 : 1) && status == FQ_OK; phase++) {
-      static const uint64_t init[2] = {~0ull, 0ull};
-      if (cudaMemcpyAsync(and_or, init, 16, cudaMemcpyHostToDevice, s) != cudaSuccess) { status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(cudaGetLastError())); break; }
-      fq_sort_encode_params a;
-      memset(&a, 0, sizeof a);
-      a.col = k->ptr;
-      a.valid_bytes = k->validity ? (const fq_u8 *)k->validity->ptr : nullptr;
-      a.valid_bits = (!k->validity && k->validity_bits) ? k->validity_bits->ptr : nullptr;
-      a.valid_bit0 = k->validity_bit0;
-      a.perm = have_perm ? idx[cur] : nullptr;
-      a.code_out = code[cur];
-      a.idx_out = idx[cur];
-      a.and_or = and_or;
-      a.n = n;
-      a.dtype = (int)k->dtype;
-      a.bits = 8 * (int)fq::dtype_size(k->dtype);
-      a.descending = (descending && descending[j]) ? 1 : 0;
-      a.flags_only = phase;
-      fq_sort_encode<<<enc_grid, 256, 0, s>>>(a);
-      ctx->launches++;
-      have_perm = true;
-      uint64_t h_and_or[2];
-      cudaError_t ce = cudaMemcpyAsync(h_and_or, and_or, 16, cudaMemcpyDeviceToHost, s);
-      if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-      if (ce != cudaSuccess) { status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(ce)); break; }
-      const uint64_t varying = h_and_or[0] ^ h_and_or[1];   // bits that differ between some two codes
-      const int digits = phase ? 1 : a.bits / 8;
-      for (int d = 0; d < digits; d++) {
-        if (((varying >> (8 * d)) & 255) == 0) continue;    // every row has the same digit: the pass would be the identity
-        fq_sort_hist<<<n_tiles, FQ_SORT_THREADS, 0, s>>>(code[cur], n, n_tiles, 8 * d, hist);
-        ctx->launches++;
-        if ((status = sort_scan(ctx, hist, hist_len, sums, s)) != FQ_OK) break;
-        fq_sort_scatter<<<n_tiles, FQ_SORT_THREADS, FQ_SORT_SMEM, s>>>(code[cur], idx[cur], code[cur ^ 1], idx[cur ^ 1], hist, n, n_tiles, 8 * d);
-        ctx->launches++;
-        cur ^= 1;
-      }
-    }
-  }
-  if (status == FQ_OK) {
-    cudaError_t ce = cudaMemcpyAsync(indices->ptr, idx[cur], 4 * n, cudaMemcpyDeviceToDevice, s);
-    if (ce == cudaSuccess) ce = cudaGetLastError();
-    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->sort_done, s);
-    if (ce != cudaSuccess) status = set_err(FQ_ERR_CUDA, "CUDA error: sort: %s", cudaGetErrorString(ce));
-  }
-  return status;
+  SortJob job{ctx, (cudaStream_t)stream};
+  if (fq_status st = job.acquire(n_rows)) return st;
+  if (fq_status st = job.sort_by_keys(keys, descending, n_keys, n_rows, false)) return st;
+  return job.finish(indices, n_rows);
+}
+
+fq_status fq_sort_indices_limit(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
+                                uint64_t limit, fq_column *indices, uint64_t *n_out, void *stream) {
+  if (fq_status st = use(ctx)) return st;
+  const uint64_t count = std::min(limit, n_rows);
+  if (fq_status st = sort_check(ctx, keys, n_keys, n_rows, count, indices)) return st;
+  if (n_out) *n_out = count;
+  if (count == 0) return FQ_OK;
+  std::lock_guard<std::mutex> sort_lock(ctx->sort_mu);
+  SortJob job{ctx, (cudaStream_t)stream};
+  if (fq_status st = job.acquire(n_rows)) return st;
+  // radix select pays when the result is a small part of the table and the order is decided by one NOT NULL key
+  const bool select = n_keys == 1 && !keys[0]->validity && !keys[0]->validity_bits && limit < n_rows / 64 && n_rows >= (1ull << 20);
+  if (select) return job.top_k(keys[0], descending && descending[0], n_rows, limit, indices);
+  if (fq_status st = job.sort_by_keys(keys, descending, n_keys, n_rows, false)) return st;
+  return job.finish(indices, count);
 }
 
 fq_status fq_column_take(fq_ctx *ctx, const fq_column *src, const fq_column *rows, uint64_t n, fq_column *out, fq_column *out_valid,

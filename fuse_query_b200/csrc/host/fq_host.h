@@ -673,7 +673,8 @@ class GpuGroupByTransform : public IProcessor {
 // The reference has no sort operator (README.md:28 "[ ] Sorting"); semantics in oracle/sort.py.
 class GpuSortTransform : public IProcessor {
  public:
-  GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending);
+  // `limit`: the LIMIT that follows the sort in the plan, if any — only that many rows are ordered and gathered
+  GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending, std::optional<size_t> limit = std::nullopt);
   FUSE_TRANSFORM_COMMON("GpuSortTransform")
   SendableDataBlockStream execute() override;
 
@@ -681,6 +682,7 @@ class GpuSortTransform : public IProcessor {
   FuseQueryContextRef ctx_;
   std::vector<ExpressionPlan> keys_;
   std::vector<bool> descending_;
+  std::optional<size_t> limit_;
   IProcessorRef input_ = std::make_shared<EmptyProcessor>();
 };
 

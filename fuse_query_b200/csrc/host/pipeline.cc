@@ -414,8 +414,8 @@ SendableDataBlockStream LimitTransform::execute() { return std::make_unique<Limi
 // ---------------------------------------------------------------------------------------------
 // GpuSortTransform — ORDER BY (no counterpart in the reference: README.md:28 "[ ] Sorting")
 // ---------------------------------------------------------------------------------------------
-GpuSortTransform::GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending)
-    : ctx_(std::move(ctx)), keys_(std::move(keys)), descending_(std::move(descending)) {
+GpuSortTransform::GpuSortTransform(FuseQueryContextRef ctx, std::vector<ExpressionPlan> keys, std::vector<bool> descending, std::optional<size_t> limit)
+    : ctx_(std::move(ctx)), keys_(std::move(keys)), descending_(std::move(descending)), limit_(limit) {
   descending_.resize(keys_.size(), false);
 }
 SendableDataBlockStream GpuSortTransform::execute() {
@@ -475,13 +475,19 @@ SendableDataBlockStream GpuSortTransform::execute() {
     key_cols.push_back(keys.columns[k]->column());
     desc.push_back(descending_[k] ? 1 : 0);
   }
-  DataArrayRef rows = DataArray::alloc(gpu, FQ_U32, n);
-  gpu->check(fq_sort_indices(gpu->raw(), key_cols.data(), desc.data(), (int32_t)key_cols.size(), n, rows->column(), gpu->stream));
+  // with a LIMIT behind the sort only its rows are ordered (radix select when one NOT NULL key decides) and gathered
+  uint64_t out_rows = limit_ ? std::min<uint64_t>(*limit_, n) : n;
+  DataArrayRef rows = DataArray::alloc(gpu, FQ_U32, std::max<uint64_t>(out_rows, 1));
+  if (limit_)
+    gpu->check(fq_sort_indices_limit(gpu->raw(), key_cols.data(), desc.data(), (int32_t)key_cols.size(), n, *limit_, rows->column(), &out_rows, gpu->stream));
+  else
+    gpu->check(fq_sort_indices(gpu->raw(), key_cols.data(), desc.data(), (int32_t)key_cols.size(), n, rows->column(), gpu->stream));
+  if (out_rows == 0) return std::make_unique<DataBlockStream>(std::vector<DataBlock>{});
   std::vector<DataArrayRef> sorted(n_cols);
   for (size_t c = 0; c < n_cols; c++) {
-    sorted[c] = DataArray::alloc(gpu, cols[c]->data_type(), n);
-    DataArrayRef valid = cols[c]->validity() ? DataArray::alloc(gpu, FQ_BOOL, n) : nullptr;
-    gpu->check(fq_column_take(gpu->raw(), cols[c]->column(), rows->column(), n, sorted[c]->column(), valid ? valid->column() : nullptr, gpu->stream));
+    sorted[c] = DataArray::alloc(gpu, cols[c]->data_type(), out_rows);
+    DataArrayRef valid = cols[c]->validity() ? DataArray::alloc(gpu, FQ_BOOL, out_rows) : nullptr;
+    gpu->check(fq_column_take(gpu->raw(), cols[c]->column(), rows->column(), out_rows, sorted[c]->column(), valid ? valid->column() : nullptr, gpu->stream));
     if (valid) sorted[c]->set_validity(valid);
   }
   gpu->check(fq_stream_synchronize(gpu->raw(), gpu->stream));
@@ -931,7 +937,11 @@ Pipeline PipelineBuilder::build() const {
       }
       case PlanNode::Sort:   // a pipeline breaker: every pipe meets in one sort processor
         if (pipeline.pipe_num() > 1) pipeline.merge_processor();
-        pipeline.add_simple_transform([&]() { return std::make_shared<GpuSortTransform>(ctx, plan.expr, plan.descending); });
+        {
+          std::optional<size_t> limit;
+          if (i + 1 < plans.size() && plans[i + 1].kind == PlanNode::Limit) limit = plans[i + 1].n;   // the LimitTransform still follows
+          pipeline.add_simple_transform([&]() { return std::make_shared<GpuSortTransform>(ctx, plan.expr, plan.descending, limit); });
+        }
         break;
       case PlanNode::Projection:
         pipeline.add_simple_transform([&]() { return std::make_shared<ProjectionTransform>(ctx, plan.schema(), plan.expr); });

@@ -290,6 +290,56 @@ __global__ void __launch_bounds__(FQ_SCAN_THREADS) fq_scan_tiles(fq_u32 *a, fq_u
   }
 }
 
+// ---- ORDER BY ... LIMIT k: radix select ----
+// The k smallest codes are found from the most significant digit down: a 256-bin histogram of the candidates' digit says
+// in which bucket the k-th smallest lies; rows of smaller buckets are winners, rows of that bucket are the next round's
+// candidates, everything else is dropped.  Two reads of the candidates per round, and the candidates shrink by up to
+// 256x per round; what is left (winners + last candidates) is sorted by (code, row) with the passes above.
+__global__ void __launch_bounds__(256) fq_topk_hist(const fq_u64 *code, fq_u64 m, int shift, fq_u32 *ghist) {
+  __shared__ fq_u32 cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (fq_u64)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[(fq_u32)(code[i] >> shift) & 255u], 1u);
+  __syncthreads();
+  if (cnt[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// winners (digit < bucket) -> win[], candidates (digit == bucket) -> (cand_code, cand_row); order inside each is arbitrary
+// (one atomicAdd per warp and output; the final sort orders by code and row).  cursors: [0] winners, [1] candidates.
+__global__ void __launch_bounds__(256) fq_topk_partition(const fq_u64 *code, const fq_u32 *rows, fq_u64 m, int shift, fq_u32 bucket, fq_u32 *win,
+                                                         fq_u64 *cand_code, fq_u32 *cand_row, fq_u32 *cursors) {
+  const int lane = threadIdx.x & 31;
+  const fq_u64 warps = ((fq_u64)gridDim.x * blockDim.x) >> 5;
+  for (fq_u64 i0 = (((fq_u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5; i0 < m; i0 += warps << 5) {
+    const fq_u64 i = i0 + lane;
+    const bool in = i < m;
+    const fq_u64 c = in ? code[i] : 0;
+    const fq_u32 d = (fq_u32)(c >> shift) & 255u;
+    const bool is_win = in && d < bucket, is_cand = in && d == bucket;
+    const fq_u32 mw = __ballot_sync(0xffffffffu, is_win), mc = __ballot_sync(0xffffffffu, is_cand);
+    fq_u32 bw = 0, bc = 0;
+    if (lane == 0) {
+      if (mw) bw = atomicAdd(&cursors[0], (fq_u32)__popc(mw));
+      if (mc) bc = atomicAdd(&cursors[1], (fq_u32)__popc(mc));
+    }
+    bw = __shfl_sync(0xffffffffu, bw, 0);
+    bc = __shfl_sync(0xffffffffu, bc, 0);
+    const fq_u32 below = (1u << lane) - 1;
+    if (is_win) win[bw + __popc(mw & below)] = rows[i];
+    if (is_cand) {
+      const fq_u32 at = bc + __popc(mc & below);
+      cand_code[at] = c;
+      cand_row[at] = rows[i];
+    }
+  }
+}
+
+// code = row index: the first sort of the final set, so that the stable key passes that follow break ties by input order
+__global__ void __launch_bounds__(256) fq_sort_rows_as_codes(const fq_u32 *rows, fq_u64 *code, fq_u64 m) {
+  for (fq_u64 i = (fq_u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (fq_u64)gridDim.x * blockDim.x) code[i] = rows[i];
+}
+
 // ---- gather: out[i] = src[rows[i]] (values of `width` bytes; validity bytes or bits -> validity bytes) ----
 struct fq_take_params {
   const void *src;

@@ -385,6 +385,11 @@ fq_status fq_pipe_fetch_limit_row(fq_ctx *ctx, fq_pipe *pipe, uint64_t *row);
 fq_status fq_ctx_trim(fq_ctx *ctx);   /* frees cached scratch memory (synchronises the device) */
 fq_status fq_sort_indices(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
                           fq_column *indices, void *stream);
+/* ORDER BY ... LIMIT: the first min(limit, n_rows) indexes of the same order (`indices` needs only that many slots).  When one
+ * NOT NULL key decides the order and the result is a small part of the table the rows are found by radix select (a
+ * histogram and a partition per digit, from the most significant one down) and only what is left is sorted. */
+fq_status fq_sort_indices_limit(fq_ctx *ctx, const fq_column *const *keys, const uint8_t *descending, int32_t n_keys, uint64_t n_rows,
+                                uint64_t limit, fq_column *indices, uint64_t *n_out, void *stream);
 fq_status fq_column_take(fq_ctx *ctx, const fq_column *src, const fq_column *rows, uint64_t n, fq_column *out, fq_column *out_valid,
                          void *stream);
 

@@ -85,6 +85,39 @@ def test_three_keys_mixed_directions(ctx):
         c.free()
 
 
+@pytest.mark.parametrize("limit", [1, 10, 1000, 40_000])
+def test_order_by_limit_is_the_head_of_the_full_order(ctx, limit):
+    """fq_sort_indices_limit: radix select (one NOT NULL key, small result) or full sort + cut — either way the first `limit`
+    entries of the stable order, ties resolved by input order."""
+    rng = np.random.default_rng(limit)
+    n = 3_000_017
+    cases = {"ties": rng.integers(0, 1000, n).astype(np.uint64),                 # ~3000 rows per value: stability decides
+             "u64": rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + np.uint64(1),
+             "i32": rng.integers(-2**31, 2**31 - 1, n).astype(np.int32),
+             "f64": rng.normal(size=n),
+             "same": np.full(n, 7, dtype=np.uint16)}
+    for name, a in cases.items():
+        col = ctx.from_numpy(a)
+        for desc in (False, True):
+            want = sort_indices([a], descending=[desc])[:limit]
+            idx, count = ctx.sort_indices_limit([col], n, limit, [desc])
+            assert count == limit and idx.to_numpy(count).astype(np.int64).tolist() == want.tolist(), (name, desc)
+            idx.free()
+        col.free()
+    # nullable or several keys: the full sort, cut
+    a = cases["ties"]
+    ok = rng.random(n) > 0.5
+    b = cases["i32"]
+    cols = [ctx.from_numpy(a, ok), ctx.from_numpy(b)]
+    idx, count = ctx.sort_indices_limit(cols, n, limit, [True, False])
+    assert idx.to_numpy(count).astype(np.int64).tolist() == sort_indices([a, b], [ok, None], [True, False])[:limit].tolist()
+    idx.free()
+    idx, count = ctx.sort_indices_limit([cols[1]], 100, 1000)          # limit beyond the rows
+    assert count == 100 and idx.to_numpy(100).astype(np.int64).tolist() == sort_indices([b[:100]]).tolist()
+    for c in cols + [idx]:
+        c.free()
+
+
 def test_numbers_descending_at_scale_and_errors(ctx):
     n = 30_000_000
     col = ctx.numbers(5, n)
