@@ -779,6 +779,19 @@ def order_by_table(rig: Rig, col):
         del t, rows
         idx.free()
         taken.free()
+        # ORDER BY key LIMIT 10: radix select instead of the full sort; checked against the head of the full order
+        def top():
+            i2, _ = ctx.sort_indices_limit([key], n, 10, [desc], stream=rig.stream)
+            i2.free()
+        ms_top = timed(rig, top, 3, warm=1)
+        i2, cnt = ctx.sort_indices_limit([key], n, 10, [desc], stream=rig.stream)
+        head10 = ctx.take(key, i2, cnt, stream=rig.stream).to_numpy(cnt)
+        if desc:
+            assert head10.tolist() == [n - 1 - j for j in range(10)], head10
+        else:
+            assert bool((head10[1:] >= head10[:-1]).all()) and int(head10[0]) == int(torch.as_tensor(DevPtr(key.device_ptr, n), device=rig.dev).view(torch.int64).bitwise_xor(-(1 << 63)).min().item() ^ -(1 << 63)) & M64
+        out[name]["limit_10_ms"] = round(ms_top, 3)
+        i2.free()
     scrambled.free()
     ctx.trim()           # 24 GB of sort scratch back to the device before the e2e leg
     return out
