@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   const std::vector<std::string> toks = {
       "select", "from", "where", "limit", "group", "by", "as", "and", "or", "not", "explain", "system", ".", "numbers_mt", "number",
       "(", ")", ",", "*", "+", "-", "/", "%", "=", "<", ">", "<=", ">=", "<>", "!=", "1", "0", "10000", "1.5", "'a'", "sum", "count",
-      "max", "min", "avg", "x", "t", ";", "having", "order", "join", "union", "-1", "1e10", "99999999999999999999", "\"q\"", "`b`",
+      "max", "min", "avg", "x", "t", ";", "having", "order", "asc", "desc", "join", "union", "-1", "1e10", "99999999999999999999", "\"q\"", "`b`",
       "'", "''", "\\", "/*", "--", "\t", "\n", "0x10", "1.", ".5", "e", "1e", "select(", "))", "((", "system.numbers_mt(10)"};
   auto pick = [&](size_t n) { return (size_t)(rng() % n); };
   // a grammar-shaped generator beside the token soup, so that the optimizer, EXPLAIN and the pipeline builder see plans too
@@ -42,6 +42,10 @@ int main(int argc, char **argv) {
     else q += " from system.numbers_mt(" + std::string(pick(5) ? "100000" : "number") + ")";
     if (pick(2)) q += " where " + expr(3);
     if (pick(6) == 0) q += " group by " + expr(1);
+    if (pick(4) == 0) {   // ORDER BY: output columns, arbitrary expressions, both directions
+      q += " order by ";
+      for (size_t i = 0, m = 1 + pick(2); i < m; i++) q += (i ? ", " : "") + (pick(2) ? "c" + std::to_string(1 + pick(3)) : expr(2)) + (pick(3) == 0 ? " desc" : pick(2) ? " asc" : "");
+    }
     if (pick(3) == 0) q += " limit " + std::string(pick(4) ? "3" : "x");
     return (pick(5) == 0 ? "explain " : "") + q;
   };

@@ -183,7 +183,7 @@ def test_planner_survives_token_soup(ctx):
     import random
     toks = ["select", "from", "where", "limit", "group", "by", "as", "and", "or", "not", "explain", "system", ".", "numbers_mt", "number",
             "(", ")", ",", "*", "+", "-", "/", "%", "=", "<", ">", "<=", ">=", "<>", "!=", "1", "0", "10000", "1.5", "'a'", "sum", "count",
-            "max", "min", "avg", "x", "t", ";", "having", "order", "join", "union", "-1", "1e10", "99999999999999999999", '"q"', "`b`"]
+            "max", "min", "avg", "x", "t", ";", "having", "order", "asc", "desc", "join", "union", "-1", "1e10", "99999999999999999999", '"q"', "`b`"]
     rng = random.Random(20201)
     planned = 0
     for _ in range(4000):
