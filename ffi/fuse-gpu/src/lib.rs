@@ -219,6 +219,20 @@ impl Column {
         Ok(col)
     }
 
+    /// attach a byte-per-row validity column this column does not own (the caller keeps it alive)
+    pub fn set_validity(&self, validity: &Column) -> FuseQueryResult<()> {
+        check(self.ctx.raw, unsafe { sys::fq_column_set_validity(self.ctx.raw, self.raw, validity.raw) })
+    }
+
+    /// the validity column uploaded or gathered with this column, if any
+    pub fn validity(&self) -> Option<&Column> {
+        self.validity.as_deref()
+    }
+
+    pub fn is_nullable(&self) -> bool {
+        self.validity.is_some()
+    }
+
     pub fn len(&self) -> u64 {
         unsafe { sys::fq_column_len(self.raw) }
     }

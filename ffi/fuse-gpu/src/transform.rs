@@ -1,4 +1,4 @@
-//! `GpuPipeTransform` / `GpuGroupByTransform`: the processors PipelineBuilder::build adds instead of a
+//! `GpuPipeTransform` / `GpuGroupByTransform` / `GpuSortTransform`: the processors PipelineBuilder::build adds instead of a
 //! Source -> [Filter] -> (Projection | AggregatePartial) [-> Limit] chain (processors/pipeline_builder.rs:26-106).  Each emits
 //! exactly what that chain would hand to the next processor — the partial-state Utf8/JSON block
 //! (transform_aggregate_partial.rs:61-72) or the filtered + projected (+ limited) rows — so MergeProcessor,
@@ -345,5 +345,97 @@ impl IProcessor for GpuGroupByTransform {
     async fn execute(&self) -> FuseQueryResult<SendableDataBlockStream> {
         let block = self.run()?;
         Ok(Box::pin(DataBlockStream::create(self.schema.clone(), None, vec![block])))
+    }
+}
+
+/// ORDER BY (no counterpart in the reference: README.md:28 lists sorting as open; sqlparser parses the clause and
+/// plan_parser.rs never reads `query.order_by`).  A pipeline breaker: every block of the input is uploaded as one block, the
+/// key expressions — over the input's OUTPUT columns — are evaluated by one projection pipe, the row indexes are sorted on the
+/// device (ascending unless `descending[j]`, NULLs first, ties in input order) and every column is gathered in that order;
+/// with the LIMIT that follows it in the plan only those rows are ordered (radix select) and gathered.
+pub struct GpuSortTransform {
+    gpu: Arc<GpuContext>,
+    keys: Vec<ExpressionPlan>,
+    descending: Vec<bool>,
+    limit: Option<usize>,
+    input: Arc<dyn IProcessor>,
+}
+
+impl GpuSortTransform {
+    pub fn try_create(gpu: Arc<GpuContext>, keys: Vec<ExpressionPlan>, descending: Vec<bool>, limit: Option<usize>) -> FuseQueryResult<Self> {
+        if let Some(k) = keys.iter().find(|k| k.is_aggregate()) {
+            return Err(FuseQueryError::Plan(format!("ORDER BY sorts the query's output columns: name the aggregate's column (or its alias) instead of {:?}", k)));
+        }
+        Ok(GpuSortTransform { gpu, keys, descending, limit, input: Arc::new(crate::processors::EmptyProcessor::create()) })
+    }
+
+    fn sort(&self, blocks: Vec<DataBlock>) -> FuseQueryResult<Option<DataBlock>> {
+        let blocks: Vec<DataBlock> = blocks.into_iter().filter(|b| b.num_rows() > 0).collect();
+        if blocks.is_empty() {
+            return Ok(None);
+        }
+        let schema = blocks[0].schema().clone();
+        let n: u64 = blocks.iter().map(|b| b.num_rows() as u64).sum();
+        // one device column per field: the blocks' arrays concatenated by arrow, then uploaded with their null bitmaps as they are
+        let mut cols = vec![];
+        for c in 0..schema.fields().len() {
+            let parts: Vec<arrow::array::ArrayRef> = blocks.iter().map(|b| b.column(c).clone()).collect();
+            let whole = arrow::compute::concat(&parts).map_err(|e| FuseQueryError::Internal(e.to_string()))?;
+            cols.push(Column::from_arrow(&self.gpu, &whole, ptr::null_mut())?);
+        }
+        // the keys in one projection launch over that block
+        let mut lw = Lowering::new(false);
+        let roots = self.keys.iter().map(|e| lw.lower(e, &schema)).collect::<FuseQueryResult<Vec<_>>>()?;
+        let proj = Pipe::compile(&self.gpu, &lw.desc(sys::FQ_PIPE_PROJECT, -1, &roots, &[])?)?;
+        let (key_cols, key_valid) = proj.alloc_outputs(n)?;
+        let inputs: Vec<&Column> = lw.block_cols.iter().map(|&bi| &cols[bi]).collect();
+        proj.launch_project(&Source { n_rows: n, cols: inputs, generated: false, numbers_begin: 0 }, &key_cols, &key_valid, n, None, false, ptr::null_mut())?;
+        proj.fetch_project()?;
+        for (k, v) in key_cols.iter().zip(key_valid.iter()) {
+            if let Some(v) = v {
+                k.set_validity(v)?;     // the sort reads a key's validity from the column itself
+            }
+        }
+        let key_refs: Vec<&Column> = key_cols.iter().collect();
+        let (rows, count) = match self.limit {
+            Some(l) => Column::sort_indices_limit(&self.gpu, &key_refs, &self.descending, n, l as u64, ptr::null_mut())?,
+            None => (Column::sort_indices(&self.gpu, &key_refs, &self.descending, n, ptr::null_mut())?, n),
+        };
+        if count == 0 {
+            return Ok(None);
+        }
+        let mut arrays = vec![];
+        for c in cols.iter() {
+            let taken = c.take(&rows, count, c.is_nullable(), ptr::null_mut())?;
+            arrays.push(taken.to_arrow(count, taken.validity(), ptr::null_mut())?);
+        }
+        Ok(Some(DataBlock::create(schema, arrays)))
+    }
+}
+
+#[async_trait]
+impl IProcessor for GpuSortTransform {
+    fn name(&self) -> &str {
+        "GpuSortTransform"
+    }
+
+    fn connect_to(&mut self, input: Arc<dyn IProcessor>) -> FuseQueryResult<()> {
+        self.input = input;
+        Ok(())
+    }
+
+    async fn execute(&self) -> FuseQueryResult<SendableDataBlockStream> {
+        use futures::stream::StreamExt;
+        let mut stream = self.input.execute().await?;
+        let mut blocks = vec![];
+        let mut schema: Option<DataSchemaRef> = None;
+        while let Some(block) = stream.next().await {
+            let block = block?;
+            schema.get_or_insert_with(|| block.schema().clone());
+            blocks.push(block);
+        }
+        let schema = schema.unwrap_or_else(|| Arc::new(crate::datavalues::DataSchema::empty()));
+        let out = self.sort(blocks)?.into_iter().collect::<Vec<_>>();
+        Ok(Box::pin(DataBlockStream::create(schema, None, out)))
     }
 }
