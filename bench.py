@@ -290,8 +290,11 @@ class Rig:
         self.dev = f"cuda:{self.local}"
         self.affinity = bind_to_gpu_cpus(self.local)
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
+            # stdout carries the one JSON line.  NCCL_DEBUG=VERSION (set in the GPU image) makes NCCL printf "NCCL version ..."
+            # to stdout, past NCCL_DEBUG_FILE; the level logs nothing else, so it is dropped.  Other levels go to stderr.
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                del os.environ["NCCL_DEBUG"]
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self.ctx = cabi.Context(self.local)
         self.stream = torch.cuda.current_stream().cuda_stream
